@@ -1,0 +1,295 @@
+"""ctypes loader for the float64 C oracle + a NumPy twin of the same arithmetic.
+
+TEST INFRASTRUCTURE ONLY.  Importable from tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py -- never from the product package
+(rome.jl_b200/ must not import anything under oracle/).
+
+Parity status: PINNED (tests/test_oracle_golden.py checks every function here against
+the reference's own known-answer vectors in tests/golden/known_answers.json).
+
+Reference lines restated (paths relative to /root/reference):
+  src/factors/Pose2D.jl:51-67, src/factors/PriorPose2.jl:19-25,37-47,
+  src/factors/BearingRange2D.jl:48-64, src/factors/Pose3Pose3.jl:17-29,
+  src/factors/Pose3D.jl:15-19.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "librome_oracle.so")
+
+
+def build(force: bool = False) -> str:
+    """Compile oracle/rome_oracle.c with the committed Makefile (gcc, OpenMP)."""
+    src = os.path.join(_HERE, "rome_oracle.c")
+    stale = (not os.path.exists(_SO)) or os.path.getmtime(_SO) < os.path.getmtime(src)
+    if force or stale:
+        subprocess.run(["make", "-C", _HERE, "-B"], check=True, stdout=subprocess.DEVNULL)
+    return _SO
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        d, i32, u64 = C.POINTER(C.c_double), C.POINTER(C.c_int32), C.c_uint64
+        _lib.rome_oracle_sym_rem.restype = C.c_double
+        _lib.rome_oracle_sym_rem.argtypes = [C.c_double]
+        for name, n in [("pose2pose2", 4), ("priorpose2", 3), ("bearingrange", 4), ("pose3pose3", 4),
+                        ("priorpose3", 3), ("pose2pose2_fwd", 3), ("pose2pose2_bwd", 3),
+                        ("bearingrange_fwd", 3), ("pose3pose3_fwd", 3), ("pose3pose3_bwd", 3),
+                        ("so3_exp", 2), ("so3_log", 2)]:
+            fn = getattr(_lib, "rome_oracle_" + name)
+            fn.restype = None
+            fn.argtypes = [d] * n
+        _lib.rome_oracle_sweep_pose2pose2.argtypes = [C.c_int, C.c_int, i32, i32, d, d, d, C.c_int]
+        _lib.rome_oracle_sweep_pose3pose3.argtypes = [C.c_int, C.c_int, i32, i32, d, d, d, C.c_int]
+        _lib.rome_oracle_sweep_priorpose2.argtypes = [C.c_int, C.c_int, i32, d, d, d, C.c_int]
+        _lib.rome_oracle_sweep_priorpose3.argtypes = [C.c_int, C.c_int, i32, d, d, d, C.c_int]
+        _lib.rome_oracle_sweep_bearingrange.argtypes = [C.c_int, C.c_int, i32, i32, d, d, d, d, C.c_int]
+        _lib.rome_oracle_conv_nm_pose2pose2.argtypes = [C.c_int, C.c_int, i32, i32, d, d, C.c_int, C.c_int,
+                                                        C.c_double, u64, d, C.POINTER(u64), C.c_int]
+        _lib.rome_oracle_philox4x32_10.restype = None
+        _lib.rome_oracle_philox4x32_10.argtypes = [C.POINTER(C.c_uint32)] * 3
+        _lib.rome_oracle_normal4.restype = None
+        _lib.rome_oracle_normal4.argtypes = [u64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, d]
+    return _lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+# ----------------------------------------------------------------------------------
+# single evaluations (== calcFactorResidualTemporary on coordinates)
+# ----------------------------------------------------------------------------------
+def _call(name, nout, *args):
+    arrs = [_f64(a) for a in args]
+    out = np.zeros(nout)
+    getattr(lib(), "rome_oracle_" + name)(*[_dp(a) for a in arrs], _dp(out))
+    return out
+
+
+def pose2pose2(X, p, q):
+    return _call("pose2pose2", 3, X, p, q)
+
+
+def priorpose2(m, p):
+    return _call("priorpose2", 3, m, p)
+
+
+def bearingrange(meas, p, l):
+    return _call("bearingrange", 2, meas, p, l)
+
+
+def pose3pose3(X, p, q):
+    return _call("pose3pose3", 6, X, p, q)
+
+
+def priorpose3(m, p):
+    return _call("priorpose3", 6, m, p)
+
+
+def pose2pose2_fwd(X, p):
+    return _call("pose2pose2_fwd", 3, X, p)
+
+
+def pose2pose2_bwd(X, q):
+    return _call("pose2pose2_bwd", 3, X, q)
+
+
+def bearingrange_fwd(meas, p):
+    return _call("bearingrange_fwd", 2, meas, p)
+
+
+def pose3pose3_fwd(X, p):
+    return _call("pose3pose3_fwd", 6, X, p)
+
+
+def pose3pose3_bwd(X, q):
+    return _call("pose3pose3_bwd", 6, X, q)
+
+
+def so3_exp(w):
+    return _call("so3_exp", 9, w).reshape(3, 3)
+
+
+def so3_log(R):
+    return _call("so3_log", 3, np.asarray(R).reshape(9))
+
+
+def sym_rem(x):
+    return lib().rome_oracle_sym_rem(float(x))
+
+
+# ----------------------------------------------------------------------------------
+# batched sweeps; arrays in the reference's particle-major layout
+#   vars [nvars][N][d], meas [nF][N][dm] -> res [nF][N][dr]
+# ----------------------------------------------------------------------------------
+def sweep_pose2pose2(ip, iq, poses, meas, nthreads=0):
+    ip, iq, poses, meas = _i32(ip), _i32(iq), _f64(poses), _f64(meas)
+    nF, N = meas.shape[0], meas.shape[1]
+    res = np.empty((nF, N, 3))
+    lib().rome_oracle_sweep_pose2pose2(nF, N, _ip(ip), _ip(iq), _dp(poses), _dp(meas), _dp(res), nthreads)
+    return res
+
+
+def sweep_priorpose2(ip, poses, meas, nthreads=0):
+    ip, poses, meas = _i32(ip), _f64(poses), _f64(meas)
+    nF, N = meas.shape[0], meas.shape[1]
+    res = np.empty((nF, N, 3))
+    lib().rome_oracle_sweep_priorpose2(nF, N, _ip(ip), _dp(poses), _dp(meas), _dp(res), nthreads)
+    return res
+
+
+def sweep_bearingrange(ip, il, poses, points, meas, nthreads=0):
+    ip, il, poses, points, meas = _i32(ip), _i32(il), _f64(poses), _f64(points), _f64(meas)
+    nF, N = meas.shape[0], meas.shape[1]
+    res = np.empty((nF, N, 2))
+    lib().rome_oracle_sweep_bearingrange(nF, N, _ip(ip), _ip(il), _dp(poses), _dp(points), _dp(meas),
+                                         _dp(res), nthreads)
+    return res
+
+
+def sweep_pose3pose3(ip, iq, poses, meas, nthreads=0):
+    ip, iq, poses, meas = _i32(ip), _i32(iq), _f64(poses), _f64(meas)
+    nF, N = meas.shape[0], meas.shape[1]
+    res = np.empty((nF, N, 6))
+    lib().rome_oracle_sweep_pose3pose3(nF, N, _ip(ip), _ip(iq), _dp(poses), _dp(meas), _dp(res), nthreads)
+    return res
+
+
+def sweep_priorpose3(ip, poses, meas, nthreads=0):
+    ip, poses, meas = _i32(ip), _f64(poses), _f64(meas)
+    nF, N = meas.shape[0], meas.shape[1]
+    res = np.empty((nF, N, 6))
+    lib().rome_oracle_sweep_priorpose3(nF, N, _ip(ip), _dp(poses), _dp(meas), _dp(res), nthreads)
+    return res
+
+
+def conv_nm_pose2pose2(ip, iq, poses, meas, fwd=True, inflate_cycles=3, inflation=5.0, seed=0, nthreads=0):
+    """Reference-shaped convolution (Nelder-Mead per particle). Returns (proposals, n_evals, threads)."""
+    ip, iq, poses, meas = _i32(ip), _i32(iq), _f64(poses), _f64(meas)
+    nF, N = meas.shape[0], meas.shape[1]
+    out = np.empty((nF, N, 3))
+    ne = C.c_uint64(0)
+    nt = lib().rome_oracle_conv_nm_pose2pose2(nF, N, _ip(ip), _ip(iq), _dp(poses), _dp(meas), int(fwd),
+                                              inflate_cycles, inflation, seed, _dp(out), C.byref(ne), nthreads)
+    return out, int(ne.value), nt
+
+
+# ----------------------------------------------------------------------------------
+# sampler twin (device Philox4x32-10 + Box-Muller restated on the host)
+# ----------------------------------------------------------------------------------
+def philox4x32_10(ctr, key):
+    c = np.ascontiguousarray(ctr, dtype=np.uint32)
+    k = np.ascontiguousarray(key, dtype=np.uint32)
+    o = np.zeros(4, dtype=np.uint32)
+    u = C.POINTER(C.c_uint32)
+    lib().rome_oracle_philox4x32_10(c.ctypes.data_as(u), k.ctypes.data_as(u), o.ctypes.data_as(u))
+    return o
+
+
+def normal4(seed, stream, factor, particle, block=0):
+    z = np.zeros(4)
+    lib().rome_oracle_normal4(seed, stream, factor, particle, block, _dp(z))
+    return z
+
+
+# ----------------------------------------------------------------------------------
+# NumPy twin (vectorised over leading axes) -- an independent second statement of the
+# same formulas, used to cross-check the C code and for quick array-level checks.
+# ----------------------------------------------------------------------------------
+def np_wrap(a):
+    return np.arctan2(np.sin(a), np.cos(a))
+
+
+def np_sym_rem(x):
+    x = np.asarray(x, dtype=np.float64)
+    r = np.remainder(x + np.pi, 2 * np.pi) - np.pi  # [-pi, pi)
+    # IEEE remainder keeps +pi for inputs just below an odd multiple... sym_rem maps x~pi to -pi
+    return np.where(np.isclose(x, np.pi, rtol=1.4901161193847656e-08, atol=0), -np.pi, r)
+
+
+def np_pose2pose2(X, p, q):
+    X, p, q = (np.asarray(a, dtype=np.float64) for a in (X, p, q))
+    c, s = np.cos(p[..., 2]), np.sin(p[..., 2])
+    r = np.empty(np.broadcast_shapes(X.shape, p.shape, q.shape))
+    r[..., 0] = p[..., 0] + c * X[..., 0] - s * X[..., 1] - q[..., 0]
+    r[..., 1] = p[..., 1] + s * X[..., 0] + c * X[..., 1] - q[..., 1]
+    r[..., 2] = np_wrap(p[..., 2] + X[..., 2] - q[..., 2])
+    return r
+
+
+def np_priorpose2(m, p):
+    m, p = np.asarray(m, dtype=np.float64), np.asarray(p, dtype=np.float64)
+    r = np.empty(np.broadcast_shapes(m.shape, p.shape))
+    r[..., :2] = m[..., :2] - p[..., :2]
+    r[..., 2] = np_wrap(m[..., 2] - p[..., 2])
+    return r
+
+
+def np_bearingrange(meas, p, l):
+    meas, p, l = (np.asarray(a, dtype=np.float64) for a in (meas, p, l))
+    c, s = np.cos(p[..., 2]), np.sin(p[..., 2])
+    dx, dy = l[..., 0] - p[..., 0], l[..., 1] - p[..., 1]
+    plx, ply = c * dx + s * dy, -s * dx + c * dy
+    return np.stack([np_sym_rem(meas[..., 0] - np.arctan2(ply, plx)), meas[..., 1] - np.hypot(plx, ply)], -1)
+
+
+def np_so3_exp(w):
+    w = np.asarray(w, dtype=np.float64)
+    t = np.linalg.norm(w, axis=-1)[..., None, None]
+    K = np.zeros(w.shape[:-1] + (3, 3))
+    K[..., 0, 1], K[..., 0, 2] = -w[..., 2], w[..., 1]
+    K[..., 1, 0], K[..., 1, 2] = w[..., 2], -w[..., 0]
+    K[..., 2, 0], K[..., 2, 1] = -w[..., 1], w[..., 0]
+    with np.errstate(invalid="ignore", divide="ignore"):
+        a = np.where(t < 1e-6, 1 - t * t / 6, np.sin(t) / t)
+        b = np.where(t < 1e-6, 0.5 - t * t / 24, (1 - np.cos(t)) / (t * t))
+    return np.eye(3) + a * K + b * (K @ K)
+
+
+def np_so3_log(R):
+    """Quaternion-free log via the reference's generic branch; inputs away from theta=pi."""
+    R = np.asarray(R, dtype=np.float64)
+    c = np.clip(0.5 * (np.trace(R, axis1=-2, axis2=-1) - 1), -1, 1)
+    th = np.arccos(c)
+    v = np.stack([R[..., 2, 1] - R[..., 1, 2], R[..., 0, 2] - R[..., 2, 0], R[..., 1, 0] - R[..., 0, 1]], -1)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        k = np.where(th < 1e-8, 0.5, th / (2 * np.sin(th)))
+    return k[..., None] * v
+
+
+def np_pose3pose3(X, p, q):
+    X, p, q = (np.asarray(a, dtype=np.float64) for a in (X, p, q))
+    Rp, Rq, M = np_so3_exp(p[..., 3:]), np_so3_exp(q[..., 3:]), np_so3_exp(X[..., 3:])
+    rt = p[..., :3] + np.einsum("...ij,...j->...i", Rp, X[..., :3]) - q[..., :3]
+    U = np.swapaxes(Rq, -1, -2) @ Rp @ M
+    return np.concatenate([rt, np_so3_log(U)], -1)
+
+
+def np_priorpose3(m, p):
+    m, p = np.asarray(m, dtype=np.float64), np.asarray(p, dtype=np.float64)
+    U = np.swapaxes(np_so3_exp(p[..., 3:]), -1, -2) @ np_so3_exp(m[..., 3:])
+    return np.concatenate([m[..., :3] - p[..., :3], np_so3_log(U)], -1)

@@ -1,0 +1,470 @@
+/*
+ * rome_oracle.c -- float64 CPU restatement of the RoME.jl factor-residual hot path.
+ * TEST INFRASTRUCTURE ONLY (see rome_oracle.h).  Parity status: PINNED against the
+ * reference's own known-answer tests (tests/golden/known_answers.json).
+ *
+ * Every function cites the reference lines it follows (paths relative to
+ * /root/reference).  Arithmetic that lives in unvendored dependencies is restated
+ * from their published algorithm and named where used:
+ *   Manifolds.jl 0.10  (Project.toml:69)  exp/log/compose/hat/vee/sym_rem/usinc_from_cos
+ *   Optim.jl 0.22/1    (Project.toml:71)  NelderMead (adaptive parameters, affine simplexer)
+ */
+#include "rome_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+/* ================================================================================== */
+/* scalar helpers                                                                     */
+/* ================================================================================== */
+
+/* Manifolds.sym_rem(x, T=pi) [Manifolds.jl utils]: (x ~ T ? -T : rem(x, 2T, RoundNearest)).
+ * Used by src/factors/BearingRange2D.jl:61. isapprox default rtol = sqrt(eps). */
+double rome_oracle_sym_rem(double x) {
+    const double T = M_PI;
+    if (fabs(x - T) <= 1.4901161193847656e-08 * fmax(fabs(x), T)) return -T;
+    return remainder(x, 2.0 * T); /* IEEE remainder == rem(.., RoundNearest) */
+}
+
+/* so(2) log as the reference evaluates it: atan(U21, U11) of the relative rotation
+ * (Manifolds log on SpecialOrthogonal(2); see src/factors/Pose2D.jl:64). */
+double rome_oracle_wrap_atan(double a) { return atan2(sin(a), cos(a)); }
+
+static void mat3_mul(const double A[9], const double B[9], double C[9]) {
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+            C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+}
+static void mat3_tmul(const double A[9], const double B[9], double C[9]) { /* A' * B */
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+            C[3 * i + j] = A[i] * B[j] + A[3 + i] * B[3 + j] + A[6 + i] * B[6 + j];
+}
+static void mat3_vec(const double A[9], const double v[3], double o[3]) {
+    for (int i = 0; i < 3; ++i) o[i] = A[3 * i] * v[0] + A[3 * i + 1] * v[1] + A[3 * i + 2] * v[2];
+}
+
+/* Exp on SO(3) (Rodrigues), Manifolds.jl exp for Rotations(3):
+ *   R = I + sin(t)/t K + (1-cos t)/t^2 K^2,  K = hat(w).  */
+void rome_oracle_so3_exp(const double w[3], double R[9]) {
+    const double t2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+    const double t = sqrt(t2);
+    double a, b; /* sin t / t, (1 - cos t)/t^2 */
+    if (t < 1e-6) {
+        a = 1.0 - t2 / 6.0 + t2 * t2 / 120.0;
+        b = 0.5 - t2 / 24.0 + t2 * t2 / 720.0;
+    } else {
+        a = sin(t) / t;
+        const double sh = sin(0.5 * t);
+        b = 2.0 * sh * sh / t2;
+    }
+    const double x = w[0], y = w[1], z = w[2];
+    R[0] = 1.0 - b * (y * y + z * z); R[1] = -a * z + b * x * y;       R[2] = a * y + b * x * z;
+    R[3] = a * z + b * x * y;         R[4] = 1.0 - b * (x * x + z * z); R[5] = -a * x + b * y * z;
+    R[6] = -a * y + b * x * z;        R[7] = a * x + b * y * z;         R[8] = 1.0 - b * (x * x + y * y);
+}
+
+/* Log on SO(3), restating Manifolds.jl log for Rotations(3):
+ *   cos t = (tr R - 1)/2;  generic: X = (R - R')/(2 usinc_from_cos(cos t));
+ *   cos t ~ -1 (isapprox, rtol sqrt(eps)): pi * (eigenvector of eigenvalue 1).
+ * The pi-branch sign is ambiguous in the reference too (compare as rotations there);
+ * here the axis is taken from the dominant column of (R + I)/2 and its sign fixed so
+ * it agrees with vee(R - R') whenever that is non-zero. */
+void rome_oracle_so3_log(const double R[9], double w[3]) {
+    double c = 0.5 * (R[0] + R[4] + R[8] - 1.0);
+    const double v[3] = {R[7] - R[5], R[2] - R[6], R[3] - R[1]}; /* (X32, X13, X21) * 2 sin t */
+    if (fabs(c + 1.0) <= 1.4901161193847656e-08 * fmax(fabs(c), 1.0)) {
+        double B[9];
+        for (int i = 0; i < 9; ++i) B[i] = 0.5 * R[i];
+        B[0] += 0.5; B[4] += 0.5; B[8] += 0.5; /* (R+I)/2 = a a' at t = pi */
+        int k = 0;
+        if (B[4] > B[0]) k = 1;
+        if (B[8] > B[4 * k]) k = 2;
+        double ax[3] = {B[k], B[3 + k], B[6 + k]};
+        const double n = sqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]);
+        for (int i = 0; i < 3; ++i) ax[i] /= n;
+        if (ax[0] * v[0] + ax[1] * v[1] + ax[2] * v[2] < 0.0)
+            for (int i = 0; i < 3; ++i) ax[i] = -ax[i];
+        for (int i = 0; i < 3; ++i) w[i] = M_PI * ax[i];
+        return;
+    }
+    double us; /* usinc_from_cos */
+    if (c >= 1.0) us = 1.0;
+    else if (c <= -1.0) us = 0.0;
+    else us = sqrt(1.0 - c * c) / acos(c);
+    for (int i = 0; i < 3; ++i) w[i] = v[i] / (2.0 * us);
+}
+
+/* getPoint(Pose3, c) = exp(M, e, hat(M, e, c)) under Hybrid semantics:
+ * (t = c[1:3], R = Exp(c[4:6])); test/testPose3.jl:9-23, src/services/ManifoldUtils.jl:8-23 */
+void rome_oracle_pose3_point(const double c[6], double t[3], double R[9]) {
+    t[0] = c[0]; t[1] = c[1]; t[2] = c[2];
+    rome_oracle_so3_exp(c + 3, R);
+}
+void rome_oracle_pose3_coords(const double t[3], const double R[9], double c[6]) {
+    c[0] = t[0]; c[1] = t[1]; c[2] = t[2];
+    rome_oracle_so3_log(R, c + 3);
+}
+
+/* ================================================================================== */
+/* residuals                                                                          */
+/* ================================================================================== */
+
+/* src/factors/Pose2D.jl:51-67 with _compose/_vee of src/factors/PriorPose2.jl:19-25:
+ *   eX = exp(M, e0, X) = (X.t, R(X.theta))
+ *   qhat = (p.t + p.R eX.t, p.R eX.R)
+ *   Xhat = log(M, q, qhat) = (qhat.t - q.t, log(q.R' qhat.R))
+ *   return (Xhat.t[1], Xhat.t[2], Xhat.R[2,1]) */
+void rome_oracle_pose2pose2(const double X[3], const double p[3], const double q[3], double r[3]) {
+    const double cp = cos(p[2]), sp = sin(p[2]);
+    const double cm = cos(X[2]), sm = sin(X[2]);
+    const double cq = cos(q[2]), sq = sin(q[2]);
+    /* qhat */
+    const double tx = p[0] + cp * X[0] - sp * X[1];
+    const double ty = p[1] + sp * X[0] + cp * X[1];
+    const double h11 = cp * cm - sp * sm, h21 = sp * cm + cp * sm; /* first column of p.R eX.R */
+    /* U = q.R' qhat.R, first column */
+    const double u11 = cq * h11 + sq * h21;
+    const double u21 = -sq * h11 + cq * h21;
+    r[0] = tx - q[0];
+    r[1] = ty - q[1];
+    r[2] = atan2(u21, u11);
+}
+
+/* src/factors/PriorPose2.jl:37-47: _vee(log(M, p, m)) = (m.t - p.t, log(p.R' m.R)[2,1]) */
+void rome_oracle_priorpose2(const double m[3], const double p[3], double r[3]) {
+    const double cp = cos(p[2]), sp = sin(p[2]);
+    const double cm = cos(m[2]), sm = sin(m[2]);
+    r[0] = m[0] - p[0];
+    r[1] = m[1] - p[1];
+    r[2] = atan2(-sp * cm + cp * sm, cp * cm + sp * sm);
+}
+
+/* src/factors/BearingRange2D.jl:48-64:
+ *   pl = p.R' (l - p.t);  dtheta = sym_rem(b - atan(pl[2], pl[1]));  dr = rho - norm(pl) */
+void rome_oracle_bearingrange(const double meas[2], const double p[3], const double l[2], double r[2]) {
+    const double cp = cos(p[2]), sp = sin(p[2]);
+    const double dx = l[0] - p[0], dy = l[1] - p[1];
+    const double plx = cp * dx + sp * dy;
+    const double ply = -sp * dx + cp * dy;
+    r[0] = rome_oracle_sym_rem(meas[0] - atan2(ply, plx));
+    r[1] = meas[1] - sqrt(plx * plx + ply * ply); /* LinearAlgebra.norm of a 2-vector */
+}
+
+/* src/factors/Pose3Pose3.jl:17-29:
+ *   qhat = compose(M, p, exp(M, e, X)) = (p.t + p.R X.t, p.R Exp(X.w))
+ *   Xc = get_coordinates(M, q, log(M, q, qhat)) = (qhat.t - q.t, vee(Log(q.R' qhat.R))) */
+void rome_oracle_pose3pose3(const double X[6], const double p[6], const double q[6], double r[6]) {
+    double tp[3], Rp[9], tq[3], Rq[9], M[9], Rh[9], U[9], v[3];
+    rome_oracle_pose3_point(p, tp, Rp);
+    rome_oracle_pose3_point(q, tq, Rq);
+    rome_oracle_so3_exp(X + 3, M);
+    mat3_vec(Rp, X, v);
+    mat3_mul(Rp, M, Rh);
+    mat3_tmul(Rq, Rh, U);
+    for (int i = 0; i < 3; ++i) r[i] = tp[i] + v[i] - tq[i];
+    rome_oracle_so3_log(U, r + 3);
+}
+
+/* src/factors/Pose3D.jl:15-19: vee(M, p, log(M, p, m)) = (m.t - p.t, vee(Log(p.R' m.R))) */
+void rome_oracle_priorpose3(const double m[6], const double p[6], double r[6]) {
+    double tp[3], Rp[9], tm[3], Rm[9], U[9];
+    rome_oracle_pose3_point(p, tp, Rp);
+    rome_oracle_pose3_point(m, tm, Rm);
+    mat3_tmul(Rp, Rm, U);
+    for (int i = 0; i < 3; ++i) r[i] = tm[i] - tp[i];
+    rome_oracle_so3_log(U, r + 3);
+}
+
+/* ================================================================================== */
+/* closed-form roots                                                                  */
+/* ================================================================================== */
+
+/* q = p o Exp(X); in-tree twin: addPose2Pose2 = se2vee(SE2(x)*SE2(dx)),
+ * src/services/OdometryUtils.jl:132-142 */
+void rome_oracle_pose2pose2_fwd(const double X[3], const double p[3], double q[3]) {
+    const double cp = cos(p[2]), sp = sin(p[2]);
+    q[0] = p[0] + cp * X[0] - sp * X[1];
+    q[1] = p[1] + sp * X[0] + cp * X[1];
+    q[2] = rome_oracle_wrap_atan(p[2] + X[2]);
+}
+/* p with residual(X, p, q) == 0: theta_p = theta_q - m_theta, t_p = t_q - R(theta_p) m_t */
+void rome_oracle_pose2pose2_bwd(const double X[3], const double q[3], double p[3]) {
+    const double th = rome_oracle_wrap_atan(q[2] - X[2]);
+    const double c = cos(th), s = sin(th);
+    p[0] = q[0] - (c * X[0] - s * X[1]);
+    p[1] = q[1] - (s * X[0] + c * X[1]);
+    p[2] = th;
+}
+/* l = t_p + rho R(theta_p) (cos b, sin b); inverse of calcPosePointBearingRange,
+ * src/services/SimulationUtils.jl:47-62 */
+void rome_oracle_bearingrange_fwd(const double meas[2], const double p[3], double l[2]) {
+    const double a = p[2] + meas[0];
+    l[0] = p[0] + meas[1] * cos(a);
+    l[1] = p[1] + meas[1] * sin(a);
+}
+void rome_oracle_pose3pose3_fwd(const double X[6], const double p[6], double q[6]) {
+    double tp[3], Rp[9], M[9], Rh[9], v[3], t[3];
+    rome_oracle_pose3_point(p, tp, Rp);
+    rome_oracle_so3_exp(X + 3, M);
+    mat3_vec(Rp, X, v);
+    mat3_mul(Rp, M, Rh);
+    for (int i = 0; i < 3; ++i) t[i] = tp[i] + v[i];
+    rome_oracle_pose3_coords(t, Rh, q);
+}
+void rome_oracle_pose3pose3_bwd(const double X[6], const double q[6], double p[6]) {
+    double tq[3], Rq[9], M[9], Mt[9], Rp[9], v[3], t[3];
+    rome_oracle_pose3_point(q, tq, Rq);
+    rome_oracle_so3_exp(X + 3, M);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) Mt[3 * i + j] = M[3 * j + i];
+    mat3_mul(Rq, Mt, Rp);
+    mat3_vec(Rp, X, v);
+    for (int i = 0; i < 3; ++i) t[i] = tq[i] - v[i];
+    rome_oracle_pose3_coords(t, Rp, p);
+}
+
+/* ================================================================================== */
+/* batched sweeps -- the loop IIF runs per factor over n = 1:N (SURVEY.md 3.1 HOT LOOP)*/
+/* ================================================================================== */
+
+static int set_threads(int nthreads) {
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+    return nthreads;
+#else
+    (void)nthreads;
+    return 1;
+#endif
+}
+
+int rome_oracle_sweep_pose2pose2(int nF, int N, const int32_t* ip, const int32_t* iq,
+                                 const double* poses, const double* meas, double* res, int nthreads) {
+    const int nt = set_threads(nthreads);
+#pragma omp parallel for schedule(static) num_threads(nt)
+    for (int f = 0; f < nF; ++f) {
+        const double* P = poses + (size_t)ip[f] * N * 3;
+        const double* Q = poses + (size_t)iq[f] * N * 3;
+        const double* X = meas + (size_t)f * N * 3;
+        double* R = res + (size_t)f * N * 3;
+        for (int n = 0; n < N; ++n) rome_oracle_pose2pose2(X + 3 * n, P + 3 * n, Q + 3 * n, R + 3 * n);
+    }
+    return nt;
+}
+
+int rome_oracle_sweep_priorpose2(int nF, int N, const int32_t* ip, const double* poses,
+                                 const double* meas, double* res, int nthreads) {
+    const int nt = set_threads(nthreads);
+#pragma omp parallel for schedule(static) num_threads(nt)
+    for (int f = 0; f < nF; ++f) {
+        const double* P = poses + (size_t)ip[f] * N * 3;
+        const double* X = meas + (size_t)f * N * 3;
+        double* R = res + (size_t)f * N * 3;
+        for (int n = 0; n < N; ++n) rome_oracle_priorpose2(X + 3 * n, P + 3 * n, R + 3 * n);
+    }
+    return nt;
+}
+
+int rome_oracle_sweep_bearingrange(int nF, int N, const int32_t* ip, const int32_t* il,
+                                   const double* poses, const double* points, const double* meas,
+                                   double* res, int nthreads) {
+    const int nt = set_threads(nthreads);
+#pragma omp parallel for schedule(static) num_threads(nt)
+    for (int f = 0; f < nF; ++f) {
+        const double* P = poses + (size_t)ip[f] * N * 3;
+        const double* L = points + (size_t)il[f] * N * 2;
+        const double* X = meas + (size_t)f * N * 2;
+        double* R = res + (size_t)f * N * 2;
+        for (int n = 0; n < N; ++n) rome_oracle_bearingrange(X + 2 * n, P + 3 * n, L + 2 * n, R + 2 * n);
+    }
+    return nt;
+}
+
+int rome_oracle_sweep_pose3pose3(int nF, int N, const int32_t* ip, const int32_t* iq,
+                                 const double* poses, const double* meas, double* res, int nthreads) {
+    const int nt = set_threads(nthreads);
+#pragma omp parallel for schedule(static) num_threads(nt)
+    for (int f = 0; f < nF; ++f) {
+        const double* P = poses + (size_t)ip[f] * N * 6;
+        const double* Q = poses + (size_t)iq[f] * N * 6;
+        const double* X = meas + (size_t)f * N * 6;
+        double* R = res + (size_t)f * N * 6;
+        for (int n = 0; n < N; ++n) rome_oracle_pose3pose3(X + 6 * n, P + 6 * n, Q + 6 * n, R + 6 * n);
+    }
+    return nt;
+}
+
+int rome_oracle_sweep_priorpose3(int nF, int N, const int32_t* ip, const double* poses,
+                                 const double* meas, double* res, int nthreads) {
+    const int nt = set_threads(nthreads);
+#pragma omp parallel for schedule(static) num_threads(nt)
+    for (int f = 0; f < nF; ++f) {
+        const double* P = poses + (size_t)ip[f] * N * 6;
+        const double* X = meas + (size_t)f * N * 6;
+        double* R = res + (size_t)f * N * 6;
+        for (int n = 0; n < N; ++n) rome_oracle_priorpose3(X + 6 * n, P + 6 * n, R + 6 * n);
+    }
+    return nt;
+}
+
+/* ================================================================================== */
+/* sampler twin: Philox4x32-10 + Box-Muller, identical to csrc/philox.cuh             */
+/* ================================================================================== */
+
+void rome_oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
+    uint32_t k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        const uint32_t n1 = (uint32_t)p1;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        const uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+void rome_oracle_normal4(uint64_t seed, uint32_t stream, uint32_t factor, uint32_t particle,
+                         uint32_t block, double z[4]) {
+    const uint32_t ctr[4] = {particle, factor, stream, block};
+    const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    uint32_t x[4];
+    rome_oracle_philox4x32_10(ctr, key, x);
+    for (int h = 0; h < 2; ++h) {
+        const double u1 = ((double)(x[2 * h] >> 9) + 0.5) * (1.0 / 8388608.0);
+        const double u2 = ((double)(x[2 * h + 1] >> 9) + 0.5) * (1.0 / 8388608.0);
+        const double rad = sqrt(-2.0 * log(u1));
+        z[2 * h] = rad * cos(2.0 * M_PI * u2);
+        z[2 * h + 1] = rad * sin(2.0 * M_PI * u2);
+    }
+}
+
+/* ================================================================================== */
+/* reference-shaped convolution: Nelder-Mead per particle                             */
+/* ================================================================================== */
+
+/* cost(x) = || cf(meas, p, q(x)) ||^2 with the solve-for variable replaced by the
+ * candidate coordinates x (_solveCCWNumeric! [IIF-knowledge]). */
+typedef struct {
+    const double* X; /* measurement */
+    const double* other; /* the fixed variable's particle */
+    int fwd;
+    uint64_t evals;
+} nm_ctx;
+
+static double nm_cost(nm_ctx* c, const double x[3]) {
+    double r[3];
+    if (c->fwd) rome_oracle_pose2pose2(c->X, c->other, x, r);
+    else rome_oracle_pose2pose2(c->X, x, c->other, r);
+    c->evals++;
+    return r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+}
+
+/* Optim.jl NelderMead() defaults restated: AffineSimplexer(a=0.025, b=0.5) initial simplex
+ * x_i = x0 + (b*x0[i] + a) e_i; AdaptiveParameters alpha=1, beta=1+2/n, gamma=0.75-1/(2n),
+ * delta=1-1/n; stop when sqrt(var(f_simplex) * n/(n+1)) < g_tol (1e-8) or iterations = 1000. */
+static void nelder_mead3(nm_ctx* c, double x0[3]) {
+    enum { n = 3 };
+    const double alpha = 1.0, beta = 1.0 + 2.0 / n, gamma = 0.75 - 1.0 / (2.0 * n), delta = 1.0 - 1.0 / n;
+    double S[n + 1][n], f[n + 1];
+    for (int i = 0; i <= n; ++i) {
+        for (int j = 0; j < n; ++j) S[i][j] = x0[j];
+        if (i > 0) S[i][i - 1] += 0.5 * x0[i - 1] + 0.025;
+        f[i] = nm_cost(c, S[i]);
+    }
+    for (int it = 0; it < 1000; ++it) {
+        /* order */
+        int idx[n + 1] = {0, 1, 2, 3};
+        for (int a = 0; a <= n; ++a)
+            for (int b = a + 1; b <= n; ++b)
+                if (f[idx[b]] < f[idx[a]]) { int t = idx[a]; idx[a] = idx[b]; idx[b] = t; }
+        const int lo = idx[0], hi = idx[n], nh = idx[n - 1];
+        double mean = 0.0, var = 0.0;
+        for (int i = 0; i <= n; ++i) mean += f[i];
+        mean /= (n + 1);
+        for (int i = 0; i <= n; ++i) var += (f[i] - mean) * (f[i] - mean);
+        var /= n; /* Julia var: unbiased */
+        if (sqrt(var * n / (n + 1.0)) < 1e-8) break;
+        double cen[n] = {0, 0, 0};
+        for (int i = 0; i <= n; ++i)
+            if (i != hi) for (int j = 0; j < n; ++j) cen[j] += S[i][j] / n;
+        double xr[n], xe[n], xc[n];
+        for (int j = 0; j < n; ++j) xr[j] = cen[j] + alpha * (cen[j] - S[hi][j]);
+        const double fr = nm_cost(c, xr);
+        if (fr < f[lo]) {
+            for (int j = 0; j < n; ++j) xe[j] = cen[j] + beta * (xr[j] - cen[j]);
+            const double fe = nm_cost(c, xe);
+            if (fe < fr) { memcpy(S[hi], xe, sizeof xe); f[hi] = fe; }
+            else { memcpy(S[hi], xr, sizeof xr); f[hi] = fr; }
+        } else if (fr < f[nh]) {
+            memcpy(S[hi], xr, sizeof xr); f[hi] = fr;
+        } else {
+            int shrink = 0;
+            if (fr < f[hi]) { /* outside contraction */
+                for (int j = 0; j < n; ++j) xc[j] = cen[j] + gamma * (xr[j] - cen[j]);
+                const double fc = nm_cost(c, xc);
+                if (fc <= fr) { memcpy(S[hi], xc, sizeof xc); f[hi] = fc; } else shrink = 1;
+            } else { /* inside contraction */
+                for (int j = 0; j < n; ++j) xc[j] = cen[j] - gamma * (xr[j] - cen[j]);
+                const double fc = nm_cost(c, xc);
+                if (fc < f[hi]) { memcpy(S[hi], xc, sizeof xc); f[hi] = fc; } else shrink = 1;
+            }
+            if (shrink)
+                for (int i = 0; i <= n; ++i)
+                    if (i != lo) {
+                        for (int j = 0; j < n; ++j) S[i][j] = S[lo][j] + delta * (S[i][j] - S[lo][j]);
+                        f[i] = nm_cost(c, S[i]);
+                    }
+        }
+    }
+    int best = 0;
+    for (int i = 1; i <= n; ++i) if (f[i] < f[best]) best = i;
+    memcpy(x0, S[best], sizeof(double) * n);
+}
+
+int rome_oracle_conv_nm_pose2pose2(int nF, int N, const int32_t* ip, const int32_t* iq,
+                                   const double* poses, const double* meas, int fwd,
+                                   int inflate_cycles, double inflation, uint64_t seed,
+                                   double* out, uint64_t* n_evals, int nthreads) {
+    const int nt = set_threads(nthreads);
+    uint64_t total = 0;
+#pragma omp parallel for schedule(static) num_threads(nt) reduction(+ : total)
+    for (int f = 0; f < nF; ++f) {
+        const double* P = poses + (size_t)ip[f] * N * 3;
+        const double* Q = poses + (size_t)iq[f] * N * 3;
+        const double* tgt = fwd ? Q : P;
+        /* spread of the target belief per coordinate (IIF perturbs the start point by
+         * inflation * spread * randn each cycle [IIF-knowledge]) */
+        double mu[3] = {0, 0, 0}, sd[3] = {0, 0, 0};
+        for (int n = 0; n < N; ++n) for (int j = 0; j < 3; ++j) mu[j] += tgt[3 * n + j] / N;
+        for (int n = 0; n < N; ++n)
+            for (int j = 0; j < 3; ++j) sd[j] += (tgt[3 * n + j] - mu[j]) * (tgt[3 * n + j] - mu[j]) / N;
+        for (int j = 0; j < 3; ++j) sd[j] = sqrt(sd[j]);
+        for (int n = 0; n < N; ++n) {
+            nm_ctx c = {meas + ((size_t)f * N + n) * 3, (fwd ? P : Q) + 3 * n, fwd, 0};
+            double x[3] = {tgt[3 * n], tgt[3 * n + 1], tgt[3 * n + 2]};
+            for (int cyc = 0; cyc < inflate_cycles; ++cyc) {
+                double z[4];
+                rome_oracle_normal4(seed, 0x4e4du + (uint32_t)cyc, (uint32_t)f, (uint32_t)n, 0, z);
+                for (int j = 0; j < 3; ++j) x[j] += inflation * sd[j] * z[j];
+                nelder_mead3(&c, x);
+            }
+            memcpy(out + ((size_t)f * N + n) * 3, x, sizeof x);
+            total += c.evals;
+        }
+    }
+    if (n_evals) *n_evals = total;
+    return nt;
+}
