@@ -1,0 +1,179 @@
+/*
+ * rome_b200.h -- C ABI of librome_b200.so: the B200 (sm_100a) implementation of RoME.jl's
+ * factor-residual / convolution hot path (BASELINE.json north_star).
+ *
+ * What it replaces.  In the reference, IncrementalInference calls the factor functor
+ *   (cf::CalcFactor{<:F})(meas, vars...)                 once per particle per optimiser step
+ * and `getSample(cf)` once per particle per convolution.  This library
+ * evaluates the same arithmetic for ALL factors of one family x ALL particles per call:
+ *
+ *   family ROME_B200_POSE2POSE2    src/factors/Pose2D.jl:51-67  (+ _compose/_vee PriorPose2.jl:19-25)
+ *   family ROME_B200_PRIORPOSE2    src/factors/PriorPose2.jl:37-47
+ *   family ROME_B200_BEARINGRANGE  src/factors/BearingRange2D.jl:48-64, getSample :17-27
+ *   family ROME_B200_POSE3POSE3    src/factors/Pose3Pose3.jl:17-29
+ *   family ROME_B200_PRIORPOSE3    src/factors/Pose3D.jl:15-19
+ *   default getSample on the `.Z` field (IIF sampleTangent/samplePoint; Pose2D.jl:31,
+ *   PriorPose2.jl:14, Pose3Pose3.jl:10, Pose3D.jl:10)   -> ROME_B200_SAMPLE
+ *
+ * The reference-side binding (Julia `ccall`) is shown in INTEGRATION.md and
+ * rome.jl_b200/julia/RoMEB200.jl; tests drive the identical ABI through ctypes.
+ *
+ * Conventions
+ *   - plain C, no exceptions; every call returns 0 (ROME_B200_OK) or a negative status;
+ *     rome_b200_last_error() gives the message.  NaN/Inf inputs propagate (no trapping),
+ *     as in the reference.
+ *   - one rome_b200_ctx per host thread / GPU; calls on one ctx are not re-entrant; different
+ *     contexts are independent (no global mutable state).
+ *   - the caller owns every buffer it passes; the ctx owns particle storage, factor tables
+ *     and staging scratch only.
+ *   - variable coordinates use the reference's own layout: Float64, particle-major
+ *     `[nvars][N][d]` (DFG `vecval`), d = 3 (Pose2: x,y,theta), 2 (Point2), 6 (Pose3: x,y,z,
+ *     rotation vector) -- src/variables/VariableTypes.jl:13,35,47.
+ *   - device layout ("anchored float32"): value = anchor(Float64, per variable / per factor
+ *     mean) + offset(float32).  Particles  [nvars][d][Npad] offsets + [nvars][d] anchors;
+ *     measurements [nF][dm][Npad] offsets from the factor mean; residuals [nF][dr][Npad]
+ *     float32; proposals [nF][dv][Npad] offsets from the TARGET variable's anchor.
+ *     Npad = N rounded up to a multiple of 8 (32-byte sectors); padding lanes hold 0.
+ *     Arithmetic inside the kernels is Float64.
+ */
+#ifndef ROME_B200_H
+#define ROME_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ROME_B200_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define ROME_B200_API __attribute__((visibility("default")))
+#else
+#define ROME_B200_API
+#endif
+
+typedef struct rome_b200_ctx rome_b200_ctx;
+
+enum rome_b200_status {
+    ROME_B200_OK = 0,
+    ROME_B200_BAD_ARG = -1,
+    ROME_B200_CUDA_ERROR = -2,
+    ROME_B200_SHAPE_MISMATCH = -3,
+    ROME_B200_NOT_SET = -4,
+    ROME_B200_NO_DEVICE = -5
+};
+
+/* variable types: src/variables/VariableTypes.jl:35 (Pose2), :13 (Point2), :47 (Pose3) */
+enum rome_b200_vartype { ROME_B200_POSE2 = 0, ROME_B200_POINT2 = 1, ROME_B200_POSE3 = 2, ROME_B200_NVARTYPES = 3 };
+
+enum rome_b200_family {
+    ROME_B200_POSE2POSE2 = 0,
+    ROME_B200_PRIORPOSE2 = 1,
+    ROME_B200_BEARINGRANGE = 2,
+    ROME_B200_POSE3POSE3 = 3,
+    ROME_B200_PRIORPOSE3 = 4,
+    ROME_B200_NFAMILIES = 5
+};
+
+/* eval flags */
+#define ROME_B200_RESIDUAL 1u     /* write the residual coordinates                                  */
+#define ROME_B200_PROPOSAL_FWD 2u /* closed-form root for the LAST variable (q / landmark / prior var) */
+#define ROME_B200_PROPOSAL_BWD 4u /* closed-form root for the FIRST variable (Pose2Pose2, Pose3Pose3) */
+#define ROME_B200_STATS 8u        /* per-factor statistics (warp-shuffle reductions)                 */
+#define ROME_B200_SAMPLE 16u      /* getSample fused in-kernel (Philox4x32-10); `meas` is not read   */
+#define ROME_B200_WRITE_MEAS 32u  /* with SAMPLE: also store the drawn measurement offsets            */
+#define ROME_B200_JACOBIAN 64u    /* compact analytic Jacobian blocks                */
+
+/* Buffers of one eval call.  Unused members may be NULL.  `_host` entry points take host
+ * pointers with the same shapes; plain entry points take device pointers. */
+typedef struct rome_b200_buffers {
+    const float* meas; /* in : [nF][dm][Npad] offsets from the factor mean (ignored with SAMPLE) */
+    float* meas_out;   /* out: same shape, with SAMPLE|WRITE_MEAS                               */
+    float* res;        /* out: [nF][dr][Npad]                                                   */
+    float* prop_fwd;   /* out: [nF][dv_last][Npad]  offsets from the last variable's anchor      */
+    float* prop_bwd;   /* out: [nF][dv_first][Npad] offsets from the first variable's anchor     */
+    float* stats;      /* out: [nF][16] (SE(2) families) or [nF][32] (SE(3) families)            */
+    float* jac;        /* out: [nF][dj][Npad] compact Jacobian entries                           */
+} rome_b200_buffers;
+
+/* ---- life cycle -------------------------------------------------------------------------- */
+ROME_B200_API int rome_b200_version(void);
+/* Fails with ROME_B200_NO_DEVICE when no CUDA device is usable: there is NO CPU fallback. */
+ROME_B200_API int rome_b200_create(int device, rome_b200_ctx** out);
+ROME_B200_API int rome_b200_destroy(rome_b200_ctx* ctx);
+ROME_B200_API const char* rome_b200_last_error(const rome_b200_ctx* ctx); /* ctx may be NULL (creation errors) */
+/* Use a caller-owned cudaStream_t for all work of this ctx (NULL -> the ctx's own stream). */
+ROME_B200_API int rome_b200_set_stream(rome_b200_ctx* ctx, void* cuda_stream);
+ROME_B200_API int rome_b200_synchronize(rome_b200_ctx* ctx);
+/* family/vartype dimensions: dm (measurement), dr (residual), stats width, jacobian rows */
+ROME_B200_API int rome_b200_family_dims(int family, int* dm, int* dr, int* nstats, int* dj);
+ROME_B200_API int rome_b200_vartype_dim(int vartype);
+ROME_B200_API int rome_b200_npad(int N);
+
+/* ---- variables: replaces the per-variable `Vector{ArrayPartition}` particle storage -------- */
+/* Upload Float64 coordinates [nvars][N][d] (host); converts on device to anchored float32 SoA.
+ * anchor of a variable = its first particle.  N must be equal for all vartypes of one ctx. */
+ROME_B200_API int rome_b200_set_particles(rome_b200_ctx* ctx, int vartype, int nvars, int N, const double* coords_host);
+ROME_B200_API int rome_b200_get_particles(rome_b200_ctx* ctx, int vartype, double* coords_host);
+/* Device views (zero-copy interop): offsets [nvars][d][Npad], anchors [nvars][d]. */
+ROME_B200_API int rome_b200_particles_device(rome_b200_ctx* ctx, int vartype, float** d_offsets, double** d_anchors,
+                               int* nvars, int* N, int* Npad);
+/* Replace the particles of variable `var` by proposal row `factor` of a device proposal buffer
+ * (offsets from that variable's anchor) -- used to chain convolutions (graph init). */
+ROME_B200_API int rome_b200_adopt_proposal(rome_b200_ctx* ctx, int vartype, int var, const float* d_prop, int factor);
+
+/* ---- factors: replaces the factor structs' belief fields ----------------------------------- */
+/* Pose2Pose2(MvNormal(mu, cov)): src/factors/Pose2D.jl:30-32.  cov row-major [nF][3][3]. */
+ROME_B200_API int rome_b200_set_factors_pose2pose2(rome_b200_ctx* ctx, int nF, const int32_t* ip, const int32_t* iq,
+                                     const double* mu, const double* cov);
+/* PriorPose2(MvNormal(mu, cov)): src/factors/PriorPose2.jl:13-15 */
+ROME_B200_API int rome_b200_set_factors_priorpose2(rome_b200_ctx* ctx, int nF, const int32_t* ip, const double* mu,
+                                     const double* cov);
+/* Pose2Point2BearingRange(Normal(mu_b, sig_b), Normal(mu_r, sig_r)): BearingRange2D.jl:10-13.
+ * bearing/range: [nF][2] = (mean, standard deviation). */
+ROME_B200_API int rome_b200_set_factors_bearingrange(rome_b200_ctx* ctx, int nF, const int32_t* ip, const int32_t* il,
+                                       const double* bearing, const double* range);
+/* Pose3Pose3(MvNormal(mu, cov)): src/factors/Pose3Pose3.jl:9-11.  cov row-major [nF][6][6]. */
+ROME_B200_API int rome_b200_set_factors_pose3pose3(rome_b200_ctx* ctx, int nF, const int32_t* ip, const int32_t* iq,
+                                     const double* mu, const double* cov);
+/* PriorPose3(MvNormal(mu, cov)): src/factors/Pose3D.jl:9-11 */
+ROME_B200_API int rome_b200_set_factors_priorpose3(rome_b200_ctx* ctx, int nF, const int32_t* ip, const double* mu,
+                                     const double* cov);
+ROME_B200_API int rome_b200_num_factors(rome_b200_ctx* ctx, int family);
+
+/* ---- the hot path --------------------------------------------------------------------------- */
+/* Evaluate factors [first, first+count) of `family` (count < 0: through the last factor) for all
+ * N particles.  Buffers are indexed by GLOBAL factor id, so ranks of a multi-GPU job that split the
+ * factor list write disjoint slices of identically shaped buffers.  Asynchronous on the ctx stream.
+ * (seed, stream_id, factor, particle) keys the in-kernel sampler. */
+ROME_B200_API int rome_b200_eval(rome_b200_ctx* ctx, int family, uint32_t flags, uint64_t seed, uint32_t stream_id,
+                   int first, int count, const rome_b200_buffers* device_buffers);
+/* Same with HOST buffers: copies `meas` in (unless SAMPLE), launches, copies every requested output
+ * back, and synchronises.  This is the call a host-resident caller (Julia/IIF) makes. */
+ROME_B200_API int rome_b200_eval_host(rome_b200_ctx* ctx, int family, uint32_t flags, uint64_t seed, uint32_t stream_id,
+                        int first, int count, const rome_b200_buffers* host_buffers);
+
+/* ---- CUDA-graph capture of a sweep (several eval calls replayed with one launch) ------------- */
+ROME_B200_API int rome_b200_graph_begin(rome_b200_ctx* ctx);
+ROME_B200_API int rome_b200_graph_end(rome_b200_ctx* ctx, int* graph_id);
+ROME_B200_API int rome_b200_graph_launch(rome_b200_ctx* ctx, int graph_id);
+
+/* ---- memory helpers for callers without a CUDA runtime binding ------------------------------- */
+ROME_B200_API int rome_b200_malloc_device(rome_b200_ctx* ctx, size_t bytes, void** out);
+ROME_B200_API int rome_b200_free_device(rome_b200_ctx* ctx, void* p);
+ROME_B200_API int rome_b200_malloc_host(rome_b200_ctx* ctx, size_t bytes, void** out); /* pinned */
+ROME_B200_API int rome_b200_free_host(rome_b200_ctx* ctx, void* p);
+ROME_B200_API int rome_b200_memcpy_h2d(rome_b200_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+ROME_B200_API int rome_b200_memcpy_d2h(rome_b200_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+
+/* ---- instrumentation --------------------------------------------------------------------------- */
+/* Number of hot-path kernel launches issued by this ctx since creation (graph replays count the
+ * kernels inside the graph). */
+ROME_B200_API uint64_t rome_b200_launch_count(const rome_b200_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ROME_B200_H */

@@ -1,0 +1,89 @@
+"""ctypes binding of librome_b200.so (include/rome_b200.h) -- the same C ABI a Julia `ccall`
+binds.  There is no fallback: a missing library or a missing GPU raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(HERE, "librome_b200.so")
+
+# enums of include/rome_b200.h
+OK, BAD_ARG, CUDA_ERROR, SHAPE_MISMATCH, NOT_SET, NO_DEVICE = 0, -1, -2, -3, -4, -5
+POSE2, POINT2, POSE3 = 0, 1, 2
+POSE2POSE2, PRIORPOSE2, BEARINGRANGE, POSE3POSE3, PRIORPOSE3 = 0, 1, 2, 3, 4
+RESIDUAL, PROPOSAL_FWD, PROPOSAL_BWD, STATS, SAMPLE, WRITE_MEAS, JACOBIAN = 1, 2, 4, 8, 16, 32, 64
+
+# every symbol include/rome_b200.h declares (tests check the library exports each one)
+SYMBOLS = [
+    "rome_b200_version", "rome_b200_create", "rome_b200_destroy", "rome_b200_last_error", "rome_b200_set_stream",
+    "rome_b200_synchronize", "rome_b200_family_dims", "rome_b200_vartype_dim", "rome_b200_npad",
+    "rome_b200_set_particles", "rome_b200_get_particles", "rome_b200_particles_device", "rome_b200_adopt_proposal",
+    "rome_b200_set_factors_pose2pose2", "rome_b200_set_factors_priorpose2", "rome_b200_set_factors_bearingrange",
+    "rome_b200_set_factors_pose3pose3", "rome_b200_set_factors_priorpose3", "rome_b200_num_factors",
+    "rome_b200_eval", "rome_b200_eval_host", "rome_b200_graph_begin", "rome_b200_graph_end",
+    "rome_b200_graph_launch", "rome_b200_malloc_device", "rome_b200_free_device", "rome_b200_malloc_host",
+    "rome_b200_free_host", "rome_b200_memcpy_h2d", "rome_b200_memcpy_d2h", "rome_b200_launch_count",
+]
+
+
+class Buffers(C.Structure):
+    """struct rome_b200_buffers"""
+    _fields_ = [("meas", C.c_void_p), ("meas_out", C.c_void_p), ("res", C.c_void_p), ("prop_fwd", C.c_void_p),
+                ("prop_bwd", C.c_void_p), ("stats", C.c_void_p), ("jac", C.c_void_p)]
+
+
+class RomeB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"rome_b200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise ImportError(f"{SO_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`"
+                          " (nvcc, sm_100a). There is no CPU fallback.")
+    lib = C.CDLL(SO_PATH)
+    vp, i, u32, u64, dp, ip32 = C.c_void_p, C.c_int, C.c_uint32, C.c_uint64, C.POINTER(C.c_double), C.POINTER(C.c_int32)
+    lib.rome_b200_version.restype = i
+    lib.rome_b200_create.argtypes = [i, C.POINTER(vp)]
+    lib.rome_b200_destroy.argtypes = [vp]
+    lib.rome_b200_last_error.restype = C.c_char_p
+    lib.rome_b200_last_error.argtypes = [vp]
+    lib.rome_b200_set_stream.argtypes = [vp, vp]
+    lib.rome_b200_synchronize.argtypes = [vp]
+    lib.rome_b200_family_dims.argtypes = [i] + [C.POINTER(i)] * 4
+    lib.rome_b200_vartype_dim.argtypes = [i]
+    lib.rome_b200_npad.argtypes = [i]
+    lib.rome_b200_set_particles.argtypes = [vp, i, i, i, vp]
+    lib.rome_b200_get_particles.argtypes = [vp, i, vp]
+    lib.rome_b200_particles_device.argtypes = [vp, i, C.POINTER(vp), C.POINTER(vp), C.POINTER(i), C.POINTER(i),
+                                               C.POINTER(i)]
+    lib.rome_b200_adopt_proposal.argtypes = [vp, i, i, vp, i]
+    lib.rome_b200_set_factors_pose2pose2.argtypes = [vp, i, ip32, ip32, dp, dp]
+    lib.rome_b200_set_factors_priorpose2.argtypes = [vp, i, ip32, dp, dp]
+    lib.rome_b200_set_factors_bearingrange.argtypes = [vp, i, ip32, ip32, dp, dp]
+    lib.rome_b200_set_factors_pose3pose3.argtypes = [vp, i, ip32, ip32, dp, dp]
+    lib.rome_b200_set_factors_priorpose3.argtypes = [vp, i, ip32, dp, dp]
+    lib.rome_b200_num_factors.argtypes = [vp, i]
+    lib.rome_b200_eval.argtypes = [vp, i, u32, u64, u32, i, i, C.POINTER(Buffers)]
+    lib.rome_b200_eval_host.argtypes = [vp, i, u32, u64, u32, i, i, C.POINTER(Buffers)]
+    lib.rome_b200_graph_begin.argtypes = [vp]
+    lib.rome_b200_graph_end.argtypes = [vp, C.POINTER(i)]
+    lib.rome_b200_graph_launch.argtypes = [vp, i]
+    lib.rome_b200_malloc_device.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+    lib.rome_b200_free_device.argtypes = [vp, vp]
+    lib.rome_b200_malloc_host.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+    lib.rome_b200_free_host.argtypes = [vp, vp]
+    lib.rome_b200_memcpy_h2d.argtypes = [vp, vp, vp, C.c_size_t]
+    lib.rome_b200_memcpy_d2h.argtypes = [vp, vp, vp, C.c_size_t]
+    lib.rome_b200_launch_count.restype = u64
+    lib.rome_b200_launch_count.argtypes = [vp]
+    _lib = lib
+    return lib

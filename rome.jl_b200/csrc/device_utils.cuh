@@ -1,0 +1,160 @@
+// device_utils.cuh -- sm_100a building blocks shared by the factor kernels:
+// TMA 1-D bulk copy + mbarrier (per-factor table staging), cache-hinted vector loads/stores,
+// Philox4x32-10 sampler, Float64 wrap helpers, and the halving-butterfly warp reduction used for
+// the per-factor statistics.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rome {
+
+constexpr double kPi = 3.14159265358979323846;
+constexpr double kTwoPi = 6.28318530717958647692;
+constexpr double kTwoPiLo = 2.4492935982947064e-16;  // 2*pi - double(2*pi)
+constexpr double kInvTwoPi = 0.15915494309189533577;
+
+// ---------------------------------------------------------------------------------------------
+// mbarrier + TMA (cp.async.bulk) -- SASS: SYNCS.* / UBLKCP
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(phase)
+            : "memory");
+    } while (!ok);
+}
+// global -> shared 1-D bulk copy, completion signalled on `bar` (bytes % 16 == 0, 16-B aligned)
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// global memory access with cache hints
+// ---------------------------------------------------------------------------------------------
+// streaming read (touched once): bypass L1 allocation
+__device__ __forceinline__ float4 ld_stream4(const float* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+// particle read (re-used by neighbouring factors): read-only path, keep in L1/L2
+__device__ __forceinline__ float4 ld_reuse4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// streaming store
+__device__ __forceinline__ void st_stream4(float* p, float4 v) { __stcs(reinterpret_cast<float4*>(p), v); }
+
+__device__ __forceinline__ float& f4(float4& v, int j) { return reinterpret_cast<float*>(&v)[j]; }
+__device__ __forceinline__ float f4c(const float4& v, int j) { return reinterpret_cast<const float*>(&v)[j]; }
+
+// ---------------------------------------------------------------------------------------------
+// Float64 angle helpers
+// ---------------------------------------------------------------------------------------------
+// a - 2*pi*rint(a/2pi) in [-pi, pi]; equals atan(sin a, cos a) of src/factors/Pose2D.jl:64 away from
+// the branch cut, and |.| = pi on it.
+__device__ __forceinline__ double wrap_pi(double a) {
+    const double k = rint(a * kInvTwoPi);
+    return fma(-k, kTwoPiLo, fma(-k, kTwoPi, a));
+}
+// Manifolds.sym_rem (src/factors/BearingRange2D.jl:61): [-pi, pi], x ~ pi -> -pi
+__device__ __forceinline__ double sym_rem(double x) {
+    const double r = wrap_pi(x);
+    return (fabs(x - kPi) <= 1.4901161193847656e-08 * fmax(fabs(x), kPi)) ? -kPi : r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 counter RNG + Box-Muller; host twin: oracle/rome_oracle.c rome_oracle_normal4
+// counter = (particle, factor, stream, block), key = seed
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return c;
+}
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
+    const float u1 = (static_cast<float>(a >> 9) + 0.5f) * (1.0f / 8388608.0f);  // exact, in (0,1)
+    const float u2 = (static_cast<float>(b >> 9) + 0.5f) * (1.0f / 8388608.0f);
+    const float rad = sqrtf(-2.0f * logf(u1));
+    float s, c;
+    sincospif(2.0f * u2, &s, &c);
+    z0 = rad * c;
+    z1 = rad * s;
+}
+__device__ __forceinline__ void normal4(uint32_t seed_lo, uint32_t seed_hi, uint32_t stream, uint32_t factor,
+                                        uint32_t particle, uint32_t block, float z[4]) {
+    const uint4 x = philox4x32_10(make_uint4(particle, factor, stream, block), seed_lo, seed_hi);
+    box_muller(x.x, x.y, z[0], z[1]);
+    box_muller(x.z, x.w, z[2], z[3]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// warp reductions: halving butterfly ("reduce-scatter" over lanes).  K values per lane in,
+// after log2(K) exchange steps every lane owns ONE fully reduced value: K=16 -> value index
+// lane>>1 (16 shuffles instead of 80), K=32 -> value index lane (31 shuffles instead of 160).
+// ---------------------------------------------------------------------------------------------
+template <int K, int BIT>
+struct HalvingStep {
+    static __device__ __forceinline__ float run(float (&v)[K], int lane) {
+        constexpr int H = K / 2;
+        float w[H];
+        const bool up = (lane & BIT) != 0;
+#pragma unroll
+        for (int i = 0; i < H; ++i) {
+            const float send = up ? v[i] : v[i + H];
+            const float keep = up ? v[i + H] : v[i];
+            w[i] = keep + __shfl_xor_sync(0xffffffffu, send, BIT);
+        }
+        return HalvingStep<H, BIT / 2>::run(w, lane);
+    }
+};
+template <int BIT>
+struct HalvingStep<1, BIT> {
+    static __device__ __forceinline__ float run(float (&v)[1], int) {
+        float x = v[0];
+#pragma unroll
+        for (int b = BIT; b >= 1; b >>= 1) x += __shfl_xor_sync(0xffffffffu, x, b);
+        return x;
+    }
+};
+// 16 values per lane -> lane holds total of value (lane >> 1)
+__device__ __forceinline__ float warp_reduce_scatter16(float (&v)[16], int lane) {
+    return HalvingStep<16, 16>::run(v, lane);
+}
+// 32 values per lane -> lane holds total of value `lane`
+__device__ __forceinline__ float warp_reduce_scatter32(float (&v)[32], int lane) {
+    return HalvingStep<32, 16>::run(v, lane);
+}
+
+}  // namespace rome

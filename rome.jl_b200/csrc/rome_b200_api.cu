@@ -1,0 +1,581 @@
+// rome_b200_api.cu -- the C ABI (include/rome_b200.h): context, particle/factor stores, eval
+// entry points, CUDA-graph capture.  No CPU fallback: every compute entry point needs a device.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/rome_b200.h"
+#include "tables.h"
+
+using namespace rome;
+
+namespace {
+
+struct VarStore {
+    int nvars = 0, N = 0, Npad = 0;
+    float* off = nullptr;
+    double* anchors = nullptr;
+    size_t cap_off = 0, cap_anchor = 0;  // bytes
+};
+struct FactorStore {
+    int nF = 0;
+    void* rows = nullptr;
+    size_t cap = 0;
+    int max_i0 = -1, max_i1 = -1;
+};
+struct Scratch {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+const int kVarDim[ROME_B200_NVARTYPES] = {3, 2, 6};
+const int kWrapDim[ROME_B200_NVARTYPES] = {2, -1, -1};
+// family -> (first variable type, second variable type or -1, dm, dr, nstats, dj, row bytes, prop dims fwd/bwd)
+struct FamInfo {
+    int vt0, vt1, dm, dr, nstats, dj, row_bytes, dfwd, dbwd;
+};
+const FamInfo kFam[ROME_B200_NFAMILIES] = {
+    {ROME_B200_POSE2, ROME_B200_POSE2, 3, 3, 16, 4, (int)sizeof(RowSE2), 3, 3},
+    {ROME_B200_POSE2, -1, 3, 3, 16, 0, (int)sizeof(RowSE2), 3, 0},
+    {ROME_B200_POSE2, ROME_B200_POINT2, 2, 2, 16, 4, (int)sizeof(RowBR), 2, 0},
+    {ROME_B200_POSE3, ROME_B200_POSE3, 6, 6, 32, 0, (int)sizeof(RowSE3), 6, 6},
+    {ROME_B200_POSE3, -1, 6, 6, 32, 0, (int)sizeof(RowSE3), 6, 0},
+};
+
+thread_local std::string g_create_error;
+
+}  // namespace
+
+struct rome_b200_ctx {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::string err;
+    VarStore vars[ROME_B200_NVARTYPES];
+    FactorStore fac[ROME_B200_NFAMILIES];
+    int occ[ROME_B200_NFAMILIES][2];
+    Scratch stage_dev, stage_host;            // particle upload/download staging
+    Scratch out_dev[8];                       // eval_host device mirrors: meas, meas_out, res, fwd, bwd, stats, jac
+    std::vector<cudaGraphExec_t> graphs;
+    std::vector<uint64_t> graph_kernels;
+    bool capturing = false;
+    uint64_t capture_kernels = 0;
+    uint64_t launches = 0;
+};
+
+namespace {
+
+int fail(rome_b200_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg;
+    else g_create_error = msg;
+    return code;
+}
+int cuda_fail(rome_b200_ctx* c, cudaError_t e, const char* what) {
+    return fail(c, ROME_B200_CUDA_ERROR, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CK(call)                                                   \
+    do {                                                           \
+        cudaError_t e__ = (call);                                  \
+        if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #call); \
+    } while (0)
+
+int bind(rome_b200_ctx* ctx) {
+    CK(cudaSetDevice(ctx->device));
+    return 0;
+}
+int grow_dev(rome_b200_ctx* ctx, Scratch& s, size_t bytes) {
+    if (bytes <= s.cap) return 0;
+    if (s.p) CK(cudaFree(s.p));
+    s.p = nullptr; s.cap = 0;
+    CK(cudaMalloc(&s.p, bytes));
+    s.cap = bytes;
+    return 0;
+}
+int grow_host(rome_b200_ctx* ctx, Scratch& s, size_t bytes) {
+    if (bytes <= s.cap) return 0;
+    if (s.p) CK(cudaFreeHost(s.p));
+    s.p = nullptr; s.cap = 0;
+    CK(cudaMallocHost(&s.p, bytes));
+    s.cap = bytes;
+    return 0;
+}
+bool is_pinned_or_device(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// lower Cholesky factor of a symmetric d x d matrix (row-major), Float64; false if not positive definite
+bool cholesky(const double* A, int d, double* L) {
+    for (int i = 0; i < d * d; ++i) L[i] = 0.0;
+    for (int j = 0; j < d; ++j) {
+        double s = A[j * d + j];
+        for (int k = 0; k < j; ++k) s -= L[j * d + k] * L[j * d + k];
+        if (!(s > 0.0)) return false;
+        L[j * d + j] = std::sqrt(s);
+        for (int i = j + 1; i < d; ++i) {
+            double t = 0.5 * (A[i * d + j] + A[j * d + i]);
+            for (int k = 0; k < j; ++k) t -= L[i * d + k] * L[j * d + k];
+            L[i * d + j] = t / L[j * d + j];
+        }
+    }
+    return true;
+}
+
+int upload_rows(rome_b200_ctx* ctx, int family, const void* host_rows, int nF, int max_i0, int max_i1) {
+    if (int e = bind(ctx)) return e;
+    FactorStore& fs = ctx->fac[family];
+    const size_t bytes = (size_t)nF * kFam[family].row_bytes;
+    if (bytes > fs.cap) {
+        if (fs.rows) CK(cudaFree(fs.rows));
+        fs.rows = nullptr; fs.cap = 0;
+        CK(cudaMalloc(&fs.rows, bytes ? bytes : 256));
+        fs.cap = bytes ? bytes : 256;
+    }
+    if (bytes) {
+        CK(cudaMemcpyAsync(fs.rows, host_rows, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));  // host_rows is a temporary
+    }
+    fs.nF = nF; fs.max_i0 = max_i0; fs.max_i1 = max_i1;
+    return 0;
+}
+
+template <class Row, int D>
+int set_gaussian_factors(rome_b200_ctx* ctx, int family, int nF, const int32_t* ip, const int32_t* iq,
+                         const double* mu, const double* cov) {
+    if (!ctx) return ROME_B200_BAD_ARG;
+    if (nF < 0 || (nF > 0 && (!ip || !mu || !cov))) return fail(ctx, ROME_B200_BAD_ARG, "null factor arrays");
+    std::vector<Row> rows((size_t)nF);
+    int m0 = -1, m1 = -1;
+    double L[D * D];
+    for (int f = 0; f < nF; ++f) {
+        Row& r = rows[f];
+        std::memset(&r, 0, sizeof(Row));
+        r.ip = ip[f];
+        r.iq = iq ? iq[f] : -1;
+        if (r.ip < 0 || (iq && r.iq < 0)) return fail(ctx, ROME_B200_BAD_ARG, "negative variable index");
+        if (r.ip > m0) m0 = r.ip;
+        if (r.iq > m1) m1 = r.iq;
+        for (int i = 0; i < D; ++i) r.mu[i] = mu[(size_t)f * D + i];
+        if (!cholesky(cov + (size_t)f * D * D, D, L)) {
+            char b[96];
+            std::snprintf(b, sizeof b, "covariance of factor %d is not positive definite", f);
+            return fail(ctx, ROME_B200_BAD_ARG, b);
+        }
+        int k = 0;
+        for (int i = 0; i < D; ++i)
+            for (int j = 0; j <= i; ++j) r.L[k++] = (float)L[i * D + j];
+    }
+    return upload_rows(ctx, family, rows.data(), nF, m0, m1);
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+int rome_b200_version(void) { return ROME_B200_VERSION; }
+
+int rome_b200_create(int device, rome_b200_ctx** out) {
+    if (!out) return fail(nullptr, ROME_B200_BAD_ARG, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(nullptr, ROME_B200_NO_DEVICE,
+                    std::string("no CUDA device (librome_b200 has no CPU fallback): ") + cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(nullptr, ROME_B200_BAD_ARG, "device index out of range");
+    rome_b200_ctx* ctx = new (std::nothrow) rome_b200_ctx();
+    if (!ctx) return fail(nullptr, ROME_B200_BAD_ARG, "out of host memory");
+    ctx->device = device;
+    if ((e = cudaSetDevice(device)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) {
+        delete ctx;
+        return fail(nullptr, ROME_B200_CUDA_ERROR, std::string("context creation: ") + cudaGetErrorString(e));
+    }
+    ctx->stream = ctx->own_stream;
+    for (int f = 0; f < ROME_B200_NFAMILIES; ++f)
+        for (int s = 0; s < 2; ++s) ctx->occ[f][s] = max_resident_ctas(f, s != 0);
+    if ((e = cudaGetLastError()) != cudaSuccess) {
+        // e.g. no kernel image for this device: the library is built for sm_100a only
+        cudaStreamDestroy(ctx->own_stream);
+        delete ctx;
+        return fail(nullptr, ROME_B200_CUDA_ERROR, std::string("kernel image unusable on this device: ") +
+                                                       cudaGetErrorString(e));
+    }
+    *out = ctx;
+    return ROME_B200_OK;
+}
+
+int rome_b200_destroy(rome_b200_ctx* ctx) {
+    if (!ctx) return ROME_B200_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto g : ctx->graphs) cudaGraphExecDestroy(g);
+    for (auto& v : ctx->vars) { cudaFree(v.off); cudaFree(v.anchors); }
+    for (auto& f : ctx->fac) cudaFree(f.rows);
+    cudaFree(ctx->stage_dev.p);
+    cudaFreeHost(ctx->stage_host.p);
+    for (auto& s : ctx->out_dev) cudaFree(s.p);
+    cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return ROME_B200_OK;
+}
+
+const char* rome_b200_last_error(const rome_b200_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int rome_b200_set_stream(rome_b200_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return ROME_B200_BAD_ARG;
+    if (ctx->capturing) return fail(ctx, ROME_B200_BAD_ARG, "cannot change stream during graph capture");
+    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return ROME_B200_OK;
+}
+
+int rome_b200_synchronize(rome_b200_ctx* ctx) {
+    if (!ctx) return ROME_B200_BAD_ARG;
+    if (int e = bind(ctx)) return e;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ROME_B200_OK;
+}
+
+int rome_b200_family_dims(int family, int* dm, int* dr, int* nstats, int* dj) {
+    if (family < 0 || family >= ROME_B200_NFAMILIES) return ROME_B200_BAD_ARG;
+    if (dm) *dm = kFam[family].dm;
+    if (dr) *dr = kFam[family].dr;
+    if (nstats) *nstats = kFam[family].nstats;
+    if (dj) *dj = kFam[family].dj;
+    return ROME_B200_OK;
+}
+int rome_b200_vartype_dim(int vartype) {
+    return (vartype < 0 || vartype >= ROME_B200_NVARTYPES) ? ROME_B200_BAD_ARG : kVarDim[vartype];
+}
+int rome_b200_npad(int N) { return N <= 0 ? ROME_B200_BAD_ARG : (N + 7) / 8 * 8; }
+
+// ---------------------------------------------------------------------------------------------
+int rome_b200_set_particles(rome_b200_ctx* ctx, int vartype, int nvars, int N, const double* coords_host) {
+    if (!ctx) return ROME_B200_BAD_ARG;
+    if (vartype < 0 || vartype >= ROME_B200_NVARTYPES) return fail(ctx, ROME_B200_BAD_ARG, "bad vartype");
+    if (nvars < 0 || N <= 0 || (nvars > 0 && !coords_host)) return fail(ctx, ROME_B200_BAD_ARG, "bad particle shape");
+    if (ctx->capturing) return fail(ctx, ROME_B200_BAD_ARG, "set_particles during graph capture");
+    for (int t = 0; t < ROME_B200_NVARTYPES; ++t)
+        if (t != vartype && ctx->vars[t].nvars > 0 && ctx->vars[t].N != N)
+            return fail(ctx, ROME_B200_SHAPE_MISMATCH, "all variable types of one context must share N");
+    if (int e = bind(ctx)) return e;
+    const int d = kVarDim[vartype], Npad = rome_b200_npad(N);
+    VarStore& vs = ctx->vars[vartype];
+    const size_t off_bytes = (size_t)nvars * d * Npad * sizeof(float);
+    const size_t anc_bytes = (size_t)nvars * d * sizeof(double);
+    if (off_bytes > vs.cap_off) {
+        if (vs.off) CK(cudaFree(vs.off));
+        vs.off = nullptr; vs.cap_off = 0;
+        CK(cudaMalloc(&vs.off, off_bytes));
+        vs.cap_off = off_bytes;
+    }
+    if (anc_bytes > vs.cap_anchor) {
+        if (vs.anchors) CK(cudaFree(vs.anchors));
+        vs.anchors = nullptr; vs.cap_anchor = 0;
+        CK(cudaMalloc(&vs.anchors, anc_bytes));
+        vs.cap_anchor = anc_bytes;
+    }
+    vs.nvars = nvars; vs.N = N; vs.Npad = Npad;
+    if (nvars == 0) return ROME_B200_OK;
+    const size_t in_bytes = (size_t)nvars * N * d * sizeof(double);
+    if (int e = grow_dev(ctx, ctx->stage_dev, in_bytes)) return e;
+    const void* src = coords_host;
+    if (!is_pinned_or_device(coords_host)) {  // pageable caller memory: stage through pinned memory
+        if (int e = grow_host(ctx, ctx->stage_host, in_bytes)) return e;
+        CK(cudaStreamSynchronize(ctx->stream));  // staging buffer may still be in flight
+        std::memcpy(ctx->stage_host.p, coords_host, in_bytes);
+        src = ctx->stage_host.p;
+    }
+    CK(cudaMemcpyAsync(ctx->stage_dev.p, src, in_bytes, cudaMemcpyDefault, ctx->stream));
+    int e = launch_pack(d, kWrapDim[vartype], nvars, N, Npad, static_cast<const double*>(ctx->stage_dev.p), vs.off,
+                        vs.anchors, ctx->stream);
+    if (e) return cuda_fail(ctx, (cudaError_t)e, "pack kernel");
+    return ROME_B200_OK;
+}
+
+int rome_b200_get_particles(rome_b200_ctx* ctx, int vartype, double* coords_host) {
+    if (!ctx) return ROME_B200_BAD_ARG;
+    if (vartype < 0 || vartype >= ROME_B200_NVARTYPES || !coords_host) return fail(ctx, ROME_B200_BAD_ARG, "bad argument");
+    VarStore& vs = ctx->vars[vartype];
+    if (vs.nvars == 0) return fail(ctx, ROME_B200_NOT_SET, "particles of this variable type are not set");
+    if (int e = bind(ctx)) return e;
+    const int d = kVarDim[vartype];
+    const size_t bytes = (size_t)vs.nvars * vs.N * d * sizeof(double);
+    if (int e = grow_dev(ctx, ctx->stage_dev, bytes)) return e;
+    int e = launch_unpack(d, kWrapDim[vartype], vs.nvars, vs.N, vs.Npad, vs.off, vs.anchors,
+                          static_cast<double*>(ctx->stage_dev.p), ctx->stream);
+    if (e) return cuda_fail(ctx, (cudaError_t)e, "unpack kernel");
+    CK(cudaMemcpyAsync(coords_host, ctx->stage_dev.p, bytes, cudaMemcpyDefault, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ROME_B200_OK;
+}
+
+int rome_b200_particles_device(rome_b200_ctx* ctx, int vartype, float** d_offsets, double** d_anchors, int* nvars,
+                               int* N, int* Npad) {
+    if (!ctx) return ROME_B200_BAD_ARG;
+    if (vartype < 0 || vartype >= ROME_B200_NVARTYPES) return fail(ctx, ROME_B200_BAD_ARG, "bad vartype");
+    VarStore& vs = ctx->vars[vartype];
+    if (vs.nvars == 0) return fail(ctx, ROME_B200_NOT_SET, "particles of this variable type are not set");
+    if (d_offsets) *d_offsets = vs.off;
+    if (d_anchors) *d_anchors = vs.anchors;
+    if (nvars) *nvars = vs.nvars;
+    if (N) *N = vs.N;
+    if (Npad) *Npad = vs.Npad;
+    return ROME_B200_OK;
+}
+
+int rome_b200_adopt_proposal(rome_b200_ctx* ctx, int vartype, int var, const float* d_prop, int factor) {
+    if (!ctx) return ROME_B200_BAD_ARG;
+    if (vartype < 0 || vartype >= ROME_B200_NVARTYPES || !d_prop || factor < 0)
+        return fail(ctx, ROME_B200_BAD_ARG, "bad argument");
+    VarStore& vs = ctx->vars[vartype];
+    if (var < 0 || var >= vs.nvars) return fail(ctx, ROME_B200_BAD_ARG, "variable index out of range");
+    if (int e = bind(ctx)) return e;
+    int e = launch_adopt(kVarDim[vartype], vs.Npad, vs.off, var, d_prop, factor, ctx->stream);
+    if (e) return cuda_fail(ctx, (cudaError_t)e, "adopt kernel");
+    if (ctx->capturing) ctx->capture_kernels++; else ctx->launches++;
+    return ROME_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+int rome_b200_set_factors_pose2pose2(rome_b200_ctx* ctx, int nF, const int32_t* ip, const int32_t* iq,
+                                     const double* mu, const double* cov) {
+    if (ctx && nF > 0 && !iq) return fail(ctx, ROME_B200_BAD_ARG, "iq is NULL");
+    return set_gaussian_factors<RowSE2, 3>(ctx, ROME_B200_POSE2POSE2, nF, ip, iq, mu, cov);
+}
+int rome_b200_set_factors_priorpose2(rome_b200_ctx* ctx, int nF, const int32_t* ip, const double* mu,
+                                     const double* cov) {
+    return set_gaussian_factors<RowSE2, 3>(ctx, ROME_B200_PRIORPOSE2, nF, ip, nullptr, mu, cov);
+}
+int rome_b200_set_factors_pose3pose3(rome_b200_ctx* ctx, int nF, const int32_t* ip, const int32_t* iq,
+                                     const double* mu, const double* cov) {
+    if (ctx && nF > 0 && !iq) return fail(ctx, ROME_B200_BAD_ARG, "iq is NULL");
+    return set_gaussian_factors<RowSE3, 6>(ctx, ROME_B200_POSE3POSE3, nF, ip, iq, mu, cov);
+}
+int rome_b200_set_factors_priorpose3(rome_b200_ctx* ctx, int nF, const int32_t* ip, const double* mu,
+                                     const double* cov) {
+    return set_gaussian_factors<RowSE3, 6>(ctx, ROME_B200_PRIORPOSE3, nF, ip, nullptr, mu, cov);
+}
+int rome_b200_set_factors_bearingrange(rome_b200_ctx* ctx, int nF, const int32_t* ip, const int32_t* il,
+                                       const double* bearing, const double* range) {
+    if (!ctx) return ROME_B200_BAD_ARG;
+    if (nF < 0 || (nF > 0 && (!ip || !il || !bearing || !range))) return fail(ctx, ROME_B200_BAD_ARG, "null factor arrays");
+    std::vector<RowBR> rows((size_t)nF);
+    int m0 = -1, m1 = -1;
+    for (int f = 0; f < nF; ++f) {
+        RowBR& r = rows[f];
+        r.ip = ip[f]; r.il = il[f];
+        if (r.ip < 0 || r.il < 0) return fail(ctx, ROME_B200_BAD_ARG, "negative variable index");
+        if (!(bearing[2 * f + 1] > 0.0) || !(range[2 * f + 1] > 0.0))
+            return fail(ctx, ROME_B200_BAD_ARG, "standard deviation must be positive");
+        if (r.ip > m0) m0 = r.ip;
+        if (r.il > m1) m1 = r.il;
+        r.mu_b = bearing[2 * f]; r.sig_b = (float)bearing[2 * f + 1];
+        r.mu_r = range[2 * f]; r.sig_r = (float)range[2 * f + 1];
+    }
+    return upload_rows(ctx, ROME_B200_BEARINGRANGE, rows.data(), nF, m0, m1);
+}
+int rome_b200_num_factors(rome_b200_ctx* ctx, int family) {
+    if (!ctx || family < 0 || family >= ROME_B200_NFAMILIES) return ROME_B200_BAD_ARG;
+    return ctx->fac[family].nF;
+}
+
+// ---------------------------------------------------------------------------------------------
+static int check_eval(rome_b200_ctx* ctx, int family, uint32_t flags, int first, int& count,
+                      const rome_b200_buffers* b) {
+    if (!ctx) return ROME_B200_BAD_ARG;
+    if (family < 0 || family >= ROME_B200_NFAMILIES) return fail(ctx, ROME_B200_BAD_ARG, "bad family");
+    if (!b) return fail(ctx, ROME_B200_BAD_ARG, "buffers is NULL");
+    const FamInfo& fi = kFam[family];
+    FactorStore& fs = ctx->fac[family];
+    if (fs.rows == nullptr) return fail(ctx, ROME_B200_NOT_SET, "factors of this family are not set");
+    if (count < 0) count = fs.nF - first;
+    if (first < 0 || count < 0 || first + count > fs.nF) return fail(ctx, ROME_B200_BAD_ARG, "factor range out of bounds");
+    const VarStore& v0 = ctx->vars[fi.vt0];
+    if (v0.nvars == 0) return fail(ctx, ROME_B200_NOT_SET, "particles of the first variable type are not set");
+    if (fs.max_i0 >= v0.nvars) return fail(ctx, ROME_B200_SHAPE_MISMATCH, "factor refers to a variable index beyond the particle store");
+    if (fi.vt1 >= 0) {
+        const VarStore& v1 = ctx->vars[fi.vt1];
+        if (v1.nvars == 0) return fail(ctx, ROME_B200_NOT_SET, "particles of the second variable type are not set");
+        if (fs.max_i1 >= v1.nvars) return fail(ctx, ROME_B200_SHAPE_MISMATCH, "factor refers to a variable index beyond the particle store");
+        if (v1.N != v0.N) return fail(ctx, ROME_B200_SHAPE_MISMATCH, "particle counts differ between variable types");
+    }
+    if (!(flags & ROME_B200_SAMPLE) && !b->meas) return fail(ctx, ROME_B200_BAD_ARG, "meas is NULL and SAMPLE is not set");
+    if ((flags & ROME_B200_WRITE_MEAS) && (!(flags & ROME_B200_SAMPLE) || !b->meas_out))
+        return fail(ctx, ROME_B200_BAD_ARG, "WRITE_MEAS needs SAMPLE and meas_out");
+    if ((flags & ROME_B200_RESIDUAL) && !b->res) return fail(ctx, ROME_B200_BAD_ARG, "res is NULL");
+    if ((flags & ROME_B200_PROPOSAL_FWD) && !b->prop_fwd) return fail(ctx, ROME_B200_BAD_ARG, "prop_fwd is NULL");
+    if (flags & ROME_B200_PROPOSAL_BWD) {
+        if (fi.dbwd == 0) return fail(ctx, ROME_B200_BAD_ARG, "this family has no closed-form backward proposal");
+        if (!b->prop_bwd) return fail(ctx, ROME_B200_BAD_ARG, "prop_bwd is NULL");
+    }
+    if ((flags & ROME_B200_STATS) && !b->stats) return fail(ctx, ROME_B200_BAD_ARG, "stats is NULL");
+    if (flags & ROME_B200_JACOBIAN) {
+        if (fi.dj == 0) return fail(ctx, ROME_B200_BAD_ARG, "this family has no Jacobian output");
+        if (!b->jac) return fail(ctx, ROME_B200_BAD_ARG, "jac is NULL");
+    }
+    return ROME_B200_OK;
+}
+
+int rome_b200_eval(rome_b200_ctx* ctx, int family, uint32_t flags, uint64_t seed, uint32_t stream_id, int first,
+                   int count, const rome_b200_buffers* b) {
+    if (int e = check_eval(ctx, family, flags, first, count, b)) return e;
+    if (count == 0) return ROME_B200_OK;
+    if (int e = bind(ctx)) return e;
+    const FamInfo& fi = kFam[family];
+    const VarStore& v0 = ctx->vars[fi.vt0];
+    const VarStore& v1 = ctx->vars[fi.vt1 >= 0 ? fi.vt1 : fi.vt0];
+    EvalParams p;
+    p.rows = ctx->fac[family].rows;
+    p.first = first; p.count = count;
+    p.N = v0.N; p.Npad = v0.Npad;
+    p.v0 = v0.off; p.a0 = v0.anchors; p.v1 = v1.off; p.a1 = v1.anchors;
+    p.meas = b->meas; p.meas_out = b->meas_out; p.res = b->res; p.prop_fwd = b->prop_fwd; p.prop_bwd = b->prop_bwd;
+    p.stats = b->stats; p.jac = b->jac;
+    p.flags = flags;
+    p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32); p.stream_id = stream_id;
+    const int nTiles = (count + kWarpsPerCta - 1) / kWarpsPerCta;
+    const int resident = ctx->num_sms * ctx->occ[family][(flags & ROME_B200_SAMPLE) ? 1 : 0];
+    const int grid = nTiles < resident ? nTiles : resident;
+    int e = launch_eval(family, p, grid, ctx->stream);
+    if (e) return cuda_fail(ctx, (cudaError_t)e, "eval kernel launch");
+    if (ctx->capturing) ctx->capture_kernels++; else ctx->launches++;
+    return ROME_B200_OK;
+}
+
+int rome_b200_eval_host(rome_b200_ctx* ctx, int family, uint32_t flags, uint64_t seed, uint32_t stream_id, int first,
+                        int count, const rome_b200_buffers* hb) {
+    if (int e = check_eval(ctx, family, flags, first, count, hb)) return e;
+    if (ctx->capturing) return fail(ctx, ROME_B200_BAD_ARG, "eval_host during graph capture");
+    if (count == 0) return ROME_B200_OK;
+    if (int e = bind(ctx)) return e;
+    const FamInfo& fi = kFam[family];
+    const int Npad = ctx->vars[fi.vt0].Npad;
+    // per-factor strides (floats) of each buffer; device mirrors cover factors [first, first+count)
+    const size_t sm = (size_t)fi.dm * Npad, sr = (size_t)fi.dr * Npad, sf = (size_t)fi.dfwd * Npad,
+                 sb = (size_t)fi.dbwd * Npad, ss = (size_t)fi.nstats, sj = (size_t)fi.dj * Npad;
+    rome_b200_buffers db;
+    std::memset(&db, 0, sizeof db);
+    auto mirror = [&](int slot, size_t stride, float** out) -> int {
+        if (int e = grow_dev(ctx, ctx->out_dev[slot], (size_t)count * stride * sizeof(float))) return e;
+        // kernels index buffers by global factor id: bias the mirror base by -first
+        *out = static_cast<float*>(ctx->out_dev[slot].p) - (size_t)first * stride;
+        return 0;
+    };
+    float* tmp = nullptr;
+    if (!(flags & ROME_B200_SAMPLE)) {
+        if (int e = mirror(0, sm, &tmp)) return e;
+        CK(cudaMemcpyAsync(ctx->out_dev[0].p, hb->meas + (size_t)first * sm, (size_t)count * sm * sizeof(float),
+                           cudaMemcpyDefault, ctx->stream));
+        db.meas = tmp;
+    }
+    if (flags & ROME_B200_WRITE_MEAS) { if (int e = mirror(1, sm, &db.meas_out)) return e; }
+    if (flags & ROME_B200_RESIDUAL) { if (int e = mirror(2, sr, &db.res)) return e; }
+    if (flags & ROME_B200_PROPOSAL_FWD) { if (int e = mirror(3, sf, &db.prop_fwd)) return e; }
+    if (flags & ROME_B200_PROPOSAL_BWD) { if (int e = mirror(4, sb, &db.prop_bwd)) return e; }
+    if (flags & ROME_B200_STATS) { if (int e = mirror(5, ss, &db.stats)) return e; }
+    if (flags & ROME_B200_JACOBIAN) { if (int e = mirror(6, sj, &db.jac)) return e; }
+    if (int e = rome_b200_eval(ctx, family, flags, seed, stream_id, first, count, &db)) return e;
+    auto back = [&](int slot, size_t stride, float* host) -> int {
+        CK(cudaMemcpyAsync(host + (size_t)first * stride, ctx->out_dev[slot].p, (size_t)count * stride * sizeof(float),
+                           cudaMemcpyDefault, ctx->stream));
+        return 0;
+    };
+    if (flags & ROME_B200_WRITE_MEAS) { if (int e = back(1, sm, hb->meas_out)) return e; }
+    if (flags & ROME_B200_RESIDUAL) { if (int e = back(2, sr, hb->res)) return e; }
+    if (flags & ROME_B200_PROPOSAL_FWD) { if (int e = back(3, sf, hb->prop_fwd)) return e; }
+    if (flags & ROME_B200_PROPOSAL_BWD) { if (int e = back(4, sb, hb->prop_bwd)) return e; }
+    if (flags & ROME_B200_STATS) { if (int e = back(5, ss, hb->stats)) return e; }
+    if (flags & ROME_B200_JACOBIAN) { if (int e = back(6, sj, hb->jac)) return e; }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ROME_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+int rome_b200_graph_begin(rome_b200_ctx* ctx) {
+    if (!ctx) return ROME_B200_BAD_ARG;
+    if (ctx->capturing) return fail(ctx, ROME_B200_BAD_ARG, "graph capture already active");
+    if (int e = bind(ctx)) return e;
+    CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    ctx->capturing = true;
+    ctx->capture_kernels = 0;
+    return ROME_B200_OK;
+}
+int rome_b200_graph_end(rome_b200_ctx* ctx, int* graph_id) {
+    if (!ctx || !graph_id) return ROME_B200_BAD_ARG;
+    if (!ctx->capturing) return fail(ctx, ROME_B200_BAD_ARG, "no graph capture active");
+    ctx->capturing = false;
+    cudaGraph_t g = nullptr;
+    CK(cudaStreamEndCapture(ctx->stream, &g));
+    cudaGraphExec_t ge = nullptr;
+    cudaError_t e = cudaGraphInstantiate(&ge, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaGraphInstantiate");
+    ctx->graphs.push_back(ge);
+    ctx->graph_kernels.push_back(ctx->capture_kernels);
+    *graph_id = (int)ctx->graphs.size() - 1;
+    return ROME_B200_OK;
+}
+int rome_b200_graph_launch(rome_b200_ctx* ctx, int graph_id) {
+    if (!ctx) return ROME_B200_BAD_ARG;
+    if (graph_id < 0 || graph_id >= (int)ctx->graphs.size()) return fail(ctx, ROME_B200_BAD_ARG, "bad graph id");
+    if (int e = bind(ctx)) return e;
+    CK(cudaGraphLaunch(ctx->graphs[graph_id], ctx->stream));
+    ctx->launches += ctx->graph_kernels[graph_id];
+    return ROME_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+int rome_b200_malloc_device(rome_b200_ctx* ctx, size_t bytes, void** out) {
+    if (!ctx || !out) return ROME_B200_BAD_ARG;
+    if (int e = bind(ctx)) return e;
+    CK(cudaMalloc(out, bytes ? bytes : 1));
+    return ROME_B200_OK;
+}
+int rome_b200_free_device(rome_b200_ctx* ctx, void* p) {
+    if (!ctx) return ROME_B200_BAD_ARG;
+    if (int e = bind(ctx)) return e;
+    CK(cudaFree(p));
+    return ROME_B200_OK;
+}
+int rome_b200_malloc_host(rome_b200_ctx* ctx, size_t bytes, void** out) {
+    if (!ctx || !out) return ROME_B200_BAD_ARG;
+    if (int e = bind(ctx)) return e;
+    CK(cudaMallocHost(out, bytes ? bytes : 1));
+    return ROME_B200_OK;
+}
+int rome_b200_free_host(rome_b200_ctx* ctx, void* p) {
+    if (!ctx) return ROME_B200_BAD_ARG;
+    if (int e = bind(ctx)) return e;
+    CK(cudaFreeHost(p));
+    return ROME_B200_OK;
+}
+int rome_b200_memcpy_h2d(rome_b200_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
+    if (!ctx) return ROME_B200_BAD_ARG;
+    if (int e = bind(ctx)) return e;
+    CK(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ROME_B200_OK;
+}
+int rome_b200_memcpy_d2h(rome_b200_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes) {
+    if (!ctx) return ROME_B200_BAD_ARG;
+    if (int e = bind(ctx)) return e;
+    CK(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ROME_B200_OK;
+}
+
+uint64_t rome_b200_launch_count(const rome_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,254 @@
+"""Thin object wrapper over the C ABI (include/rome_b200.h) plus the layout helpers a host caller
+needs (reference Float64 particle-major arrays <-> anchored float32 SoA device rows).
+
+All compute goes through librome_b200.so; nothing here evaluates a factor on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from ._lib import (BEARINGRANGE, JACOBIAN, POINT2, POSE2, POSE2POSE2, POSE3, POSE3POSE3, PRIORPOSE2, PRIORPOSE3,
+                   PROPOSAL_BWD, PROPOSAL_FWD, RESIDUAL, SAMPLE, STATS, WRITE_MEAS, Buffers, RomeB200Error)
+
+VAR_DIM = {POSE2: 3, POINT2: 2, POSE3: 6}
+# family -> (vartype of first variable, vartype of second variable or None, dm, dr, nstats, dj, dfwd, dbwd)
+FAMILY = {
+    POSE2POSE2: (POSE2, POSE2, 3, 3, 16, 4, 3, 3),
+    PRIORPOSE2: (POSE2, None, 3, 3, 16, 0, 3, 0),
+    BEARINGRANGE: (POSE2, POINT2, 2, 2, 16, 4, 2, 0),
+    POSE3POSE3: (POSE3, POSE3, 6, 6, 32, 0, 6, 6),
+    PRIORPOSE3: (POSE3, None, 6, 6, 32, 0, 6, 0),
+}
+# algorithmic bytes per factor-particle eval with this layout (DESIGN.md "bytes per eval"):
+# read both variables' offsets + the measurement offsets, write the residual (float32 each)
+BYTES_PER_EVAL = {POSE2POSE2: 48, PRIORPOSE2: 36, BEARINGRANGE: 36, POSE3POSE3: 96, PRIORPOSE3: 72}
+BYTES_PER_EVAL_SAMPLED = {POSE2POSE2: 36, PRIORPOSE2: 24, BEARINGRANGE: 28, POSE3POSE3: 72, PRIORPOSE3: 48}
+
+
+def npad(N: int) -> int:
+    return (N + 7) // 8 * 8
+
+
+def _ptr(x):
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    if hasattr(x, "data_ptr"):
+        return x.data_ptr()
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data
+    raise TypeError(f"cannot take a pointer of {type(x)}")
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class Context:
+    """One rome_b200_ctx: particle stores, factor tables and the stream work is issued on."""
+
+    def __init__(self, device: int = 0):
+        self._lib = L.load()
+        h = C.c_void_p()
+        rc = self._lib.rome_b200_create(device, C.byref(h))
+        if rc != 0:
+            raise RomeB200Error(rc, self._lib.rome_b200_last_error(None).decode())
+        self._h = h
+        self.device = device
+
+    # -- plumbing ------------------------------------------------------------------------------
+    def _ck(self, rc):
+        if rc != 0:
+            raise RomeB200Error(rc, self._lib.rome_b200_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.rome_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_stream(self, cuda_stream_ptr):
+        self._ck(self._lib.rome_b200_set_stream(self._h, cuda_stream_ptr))
+
+    def use_torch_stream(self):
+        import torch
+        self.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def synchronize(self):
+        self._ck(self._lib.rome_b200_synchronize(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.rome_b200_launch_count(self._h))
+
+    # -- variables -----------------------------------------------------------------------------
+    def set_particles(self, vartype: int, coords):
+        """coords: Float64 [nvars][N][d] (reference layout); numpy array or pinned torch tensor."""
+        if isinstance(coords, np.ndarray):
+            coords = _f64(coords)
+        nvars, N, d = coords.shape
+        if d != VAR_DIM[vartype]:
+            raise ValueError("coordinate dimension does not match the variable type")
+        self._ck(self._lib.rome_b200_set_particles(self._h, vartype, nvars, N, _ptr(coords)))
+        self._keep = coords  # keep alive until the async copy is consumed
+
+    def get_particles(self, vartype: int) -> np.ndarray:
+        _, _, nvars, N, _ = self.particles_device(vartype)
+        out = np.empty((nvars, N, VAR_DIM[vartype]))
+        self._ck(self._lib.rome_b200_get_particles(self._h, vartype, out.ctypes.data))
+        return out
+
+    def particles_device(self, vartype: int):
+        po, pa = C.c_void_p(), C.c_void_p()
+        nv, N, Np = C.c_int(), C.c_int(), C.c_int()
+        self._ck(self._lib.rome_b200_particles_device(self._h, vartype, C.byref(po), C.byref(pa), C.byref(nv),
+                                                      C.byref(N), C.byref(Np)))
+        return po.value, pa.value, nv.value, N.value, Np.value
+
+    def get_anchors(self, vartype: int) -> np.ndarray:
+        _, pa, nvars, _, _ = self.particles_device(vartype)
+        out = np.empty((nvars, VAR_DIM[vartype]))
+        self._ck(self._lib.rome_b200_memcpy_d2h(self._h, out.ctypes.data, pa, out.nbytes))
+        return out
+
+    def get_offsets(self, vartype: int) -> np.ndarray:
+        po, _, nvars, _, Np = self.particles_device(vartype)
+        out = np.empty((nvars, VAR_DIM[vartype], Np), dtype=np.float32)
+        self._ck(self._lib.rome_b200_memcpy_d2h(self._h, out.ctypes.data, po, out.nbytes))
+        return out
+
+    def adopt_proposal(self, vartype: int, var: int, d_prop, factor: int):
+        self._ck(self._lib.rome_b200_adopt_proposal(self._h, vartype, var, _ptr(d_prop), factor))
+
+    # -- factors -------------------------------------------------------------------------------
+    def _dp(self, a):
+        return a.ctypes.data_as(C.POINTER(C.c_double))
+
+    def _ip(self, a):
+        return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+    def set_factors_pose2pose2(self, ip, iq, mu, cov):
+        ip, iq, mu, cov = _i32(ip), _i32(iq), _f64(mu), _f64(cov)
+        self._ck(self._lib.rome_b200_set_factors_pose2pose2(self._h, len(ip), self._ip(ip), self._ip(iq),
+                                                            self._dp(mu), self._dp(cov)))
+
+    def set_factors_priorpose2(self, ip, mu, cov):
+        ip, mu, cov = _i32(ip), _f64(mu), _f64(cov)
+        self._ck(self._lib.rome_b200_set_factors_priorpose2(self._h, len(ip), self._ip(ip), self._dp(mu),
+                                                            self._dp(cov)))
+
+    def set_factors_bearingrange(self, ip, il, bearing, rng):
+        ip, il, bearing, rng = _i32(ip), _i32(il), _f64(bearing), _f64(rng)
+        self._ck(self._lib.rome_b200_set_factors_bearingrange(self._h, len(ip), self._ip(ip), self._ip(il),
+                                                              self._dp(bearing), self._dp(rng)))
+
+    def set_factors_pose3pose3(self, ip, iq, mu, cov):
+        ip, iq, mu, cov = _i32(ip), _i32(iq), _f64(mu), _f64(cov)
+        self._ck(self._lib.rome_b200_set_factors_pose3pose3(self._h, len(ip), self._ip(ip), self._ip(iq),
+                                                            self._dp(mu), self._dp(cov)))
+
+    def set_factors_priorpose3(self, ip, mu, cov):
+        ip, mu, cov = _i32(ip), _f64(mu), _f64(cov)
+        self._ck(self._lib.rome_b200_set_factors_priorpose3(self._h, len(ip), self._ip(ip), self._dp(mu),
+                                                            self._dp(cov)))
+
+    def num_factors(self, family: int) -> int:
+        return self._lib.rome_b200_num_factors(self._h, family)
+
+    # -- hot path ------------------------------------------------------------------------------
+    @staticmethod
+    def _buffers(meas, meas_out, res, prop_fwd, prop_bwd, stats, jac) -> Buffers:
+        return Buffers(_ptr(meas), _ptr(meas_out), _ptr(res), _ptr(prop_fwd), _ptr(prop_bwd), _ptr(stats), _ptr(jac))
+
+    def eval(self, family, flags, *, seed=0, stream_id=0, first=0, count=-1, meas=None, meas_out=None, res=None,
+             prop_fwd=None, prop_bwd=None, stats=None, jac=None):
+        """Asynchronous launch on the ctx stream; buffers are DEVICE pointers / CUDA tensors."""
+        b = self._buffers(meas, meas_out, res, prop_fwd, prop_bwd, stats, jac)
+        self._ck(self._lib.rome_b200_eval(self._h, family, flags, seed, stream_id, first, count, C.byref(b)))
+
+    def eval_host(self, family, flags, *, seed=0, stream_id=0, first=0, count=-1, meas=None, meas_out=None,
+                  res=None, prop_fwd=None, prop_bwd=None, stats=None, jac=None):
+        """Synchronous call with HOST buffers (numpy float32 / pinned tensors)."""
+        b = self._buffers(meas, meas_out, res, prop_fwd, prop_bwd, stats, jac)
+        self._ck(self._lib.rome_b200_eval_host(self._h, family, flags, seed, stream_id, first, count, C.byref(b)))
+
+    def alloc_host_outputs(self, family, flags):
+        """numpy float32 output arrays, shaped for all factors of the family, for eval_host."""
+        vt0, _, dm, dr, ns, dj, dfwd, dbwd = FAMILY[family]
+        nF = self.num_factors(family)
+        Np = self.particles_device(vt0)[4]
+        out = {}
+        if flags & WRITE_MEAS:
+            out["meas_out"] = np.zeros((nF, dm, Np), np.float32)
+        if flags & RESIDUAL:
+            out["res"] = np.zeros((nF, dr, Np), np.float32)
+        if flags & PROPOSAL_FWD:
+            out["prop_fwd"] = np.zeros((nF, dfwd, Np), np.float32)
+        if flags & PROPOSAL_BWD:
+            out["prop_bwd"] = np.zeros((nF, dbwd, Np), np.float32)
+        if flags & STATS:
+            out["stats"] = np.zeros((nF, ns), np.float32)
+        if flags & JACOBIAN:
+            out["jac"] = np.zeros((nF, dj, Np), np.float32)
+        return out
+
+    # -- CUDA graphs ---------------------------------------------------------------------------
+    def graph_begin(self):
+        self._ck(self._lib.rome_b200_graph_begin(self._h))
+
+    def graph_end(self) -> int:
+        g = C.c_int()
+        self._ck(self._lib.rome_b200_graph_end(self._h, C.byref(g)))
+        return g.value
+
+    def graph_launch(self, graph_id: int):
+        self._ck(self._lib.rome_b200_graph_launch(self._h, graph_id))
+
+
+# ----------------------------------------------------------------------------------------------
+# layout helpers (host side, numpy): reference layout <-> device rows
+# ----------------------------------------------------------------------------------------------
+def meas_to_offsets(meas, mu, Npad=None) -> np.ndarray:
+    """Float64 samples [nF][N][dm] (reference `sampleFactor` output, coordinates) -> float32 offsets from
+    the factor mean, SoA [nF][dm][Npad]."""
+    meas, mu = _f64(meas), _f64(mu)
+    nF, N, dm = meas.shape
+    Np = Npad or npad(N)
+    out = np.zeros((nF, dm, Np), np.float32)
+    out[:, :, :N] = np.transpose(meas - mu[:, None, :], (0, 2, 1))
+    return out
+
+
+def offsets_to_meas(off, mu, N) -> np.ndarray:
+    off = np.asarray(off, dtype=np.float64)
+    return np.transpose(off[:, :, :N], (0, 2, 1)) + _f64(mu)[:, None, :]
+
+
+def rows_to_particle_major(rows, N) -> np.ndarray:
+    """device rows [nF][d][Npad] -> [nF][N][d] Float64"""
+    return np.transpose(np.asarray(rows, dtype=np.float64)[:, :, :N], (0, 2, 1))
+
+
+def dequantized_particles(anchors, offsets, N, wrap_dim=None) -> np.ndarray:
+    """The exact Float64 values the kernels see: anchor + float32 offset, [nvars][N][d]."""
+    x = _f64(anchors)[:, None, :] + np.transpose(np.asarray(offsets, dtype=np.float64)[:, :, :N], (0, 2, 1))
+    return x

@@ -1,0 +1,373 @@
+"""GPU parity of every factor family through the C ABI against the float64 oracle, on random
+graphs (seeded), in parity mode (measurement supplied) and fused-sample mode.
+
+Tolerance (north_star: 1e-5 relative on residuals): |gpu - oracle| <= 1e-5 * max(|oracle|, 1e-3)
+per component, the oracle being evaluated in Float64 on the ORIGINAL Float64 inputs (before the
+anchored-float32 quantisation).  Headings/bearing residuals within 1e-6 of the +-pi branch cut are
+compared modulo 2 pi."""
+import numpy as np
+import pytest
+
+import rome_b200 as rb
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL, FLOOR = 1e-5, 1e-3
+
+
+def assert_close(gpu, ref, angle_cols=(), what=""):
+    gpu, ref = np.asarray(gpu, float), np.asarray(ref, float)
+    d = gpu - ref
+    for c in angle_cols:
+        d[..., c] = np.abs(O.np_wrap(d[..., c]))
+    tol = RTOL * np.maximum(np.abs(ref), FLOOR)
+    bad = np.abs(d) > tol
+    assert not bad.any(), f"{what}: {bad.sum()} of {bad.size} off; worst abs {np.abs(d).max():.3e}"
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = rb.Context(0)
+    yield c
+    c.close()
+
+
+def make_pose2_graph(rng, nvars, nF, N, spread=(0.1, 0.12, 0.02), extent=100.0):
+    mean = np.column_stack([rng.uniform(-extent, extent, nvars), rng.uniform(-extent, extent, nvars),
+                            rng.uniform(-np.pi, np.pi, nvars)])
+    poses = mean[:, None, :] + rng.normal(size=(nvars, N, 3)) * spread
+    ip = rng.integers(0, nvars, nF)
+    iq = (ip + rng.integers(1, nvars, nF)) % nvars
+    return poses, ip.astype(np.int32), iq.astype(np.int32)
+
+
+def rand_cov(rng, nF, d, scale):
+    A = rng.normal(size=(nF, d, d)) * 0.3 + np.eye(d)
+    S = A @ np.transpose(A, (0, 2, 1)) * (np.asarray(scale)[:, None] * np.asarray(scale)[None, :])
+    return S
+
+
+@pytest.mark.parametrize("N", [100, 37, 200])
+def test_pose2pose2_parity(ctx, N):
+    rng = np.random.default_rng(10 + N)
+    nvars, nF = 53, 211
+    poses, ip, iq = make_pose2_graph(rng, nvars, nF, N)
+    # measurement consistent with the graph so residuals are small (the hard case for relative error)
+    mu = np.stack([O.pose2pose2_bwd(np.zeros(3), np.zeros(3)) for _ in range(nF)])  # zeros
+    for f in range(nF):
+        p, q = poses[ip[f]].mean(0), poses[iq[f]].mean(0)
+        c, s = np.cos(p[2]), np.sin(p[2])
+        d = q[:2] - p[:2]
+        mu[f] = [c * d[0] + s * d[1], -s * d[0] + c * d[1], O.np_wrap(q[2] - p[2])]
+    cov = rand_cov(rng, nF, 3, [0.1, 0.1, 0.02])
+    meas = mu[:, None, :] + np.einsum("fij,fnj->fni", np.linalg.cholesky(cov), rng.normal(size=(nF, N, 3)))
+    ctx.set_particles(rb.POSE2, poses)
+    ctx.set_factors_pose2pose2(ip, iq, mu, cov)
+    flags = rb.RESIDUAL | rb.PROPOSAL_FWD | rb.PROPOSAL_BWD | rb.STATS | rb.JACOBIAN
+    out = ctx.alloc_host_outputs(rb.POSE2POSE2, flags)
+    ctx.eval_host(rb.POSE2POSE2, flags, meas=rb.meas_to_offsets(meas, mu), **out)
+    ref = O.sweep_pose2pose2(ip, iq, poses, meas)
+    res = rb.rows_to_particle_major(out["res"], N)
+    assert_close(res, ref, angle_cols=(2,), what="pose2pose2 residual")
+    assert np.abs(ref).max() < 2.0  # residuals are small: the comparison is a relative one
+    # proposals are roots of the residual
+    anchors = ctx.get_anchors(rb.POSE2)
+    fwd = rb.rows_to_particle_major(out["prop_fwd"], N) + anchors[iq][:, None, :]
+    bwd = rb.rows_to_particle_major(out["prop_bwd"], N) + anchors[ip][:, None, :]
+    r_f = O.np_pose2pose2(meas, poses[ip], fwd)
+    r_b = O.np_pose2pose2(meas, bwd, poses[iq])
+    assert np.abs(r_f).max() < 2e-5 and np.abs(r_b).max() < 2e-5, (np.abs(r_f).max(), np.abs(r_b).max())
+    # statistics
+    st = out["stats"]
+    assert np.allclose(st[:, 0:3], res.sum(1), rtol=1e-4, atol=1e-4)
+    rr = np.einsum("fni,fnj->fij", res, res)
+    assert np.allclose(st[:, 3:9], np.stack([rr[:, 0, 0], rr[:, 0, 1], rr[:, 0, 2], rr[:, 1, 1], rr[:, 1, 2],
+                                             rr[:, 2, 2]], 1), rtol=1e-4, atol=1e-4)
+    po = rb.rows_to_particle_major(out["prop_fwd"], N)
+    assert np.allclose(st[:, 9:11], po[:, :, :2].sum(1), rtol=1e-4, atol=1e-3)
+    assert np.allclose(st[:, 11], np.cos(po[:, :, 2]).sum(1), rtol=1e-4, atol=1e-3)
+    assert np.allclose(st[:, 12], np.sin(po[:, :, 2]).sum(1), rtol=1e-4, atol=1e-3)
+    # jacobian entries vs finite differences of the oracle
+    jac = rb.rows_to_particle_major(out["jac"], N)
+    h = 1e-6
+    pp = poses[ip].copy(); pp[..., 2] += h
+    pm = poses[ip].copy(); pm[..., 2] -= h
+    fd = (O.np_pose2pose2(meas, pp, poses[iq]) - O.np_pose2pose2(meas, pm, poses[iq])) / (2 * h)
+    assert np.allclose(jac[..., 0], fd[..., 0], atol=1e-4) and np.allclose(jac[..., 1], fd[..., 1], atol=1e-4)
+    assert np.allclose(jac[..., 2], np.cos(poses[ip][..., 2]), atol=1e-6)
+    assert np.allclose(jac[..., 3], np.sin(poses[ip][..., 2]), atol=1e-6)
+
+
+def test_priorpose2_parity(ctx):
+    rng = np.random.default_rng(3)
+    nvars, N = 40, 100
+    poses, _, _ = make_pose2_graph(rng, nvars, 1, N)
+    ip = np.arange(nvars, dtype=np.int32)
+    mu = poses.mean(1)
+    cov = rand_cov(rng, nvars, 3, [0.1, 0.1, 0.05])
+    meas = mu[:, None, :] + np.einsum("fij,fnj->fni", np.linalg.cholesky(cov), rng.normal(size=(nvars, N, 3)))
+    ctx.set_particles(rb.POSE2, poses)
+    ctx.set_factors_priorpose2(ip, mu, cov)
+    flags = rb.RESIDUAL | rb.PROPOSAL_FWD | rb.STATS
+    out = ctx.alloc_host_outputs(rb.PRIORPOSE2, flags)
+    ctx.eval_host(rb.PRIORPOSE2, flags, meas=rb.meas_to_offsets(meas, mu), **out)
+    ref = O.sweep_priorpose2(ip, poses, meas)
+    assert_close(rb.rows_to_particle_major(out["res"], N), ref, angle_cols=(2,), what="priorpose2 residual")
+    prop = rb.rows_to_particle_major(out["prop_fwd"], N) + ctx.get_anchors(rb.POSE2)[ip][:, None, :]
+    d = prop - meas
+    d[..., 2] = O.np_wrap(d[..., 2])
+    assert np.abs(d).max() < 1e-5
+
+
+def test_bearingrange_parity(ctx):
+    rng = np.random.default_rng(4)
+    nvars, nl, nF, N = 60, 17, 150, 200
+    poses, _, _ = make_pose2_graph(rng, nvars, 1, N)
+    lm_mean = rng.uniform(-100, 100, (nl, 2))
+    points = lm_mean[:, None, :] + rng.normal(size=(nl, N, 2)) * 0.3
+    ip = rng.integers(0, nvars, nF).astype(np.int32)
+    il = rng.integers(0, nl, nF).astype(np.int32)
+    pm, lmn = poses.mean(1)[ip], lm_mean[il]
+    d = lmn - pm[:, :2]
+    mu_b = O.np_wrap(np.arctan2(d[:, 1], d[:, 0]) - pm[:, 2])
+    mu_r = np.hypot(d[:, 0], d[:, 1])
+    bearing = np.column_stack([mu_b, np.full(nF, 0.03)])
+    rng_ = np.column_stack([mu_r, np.full(nF, 0.5)])
+    meas = np.stack([mu_b[:, None] + 0.03 * rng.normal(size=(nF, N)), mu_r[:, None] + 0.5 * rng.normal(size=(nF, N))], -1)
+    ctx.set_particles(rb.POSE2, poses)
+    ctx.set_particles(rb.POINT2, points)
+    ctx.set_factors_bearingrange(ip, il, bearing, rng_)
+    flags = rb.RESIDUAL | rb.PROPOSAL_FWD | rb.STATS | rb.JACOBIAN
+    out = ctx.alloc_host_outputs(rb.BEARINGRANGE, flags)
+    ctx.eval_host(rb.BEARINGRANGE, flags, meas=rb.meas_to_offsets(meas, np.column_stack([mu_b, mu_r])), **out)
+    ref = O.sweep_bearingrange(ip, il, poses, points, meas)
+    assert_close(rb.rows_to_particle_major(out["res"], N), ref, angle_cols=(0,), what="bearingrange residual")
+    prop = rb.rows_to_particle_major(out["prop_fwd"], N) + ctx.get_anchors(rb.POINT2)[il][:, None, :]
+    r_f = O.np_bearingrange(meas, poses[ip], prop)
+    assert np.abs(r_f).max() < 2e-5
+    jac = rb.rows_to_particle_major(out["jac"], N)
+    h = 1e-6
+    for k in range(2):
+        lp = points[il].copy(); lp[..., k] += h
+        lm = points[il].copy(); lm[..., k] -= h
+        fd = (O.np_bearingrange(meas, poses[ip], lp) - O.np_bearingrange(meas, poses[ip], lm)) / (2 * h)
+        assert np.allclose(jac[..., k], fd[..., 0], atol=1e-5)
+        assert np.allclose(jac[..., 2 + k], fd[..., 1], atol=1e-5)
+
+
+def make_pose3(rng, nvars, N):
+    mean = np.column_stack([rng.uniform(-50, 50, (nvars, 3)), rng.normal(size=(nvars, 3)) * 0.9])
+    return mean[:, None, :] + rng.normal(size=(nvars, N, 6)) * [0.1, 0.1, 0.1, 0.02, 0.02, 0.02]
+
+
+def rot_close(w_gpu, w_ref, tol):
+    """compare rotation vectors as rotations"""
+    d = O.np_so3_log(np.swapaxes(O.np_so3_exp(w_ref), -1, -2) @ O.np_so3_exp(w_gpu))
+    return np.abs(d).max() < tol
+
+
+@pytest.mark.parametrize("N", [100, 64])
+def test_pose3pose3_parity(ctx, N):
+    rng = np.random.default_rng(5)
+    nvars, nF = 31, 97
+    poses = make_pose3(rng, nvars, N)
+    ip = rng.integers(0, nvars, nF).astype(np.int32)
+    iq = ((ip + rng.integers(1, nvars, nF)) % nvars).astype(np.int32)
+    mu = np.stack([O.pose3pose3(np.zeros(6), poses[iq[f]].mean(0) * 0, np.zeros(6)) for f in range(nF)])
+    for f in range(nF):  # mean measurement = relative pose of the variable means (so residuals are small)
+        p, q = poses[ip[f], 0], poses[iq[f], 0]
+        Rp, Rq = O.so3_exp(p[3:]), O.so3_exp(q[3:])
+        mu[f, :3] = Rp.T @ (q[:3] - p[:3])
+        mu[f, 3:] = O.so3_log(Rp.T @ Rq)
+    cov = rand_cov(rng, nF, 6, [0.1, 0.1, 0.1, 0.01, 0.01, 0.01])
+    meas = mu[:, None, :] + np.einsum("fij,fnj->fni", np.linalg.cholesky(cov), rng.normal(size=(nF, N, 6)))
+    ctx.set_particles(rb.POSE3, poses)
+    ctx.set_factors_pose3pose3(ip, iq, mu, cov)
+    flags = rb.RESIDUAL | rb.PROPOSAL_FWD | rb.PROPOSAL_BWD | rb.STATS
+    out = ctx.alloc_host_outputs(rb.POSE3POSE3, flags)
+    ctx.eval_host(rb.POSE3POSE3, flags, meas=rb.meas_to_offsets(meas, mu), **out)
+    ref = O.sweep_pose3pose3(ip, iq, poses, meas)
+    res = rb.rows_to_particle_major(out["res"], N)
+    assert_close(res, ref, what="pose3pose3 residual")
+    anchors = ctx.get_anchors(rb.POSE3)
+    fwd = rb.rows_to_particle_major(out["prop_fwd"], N) + anchors[iq][:, None, :]
+    bwd = rb.rows_to_particle_major(out["prop_bwd"], N) + anchors[ip][:, None, :]
+    assert np.abs(O.np_pose3pose3(meas, poses[ip], fwd)).max() < 5e-5
+    assert np.abs(O.np_pose3pose3(meas, bwd, poses[iq])).max() < 5e-5
+    st = out["stats"]
+    assert np.allclose(st[:, :6], res.sum(1), rtol=1e-4, atol=1e-4)
+    assert np.allclose(st[:, 31], (res ** 2).sum((1, 2)), rtol=1e-4, atol=1e-4)
+
+
+def test_priorpose3_parity(ctx):
+    rng = np.random.default_rng(6)
+    nvars, N = 20, 100
+    poses = make_pose3(rng, nvars, N)
+    ip = np.arange(nvars, dtype=np.int32)
+    mu = poses[:, 0, :].copy()
+    cov = rand_cov(rng, nvars, 6, [0.1, 0.1, 0.1, 0.01, 0.01, 0.01])
+    meas = mu[:, None, :] + np.einsum("fij,fnj->fni", np.linalg.cholesky(cov), rng.normal(size=(nvars, N, 6)))
+    ctx.set_particles(rb.POSE3, poses)
+    ctx.set_factors_priorpose3(ip, mu, cov)
+    flags = rb.RESIDUAL | rb.PROPOSAL_FWD | rb.STATS
+    out = ctx.alloc_host_outputs(rb.PRIORPOSE3, flags)
+    ctx.eval_host(rb.PRIORPOSE3, flags, meas=rb.meas_to_offsets(meas, mu), **out)
+    ref = O.sweep_priorpose3(ip, poses, meas)
+    assert_close(rb.rows_to_particle_major(out["res"], N), ref, what="priorpose3 residual")
+    prop = rb.rows_to_particle_major(out["prop_fwd"], N) + ctx.get_anchors(rb.POSE3)[ip][:, None, :]
+    assert np.abs(prop - meas).max() < 1e-5
+
+
+def test_particle_roundtrip(ctx):
+    rng = np.random.default_rng(7)
+    poses, _, _ = make_pose2_graph(rng, 25, 1, 100)
+    poses[..., 2] = O.np_wrap(poses[..., 2])
+    ctx.set_particles(rb.POSE2, poses)
+    back = ctx.get_particles(rb.POSE2)
+    d = back - poses
+    d[..., 2] = O.np_wrap(d[..., 2])
+    assert np.abs(d).max() < 1e-6
+    p3 = make_pose3(rng, 9, 100)
+    ctx.set_particles(rb.POSE3, p3)
+    assert np.abs(ctx.get_particles(rb.POSE3) - p3).max() < 1e-6
+
+
+@pytest.mark.parametrize("family", ["pose2pose2", "priorpose2", "bearingrange", "pose3pose3", "priorpose3"])
+def test_fused_sampling_matches_supplied_and_host_twin(ctx, family):
+    """SAMPLE|WRITE_MEAS: (1) residuals are bit-identical to a second call that is handed the written
+    samples; (2) the samples reproduce the host Philox/Box-Muller twin; (3) moments match (mu, Sigma)."""
+    rng = np.random.default_rng(8)
+    N, seed, sid = 100, 0x1234567811, 3
+    if family in ("pose2pose2", "priorpose2", "bearingrange"):
+        poses, ip, iq = make_pose2_graph(rng, 30, 64, N)
+        ctx.set_particles(rb.POSE2, poses)
+    if family == "pose2pose2":
+        fam, d = rb.POSE2POSE2, 3
+        mu = rng.normal(size=(64, 3)) * [5, 5, 1]
+        cov = rand_cov(rng, 64, 3, [0.1, 0.2, 0.05])
+        ctx.set_factors_pose2pose2(ip, iq, mu, cov)
+        Lc = np.linalg.cholesky(cov)
+    elif family == "priorpose2":
+        fam, d = rb.PRIORPOSE2, 3
+        mu = rng.normal(size=(64, 3)) * [5, 5, 1]
+        cov = rand_cov(rng, 64, 3, [0.1, 0.2, 0.05])
+        ctx.set_factors_priorpose2(ip, mu, cov)
+        Lc = np.linalg.cholesky(cov)
+    elif family == "bearingrange":
+        fam, d = rb.BEARINGRANGE, 2
+        points = rng.uniform(-50, 50, (8, 1, 2)) + rng.normal(size=(8, N, 2)) * 0.2
+        ctx.set_particles(rb.POINT2, points)
+        il = rng.integers(0, 8, 64).astype(np.int32)
+        mu = np.column_stack([rng.uniform(-3, 3, 64), rng.uniform(5, 30, 64)])
+        sig = np.column_stack([rng.uniform(0.01, 0.1, 64), rng.uniform(0.1, 1, 64)])
+        ctx.set_factors_bearingrange(ip, il, np.column_stack([mu[:, 0], sig[:, 0]]), np.column_stack([mu[:, 1], sig[:, 1]]))
+        Lc = np.stack([np.diag(s) for s in sig])
+    else:
+        poses = make_pose3(rng, 30, N)
+        ctx.set_particles(rb.POSE3, poses)
+        ip = rng.integers(0, 30, 64).astype(np.int32)
+        iq = ((ip + 1) % 30).astype(np.int32)
+        d = 6
+        mu = rng.normal(size=(64, 6)) * [1, 1, 1, .2, .2, .2]
+        cov = rand_cov(rng, 64, 6, [0.1, 0.1, 0.1, 0.01, 0.01, 0.01])
+        Lc = np.linalg.cholesky(cov)
+        if family == "pose3pose3":
+            fam = rb.POSE3POSE3
+            ctx.set_factors_pose3pose3(ip, iq, mu, cov)
+        else:
+            fam = rb.PRIORPOSE3
+            ctx.set_factors_priorpose3(ip, mu, cov)
+    flags = rb.RESIDUAL | rb.SAMPLE | rb.WRITE_MEAS
+    out = ctx.alloc_host_outputs(fam, flags)
+    ctx.eval_host(fam, flags, seed=seed, stream_id=sid, **out)
+    out2 = ctx.alloc_host_outputs(fam, rb.RESIDUAL)
+    ctx.eval_host(fam, rb.RESIDUAL, meas=out["meas_out"], **out2)
+    assert np.array_equal(out["res"][:, :, :N], out2["res"][:, :, :N])
+    delta = rb.rows_to_particle_major(out["meas_out"], N)  # [nF][N][d] offsets from mu
+    # host twin for a few (factor, particle) pairs
+    for f in (0, 7, 63):
+        for n in (0, 1, 50, 99):
+            z = np.concatenate([O.normal4(seed, sid, f, n, 0), O.normal4(seed, sid, f, n, 1)])[:d]
+            want = Lc[f].astype(np.float32).astype(np.float64) @ z
+            assert np.allclose(delta[f, n], want, rtol=2e-5, atol=2e-6), (f, n, delta[f, n], want)
+    # moments: whiten and check identity covariance / zero mean over all factors x particles
+    zw = np.linalg.solve(Lc, np.transpose(delta, (0, 2, 1)))  # [nF][d][N]
+    zs = np.transpose(zw, (1, 0, 2)).reshape(d, -1)
+    assert np.abs(zs.mean(1)).max() < 0.05
+    assert np.abs(np.cov(zs) - np.eye(d)).max() < 0.06
+    # a different stream id gives different draws
+    out3 = ctx.alloc_host_outputs(fam, flags)
+    ctx.eval_host(fam, flags, seed=seed, stream_id=sid + 1, **out3)
+    assert not np.array_equal(out3["meas_out"], out["meas_out"])
+
+
+def test_device_pointer_path_and_graph(ctx):
+    """eval() with device buffers (torch tensors) == eval_host(); factor sub-ranges write disjoint slices;
+    a captured CUDA graph replays the same result."""
+    import torch
+    rng = np.random.default_rng(9)
+    N, nF = 100, 1000
+    poses, ip, iq = make_pose2_graph(rng, 200, nF, N)
+    mu = rng.normal(size=(nF, 3))
+    cov = rand_cov(rng, nF, 3, [0.1, 0.1, 0.02])
+    ctx.set_particles(rb.POSE2, poses)
+    ctx.set_factors_pose2pose2(ip, iq, mu, cov)
+    Np = rb.npad(N)
+    moff = rb.meas_to_offsets(mu[:, None, :] + rng.normal(size=(nF, N, 3)) * 0.1, mu)
+    out = ctx.alloc_host_outputs(rb.POSE2POSE2, rb.RESIDUAL | rb.STATS)
+    ctx.eval_host(rb.POSE2POSE2, rb.RESIDUAL | rb.STATS, meas=moff, **out)
+    ctx.use_torch_stream()
+    try:
+        dm = torch.from_numpy(moff).cuda()
+        res = torch.zeros((nF, 3, Np), device="cuda")
+        st = torch.zeros((nF, 16), device="cuda")
+        ctx.eval(rb.POSE2POSE2, rb.RESIDUAL | rb.STATS, first=0, count=300, meas=dm, res=res, stats=st)
+        ctx.eval(rb.POSE2POSE2, rb.RESIDUAL | rb.STATS, first=300, count=-1, meas=dm, res=res, stats=st)
+        torch.cuda.synchronize()
+        assert np.array_equal(res.cpu().numpy(), out["res"])
+        assert np.array_equal(st.cpu().numpy(), out["stats"])
+        res.zero_()
+        torch.cuda.synchronize()
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            ctx.use_torch_stream()
+            ctx.graph_begin()
+            ctx.eval(rb.POSE2POSE2, rb.RESIDUAL | rb.STATS, meas=dm, res=res, stats=st)
+            g = ctx.graph_end()
+            before = ctx.launch_count
+            ctx.graph_launch(g)
+            s.synchronize()
+            assert ctx.launch_count == before + 1
+        assert np.array_equal(res.cpu().numpy(), out["res"])
+    finally:
+        ctx.set_stream(None)
+
+
+def test_error_behaviour(ctx):
+    with pytest.raises(rb.RomeB200Error):
+        ctx.set_factors_pose2pose2([0], [1], [[0, 0, 0]], [np.zeros((3, 3))])  # not positive definite
+    c2 = rb.Context(0)
+    try:
+        with pytest.raises(rb.RomeB200Error) as ei:
+            c2.eval_host(rb.POSE2POSE2, rb.RESIDUAL, meas=np.zeros(1, np.float32), res=np.zeros(1, np.float32))
+        assert ei.value.code == -4  # NOT_SET
+        c2.set_particles(rb.POSE2, np.zeros((2, 10, 3)))
+        c2.set_factors_pose2pose2([0], [5], [[0, 0, 0]], [np.eye(3)])
+        with pytest.raises(rb.RomeB200Error) as ei:
+            c2.eval_host(rb.POSE2POSE2, rb.RESIDUAL, meas=np.zeros(3 * 16, np.float32), res=np.zeros(3 * 16, np.float32))
+        assert ei.value.code == -3  # SHAPE_MISMATCH: variable index beyond the store
+        with pytest.raises(rb.RomeB200Error):
+            c2.eval_host(rb.PRIORPOSE2, rb.PROPOSAL_BWD, prop_bwd=np.zeros(1, np.float32))
+    finally:
+        c2.close()
+
+
+def test_nan_propagates(ctx):
+    poses = np.zeros((2, 16, 3))
+    poses[1, 3, 0] = np.nan
+    ctx.set_particles(rb.POSE2, poses)
+    ctx.set_factors_pose2pose2([0], [1], [[1, 0, 0]], [np.eye(3) * 0.01])
+    out = ctx.alloc_host_outputs(rb.POSE2POSE2, rb.RESIDUAL)
+    ctx.eval_host(rb.POSE2POSE2, rb.RESIDUAL, meas=np.zeros((1, 3, 16), np.float32), **out)
+    assert np.isnan(out["res"][0, 0, 3]) and np.isfinite(out["res"][0, 0, 2])
