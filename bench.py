@@ -1,0 +1,441 @@
+#!/usr/bin/env python
+"""bench.py -- factor-particle residual evals/s of the RoME hot path on B200.
+
+Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON line.
+
+Workload (config.workload = "manhattan_shaped_10k_se2_N100"): the configuration BASELINE.json's target is
+quoted on -- a synthetic Manhattan-world SE(2) graph of 10 000 Pose2 x N=100 particles with 9 999 odometry +
+2 000 loop-closure Pose2Pose2 factors and one PriorPose2 (rome_b200.generateGraph_ManhattanShaped, seed 2;
+particles = simulated truth + sigma (0.1, 0.12, 0.02), seed 1).
+A STEP is one pass of the hot path over the whole graph: for every factor x every particle, getSample
+(in-kernel Philox) + residual + per-factor statistics -- one launch of the fused Pose2Pose2 kernel and one of
+the PriorPose2 kernel.  With --gpus N > 1 the graph is replicated N times (weak scaling: one 10k-pose graph's
+factors per rank, particles of all N graphs resident on every GPU), each rank also writes the closed-form
+proposals of its factors and one NCCL all-gather per step exchanges them.
+
+Timing: W warm-up steps, then EXACTLY K steps inside one CUDA-event pair on the launch stream, bracketed by a
+barrier + torch.cuda.synchronize(); max over ranks.  L2: the K steps rotate through `sets` independent copies
+of the whole working set (particles + tables + outputs; > 2x the 126 MB L2), so no step finds its inputs in L2.
+The K steps are replayed from one CUDA graph (launch latency is otherwise comparable to the 10-20 us kernel).
+
+`e2e`: the same metric through the public host API with HOST buffers every step: pinned Float64 particles in
+the reference layout -> rome_b200_set_particles (H2D + layout kernel) -> rome_b200_eval_host (kernels + D2H of
+residuals and statistics).
+`cpu_baseline` / `--impl reference`: the float64 C restatement (oracle/) of the same residual sweep on the
+host cores (kind "port": the Julia reference cannot run in this image).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "factor_particle_residual_evals_per_sec"
+UNIT = "evals/s"
+WORKLOAD = "manhattan_shaped_10k_se2_N100"
+NPOSES, NPART = 10000, 100
+
+
+# --------------------------------------------------------------------------------------------------------
+def build_workload(copies=1):
+    """arrays of `copies` independent 10k-pose graphs with globally numbered variables"""
+    import rome_b200 as rb
+    fg = rb.generateGraph_ManhattanShaped(NPOSES, seed=2, N=NPART)
+    rb.seed_particles(fg, seed=1)
+    idx = {l: v.index for l, v in fg.variables.items()}
+    p2 = [f for f in fg.factors.values() if isinstance(f.fnc, rb.Pose2Pose2)]
+    pr = [f for f in fg.factors.values() if isinstance(f.fnc, rb.PriorPose2)]
+    base = dict(
+        poses=np.stack([v.val for v in fg.variables.values()]),
+        ip=np.array([idx[f.variableOrderSymbols[0]] for f in p2], np.int32),
+        iq=np.array([idx[f.variableOrderSymbols[1]] for f in p2], np.int32),
+        mu=np.stack([f.fnc.Z.mu for f in p2]), cov=np.stack([f.fnc.Z.Sigma for f in p2]),
+        pr_ip=np.array([idx[f.variableOrderSymbols[0]] for f in pr], np.int32),
+        pr_mu=np.stack([f.fnc.Z.mu for f in pr]), pr_cov=np.stack([f.fnc.Z.Sigma for f in pr]))
+    if copies == 1:
+        return base
+    rng = np.random.default_rng(11)
+    V = base["poses"].shape[0]
+    out = {k: [] for k in base}
+    for c in range(copies):
+        out["poses"].append(base["poses"] + (rng.normal(size=base["poses"].shape) * 1e-3 if c else 0.0))
+        for k in ("ip", "iq", "pr_ip"):
+            out[k].append(base[k] + c * V)
+        for k in ("mu", "cov", "pr_mu", "pr_cov"):
+            out[k].append(base[k])
+    return {k: np.concatenate(v) for k, v in out.items()}
+
+
+class ClockSampler:
+    """samples SM clock / throttle reasons through NVML while the timed region runs"""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _once(self):
+        nv = self.nv
+        self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+                 0x80: "hw_power_brake_slowdown"}
+        for bit, n in names.items():
+            if r & bit:
+                self.reasons.add(n)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self._once()
+            except Exception:
+                return
+            time.sleep(0.0005)
+
+    def start(self):
+        if self.nv:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        if self._t:
+            self._stop.set()
+            self._t.join()
+            self._t = None
+            self._stop = threading.Event()
+
+    def summary(self, window):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0, "window": window}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples), "window": window}
+
+
+# --------------------------------------------------------------------------------------------------------
+def cpu_sweep_rate(w, seconds=12.0, nthreads=0):
+    """bare residual sweep of the oracle port over the workload's Pose2Pose2 + PriorPose2 factors"""
+    from oracle import oracle as O
+    rng = np.random.default_rng(5)
+    F, N = len(w["ip"]), w["poses"].shape[1]
+    L = np.linalg.cholesky(w["cov"])
+    meas = w["mu"][:, None, :] + np.einsum("fij,fnj->fni", L, rng.normal(size=(F, N, 3)))
+    pm = w["pr_mu"][:, None, :] + rng.normal(size=(len(w["pr_ip"]), N, 3)) * 0.1
+    O.sweep_pose2pose2(w["ip"], w["iq"], w["poses"], meas, nthreads)  # warm-up
+    lib, C = O.lib(), O.C
+    ip, iq, poses, meas = O._i32(w["ip"]), O._i32(w["iq"]), O._f64(w["poses"]), O._f64(meas)
+    pip, pm = O._i32(w["pr_ip"]), O._f64(pm)
+    res = np.empty((F, N, 3))
+    pres = np.empty((len(pip), N, 3))
+    reps, t0, nt = 0, time.perf_counter(), 1
+    while True:
+        nt = lib.rome_oracle_sweep_pose2pose2(F, N, O._ip(ip), O._ip(iq), O._dp(poses), O._dp(meas), O._dp(res), nthreads)
+        lib.rome_oracle_sweep_priorpose2(len(pip), N, O._ip(pip), O._dp(poses), O._dp(pm), O._dp(pres), nthreads)
+        reps += 1
+        dt = time.perf_counter() - t0
+        if dt >= seconds:
+            break
+    evals = reps * (F + len(pip)) * N
+    return evals / dt, nt, reps, dt
+
+
+def cpu_reference_shaped(w, nfac=96, nthreads=0):
+    """Nelder-Mead per particle x inflateCycles (IIF-shaped convolution) on the first `nfac` factors"""
+    from oracle import oracle as O
+    rng = np.random.default_rng(6)
+    N = w["poses"].shape[1]
+    L = np.linalg.cholesky(w["cov"][:nfac])
+    meas = w["mu"][:nfac, None, :] + np.einsum("fij,fnj->fni", L, rng.normal(size=(nfac, N, 3)))
+    t0 = time.perf_counter()
+    _, nev, nt = O.conv_nm_pose2pose2(w["ip"][:nfac], w["iq"][:nfac], w["poses"], meas, fwd=True, inflate_cycles=3,
+                                      inflation=5.0, seed=1, nthreads=nthreads)
+    dt = time.perf_counter() - t0
+    return dict(residual_evals_per_s=nev / dt, convolved_particles_per_s=nfac * N / dt, residual_calls_per_particle=nev / (nfac * N),
+                cores=nt, sample=f"{nfac} Pose2Pose2 factors x {N} particles, NelderMead x 3 inflation cycles")
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port) on this box's host cores"""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    O.build()
+    w = build_workload(1)
+    F, N = len(w["ip"]) + len(w["pr_ip"]), w["poses"].shape[1]
+    rng = np.random.default_rng(5)
+    L = np.linalg.cholesky(w["cov"])
+    meas = w["mu"][:, None, :] + np.einsum("fij,fnj->fni", L, rng.normal(size=(len(w["ip"]), N, 3)))
+    pm = w["pr_mu"][:, None, :] + rng.normal(size=(len(w["pr_ip"]), N, 3)) * 0.1
+
+    def step():
+        O.sweep_pose2pose2(w["ip"], w["iq"], w["poses"], meas, 0)
+        O.sweep_priorpose2(w["pr_ip"], w["poses"], pm, 0)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = args.steps * F * N / dt
+    nt = O.lib().rome_oracle_sweep_priorpose2(0, N, None, None, None, None, 0)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "poses": NPOSES, "particles": N, "factors": F,
+                       "step": "one bare residual sweep over all factors x particles (no optimiser, no sampling)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": nt, "kind": "port",
+                             "sample": f"{args.steps} full sweeps of {F} factors x {N} particles"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "Julia reference cannot run here (no julia, unvendored deps); this is the float64 C restatement"}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=600)
+    ap.add_argument("--warmup", type=int, default=60)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--sets", type=int, default=12, help="independent working-set copies rotated through (L2 defeat)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=20)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import rome_b200 as rb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: librome_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    G = world
+    w = build_workload(G)
+    F0 = len(w["ip"]) // G  # Pose2Pose2 factors per graph copy == per rank
+    F, N, Np, V = len(w["ip"]), NPART, rb.npad(NPART), w["poses"].shape[0]
+    first = rank * F0
+    multi = G > 1
+    flags = rb.SAMPLE | rb.RESIDUAL | rb.STATS | (rb.PROPOSAL_FWD if multi else 0)
+    stream = torch.cuda.Stream()
+    S = args.sets
+    sets = []
+    with torch.cuda.stream(stream):
+        for s in range(S):
+            c = rb.Context(local)
+            c.use_torch_stream()
+            c.set_particles(rb.POSE2, w["poses"] + (1e-4 * s))
+            c.set_factors_pose2pose2(w["ip"], w["iq"], w["mu"], w["cov"])
+            c.set_factors_priorpose2(w["pr_ip"], w["pr_mu"], w["pr_cov"])
+            bufs = dict(res=torch.zeros((F, 3, Np), device="cuda"), stats=torch.zeros((F, 16), device="cuda"))
+            if multi:
+                bufs["prop_fwd"] = torch.zeros((F, 3, Np), device="cuda")
+            pb = dict(res=torch.zeros((len(w["pr_ip"]), 3, Np), device="cuda"),
+                      stats=torch.zeros((len(w["pr_ip"]), 16), device="cuda"))
+            if multi:
+                pb["prop_fwd"] = torch.zeros((len(w["pr_ip"]), 3, Np), device="cuda")
+            sets.append((c, bufs, pb))
+        stream.synchronize()
+
+    n_prior = len(w["pr_ip"]) // G
+    evals_per_step_rank = (F0 + n_prior) * N
+    evals_per_step = evals_per_step_rank * G
+
+    def step(k):
+        c, bufs, pb = sets[k % S]
+        c.eval(rb.POSE2POSE2, flags, seed=7, stream_id=k, first=first, count=F0, **bufs)
+        c.eval(rb.PRIORPOSE2, flags, seed=7, stream_id=k, first=rank * n_prior, count=n_prior, **pb)
+        if multi:  # the one exchange of the path: proposals of every rank's factors to every rank
+            dist.all_gather_into_tensor(bufs["prop_fwd"], bufs["prop_fwd"][first:first + F0])
+
+    clocks = ClockSampler(local)
+    with torch.cuda.stream(stream):
+        for k in range(args.warmup):
+            step(k)
+        stream.synchronize()
+        # capture the K timed steps into one CUDA graph
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=stream):
+            for c, _, _ in sets:
+                c.use_torch_stream()
+            for k in range(args.steps):
+                step(args.warmup + k)
+        for c, _, _ in sets:
+            c.use_torch_stream()
+        g.replay()  # untimed replay: graph upload + warm instruction caches
+        stream.synchronize()
+        if multi:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        clocks.start()
+        e0.record(stream)
+        g.replay()
+        e1.record(stream)
+        stream.synchronize()
+        clocks.stop()
+        if multi:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        window = "timed"
+        if len(clocks.samples) < 5:  # timed region too short to sample: keep sampling under identical replays
+            clocks.start()
+            t_end = time.perf_counter() + 0.3
+            while time.perf_counter() < t_end:
+                g.replay()
+                stream.synchronize()
+            clocks.stop()
+            window = "timed+identical replays"
+        # dominant kernel alone (Pose2Pose2 fused kernel): live CUDA-event timing over K launches
+        gk = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gk, stream=stream):
+            for k in range(args.steps):
+                c, bufs, _ = sets[k % S]
+                c.eval(rb.POSE2POSE2, flags, seed=7, stream_id=k, first=first, count=F0, **bufs)
+        for c, _, _ in sets:
+            c.use_torch_stream()
+        gk.replay()
+        stream.synchronize()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record(stream)
+        gk.replay()
+        k1.record(stream)
+        stream.synchronize()
+        kms = k0.elapsed_time(k1) / args.steps
+        # same kernel with the measurement supplied from HBM (parity mode, 48 B/eval)
+        pflags = rb.RESIDUAL | rb.STATS
+        meas_sets = [torch.randn((F, 3, Np), device="cuda") * 0.05 for _ in range(S)]
+        gp = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gp, stream=stream):
+            for k in range(args.steps):
+                c, bufs, _ = sets[k % S]
+                c.eval(rb.POSE2POSE2, pflags, first=first, count=F0, meas=meas_sets[k % S], res=bufs["res"],
+                       stats=bufs["stats"])
+        for c, _, _ in sets:
+            c.use_torch_stream()
+        gp.replay()
+        stream.synchronize()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record(stream)
+        gp.replay()
+        p1.record(stream)
+        stream.synchronize()
+        pms = p0.elapsed_time(p1) / args.steps
+        del meas_sets
+
+    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    if multi:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = evals_per_step * args.steps / (ms * 1e-3)
+
+    # ---- e2e through the host API (per rank, host buffers, copies inside the timed region) ----
+    c, _, _ = sets[0]
+    c.set_stream(None)
+    host_poses = torch.from_numpy(w["poses"]).pin_memory()
+    hres = torch.zeros((F, 3, Np), dtype=torch.float32).pin_memory()
+    hstats = torch.zeros((F, 16), dtype=torch.float32).pin_memory()
+    hpres = torch.zeros((len(w["pr_ip"]), 3, Np), dtype=torch.float32).pin_memory()
+    hpstats = torch.zeros((len(w["pr_ip"]), 16), dtype=torch.float32).pin_memory()
+    eflags = rb.SAMPLE | rb.RESIDUAL | rb.STATS
+
+    def e2e_step(k):
+        c.set_particles(rb.POSE2, host_poses)
+        c.eval_host(rb.POSE2POSE2, eflags, seed=9, stream_id=k, first=first, count=F0, res=hres, stats=hstats)
+        c.eval_host(rb.PRIORPOSE2, eflags, seed=9, stream_id=k, first=rank * n_prior, count=n_prior, res=hpres,
+                    stats=hpstats)
+
+    for k in range(3):
+        e2e_step(k)
+    if multi:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for k in range(args.e2e_steps):
+        e2e_step(k)
+    torch.cuda.synchronize()
+    edt = time.perf_counter() - t0
+    et = torch.tensor([edt], device="cuda", dtype=torch.float64)
+    if multi:
+        dist.all_reduce(et, op=dist.ReduceOp.MAX)
+    edt = float(et.item())
+    e2e_value = evals_per_step * args.e2e_steps / edt
+    h2d = V * N * 3 * 8
+    d2h = (F0 * 3 * Np + F0 * 16 + n_prior * 3 * Np + n_prior * 16) * 4
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        bpe = rb.BYTES_PER_EVAL_SAMPLED[rb.POSE2POSE2] + (12 if multi else 0)
+        ach = F0 * N * bpe / (kms * 1e-3) / 1e9
+        pach = F0 * N * rb.BYTES_PER_EVAL[rb.POSE2POSE2] / (pms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": G, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "poses_per_gpu": NPOSES, "particles": N, "npad": Np,
+                       "factors_per_gpu": F0 + n_prior, "evals_per_step": evals_per_step,
+                       "step": "getSample (in-kernel Philox) + residual + per-factor stats for every factor x particle"
+                               + ("; + closed-form proposals and one NCCL all-gather of them" if multi else ""),
+                       "storage": "anchored float32 (Float64 anchor + float32 offset)",
+                       "l2": f"{S} rotating working-set copies (> 2x L2); K steps replayed from one CUDA graph",
+                       "parallelism": f"factor-list sharding x{G}" if multi else "single GPU"},
+            "roofline": {"bound": "hbm", "kernel": "eval_kernel<FamPose2Pose2, sample=true>", "achieved": ach, "peak": peak,
+                         "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
+                         "bytes_per_eval": bpe, "evals_per_launch": F0 * N, "us_per_launch": kms * 1e3},
+            "roofline_supplied_meas": {"kernel": "eval_kernel<FamPose2Pose2, sample=false>", "achieved": pach, "peak": peak,
+                                       "unit": "GB/s", "frac": pach / peak, "bytes_per_eval": rb.BYTES_PER_EVAL[rb.POSE2POSE2],
+                                       "us_per_launch": pms * 1e3, "evals_per_s": F0 * N / (pms * 1e-3)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * edt / args.e2e_steps, "steps": args.e2e_steps,
+                    "api": "rome_b200_set_particles(host f64) + rome_b200_eval_host(host f32 outputs)"},
+            "gpu_launches": 2 * args.steps,
+            "clocks": clocks.summary(window),
+        }
+        if not args.no_cpu and G == 1:
+            from oracle import oracle as O
+            O.build()
+            v, nt, reps, dt = cpu_sweep_rate(w, args.cpu_seconds)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": nt, "kind": "port",
+                                    "sample": f"{reps} full residual sweeps ({F0 + n_prior} factors x {N} particles) in {dt:.1f} s"}
+            line["cpu_reference_shaped"] = cpu_reference_shaped(w)
+        print(json.dumps(line))
+    if multi:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -114,7 +114,8 @@ ROME_B200_API int rome_b200_npad(int N);
 
 /* ---- variables: replaces the per-variable `Vector{ArrayPartition}` particle storage -------- */
 /* Upload Float64 coordinates [nvars][N][d] (host); converts on device to anchored float32 SoA.
- * anchor of a variable = its first particle.  N must be equal for all vartypes of one ctx. */
+ * anchor of a variable = its first particle.  The variable types a factor family touches must
+ * hold the same N when that family is evaluated (checked by rome_b200_eval). */
 ROME_B200_API int rome_b200_set_particles(rome_b200_ctx* ctx, int vartype, int nvars, int N, const double* coords_host);
 ROME_B200_API int rome_b200_get_particles(rome_b200_ctx* ctx, int vartype, double* coords_host);
 /* Device views (zero-copy interop): offsets [nvars][d][Npad], anchors [nvars][d]. */

@@ -9,4 +9,14 @@ from ._lib import (BEARINGRANGE, JACOBIAN, POINT2, POSE2, POSE2POSE2, POSE3, POS
 from .engine import (BYTES_PER_EVAL, BYTES_PER_EVAL_SAMPLED, FAMILY, VAR_DIM, Context, dequantized_particles,
                      meas_to_offsets, npad, offsets_to_meas, rows_to_particle_major)
 
+from .factors import (MvNormal, Normal, Point2, Pose2, Pose2Point2BearingRange, Pose2Pose2, Pose3, Pose3Pose3,
+                      PriorPose2, PriorPose3, getManifold, getMeasurementParametric, pack, unpack)
+from .graph import (DeviceGraph, FactorGraph, SolverParams, addFactor, addVariable, approxConv, approxConvBelief,
+                    calcFactorResidual, calcFactorResidualTemporary, default_context, getSample, getSolverParams,
+                    getVal, initAll, initfg, ls, lsf, sampleFactor, setVal)
+from .canonical import (generateGraph_Beehive, generateGraph_Circle, generateGraph_Hexagonal,
+                        generateGraph_ManhattanShaped, generateGraph_Pose3Chain, generateGraph_ZeroPose,
+                        seed_particles)
+from .g2o import graphFromEdgeArrays, importG2o, loadG2o, parseG2oInstruction
+
 __version__ = "0.1.0"

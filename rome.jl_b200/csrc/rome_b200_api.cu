@@ -266,9 +266,6 @@ int rome_b200_set_particles(rome_b200_ctx* ctx, int vartype, int nvars, int N, c
     if (vartype < 0 || vartype >= ROME_B200_NVARTYPES) return fail(ctx, ROME_B200_BAD_ARG, "bad vartype");
     if (nvars < 0 || N <= 0 || (nvars > 0 && !coords_host)) return fail(ctx, ROME_B200_BAD_ARG, "bad particle shape");
     if (ctx->capturing) return fail(ctx, ROME_B200_BAD_ARG, "set_particles during graph capture");
-    for (int t = 0; t < ROME_B200_NVARTYPES; ++t)
-        if (t != vartype && ctx->vars[t].nvars > 0 && ctx->vars[t].N != N)
-            return fail(ctx, ROME_B200_SHAPE_MISMATCH, "all variable types of one context must share N");
     if (int e = bind(ctx)) return e;
     const int d = kVarDim[vartype], Npad = rome_b200_npad(N);
     VarStore& vs = ctx->vars[vartype];

@@ -1,0 +1,181 @@
+"""CPU-only tests: the C-ABI library loads and exports every declared symbol, host-side graph logic,
+generators, g2o reader, Packed* round trips, layout helpers.  No compute calls (no GPU here)."""
+import ctypes
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+
+import rome_b200 as rb
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "rome_b200.h")).read()
+    declared = sorted(set(re.findall(r"ROME_B200_API[^;]*?(rome_b200_\w+)\s*\(", hdr)))
+    assert declared == sorted(rb.SYMBOLS)
+    lib = ctypes.CDLL(rb.SO_PATH)
+    for s in declared:
+        assert hasattr(lib, s), s
+    assert lib.rome_b200_version() == 100
+
+
+def test_library_is_sm100a_only_and_uses_tma():
+    import subprocess
+    out = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-lelf", rb.SO_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out and "sm_90" not in out and "sm_80" not in out
+    sass = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-sass", "-fun",
+                           "_ZN4rome11eval_kernelINS_13FamPose2Pose2ELb0EEEvNS_10EvalParamsE", rb.SO_PATH],
+                          capture_output=True, text=True).stdout
+    assert "UBLKCP" in sass  # cp.async.bulk (TMA 1-D) staging of the factor table
+    assert "SYNCS" in sass   # mbarrier
+    assert "SHFL" in sass    # warp-shuffle statistics
+    assert "DFMA" in sass    # Float64 arithmetic
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(rb.RomeB200Error) as ei:
+        rb.Context(0)
+    assert ei.value.code == -5
+
+
+def test_dims_queries():
+    lib = ctypes.CDLL(rb.SO_PATH)
+    for fam, (vt0, vt1, dm, dr, ns, dj, dfwd, dbwd) in rb.FAMILY.items():
+        a, b, c, d = (ctypes.c_int() for _ in range(4))
+        assert lib.rome_b200_family_dims(fam, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c), ctypes.byref(d)) == 0
+        assert (a.value, b.value, c.value, d.value) == (dm, dr, ns, dj)
+    assert lib.rome_b200_family_dims(9, None, None, None, None) == -1
+    assert [lib.rome_b200_vartype_dim(t) for t in (0, 1, 2)] == [3, 2, 6]
+    assert lib.rome_b200_npad(100) == 104 == rb.npad(100) and lib.rome_b200_npad(200) == 200 and lib.rome_b200_npad(1) == 8
+
+
+def test_hexagonal_graph_structure():
+    """src/canonical/GenerateHexagonal.jl:27-42 / GenerateCircular.jl:57-90"""
+    fg = rb.generateGraph_Hexagonal()
+    assert rb.ls(fg) == [f"x{i}" for i in range(7)] + ["l1"]
+    assert rb.lsf(fg) == ["x0f1"] + [f"x{i}x{i+1}f1" for i in range(6)] + ["x0l1f1", "x6l1f1"]
+    assert rb.getSolverParams(fg).N == 100
+    f = fg["x2x3f1"].fnc
+    assert np.allclose(f.Z.mu, [10, 0, math.pi / 3]) and np.allclose(f.Z.Sigma, np.diag([0.01] * 3))
+    assert np.allclose(fg["x0f1"].fnc.Z.Sigma, 0.01 * np.eye(3))
+    br = fg["x6l1f1"].fnc
+    assert (br.bearing.mu, br.bearing.sigma, br.range.mu, br.range.sigma) == (0, 0.1, 20.0, 1.0)
+    # simulated truth closes the hexagon (test/testHexagonal2D_CliqByCliq.jl:37-79)
+    assert np.allclose(fg["x6"].simulated, [0, 0, 0], atol=1e-9)
+    assert np.allclose(fg["x3"].simulated[:2], [10, 17.3205], atol=1e-3)
+
+
+def test_graph_api_errors():
+    fg = rb.initfg()
+    rb.addVariable(fg, "x0", rb.Pose2)
+    rb.addVariable(fg, "l0", rb.Point2)
+    with pytest.raises(KeyError):
+        rb.addVariable(fg, "x0", rb.Pose2)
+    with pytest.raises(KeyError):
+        rb.addFactor(fg, ["x0", "x9"], rb.Pose2Pose2())
+    with pytest.raises(TypeError):
+        rb.addFactor(fg, ["x0", "l0"], rb.Pose2Pose2())
+    with pytest.raises(ValueError):
+        rb.addFactor(fg, ["x0"], rb.Pose2Pose2())
+    with pytest.raises(ValueError):
+        rb.MvNormal(np.zeros(3), np.zeros((3, 3)))
+    with pytest.raises(ValueError):
+        rb.Normal(0, -1)
+    with pytest.raises(ValueError):
+        rb.getVal(fg, "x0")
+    f1 = rb.addFactor(fg, ["x0", "l0"], rb.Pose2Point2BearingRange(rb.Normal(0, 0.1), rb.Normal(20, 1)))
+    f2 = rb.addFactor(fg, ["x0", "l0"], rb.Pose2Point2BearingRange(rb.Normal(0, 0.1), rb.Normal(20, 1)))
+    assert (f1.label, f2.label) == ("x0l0f1", "x0l0f2")
+
+
+def test_defaults_match_reference_structs():
+    assert np.allclose(rb.Pose2Pose2().Z.Sigma, np.eye(3))                       # Pose2D.jl:31
+    assert np.allclose(np.diag(rb.PriorPose2().Z.Sigma), [1, 1, 0.1])            # PriorPose2.jl:14
+    assert np.allclose(np.diag(rb.Pose3Pose3().Z.Sigma), [0.01] * 3 + [1e-4] * 3)  # Pose3Pose3.jl:10
+    assert np.allclose(np.diag(rb.PriorPose3().Z.Sigma), [0.01] * 3 + [1e-4] * 3)  # Pose3D.jl:10
+    assert "SpecialEuclidean(2" in rb.getManifold(rb.Pose2Pose2) and "Hybrid" in rb.getManifold(rb.PriorPose2())
+    assert "SpecialOrthogonal(2), TranslationGroup(1)" in rb.getManifold(
+        rb.Pose2Point2BearingRange(rb.Normal(), rb.Normal()))
+
+
+def test_get_measurement_parametric():
+    m, iS = rb.getMeasurementParametric(rb.Pose2Point2BearingRange(rb.Normal(0.1, 0.2), rb.Normal(20, 0.5)))
+    assert np.allclose(m, [0.1, 20]) and np.allclose(iS, np.diag([25.0, 4.0]))  # BearingRange2D.jl:30-37
+
+
+def test_packed_roundtrip():
+    for f in (rb.Pose2Pose2(rb.MvNormal([1, 2, 3.0], np.diag([1, 2, 3.0]))), rb.PriorPose2(), rb.Pose3Pose3(),
+              rb.PriorPose3(), rb.Pose2Point2BearingRange(rb.Normal(0.1, 0.2), rb.Normal(20, 0.5))):
+        g = rb.unpack(rb.pack(f))
+        assert type(g) is type(f)
+        if hasattr(f, "Z"):
+            assert np.array_equal(g.Z.mu, f.Z.mu) and np.array_equal(g.Z.Sigma, f.Z.Sigma)
+        else:
+            assert g == f
+
+
+def test_g2o_reader(golden_dir, tmp_path):
+    """test/testG2oParser.jl:4-23 imports test/octagon.g2o; info -> Sigma per g2oParser.jl:103-109"""
+    z = np.load(os.path.join(golden_dir, "octagon_g2o.npz"))
+    p = tmp_path / "oct.g2o"
+    with open(p, "w") as fh:
+        for (a, b), m, i in zip(z["ids"], z["mu"], z["info"]):
+            fh.write("EDGE_SE2 %d %d " % (a, b) + " ".join(repr(float(v)) for v in list(m) + list(i)) + "\n")
+    fg = rb.loadG2o(str(p))
+    assert len(rb.ls(fg)) == 8 and len(rb.lsf(fg)) == 8
+    f = fg["x0x1f1"].fnc
+    i = z["info"][0]
+    info = np.array([[i[0], i[1], i[2]], [i[1], i[3], i[4]], [i[2], i[4], i[5]]])
+    assert np.allclose(f.Z.Sigma @ info, np.eye(3), atol=1e-9) and np.allclose(f.Z.Sigma, f.Z.Sigma.T)
+    assert np.allclose(f.Z.mu, z["mu"][0])
+    zz = np.load(os.path.join(golden_dir, "manhattan_g2o.npz"))
+    assert zz["ids"].shape == (5453, 2) and zz["ids"].max() == 3499  # examples/manhattan.g2o
+
+
+def test_g2o_se3_quat():
+    fg = rb.initfg()
+    info = []
+    for r in range(6):
+        for c in range(r, 6):
+            info.append("100.0" if r == c else "0.0")
+    s = math.sin(0.25)
+    rb.parseG2oInstruction(fg, ["EDGE_SE3:QUAT", "0", "1", "1", "2", "3", "0", "0", repr(s), repr(math.cos(0.25))] + info)
+    f = fg["x0x1f1"].fnc
+    assert isinstance(f, rb.Pose3Pose3) and np.allclose(f.Z.mu, [1, 2, 3, 0, 0, 0.5]) and np.allclose(f.Z.Sigma, 0.01 * np.eye(6))
+
+
+def test_generators_shapes():
+    fg = rb.generateGraph_ManhattanShaped(500, seed=2)
+    assert len(rb.ls(fg)) == 500 and len(rb.lsf(fg, rb.Pose2Pose2)) >= 499 and len(rb.lsf(fg, rb.PriorPose2)) == 1
+    # every factor's mean is close to the relative pose of the simulated truth
+    for l in rb.lsf(fg, rb.Pose2Pose2)[:50]:
+        f = fg[l]
+        p, q = fg[f.variableOrderSymbols[0]].simulated, fg[f.variableOrderSymbols[1]].simulated
+        c, s = math.cos(p[2]), math.sin(p[2])
+        d = q[:2] - p[:2]
+        assert abs(c * d[0] + s * d[1] - f.fnc.Z.mu[0]) < 1.0
+    bh = rb.generateGraph_Beehive(40)
+    assert len(rb.ls(bh, rb.Pose2)) == 41 and len(rb.lsf(bh, rb.Pose2Point2BearingRange)) == 41
+    assert len(rb.ls(bh, rb.Point2)) < 41  # lattice landmarks are re-sighted (loop closures)
+    p3 = rb.generateGraph_Pose3Chain(300, loops=20)
+    assert len(rb.ls(p3, rb.Pose3)) == 300 and len(rb.lsf(p3, rb.PriorPose3)) == 1
+    rb.seed_particles(p3, N=16)
+    assert rb.getVal(p3, "x5").shape == (16, 6)
+
+
+def test_layout_helpers():
+    rng = np.random.default_rng(0)
+    meas = rng.normal(size=(5, 100, 3))
+    mu = rng.normal(size=(5, 3))
+    off = rb.meas_to_offsets(meas, mu)
+    assert off.shape == (5, 3, 104) and off.dtype == np.float32 and np.all(off[:, :, 100:] == 0)
+    back = rb.offsets_to_meas(off, mu, 100)
+    assert np.abs(back - meas).max() < 1e-6
+    assert rb.rows_to_particle_major(off, 100).shape == (5, 100, 3)
