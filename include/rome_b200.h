@@ -30,7 +30,7 @@
  *     `[nvars][N][d]` (DFG `vecval`), d = 3 (Pose2: x,y,theta), 2 (Point2), 6 (Pose3: x,y,z,
  *     rotation vector) -- src/variables/VariableTypes.jl:13,35,47.
  *   - device layout ("anchored float32"): value = anchor(Float64, per variable / per factor
- *     mean) + offset(float32).  Particles  [nvars][d][Npad] offsets + [nvars][d] anchors;
+ *     mean) + offset(float32).  Particles: one block per variable {anchor f64[d], d rows x Npad f32};
  *     measurements [nF][dm][Npad] offsets from the factor mean; residuals [nF][dr][Npad]
  *     float32; proposals [nF][dv][Npad] offsets from the TARGET variable's anchor.
  *     Npad = N rounded up to a multiple of 8 (32-byte sectors); padding lanes hold 0.
@@ -118,9 +118,10 @@ ROME_B200_API int rome_b200_npad(int N);
  * hold the same N when that family is evaluated (checked by rome_b200_eval). */
 ROME_B200_API int rome_b200_set_particles(rome_b200_ctx* ctx, int vartype, int nvars, int N, const double* coords_host);
 ROME_B200_API int rome_b200_get_particles(rome_b200_ctx* ctx, int vartype, double* coords_host);
-/* Device views (zero-copy interop): offsets [nvars][d][Npad], anchors [nvars][d]. */
-ROME_B200_API int rome_b200_particles_device(rome_b200_ctx* ctx, int vartype, float** d_offsets, double** d_anchors,
-                               int* nvars, int* N, int* Npad);
+/* Device view of the particle store (zero-copy interop): nvars contiguous blocks of `block_bytes`, each
+ * { anchor: d doubles padded to `header_bytes` }{ d rows x Npad float32 offsets }. */
+ROME_B200_API int rome_b200_particles_device(rome_b200_ctx* ctx, int vartype, void** d_store, int* block_bytes,
+                                             int* header_bytes, int* nvars, int* N, int* Npad);
 /* Replace the particles of variable `var` by proposal row `factor` of a device proposal buffer
  * (offsets from that variable's anchor) -- used to chain convolutions (graph init). */
 ROME_B200_API int rome_b200_adopt_proposal(rome_b200_ctx* ctx, int vartype, int var, const float* d_prop, int factor);

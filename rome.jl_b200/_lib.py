@@ -63,8 +63,7 @@ def load() -> C.CDLL:
     lib.rome_b200_npad.argtypes = [i]
     lib.rome_b200_set_particles.argtypes = [vp, i, i, i, vp]
     lib.rome_b200_get_particles.argtypes = [vp, i, vp]
-    lib.rome_b200_particles_device.argtypes = [vp, i, C.POINTER(vp), C.POINTER(vp), C.POINTER(i), C.POINTER(i),
-                                               C.POINTER(i)]
+    lib.rome_b200_particles_device.argtypes = [vp, i, C.POINTER(vp)] + [C.POINTER(i)] * 5
     lib.rome_b200_adopt_proposal.argtypes = [vp, i, i, vp, i]
     lib.rome_b200_set_factors_pose2pose2.argtypes = [vp, i, ip32, ip32, dp, dp]
     lib.rome_b200_set_factors_priorpose2.argtypes = [vp, i, ip32, dp, dp]

@@ -33,6 +33,9 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
     const uint32_t addr = smem_u32(bar);
     uint32_t ok;
@@ -53,6 +56,17 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
                  "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+
+// shared -> global 1-D bulk store (bulk async-group completion)
+__device__ __forceinline__ void tma_store_1d(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all of this thread's bulk stores have finished READING shared memory (the source may be overwritten)
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------
 // global memory access with cache hints
@@ -88,6 +102,37 @@ __device__ __forceinline__ double sym_rem(double x) {
     return (fabs(x - kPi) <= 1.4901161193847656e-08 * fmax(fabs(x), kPi)) ? -kPi : r;
 }
 
+// sin/cos of a SMALL angle |x| <= pi/4 (the float32 heading offset of a particle from its variable's
+// anchor heading): fdlibm __kernel_sin/__kernel_cos minimax polynomials, coefficients in constant memory so
+// that every DFMA takes its coefficient as a constant-bank operand.  |error| < 1e-16.
+__constant__ double kSinC[6] = {-1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04,
+                                2.75573137070700676789e-06,  -2.50507602534068634195e-08, 1.58969099521155010221e-10};
+__constant__ double kCosC[6] = {4.16666666666666019037e-02,  -1.38888888888741095749e-03, 2.48015872894767294178e-05,
+                                -2.75573143513906633035e-07, 2.08757232129817482790e-09,  -1.13596475577881948265e-11};
+constexpr double kSmallAngle = 0.78;
+__device__ __forceinline__ void sincos_small(double x, double& s, double& c) {
+    const double z = x * x;
+    double ps = fma(z, kSinC[5], kSinC[4]);
+    double pc = fma(z, kCosC[5], kCosC[4]);
+    ps = fma(z, ps, kSinC[3]); pc = fma(z, pc, kCosC[3]);
+    ps = fma(z, ps, kSinC[2]); pc = fma(z, pc, kCosC[2]);
+    ps = fma(z, ps, kSinC[1]); pc = fma(z, pc, kCosC[1]);
+    ps = fma(z, ps, kSinC[0]); pc = fma(z, pc, kCosC[0]);
+    s = fma(x * z, ps, x);
+    c = fma(z * z, pc, fma(z, -0.5, 1.0));
+}
+// sin/cos of (anchor + x) given (ca, sa) = cos/sin(anchor): angle addition for small x, general path otherwise
+__device__ __forceinline__ void sincos_anchored(double anchor, double ca, double sa, double x, double& s, double& c) {
+    if (fabs(x) <= kSmallAngle) {
+        double sx, cx;
+        sincos_small(x, sx, cx);
+        s = fma(sa, cx, ca * sx);
+        c = fma(ca, cx, -sa * sx);
+    } else {
+        sincos(anchor + x, &s, &c);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Philox4x32-10 counter RNG + Box-Muller; host twin: oracle/rome_oracle.c rome_oracle_normal4
 // counter = (particle, factor, stream, block), key = seed
@@ -103,12 +148,22 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1
     }
     return c;
 }
+// Box-Muller on the special-function unit (MUFU.LG2 / MUFU.SIN / MUFU.COS): the draws differ from the
+// Float64 host twin by <= ~1e-4 sigma (tests/test_gpu_parity_raw.py); exact parity of a sweep is taken on
+// the samples the kernel writes back (ROME_B200_WRITE_MEAS), never on re-derived ones.
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
     const float u1 = (static_cast<float>(a >> 9) + 0.5f) * (1.0f / 8388608.0f);  // exact, in (0,1)
     const float u2 = (static_cast<float>(b >> 9) + 0.5f) * (1.0f / 8388608.0f);
+#ifdef ROME_B200_ACCURATE_SAMPLER
     const float rad = sqrtf(-2.0f * logf(u1));
     float s, c;
     sincospif(2.0f * u2, &s, &c);
+#else
+    const float rad = sqrtf(fmaxf(-2.0f * __logf(u1), 0.0f));
+    float s, c;  // cos(2 pi u) = -cos(2 pi u - pi): keeps the MUFU argument inside [-pi, pi]
+    __sincosf(6.28318530717958647692f * (u2 - 0.5f), &s, &c);
+    s = -s; c = -c;
+#endif
     z0 = rad * c;
     z1 = rad * s;
 }

@@ -5,12 +5,14 @@
 // group operation, applies the measurement and writes the residual coordinates, the closed-form
 // proposal(s), compact Jacobian entries and per-factor statistics.
 //
-//   persistent CTAs (8 warps) loop over tiles of 8 factors, one warp per factor;
-//   the tile's factor-table rows {var ids, mu (f64), chol(Sigma) (f32)} are staged into shared
-//   memory by a 1-D TMA bulk copy (cp.async.bulk + mbarrier), double buffered two tiles ahead;
-//   particles / measurements / residuals are SoA float32 rows [.][comp][Npad]: a warp reads a row
-//   as coalesced 16-B (SE(2)) or 4-B (SE(3)) lane accesses; residual rows are written with
-//   streaming stores; arithmetic is Float64 on anchored float32 storage (DESIGN.md "precision");
+//   persistent CTAs = FT consumer warps (one factor each per tile of FT factors) + 1 producer warp;
+//   the producer stages, per tile and S tiles ahead, everything the consumers read into shared memory
+//   with 1-D TMA bulk copies (cp.async.bulk, completion on an mbarrier per stage): the tile's factor-table
+//   rows {var ids, mu (f64), chol(Sigma) (f32)}, its measurement block, and -- gathered by variable id --
+//   one contiguous particle block {anchor (f64), d rows x Npad float32 offsets} per factor slot;
+//   consumers never issue a global load: they wait on the stage's "full" barrier, compute in Float64 on
+//   the anchored float32 data (DESIGN.md "precision"), write residual / proposal rows with coalesced
+//   16-B streaming stores and release the stage through its "empty" barrier;
 //   statistics are reduced with a halving-butterfly of __shfl_xor_sync (device_utils.cuh).
 //
 // Reference arithmetic (paths relative to /root/reference):
@@ -103,270 +105,219 @@ __device__ __forceinline__ void write_stats16(float (&st)[16], float* stats, int
     const float tot = warp_reduce_scatter16(st, lane);
     if ((lane & 1) == 0) stats[(size_t)f * 16 + (lane >> 1)] = tot;
 }
+// What a consumer warp sees of its factor: inputs already in shared memory, plus its private output slice.
+struct FactorView {
+    const unsigned char* b0;  // particle block of the first variable  {anchor, rows}
+    const unsigned char* b1;  // particle block of the second variable (nullptr for priors)
+    const float* meas;        // [dm][Npad] measurement offsets (nullptr with SAMPLE)
+    float* out_res;           // [dr][Npad] residual rows, flushed by a warp-local TMA bulk store
+    float* out_fwd;           // [dfwd][Npad] forward-proposal rows, same
+};
+constexpr uint32_t kHot1 = ROME_B200_RESIDUAL | ROME_B200_STATS;
+constexpr uint32_t kHot2 = ROME_B200_RESIDUAL | ROME_B200_STATS | ROME_B200_PROPOSAL_FWD;
 
 // =============================================================================================
-// Pose2Pose2
+// SE(2) families: one particle per lane per iteration (conflict-free 4-B shared-memory accesses).
+// kStatic != 0 fixes the output flags at compile time (hot variants); 0 reads them from P.flags.
 // =============================================================================================
+__device__ __forceinline__ void sample3(const RowSE2& row, const EvalParams& P, int f, int n, float& mx, float& my,
+                                        float& mt) {
+    float z[4];
+    normal4(P.seed_lo, P.seed_hi, P.stream_id, (uint32_t)f, (uint32_t)n, 0u, z);
+    mx = row.L[0] * z[0];
+    my = fmaf(row.L[2], z[1], row.L[1] * z[0]);
+    mt = fmaf(row.L[5], z[2], fmaf(row.L[4], z[1], row.L[3] * z[0]));
+}
+
 struct FamPose2Pose2 {
     using Row = RowSE2;
-    template <bool kSample>
-    static __device__ __forceinline__ void factor(const Row& row, const EvalParams& P, int f, int lane) {
+    static constexpr int D0 = 3, D1 = 3, DM = 3, DR = 3, DFWD = 3, kMinCtas = 2;
+    template <uint32_t kStatic, bool kSample>
+    static __device__ __forceinline__ void factor(const Row& row, const EvalParams& P, const FactorView& V, int f,
+                                                  int lane) {
         const int Npad = P.Npad, N = P.N;
-        const uint32_t flags = P.flags;
-        const float* __restrict__ Pp = P.v0 + (size_t)row.ip * 3 * Npad;
-        const float* __restrict__ Qp = P.v1 + (size_t)row.iq * 3 * Npad;
-        const double apx = P.a0[row.ip * 3], apy = P.a0[row.ip * 3 + 1], apt = P.a0[row.ip * 3 + 2];
-        const double aqx = P.a1[row.iq * 3], aqy = P.a1[row.iq * 3 + 1], aqt = P.a1[row.iq * 3 + 2];
-        const double dax = apx - aqx, day = apy - aqy, dat = apt - aqt;  // anchor deltas (exact Float64)
+        const uint32_t flags = kStatic ? kStatic : P.flags;
+        const double* ap = reinterpret_cast<const double*>(V.b0);  // {x, y, theta, cos, sin}
+        const double* aq = reinterpret_cast<const double*>(V.b1);
+        const float* Pp = reinterpret_cast<const float*>(V.b0 + var_header_bytes(3));
+        const float* Qp = reinterpret_cast<const float*>(V.b1 + var_header_bytes(3));
+        const double apt = ap[2], ca = ap[3], sa = ap[4];
+        const double dax = ap[0] - aq[0], day = ap[1] - aq[1], dat = apt - aq[2];  // anchor deltas (exact Float64)
+        const double mu0 = row.mu[0], mu1 = row.mu[1], mu2 = row.mu[2];
         const size_t fo = (size_t)f * 3 * Npad;
         const bool want_stats = flags & ROME_B200_STATS;
         float st[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) st[i] = 0.f;
 
-        for (int base = lane * 4; base < Npad; base += 128) {
-            const float4 px = ld_reuse4(Pp + base), py = ld_reuse4(Pp + Npad + base),
-                         pt = ld_reuse4(Pp + 2 * Npad + base);
-            const float4 qx = ld_reuse4(Qp + base), qy = ld_reuse4(Qp + Npad + base),
-                         qt = ld_reuse4(Qp + 2 * Npad + base);
-            float4 mx, my, mt;
+        for (int n = lane; n < Npad; n += 32) {
+            const double dpx = Pp[n], dpy = Pp[Npad + n], dpt = Pp[2 * Npad + n];
+            const double dqx = Qp[n], dqy = Qp[Npad + n], dqt = Qp[2 * Npad + n];
+            float mx, my, mt;
             if (!kSample) {
-                mx = ld_stream4(P.meas + fo + base);
-                my = ld_stream4(P.meas + fo + Npad + base);
-                mt = ld_stream4(P.meas + fo + 2 * Npad + base);
+                mx = V.meas[n]; my = V.meas[Npad + n]; mt = V.meas[2 * Npad + n];
             } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float z[4];
-                    normal4(P.seed_lo, P.seed_hi, P.stream_id, (uint32_t)f, (uint32_t)(base + j), 0u, z);
-                    f4(mx, j) = row.L[0] * z[0];
-                    f4(my, j) = fmaf(row.L[2], z[1], row.L[1] * z[0]);
-                    f4(mt, j) = fmaf(row.L[5], z[2], fmaf(row.L[4], z[1], row.L[3] * z[0]));
+                sample3(row, P, f, n, mx, my, mt);
+                if (flags & ROME_B200_WRITE_MEAS) {
+                    __stcs(P.meas_out + fo + n, mx);
+                    __stcs(P.meas_out + fo + Npad + n, my);
+                    __stcs(P.meas_out + fo + 2 * Npad + n, mt);
                 }
             }
-            float4 r1, r2, r3, fx, fy, ft, bx, by, bt, j0, j1, j2, j3;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const double dpx = f4c(px, j), dpy = f4c(py, j), dpt = f4c(pt, j);
-                const double dqx = f4c(qx, j), dqy = f4c(qy, j), dqt = f4c(qt, j);
-                const double Xx = row.mu[0] + (double)f4c(mx, j);
-                const double Xy = row.mu[1] + (double)f4c(my, j);
-                const double Xt = row.mu[2] + (double)f4c(mt, j);
-                double s, c;
-                sincos(apt + dpt, &s, &c);
-                const double rx = c * Xx - s * Xy;  // R(theta_p) X.t
-                const double ry = s * Xx + c * Xy;
-                // qhat - q, Pose2D.jl:62-65 ; qhat offsets are relative to q's anchor
-                const double hx = (dax + dpx) + rx, hy = (day + dpy) + ry;
-                const double ht = (dat + dpt) + Xt;
-                const float e1 = (float)(hx - dqx), e2 = (float)(hy - dqy), e3 = (float)wrap_pi(ht - dqt);
-                f4(r1, j) = e1; f4(r2, j) = e2; f4(r3, j) = e3;
-                const float msk = (base + j < N) ? 1.f : 0.f;
-                if (want_stats) acc_res3(st, msk, e1, e2, e3);
-                if (flags & ROME_B200_PROPOSAL_FWD) {
-                    const float ox = (float)hx, oy = (float)hy, ot = (float)wrap_pi(ht);
-                    f4(fx, j) = ox; f4(fy, j) = oy; f4(ft, j) = ot;
-                    if (want_stats) { acc_prop2(st, msk, ox, oy); acc_heading(st, msk, ot); }
-                }
-                if (flags & ROME_B200_PROPOSAL_BWD) {
-                    // theta_p = theta_q - m_theta ; t_p = t_q - R(theta_p) m_t   (offsets from p's anchor)
-                    const double tb = (dqt - dat) - Xt;  // offset from apt
-                    double sb, cb;
-                    sincos(apt + tb, &sb, &cb);
-                    const float ox = (float)((dqx - dax) - (cb * Xx - sb * Xy));
-                    const float oy = (float)((dqy - day) - (sb * Xx + cb * Xy));
-                    const float ot = (float)wrap_pi(tb);
-                    f4(bx, j) = ox; f4(by, j) = oy; f4(bt, j) = ot;
-                    if (want_stats && !(flags & ROME_B200_PROPOSAL_FWD)) {
-                        acc_prop2(st, msk, ox, oy); acc_heading(st, msk, ot);
-                    }
-                }
-                if (flags & ROME_B200_JACOBIAN) {  // d r/d theta_p = (-ry, rx, 1); d r/d m = R(theta_p) (+) 1
-                    f4(j0, j) = (float)(-ry); f4(j1, j) = (float)rx; f4(j2, j) = (float)c; f4(j3, j) = (float)s;
-                }
-            }
-            if (kSample && (flags & ROME_B200_WRITE_MEAS)) {
-                st_stream4(P.meas_out + fo + base, mx);
-                st_stream4(P.meas_out + fo + Npad + base, my);
-                st_stream4(P.meas_out + fo + 2 * Npad + base, mt);
-            }
+            const double Xx = mu0 + (double)mx, Xy = mu1 + (double)my, Xt = mu2 + (double)mt;
+            double s, c;
+            sincos_anchored(apt, ca, sa, dpt, s, c);
+            const double rx = c * Xx - s * Xy;  // R(theta_p) X.t
+            const double ry = s * Xx + c * Xy;
+            // qhat - q, Pose2D.jl:62-65 ; qhat offsets are relative to q's anchor
+            const double hx = (dax + dpx) + rx, hy = (day + dpy) + ry;
+            const double ht = (dat + dpt) + Xt;
+            const float e1 = (float)(hx - dqx), e2 = (float)(hy - dqy), e3 = (float)wrap_pi(ht - dqt);
+            const float msk = (n < N) ? 1.f : 0.f;
             if (flags & ROME_B200_RESIDUAL) {
-                st_stream4(P.res + fo + base, r1);
-                st_stream4(P.res + fo + Npad + base, r2);
-                st_stream4(P.res + fo + 2 * Npad + base, r3);
+                V.out_res[n] = e1; V.out_res[Npad + n] = e2; V.out_res[2 * Npad + n] = e3;
             }
+            if (want_stats) acc_res3(st, msk, e1, e2, e3);
             if (flags & ROME_B200_PROPOSAL_FWD) {
-                st_stream4(P.prop_fwd + fo + base, fx);
-                st_stream4(P.prop_fwd + fo + Npad + base, fy);
-                st_stream4(P.prop_fwd + fo + 2 * Npad + base, ft);
+                const float ox = (float)hx, oy = (float)hy, ot = (float)wrap_pi(ht);
+                V.out_fwd[n] = ox; V.out_fwd[Npad + n] = oy; V.out_fwd[2 * Npad + n] = ot;
+                if (want_stats) { acc_prop2(st, msk, ox, oy); acc_heading(st, msk, ot); }
             }
             if (flags & ROME_B200_PROPOSAL_BWD) {
-                st_stream4(P.prop_bwd + fo + base, bx);
-                st_stream4(P.prop_bwd + fo + Npad + base, by);
-                st_stream4(P.prop_bwd + fo + 2 * Npad + base, bt);
+                // theta_p = theta_q - m_theta ; t_p = t_q - R(theta_p) m_t   (offsets from p's anchor)
+                const double tb = (dqt - dat) - Xt;  // offset from apt
+                double sb, cb;
+                sincos(apt + tb, &sb, &cb);
+                const float ox = (float)((dqx - dax) - (cb * Xx - sb * Xy));
+                const float oy = (float)((dqy - day) - (sb * Xx + cb * Xy));
+                const float ot = (float)wrap_pi(tb);
+                __stcs(P.prop_bwd + fo + n, ox);
+                __stcs(P.prop_bwd + fo + Npad + n, oy);
+                __stcs(P.prop_bwd + fo + 2 * Npad + n, ot);
+                if (want_stats && !(flags & ROME_B200_PROPOSAL_FWD)) {
+                    acc_prop2(st, msk, ox, oy); acc_heading(st, msk, ot);
+                }
             }
-            if (flags & ROME_B200_JACOBIAN) {
-                float* J = P.jac + (size_t)f * 4 * Npad + base;
-                st_stream4(J, j0); st_stream4(J + Npad, j1); st_stream4(J + 2 * Npad, j2); st_stream4(J + 3 * Npad, j3);
+            if (flags & ROME_B200_JACOBIAN) {  // d r/d theta_p = (-ry, rx, 1); d r/d m = R(theta_p) (+) 1
+                float* J = P.jac + (size_t)f * 4 * Npad + n;
+                __stcs(J, (float)(-ry)); __stcs(J + Npad, (float)rx);
+                __stcs(J + 2 * Npad, (float)c); __stcs(J + 3 * Npad, (float)s);
             }
         }
         if (want_stats) write_stats16(st, P.stats, f, lane);
     }
 };
 
-// =============================================================================================
 // PriorPose2: r = (m.t - p.t, wrap(m.theta - p.theta)); proposal = the sampled point m
-// =============================================================================================
 struct FamPriorPose2 {
     using Row = RowSE2;
-    template <bool kSample>
-    static __device__ __forceinline__ void factor(const Row& row, const EvalParams& P, int f, int lane) {
+    static constexpr int D0 = 3, D1 = 0, DM = 3, DR = 3, DFWD = 3, kMinCtas = 2;
+    template <uint32_t kStatic, bool kSample>
+    static __device__ __forceinline__ void factor(const Row& row, const EvalParams& P, const FactorView& V, int f,
+                                                  int lane) {
         const int Npad = P.Npad, N = P.N;
-        const uint32_t flags = P.flags;
-        const float* __restrict__ Pp = P.v0 + (size_t)row.ip * 3 * Npad;
+        const uint32_t flags = kStatic ? kStatic : P.flags;
+        const double* ap = reinterpret_cast<const double*>(V.b0);
+        const float* Pp = reinterpret_cast<const float*>(V.b0 + var_header_bytes(3));
         // mean relative to the variable's anchor
-        const double mx0 = row.mu[0] - P.a0[row.ip * 3], my0 = row.mu[1] - P.a0[row.ip * 3 + 1],
-                     mt0 = row.mu[2] - P.a0[row.ip * 3 + 2];
+        const double mx0 = row.mu[0] - ap[0], my0 = row.mu[1] - ap[1], mt0 = row.mu[2] - ap[2];
         const size_t fo = (size_t)f * 3 * Npad;
         const bool want_stats = flags & ROME_B200_STATS;
         float st[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) st[i] = 0.f;
-        for (int base = lane * 4; base < Npad; base += 128) {
-            const float4 px = ld_reuse4(Pp + base), py = ld_reuse4(Pp + Npad + base),
-                         pt = ld_reuse4(Pp + 2 * Npad + base);
-            float4 mx, my, mt;
+        for (int n = lane; n < Npad; n += 32) {
+            const double dpx = Pp[n], dpy = Pp[Npad + n], dpt = Pp[2 * Npad + n];
+            float mx, my, mt;
             if (!kSample) {
-                mx = ld_stream4(P.meas + fo + base);
-                my = ld_stream4(P.meas + fo + Npad + base);
-                mt = ld_stream4(P.meas + fo + 2 * Npad + base);
+                mx = V.meas[n]; my = V.meas[Npad + n]; mt = V.meas[2 * Npad + n];
             } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float z[4];
-                    normal4(P.seed_lo, P.seed_hi, P.stream_id, (uint32_t)f, (uint32_t)(base + j), 0u, z);
-                    f4(mx, j) = row.L[0] * z[0];
-                    f4(my, j) = fmaf(row.L[2], z[1], row.L[1] * z[0]);
-                    f4(mt, j) = fmaf(row.L[5], z[2], fmaf(row.L[4], z[1], row.L[3] * z[0]));
+                sample3(row, P, f, n, mx, my, mt);
+                if (flags & ROME_B200_WRITE_MEAS) {
+                    __stcs(P.meas_out + fo + n, mx);
+                    __stcs(P.meas_out + fo + Npad + n, my);
+                    __stcs(P.meas_out + fo + 2 * Npad + n, mt);
                 }
             }
-            float4 r1, r2, r3, fx, fy, ft;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const double hx = mx0 + (double)f4c(mx, j), hy = my0 + (double)f4c(my, j),
-                             ht = mt0 + (double)f4c(mt, j);  // m as offset from the anchor
-                const float e1 = (float)(hx - (double)f4c(px, j)), e2 = (float)(hy - (double)f4c(py, j)),
-                            e3 = (float)wrap_pi(ht - (double)f4c(pt, j));
-                f4(r1, j) = e1; f4(r2, j) = e2; f4(r3, j) = e3;
-                const float msk = (base + j < N) ? 1.f : 0.f;
-                if (want_stats) acc_res3(st, msk, e1, e2, e3);
-                if (flags & ROME_B200_PROPOSAL_FWD) {
-                    const float ox = (float)hx, oy = (float)hy, ot = (float)wrap_pi(ht);
-                    f4(fx, j) = ox; f4(fy, j) = oy; f4(ft, j) = ot;
-                    if (want_stats) { acc_prop2(st, msk, ox, oy); acc_heading(st, msk, ot); }
-                }
-            }
-            if (kSample && (flags & ROME_B200_WRITE_MEAS)) {
-                st_stream4(P.meas_out + fo + base, mx);
-                st_stream4(P.meas_out + fo + Npad + base, my);
-                st_stream4(P.meas_out + fo + 2 * Npad + base, mt);
-            }
+            const double hx = mx0 + (double)mx, hy = my0 + (double)my, ht = mt0 + (double)mt;  // m - anchor
+            const float e1 = (float)(hx - dpx), e2 = (float)(hy - dpy), e3 = (float)wrap_pi(ht - dpt);
+            const float msk = (n < N) ? 1.f : 0.f;
             if (flags & ROME_B200_RESIDUAL) {
-                st_stream4(P.res + fo + base, r1);
-                st_stream4(P.res + fo + Npad + base, r2);
-                st_stream4(P.res + fo + 2 * Npad + base, r3);
+                V.out_res[n] = e1; V.out_res[Npad + n] = e2; V.out_res[2 * Npad + n] = e3;
             }
+            if (want_stats) acc_res3(st, msk, e1, e2, e3);
             if (flags & ROME_B200_PROPOSAL_FWD) {
-                st_stream4(P.prop_fwd + fo + base, fx);
-                st_stream4(P.prop_fwd + fo + Npad + base, fy);
-                st_stream4(P.prop_fwd + fo + 2 * Npad + base, ft);
+                const float ox = (float)hx, oy = (float)hy, ot = (float)wrap_pi(ht);
+                V.out_fwd[n] = ox; V.out_fwd[Npad + n] = oy; V.out_fwd[2 * Npad + n] = ot;
+                if (want_stats) { acc_prop2(st, msk, ox, oy); acc_heading(st, msk, ot); }
             }
         }
         if (want_stats) write_stats16(st, P.stats, f, lane);
     }
 };
 
-// =============================================================================================
 // Pose2Point2BearingRange: pl = R_p'(l - t_p); r = (sym_rem(b - atan(pl)), rho - |pl|)
 // evaluated as atan(pl) = atan(l - t_p) - theta_p and |pl| = |l - t_p| (same values, no rotation)
-// =============================================================================================
 struct FamBearingRange {
     using Row = RowBR;
-    template <bool kSample>
-    static __device__ __forceinline__ void factor(const Row& row, const EvalParams& P, int f, int lane) {
+    static constexpr int D0 = 3, D1 = 2, DM = 2, DR = 2, DFWD = 2, kMinCtas = 2;
+    template <uint32_t kStatic, bool kSample>
+    static __device__ __forceinline__ void factor(const Row& row, const EvalParams& P, const FactorView& V, int f,
+                                                  int lane) {
         const int Npad = P.Npad, N = P.N;
-        const uint32_t flags = P.flags;
-        const float* __restrict__ Pp = P.v0 + (size_t)row.ip * 3 * Npad;
-        const float* __restrict__ Lp = P.v1 + (size_t)row.il * 2 * Npad;
-        const double apt = P.a0[row.ip * 3 + 2];
-        const double dax = P.a1[row.il * 2] - P.a0[row.ip * 3];  // anchor(l) - anchor(p)
-        const double day = P.a1[row.il * 2 + 1] - P.a0[row.ip * 3 + 1];
+        const uint32_t flags = kStatic ? kStatic : P.flags;
+        const double* ap = reinterpret_cast<const double*>(V.b0);
+        const double* al = reinterpret_cast<const double*>(V.b1);
+        const float* Pp = reinterpret_cast<const float*>(V.b0 + var_header_bytes(3));
+        const float* Lp = reinterpret_cast<const float*>(V.b1 + var_header_bytes(2));
+        const double apt = ap[2];
+        const double dax = al[0] - ap[0], day = al[1] - ap[1];  // anchor(l) - anchor(p)
         const size_t fo = (size_t)f * 2 * Npad;
         const bool want_stats = flags & ROME_B200_STATS;
         float st[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) st[i] = 0.f;
-        for (int base = lane * 4; base < Npad; base += 128) {
-            const float4 px = ld_reuse4(Pp + base), py = ld_reuse4(Pp + Npad + base),
-                         pt = ld_reuse4(Pp + 2 * Npad + base);
-            const float4 lx = ld_reuse4(Lp + base), ly = ld_reuse4(Lp + Npad + base);
-            float4 mb, mr;
+        for (int n = lane; n < Npad; n += 32) {
+            const double dpx = Pp[n], dpy = Pp[Npad + n], dpt = Pp[2 * Npad + n];
+            const double dlx = Lp[n], dly = Lp[Npad + n];
+            float mb, mr;
             if (!kSample) {
-                mb = ld_stream4(P.meas + fo + base);
-                mr = ld_stream4(P.meas + fo + Npad + base);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {  // two independent scalar draws, BearingRange2D.jl:23
-                    float z[4];
-                    normal4(P.seed_lo, P.seed_hi, P.stream_id, (uint32_t)f, (uint32_t)(base + j), 0u, z);
-                    f4(mb, j) = row.sig_b * z[0];
-                    f4(mr, j) = row.sig_r * z[1];
+                mb = V.meas[n]; mr = V.meas[Npad + n];
+            } else {  // two independent scalar draws, BearingRange2D.jl:23
+                float z[4];
+                normal4(P.seed_lo, P.seed_hi, P.stream_id, (uint32_t)f, (uint32_t)n, 0u, z);
+                mb = row.sig_b * z[0];
+                mr = row.sig_r * z[1];
+                if (flags & ROME_B200_WRITE_MEAS) {
+                    __stcs(P.meas_out + fo + n, mb);
+                    __stcs(P.meas_out + fo + Npad + n, mr);
                 }
             }
-            float4 r1, r2, fx, fy, j0, j1, j2, j3;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const double b = row.mu_b + (double)f4c(mb, j), rho = row.mu_r + (double)f4c(mr, j);
-                const double dx = dax + ((double)f4c(lx, j) - (double)f4c(px, j));
-                const double dy = day + ((double)f4c(ly, j) - (double)f4c(py, j));
-                const double th = apt + (double)f4c(pt, j);
-                const double d2 = dx * dx + dy * dy;
-                const double rng = sqrt(d2);
-                double e1d = wrap_pi(b + th - atan2(dy, dx));
-                if (fabs(e1d - kPi) <= 1.4901161193847656e-08 * kPi) e1d = -kPi;  // sym_rem: +pi -> -pi
-                const float e1 = (float)e1d, e2 = (float)(rho - rng);
-                f4(r1, j) = e1; f4(r2, j) = e2;
-                const float msk = (base + j < N) ? 1.f : 0.f;
-                if (want_stats) acc_res3(st, msk, e1, e2, 0.f);
-                if (flags & ROME_B200_PROPOSAL_FWD) {  // l = t_p + rho R(theta_p)(cos b, sin b), offset from l's anchor
-                    double s, c;
-                    sincos(th + b, &s, &c);
-                    const float ox = (float)(((double)f4c(px, j) - dax) + rho * c);
-                    const float oy = (float)(((double)f4c(py, j) - day) + rho * s);
-                    f4(fx, j) = ox; f4(fy, j) = oy;
-                    if (want_stats) acc_prop2(st, msk, ox, oy);
-                }
-                if (flags & ROME_B200_JACOBIAN) {  // d r1/d l = (dy,-dx)/rho^2 ; d r2/d l = -d/rho
-                    const double i2 = 1.0 / d2, i1 = 1.0 / rng;
-                    f4(j0, j) = (float)(dy * i2); f4(j1, j) = (float)(-dx * i2);
-                    f4(j2, j) = (float)(-dx * i1); f4(j3, j) = (float)(-dy * i1);
-                }
-            }
-            if (kSample && (flags & ROME_B200_WRITE_MEAS)) {
-                st_stream4(P.meas_out + fo + base, mb);
-                st_stream4(P.meas_out + fo + Npad + base, mr);
-            }
+            const double b = row.mu_b + (double)mb, rho = row.mu_r + (double)mr;
+            const double dx = dax + (dlx - dpx), dy = day + (dly - dpy);
+            const double th = apt + dpt;
+            const double d2 = dx * dx + dy * dy;
+            const double rng = sqrt(d2);
+            double e1d = wrap_pi(b + th - atan2(dy, dx));
+            if (fabs(e1d - kPi) <= 1.4901161193847656e-08 * kPi) e1d = -kPi;  // sym_rem: +pi -> -pi
+            const float e1 = (float)e1d, e2 = (float)(rho - rng);
+            const float msk = (n < N) ? 1.f : 0.f;
             if (flags & ROME_B200_RESIDUAL) {
-                st_stream4(P.res + fo + base, r1);
-                st_stream4(P.res + fo + Npad + base, r2);
+                V.out_res[n] = e1; V.out_res[Npad + n] = e2;
             }
-            if (flags & ROME_B200_PROPOSAL_FWD) {
-                st_stream4(P.prop_fwd + fo + base, fx);
-                st_stream4(P.prop_fwd + fo + Npad + base, fy);
+            if (want_stats) acc_res3(st, msk, e1, e2, 0.f);
+            if (flags & ROME_B200_PROPOSAL_FWD) {  // l = t_p + rho R(theta_p)(cos b, sin b), offset from l's anchor
+                double s, c;
+                sincos(th + b, &s, &c);
+                const float ox = (float)((dpx - dax) + rho * c), oy = (float)((dpy - day) + rho * s);
+                V.out_fwd[n] = ox; V.out_fwd[Npad + n] = oy;
+                if (want_stats) acc_prop2(st, msk, ox, oy);
             }
-            if (flags & ROME_B200_JACOBIAN) {
-                float* J = P.jac + (size_t)f * 4 * Npad + base;
-                st_stream4(J, j0); st_stream4(J + Npad, j1); st_stream4(J + 2 * Npad, j2); st_stream4(J + 3 * Npad, j3);
+            if (flags & ROME_B200_JACOBIAN) {  // d r1/d l = (dy,-dx)/rho^2 ; d r2/d l = -d/rho
+                const double i2 = 1.0 / d2, i1 = 1.0 / rng;
+                float* J = P.jac + (size_t)f * 4 * Npad + n;
+                __stcs(J, (float)(dy * i2)); __stcs(J + Npad, (float)(-dx * i2));
+                __stcs(J + 2 * Npad, (float)(-dx * i1)); __stcs(J + 3 * Npad, (float)(-dy * i1));
             }
         }
         if (want_stats) write_stats16(st, P.stats, f, lane);
@@ -374,7 +325,7 @@ struct FamBearingRange {
 };
 
 // =============================================================================================
-// SE(3) families: one particle per lane per iteration (coalesced 4-B lane accesses)
+// SE(3) families: one particle per lane per iteration
 //   stats[32]: 0..5 sum r | 6..26 sum r r' upper triangle (row-major) | 27..29 sum proposal dt |
 //              30 sum |dt|^2 | 31 sum |r|^2
 // =============================================================================================
@@ -413,15 +364,16 @@ __device__ __forceinline__ void sample6(const RowSE3& row, const EvalParams& P, 
 
 struct FamPose3Pose3 {
     using Row = RowSE3;
-    template <bool kSample>
-    static __device__ __forceinline__ void factor(const Row& row, const EvalParams& P, int f, int lane) {
+    static constexpr int D0 = 6, D1 = 6, DM = 6, DR = 6, DFWD = 6, kMinCtas = 1;
+    template <uint32_t kStatic, bool kSample>
+    static __device__ __forceinline__ void factor(const Row& row, const EvalParams& P, const FactorView& V, int f,
+                                                  int lane) {
         const int Npad = P.Npad, N = P.N;
-        const uint32_t flags = P.flags;
-        const float* __restrict__ Pp = P.v0 + (size_t)row.ip * 6 * Npad;
-        const float* __restrict__ Qp = P.v1 + (size_t)row.iq * 6 * Npad;
-        double ap[6], aq[6];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) { ap[i] = P.a0[row.ip * 6 + i]; aq[i] = P.a1[row.iq * 6 + i]; }
+        const uint32_t flags = kStatic ? kStatic : P.flags;
+        const double* ap = reinterpret_cast<const double*>(V.b0);
+        const double* aq = reinterpret_cast<const double*>(V.b1);
+        const float* Pp = reinterpret_cast<const float*>(V.b0 + var_header_bytes(6));
+        const float* Qp = reinterpret_cast<const float*>(V.b1 + var_header_bytes(6));
         const size_t fo = (size_t)f * 6 * Npad;
         const bool want_stats = flags & ROME_B200_STATS;
         float st[32];
@@ -430,10 +382,10 @@ struct FamPose3Pose3 {
         for (int n = lane; n < Npad; n += 32) {
             float p[6], q[6], m[6];
 #pragma unroll
-            for (int i = 0; i < 6; ++i) { p[i] = __ldg(Pp + i * Npad + n); q[i] = __ldg(Qp + i * Npad + n); }
+            for (int i = 0; i < 6; ++i) { p[i] = Pp[i * Npad + n]; q[i] = Qp[i * Npad + n]; }
             if (!kSample) {
 #pragma unroll
-                for (int i = 0; i < 6; ++i) m[i] = __ldcs(P.meas + fo + i * Npad + n);
+                for (int i = 0; i < 6; ++i) m[i] = V.meas[i * Npad + n];
             } else {
                 sample6(row, P, f, n, m);
             }
@@ -462,7 +414,7 @@ struct FamPose3Pose3 {
             }
             if (flags & ROME_B200_RESIDUAL) {
 #pragma unroll
-                for (int i = 0; i < 6; ++i) __stcs(P.res + fo + i * Npad + n, r[i]);
+                for (int i = 0; i < 6; ++i) V.out_res[i * Npad + n] = r[i];
             }
             if (flags & ROME_B200_PROPOSAL_FWD) {  // q = p o Exp(X): coordinates as offsets from q's anchor
                 double ox, oy, oz;
@@ -470,7 +422,7 @@ struct FamPose3Pose3 {
                 const float o[6] = {(float)hx, (float)hy, (float)hz, (float)(ox - aq[3]), (float)(oy - aq[4]),
                                     (float)(oz - aq[5])};
 #pragma unroll
-                for (int i = 0; i < 6; ++i) __stcs(P.prop_fwd + fo + i * Npad + n, o[i]);
+                for (int i = 0; i < 6; ++i) V.out_fwd[i * Npad + n] = o[i];
                 if (want_stats) acc_prop3(st, msk, o[0], o[1], o[2]);
             }
             if (flags & ROME_B200_PROPOSAL_BWD) {  // R_p = R_q Exp(X.w)' ; t_p = t_q - R_p X.t
@@ -496,14 +448,14 @@ struct FamPose3Pose3 {
 
 struct FamPriorPose3 {
     using Row = RowSE3;
-    template <bool kSample>
-    static __device__ __forceinline__ void factor(const Row& row, const EvalParams& P, int f, int lane) {
+    static constexpr int D0 = 6, D1 = 0, DM = 6, DR = 6, DFWD = 6, kMinCtas = 1;
+    template <uint32_t kStatic, bool kSample>
+    static __device__ __forceinline__ void factor(const Row& row, const EvalParams& P, const FactorView& V, int f,
+                                                  int lane) {
         const int Npad = P.Npad, N = P.N;
-        const uint32_t flags = P.flags;
-        const float* __restrict__ Pp = P.v0 + (size_t)row.ip * 6 * Npad;
-        double ap[6];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) ap[i] = P.a0[row.ip * 6 + i];
+        const uint32_t flags = kStatic ? kStatic : P.flags;
+        const double* ap = reinterpret_cast<const double*>(V.b0);
+        const float* Pp = reinterpret_cast<const float*>(V.b0 + var_header_bytes(6));
         const size_t fo = (size_t)f * 6 * Npad;
         const bool want_stats = flags & ROME_B200_STATS;
         float st[32];
@@ -512,10 +464,10 @@ struct FamPriorPose3 {
         for (int n = lane; n < Npad; n += 32) {
             float p[6], m[6];
 #pragma unroll
-            for (int i = 0; i < 6; ++i) p[i] = __ldg(Pp + i * Npad + n);
+            for (int i = 0; i < 6; ++i) p[i] = Pp[i * Npad + n];
             if (!kSample) {
 #pragma unroll
-                for (int i = 0; i < 6; ++i) m[i] = __ldcs(P.meas + fo + i * Npad + n);
+                for (int i = 0; i < 6; ++i) m[i] = V.meas[i * Npad + n];
             } else {
                 sample6(row, P, f, n, m);
             }
@@ -537,13 +489,13 @@ struct FamPriorPose3 {
             }
             if (flags & ROME_B200_RESIDUAL) {
 #pragma unroll
-                for (int i = 0; i < 6; ++i) __stcs(P.res + fo + i * Npad + n, r[i]);
+                for (int i = 0; i < 6; ++i) V.out_res[i * Npad + n] = r[i];
             }
             if (flags & ROME_B200_PROPOSAL_FWD) {  // proposal = the sampled point, offsets from the anchor
                 const float o[6] = {(float)hx, (float)hy, (float)hz, (float)(X[3] - ap[3]), (float)(X[4] - ap[4]),
                                     (float)(X[5] - ap[5])};
 #pragma unroll
-                for (int i = 0; i < 6; ++i) __stcs(P.prop_fwd + fo + i * Npad + n, o[i]);
+                for (int i = 0; i < 6; ++i) V.out_fwd[i * Npad + n] = o[i];
                 if (want_stats) acc_prop3(st, msk, o[0], o[1], o[2]);
             }
         }
@@ -555,107 +507,249 @@ struct FamPriorPose3 {
 };
 
 // =============================================================================================
-// persistent tile loop with TMA-staged factor rows
+// stage layout (shared by host planning and the kernel)
 // =============================================================================================
-template <class Fam, bool kSample>
-__global__ void __launch_bounds__(kThreads) eval_kernel(const __grid_constant__ EvalParams P) {
+struct StageLayout {
+    int rows_off, v0_off, v1_off, meas_off, bytes;
+    int b0, b1, mb;  // bytes of one slot-0 block, slot-1 block, one factor's measurement block
+};
+__host__ __device__ inline StageLayout stage_layout(int ft, int row_bytes, int d0, int d1, int dm, bool sample,
+                                                    int Npad) {
+    StageLayout L;
+    L.b0 = var_block_bytes(d0, Npad);
+    L.b1 = d1 ? var_block_bytes(d1, Npad) : 0;
+    L.mb = sample ? 0 : dm * Npad * 4;
+    L.rows_off = 0;
+    L.v0_off = (ft * row_bytes + 127) / 128 * 128;
+    L.v1_off = L.v0_off + ft * L.b0;
+    L.meas_off = L.v1_off + ft * L.b1;
+    L.bytes = (L.meas_off + ft * L.mb + 127) / 128 * 128;
+    return L;
+}
+constexpr int kBarrierBytes = 128;
+constexpr int kMaxStages = 6;
+
+// =============================================================================================
+// persistent producer/consumer pipeline
+//   smem: [full[], empty[] mbarriers | S input stages | FT per-warp output slices]
+// =============================================================================================
+template <class Fam, uint32_t kStatic, bool kSample, int FT>
+__global__ void __launch_bounds__((FT + 1) * 32, Fam::kMinCtas) eval_kernel(const __grid_constant__ EvalParams P) {
     using Row = typename Fam::Row;
-    __shared__ alignas(128) Row rows[2][kWarpsPerCta];
-    __shared__ alignas(8) uint64_t full[2];
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* empty = full + kMaxStages;
+    unsigned char* stage0 = smem + kBarrierBytes;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nTiles = (P.count + kWarpsPerCta - 1) / kWarpsPerCta;
+    const int S = P.stages;
+    const int nTiles = (P.count + FT - 1) / FT;
+    const StageLayout L = stage_layout(FT, (int)sizeof(Row), Fam::D0, Fam::D1, Fam::DM, kSample, P.Npad);
     const Row* __restrict__ table = reinterpret_cast<const Row*>(P.rows) + P.first;
+    const uint32_t flags = kStatic ? kStatic : P.flags;
 
     if (threadIdx.x == 0) {
-        mbar_init(&full[0], 1);
-        mbar_init(&full[1], 1);
+        for (int s = 0; s < S; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], FT);
+        }
         fence_mbar_init();
     }
     __syncthreads();
-    auto issue = [&](int tile, int buf) {
-        const int nrows = min(kWarpsPerCta, P.count - tile * kWarpsPerCta);
-        const uint32_t bytes = (uint32_t)(nrows * sizeof(Row));
-        mbar_arrive_expect_tx(&full[buf], bytes);
-        tma_load_1d(&rows[buf][0], table + (size_t)tile * kWarpsPerCta, bytes, &full[buf]);
-    };
-    if (threadIdx.x == 0) {
-        if ((int)blockIdx.x < nTiles) issue(blockIdx.x, 0);
-        if ((int)(blockIdx.x + gridDim.x) < nTiles) issue(blockIdx.x + gridDim.x, 1);
-    }
-    int it = 0;
-    for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        mbar_wait(&full[buf], (uint32_t)((it >> 1) & 1));
-        const int fl = tile * kWarpsPerCta + warp;
-        const bool valid = fl < P.count;
-        Row row;
-        if (valid) row = rows[buf][warp];
-        __syncthreads();  // every warp holds its row in registers: the buffer may be refilled
-        if (threadIdx.x == 0) {
-            const int nt = tile + 2 * gridDim.x;
-            if (nt < nTiles) {
+
+    if (warp == FT) {
+        // ---------------- producer warp: lane l gathers the particle blocks of the tile's l-th factor ----------
+        int tile = blockIdx.x;
+        int ip = 0, iq = 0;
+        auto fetch_ids = [&](int t) {
+            const int fl = t * FT + lane;
+            if (lane < FT && fl < P.count) {
+                const int2 ids = __ldg(reinterpret_cast<const int2*>(table + fl));
+                ip = ids.x; iq = ids.y;
+            }
+        };
+        if (tile < nTiles) fetch_ids(tile);
+        for (int it = 0; tile < nTiles; tile += gridDim.x, ++it) {
+            const int s = it % S, round = it / S;
+            const int my_ip = ip, my_iq = iq;
+            const int next = tile + gridDim.x;
+            if (next < nTiles) fetch_ids(next);  // ids of the next tile are in flight while we wait
+            if (round > 0) mbar_wait(&empty[s], (uint32_t)((round - 1) & 1));
+            unsigned char* st = stage0 + (size_t)s * L.bytes;
+            const int nf = min(FT, P.count - tile * FT);
+            if (lane == 0) {
                 fence_proxy_async();
-                issue(nt, buf);
+                mbar_arrive_expect_tx(&full[s], (uint32_t)(nf * ((int)sizeof(Row) + L.b0 + L.b1 + L.mb)));
+                tma_load_1d(st + L.rows_off, table + (size_t)tile * FT, (uint32_t)(nf * sizeof(Row)), &full[s]);
+                if (!kSample)
+                    tma_load_1d(st + L.meas_off, P.meas + (size_t)(P.first + tile * FT) * Fam::DM * P.Npad,
+                                (uint32_t)(nf * L.mb), &full[s]);
+            }
+            __syncwarp();
+            if (lane < nf) {
+                tma_load_1d(st + L.v0_off + lane * L.b0, P.v0 + (size_t)my_ip * L.b0, (uint32_t)L.b0, &full[s]);
+                if (Fam::D1)
+                    tma_load_1d(st + L.v1_off + lane * L.b1, P.v1 + (size_t)my_iq * L.b1, (uint32_t)L.b1, &full[s]);
             }
         }
-        if (valid) Fam::template factor<kSample>(row, P, P.first + fl, lane);
+    } else {
+        // ---------------- consumer warps: warp w owns the tile's w-th factor ----------------------------------
+        float* out = reinterpret_cast<float*>(stage0 + (size_t)S * L.bytes + (size_t)warp * P.out_warp_bytes);
+        const int res_floats = Fam::DR * P.Npad;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x, ++it) {
+            const int s = it % S, round = it / S;
+            mbar_wait(&full[s], (uint32_t)(round & 1));
+            const unsigned char* st = stage0 + (size_t)s * L.bytes;
+            const int fl = tile * FT + warp;
+            if (fl < P.count) {
+                const int f = P.first + fl;
+                const Row row = reinterpret_cast<const Row*>(st + L.rows_off)[warp];
+                FactorView V;
+                V.b0 = st + L.v0_off + warp * L.b0;
+                V.b1 = Fam::D1 ? st + L.v1_off + warp * L.b1 : nullptr;
+                V.meas = kSample ? nullptr : reinterpret_cast<const float*>(st + L.meas_off + (size_t)warp * L.mb);
+                V.out_res = out;
+                V.out_fwd = out + res_floats;
+                if (flags & (ROME_B200_RESIDUAL | ROME_B200_PROPOSAL_FWD)) {
+                    if (lane == 0) tma_store_wait_read();  // the previous tile's rows have left the slice
+                    __syncwarp();
+                }
+                Fam::template factor<kStatic, kSample>(row, P, V, f, lane);
+                if (flags & (ROME_B200_RESIDUAL | ROME_B200_PROPOSAL_FWD)) {
+                    fence_proxy_async();  // generic-proxy writes of the slice -> visible to the bulk-copy engine
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (flags & ROME_B200_RESIDUAL)
+                            tma_store_1d(P.res + (size_t)f * res_floats, V.out_res, (uint32_t)(res_floats * 4));
+                        if (flags & ROME_B200_PROPOSAL_FWD)
+                            tma_store_1d(P.prop_fwd + (size_t)f * Fam::DFWD * P.Npad, V.out_fwd,
+                                         (uint32_t)(Fam::DFWD * P.Npad * 4));
+                        tma_store_commit();
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+        }
+        if (lane == 0) tma_store_wait_all();
     }
 }
 
-template <class Fam>
-static int launch_family(const EvalParams& p, int grid, cudaStream_t s) {
-    if (p.flags & ROME_B200_SAMPLE)
-        eval_kernel<Fam, true><<<grid, kThreads, 0, s>>>(p);
-    else
-        eval_kernel<Fam, false><<<grid, kThreads, 0, s>>>(p);
-    return (int)cudaGetLastError();
+// =============================================================================================
+// host side: launch planning + dispatch
+// =============================================================================================
+struct FamDims {
+    int row_bytes, d0, d1, dm, dr, dfwd;
+};
+static FamDims fam_dims(int family) {
+    switch (family) {
+        case ROME_B200_POSE2POSE2: return {(int)sizeof(RowSE2), 3, 3, 3, 3, 3};
+        case ROME_B200_PRIORPOSE2: return {(int)sizeof(RowSE2), 3, 0, 3, 3, 3};
+        case ROME_B200_BEARINGRANGE: return {(int)sizeof(RowBR), 3, 2, 2, 2, 2};
+        case ROME_B200_POSE3POSE3: return {(int)sizeof(RowSE3), 6, 6, 6, 6, 6};
+        default: return {(int)sizeof(RowSE3), 6, 0, 6, 6, 6};
+    }
 }
 
-int launch_eval(int family, const EvalParams& p, int grid, void* stream) {
+int plan_launch(int family, uint32_t flags, int Npad, int smem_per_sm, int smem_per_cta_max, LaunchPlan* plan) {
+    const FamDims fd = fam_dims(family);
+    const bool sample = (flags & ROME_B200_SAMPLE) != 0;
+    const bool se3 = family == ROME_B200_POSE3POSE3 || family == ROME_B200_PRIORPOSE3;
+    const uint32_t out_flags = flags & ~(ROME_B200_SAMPLE);
+    const int variant = out_flags == kHot1 ? 1 : out_flags == kHot2 ? 2 : 0;
+    // per-warp output slice: residual rows, then forward-proposal rows (generic variant reserves both)
+    const int out_warp = (fd.dr + (variant == 1 ? 0 : fd.dfwd)) * Npad * 4;
+    static const int fts[3] = {8, 2, 1};
+    for (int k = 0; k < 3; ++k) {
+        const int ft = fts[k];
+        const StageLayout L = stage_layout(ft, fd.row_bytes, fd.d0, fd.d1, fd.dm, sample, Npad);
+        // prefer 2 CTAs/SM (register cap of the SE(2) kernels allows it) with >= 3 stages each, else 1 CTA/SM
+        for (int ctas = (se3 ? 1 : 2); ctas >= 1; --ctas) {
+            const int budget = (smem_per_sm / ctas) - 1024;  // 1 KB per CTA is reserved by the system
+            const int cap = budget < smem_per_cta_max ? budget : smem_per_cta_max;
+            int stages = (cap - kBarrierBytes - ft * out_warp) / L.bytes;
+            if (stages > kMaxStages) stages = kMaxStages;
+            const int need = ctas == 2 ? 3 : 2;
+            if (stages >= need) {
+                if (ctas == 2 && stages > 4) stages = 4;
+                plan->ft = ft; plan->variant = ft == 8 ? variant : 0; plan->stages = stages;
+                plan->stage_bytes = L.bytes;
+                plan->out_warp_bytes = (fd.dr + (plan->variant == 1 ? 0 : fd.dfwd)) * Npad * 4;
+                plan->smem_bytes = kBarrierBytes + stages * L.bytes + ft * out_warp;
+                plan->ctas_per_sm = ctas;
+                return 0;
+            }
+        }
+    }
+    return (int)cudaErrorInvalidConfiguration;  // N too large for the shared-memory pipeline
+}
+
+template <class Fam, uint32_t kStatic, bool kSample, int FT>
+static int launch_ft(const EvalParams& p, const LaunchPlan& plan, int grid, cudaStream_t s) {
+    auto k = eval_kernel<Fam, kStatic, kSample, FT>;
+    static int configured[64] = {0};  // per-instantiation, per-device cache of the opt-in shared memory size
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || plan.smem_bytes > configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes);
+        if (e != cudaSuccess) return (int)e;
+        if (dev >= 0 && dev < 64) configured[dev] = plan.smem_bytes;
+    }
+    k<<<grid, (FT + 1) * 32, plan.smem_bytes, s>>>(p);
+    return (int)cudaGetLastError();
+}
+template <class Fam, bool kSample>
+static int launch_sample(const EvalParams& p, const LaunchPlan& plan, int grid, cudaStream_t s) {
+    constexpr uint32_t smp = kSample ? ROME_B200_SAMPLE : 0u;
+    if (plan.ft == 8) {
+        if (plan.variant == 1) return launch_ft<Fam, kHot1 | smp, kSample, 8>(p, plan, grid, s);
+        if (plan.variant == 2) return launch_ft<Fam, kHot2 | smp, kSample, 8>(p, plan, grid, s);
+        return launch_ft<Fam, 0u, kSample, 8>(p, plan, grid, s);
+    }
+    if (plan.ft == 2) return launch_ft<Fam, 0u, kSample, 2>(p, plan, grid, s);
+    if (plan.ft == 1) return launch_ft<Fam, 0u, kSample, 1>(p, plan, grid, s);
+    return (int)cudaErrorInvalidValue;
+}
+template <class Fam>
+static int launch_family(const EvalParams& p, const LaunchPlan& plan, int grid, cudaStream_t s) {
+    return (p.flags & ROME_B200_SAMPLE) ? launch_sample<Fam, true>(p, plan, grid, s)
+                                        : launch_sample<Fam, false>(p, plan, grid, s);
+}
+
+int launch_eval(int family, const EvalParams& p, const LaunchPlan& plan, int grid, void* stream) {
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     switch (family) {
-        case ROME_B200_POSE2POSE2: return launch_family<FamPose2Pose2>(p, grid, s);
-        case ROME_B200_PRIORPOSE2: return launch_family<FamPriorPose2>(p, grid, s);
-        case ROME_B200_BEARINGRANGE: return launch_family<FamBearingRange>(p, grid, s);
-        case ROME_B200_POSE3POSE3: return launch_family<FamPose3Pose3>(p, grid, s);
-        case ROME_B200_PRIORPOSE3: return launch_family<FamPriorPose3>(p, grid, s);
+        case ROME_B200_POSE2POSE2: return launch_family<FamPose2Pose2>(p, plan, grid, s);
+        case ROME_B200_PRIORPOSE2: return launch_family<FamPriorPose2>(p, plan, grid, s);
+        case ROME_B200_BEARINGRANGE: return launch_family<FamBearingRange>(p, plan, grid, s);
+        case ROME_B200_POSE3POSE3: return launch_family<FamPose3Pose3>(p, plan, grid, s);
+        case ROME_B200_PRIORPOSE3: return launch_family<FamPriorPose3>(p, plan, grid, s);
     }
     return (int)cudaErrorInvalidValue;
 }
 
-template <class Fam>
-static int occ_family(bool sample) {
-    int n = 0;
-    cudaError_t e = sample ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, eval_kernel<Fam, true>, kThreads, 0)
-                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, eval_kernel<Fam, false>, kThreads, 0);
-    return e == cudaSuccess ? n : 1;
-}
-int max_resident_ctas(int family, bool sample) {
-    switch (family) {
-        case ROME_B200_POSE2POSE2: return occ_family<FamPose2Pose2>(sample);
-        case ROME_B200_PRIORPOSE2: return occ_family<FamPriorPose2>(sample);
-        case ROME_B200_BEARINGRANGE: return occ_family<FamBearingRange>(sample);
-        case ROME_B200_POSE3POSE3: return occ_family<FamPose3Pose3>(sample);
-        case ROME_B200_PRIORPOSE3: return occ_family<FamPriorPose3>(sample);
-    }
-    return 1;
-}
-
 // =============================================================================================
-// layout conversion: reference layout (Float64 particle-major [var][N][d]) <-> anchored float32 SoA
-// one warp per variable; anchor = first particle; heading offsets (wrap_dim) wrapped to (-pi, pi]
+// layout conversion: reference layout (Float64 particle-major [var][N][d]) <-> particle store blocks
+// one warp per variable; anchor = first particle; heading offsets (wrap_dim) wrapped to [-pi, pi]
 // =============================================================================================
 template <int D>
 __global__ void pack_kernel(int nvars, int N, int Npad, int wrap_dim, const double* __restrict__ coords,
-                            float* __restrict__ offsets, double* __restrict__ anchors) {
+                            unsigned char* __restrict__ store) {
     const int v = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (v >= nvars) return;
     const double* src = coords + (size_t)v * N * D;
+    unsigned char* blk = store + (size_t)v * var_block_bytes(D, Npad);
     double a[D];
 #pragma unroll
     for (int c = 0; c < D; ++c) a[c] = src[c];
-    if (lane < D) anchors[(size_t)v * D + lane] = src[lane];
-    float* dst = offsets + (size_t)v * D * Npad;
+    double* hdr = reinterpret_cast<double*>(blk);
+    if (lane < var_header_bytes(D) / 8) {
+        double h = lane < D ? src[lane] : 0.0;
+        if (wrap_dim >= 0 && lane == D) h = cos(src[wrap_dim]);      // Pose2 header: {x, y, theta, cos, sin, 0}
+        if (wrap_dim >= 0 && lane == D + 1) h = sin(src[wrap_dim]);
+        hdr[lane] = h;
+    }
+    float* dst = reinterpret_cast<float*>(blk + var_header_bytes(D));
     for (int n = lane; n < Npad; n += 32) {
 #pragma unroll
         for (int c = 0; c < D; ++c) {
@@ -669,53 +763,56 @@ __global__ void pack_kernel(int nvars, int N, int Npad, int wrap_dim, const doub
     }
 }
 template <int D>
-__global__ void unpack_kernel(int nvars, int N, int Npad, int wrap_dim, const float* __restrict__ offsets,
-                              const double* __restrict__ anchors, double* __restrict__ coords) {
+__global__ void unpack_kernel(int nvars, int N, int Npad, int wrap_dim, const unsigned char* __restrict__ store,
+                              double* __restrict__ coords) {
     const int v = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (v >= nvars) return;
-    const float* src = offsets + (size_t)v * D * Npad;
+    const unsigned char* blk = store + (size_t)v * var_block_bytes(D, Npad);
+    const double* hdr = reinterpret_cast<const double*>(blk);
+    const float* src = reinterpret_cast<const float*>(blk + var_header_bytes(D));
     double* dst = coords + (size_t)v * N * D;
     for (int n = lane; n < N; n += 32) {
 #pragma unroll
         for (int c = 0; c < D; ++c) {
-            double x = anchors[(size_t)v * D + c] + (double)src[(size_t)c * Npad + n];
+            double x = hdr[c] + (double)src[(size_t)c * Npad + n];
             if (c == wrap_dim) x = wrap_pi(x);
             dst[(size_t)n * D + c] = x;
         }
     }
 }
-__global__ void adopt_kernel(int d, int Npad, float* __restrict__ offsets, int var, const float* __restrict__ prop,
-                             int factor) {
+__global__ void adopt_kernel(int d, int Npad, unsigned char* __restrict__ store, int var,
+                             const float* __restrict__ prop, int factor) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < d * Npad) offsets[(size_t)var * d * Npad + i] = prop[(size_t)factor * d * Npad + i];
+    float* dst = reinterpret_cast<float*>(store + (size_t)var * var_block_bytes(d, Npad) + var_header_bytes(d));
+    if (i < d * Npad) dst[i] = prop[(size_t)factor * d * Npad + i];
 }
 
-int launch_pack(int d, int wrap_dim, int nvars, int N, int Npad, const double* coords, float* offsets, double* anchors,
+int launch_pack(int d, int wrap_dim, int nvars, int N, int Npad, const double* coords, unsigned char* store,
                 void* stream) {
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int grid = (nvars + 7) / 8;
     if (nvars == 0) return 0;
-    if (d == 3) pack_kernel<3><<<grid, 256, 0, s>>>(nvars, N, Npad, wrap_dim, coords, offsets, anchors);
-    else if (d == 2) pack_kernel<2><<<grid, 256, 0, s>>>(nvars, N, Npad, wrap_dim, coords, offsets, anchors);
-    else if (d == 6) pack_kernel<6><<<grid, 256, 0, s>>>(nvars, N, Npad, wrap_dim, coords, offsets, anchors);
+    if (d == 3) pack_kernel<3><<<grid, 256, 0, s>>>(nvars, N, Npad, wrap_dim, coords, store);
+    else if (d == 2) pack_kernel<2><<<grid, 256, 0, s>>>(nvars, N, Npad, wrap_dim, coords, store);
+    else if (d == 6) pack_kernel<6><<<grid, 256, 0, s>>>(nvars, N, Npad, wrap_dim, coords, store);
     else return (int)cudaErrorInvalidValue;
     return (int)cudaGetLastError();
 }
-int launch_unpack(int d, int wrap_dim, int nvars, int N, int Npad, const float* offsets, const double* anchors,
-                  double* coords, void* stream) {
+int launch_unpack(int d, int wrap_dim, int nvars, int N, int Npad, const unsigned char* store, double* coords,
+                  void* stream) {
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int grid = (nvars + 7) / 8;
     if (nvars == 0) return 0;
-    if (d == 3) unpack_kernel<3><<<grid, 256, 0, s>>>(nvars, N, Npad, wrap_dim, offsets, anchors, coords);
-    else if (d == 2) unpack_kernel<2><<<grid, 256, 0, s>>>(nvars, N, Npad, wrap_dim, offsets, anchors, coords);
-    else if (d == 6) unpack_kernel<6><<<grid, 256, 0, s>>>(nvars, N, Npad, wrap_dim, offsets, anchors, coords);
+    if (d == 3) unpack_kernel<3><<<grid, 256, 0, s>>>(nvars, N, Npad, wrap_dim, store, coords);
+    else if (d == 2) unpack_kernel<2><<<grid, 256, 0, s>>>(nvars, N, Npad, wrap_dim, store, coords);
+    else if (d == 6) unpack_kernel<6><<<grid, 256, 0, s>>>(nvars, N, Npad, wrap_dim, store, coords);
     else return (int)cudaErrorInvalidValue;
     return (int)cudaGetLastError();
 }
-int launch_adopt(int d, int Npad, float* offsets, int var, const float* prop, int factor, void* stream) {
+int launch_adopt(int d, int Npad, unsigned char* store, int var, const float* prop, int factor, void* stream) {
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int n = d * Npad;
-    adopt_kernel<<<(n + 255) / 256, 256, 0, s>>>(d, Npad, offsets, var, prop, factor);
+    adopt_kernel<<<(n + 255) / 256, 256, 0, s>>>(d, Npad, store, var, prop, factor);
     return (int)cudaGetLastError();
 }
 

@@ -18,9 +18,8 @@ namespace {
 
 struct VarStore {
     int nvars = 0, N = 0, Npad = 0;
-    float* off = nullptr;
-    double* anchors = nullptr;
-    size_t cap_off = 0, cap_anchor = 0;  // bytes
+    unsigned char* store = nullptr;  // nvars blocks of var_block_bytes(d, Npad): {anchor f64[d] (padded), d rows x Npad f32}
+    size_t cap = 0;                  // bytes
 };
 struct FactorStore {
     int nF = 0;
@@ -58,7 +57,7 @@ struct rome_b200_ctx {
     std::string err;
     VarStore vars[ROME_B200_NVARTYPES];
     FactorStore fac[ROME_B200_NFAMILIES];
-    int occ[ROME_B200_NFAMILIES][2];
+    int smem_per_sm = 0, smem_per_cta_max = 0;
     Scratch stage_dev, stage_host;            // particle upload/download staging
     Scratch out_dev[8];                       // eval_host device mirrors: meas, meas_out, res, fwd, bwd, stats, jac
     std::vector<cudaGraphExec_t> graphs;
@@ -203,14 +202,14 @@ int rome_b200_create(int device, rome_b200_ctx** out) {
         return fail(nullptr, ROME_B200_CUDA_ERROR, std::string("context creation: ") + cudaGetErrorString(e));
     }
     ctx->stream = ctx->own_stream;
-    for (int f = 0; f < ROME_B200_NFAMILIES; ++f)
-        for (int s = 0; s < 2; ++s) ctx->occ[f][s] = max_resident_ctas(f, s != 0);
-    if ((e = cudaGetLastError()) != cudaSuccess) {
-        // e.g. no kernel image for this device: the library is built for sm_100a only
+    int cc_major = 0;
+    cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, device);
+    cudaDeviceGetAttribute(&ctx->smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
+    cudaDeviceGetAttribute(&ctx->smem_per_cta_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    if (cc_major != 10) {  // the library carries sm_100a code only (TMA bulk copies, mbarrier pipeline)
         cudaStreamDestroy(ctx->own_stream);
         delete ctx;
-        return fail(nullptr, ROME_B200_CUDA_ERROR, std::string("kernel image unusable on this device: ") +
-                                                       cudaGetErrorString(e));
+        return fail(nullptr, ROME_B200_NO_DEVICE, "device is not sm_100 (B200): librome_b200 is built for sm_100a only");
     }
     *out = ctx;
     return ROME_B200_OK;
@@ -221,7 +220,7 @@ int rome_b200_destroy(rome_b200_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto g : ctx->graphs) cudaGraphExecDestroy(g);
-    for (auto& v : ctx->vars) { cudaFree(v.off); cudaFree(v.anchors); }
+    for (auto& v : ctx->vars) cudaFree(v.store);
     for (auto& f : ctx->fac) cudaFree(f.rows);
     cudaFree(ctx->stage_dev.p);
     cudaFreeHost(ctx->stage_host.p);
@@ -269,19 +268,12 @@ int rome_b200_set_particles(rome_b200_ctx* ctx, int vartype, int nvars, int N, c
     if (int e = bind(ctx)) return e;
     const int d = kVarDim[vartype], Npad = rome_b200_npad(N);
     VarStore& vs = ctx->vars[vartype];
-    const size_t off_bytes = (size_t)nvars * d * Npad * sizeof(float);
-    const size_t anc_bytes = (size_t)nvars * d * sizeof(double);
-    if (off_bytes > vs.cap_off) {
-        if (vs.off) CK(cudaFree(vs.off));
-        vs.off = nullptr; vs.cap_off = 0;
-        CK(cudaMalloc(&vs.off, off_bytes));
-        vs.cap_off = off_bytes;
-    }
-    if (anc_bytes > vs.cap_anchor) {
-        if (vs.anchors) CK(cudaFree(vs.anchors));
-        vs.anchors = nullptr; vs.cap_anchor = 0;
-        CK(cudaMalloc(&vs.anchors, anc_bytes));
-        vs.cap_anchor = anc_bytes;
+    const size_t store_bytes = (size_t)nvars * var_block_bytes(d, Npad);
+    if (store_bytes > vs.cap) {
+        if (vs.store) CK(cudaFree(vs.store));
+        vs.store = nullptr; vs.cap = 0;
+        CK(cudaMalloc(&vs.store, store_bytes));
+        vs.cap = store_bytes;
     }
     vs.nvars = nvars; vs.N = N; vs.Npad = Npad;
     if (nvars == 0) return ROME_B200_OK;
@@ -295,8 +287,8 @@ int rome_b200_set_particles(rome_b200_ctx* ctx, int vartype, int nvars, int N, c
         src = ctx->stage_host.p;
     }
     CK(cudaMemcpyAsync(ctx->stage_dev.p, src, in_bytes, cudaMemcpyDefault, ctx->stream));
-    int e = launch_pack(d, kWrapDim[vartype], nvars, N, Npad, static_cast<const double*>(ctx->stage_dev.p), vs.off,
-                        vs.anchors, ctx->stream);
+    int e = launch_pack(d, kWrapDim[vartype], nvars, N, Npad, static_cast<const double*>(ctx->stage_dev.p), vs.store,
+                        ctx->stream);
     if (e) return cuda_fail(ctx, (cudaError_t)e, "pack kernel");
     return ROME_B200_OK;
 }
@@ -310,7 +302,7 @@ int rome_b200_get_particles(rome_b200_ctx* ctx, int vartype, double* coords_host
     const int d = kVarDim[vartype];
     const size_t bytes = (size_t)vs.nvars * vs.N * d * sizeof(double);
     if (int e = grow_dev(ctx, ctx->stage_dev, bytes)) return e;
-    int e = launch_unpack(d, kWrapDim[vartype], vs.nvars, vs.N, vs.Npad, vs.off, vs.anchors,
+    int e = launch_unpack(d, kWrapDim[vartype], vs.nvars, vs.N, vs.Npad, vs.store,
                           static_cast<double*>(ctx->stage_dev.p), ctx->stream);
     if (e) return cuda_fail(ctx, (cudaError_t)e, "unpack kernel");
     CK(cudaMemcpyAsync(coords_host, ctx->stage_dev.p, bytes, cudaMemcpyDefault, ctx->stream));
@@ -318,14 +310,15 @@ int rome_b200_get_particles(rome_b200_ctx* ctx, int vartype, double* coords_host
     return ROME_B200_OK;
 }
 
-int rome_b200_particles_device(rome_b200_ctx* ctx, int vartype, float** d_offsets, double** d_anchors, int* nvars,
-                               int* N, int* Npad) {
+int rome_b200_particles_device(rome_b200_ctx* ctx, int vartype, void** d_store, int* block_bytes, int* header_bytes,
+                               int* nvars, int* N, int* Npad) {
     if (!ctx) return ROME_B200_BAD_ARG;
     if (vartype < 0 || vartype >= ROME_B200_NVARTYPES) return fail(ctx, ROME_B200_BAD_ARG, "bad vartype");
     VarStore& vs = ctx->vars[vartype];
     if (vs.nvars == 0) return fail(ctx, ROME_B200_NOT_SET, "particles of this variable type are not set");
-    if (d_offsets) *d_offsets = vs.off;
-    if (d_anchors) *d_anchors = vs.anchors;
+    if (d_store) *d_store = vs.store;
+    if (block_bytes) *block_bytes = var_block_bytes(kVarDim[vartype], vs.Npad);
+    if (header_bytes) *header_bytes = var_header_bytes(kVarDim[vartype]);
     if (nvars) *nvars = vs.nvars;
     if (N) *N = vs.N;
     if (Npad) *Npad = vs.Npad;
@@ -339,7 +332,7 @@ int rome_b200_adopt_proposal(rome_b200_ctx* ctx, int vartype, int var, const flo
     VarStore& vs = ctx->vars[vartype];
     if (var < 0 || var >= vs.nvars) return fail(ctx, ROME_B200_BAD_ARG, "variable index out of range");
     if (int e = bind(ctx)) return e;
-    int e = launch_adopt(kVarDim[vartype], vs.Npad, vs.off, var, d_prop, factor, ctx->stream);
+    int e = launch_adopt(kVarDim[vartype], vs.Npad, vs.store, var, d_prop, factor, ctx->stream);
     if (e) return cuda_fail(ctx, (cudaError_t)e, "adopt kernel");
     if (ctx->capturing) ctx->capture_kernels++; else ctx->launches++;
     return ROME_B200_OK;
@@ -372,12 +365,12 @@ int rome_b200_set_factors_bearingrange(rome_b200_ctx* ctx, int nF, const int32_t
     int m0 = -1, m1 = -1;
     for (int f = 0; f < nF; ++f) {
         RowBR& r = rows[f];
-        r.ip = ip[f]; r.il = il[f];
-        if (r.ip < 0 || r.il < 0) return fail(ctx, ROME_B200_BAD_ARG, "negative variable index");
+        r.ip = ip[f]; r.iq = il[f];
+        if (r.ip < 0 || r.iq < 0) return fail(ctx, ROME_B200_BAD_ARG, "negative variable index");
         if (!(bearing[2 * f + 1] > 0.0) || !(range[2 * f + 1] > 0.0))
             return fail(ctx, ROME_B200_BAD_ARG, "standard deviation must be positive");
         if (r.ip > m0) m0 = r.ip;
-        if (r.il > m1) m1 = r.il;
+        if (r.iq > m1) m1 = r.iq;
         r.mu_b = bearing[2 * f]; r.sig_b = (float)bearing[2 * f + 1];
         r.mu_r = range[2 * f]; r.sig_r = (float)range[2 * f + 1];
     }
@@ -413,6 +406,11 @@ static int check_eval(rome_b200_ctx* ctx, int family, uint32_t flags, int first,
         return fail(ctx, ROME_B200_BAD_ARG, "WRITE_MEAS needs SAMPLE and meas_out");
     if ((flags & ROME_B200_RESIDUAL) && !b->res) return fail(ctx, ROME_B200_BAD_ARG, "res is NULL");
     if ((flags & ROME_B200_PROPOSAL_FWD) && !b->prop_fwd) return fail(ctx, ROME_B200_BAD_ARG, "prop_fwd is NULL");
+    // meas / res / prop_fwd rows move through 1-D TMA bulk copies: 16-byte alignment is required
+    if (((flags & ROME_B200_RESIDUAL) && ((uintptr_t)b->res & 15)) ||
+        ((flags & ROME_B200_PROPOSAL_FWD) && ((uintptr_t)b->prop_fwd & 15)) ||
+        (!(flags & ROME_B200_SAMPLE) && ((uintptr_t)b->meas & 15)))
+        return fail(ctx, ROME_B200_BAD_ARG, "meas, res and prop_fwd must be 16-byte aligned");
     if (flags & ROME_B200_PROPOSAL_BWD) {
         if (fi.dbwd == 0) return fail(ctx, ROME_B200_BAD_ARG, "this family has no closed-form backward proposal");
         if (!b->prop_bwd) return fail(ctx, ROME_B200_BAD_ARG, "prop_bwd is NULL");
@@ -437,15 +435,19 @@ int rome_b200_eval(rome_b200_ctx* ctx, int family, uint32_t flags, uint64_t seed
     p.rows = ctx->fac[family].rows;
     p.first = first; p.count = count;
     p.N = v0.N; p.Npad = v0.Npad;
-    p.v0 = v0.off; p.a0 = v0.anchors; p.v1 = v1.off; p.a1 = v1.anchors;
+    p.v0 = v0.store; p.v1 = v1.store;
     p.meas = b->meas; p.meas_out = b->meas_out; p.res = b->res; p.prop_fwd = b->prop_fwd; p.prop_bwd = b->prop_bwd;
     p.stats = b->stats; p.jac = b->jac;
     p.flags = flags;
     p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32); p.stream_id = stream_id;
-    const int nTiles = (count + kWarpsPerCta - 1) / kWarpsPerCta;
-    const int resident = ctx->num_sms * ctx->occ[family][(flags & ROME_B200_SAMPLE) ? 1 : 0];
+    LaunchPlan plan;
+    if (plan_launch(family, flags, v0.Npad, ctx->smem_per_sm, ctx->smem_per_cta_max, &plan))
+        return fail(ctx, ROME_B200_SHAPE_MISMATCH, "N is too large for the shared-memory pipeline of this family");
+    p.stages = plan.stages; p.stage_bytes = plan.stage_bytes; p.out_warp_bytes = plan.out_warp_bytes;
+    const int nTiles = (count + plan.ft - 1) / plan.ft;
+    const int resident = ctx->num_sms * plan.ctas_per_sm;
     const int grid = nTiles < resident ? nTiles : resident;
-    int e = launch_eval(family, p, grid, ctx->stream);
+    int e = launch_eval(family, p, plan, grid, ctx->stream);
     if (e) return cuda_fail(ctx, (cudaError_t)e, "eval kernel launch");
     if (ctx->capturing) ctx->capture_kernels++; else ctx->launches++;
     return ROME_B200_OK;

@@ -1,7 +1,9 @@
-// tables.h -- per-factor table rows (AoS, sized/aligned for 1-D TMA bulk copies) and the kernel
-// parameter block shared by the host API (rome_b200_api.cu) and the kernels (factor_kernels.cu).
+// tables.h -- per-factor table rows (AoS, sized/aligned for 1-D TMA bulk copies), the particle-store
+// block layout and the kernel parameter block shared by the host API (rome_b200_api.cu) and the
+// kernels (factor_kernels.cu).
 #pragma once
 
+#include <stddef.h>
 #include <stdint.h>
 
 namespace rome {
@@ -18,7 +20,7 @@ static_assert(sizeof(RowSE2) == 64, "RowSE2 must be 64 B");
 
 // Pose2Point2BearingRange: Normal(mu_b, sig_b), Normal(mu_r, sig_r). src/factors/BearingRange2D.jl:10-13
 struct alignas(32) RowBR {
-    int32_t ip, il;
+    int32_t ip, iq;  // iq = landmark index
     double mu_b, mu_r;
     float sig_b, sig_r;
 };
@@ -33,14 +35,21 @@ struct alignas(32) RowSE3 {
 };
 static_assert(sizeof(RowSE3) == 160, "RowSE3 must be 160 B");
 
+// Particle store: one contiguous BLOCK per variable so that a single 1-D TMA bulk copy brings a whole
+// variable (anchor + all particles) into shared memory:
+//     [ anchor: d doubles, padded to a multiple of 16 B ][ d rows x Npad float32 offsets ]
+//   Pose2 (d=3): anchor = {x, y, theta, cos(theta), sin(theta), 0}  (48 B; the heading's cos/sin are computed once
+//                when the particles are packed so the kernels only evaluate small-angle polynomials)
+//   Point2 (d=2): {x, y} (16 B);  Pose3 (d=6): {x, y, z, wx, wy, wz} (48 B)
+__host__ __device__ inline int var_header_bytes(int d) { return d == 2 ? 16 : 48; }
+__host__ __device__ inline int var_block_bytes(int d, int Npad) { return var_header_bytes(d) + d * Npad * 4; }
+
 struct EvalParams {
     const void* rows;  // factor table (device)
     int first, count;  // factor range [first, first+count)
     int N, Npad;
-    const float* v0;  // offsets of the first variable's type  [nvars][d][Npad]
-    const double* a0; // anchors                                  [nvars][d]
-    const float* v1;  // second variable's type (may alias v0)
-    const double* a1;
+    const unsigned char* v0;  // particle store of the first variable's type
+    const unsigned char* v1;  // second variable's type (may alias v0; unused for priors)
     const float* meas;
     float* meas_out;
     float* res;
@@ -50,18 +59,28 @@ struct EvalParams {
     float* jac;
     uint32_t flags;
     uint32_t seed_lo, seed_hi, stream_id;
+    int stages;          // pipeline depth
+    int stage_bytes;     // shared memory per stage
+    int out_warp_bytes;  // shared-memory output staging per consumer warp (residual rows [+ forward proposal rows])
 };
 
-constexpr int kWarpsPerCta = 8;        // one factor per warp per tile
-constexpr int kThreads = kWarpsPerCta * 32;
+// launch geometry chosen on the host for (family, sample, Npad)
+struct LaunchPlan {
+    int ft;           // factors per tile == consumer warps per CTA (8, 2 or 1)
+    int variant;      // 0: runtime flags; 1: RESIDUAL|STATS; 2: RESIDUAL|STATS|PROPOSAL_FWD (compile-time flags)
+    int stages;
+    int stage_bytes;
+    int out_warp_bytes;
+    int smem_bytes;   // dynamic shared memory per CTA
+    int ctas_per_sm;
+};
 
-// launchers (factor_kernels.cu); return cudaError_t as int
-int launch_eval(int family, const EvalParams& p, int grid, void* stream);
-int launch_pack(int d, int wrap_dim, int nvars, int N, int Npad, const double* coords, float* offsets,
-                double* anchors, void* stream);
-int launch_unpack(int d, int wrap_dim, int nvars, int N, int Npad, const float* offsets, const double* anchors,
-                  double* coords, void* stream);
-int launch_adopt(int d, int Npad, float* offsets, int var, const float* prop, int factor, void* stream);
-int max_resident_ctas(int family, bool sample);
+int plan_launch(int family, uint32_t flags, int Npad, int smem_per_sm, int smem_per_cta_max, LaunchPlan* plan);
+int launch_eval(int family, const EvalParams& p, const LaunchPlan& plan, int grid, void* stream);
+int launch_pack(int d, int wrap_dim, int nvars, int N, int Npad, const double* coords, unsigned char* store,
+                void* stream);
+int launch_unpack(int d, int wrap_dim, int nvars, int N, int Npad, const unsigned char* store, double* coords,
+                  void* stream);
+int launch_adopt(int d, int Npad, unsigned char* store, int var, const float* prop, int factor, void* stream);
 
 }  // namespace rome

@@ -112,29 +112,37 @@ class Context:
         self._keep = coords  # keep alive until the async copy is consumed
 
     def get_particles(self, vartype: int) -> np.ndarray:
-        _, _, nvars, N, _ = self.particles_device(vartype)
+        nvars, N = self.particles_device(vartype)[3:5]
         out = np.empty((nvars, N, VAR_DIM[vartype]))
         self._ck(self._lib.rome_b200_get_particles(self._h, vartype, out.ctypes.data))
         return out
 
     def particles_device(self, vartype: int):
-        po, pa = C.c_void_p(), C.c_void_p()
-        nv, N, Np = C.c_int(), C.c_int(), C.c_int()
-        self._ck(self._lib.rome_b200_particles_device(self._h, vartype, C.byref(po), C.byref(pa), C.byref(nv),
-                                                      C.byref(N), C.byref(Np)))
-        return po.value, pa.value, nv.value, N.value, Np.value
+        """(store pointer, block bytes, header bytes, nvars, N, Npad) of the device particle store"""
+        ps = C.c_void_p()
+        bb, hb, nv, N, Np = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        self._ck(self._lib.rome_b200_particles_device(self._h, vartype, C.byref(ps), C.byref(bb), C.byref(hb),
+                                                      C.byref(nv), C.byref(N), C.byref(Np)))
+        return ps.value, bb.value, hb.value, nv.value, N.value, Np.value
+
+    def _store_bytes(self, vartype: int):
+        ps, bb, hb, nvars, N, Np = self.particles_device(vartype)
+        self.synchronize()
+        raw = np.empty((nvars, bb), dtype=np.uint8)
+        self._ck(self._lib.rome_b200_memcpy_d2h(self._h, raw.ctypes.data, ps, raw.nbytes))
+        return raw, hb, Np
 
     def get_anchors(self, vartype: int) -> np.ndarray:
-        _, pa, nvars, _, _ = self.particles_device(vartype)
-        out = np.empty((nvars, VAR_DIM[vartype]))
-        self._ck(self._lib.rome_b200_memcpy_d2h(self._h, out.ctypes.data, pa, out.nbytes))
-        return out
+        """Float64 anchors [nvars][d] read back from the device store"""
+        raw, hb, _ = self._store_bytes(vartype)
+        d = VAR_DIM[vartype]
+        return np.ascontiguousarray(raw[:, :d * 8]).view(np.float64).reshape(-1, d).copy()
 
     def get_offsets(self, vartype: int) -> np.ndarray:
-        po, _, nvars, _, Np = self.particles_device(vartype)
-        out = np.empty((nvars, VAR_DIM[vartype], Np), dtype=np.float32)
-        self._ck(self._lib.rome_b200_memcpy_d2h(self._h, out.ctypes.data, po, out.nbytes))
-        return out
+        """float32 offsets [nvars][d][Npad] read back from the device store"""
+        raw, hb, Np = self._store_bytes(vartype)
+        d = VAR_DIM[vartype]
+        return np.ascontiguousarray(raw[:, hb:]).view(np.float32).reshape(-1, d, Np).copy()
 
     def adopt_proposal(self, vartype: int, var: int, d_prop, factor: int):
         self._ck(self._lib.rome_b200_adopt_proposal(self._h, vartype, var, _ptr(d_prop), factor))
@@ -195,7 +203,7 @@ class Context:
         """numpy float32 output arrays, shaped for all factors of the family, for eval_host."""
         vt0, _, dm, dr, ns, dj, dfwd, dbwd = FAMILY[family]
         nF = self.num_factors(family)
-        Np = self.particles_device(vt0)[4]
+        Np = self.particles_device(vt0)[5]
         out = {}
         if flags & WRITE_MEAS:
             out["meas_out"] = np.zeros((nF, dm, Np), np.float32)

@@ -50,10 +50,16 @@ def test_known_answers_bearingrange(ka):
 
 def test_known_answers_pose3pose3(ka):
     """test/testPartialPose3.jl:398-436, test/threeDimLinearProductTest.jl:150-167 (incl. [pi,pi,pi])"""
+    # the factor mean is 0 here while the tested measurement is (10, .., pi, pi, pi): the measurement offset from
+    # the mean is stored as float32, so pi carries float32 rounding (8.7e-8 per component)
     f = rb.Pose3Pose3()
     for c in ka["pose3pose3"]:
         r = rb.calcFactorResidualTemporary(f, (rb.Pose3, rb.Pose3), c["X"], (c["p"], c["q"]))
-        _check(r, c, 1e-7)
+        _check(r, c, 5e-7)
+        # with the factor mean AT the measurement the offset is exactly 0 and the residual is float32-exact
+        g = rb.Pose3Pose3(rb.MvNormal(c["X"], np.diag([0.01] * 3 + [1e-4] * 3)))
+        r = rb.calcFactorResidualTemporary(g, (rb.Pose3, rb.Pose3), c["X"], (c["p"], c["q"]))
+        _check(r, c, 1e-12)
 
 
 def test_priors_zero_at_measurement():

@@ -92,7 +92,7 @@ def test_pose2pose2_parity(ctx, N):
     assert_close(res, ref, angle_cols=(2,), what="pose2pose2 residual (B)")
     ref_same = O.sweep_pose2pose2(ip, iq, seen(ctx, rb.POSE2, N), seen_meas(moff, mu, N))
     assert_close(res, ref_same, angle_cols=(2,), what="pose2pose2 residual (A)", floor=FLOOR_SAME)
-    assert np.abs(ref).max() < 2.0  # residuals are small: the comparison is a relative one
+    assert np.abs(ref).max() < 5.0  # residuals are small: the comparison is a relative one
     # proposals are roots of the residual
     anchors = ctx.get_anchors(rb.POSE2)
     fwd = rb.rows_to_particle_major(out["prop_fwd"], N) + anchors[iq][:, None, :]
