@@ -253,13 +253,13 @@ def main():
             c.set_particles(rb.POSE2, w["poses"] + (1e-4 * s))
             c.set_factors_pose2pose2(w["ip"], w["iq"], w["mu"], w["cov"])
             c.set_factors_priorpose2(w["pr_ip"], w["pr_mu"], w["pr_cov"])
-            bufs = dict(res=torch.zeros((F, 3, Np), device="cuda"), stats=torch.zeros((F, 16), device="cuda"))
+            bufs = dict(res=torch.zeros((F, Np, 3), device="cuda"), stats=torch.zeros((F, 16), device="cuda"))
             if multi:
-                bufs["prop_fwd"] = torch.zeros((F, 3, Np), device="cuda")
-            pb = dict(res=torch.zeros((len(w["pr_ip"]), 3, Np), device="cuda"),
+                bufs["prop_fwd"] = torch.zeros((F, Np, 3), device="cuda")
+            pb = dict(res=torch.zeros((len(w["pr_ip"]), Np, 3), device="cuda"),
                       stats=torch.zeros((len(w["pr_ip"]), 16), device="cuda"))
             if multi:
-                pb["prop_fwd"] = torch.zeros((len(w["pr_ip"]), 3, Np), device="cuda")
+                pb["prop_fwd"] = torch.zeros((len(w["pr_ip"]), Np, 3), device="cuda")
             sets.append((c, bufs, pb))
         stream.synchronize()
 
@@ -267,10 +267,18 @@ def main():
     evals_per_step_rank = (F0 + n_prior) * N
     evals_per_step = evals_per_step_rank * G
 
+    side = torch.cuda.Stream()
+
     def step(k):
+        """one pass of the hot path over the graph: the two family kernels have no mutual dependency and run
+        concurrently (fork/join on a side stream, captured into the graph as parallel branches)"""
         c, bufs, pb = sets[k % S]
-        c.eval(rb.POSE2POSE2, flags, seed=7, stream_id=k, first=first, count=F0, **bufs)
+        side.wait_stream(stream)
+        c.set_stream(side.cuda_stream)
         c.eval(rb.PRIORPOSE2, flags, seed=7, stream_id=k, first=rank * n_prior, count=n_prior, **pb)
+        c.set_stream(stream.cuda_stream)
+        c.eval(rb.POSE2POSE2, flags, seed=7, stream_id=k, first=first, count=F0, **bufs)
+        stream.wait_stream(side)
         if multi:  # the one exchange of the path: proposals of every rank's factors to every rank
             dist.all_gather_into_tensor(bufs["prop_fwd"], bufs["prop_fwd"][first:first + F0])
 
@@ -331,7 +339,7 @@ def main():
         kms = k0.elapsed_time(k1) / args.steps
         # same kernel with the measurement supplied from HBM (parity mode, 48 B/eval)
         pflags = rb.RESIDUAL | rb.STATS
-        meas_sets = [torch.randn((F, 3, Np), device="cuda") * 0.05 for _ in range(S)]
+        meas_sets = [torch.randn((F, Np, 3), device="cuda") * 0.05 for _ in range(S)]
         gp = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gp, stream=stream):
             for k in range(args.steps):
@@ -360,9 +368,9 @@ def main():
     c, _, _ = sets[0]
     c.set_stream(None)
     host_poses = torch.from_numpy(w["poses"]).pin_memory()
-    hres = torch.zeros((F, 3, Np), dtype=torch.float32).pin_memory()
+    hres = torch.zeros((F, Np, 3), dtype=torch.float32).pin_memory()
     hstats = torch.zeros((F, 16), dtype=torch.float32).pin_memory()
-    hpres = torch.zeros((len(w["pr_ip"]), 3, Np), dtype=torch.float32).pin_memory()
+    hpres = torch.zeros((len(w["pr_ip"]), Np, 3), dtype=torch.float32).pin_memory()
     hpstats = torch.zeros((len(w["pr_ip"]), 16), dtype=torch.float32).pin_memory()
     eflags = rb.SAMPLE | rb.RESIDUAL | rb.STATS
 

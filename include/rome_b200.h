@@ -30,10 +30,12 @@
  *     `[nvars][N][d]` (DFG `vecval`), d = 3 (Pose2: x,y,theta), 2 (Point2), 6 (Pose3: x,y,z,
  *     rotation vector) -- src/variables/VariableTypes.jl:13,35,47.
  *   - device layout ("anchored float32"): value = anchor(Float64, per variable / per factor
- *     mean) + offset(float32).  Particles: one block per variable {anchor f64[d], d rows x Npad f32};
- *     measurements [nF][dm][Npad] offsets from the factor mean; residuals [nF][dr][Npad]
- *     float32; proposals [nF][dv][Npad] offsets from the TARGET variable's anchor.
- *     Npad = N rounded up to a multiple of 8 (32-byte sectors); padding lanes hold 0.
+ *     mean) + offset(float32).  Every row set is PARTICLE-MAJOR like the reference's arrays:
+ *     particles: one block per variable {anchor header, [Npad][d] float32 offsets};
+ *     measurements [nF][Npad][dm] offsets from the factor mean; residuals [nF][Npad][dr] float32;
+ *     proposals [nF][Npad][dv] offsets from the TARGET variable's anchor; jac [nF][Npad][dj].
+ *     Npad = N rounded up to a multiple of 8; padding particles hold 0 on input and are ignored.
+ *     meas, res and prop_fwd must be 16-byte aligned (they move through 1-D TMA bulk copies).
  *     Arithmetic inside the kernels is Float64.
  */
 #ifndef ROME_B200_H
@@ -89,13 +91,13 @@ enum rome_b200_family {
 /* Buffers of one eval call.  Unused members may be NULL.  `_host` entry points take host
  * pointers with the same shapes; plain entry points take device pointers. */
 typedef struct rome_b200_buffers {
-    const float* meas; /* in : [nF][dm][Npad] offsets from the factor mean (ignored with SAMPLE) */
+    const float* meas; /* in : [nF][Npad][dm] offsets from the factor mean (ignored with SAMPLE) */
     float* meas_out;   /* out: same shape, with SAMPLE|WRITE_MEAS                               */
-    float* res;        /* out: [nF][dr][Npad]                                                   */
-    float* prop_fwd;   /* out: [nF][dv_last][Npad]  offsets from the last variable's anchor      */
-    float* prop_bwd;   /* out: [nF][dv_first][Npad] offsets from the first variable's anchor     */
+    float* res;        /* out: [nF][Npad][dr]                                                   */
+    float* prop_fwd;   /* out: [nF][Npad][dv_last]  offsets from the last variable's anchor      */
+    float* prop_bwd;   /* out: [nF][Npad][dv_first] offsets from the first variable's anchor     */
     float* stats;      /* out: [nF][16] (SE(2) families) or [nF][32] (SE(3) families)            */
-    float* jac;        /* out: [nF][dj][Npad] compact Jacobian entries                           */
+    float* jac;        /* out: [nF][Npad][dj] compact Jacobian entries                           */
 } rome_b200_buffers;
 
 /* ---- life cycle -------------------------------------------------------------------------- */
@@ -119,7 +121,7 @@ ROME_B200_API int rome_b200_npad(int N);
 ROME_B200_API int rome_b200_set_particles(rome_b200_ctx* ctx, int vartype, int nvars, int N, const double* coords_host);
 ROME_B200_API int rome_b200_get_particles(rome_b200_ctx* ctx, int vartype, double* coords_host);
 /* Device view of the particle store (zero-copy interop): nvars contiguous blocks of `block_bytes`, each
- * { anchor: d doubles padded to `header_bytes` }{ d rows x Npad float32 offsets }. */
+ * { anchor header of `header_bytes` (Pose2: x,y,theta,cos,sin) }{ [Npad][d] float32 offsets }. */
 ROME_B200_API int rome_b200_particles_device(rome_b200_ctx* ctx, int vartype, void** d_store, int* block_bytes,
                                              int* header_bytes, int* nvars, int* N, int* Npad);
 /* Replace the particles of variable `var` by proposal row `factor` of a device proposal buffer

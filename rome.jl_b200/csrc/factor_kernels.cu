@@ -117,16 +117,17 @@ constexpr uint32_t kHot1 = ROME_B200_RESIDUAL | ROME_B200_STATS;
 constexpr uint32_t kHot2 = ROME_B200_RESIDUAL | ROME_B200_STATS | ROME_B200_PROPOSAL_FWD;
 
 // =============================================================================================
-// SE(2) families: one particle per lane per iteration (conflict-free 4-B shared-memory accesses).
-// kStatic != 0 fixes the output flags at compile time (hot variants); 0 reads them from P.flags.
+// SE(2) families.  Rows are particle-major ([Npad][d], the reference's own `vecval` order): lane l owns
+// particles l, l+32, l+64, ...; consecutive lanes read consecutive 12-B (8-B) records -> bank-conflict free.
+// The slot loop is unrolled by four: one Philox/Box-Muller batch serves four particles of a lane and the
+// Float64 chains of the four slots interleave.  kStatic != 0 fixes the output flags at compile time.
 // =============================================================================================
-__device__ __forceinline__ void sample3(const RowSE2& row, const EvalParams& P, int f, int n, float& mx, float& my,
-                                        float& mt) {
-    float z[4];
-    normal4(P.seed_lo, P.seed_hi, P.stream_id, (uint32_t)f, (uint32_t)n, 0u, z);
-    mx = row.L[0] * z[0];
-    my = fmaf(row.L[2], z[1], row.L[1] * z[0]);
-    mt = fmaf(row.L[5], z[2], fmaf(row.L[4], z[1], row.L[3] * z[0]));
+// normals for the lane's slots [4g, 4g+4) of factor f: D normals per particle, 4 per Philox call
+template <int D>
+__device__ __forceinline__ void normals_for_group(const EvalParams& P, int f, int lane, int g, float (&z)[4 * D]) {
+#pragma unroll
+    for (int b = 0; b < D; ++b)
+        normal4(P.seed_lo, P.seed_hi, P.stream_id, (uint32_t)f, (uint32_t)lane, (uint32_t)(g * D + b), &z[4 * b]);
 }
 
 struct FamPose2Pose2 {
@@ -150,58 +151,65 @@ struct FamPose2Pose2 {
 #pragma unroll
         for (int i = 0; i < 16; ++i) st[i] = 0.f;
 
-        for (int n = lane; n < Npad; n += 32) {
-            const double dpx = Pp[n], dpy = Pp[Npad + n], dpt = Pp[2 * Npad + n];
-            const double dqx = Qp[n], dqy = Qp[Npad + n], dqt = Qp[2 * Npad + n];
-            float mx, my, mt;
-            if (!kSample) {
-                mx = V.meas[n]; my = V.meas[Npad + n]; mt = V.meas[2 * Npad + n];
-            } else {
-                sample3(row, P, f, n, mx, my, mt);
-                if (flags & ROME_B200_WRITE_MEAS) {
-                    __stcs(P.meas_out + fo + n, mx);
-                    __stcs(P.meas_out + fo + Npad + n, my);
-                    __stcs(P.meas_out + fo + 2 * Npad + n, mt);
+        for (int g = 0, n0 = lane; n0 < Npad; ++g, n0 += 128) {
+            float z[12];
+            if (kSample) normals_for_group<3>(P, f, lane, g, z);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int n = n0 + 32 * k;
+                if (n < Npad) {
+                    const double dpx = Pp[3 * n], dpy = Pp[3 * n + 1], dpt = Pp[3 * n + 2];
+                    const double dqx = Qp[3 * n], dqy = Qp[3 * n + 1], dqt = Qp[3 * n + 2];
+                    float mx, my, mt;
+                    if (!kSample) {
+                        mx = V.meas[3 * n]; my = V.meas[3 * n + 1]; mt = V.meas[3 * n + 2];
+                    } else {
+                        mx = row.L[0] * z[3 * k];
+                        my = fmaf(row.L[2], z[3 * k + 1], row.L[1] * z[3 * k]);
+                        mt = fmaf(row.L[5], z[3 * k + 2], fmaf(row.L[4], z[3 * k + 1], row.L[3] * z[3 * k]));
+                        if (flags & ROME_B200_WRITE_MEAS) {
+                            float* M = P.meas_out + fo + 3 * n;
+                            __stcs(M, mx); __stcs(M + 1, my); __stcs(M + 2, mt);
+                        }
+                    }
+                    const double Xx = mu0 + (double)mx, Xy = mu1 + (double)my, Xt = mu2 + (double)mt;
+                    double s, c;
+                    sincos_anchored(apt, ca, sa, dpt, s, c);
+                    const double rx = c * Xx - s * Xy;  // R(theta_p) X.t
+                    const double ry = s * Xx + c * Xy;
+                    // qhat - q, Pose2D.jl:62-65 ; qhat offsets are relative to q's anchor
+                    const double hx = (dax + dpx) + rx, hy = (day + dpy) + ry;
+                    const double ht = (dat + dpt) + Xt;
+                    const float e1 = (float)(hx - dqx), e2 = (float)(hy - dqy), e3 = (float)wrap_pi(ht - dqt);
+                    const float msk = (n < N) ? 1.f : 0.f;
+                    if (flags & ROME_B200_RESIDUAL) {
+                        V.out_res[3 * n] = e1; V.out_res[3 * n + 1] = e2; V.out_res[3 * n + 2] = e3;
+                    }
+                    if (want_stats) acc_res3(st, msk, e1, e2, e3);
+                    if (flags & ROME_B200_PROPOSAL_FWD) {
+                        const float ox = (float)hx, oy = (float)hy, ot = (float)wrap_pi(ht);
+                        V.out_fwd[3 * n] = ox; V.out_fwd[3 * n + 1] = oy; V.out_fwd[3 * n + 2] = ot;
+                        if (want_stats) { acc_prop2(st, msk, ox, oy); acc_heading(st, msk, ot); }
+                    }
+                    if (flags & ROME_B200_PROPOSAL_BWD) {
+                        // theta_p = theta_q - m_theta ; t_p = t_q - R(theta_p) m_t   (offsets from p's anchor)
+                        const double tb = (dqt - dat) - Xt;  // offset from apt
+                        double sb, cb;
+                        sincos(apt + tb, &sb, &cb);
+                        const float ox = (float)((dqx - dax) - (cb * Xx - sb * Xy));
+                        const float oy = (float)((dqy - day) - (sb * Xx + cb * Xy));
+                        const float ot = (float)wrap_pi(tb);
+                        float* B = P.prop_bwd + fo + 3 * n;
+                        __stcs(B, ox); __stcs(B + 1, oy); __stcs(B + 2, ot);
+                        if (want_stats && !(flags & ROME_B200_PROPOSAL_FWD)) {
+                            acc_prop2(st, msk, ox, oy); acc_heading(st, msk, ot);
+                        }
+                    }
+                    if (flags & ROME_B200_JACOBIAN) {  // d r/d theta_p = (-ry, rx, 1); d r/d m = R(theta_p) (+) 1
+                        float4* J = reinterpret_cast<float4*>(P.jac + ((size_t)f * Npad + n) * 4);
+                        __stcs(J, make_float4((float)(-ry), (float)rx, (float)c, (float)s));
+                    }
                 }
-            }
-            const double Xx = mu0 + (double)mx, Xy = mu1 + (double)my, Xt = mu2 + (double)mt;
-            double s, c;
-            sincos_anchored(apt, ca, sa, dpt, s, c);
-            const double rx = c * Xx - s * Xy;  // R(theta_p) X.t
-            const double ry = s * Xx + c * Xy;
-            // qhat - q, Pose2D.jl:62-65 ; qhat offsets are relative to q's anchor
-            const double hx = (dax + dpx) + rx, hy = (day + dpy) + ry;
-            const double ht = (dat + dpt) + Xt;
-            const float e1 = (float)(hx - dqx), e2 = (float)(hy - dqy), e3 = (float)wrap_pi(ht - dqt);
-            const float msk = (n < N) ? 1.f : 0.f;
-            if (flags & ROME_B200_RESIDUAL) {
-                V.out_res[n] = e1; V.out_res[Npad + n] = e2; V.out_res[2 * Npad + n] = e3;
-            }
-            if (want_stats) acc_res3(st, msk, e1, e2, e3);
-            if (flags & ROME_B200_PROPOSAL_FWD) {
-                const float ox = (float)hx, oy = (float)hy, ot = (float)wrap_pi(ht);
-                V.out_fwd[n] = ox; V.out_fwd[Npad + n] = oy; V.out_fwd[2 * Npad + n] = ot;
-                if (want_stats) { acc_prop2(st, msk, ox, oy); acc_heading(st, msk, ot); }
-            }
-            if (flags & ROME_B200_PROPOSAL_BWD) {
-                // theta_p = theta_q - m_theta ; t_p = t_q - R(theta_p) m_t   (offsets from p's anchor)
-                const double tb = (dqt - dat) - Xt;  // offset from apt
-                double sb, cb;
-                sincos(apt + tb, &sb, &cb);
-                const float ox = (float)((dqx - dax) - (cb * Xx - sb * Xy));
-                const float oy = (float)((dqy - day) - (sb * Xx + cb * Xy));
-                const float ot = (float)wrap_pi(tb);
-                __stcs(P.prop_bwd + fo + n, ox);
-                __stcs(P.prop_bwd + fo + Npad + n, oy);
-                __stcs(P.prop_bwd + fo + 2 * Npad + n, ot);
-                if (want_stats && !(flags & ROME_B200_PROPOSAL_FWD)) {
-                    acc_prop2(st, msk, ox, oy); acc_heading(st, msk, ot);
-                }
-            }
-            if (flags & ROME_B200_JACOBIAN) {  // d r/d theta_p = (-ry, rx, 1); d r/d m = R(theta_p) (+) 1
-                float* J = P.jac + (size_t)f * 4 * Npad + n;
-                __stcs(J, (float)(-ry)); __stcs(J + Npad, (float)rx);
-                __stcs(J + 2 * Npad, (float)c); __stcs(J + 3 * Npad, (float)s);
             }
         }
         if (want_stats) write_stats16(st, P.stats, f, lane);
@@ -226,30 +234,39 @@ struct FamPriorPose2 {
         float st[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) st[i] = 0.f;
-        for (int n = lane; n < Npad; n += 32) {
-            const double dpx = Pp[n], dpy = Pp[Npad + n], dpt = Pp[2 * Npad + n];
-            float mx, my, mt;
-            if (!kSample) {
-                mx = V.meas[n]; my = V.meas[Npad + n]; mt = V.meas[2 * Npad + n];
-            } else {
-                sample3(row, P, f, n, mx, my, mt);
-                if (flags & ROME_B200_WRITE_MEAS) {
-                    __stcs(P.meas_out + fo + n, mx);
-                    __stcs(P.meas_out + fo + Npad + n, my);
-                    __stcs(P.meas_out + fo + 2 * Npad + n, mt);
+        for (int g = 0, n0 = lane; n0 < Npad; ++g, n0 += 128) {
+            float z[12];
+            if (kSample) normals_for_group<3>(P, f, lane, g, z);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int n = n0 + 32 * k;
+                if (n < Npad) {
+                    const double dpx = Pp[3 * n], dpy = Pp[3 * n + 1], dpt = Pp[3 * n + 2];
+                    float mx, my, mt;
+                    if (!kSample) {
+                        mx = V.meas[3 * n]; my = V.meas[3 * n + 1]; mt = V.meas[3 * n + 2];
+                    } else {
+                        mx = row.L[0] * z[3 * k];
+                        my = fmaf(row.L[2], z[3 * k + 1], row.L[1] * z[3 * k]);
+                        mt = fmaf(row.L[5], z[3 * k + 2], fmaf(row.L[4], z[3 * k + 1], row.L[3] * z[3 * k]));
+                        if (flags & ROME_B200_WRITE_MEAS) {
+                            float* M = P.meas_out + fo + 3 * n;
+                            __stcs(M, mx); __stcs(M + 1, my); __stcs(M + 2, mt);
+                        }
+                    }
+                    const double hx = mx0 + (double)mx, hy = my0 + (double)my, ht = mt0 + (double)mt;  // m - anchor
+                    const float e1 = (float)(hx - dpx), e2 = (float)(hy - dpy), e3 = (float)wrap_pi(ht - dpt);
+                    const float msk = (n < N) ? 1.f : 0.f;
+                    if (flags & ROME_B200_RESIDUAL) {
+                        V.out_res[3 * n] = e1; V.out_res[3 * n + 1] = e2; V.out_res[3 * n + 2] = e3;
+                    }
+                    if (want_stats) acc_res3(st, msk, e1, e2, e3);
+                    if (flags & ROME_B200_PROPOSAL_FWD) {
+                        const float ox = (float)hx, oy = (float)hy, ot = (float)wrap_pi(ht);
+                        V.out_fwd[3 * n] = ox; V.out_fwd[3 * n + 1] = oy; V.out_fwd[3 * n + 2] = ot;
+                        if (want_stats) { acc_prop2(st, msk, ox, oy); acc_heading(st, msk, ot); }
+                    }
                 }
-            }
-            const double hx = mx0 + (double)mx, hy = my0 + (double)my, ht = mt0 + (double)mt;  // m - anchor
-            const float e1 = (float)(hx - dpx), e2 = (float)(hy - dpy), e3 = (float)wrap_pi(ht - dpt);
-            const float msk = (n < N) ? 1.f : 0.f;
-            if (flags & ROME_B200_RESIDUAL) {
-                V.out_res[n] = e1; V.out_res[Npad + n] = e2; V.out_res[2 * Npad + n] = e3;
-            }
-            if (want_stats) acc_res3(st, msk, e1, e2, e3);
-            if (flags & ROME_B200_PROPOSAL_FWD) {
-                const float ox = (float)hx, oy = (float)hy, ot = (float)wrap_pi(ht);
-                V.out_fwd[n] = ox; V.out_fwd[Npad + n] = oy; V.out_fwd[2 * Npad + n] = ot;
-                if (want_stats) { acc_prop2(st, msk, ox, oy); acc_heading(st, msk, ot); }
             }
         }
         if (want_stats) write_stats16(st, P.stats, f, lane);
@@ -277,47 +294,51 @@ struct FamBearingRange {
         float st[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) st[i] = 0.f;
-        for (int n = lane; n < Npad; n += 32) {
-            const double dpx = Pp[n], dpy = Pp[Npad + n], dpt = Pp[2 * Npad + n];
-            const double dlx = Lp[n], dly = Lp[Npad + n];
-            float mb, mr;
-            if (!kSample) {
-                mb = V.meas[n]; mr = V.meas[Npad + n];
-            } else {  // two independent scalar draws, BearingRange2D.jl:23
-                float z[4];
-                normal4(P.seed_lo, P.seed_hi, P.stream_id, (uint32_t)f, (uint32_t)n, 0u, z);
-                mb = row.sig_b * z[0];
-                mr = row.sig_r * z[1];
-                if (flags & ROME_B200_WRITE_MEAS) {
-                    __stcs(P.meas_out + fo + n, mb);
-                    __stcs(P.meas_out + fo + Npad + n, mr);
+        for (int g = 0, n0 = lane; n0 < Npad; ++g, n0 += 128) {
+            float z[8];  // two independent scalar draws per particle, BearingRange2D.jl:23
+            if (kSample) normals_for_group<2>(P, f, lane, g, z);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int n = n0 + 32 * k;
+                if (n < Npad) {
+                    const double dpx = Pp[3 * n], dpy = Pp[3 * n + 1], dpt = Pp[3 * n + 2];
+                    const float2 lxy = *reinterpret_cast<const float2*>(Lp + 2 * n);
+                    const double dlx = lxy.x, dly = lxy.y;
+                    float mb, mr;
+                    if (!kSample) {
+                        const float2 m2 = *reinterpret_cast<const float2*>(V.meas + 2 * n);
+                        mb = m2.x; mr = m2.y;
+                    } else {
+                        mb = row.sig_b * z[2 * k];
+                        mr = row.sig_r * z[2 * k + 1];
+                        if (flags & ROME_B200_WRITE_MEAS)
+                            __stcs(reinterpret_cast<float2*>(P.meas_out + fo + 2 * n), make_float2(mb, mr));
+                    }
+                    const double b = row.mu_b + (double)mb, rho = row.mu_r + (double)mr;
+                    const double dx = dax + (dlx - dpx), dy = day + (dly - dpy);
+                    const double th = apt + dpt;
+                    const double d2 = dx * dx + dy * dy;
+                    const double rng = sqrt(d2);
+                    double e1d = wrap_pi(b + th - atan2(dy, dx));
+                    if (fabs(e1d - kPi) <= 1.4901161193847656e-08 * kPi) e1d = -kPi;  // sym_rem: +pi -> -pi
+                    const float e1 = (float)e1d, e2 = (float)(rho - rng);
+                    const float msk = (n < N) ? 1.f : 0.f;
+                    if (flags & ROME_B200_RESIDUAL)
+                        *reinterpret_cast<float2*>(V.out_res + 2 * n) = make_float2(e1, e2);
+                    if (want_stats) acc_res3(st, msk, e1, e2, 0.f);
+                    if (flags & ROME_B200_PROPOSAL_FWD) {  // l = t_p + rho R(theta_p)(cos b, sin b) - anchor(l)
+                        double s, c;
+                        sincos(th + b, &s, &c);
+                        const float ox = (float)((dpx - dax) + rho * c), oy = (float)((dpy - day) + rho * s);
+                        *reinterpret_cast<float2*>(V.out_fwd + 2 * n) = make_float2(ox, oy);
+                        if (want_stats) acc_prop2(st, msk, ox, oy);
+                    }
+                    if (flags & ROME_B200_JACOBIAN) {  // d r1/d l = (dy,-dx)/rho^2 ; d r2/d l = -d/rho
+                        const double i2 = 1.0 / d2, i1 = 1.0 / rng;
+                        float4* J = reinterpret_cast<float4*>(P.jac + ((size_t)f * Npad + n) * 4);
+                        __stcs(J, make_float4((float)(dy * i2), (float)(-dx * i2), (float)(-dx * i1), (float)(-dy * i1)));
+                    }
                 }
-            }
-            const double b = row.mu_b + (double)mb, rho = row.mu_r + (double)mr;
-            const double dx = dax + (dlx - dpx), dy = day + (dly - dpy);
-            const double th = apt + dpt;
-            const double d2 = dx * dx + dy * dy;
-            const double rng = sqrt(d2);
-            double e1d = wrap_pi(b + th - atan2(dy, dx));
-            if (fabs(e1d - kPi) <= 1.4901161193847656e-08 * kPi) e1d = -kPi;  // sym_rem: +pi -> -pi
-            const float e1 = (float)e1d, e2 = (float)(rho - rng);
-            const float msk = (n < N) ? 1.f : 0.f;
-            if (flags & ROME_B200_RESIDUAL) {
-                V.out_res[n] = e1; V.out_res[Npad + n] = e2;
-            }
-            if (want_stats) acc_res3(st, msk, e1, e2, 0.f);
-            if (flags & ROME_B200_PROPOSAL_FWD) {  // l = t_p + rho R(theta_p)(cos b, sin b), offset from l's anchor
-                double s, c;
-                sincos(th + b, &s, &c);
-                const float ox = (float)((dpx - dax) + rho * c), oy = (float)((dpy - day) + rho * s);
-                V.out_fwd[n] = ox; V.out_fwd[Npad + n] = oy;
-                if (want_stats) acc_prop2(st, msk, ox, oy);
-            }
-            if (flags & ROME_B200_JACOBIAN) {  // d r1/d l = (dy,-dx)/rho^2 ; d r2/d l = -d/rho
-                const double i2 = 1.0 / d2, i1 = 1.0 / rng;
-                float* J = P.jac + (size_t)f * 4 * Npad + n;
-                __stcs(J, (float)(dy * i2)); __stcs(J + Npad, (float)(-dx * i2));
-                __stcs(J + 2 * Npad, (float)(-dx * i1)); __stcs(J + 3 * Npad, (float)(-dy * i1));
             }
         }
         if (want_stats) write_stats16(st, P.stats, f, lane);
@@ -343,15 +364,29 @@ __device__ __forceinline__ void acc_res6(float (&st)[32], float m, const float (
     }
     st[31] += n2;
 }
+// 24-B particle-major records: three 8-B accesses (conflict-free per half-warp)
+__device__ __forceinline__ void load6(const float* p, float (&v)[6]) {
+    const float2 a = reinterpret_cast<const float2*>(p)[0], b = reinterpret_cast<const float2*>(p)[1],
+                 c = reinterpret_cast<const float2*>(p)[2];
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y;
+}
+__device__ __forceinline__ void store6(float* p, const float (&v)[6]) {
+    reinterpret_cast<float2*>(p)[0] = make_float2(v[0], v[1]);
+    reinterpret_cast<float2*>(p)[1] = make_float2(v[2], v[3]);
+    reinterpret_cast<float2*>(p)[2] = make_float2(v[4], v[5]);
+}
+__device__ __forceinline__ void store6_global(float* p, const float (&v)[6]) {
+    __stcs(reinterpret_cast<float2*>(p), make_float2(v[0], v[1]));
+    __stcs(reinterpret_cast<float2*>(p) + 1, make_float2(v[2], v[3]));
+    __stcs(reinterpret_cast<float2*>(p) + 2, make_float2(v[4], v[5]));
+}
 __device__ __forceinline__ void acc_prop3(float (&st)[32], float m, float x, float y, float z) {
     x *= m; y *= m; z *= m;
     st[27] += x; st[28] += y; st[29] += z;
     st[30] += x * x + y * y + z * z;
 }
-__device__ __forceinline__ void sample6(const RowSE3& row, const EvalParams& P, int f, int n, float (&d)[6]) {
-    float z[8];
-    normal4(P.seed_lo, P.seed_hi, P.stream_id, (uint32_t)f, (uint32_t)n, 0u, z);
-    normal4(P.seed_lo, P.seed_hi, P.stream_id, (uint32_t)f, (uint32_t)n, 1u, z + 4);
+// measurement offsets L z of slot k of the lane's group (z: 24 normals of the group)
+__device__ __forceinline__ void sample6(const RowSE3& row, const float* z, float (&d)[6]) {
     int k = 0;
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
@@ -379,15 +414,18 @@ struct FamPose3Pose3 {
         float st[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) st[i] = 0.f;
-        for (int n = lane; n < Npad; n += 32) {
+        {
+          for (int n = lane, slot = 0; n < Npad; n += 32, ++slot) {
             float p[6], q[6], m[6];
-#pragma unroll
-            for (int i = 0; i < 6; ++i) { p[i] = Pp[i * Npad + n]; q[i] = Qp[i * Npad + n]; }
+            load6(Pp + 6 * n, p);
+            load6(Qp + 6 * n, q);
             if (!kSample) {
-#pragma unroll
-                for (int i = 0; i < 6; ++i) m[i] = V.meas[i * Npad + n];
-            } else {
-                sample6(row, P, f, n, m);
+                load6(V.meas + 6 * n, m);
+            } else {  // two Philox blocks per particle (8 normals, 6 used)
+                float z[8];
+                normal4(P.seed_lo, P.seed_hi, P.stream_id, (uint32_t)f, (uint32_t)lane, (uint32_t)(2 * slot), z);
+                normal4(P.seed_lo, P.seed_hi, P.stream_id, (uint32_t)f, (uint32_t)lane, (uint32_t)(2 * slot + 1), z + 4);
+                sample6(row, z, m);
             }
             double X[6];
 #pragma unroll
@@ -409,20 +447,17 @@ struct FamPose3Pose3 {
             const float msk = (n < N) ? 1.f : 0.f;
             if (want_stats) acc_res6(st, msk, r);
             if (kSample && (flags & ROME_B200_WRITE_MEAS)) {
-#pragma unroll
-                for (int i = 0; i < 6; ++i) __stcs(P.meas_out + fo + i * Npad + n, m[i]);
+                store6_global(P.meas_out + fo + 6 * n, m);
             }
             if (flags & ROME_B200_RESIDUAL) {
-#pragma unroll
-                for (int i = 0; i < 6; ++i) V.out_res[i * Npad + n] = r[i];
+                store6(V.out_res + 6 * n, r);
             }
             if (flags & ROME_B200_PROPOSAL_FWD) {  // q = p o Exp(X): coordinates as offsets from q's anchor
                 double ox, oy, oz;
                 quat_log(Rh, ox, oy, oz);
                 const float o[6] = {(float)hx, (float)hy, (float)hz, (float)(ox - aq[3]), (float)(oy - aq[4]),
                                     (float)(oz - aq[5])};
-#pragma unroll
-                for (int i = 0; i < 6; ++i) V.out_fwd[i * Npad + n] = o[i];
+                store6(V.out_fwd + 6 * n, o);
                 if (want_stats) acc_prop3(st, msk, o[0], o[1], o[2]);
             }
             if (flags & ROME_B200_PROPOSAL_BWD) {  // R_p = R_q Exp(X.w)' ; t_p = t_q - R_p X.t
@@ -434,10 +469,10 @@ struct FamPose3Pose3 {
                                     (float)(((aq[1] - ap[1]) + (double)q[1]) - by),
                                     (float)(((aq[2] - ap[2]) + (double)q[2]) - bz),
                                     (float)(ox - ap[3]), (float)(oy - ap[4]), (float)(oz - ap[5])};
-#pragma unroll
-                for (int i = 0; i < 6; ++i) __stcs(P.prop_bwd + fo + i * Npad + n, o[i]);
+                store6_global(P.prop_bwd + fo + 6 * n, o);
                 if (want_stats && !(flags & ROME_B200_PROPOSAL_FWD)) acc_prop3(st, msk, o[0], o[1], o[2]);
             }
+          }
         }
         if (want_stats) {
             const float tot = warp_reduce_scatter32(st, lane);
@@ -461,15 +496,17 @@ struct FamPriorPose3 {
         float st[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) st[i] = 0.f;
-        for (int n = lane; n < Npad; n += 32) {
+        {
+          for (int n = lane, slot = 0; n < Npad; n += 32, ++slot) {
             float p[6], m[6];
-#pragma unroll
-            for (int i = 0; i < 6; ++i) p[i] = Pp[i * Npad + n];
+            load6(Pp + 6 * n, p);
             if (!kSample) {
-#pragma unroll
-                for (int i = 0; i < 6; ++i) m[i] = V.meas[i * Npad + n];
+                load6(V.meas + 6 * n, m);
             } else {
-                sample6(row, P, f, n, m);
+                float z[8];
+                normal4(P.seed_lo, P.seed_hi, P.stream_id, (uint32_t)f, (uint32_t)lane, (uint32_t)(2 * slot), z);
+                normal4(P.seed_lo, P.seed_hi, P.stream_id, (uint32_t)f, (uint32_t)lane, (uint32_t)(2 * slot + 1), z + 4);
+                sample6(row, z, m);
             }
             double X[6];  // sampled point coordinates: exp(e, hat(mu + L z)) = (t, Exp(w))
 #pragma unroll
@@ -484,20 +521,18 @@ struct FamPriorPose3 {
             const float msk = (n < N) ? 1.f : 0.f;
             if (want_stats) acc_res6(st, msk, r);
             if (kSample && (flags & ROME_B200_WRITE_MEAS)) {
-#pragma unroll
-                for (int i = 0; i < 6; ++i) __stcs(P.meas_out + fo + i * Npad + n, m[i]);
+                store6_global(P.meas_out + fo + 6 * n, m);
             }
             if (flags & ROME_B200_RESIDUAL) {
-#pragma unroll
-                for (int i = 0; i < 6; ++i) V.out_res[i * Npad + n] = r[i];
+                store6(V.out_res + 6 * n, r);
             }
             if (flags & ROME_B200_PROPOSAL_FWD) {  // proposal = the sampled point, offsets from the anchor
                 const float o[6] = {(float)hx, (float)hy, (float)hz, (float)(X[3] - ap[3]), (float)(X[4] - ap[4]),
                                     (float)(X[5] - ap[5])};
-#pragma unroll
-                for (int i = 0; i < 6; ++i) V.out_fwd[i * Npad + n] = o[i];
+                store6(V.out_fwd + 6 * n, o);
                 if (want_stats) acc_prop3(st, msk, o[0], o[1], o[2]);
             }
+          }
         }
         if (want_stats) {
             const float tot = warp_reduce_scatter32(st, lane);
@@ -568,12 +603,14 @@ __global__ void __launch_bounds__((FT + 1) * 32, Fam::kMinCtas) eval_kernel(cons
             }
         };
         if (tile < nTiles) fetch_ids(tile);
-        for (int it = 0; tile < nTiles; tile += gridDim.x, ++it) {
-            const int s = it % S, round = it / S;
+        int s = 0;
+        uint32_t phase = 1;  // parity of the previous round; the first pass over the ring does not wait
+        bool first_round = true;
+        for (; tile < nTiles; tile += gridDim.x) {
             const int my_ip = ip, my_iq = iq;
             const int next = tile + gridDim.x;
             if (next < nTiles) fetch_ids(next);  // ids of the next tile are in flight while we wait
-            if (round > 0) mbar_wait(&empty[s], (uint32_t)((round - 1) & 1));
+            if (!first_round) mbar_wait(&empty[s], phase);
             unsigned char* st = stage0 + (size_t)s * L.bytes;
             const int nf = min(FT, P.count - tile * FT);
             if (lane == 0) {
@@ -590,15 +627,16 @@ __global__ void __launch_bounds__((FT + 1) * 32, Fam::kMinCtas) eval_kernel(cons
                 if (Fam::D1)
                     tma_load_1d(st + L.v1_off + lane * L.b1, P.v1 + (size_t)my_iq * L.b1, (uint32_t)L.b1, &full[s]);
             }
+            if (++s == S) { s = 0; phase ^= 1u; first_round = false; }
         }
     } else {
         // ---------------- consumer warps: warp w owns the tile's w-th factor ----------------------------------
         float* out = reinterpret_cast<float*>(stage0 + (size_t)S * L.bytes + (size_t)warp * P.out_warp_bytes);
         const int res_floats = Fam::DR * P.Npad;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x, ++it) {
-            const int s = it % S, round = it / S;
-            mbar_wait(&full[s], (uint32_t)(round & 1));
+        int s = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
+            mbar_wait(&full[s], phase);
             const unsigned char* st = stage0 + (size_t)s * L.bytes;
             const int fl = tile * FT + warp;
             if (fl < P.count) {
@@ -630,6 +668,7 @@ __global__ void __launch_bounds__((FT + 1) * 32, Fam::kMinCtas) eval_kernel(cons
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
+            if (++s == S) { s = 0; phase ^= 1u; }
         }
         if (lane == 0) tma_store_wait_all();
     }
@@ -758,7 +797,7 @@ __global__ void pack_kernel(int nvars, int N, int Npad, int wrap_dim, const doub
                 o = src[(size_t)n * D + c] - a[c];
                 if (c == wrap_dim) o = wrap_pi(o);
             }
-            dst[(size_t)c * Npad + n] = (float)o;
+            dst[(size_t)n * D + c] = (float)o;
         }
     }
 }
@@ -774,7 +813,7 @@ __global__ void unpack_kernel(int nvars, int N, int Npad, int wrap_dim, const un
     for (int n = lane; n < N; n += 32) {
 #pragma unroll
         for (int c = 0; c < D; ++c) {
-            double x = hdr[c] + (double)src[(size_t)c * Npad + n];
+            double x = hdr[c] + (double)src[(size_t)n * D + c];
             if (c == wrap_dim) x = wrap_pi(x);
             dst[(size_t)n * D + c] = x;
         }

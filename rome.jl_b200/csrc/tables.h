@@ -37,7 +37,7 @@ static_assert(sizeof(RowSE3) == 160, "RowSE3 must be 160 B");
 
 // Particle store: one contiguous BLOCK per variable so that a single 1-D TMA bulk copy brings a whole
 // variable (anchor + all particles) into shared memory:
-//     [ anchor: d doubles, padded to a multiple of 16 B ][ d rows x Npad float32 offsets ]
+//     [ anchor header ][ Npad x d float32 offsets, particle-major ]
 //   Pose2 (d=3): anchor = {x, y, theta, cos(theta), sin(theta), 0}  (48 B; the heading's cos/sin are computed once
 //                when the particles are packed so the kernels only evaluate small-angle polynomials)
 //   Point2 (d=2): {x, y} (16 B);  Pose3 (d=6): {x, y, z, wx, wy, wz} (48 B)

@@ -1,5 +1,5 @@
 """Thin object wrapper over the C ABI (include/rome_b200.h) plus the layout helpers a host caller
-needs (reference Float64 particle-major arrays <-> anchored float32 SoA device rows).
+needs (reference Float64 particle-major arrays <-> anchored float32 particle-major device rows).
 
 All compute goes through librome_b200.so; nothing here evaluates a factor on the CPU.
 """
@@ -139,10 +139,10 @@ class Context:
         return np.ascontiguousarray(raw[:, :d * 8]).view(np.float64).reshape(-1, d).copy()
 
     def get_offsets(self, vartype: int) -> np.ndarray:
-        """float32 offsets [nvars][d][Npad] read back from the device store"""
+        """float32 offsets [nvars][Npad][d] read back from the device store"""
         raw, hb, Np = self._store_bytes(vartype)
         d = VAR_DIM[vartype]
-        return np.ascontiguousarray(raw[:, hb:]).view(np.float32).reshape(-1, d, Np).copy()
+        return np.ascontiguousarray(raw[:, hb:]).view(np.float32).reshape(-1, Np, d).copy()
 
     def adopt_proposal(self, vartype: int, var: int, d_prop, factor: int):
         self._ck(self._lib.rome_b200_adopt_proposal(self._h, vartype, var, _ptr(d_prop), factor))
@@ -206,17 +206,17 @@ class Context:
         Np = self.particles_device(vt0)[5]
         out = {}
         if flags & WRITE_MEAS:
-            out["meas_out"] = np.zeros((nF, dm, Np), np.float32)
+            out["meas_out"] = np.zeros((nF, Np, dm), np.float32)
         if flags & RESIDUAL:
-            out["res"] = np.zeros((nF, dr, Np), np.float32)
+            out["res"] = np.zeros((nF, Np, dr), np.float32)
         if flags & PROPOSAL_FWD:
-            out["prop_fwd"] = np.zeros((nF, dfwd, Np), np.float32)
+            out["prop_fwd"] = np.zeros((nF, Np, dfwd), np.float32)
         if flags & PROPOSAL_BWD:
-            out["prop_bwd"] = np.zeros((nF, dbwd, Np), np.float32)
+            out["prop_bwd"] = np.zeros((nF, Np, dbwd), np.float32)
         if flags & STATS:
             out["stats"] = np.zeros((nF, ns), np.float32)
         if flags & JACOBIAN:
-            out["jac"] = np.zeros((nF, dj, Np), np.float32)
+            out["jac"] = np.zeros((nF, Np, dj), np.float32)
         return out
 
     # -- CUDA graphs ---------------------------------------------------------------------------
@@ -233,30 +233,29 @@ class Context:
 
 
 # ----------------------------------------------------------------------------------------------
-# layout helpers (host side, numpy): reference layout <-> device rows
+# layout helpers (host side, numpy).  Device rows are particle-major like the reference's own arrays
+# ([nF][Npad][d] vs [nF][N][d]), so these only pad/slice, subtract/add the Float64 anchor and change dtype.
 # ----------------------------------------------------------------------------------------------
 def meas_to_offsets(meas, mu, Npad=None) -> np.ndarray:
     """Float64 samples [nF][N][dm] (reference `sampleFactor` output, coordinates) -> float32 offsets from
-    the factor mean, SoA [nF][dm][Npad]."""
+    the factor mean, [nF][Npad][dm]."""
     meas, mu = _f64(meas), _f64(mu)
     nF, N, dm = meas.shape
     Np = Npad or npad(N)
-    out = np.zeros((nF, dm, Np), np.float32)
-    out[:, :, :N] = np.transpose(meas - mu[:, None, :], (0, 2, 1))
+    out = np.zeros((nF, Np, dm), np.float32)
+    out[:, :N, :] = meas - mu[:, None, :]
     return out
 
 
 def offsets_to_meas(off, mu, N) -> np.ndarray:
-    off = np.asarray(off, dtype=np.float64)
-    return np.transpose(off[:, :, :N], (0, 2, 1)) + _f64(mu)[:, None, :]
+    return np.asarray(off, dtype=np.float64)[:, :N, :] + _f64(mu)[:, None, :]
 
 
 def rows_to_particle_major(rows, N) -> np.ndarray:
-    """device rows [nF][d][Npad] -> [nF][N][d] Float64"""
-    return np.transpose(np.asarray(rows, dtype=np.float64)[:, :, :N], (0, 2, 1))
+    """device rows [nF][Npad][d] float32 -> [nF][N][d] Float64"""
+    return np.asarray(rows, dtype=np.float64)[:, :N, :].copy()
 
 
 def dequantized_particles(anchors, offsets, N, wrap_dim=None) -> np.ndarray:
     """The exact Float64 values the kernels see: anchor + float32 offset, [nvars][N][d]."""
-    x = _f64(anchors)[:, None, :] + np.transpose(np.asarray(offsets, dtype=np.float64)[:, :, :N], (0, 2, 1))
-    return x
+    return _f64(anchors)[:, None, :] + np.asarray(offsets, dtype=np.float64)[:, :N, :]

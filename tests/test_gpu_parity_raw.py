@@ -264,6 +264,18 @@ def test_priorpose3_parity(ctx):
     assert np.abs(prop - meas).max() < 1e-5
 
 
+def twin_normals(seed, sid, f, n, d):
+    """host twin of the device sampler's addressing (csrc/factor_kernels.cu): particle n is slot n>>5 of lane n&31.
+    SE(2) families (d = 2, 3): one batch of d Philox blocks serves the 4 slots of a group; SE(3) (d = 6): two
+    blocks per slot."""
+    lane, slot = n & 31, n >> 5
+    if d == 6:
+        return np.concatenate([O.normal4(seed, sid, f, lane, 2 * slot), O.normal4(seed, sid, f, lane, 2 * slot + 1)])[:6]
+    g, k = slot >> 2, slot & 3
+    z = np.concatenate([O.normal4(seed, sid, f, lane, g * d + b) for b in range(d)])
+    return z[d * k:d * k + d]
+
+
 def test_particle_roundtrip(ctx):
     rng = np.random.default_rng(7)
     poses, _, _ = make_pose2_graph(rng, 25, 1, 100)
@@ -328,14 +340,15 @@ def test_fused_sampling_matches_supplied_and_host_twin(ctx, family):
     ctx.eval_host(fam, flags, seed=seed, stream_id=sid, **out)
     out2 = ctx.alloc_host_outputs(fam, rb.RESIDUAL)
     ctx.eval_host(fam, rb.RESIDUAL, meas=out["meas_out"], **out2)
-    assert np.array_equal(out["res"][:, :, :N], out2["res"][:, :, :N])
+    assert np.array_equal(out["res"][:, :N], out2["res"][:, :N])
     delta = rb.rows_to_particle_major(out["meas_out"], N)  # [nF][N][d] offsets from mu
     # host twin for a few (factor, particle) pairs
     for f in (0, 7, 63):
         for n in (0, 1, 50, 99):
-            z = np.concatenate([O.normal4(seed, sid, f, n, 0), O.normal4(seed, sid, f, n, 1)])[:d]
+            z = twin_normals(seed, sid, f, n, d)
             want = Lc[f].astype(np.float32).astype(np.float64) @ z
-            assert np.allclose(delta[f, n], want, rtol=2e-5, atol=2e-6), (f, n, delta[f, n], want)
+            # the device draws on the special-function unit (MUFU log/sin/cos): ~1e-4 sigma from the Float64 twin
+            assert np.allclose(delta[f, n], want, rtol=1e-3, atol=3e-4 * np.abs(Lc[f]).max()), (f, n, delta[f, n], want)
     # moments: whiten and check identity covariance / zero mean over all factors x particles
     zw = np.linalg.solve(Lc, np.transpose(delta, (0, 2, 1)))  # [nF][d][N]
     zs = np.transpose(zw, (1, 0, 2)).reshape(d, -1)
@@ -365,7 +378,7 @@ def test_device_pointer_path_and_graph(ctx):
     ctx.use_torch_stream()
     try:
         dm = torch.from_numpy(moff).cuda()
-        res = torch.zeros((nF, 3, Np), device="cuda")
+        res = torch.zeros((nF, Np, 3), device="cuda")
         st = torch.zeros((nF, 16), device="cuda")
         ctx.eval(rb.POSE2POSE2, rb.RESIDUAL | rb.STATS, first=0, count=300, meas=dm, res=res, stats=st)
         ctx.eval(rb.POSE2POSE2, rb.RESIDUAL | rb.STATS, first=300, count=-1, meas=dm, res=res, stats=st)
@@ -414,5 +427,5 @@ def test_nan_propagates(ctx):
     ctx.set_particles(rb.POSE2, poses)
     ctx.set_factors_pose2pose2([0], [1], [[1, 0, 0]], [np.eye(3) * 0.01])
     out = ctx.alloc_host_outputs(rb.POSE2POSE2, rb.RESIDUAL)
-    ctx.eval_host(rb.POSE2POSE2, rb.RESIDUAL, meas=np.zeros((1, 3, 16), np.float32), **out)
-    assert np.isnan(out["res"][0, 0, 3]) and np.isfinite(out["res"][0, 0, 2])
+    ctx.eval_host(rb.POSE2POSE2, rb.RESIDUAL, meas=np.zeros((1, 16, 3), np.float32), **out)
+    assert np.isnan(out["res"][0, 3, 0]) and np.isfinite(out["res"][0, 2, 0])

@@ -179,7 +179,7 @@ def test_layout_helpers():
     meas = rng.normal(size=(5, 100, 3))
     mu = rng.normal(size=(5, 3))
     off = rb.meas_to_offsets(meas, mu)
-    assert off.shape == (5, 3, 104) and off.dtype == np.float32 and np.all(off[:, :, 100:] == 0)
+    assert off.shape == (5, 104, 3) and off.dtype == np.float32 and np.all(off[:, 100:, :] == 0)
     back = rb.offsets_to_meas(off, mu, 100)
     assert np.abs(back - meas).max() < 1e-6
     assert rb.rows_to_particle_major(off, 100).shape == (5, 100, 3)

@@ -19,8 +19,8 @@ for s in range(4):
     c.use_torch_stream()
     c.set_particles(rb.POSE2, w["poses"] + 1e-4 * s)
     c.set_factors_pose2pose2(w["ip"], w["iq"], w["mu"], w["cov"])
-    sets.append((c, torch.zeros((F, 3, Np), device="cuda"), torch.zeros((F, 16), device="cuda"),
-                 torch.randn((F, 3, Np), device="cuda") * 0.05))
+    sets.append((c, torch.zeros((F, Np, 3), device="cuda"), torch.zeros((F, 16), device="cuda"),
+                 torch.randn((F, Np, 3), device="cuda") * 0.05))
 torch.cuda.synchronize()
 for k in range(reps):
     for c, res, st, meas in sets:
