@@ -130,12 +130,55 @@ __device__ __forceinline__ void normals_for_group(const EvalParams& P, int f, in
         normal4(P.seed_lo, P.seed_hi, P.stream_id, (uint32_t)f, (uint32_t)lane, (uint32_t)(g * D + b), &z[4 * b]);
 }
 
+// Slot loop.  A group = the lane's 4 slots {n0, n0+32, n0+64, n0+96}.  A FULL group (its 4th slot still has live
+// particles) is evaluated as branch-free straight-line code so the Float64 chains of the four particles
+// interleave: slots 0-2 are live for every lane, a lane whose 4th particle is beyond Npad reads particle `lane`
+// instead and has its stores/statistics masked.  FASTCOND (warp-uniform) selects the variant whose body may
+// assume kFast (e.g. small heading offsets -> polynomial sin/cos without a fallback branch).  The trailing
+// partial group is evaluated with warp-uniform guards per slot.
+#define ROME_SLOT_LOOP(FASTCOND, ...)                                                          \
+    for (int g = 0, n0 = lane; n0 < Npad; ++g, n0 += 128) {                                    \
+        float z[4 * DZ];                                                                       \
+        if (kSample) normals_for_group<DZ>(P, f, lane, g, z);                                  \
+        if (n0 - lane + 96 < Npad) {                                                           \
+            const int n3 = (n0 + 96 < Npad) ? n0 + 96 : lane;                                  \
+            if (FASTCOND) {                                                                    \
+                constexpr bool kFast = true; (void)kFast;                                      \
+                _Pragma("unroll") for (int k = 0; k < 4; ++k) {                                \
+                    const int nn = n0 + 32 * k;                                                \
+                    const bool live = (k < 3) || nn < Npad;                                    \
+                    const int n = (k < 3) ? nn : n3;                                           \
+                    __VA_ARGS__                                                                \
+                }                                                                              \
+            } else {                                                                           \
+                constexpr bool kFast = false; (void)kFast;                                     \
+                _Pragma("unroll") for (int k = 0; k < 4; ++k) {                                \
+                    const int nn = n0 + 32 * k;                                                \
+                    const bool live = (k < 3) || nn < Npad;                                    \
+                    const int n = (k < 3) ? nn : n3;                                           \
+                    __VA_ARGS__                                                                \
+                }                                                                              \
+            }                                                                                  \
+        } else {                                                                               \
+            constexpr bool kFast = false; (void)kFast;                                         \
+            _Pragma("unroll") for (int k = 0; k < 4; ++k) {                                    \
+                const int nn = n0 + 32 * k;                                                    \
+                if (n0 - lane + 32 * k < Npad) {                                               \
+                    const bool live = nn < Npad;                                               \
+                    const int n = live ? nn : lane;                                            \
+                    __VA_ARGS__                                                                \
+                }                                                                              \
+            }                                                                                  \
+        }                                                                                      \
+    }
+
 struct FamPose2Pose2 {
     using Row = RowSE2;
     static constexpr int D0 = 3, D1 = 3, DM = 3, DR = 3, DFWD = 3, kMinCtas = 2;
     template <uint32_t kStatic, bool kSample>
     static __device__ __forceinline__ void factor(const Row& row, const EvalParams& P, const FactorView& V, int f,
                                                   int lane) {
+        constexpr int DZ = 3;
         const int Npad = P.Npad, N = P.N;
         const uint32_t flags = kStatic ? kStatic : P.flags;
         const double* ap = reinterpret_cast<const double*>(V.b0);  // {x, y, theta, cos, sin}
@@ -151,67 +194,73 @@ struct FamPose2Pose2 {
 #pragma unroll
         for (int i = 0; i < 16; ++i) st[i] = 0.f;
 
-        for (int g = 0, n0 = lane; n0 < Npad; ++g, n0 += 128) {
-            float z[12];
-            if (kSample) normals_for_group<3>(P, f, lane, g, z);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int n = n0 + 32 * k;
-                if (n < Npad) {
-                    const double dpx = Pp[3 * n], dpy = Pp[3 * n + 1], dpt = Pp[3 * n + 2];
-                    const double dqx = Qp[3 * n], dqy = Qp[3 * n + 1], dqt = Qp[3 * n + 2];
-                    float mx, my, mt;
-                    if (!kSample) {
-                        mx = V.meas[3 * n]; my = V.meas[3 * n + 1]; mt = V.meas[3 * n + 2];
-                    } else {
-                        mx = row.L[0] * z[3 * k];
-                        my = fmaf(row.L[2], z[3 * k + 1], row.L[1] * z[3 * k]);
-                        mt = fmaf(row.L[5], z[3 * k + 2], fmaf(row.L[4], z[3 * k + 1], row.L[3] * z[3 * k]));
-                        if (flags & ROME_B200_WRITE_MEAS) {
-                            float* M = P.meas_out + fo + 3 * n;
-                            __stcs(M, mx); __stcs(M + 1, my); __stcs(M + 2, mt);
-                        }
-                    }
-                    const double Xx = mu0 + (double)mx, Xy = mu1 + (double)my, Xt = mu2 + (double)mt;
-                    double s, c;
-                    sincos_anchored(apt, ca, sa, dpt, s, c);
-                    const double rx = c * Xx - s * Xy;  // R(theta_p) X.t
-                    const double ry = s * Xx + c * Xy;
-                    // qhat - q, Pose2D.jl:62-65 ; qhat offsets are relative to q's anchor
-                    const double hx = (dax + dpx) + rx, hy = (day + dpy) + ry;
-                    const double ht = (dat + dpt) + Xt;
-                    const float e1 = (float)(hx - dqx), e2 = (float)(hy - dqy), e3 = (float)wrap_pi(ht - dqt);
-                    const float msk = (n < N) ? 1.f : 0.f;
-                    if (flags & ROME_B200_RESIDUAL) {
-                        V.out_res[3 * n] = e1; V.out_res[3 * n + 1] = e2; V.out_res[3 * n + 2] = e3;
-                    }
-                    if (want_stats) acc_res3(st, msk, e1, e2, e3);
-                    if (flags & ROME_B200_PROPOSAL_FWD) {
-                        const float ox = (float)hx, oy = (float)hy, ot = (float)wrap_pi(ht);
-                        V.out_fwd[3 * n] = ox; V.out_fwd[3 * n + 1] = oy; V.out_fwd[3 * n + 2] = ot;
-                        if (want_stats) { acc_prop2(st, msk, ox, oy); acc_heading(st, msk, ot); }
-                    }
-                    if (flags & ROME_B200_PROPOSAL_BWD) {
-                        // theta_p = theta_q - m_theta ; t_p = t_q - R(theta_p) m_t   (offsets from p's anchor)
-                        const double tb = (dqt - dat) - Xt;  // offset from apt
-                        double sb, cb;
-                        sincos(apt + tb, &sb, &cb);
-                        const float ox = (float)((dqx - dax) - (cb * Xx - sb * Xy));
-                        const float oy = (float)((dqy - day) - (sb * Xx + cb * Xy));
-                        const float ot = (float)wrap_pi(tb);
-                        float* B = P.prop_bwd + fo + 3 * n;
-                        __stcs(B, ox); __stcs(B + 1, oy); __stcs(B + 2, ot);
-                        if (want_stats && !(flags & ROME_B200_PROPOSAL_FWD)) {
-                            acc_prop2(st, msk, ox, oy); acc_heading(st, msk, ot);
-                        }
-                    }
-                    if (flags & ROME_B200_JACOBIAN) {  // d r/d theta_p = (-ry, rx, 1); d r/d m = R(theta_p) (+) 1
-                        float4* J = reinterpret_cast<float4*>(P.jac + ((size_t)f * Npad + n) * 4);
-                        __stcs(J, make_float4((float)(-ry), (float)rx, (float)c, (float)s));
-                    }
+        // warp-uniform: every heading offset of this group is small enough for the polynomial sin/cos
+#define ROME_P2P2_FAST                                                                                         \
+    (!__any_sync(0xffffffffu, fmaxf(fmaxf(fabsf(Pp[3 * n0 + 2]), fabsf(Pp[3 * (n0 + 32) + 2])),               \
+                                    fmaxf(fabsf(Pp[3 * (n0 + 64) + 2]), fabsf(Pp[3 * n3 + 2]))) > (float)kSmallAngle))
+        ROME_SLOT_LOOP(ROME_P2P2_FAST, {
+            const double dpx = Pp[3 * n], dpy = Pp[3 * n + 1], dpt = Pp[3 * n + 2];
+            const double dqx = Qp[3 * n], dqy = Qp[3 * n + 1], dqt = Qp[3 * n + 2];
+            float mx, my, mt;
+            if (!kSample) {
+                mx = V.meas[3 * n]; my = V.meas[3 * n + 1]; mt = V.meas[3 * n + 2];
+            } else {
+                mx = row.L[0] * z[3 * k];
+                my = fmaf(row.L[2], z[3 * k + 1], row.L[1] * z[3 * k]);
+                mt = fmaf(row.L[5], z[3 * k + 2], fmaf(row.L[4], z[3 * k + 1], row.L[3] * z[3 * k]));
+                if ((flags & ROME_B200_WRITE_MEAS) && live) {
+                    float* M = P.meas_out + fo + 3 * n;
+                    __stcs(M, mx); __stcs(M + 1, my); __stcs(M + 2, mt);
                 }
             }
-        }
+            const double Xx = mu0 + (double)mx, Xy = mu1 + (double)my, Xt = mu2 + (double)mt;
+            double s, c;
+            if (kFast) {  // sin/cos(anchor + small offset) by angle addition, no fallback branch
+                double sx, cx;
+                sincos_small(dpt, sx, cx);
+                s = fma(sa, cx, ca * sx);
+                c = fma(ca, cx, -sa * sx);
+            } else {
+                sincos_anchored(apt, ca, sa, dpt, s, c);
+            }
+            const double rx = c * Xx - s * Xy;  // R(theta_p) X.t
+            const double ry = s * Xx + c * Xy;
+            // qhat - q, Pose2D.jl:62-65 ; qhat offsets are relative to q's anchor
+            const double hx = (dax + dpx) + rx, hy = (day + dpy) + ry;
+            const double ht = (dat + dpt) + Xt;
+            const float e1 = (float)(hx - dqx), e2 = (float)(hy - dqy), e3 = (float)wrap_pi(ht - dqt);
+            const float msk = (nn < N) ? 1.f : 0.f;
+            if ((flags & ROME_B200_RESIDUAL) && live) {
+                V.out_res[3 * n] = e1; V.out_res[3 * n + 1] = e2; V.out_res[3 * n + 2] = e3;
+            }
+            if (want_stats) acc_res3(st, msk, e1, e2, e3);
+            if (flags & ROME_B200_PROPOSAL_FWD) {
+                const float ox = (float)hx, oy = (float)hy, ot = (float)wrap_pi(ht);
+                if (live) { V.out_fwd[3 * n] = ox; V.out_fwd[3 * n + 1] = oy; V.out_fwd[3 * n + 2] = ot; }
+                if (want_stats) { acc_prop2(st, msk, ox, oy); acc_heading(st, msk, ot); }
+            }
+            if (flags & ROME_B200_PROPOSAL_BWD) {
+                // theta_p = theta_q - m_theta ; t_p = t_q - R(theta_p) m_t   (offsets from p's anchor)
+                const double tb = (dqt - dat) - Xt;  // offset from apt
+                double sb, cb;
+                sincos(apt + tb, &sb, &cb);
+                const float ox = (float)((dqx - dax) - (cb * Xx - sb * Xy));
+                const float oy = (float)((dqy - day) - (sb * Xx + cb * Xy));
+                const float ot = (float)wrap_pi(tb);
+                if (live) {
+                    float* B = P.prop_bwd + fo + 3 * n;
+                    __stcs(B, ox); __stcs(B + 1, oy); __stcs(B + 2, ot);
+                }
+                if (want_stats && !(flags & ROME_B200_PROPOSAL_FWD)) {
+                    acc_prop2(st, msk, ox, oy); acc_heading(st, msk, ot);
+                }
+            }
+            if ((flags & ROME_B200_JACOBIAN) && live) {  // d r/d theta_p = (-ry, rx, 1); d r/d m = R(theta_p) (+) 1
+                float4* J = reinterpret_cast<float4*>(P.jac + ((size_t)f * Npad + n) * 4);
+                __stcs(J, make_float4((float)(-ry), (float)rx, (float)c, (float)s));
+            }
+        })
+#undef ROME_P2P2_FAST
         if (want_stats) write_stats16(st, P.stats, f, lane);
     }
 };
@@ -223,6 +272,7 @@ struct FamPriorPose2 {
     template <uint32_t kStatic, bool kSample>
     static __device__ __forceinline__ void factor(const Row& row, const EvalParams& P, const FactorView& V, int f,
                                                   int lane) {
+        constexpr int DZ = 3;
         const int Npad = P.Npad, N = P.N;
         const uint32_t flags = kStatic ? kStatic : P.flags;
         const double* ap = reinterpret_cast<const double*>(V.b0);
@@ -234,41 +284,33 @@ struct FamPriorPose2 {
         float st[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) st[i] = 0.f;
-        for (int g = 0, n0 = lane; n0 < Npad; ++g, n0 += 128) {
-            float z[12];
-            if (kSample) normals_for_group<3>(P, f, lane, g, z);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int n = n0 + 32 * k;
-                if (n < Npad) {
-                    const double dpx = Pp[3 * n], dpy = Pp[3 * n + 1], dpt = Pp[3 * n + 2];
-                    float mx, my, mt;
-                    if (!kSample) {
-                        mx = V.meas[3 * n]; my = V.meas[3 * n + 1]; mt = V.meas[3 * n + 2];
-                    } else {
-                        mx = row.L[0] * z[3 * k];
-                        my = fmaf(row.L[2], z[3 * k + 1], row.L[1] * z[3 * k]);
-                        mt = fmaf(row.L[5], z[3 * k + 2], fmaf(row.L[4], z[3 * k + 1], row.L[3] * z[3 * k]));
-                        if (flags & ROME_B200_WRITE_MEAS) {
-                            float* M = P.meas_out + fo + 3 * n;
-                            __stcs(M, mx); __stcs(M + 1, my); __stcs(M + 2, mt);
-                        }
-                    }
-                    const double hx = mx0 + (double)mx, hy = my0 + (double)my, ht = mt0 + (double)mt;  // m - anchor
-                    const float e1 = (float)(hx - dpx), e2 = (float)(hy - dpy), e3 = (float)wrap_pi(ht - dpt);
-                    const float msk = (n < N) ? 1.f : 0.f;
-                    if (flags & ROME_B200_RESIDUAL) {
-                        V.out_res[3 * n] = e1; V.out_res[3 * n + 1] = e2; V.out_res[3 * n + 2] = e3;
-                    }
-                    if (want_stats) acc_res3(st, msk, e1, e2, e3);
-                    if (flags & ROME_B200_PROPOSAL_FWD) {
-                        const float ox = (float)hx, oy = (float)hy, ot = (float)wrap_pi(ht);
-                        V.out_fwd[3 * n] = ox; V.out_fwd[3 * n + 1] = oy; V.out_fwd[3 * n + 2] = ot;
-                        if (want_stats) { acc_prop2(st, msk, ox, oy); acc_heading(st, msk, ot); }
-                    }
+        ROME_SLOT_LOOP(true, {
+            const double dpx = Pp[3 * n], dpy = Pp[3 * n + 1], dpt = Pp[3 * n + 2];
+            float mx, my, mt;
+            if (!kSample) {
+                mx = V.meas[3 * n]; my = V.meas[3 * n + 1]; mt = V.meas[3 * n + 2];
+            } else {
+                mx = row.L[0] * z[3 * k];
+                my = fmaf(row.L[2], z[3 * k + 1], row.L[1] * z[3 * k]);
+                mt = fmaf(row.L[5], z[3 * k + 2], fmaf(row.L[4], z[3 * k + 1], row.L[3] * z[3 * k]));
+                if ((flags & ROME_B200_WRITE_MEAS) && live) {
+                    float* M = P.meas_out + fo + 3 * n;
+                    __stcs(M, mx); __stcs(M + 1, my); __stcs(M + 2, mt);
                 }
             }
-        }
+            const double hx = mx0 + (double)mx, hy = my0 + (double)my, ht = mt0 + (double)mt;  // m - anchor
+            const float e1 = (float)(hx - dpx), e2 = (float)(hy - dpy), e3 = (float)wrap_pi(ht - dpt);
+            const float msk = (nn < N) ? 1.f : 0.f;
+            if ((flags & ROME_B200_RESIDUAL) && live) {
+                V.out_res[3 * n] = e1; V.out_res[3 * n + 1] = e2; V.out_res[3 * n + 2] = e3;
+            }
+            if (want_stats) acc_res3(st, msk, e1, e2, e3);
+            if (flags & ROME_B200_PROPOSAL_FWD) {
+                const float ox = (float)hx, oy = (float)hy, ot = (float)wrap_pi(ht);
+                if (live) { V.out_fwd[3 * n] = ox; V.out_fwd[3 * n + 1] = oy; V.out_fwd[3 * n + 2] = ot; }
+                if (want_stats) { acc_prop2(st, msk, ox, oy); acc_heading(st, msk, ot); }
+            }
+        })
         if (want_stats) write_stats16(st, P.stats, f, lane);
     }
 };
@@ -281,6 +323,7 @@ struct FamBearingRange {
     template <uint32_t kStatic, bool kSample>
     static __device__ __forceinline__ void factor(const Row& row, const EvalParams& P, const FactorView& V, int f,
                                                   int lane) {
+        constexpr int DZ = 2;
         const int Npad = P.Npad, N = P.N;
         const uint32_t flags = kStatic ? kStatic : P.flags;
         const double* ap = reinterpret_cast<const double*>(V.b0);
@@ -294,53 +337,45 @@ struct FamBearingRange {
         float st[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) st[i] = 0.f;
-        for (int g = 0, n0 = lane; n0 < Npad; ++g, n0 += 128) {
-            float z[8];  // two independent scalar draws per particle, BearingRange2D.jl:23
-            if (kSample) normals_for_group<2>(P, f, lane, g, z);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int n = n0 + 32 * k;
-                if (n < Npad) {
-                    const double dpx = Pp[3 * n], dpy = Pp[3 * n + 1], dpt = Pp[3 * n + 2];
-                    const float2 lxy = *reinterpret_cast<const float2*>(Lp + 2 * n);
-                    const double dlx = lxy.x, dly = lxy.y;
-                    float mb, mr;
-                    if (!kSample) {
-                        const float2 m2 = *reinterpret_cast<const float2*>(V.meas + 2 * n);
-                        mb = m2.x; mr = m2.y;
-                    } else {
-                        mb = row.sig_b * z[2 * k];
-                        mr = row.sig_r * z[2 * k + 1];
-                        if (flags & ROME_B200_WRITE_MEAS)
-                            __stcs(reinterpret_cast<float2*>(P.meas_out + fo + 2 * n), make_float2(mb, mr));
-                    }
-                    const double b = row.mu_b + (double)mb, rho = row.mu_r + (double)mr;
-                    const double dx = dax + (dlx - dpx), dy = day + (dly - dpy);
-                    const double th = apt + dpt;
-                    const double d2 = dx * dx + dy * dy;
-                    const double rng = sqrt(d2);
-                    double e1d = wrap_pi(b + th - atan2(dy, dx));
-                    if (fabs(e1d - kPi) <= 1.4901161193847656e-08 * kPi) e1d = -kPi;  // sym_rem: +pi -> -pi
-                    const float e1 = (float)e1d, e2 = (float)(rho - rng);
-                    const float msk = (n < N) ? 1.f : 0.f;
-                    if (flags & ROME_B200_RESIDUAL)
-                        *reinterpret_cast<float2*>(V.out_res + 2 * n) = make_float2(e1, e2);
-                    if (want_stats) acc_res3(st, msk, e1, e2, 0.f);
-                    if (flags & ROME_B200_PROPOSAL_FWD) {  // l = t_p + rho R(theta_p)(cos b, sin b) - anchor(l)
-                        double s, c;
-                        sincos(th + b, &s, &c);
-                        const float ox = (float)((dpx - dax) + rho * c), oy = (float)((dpy - day) + rho * s);
-                        *reinterpret_cast<float2*>(V.out_fwd + 2 * n) = make_float2(ox, oy);
-                        if (want_stats) acc_prop2(st, msk, ox, oy);
-                    }
-                    if (flags & ROME_B200_JACOBIAN) {  // d r1/d l = (dy,-dx)/rho^2 ; d r2/d l = -d/rho
-                        const double i2 = 1.0 / d2, i1 = 1.0 / rng;
-                        float4* J = reinterpret_cast<float4*>(P.jac + ((size_t)f * Npad + n) * 4);
-                        __stcs(J, make_float4((float)(dy * i2), (float)(-dx * i2), (float)(-dx * i1), (float)(-dy * i1)));
-                    }
-                }
+        ROME_SLOT_LOOP(true, {
+            const double dpx = Pp[3 * n], dpy = Pp[3 * n + 1], dpt = Pp[3 * n + 2];
+            const float2 lxy = *reinterpret_cast<const float2*>(Lp + 2 * n);
+            const double dlx = lxy.x, dly = lxy.y;
+            float mb, mr;
+            if (!kSample) {
+                const float2 m2 = *reinterpret_cast<const float2*>(V.meas + 2 * n);
+                mb = m2.x; mr = m2.y;
+            } else {
+                mb = row.sig_b * z[2 * k];
+                mr = row.sig_r * z[2 * k + 1];
+                if ((flags & ROME_B200_WRITE_MEAS) && live)
+                    __stcs(reinterpret_cast<float2*>(P.meas_out + fo + 2 * n), make_float2(mb, mr));
             }
-        }
+            const double b = row.mu_b + (double)mb, rho = row.mu_r + (double)mr;
+            const double dx = dax + (dlx - dpx), dy = day + (dly - dpy);
+            const double th = apt + dpt;
+            const double d2 = dx * dx + dy * dy;
+            const double rng = sqrt(d2);
+            double e1d = wrap_pi(b + th - atan2(dy, dx));
+            if (fabs(e1d - kPi) <= 1.4901161193847656e-08 * kPi) e1d = -kPi;  // sym_rem: +pi -> -pi
+            const float e1 = (float)e1d, e2 = (float)(rho - rng);
+            const float msk = (nn < N) ? 1.f : 0.f;
+            if ((flags & ROME_B200_RESIDUAL) && live)
+                *reinterpret_cast<float2*>(V.out_res + 2 * n) = make_float2(e1, e2);
+            if (want_stats) acc_res3(st, msk, e1, e2, 0.f);
+            if (flags & ROME_B200_PROPOSAL_FWD) {  // l = t_p + rho R(theta_p)(cos b, sin b) - anchor(l)
+                double s, c;
+                sincos(th + b, &s, &c);
+                const float ox = (float)((dpx - dax) + rho * c), oy = (float)((dpy - day) + rho * s);
+                if (live) *reinterpret_cast<float2*>(V.out_fwd + 2 * n) = make_float2(ox, oy);
+                if (want_stats) acc_prop2(st, msk, ox, oy);
+            }
+            if ((flags & ROME_B200_JACOBIAN) && live) {  // d r1/d l = (dy,-dx)/rho^2 ; d r2/d l = -d/rho
+                const double i2 = 1.0 / d2, i1 = 1.0 / rng;
+                float4* J = reinterpret_cast<float4*>(P.jac + ((size_t)f * Npad + n) * 4);
+                __stcs(J, make_float4((float)(dy * i2), (float)(-dx * i2), (float)(-dx * i1), (float)(-dy * i1)));
+            }
+        })
         if (want_stats) write_stats16(st, P.stats, f, lane);
     }
 };
