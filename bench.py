@@ -227,6 +227,7 @@ def main():
     import torch
     import torch.distributed as dist
     import rome_b200 as rb
+    from rome_b200 import sharding
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -280,7 +281,7 @@ def main():
         c.eval(rb.POSE2POSE2, flags, seed=7, stream_id=k, first=first, count=F0, **bufs)
         stream.wait_stream(side)
         if multi:  # the one exchange of the path: proposals of every rank's factors to every rank
-            dist.all_gather_into_tensor(bufs["prop_fwd"], bufs["prop_fwd"][first:first + F0])
+            sharding.allgather_rows(bufs["prop_fwd"], F)
 
     clocks = ClockSampler(local)
     with torch.cuda.stream(stream):
@@ -439,10 +440,16 @@ def main():
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": nt, "kind": "port",
                                     "sample": f"{reps} full residual sweeps ({F0 + n_prior} factors x {N} particles) in {dt:.1f} s"}
             line["cpu_reference_shaped"] = cpu_reference_shaped(w)
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if multi:
+        # CUDA graphs that captured NCCL work must die before the communicator; then leave without the
+        # (occasionally hanging) communicator teardown -- every rank has finished its work at the barrier.
+        del g, gk, gp
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -17,6 +17,7 @@ from .graph import (DeviceGraph, FactorGraph, SolverParams, addFactor, addVariab
 from .canonical import (generateGraph_Beehive, generateGraph_Circle, generateGraph_Hexagonal,
                         generateGraph_ManhattanShaped, generateGraph_Pose3Chain, generateGraph_ZeroPose,
                         seed_particles)
+from . import sharding
 from .g2o import graphFromEdgeArrays, importG2o, loadG2o, parseG2oInstruction
 
 __version__ = "0.1.0"
