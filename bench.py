@@ -128,6 +128,24 @@ class ClockSampler:
                 "samples": len(self.samples), "window": window}
 
 
+def ncu_traffic(kernel_substr):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu summary (profiles/), or None"""
+    import csv
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_pose2pose2_metrics.csv")), reverse=True):
+        rows = list(csv.reader(open(path)))
+        hdr, units = rows[0], rows[1]
+        try:
+            ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        except ValueError:
+            continue
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        for r in rows[2:]:
+            if kernel_substr in r[1]:
+                return float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]]
+    return None
+
+
 # --------------------------------------------------------------------------------------------------------
 def cpu_sweep_rate(w, seconds=12.0, nthreads=0):
     """bare residual sweep of the oracle port over the workload's Pose2Pose2 + PriorPose2 factors"""
@@ -219,6 +237,7 @@ def main():
     ap.add_argument("--sets", type=int, default=12, help="independent working-set copies rotated through (L2 defeat)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="do not let consecutive (independent) steps overlap")
     ap.add_argument("--e2e-steps", type=int, default=20)
     args = ap.parse_args()
     if args.impl == "reference":
@@ -269,50 +288,73 @@ def main():
     evals_per_step = evals_per_step_rank * G
 
     side = torch.cuda.Stream()
+    pflags = rb.RESIDUAL | rb.STATS
 
-    def step(k):
+    def step(k, indep):
         """one pass of the hot path over the graph: the two family kernels have no mutual dependency and run
-        concurrently (fork/join on a side stream, captured into the graph as parallel branches)"""
+        concurrently (fork/join on a side stream, captured into the graph as parallel branches).  With `indep`
+        the Pose2Pose2 launch carries ROME_B200_INDEPENDENT: consecutive steps work on different working-set copies,
+        so a step may start on SMs the previous step has already vacated (programmatic dependent launch)."""
         c, bufs, pb = sets[k % S]
         side.wait_stream(stream)
         c.set_stream(side.cuda_stream)
         c.eval(rb.PRIORPOSE2, flags, seed=7, stream_id=k, first=rank * n_prior, count=n_prior, **pb)
         c.set_stream(stream.cuda_stream)
-        c.eval(rb.POSE2POSE2, flags, seed=7, stream_id=k, first=first, count=F0, **bufs)
+        c.eval(rb.POSE2POSE2, flags | (rb.INDEPENDENT if indep else 0), seed=7, stream_id=k, first=first, count=F0,
+               **bufs)
         stream.wait_stream(side)
         if multi:  # the one exchange of the path: proposals of every rank's factors to every rank
             sharding.allgather_rows(bufs["prop_fwd"], F)
 
-    clocks = ClockSampler(local)
-    with torch.cuda.stream(stream):
-        for k in range(args.warmup):
-            step(k)
-        stream.synchronize()
-        # capture the K timed steps into one CUDA graph
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g, stream=stream):
+    def kernel_only(k, indep):
+        c, bufs, _ = sets[k % S]
+        c.eval(rb.POSE2POSE2, flags | (rb.INDEPENDENT if indep else 0), seed=7, stream_id=k, first=first, count=F0,
+               **bufs)
+
+    def kernel_only_supplied(k, indep):
+        c, bufs, _ = sets[k % S]
+        c.eval(rb.POSE2POSE2, pflags | (rb.INDEPENDENT if indep else 0), first=first, count=F0, meas=meas_sets[k % S],
+               res=bufs["res"], stats=bufs["stats"])
+
+    def capture(fn, indep):
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=stream):
             for c, _, _ in sets:
                 c.use_torch_stream()
             for k in range(args.steps):
-                step(args.warmup + k)
+                fn(args.warmup + k, indep)
         for c, _, _ in sets:
             c.use_torch_stream()
-        g.replay()  # untimed replay: graph upload + warm instruction caches
+        gr.replay()  # untimed replay: graph upload + warm instruction caches
         stream.synchronize()
+        return gr
+
+    def timed(gr, sample_clocks=False):
         if multi:
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        clocks.start()
+        if sample_clocks:
+            clocks.start()
         e0.record(stream)
-        g.replay()
+        gr.replay()
         e1.record(stream)
         stream.synchronize()
-        clocks.stop()
+        if sample_clocks:
+            clocks.stop()
         if multi:
             dist.barrier()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
+        return e0.elapsed_time(e1)
+
+    clocks = ClockSampler(local)
+    overlap = not args.no_overlap
+    with torch.cuda.stream(stream):
+        for k in range(args.warmup):
+            step(k, False)
+        stream.synchronize()
+        g = capture(step, overlap)
+        ms = timed(g, sample_clocks=True)
         window = "timed"
         if len(clocks.samples) < 5:  # timed region too short to sample: keep sampling under identical replays
             clocks.start()
@@ -322,41 +364,16 @@ def main():
                 stream.synchronize()
             clocks.stop()
             window = "timed+identical replays"
+        ms_serial = timed(capture(step, False)) if overlap else ms
         # dominant kernel alone (Pose2Pose2 fused kernel): live CUDA-event timing over K launches
-        gk = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(gk, stream=stream):
-            for k in range(args.steps):
-                c, bufs, _ = sets[k % S]
-                c.eval(rb.POSE2POSE2, flags, seed=7, stream_id=k, first=first, count=F0, **bufs)
-        for c, _, _ in sets:
-            c.use_torch_stream()
-        gk.replay()
-        stream.synchronize()
-        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        k0.record(stream)
-        gk.replay()
-        k1.record(stream)
-        stream.synchronize()
-        kms = k0.elapsed_time(k1) / args.steps
-        # same kernel with the measurement supplied from HBM (parity mode, 48 B/eval)
-        pflags = rb.RESIDUAL | rb.STATS
+        gk = capture(kernel_only, overlap)
+        kms = timed(gk) / args.steps
+        kms_serial = timed(capture(kernel_only, False)) / args.steps if overlap else kms
+        # same kernel with the measurement supplied from HBM (48 B/eval)
         meas_sets = [torch.randn((F, Np, 3), device="cuda") * 0.05 for _ in range(S)]
-        gp = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(gp, stream=stream):
-            for k in range(args.steps):
-                c, bufs, _ = sets[k % S]
-                c.eval(rb.POSE2POSE2, pflags, first=first, count=F0, meas=meas_sets[k % S], res=bufs["res"],
-                       stats=bufs["stats"])
-        for c, _, _ in sets:
-            c.use_torch_stream()
-        gp.replay()
-        stream.synchronize()
-        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        p0.record(stream)
-        gp.replay()
-        p1.record(stream)
-        stream.synchronize()
-        pms = p0.elapsed_time(p1) / args.steps
+        gp = capture(kernel_only_supplied, overlap)
+        pms = timed(gp) / args.steps
+        pms_serial = timed(capture(kernel_only_supplied, False)) / args.steps if overlap else pms
         del meas_sets
 
     t = torch.tensor([ms], device="cuda", dtype=torch.float64)
@@ -406,6 +423,7 @@ def main():
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
+        traffic = ncu_traffic("FamPose2Pose2, 25, 1, 8")
         bpe = rb.BYTES_PER_EVAL_SAMPLED[rb.POSE2POSE2] + (12 if multi else 0)
         ach = F0 * N * bpe / (kms * 1e-3) / 1e9
         pach = F0 * N * rb.BYTES_PER_EVAL[rb.POSE2POSE2] / (pms * 1e-3) / 1e9
@@ -419,14 +437,26 @@ def main():
                                + ("; + closed-form proposals and one NCCL all-gather of them" if multi else ""),
                        "storage": "anchored float32 (Float64 anchor + float32 offset)",
                        "l2": f"{S} rotating working-set copies (> 2x L2); K steps replayed from one CUDA graph",
+                       "overlap": ("consecutive steps are independent (different working-set copies) and launched with "
+                                   "ROME_B200_INDEPENDENT (programmatic dependent launch): a step may start on SMs the "
+                                   "previous one vacated; serialized figures alongside") if overlap else "none",
                        "parallelism": f"factor-list sharding x{G}" if multi else "single GPU"},
             "roofline": {"bound": "hbm", "kernel": "eval_kernel<FamPose2Pose2, sample=true>", "achieved": ach, "peak": peak,
-                         "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                         "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu "
+                                         "--set full capture (profiles/); below the algorithmic bytes because neighbouring "
+                                         "factors share particle blocks in L2 and written rows are still L2-resident when "
+                                         "the replayed launch ends",
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
-                         "bytes_per_eval": bpe, "evals_per_launch": F0 * N, "us_per_launch": kms * 1e3},
+                         "bytes_per_eval": bpe, "evals_per_launch": F0 * N, "us_per_launch": kms * 1e3,
+                         "us_per_launch_serialized": kms_serial * 1e3,
+                         "frac_serialized": F0 * N * bpe / (kms_serial * 1e-3) / 1e9 / peak},
             "roofline_supplied_meas": {"kernel": "eval_kernel<FamPose2Pose2, sample=false>", "achieved": pach, "peak": peak,
                                        "unit": "GB/s", "frac": pach / peak, "bytes_per_eval": rb.BYTES_PER_EVAL[rb.POSE2POSE2],
-                                       "us_per_launch": pms * 1e3, "evals_per_s": F0 * N / (pms * 1e-3)},
+                                       "us_per_launch": pms * 1e3, "evals_per_s": F0 * N / (pms * 1e-3),
+                                       "us_per_launch_serialized": pms_serial * 1e3,
+                                       "frac_serialized": F0 * N * rb.BYTES_PER_EVAL[rb.POSE2POSE2] / (pms_serial * 1e-3) / 1e9 / peak},
+            "ms_per_step_serialized": ms_serial / args.steps,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * edt / args.e2e_steps, "steps": args.e2e_steps,
                     "api": "rome_b200_set_particles(host f64) + rome_b200_eval_host(host f32 outputs)"},

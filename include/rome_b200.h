@@ -87,6 +87,11 @@ enum rome_b200_family {
 #define ROME_B200_SAMPLE 16u      /* getSample fused in-kernel (Philox4x32-10); `meas` is not read   */
 #define ROME_B200_WRITE_MEAS 32u  /* with SAMPLE: also store the drawn measurement offsets            */
 #define ROME_B200_JACOBIAN 64u    /* compact analytic Jacobian blocks                */
+/* Scheduling hint: this launch reads nothing that was written by launches issued on the same ctx stream since the
+ * last launch WITHOUT this flag (e.g. the family kernels of one Gibbs sweep: all read the same particle state and
+ * write different buffers).  It is then launched with programmatic dependent launch and may start on SMs the
+ * preceding kernel has already vacated.  Results are identical; only the overlap changes. */
+#define ROME_B200_INDEPENDENT 128u
 
 /* Buffers of one eval call.  Unused members may be NULL.  `_host` entry points take host
  * pointers with the same shapes; plain entry points take device pointers. */

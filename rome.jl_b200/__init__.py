@@ -4,7 +4,7 @@ The directory is named `rome.jl_b200`; import it as `rome_b200` (see /rome_b200.
 Compute lives in librome_b200.so (csrc/, hand-written CUDA behind the C ABI of
 include/rome_b200.h); this package is the host-side mirror of the reference's factor API.
 """
-from ._lib import (BEARINGRANGE, JACOBIAN, POINT2, POSE2, POSE2POSE2, POSE3, POSE3POSE3, PRIORPOSE2, PRIORPOSE3,
+from ._lib import (BEARINGRANGE, INDEPENDENT, JACOBIAN, POINT2, POSE2, POSE2POSE2, POSE3, POSE3POSE3, PRIORPOSE2, PRIORPOSE3,
                    PROPOSAL_BWD, PROPOSAL_FWD, RESIDUAL, SAMPLE, SO_PATH, STATS, SYMBOLS, WRITE_MEAS, RomeB200Error)
 from .engine import (BYTES_PER_EVAL, BYTES_PER_EVAL_SAMPLED, FAMILY, VAR_DIM, Context, dequantized_particles,
                      meas_to_offsets, npad, offsets_to_meas, rows_to_particle_major)

@@ -12,7 +12,7 @@ SO_PATH = os.path.join(HERE, "librome_b200.so")
 OK, BAD_ARG, CUDA_ERROR, SHAPE_MISMATCH, NOT_SET, NO_DEVICE = 0, -1, -2, -3, -4, -5
 POSE2, POINT2, POSE3 = 0, 1, 2
 POSE2POSE2, PRIORPOSE2, BEARINGRANGE, POSE3POSE3, PRIORPOSE3 = 0, 1, 2, 3, 4
-RESIDUAL, PROPOSAL_FWD, PROPOSAL_BWD, STATS, SAMPLE, WRITE_MEAS, JACOBIAN = 1, 2, 4, 8, 16, 32, 64
+RESIDUAL, PROPOSAL_FWD, PROPOSAL_BWD, STATS, SAMPLE, WRITE_MEAS, JACOBIAN, INDEPENDENT = 1, 2, 4, 8, 16, 32, 64, 128
 
 # every symbol include/rome_b200.h declares (tests check the library exports each one)
 SYMBOLS = [

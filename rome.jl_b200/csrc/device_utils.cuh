@@ -148,20 +148,29 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1
     }
     return c;
 }
-// Box-Muller on the special-function unit (MUFU.LG2 / MUFU.SIN / MUFU.COS): the draws differ from the
-// Float64 host twin by <= ~1e-4 sigma (tests/test_gpu_parity_raw.py); exact parity of a sweep is taken on
-// the samples the kernel writes back (ROME_B200_WRITE_MEAS), never on re-derived ones.
+// Box-Muller on the special-function unit (MUFU.LG2 / RSQ / SIN / COS): the draws differ from the Float64 host
+// twin by <= ~1e-4 sigma (tests/test_gpu_parity_raw.py); exact parity of a sweep is taken on the samples the
+// kernel writes back (ROME_B200_WRITE_MEAS), never on re-derived ones.
+//   u1 = ((a >> 9) + 0.5) / 2^23 in (0,1), built from the bit pattern of a float in [1,2);  radius = sqrt(-2 ln u1)
+//   u2 likewise;  angle = 2 pi u2 evaluated as -(cos, sin)(2 pi u2 - pi) to keep the MUFU argument in [-pi, pi]
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
-    const float u1 = (static_cast<float>(a >> 9) + 0.5f) * (1.0f / 8388608.0f);  // exact, in (0,1)
-    const float u2 = (static_cast<float>(b >> 9) + 0.5f) * (1.0f / 8388608.0f);
 #ifdef ROME_B200_ACCURATE_SAMPLER
+    const float u1 = (static_cast<float>(a >> 9) + 0.5f) * (1.0f / 8388608.0f);
+    const float u2 = (static_cast<float>(b >> 9) + 0.5f) * (1.0f / 8388608.0f);
     const float rad = sqrtf(-2.0f * logf(u1));
     float s, c;
     sincospif(2.0f * u2, &s, &c);
 #else
-    const float rad = sqrtf(fmaxf(-2.0f * __logf(u1), 0.0f));
-    float s, c;  // cos(2 pi u) = -cos(2 pi u - pi): keeps the MUFU argument inside [-pi, pi]
-    __sincosf(6.28318530717958647692f * (u2 - 0.5f), &s, &c);
+    const float f1 = __uint_as_float(0x3f800000u | (a >> 9));  // 1 + (a>>9)/2^23
+    const float f2 = __uint_as_float(0x3f800000u | (b >> 9));
+    const float u1 = f1 - (1.0f - 5.9604644775390625e-08f);    // exact: (a>>9)/2^23 + 2^-24
+    float lg, rs, s, c;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(u1));
+    const float t = fmaxf(lg * -1.3862943611198906f, 1e-12f);  // -2 ln u1 = -2 ln2 * lg2 u1
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(t));
+    const float rad = t * rs;
+    // 2 pi u2 - pi = 2 pi (f2 - 1 + 2^-24) - pi
+    __sincosf(fmaf(f2, 6.28318530717958647692f, -9.42477758f), &s, &c);
     s = -s; c = -c;
 #endif
     z0 = rad * c;

@@ -131,15 +131,18 @@ __device__ __forceinline__ void normals_for_group(const EvalParams& P, int f, in
 }
 
 // Slot loop.  A group = the lane's 4 slots {n0, n0+32, n0+64, n0+96}.  A FULL group (its 4th slot still has live
-// particles) is evaluated as branch-free straight-line code so the Float64 chains of the four particles
-// interleave: slots 0-2 are live for every lane, a lane whose 4th particle is beyond Npad reads particle `lane`
-// instead and has its stores/statistics masked.  FASTCOND (warp-uniform) selects the variant whose body may
-// assume kFast (e.g. small heading offsets -> polynomial sin/cos without a fallback branch).  The trailing
-// partial group is evaluated with warp-uniform guards per slot.
+// particles) is evaluated as branch-free straight-line code: first the four slot BODIES (loads + arithmetic into
+// registers), then the four slot STORES -- no shared-memory store sits between the loads of different slots, so
+// the Float64 chains of the four particles may interleave.  Slots 0-2 are live for every lane; a lane whose 4th
+// particle is beyond Npad reads particle `lane` instead and has its stores/statistics masked.  FASTCOND
+// (warp-uniform) selects the variant whose body may assume kFast (e.g. small heading offsets -> polynomial
+// sin/cos without a fallback branch).  The trailing partial group is evaluated with warp-uniform guards.
+// The family defines ROME_SLOT_DECL (per-group register arrays) and ROME_SLOT_STORE (uses k, n, live).
 #define ROME_SLOT_LOOP(FASTCOND, ...)                                                          \
     for (int g = 0, n0 = lane; n0 < Npad; ++g, n0 += 128) {                                    \
         float z[4 * DZ];                                                                       \
         if (kSample) normals_for_group<DZ>(P, f, lane, g, z);                                  \
+        ROME_SLOT_DECL                                                                         \
         if (n0 - lane + 96 < Npad) {                                                           \
             const int n3 = (n0 + 96 < Npad) ? n0 + 96 : lane;                                  \
             if (FASTCOND) {                                                                    \
@@ -159,6 +162,12 @@ __device__ __forceinline__ void normals_for_group(const EvalParams& P, int f, in
                     __VA_ARGS__                                                                \
                 }                                                                              \
             }                                                                                  \
+            _Pragma("unroll") for (int k = 0; k < 4; ++k) {                                    \
+                const int nn = n0 + 32 * k;                                                    \
+                const bool live = (k < 3) || nn < Npad;                                        \
+                const int n = (k < 3) ? nn : n3;                                               \
+                ROME_SLOT_STORE                                                                \
+            }                                                                                  \
         } else {                                                                               \
             constexpr bool kFast = false; (void)kFast;                                         \
             _Pragma("unroll") for (int k = 0; k < 4; ++k) {                                    \
@@ -167,9 +176,20 @@ __device__ __forceinline__ void normals_for_group(const EvalParams& P, int f, in
                     const bool live = nn < Npad;                                               \
                     const int n = live ? nn : lane;                                            \
                     __VA_ARGS__                                                                \
+                    ROME_SLOT_STORE                                                            \
                 }                                                                              \
             }                                                                                  \
         }                                                                                      \
+    }
+
+// SE(2) pose-valued families: residual and forward-proposal rows are 3 floats per particle
+#define ROME_SLOT_DECL float o_res[4][3], o_fwd[4][3]; (void)o_res; (void)o_fwd;
+#define ROME_SLOT_STORE                                                                        \
+    if ((flags & ROME_B200_RESIDUAL) && live) {                                                \
+        V.out_res[3 * n] = o_res[k][0]; V.out_res[3 * n + 1] = o_res[k][1]; V.out_res[3 * n + 2] = o_res[k][2]; \
+    }                                                                                          \
+    if ((flags & ROME_B200_PROPOSAL_FWD) && live) {                                            \
+        V.out_fwd[3 * n] = o_fwd[k][0]; V.out_fwd[3 * n + 1] = o_fwd[k][1]; V.out_fwd[3 * n + 2] = o_fwd[k][2]; \
     }
 
 struct FamPose2Pose2 {
@@ -230,13 +250,11 @@ struct FamPose2Pose2 {
             const double ht = (dat + dpt) + Xt;
             const float e1 = (float)(hx - dqx), e2 = (float)(hy - dqy), e3 = (float)wrap_pi(ht - dqt);
             const float msk = (nn < N) ? 1.f : 0.f;
-            if ((flags & ROME_B200_RESIDUAL) && live) {
-                V.out_res[3 * n] = e1; V.out_res[3 * n + 1] = e2; V.out_res[3 * n + 2] = e3;
-            }
+            o_res[k][0] = e1; o_res[k][1] = e2; o_res[k][2] = e3;
             if (want_stats) acc_res3(st, msk, e1, e2, e3);
             if (flags & ROME_B200_PROPOSAL_FWD) {
                 const float ox = (float)hx, oy = (float)hy, ot = (float)wrap_pi(ht);
-                if (live) { V.out_fwd[3 * n] = ox; V.out_fwd[3 * n + 1] = oy; V.out_fwd[3 * n + 2] = ot; }
+                o_fwd[k][0] = ox; o_fwd[k][1] = oy; o_fwd[k][2] = ot;
                 if (want_stats) { acc_prop2(st, msk, ox, oy); acc_heading(st, msk, ot); }
             }
             if (flags & ROME_B200_PROPOSAL_BWD) {
@@ -301,19 +319,25 @@ struct FamPriorPose2 {
             const double hx = mx0 + (double)mx, hy = my0 + (double)my, ht = mt0 + (double)mt;  // m - anchor
             const float e1 = (float)(hx - dpx), e2 = (float)(hy - dpy), e3 = (float)wrap_pi(ht - dpt);
             const float msk = (nn < N) ? 1.f : 0.f;
-            if ((flags & ROME_B200_RESIDUAL) && live) {
-                V.out_res[3 * n] = e1; V.out_res[3 * n + 1] = e2; V.out_res[3 * n + 2] = e3;
-            }
+            o_res[k][0] = e1; o_res[k][1] = e2; o_res[k][2] = e3;
             if (want_stats) acc_res3(st, msk, e1, e2, e3);
             if (flags & ROME_B200_PROPOSAL_FWD) {
                 const float ox = (float)hx, oy = (float)hy, ot = (float)wrap_pi(ht);
-                if (live) { V.out_fwd[3 * n] = ox; V.out_fwd[3 * n + 1] = oy; V.out_fwd[3 * n + 2] = ot; }
+                o_fwd[k][0] = ox; o_fwd[k][1] = oy; o_fwd[k][2] = ot;
                 if (want_stats) { acc_prop2(st, msk, ox, oy); acc_heading(st, msk, ot); }
             }
         })
         if (want_stats) write_stats16(st, P.stats, f, lane);
     }
 };
+
+#undef ROME_SLOT_DECL
+#undef ROME_SLOT_STORE
+// point-valued rows: 2 floats per particle
+#define ROME_SLOT_DECL float2 o_res[4], o_fwd[4]; (void)o_res; (void)o_fwd;
+#define ROME_SLOT_STORE                                                                              \
+    if ((flags & ROME_B200_RESIDUAL) && live) *reinterpret_cast<float2*>(V.out_res + 2 * n) = o_res[k]; \
+    if ((flags & ROME_B200_PROPOSAL_FWD) && live) *reinterpret_cast<float2*>(V.out_fwd + 2 * n) = o_fwd[k];
 
 // Pose2Point2BearingRange: pl = R_p'(l - t_p); r = (sym_rem(b - atan(pl)), rho - |pl|)
 // evaluated as atan(pl) = atan(l - t_p) - theta_p and |pl| = |l - t_p| (same values, no rotation)
@@ -360,14 +384,13 @@ struct FamBearingRange {
             if (fabs(e1d - kPi) <= 1.4901161193847656e-08 * kPi) e1d = -kPi;  // sym_rem: +pi -> -pi
             const float e1 = (float)e1d, e2 = (float)(rho - rng);
             const float msk = (nn < N) ? 1.f : 0.f;
-            if ((flags & ROME_B200_RESIDUAL) && live)
-                *reinterpret_cast<float2*>(V.out_res + 2 * n) = make_float2(e1, e2);
+            o_res[k] = make_float2(e1, e2);
             if (want_stats) acc_res3(st, msk, e1, e2, 0.f);
             if (flags & ROME_B200_PROPOSAL_FWD) {  // l = t_p + rho R(theta_p)(cos b, sin b) - anchor(l)
                 double s, c;
                 sincos(th + b, &s, &c);
                 const float ox = (float)((dpx - dax) + rho * c), oy = (float)((dpy - day) + rho * s);
-                if (live) *reinterpret_cast<float2*>(V.out_fwd + 2 * n) = make_float2(ox, oy);
+                o_fwd[k] = make_float2(ox, oy);
                 if (want_stats) acc_prop2(st, msk, ox, oy);
             }
             if ((flags & ROME_B200_JACOBIAN) && live) {  // d r1/d l = (dy,-dx)/rho^2 ; d r2/d l = -d/rho
@@ -379,6 +402,10 @@ struct FamBearingRange {
         if (want_stats) write_stats16(st, P.stats, f, lane);
     }
 };
+
+#undef ROME_SLOT_DECL
+#undef ROME_SLOT_STORE
+#undef ROME_SLOT_LOOP
 
 // =============================================================================================
 // SE(3) families: one particle per lane per iteration
@@ -617,6 +644,21 @@ __global__ void __launch_bounds__((FT + 1) * 32, Fam::kMinCtas) eval_kernel(cons
     const Row* __restrict__ table = reinterpret_cast<const Row*>(P.rows) + P.first;
     const uint32_t flags = kStatic ? kStatic : P.flags;
 
+    // The producer warp holds the variable ids of a CHUNK of 32/FT tiles at once (lane l <-> tile l/FT of the
+    // chunk, factor l%FT): one global-load latency per chunk instead of one per tile; the first chunk is
+    // requested before the barrier initialisation is published.
+    constexpr int TPC = 32 / FT;  // tiles per chunk
+    const int jl = lane / FT, fl_in_tile = lane % FT;
+    int2 ids_cur = make_int2(0, 0);
+    auto fetch_chunk = [&](int base_tile) {
+        const int t = base_tile + jl * (int)gridDim.x;
+        const int fl = t * FT + fl_in_tile;
+        int2 ids = make_int2(0, 0);
+        if (t < nTiles && fl < P.count) ids = __ldg(reinterpret_cast<const int2*>(table + fl));
+        return ids;
+    };
+    if (warp == FT) ids_cur = fetch_chunk(blockIdx.x);
+
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
             mbar_init(&full[s], 1);
@@ -625,44 +667,42 @@ __global__ void __launch_bounds__((FT + 1) * 32, Fam::kMinCtas) eval_kernel(cons
         fence_mbar_init();
     }
     __syncthreads();
+    // programmatic dependent launch: a following launch flagged ROME_B200_INDEPENDENT may begin as SMs free up
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (warp == FT) {
-        // ---------------- producer warp: lane l gathers the particle blocks of the tile's l-th factor ----------
-        int tile = blockIdx.x;
-        int ip = 0, iq = 0;
-        auto fetch_ids = [&](int t) {
-            const int fl = t * FT + lane;
-            if (lane < FT && fl < P.count) {
-                const int2 ids = __ldg(reinterpret_cast<const int2*>(table + fl));
-                ip = ids.x; iq = ids.y;
-            }
-        };
-        if (tile < nTiles) fetch_ids(tile);
+        // ---------------- producer warp ---------------------------------------------------------------------
         int s = 0;
         uint32_t phase = 1;  // parity of the previous round; the first pass over the ring does not wait
         bool first_round = true;
-        for (; tile < nTiles; tile += gridDim.x) {
-            const int my_ip = ip, my_iq = iq;
-            const int next = tile + gridDim.x;
-            if (next < nTiles) fetch_ids(next);  // ids of the next tile are in flight while we wait
-            if (!first_round) mbar_wait(&empty[s], phase);
-            unsigned char* st = stage0 + (size_t)s * L.bytes;
-            const int nf = min(FT, P.count - tile * FT);
-            if (lane == 0) {
-                fence_proxy_async();
-                mbar_arrive_expect_tx(&full[s], (uint32_t)(nf * ((int)sizeof(Row) + L.b0 + L.b1 + L.mb)));
-                tma_load_1d(st + L.rows_off, table + (size_t)tile * FT, (uint32_t)(nf * sizeof(Row)), &full[s]);
-                if (!kSample)
-                    tma_load_1d(st + L.meas_off, P.meas + (size_t)(P.first + tile * FT) * Fam::DM * P.Npad,
-                                (uint32_t)(nf * L.mb), &full[s]);
+        for (int base = blockIdx.x; base < nTiles; base += TPC * gridDim.x) {
+            const int2 ids_next = fetch_chunk(base + TPC * gridDim.x);  // in flight while this chunk is issued
+#pragma unroll 1
+            for (int j = 0; j < TPC; ++j) {
+                const int tile = base + j * gridDim.x;
+                if (tile >= nTiles) break;
+                if (!first_round) mbar_wait(&empty[s], phase);
+                unsigned char* st = stage0 + (size_t)s * L.bytes;
+                const int nf = min(FT, P.count - tile * FT);
+                if (lane == j * FT) {
+                    fence_proxy_async();
+                    mbar_arrive_expect_tx(&full[s], (uint32_t)(nf * ((int)sizeof(Row) + L.b0 + L.b1 + L.mb)));
+                    tma_load_1d(st + L.rows_off, table + (size_t)tile * FT, (uint32_t)(nf * sizeof(Row)), &full[s]);
+                    if (!kSample)
+                        tma_load_1d(st + L.meas_off, P.meas + (size_t)(P.first + tile * FT) * Fam::DM * P.Npad,
+                                    (uint32_t)(nf * L.mb), &full[s]);
+                }
+                __syncwarp();
+                if (jl == j && fl_in_tile < nf) {
+                    tma_load_1d(st + L.v0_off + fl_in_tile * L.b0, P.v0 + (size_t)ids_cur.x * L.b0, (uint32_t)L.b0,
+                                &full[s]);
+                    if (Fam::D1)
+                        tma_load_1d(st + L.v1_off + fl_in_tile * L.b1, P.v1 + (size_t)ids_cur.y * L.b1,
+                                    (uint32_t)L.b1, &full[s]);
+                }
+                if (++s == S) { s = 0; phase ^= 1u; first_round = false; }
             }
-            __syncwarp();
-            if (lane < nf) {
-                tma_load_1d(st + L.v0_off + lane * L.b0, P.v0 + (size_t)my_ip * L.b0, (uint32_t)L.b0, &full[s]);
-                if (Fam::D1)
-                    tma_load_1d(st + L.v1_off + lane * L.b1, P.v1 + (size_t)my_iq * L.b1, (uint32_t)L.b1, &full[s]);
-            }
-            if (++s == S) { s = 0; phase ^= 1u; first_round = false; }
+            ids_cur = ids_next;
         }
     } else {
         // ---------------- consumer warps: warp w owns the tile's w-th factor ----------------------------------
@@ -707,6 +747,8 @@ __global__ void __launch_bounds__((FT + 1) * 32, Fam::kMinCtas) eval_kernel(cons
         }
         if (lane == 0) tma_store_wait_all();
     }
+    // a launch that overlapped its predecessor must not be seen as complete before the predecessor is
+    if (P.flags & ROME_B200_INDEPENDENT) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 // =============================================================================================
@@ -729,13 +771,14 @@ int plan_launch(int family, uint32_t flags, int Npad, int smem_per_sm, int smem_
     const FamDims fd = fam_dims(family);
     const bool sample = (flags & ROME_B200_SAMPLE) != 0;
     const bool se3 = family == ROME_B200_POSE3POSE3 || family == ROME_B200_PRIORPOSE3;
-    const uint32_t out_flags = flags & ~(ROME_B200_SAMPLE);
-    const int variant = out_flags == kHot1 ? 1 : out_flags == kHot2 ? 2 : 0;
-    // per-warp output slice: residual rows, then forward-proposal rows (generic variant reserves both)
-    const int out_warp = (fd.dr + (variant == 1 ? 0 : fd.dfwd)) * Npad * 4;
+    const uint32_t out_flags = flags & ~(ROME_B200_SAMPLE | ROME_B200_INDEPENDENT);
+    const int hot = out_flags == kHot1 ? 1 : out_flags == kHot2 ? 2 : 0;
     static const int fts[3] = {8, 2, 1};
     for (int k = 0; k < 3; ++k) {
         const int ft = fts[k];
+        const int variant = ft == 8 ? hot : 0;  // compile-time flag variants exist for the 8-factor tile only
+        // per-warp output slice: residual rows, then forward-proposal rows (the generic variant reserves both)
+        const int out_warp = (fd.dr + (variant == 1 ? 0 : fd.dfwd)) * Npad * 4;
         const StageLayout L = stage_layout(ft, fd.row_bytes, fd.d0, fd.d1, fd.dm, sample, Npad);
         // prefer 2 CTAs/SM (register cap of the SE(2) kernels allows it) with >= 3 stages each, else 1 CTA/SM
         for (int ctas = (se3 ? 1 : 2); ctas >= 1; --ctas) {
@@ -746,9 +789,9 @@ int plan_launch(int family, uint32_t flags, int Npad, int smem_per_sm, int smem_
             const int need = ctas == 2 ? 3 : 2;
             if (stages >= need) {
                 if (ctas == 2 && stages > 4) stages = 4;
-                plan->ft = ft; plan->variant = ft == 8 ? variant : 0; plan->stages = stages;
+                plan->ft = ft; plan->variant = variant; plan->stages = stages;
                 plan->stage_bytes = L.bytes;
-                plan->out_warp_bytes = (fd.dr + (plan->variant == 1 ? 0 : fd.dfwd)) * Npad * 4;
+                plan->out_warp_bytes = out_warp;
                 plan->smem_bytes = kBarrierBytes + stages * L.bytes + ft * out_warp;
                 plan->ctas_per_sm = ctas;
                 return 0;
@@ -769,8 +812,17 @@ static int launch_ft(const EvalParams& p, const LaunchPlan& plan, int grid, cuda
         if (e != cudaSuccess) return (int)e;
         if (dev >= 0 && dev < 64) configured[dev] = plan.smem_bytes;
     }
-    k<<<grid, (FT + 1) * 32, plan.smem_bytes, s>>>(p);
-    return (int)cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3((FT + 1) * 32);
+    cfg.dynamicSmemBytes = plan.smem_bytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (p.flags & ROME_B200_INDEPENDENT) ? 1 : 0;
+    return (int)cudaLaunchKernelEx(&cfg, k, p);
 }
 template <class Fam, bool kSample>
 static int launch_sample(const EvalParams& p, const LaunchPlan& plan, int grid, cudaStream_t s) {

@@ -429,3 +429,104 @@ def test_nan_propagates(ctx):
     out = ctx.alloc_host_outputs(rb.POSE2POSE2, rb.RESIDUAL)
     ctx.eval_host(rb.POSE2POSE2, rb.RESIDUAL, meas=np.zeros((1, 16, 3), np.float32), **out)
     assert np.isnan(out["res"][0, 3, 0]) and np.isfinite(out["res"][0, 2, 0])
+
+
+def test_wide_heading_spread_takes_general_sincos_path(ctx):
+    """heading offsets from the anchor beyond the small-angle range (|delta| > 0.78 rad, up to +-pi): the kernel
+    must fall back to the general sin/cos; uniform headings on the whole circle"""
+    rng = np.random.default_rng(21)
+    N, nvars, nF = 100, 12, 40
+    poses = np.column_stack([rng.uniform(-5, 5, (nvars * N, 2)), rng.uniform(-np.pi, np.pi, nvars * N)]).reshape(nvars, N, 3)
+    ip = rng.integers(0, nvars, nF).astype(np.int32)
+    iq = ((ip + 1) % nvars).astype(np.int32)
+    mu = rng.normal(size=(nF, 3)) * [3, 3, 1]
+    cov = rand_cov(rng, nF, 3, [0.1, 0.1, 0.05])
+    meas = mu[:, None, :] + rng.normal(size=(nF, N, 3)) * 0.1
+    ctx.set_particles(rb.POSE2, poses)
+    ctx.set_factors_pose2pose2(ip, iq, mu, cov)
+    for flags in (rb.RESIDUAL | rb.STATS, rb.RESIDUAL | rb.STATS | rb.PROPOSAL_FWD | rb.PROPOSAL_BWD):
+        out = ctx.alloc_host_outputs(rb.POSE2POSE2, flags)
+        moff = rb.meas_to_offsets(meas, mu)
+        ctx.eval_host(rb.POSE2POSE2, flags, meas=moff, **out)
+        ref_same = O.sweep_pose2pose2(ip, iq, seen(ctx, rb.POSE2, N), seen_meas(moff, mu, N))
+        assert_close(rb.rows_to_particle_major(out["res"], N), ref_same, angle_cols=(2,), what="wide headings (A)",
+                     floor=FLOOR_SAME)
+
+
+@pytest.mark.parametrize("N", [1, 8, 33, 129, 500, 2000])
+def test_particle_count_edge_cases(ctx, N):
+    """N = 1 (calcFactorResidualTemporary), exact multiples of 8/32, partial trailing groups, and N large enough to
+    switch the kernels to the 2- and 1-factor tiles (shared-memory budget)"""
+    rng = np.random.default_rng(100 + N)
+    nvars, nF = 9, 21
+    poses, ip, iq = make_pose2_graph(rng, nvars, nF, N)
+    mu = rng.normal(size=(nF, 3))
+    cov = rand_cov(rng, nF, 3, [0.1, 0.1, 0.02])
+    meas = mu[:, None, :] + rng.normal(size=(nF, N, 3)) * 0.1
+    ctx.set_particles(rb.POSE2, poses)
+    ctx.set_factors_pose2pose2(ip, iq, mu, cov)
+    moff = rb.meas_to_offsets(meas, mu)
+    for flags in (rb.RESIDUAL | rb.STATS, rb.RESIDUAL | rb.STATS | rb.PROPOSAL_FWD, rb.RESIDUAL | rb.JACOBIAN):
+        out = ctx.alloc_host_outputs(rb.POSE2POSE2, flags)
+        ctx.eval_host(rb.POSE2POSE2, flags, meas=moff, **out)
+        res = rb.rows_to_particle_major(out["res"], N)
+        ref_same = O.sweep_pose2pose2(ip, iq, seen(ctx, rb.POSE2, N), seen_meas(moff, mu, N))
+        assert_close(res, ref_same, angle_cols=(2,), what=f"N={N} flags={flags}", floor=FLOOR_SAME)
+        if flags & rb.STATS:
+            assert np.allclose(out["stats"][:, 0:3], res.sum(1), rtol=1e-3, atol=1e-3)
+    # sampled run == supplied run on the written-back samples, for every tile variant
+    fl = rb.RESIDUAL | rb.SAMPLE | rb.WRITE_MEAS
+    o1 = ctx.alloc_host_outputs(rb.POSE2POSE2, fl)
+    ctx.eval_host(rb.POSE2POSE2, fl, seed=3, **o1)
+    o2 = ctx.alloc_host_outputs(rb.POSE2POSE2, rb.RESIDUAL)
+    ctx.eval_host(rb.POSE2POSE2, rb.RESIDUAL, meas=o1["meas_out"], **o2)
+    assert np.array_equal(o1["res"][:, :N], o2["res"][:, :N])
+
+
+def test_too_many_particles_is_an_error(ctx):
+    ctx.set_particles(rb.POSE2, np.zeros((2, 6000, 3)))
+    ctx.set_factors_pose2pose2([0], [1], [[0, 0, 0]], [np.eye(3)])
+    out = ctx.alloc_host_outputs(rb.POSE2POSE2, rb.RESIDUAL | rb.SAMPLE)
+    with pytest.raises(rb.RomeB200Error) as ei:
+        ctx.eval_host(rb.POSE2POSE2, rb.RESIDUAL | rb.SAMPLE, **out)
+    assert ei.value.code == -3
+
+
+def test_empty_range_and_zero_factors(ctx):
+    rng = np.random.default_rng(5)
+    poses, ip, iq = make_pose2_graph(rng, 5, 7, 16)
+    ctx.set_particles(rb.POSE2, poses)
+    ctx.set_factors_pose2pose2(ip, iq, np.zeros((7, 3)), np.tile(np.eye(3), (7, 1, 1)))
+    out = ctx.alloc_host_outputs(rb.POSE2POSE2, rb.RESIDUAL | rb.SAMPLE)
+    before = ctx.launch_count
+    ctx.eval_host(rb.POSE2POSE2, rb.RESIDUAL | rb.SAMPLE, first=3, count=0, **out)  # nothing to do, no launch
+    assert ctx.launch_count == before and not out["res"].any()
+    ctx.eval_host(rb.POSE2POSE2, rb.RESIDUAL | rb.SAMPLE, first=6, count=1, **out)
+    assert out["res"][6].any() and not out["res"][:6].any()
+    with pytest.raises(rb.RomeB200Error):
+        ctx.eval_host(rb.POSE2POSE2, rb.RESIDUAL | rb.SAMPLE, first=5, count=3, **out)
+
+
+def test_independent_flag_gives_identical_results(ctx):
+    """ROME_B200_INDEPENDENT only changes scheduling (programmatic dependent launch)"""
+    import torch
+    rng = np.random.default_rng(31)
+    N, nF = 100, 3000
+    poses, ip, iq = make_pose2_graph(rng, 400, nF, N)
+    mu = rng.normal(size=(nF, 3))
+    ctx.set_particles(rb.POSE2, poses)
+    ctx.set_factors_pose2pose2(ip, iq, mu, rand_cov(rng, nF, 3, [0.1, 0.1, 0.02]))
+    Np = rb.npad(N)
+    ctx.use_torch_stream()
+    try:
+        bufs = [dict(res=torch.zeros((nF, Np, 3), device="cuda"), stats=torch.zeros((nF, 16), device="cuda"))
+                for _ in range(4)]
+        fl = rb.RESIDUAL | rb.STATS | rb.SAMPLE
+        ctx.eval(rb.POSE2POSE2, fl, seed=4, stream_id=0, **bufs[0])
+        for b in bufs[1:]:
+            ctx.eval(rb.POSE2POSE2, fl | rb.INDEPENDENT, seed=4, stream_id=0, **b)
+        torch.cuda.synchronize()
+        for b in bufs[1:]:
+            assert torch.equal(b["res"], bufs[0]["res"]) and torch.equal(b["stats"], bufs[0]["stats"])
+    finally:
+        ctx.set_stream(None)
