@@ -164,6 +164,19 @@ ROME_B200_API int rome_b200_eval(rome_b200_ctx* ctx, int family, uint32_t flags,
 ROME_B200_API int rome_b200_eval_host(rome_b200_ctx* ctx, int family, uint32_t flags, uint64_t seed, uint32_t stream_id,
                         int first, int count, const rome_b200_buffers* host_buffers);
 
+/* ---- multi-GPU: proposals written straight into the peers' buffers (fused compute + all-gather) ------------
+ * With peers set for a family, every evaluation with ROME_B200_PROPOSAL_FWD stores each factor's forward-proposal
+ * rows not only to `prop_fwd` but also, from the same shared-memory slice and by the same warp-local TMA bulk
+ * stores, to the identically indexed buffer of every peer (device pointers into the peers' memory, obtained with
+ * rome_b200_ipc_import over NVLink).  Ranks that split the factor list therefore end the kernel holding all
+ * proposals -- no separate all-gather pass; only a stream-ordered barrier between the ranks is still needed.
+ * n_peers <= 7; n_peers = 0 clears. */
+ROME_B200_API int rome_b200_set_peer_proposals(rome_b200_ctx* ctx, int family, int n_peers, float* const* peer_prop_fwd);
+/* CUDA IPC plumbing for buffers allocated with rome_b200_malloc_device (64-byte opaque handles). */
+ROME_B200_API int rome_b200_ipc_export(rome_b200_ctx* ctx, void* dev_ptr, unsigned char handle[64]);
+ROME_B200_API int rome_b200_ipc_import(rome_b200_ctx* ctx, const unsigned char handle[64], void** dev_ptr);
+ROME_B200_API int rome_b200_ipc_close(rome_b200_ctx* ctx, void* dev_ptr);
+
 /* ---- CUDA-graph capture of a sweep (several eval calls replayed with one launch) ------------- */
 ROME_B200_API int rome_b200_graph_begin(rome_b200_ctx* ctx);
 ROME_B200_API int rome_b200_graph_end(rome_b200_ctx* ctx, int* graph_id);

@@ -734,9 +734,13 @@ __global__ void __launch_bounds__((FT + 1) * 32, Fam::kMinCtas) eval_kernel(cons
                     if (lane == 0) {
                         if (flags & ROME_B200_RESIDUAL)
                             tma_store_1d(P.res + (size_t)f * res_floats, V.out_res, (uint32_t)(res_floats * 4));
-                        if (flags & ROME_B200_PROPOSAL_FWD)
-                            tma_store_1d(P.prop_fwd + (size_t)f * Fam::DFWD * P.Npad, V.out_fwd,
-                                         (uint32_t)(Fam::DFWD * P.Npad * 4));
+                        if (flags & ROME_B200_PROPOSAL_FWD) {
+                            const size_t off = (size_t)f * Fam::DFWD * P.Npad;
+                            const uint32_t bytes = (uint32_t)(Fam::DFWD * P.Npad * 4);
+                            tma_store_1d(P.prop_fwd + off, V.out_fwd, bytes);
+                            // fused all-gather: the same slice goes to every peer GPU over NVLink
+                            for (int r = 0; r < P.n_peers; ++r) tma_store_1d(P.peer_fwd[r] + off, V.out_fwd, bytes);
+                        }
                         tma_store_commit();
                     }
                 }

@@ -60,6 +60,8 @@ struct rome_b200_ctx {
     int smem_per_sm = 0, smem_per_cta_max = 0;
     Scratch stage_dev, stage_host;            // particle upload/download staging
     Scratch out_dev[8];                       // eval_host device mirrors: meas, meas_out, res, fwd, bwd, stats, jac
+    int n_peers[ROME_B200_NFAMILIES] = {0, 0, 0, 0, 0};
+    float* peers[ROME_B200_NFAMILIES][7] = {};
     std::vector<cudaGraphExec_t> graphs;
     std::vector<uint64_t> graph_kernels;
     bool capturing = false;
@@ -438,6 +440,8 @@ int rome_b200_eval(rome_b200_ctx* ctx, int family, uint32_t flags, uint64_t seed
     p.v0 = v0.store; p.v1 = v1.store;
     p.meas = b->meas; p.meas_out = b->meas_out; p.res = b->res; p.prop_fwd = b->prop_fwd; p.prop_bwd = b->prop_bwd;
     p.stats = b->stats; p.jac = b->jac;
+    p.n_peers = (flags & ROME_B200_PROPOSAL_FWD) ? ctx->n_peers[family] : 0;
+    for (int r = 0; r < 7; ++r) p.peer_fwd[r] = ctx->peers[family][r];
     p.flags = flags;
     p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32); p.stream_id = stream_id;
     LaunchPlan plan;
@@ -498,6 +502,42 @@ int rome_b200_eval_host(rome_b200_ctx* ctx, int family, uint32_t flags, uint64_t
     if (flags & ROME_B200_STATS) { if (int e = back(5, ss, hb->stats)) return e; }
     if (flags & ROME_B200_JACOBIAN) { if (int e = back(6, sj, hb->jac)) return e; }
     CK(cudaStreamSynchronize(ctx->stream));
+    return ROME_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+int rome_b200_set_peer_proposals(rome_b200_ctx* ctx, int family, int n_peers, float* const* peer_prop_fwd) {
+    if (!ctx) return ROME_B200_BAD_ARG;
+    if (family < 0 || family >= ROME_B200_NFAMILIES) return fail(ctx, ROME_B200_BAD_ARG, "bad family");
+    if (n_peers < 0 || n_peers > 7 || (n_peers > 0 && !peer_prop_fwd)) return fail(ctx, ROME_B200_BAD_ARG, "bad peer list");
+    for (int r = 0; r < n_peers; ++r)
+        if (!peer_prop_fwd[r] || ((uintptr_t)peer_prop_fwd[r] & 15))
+            return fail(ctx, ROME_B200_BAD_ARG, "peer buffers must be non-NULL and 16-byte aligned");
+    ctx->n_peers[family] = n_peers;
+    for (int r = 0; r < 7; ++r) ctx->peers[family][r] = r < n_peers ? peer_prop_fwd[r] : nullptr;
+    return ROME_B200_OK;
+}
+int rome_b200_ipc_export(rome_b200_ctx* ctx, void* dev_ptr, unsigned char handle[64]) {
+    if (!ctx || !dev_ptr || !handle) return ROME_B200_BAD_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    if (int e = bind(ctx)) return e;
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, dev_ptr));
+    std::memcpy(handle, &h, 64);
+    return ROME_B200_OK;
+}
+int rome_b200_ipc_import(rome_b200_ctx* ctx, const unsigned char handle[64], void** dev_ptr) {
+    if (!ctx || !dev_ptr || !handle) return ROME_B200_BAD_ARG;
+    if (int e = bind(ctx)) return e;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    CK(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return ROME_B200_OK;
+}
+int rome_b200_ipc_close(rome_b200_ctx* ctx, void* dev_ptr) {
+    if (!ctx) return ROME_B200_BAD_ARG;
+    if (int e = bind(ctx)) return e;
+    CK(cudaIpcCloseMemHandle(dev_ptr));
     return ROME_B200_OK;
 }
 

@@ -62,6 +62,8 @@ struct EvalParams {
     int stages;          // pipeline depth
     int stage_bytes;     // shared memory per stage
     int out_warp_bytes;  // shared-memory output staging per consumer warp (residual rows [+ forward proposal rows])
+    int n_peers;         // forward proposals are also stored to these peer-GPU buffers (fused all-gather)
+    float* peer_fwd[7];
 };
 
 // launch geometry chosen on the host for (family, sample, Npad)

@@ -219,6 +219,33 @@ class Context:
             out["jac"] = np.zeros((nF, Np, dj), np.float32)
         return out
 
+    # -- multi-GPU: fused all-gather of forward proposals ---------------------------------------
+    def set_peer_proposals(self, family: int, peer_ptrs):
+        """peer_ptrs: device pointers (ints) to the peers' identically shaped prop_fwd buffers; [] clears"""
+        arr = (C.c_void_p * max(1, len(peer_ptrs)))(*peer_ptrs)
+        self._ck(self._lib.rome_b200_set_peer_proposals(self._h, family, len(peer_ptrs), arr))
+
+    def malloc_device(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        self._ck(self._lib.rome_b200_malloc_device(self._h, nbytes, C.byref(p)))
+        return p.value
+
+    def free_device(self, ptr: int):
+        self._ck(self._lib.rome_b200_free_device(self._h, ptr))
+
+    def ipc_export(self, ptr: int) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._ck(self._lib.rome_b200_ipc_export(self._h, ptr, buf))
+        return buf.raw
+
+    def ipc_import(self, handle: bytes) -> int:
+        p = C.c_void_p()
+        self._ck(self._lib.rome_b200_ipc_import(self._h, handle, C.byref(p)))
+        return p.value
+
+    def memcpy_d2h(self, dst: np.ndarray, src_ptr: int):
+        self._ck(self._lib.rome_b200_memcpy_d2h(self._h, dst.ctypes.data, src_ptr, dst.nbytes))
+
     # -- CUDA graphs ---------------------------------------------------------------------------
     def graph_begin(self):
         self._ck(self._lib.rome_b200_graph_begin(self._h))

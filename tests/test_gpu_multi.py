@@ -1,0 +1,96 @@
+"""Two-GPU test (skipped on a single-GPU box): factor list sharded over 2 ranks, forward proposals exchanged
+(a) by the NCCL all-gather and (b) by the fused peer stores of the kernel itself (rome_b200_set_peer_proposals over
+CUDA IPC); both must leave every rank with the proposals of ALL factors, identical to a single-GPU evaluation."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    import rome_b200 as rb
+    from rome_b200 import sharding
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        rng = np.random.default_rng(0)  # same graph on every rank
+        N, nvars, nF = 100, 300, 2000
+        heading = rng.uniform(-np.pi, np.pi, nvars)
+        xy = np.cumsum(10 * np.column_stack([np.cos(heading), np.sin(heading)]), 0)
+        poses = np.column_stack([xy, heading])[:, None, :] + rng.normal(size=(nvars, N, 3)) * [0.1, 0.1, 0.02]
+        ip = rng.integers(0, nvars - 1, nF).astype(np.int32)
+        iq = (ip + 1).astype(np.int32)
+        mu = rng.normal(size=(nF, 3)) * [5, 1, 0.5]
+        cov = np.tile(np.diag([0.01, 0.01, 0.001]), (nF, 1, 1))
+        Np = rb.npad(N)
+        ctx = rb.Context(rank)
+        ctx.use_torch_stream()
+        ctx.set_particles(rb.POSE2, poses)
+        ctx.set_factors_pose2pose2(ip, iq, mu, cov)
+        flags = rb.SAMPLE | rb.RESIDUAL | rb.STATS | rb.PROPOSAL_FWD
+        c = sharding.shard_size(nF, world)
+        first, count = sharding.shard_range(nF, rank, world)
+        res = torch.zeros((nF, Np, 3), device="cuda")
+        st = torch.zeros((nF, 16), device="cuda")
+        # reference: everything on this GPU
+        full = torch.zeros((world * c, Np, 3), device="cuda")
+        ctx.eval(rb.POSE2POSE2, flags, seed=5, res=res, stats=st, prop_fwd=full)
+        torch.cuda.synchronize()
+        # (a) NCCL all-gather of the rank's slice
+        a = torch.zeros((world * c, Np, 3), device="cuda")
+        ctx.eval(rb.POSE2POSE2, flags, seed=5, first=first, count=count, res=res, stats=st, prop_fwd=a)
+        sharding.allgather_rows(a, nF)
+        torch.cuda.synchronize()
+        ok_a = bool(torch.equal(a[:nF], full[:nF]))
+        # (b) fused: the kernel stores its proposal rows into every peer's buffer
+        nbytes = world * c * Np * 3 * 4
+        mine = ctx.malloc_device(nbytes)
+        torch.cuda.synchronize()
+        handles = [None] * world
+        dist.all_gather_object(handles, ctx.ipc_export(mine))
+        peers = [ctx.ipc_import(h) for r, h in enumerate(handles) if r != rank]
+        ctx.set_peer_proposals(rb.POSE2POSE2, peers)
+        ctx.eval(rb.POSE2POSE2, flags, seed=5, first=first, count=count, res=res, stats=st, prop_fwd=mine)
+        token = torch.zeros(1, device="cuda")
+        dist.all_reduce(token)  # stream-ordered barrier between the ranks
+        torch.cuda.synchronize()
+        got = np.empty((world * c, Np, 3), np.float32)
+        ctx.memcpy_d2h(got, mine)
+        ok_b = bool(np.array_equal(got[:nF], full[:nF].cpu().numpy()))
+        ctx.set_peer_proposals(rb.POSE2POSE2, [])
+        dist.barrier()
+        q.put((rank, ok_a, ok_b))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_exchange_nccl_and_fused():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in ps)
+    for p in ps:
+        p.join(timeout=120)
+    assert res == [(0, True, True), (1, True, True)], res
