@@ -238,11 +238,18 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="do not let consecutive (independent) steps overlap")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+                    help="N>1: proposals reach the peers by the kernel's own TMA stores (fused) or by an NCCL all-gather")
     ap.add_argument("--e2e-steps", type=int, default=20)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
 
+    # stdout must carry exactly one JSON line: park fd 1 on stderr while libraries (NCCL prints its version banner to
+    # stdout) initialise and run; it is restored just before the line is printed
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     import rome_b200 as rb
@@ -274,14 +281,25 @@ def main():
             c.set_factors_pose2pose2(w["ip"], w["iq"], w["mu"], w["cov"])
             c.set_factors_priorpose2(w["pr_ip"], w["pr_mu"], w["pr_cov"])
             bufs = dict(res=torch.zeros((F, Np, 3), device="cuda"), stats=torch.zeros((F, 16), device="cuda"))
-            if multi:
-                bufs["prop_fwd"] = torch.zeros((F, Np, 3), device="cuda")
             pb = dict(res=torch.zeros((len(w["pr_ip"]), Np, 3), device="cuda"),
                       stats=torch.zeros((len(w["pr_ip"]), 16), device="cuda"))
-            if multi:
+            if multi and args.exchange == "nccl":
+                bufs["prop_fwd"] = torch.zeros((F, Np, 3), device="cuda")
                 pb["prop_fwd"] = torch.zeros((len(w["pr_ip"]), Np, 3), device="cuda")
+            elif multi:  # fused exchange: plain cudaMalloc buffers that the peers map through CUDA IPC
+                bufs["prop_fwd"] = c.malloc_device(F * Np * 3 * 4)
+                pb["prop_fwd"] = c.malloc_device(len(w["pr_ip"]) * Np * 3 * 4)
             sets.append((c, bufs, pb))
         stream.synchronize()
+        if multi and args.exchange == "fused":
+            mine = [(c.ipc_export(b["prop_fwd"]), c.ipc_export(p["prop_fwd"])) for c, b, p in sets]
+            everyone = [None] * G
+            dist.all_gather_object(everyone, mine)
+            for si, (c, b, p) in enumerate(sets):
+                c.set_peer_proposals(rb.POSE2POSE2, [c.ipc_import(everyone[r][si][0]) for r in range(G) if r != rank])
+                c.set_peer_proposals(rb.PRIORPOSE2, [c.ipc_import(everyone[r][si][1]) for r in range(G) if r != rank])
+            token = torch.zeros(1, device="cuda")
+            dist.barrier()
 
     n_prior = len(w["pr_ip"]) // G
     evals_per_step_rank = (F0 + n_prior) * N
@@ -291,20 +309,28 @@ def main():
     pflags = rb.RESIDUAL | rb.STATS
 
     def step(k, indep):
-        """one pass of the hot path over the graph: the two family kernels have no mutual dependency and run
-        concurrently (fork/join on a side stream, captured into the graph as parallel branches).  With `indep`
-        the Pose2Pose2 launch carries ROME_B200_INDEPENDENT: consecutive steps work on different working-set copies,
-        so a step may start on SMs the previous step has already vacated (programmatic dependent launch)."""
+        """one pass of the hot path over the graph.  The two family kernels have no mutual dependency: PriorPose2 runs on a
+        side stream (a parallel branch of the captured graph).  With `indep` the Pose2Pose2 launch carries
+        ROME_B200_INDEPENDENT: consecutive steps work on different working-set copies, so a step may start on SMs the
+        previous step has already vacated (programmatic dependent launch).  N>1: the exchange of step k (NCCL
+        all-gather, or -- fused -- only the barrier that follows the kernels' own peer stores) is issued on the side
+        stream after both kernels of the step, and overlaps the kernels of step k+1."""
         c, bufs, pb = sets[k % S]
-        side.wait_stream(stream)
         c.set_stream(side.cuda_stream)
         c.eval(rb.PRIORPOSE2, flags, seed=7, stream_id=k, first=rank * n_prior, count=n_prior, **pb)
         c.set_stream(stream.cuda_stream)
         c.eval(rb.POSE2POSE2, flags | (rb.INDEPENDENT if indep else 0), seed=7, stream_id=k, first=first, count=F0,
                **bufs)
-        stream.wait_stream(side)
-        if multi:  # the one exchange of the path: proposals of every rank's factors to every rank
-            sharding.allgather_rows(bufs["prop_fwd"], F)
+        if multi:
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            side.wait_event(ev)
+            with torch.cuda.stream(side):
+                if args.exchange == "nccl":  # the one exchange of the path: every rank's proposals to every rank
+                    sharding.allgather_rows(bufs["prop_fwd"], F)
+                    sharding.allgather_rows(pb["prop_fwd"], len(w["pr_ip"]))
+                else:  # the kernels already stored their rows into every peer: a stream-ordered barrier is left
+                    dist.all_reduce(token)
 
     def kernel_only(k, indep):
         c, bufs, _ = sets[k % S]
@@ -321,8 +347,10 @@ def main():
         with torch.cuda.graph(gr, stream=stream):
             for c, _, _ in sets:
                 c.use_torch_stream()
+            side.wait_stream(stream)  # fork the side branch
             for k in range(args.steps):
                 fn(args.warmup + k, indep)
+            stream.wait_stream(side)  # join
         for c, _, _ in sets:
             c.use_torch_stream()
         gr.replay()  # untimed replay: graph upload + warm instruction caches
@@ -350,8 +378,10 @@ def main():
     clocks = ClockSampler(local)
     overlap = not args.no_overlap
     with torch.cuda.stream(stream):
+        side.wait_stream(stream)
         for k in range(args.warmup):
             step(k, False)
+        stream.wait_stream(side)
         stream.synchronize()
         g = capture(step, overlap)
         ms = timed(g, sample_clocks=True)
@@ -434,7 +464,9 @@ def main():
             "config": {"workload": WORKLOAD, "poses_per_gpu": NPOSES, "particles": N, "npad": Np,
                        "factors_per_gpu": F0 + n_prior, "evals_per_step": evals_per_step,
                        "step": "getSample (in-kernel Philox) + residual + per-factor stats for every factor x particle"
-                               + ("; + closed-form proposals and one NCCL all-gather of them" if multi else ""),
+                               + (("; + closed-form proposals, stored by the kernel's own TMA bulk stores into every peer GPU over NVLink "
+                                  "(fused all-gather) + a 4-byte NCCL all-reduce as barrier" if args.exchange == "fused" else
+                                  "; + closed-form proposals and one NCCL all-gather of them") if multi else ""),
                        "storage": "anchored float32 (Float64 anchor + float32 offset)",
                        "l2": f"{S} rotating working-set copies (> 2x L2); K steps replayed from one CUDA graph",
                        "overlap": ("consecutive steps are independent (different working-set copies) and launched with "
@@ -470,6 +502,8 @@ def main():
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": nt, "kind": "port",
                                     "sample": f"{reps} full residual sweeps ({F0 + n_prior} factors x {N} particles) in {dt:.1f} s"}
             line["cpu_reference_shaped"] = cpu_reference_shaped(w)
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
     if multi:
         # CUDA graphs that captured NCCL work must die before the communicator; then leave without the
