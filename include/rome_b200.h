@@ -164,6 +164,13 @@ ROME_B200_API int rome_b200_eval(rome_b200_ctx* ctx, int family, uint32_t flags,
 ROME_B200_API int rome_b200_eval_host(rome_b200_ctx* ctx, int family, uint32_t flags, uint64_t seed, uint32_t stream_id,
                         int first, int count, const rome_b200_buffers* host_buffers);
 
+/* Same without the final synchronisation: copies and kernels are only enqueued on the ctx stream; host buffers must
+ * be pinned (rome_b200_malloc_host) and stay untouched until rome_b200_synchronize(ctx).  Lets a caller overlap the
+ * upload of one context with the download of another (two contexts, two streams). */
+ROME_B200_API int rome_b200_eval_host_async(rome_b200_ctx* ctx, int family, uint32_t flags, uint64_t seed,
+                                            uint32_t stream_id, int first, int count,
+                                            const rome_b200_buffers* host_buffers);
+
 /* ---- multi-GPU: proposals written straight into the peers' buffers (fused compute + all-gather) ------------
  * With peers set for a family, every evaluation with ROME_B200_PROPOSAL_FWD stores each factor's forward-proposal
  * rows not only to `prop_fwd` but also, from the same shared-memory slice and by the same warp-local TMA bulk

@@ -21,7 +21,7 @@ SYMBOLS = [
     "rome_b200_set_particles", "rome_b200_get_particles", "rome_b200_particles_device", "rome_b200_adopt_proposal",
     "rome_b200_set_factors_pose2pose2", "rome_b200_set_factors_priorpose2", "rome_b200_set_factors_bearingrange",
     "rome_b200_set_factors_pose3pose3", "rome_b200_set_factors_priorpose3", "rome_b200_num_factors",
-    "rome_b200_eval", "rome_b200_eval_host", "rome_b200_set_peer_proposals", "rome_b200_ipc_export",
+    "rome_b200_eval", "rome_b200_eval_host", "rome_b200_eval_host_async", "rome_b200_set_peer_proposals", "rome_b200_ipc_export",
     "rome_b200_ipc_import", "rome_b200_ipc_close", "rome_b200_graph_begin", "rome_b200_graph_end",
     "rome_b200_graph_launch", "rome_b200_malloc_device", "rome_b200_free_device", "rome_b200_malloc_host",
     "rome_b200_free_host", "rome_b200_memcpy_h2d", "rome_b200_memcpy_d2h", "rome_b200_launch_count",
@@ -74,6 +74,7 @@ def load() -> C.CDLL:
     lib.rome_b200_num_factors.argtypes = [vp, i]
     lib.rome_b200_eval.argtypes = [vp, i, u32, u64, u32, i, i, C.POINTER(Buffers)]
     lib.rome_b200_eval_host.argtypes = [vp, i, u32, u64, u32, i, i, C.POINTER(Buffers)]
+    lib.rome_b200_eval_host_async.argtypes = [vp, i, u32, u64, u32, i, i, C.POINTER(Buffers)]
     lib.rome_b200_set_peer_proposals.argtypes = [vp, i, i, C.POINTER(vp)]
     lib.rome_b200_ipc_export.argtypes = [vp, vp, C.c_char_p]
     lib.rome_b200_ipc_import.argtypes = [vp, C.c_char_p, C.POINTER(vp)]

@@ -59,7 +59,7 @@ struct rome_b200_ctx {
     FactorStore fac[ROME_B200_NFAMILIES];
     int smem_per_sm = 0, smem_per_cta_max = 0;
     Scratch stage_dev, stage_host;            // particle upload/download staging
-    Scratch out_dev[8];                       // eval_host device mirrors: meas, meas_out, res, fwd, bwd, stats, jac
+    Scratch out_dev[ROME_B200_NFAMILIES][8];  // eval_host device mirrors per family: meas, meas_out, res, fwd, bwd, stats, jac
     int n_peers[ROME_B200_NFAMILIES] = {0, 0, 0, 0, 0};
     float* peers[ROME_B200_NFAMILIES][7] = {};
     std::vector<cudaGraphExec_t> graphs;
@@ -226,7 +226,7 @@ int rome_b200_destroy(rome_b200_ctx* ctx) {
     for (auto& f : ctx->fac) cudaFree(f.rows);
     cudaFree(ctx->stage_dev.p);
     cudaFreeHost(ctx->stage_host.p);
-    for (auto& s : ctx->out_dev) cudaFree(s.p);
+    for (auto& f : ctx->out_dev) for (auto& s : f) cudaFree(s.p);
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return ROME_B200_OK;
@@ -457,8 +457,8 @@ int rome_b200_eval(rome_b200_ctx* ctx, int family, uint32_t flags, uint64_t seed
     return ROME_B200_OK;
 }
 
-int rome_b200_eval_host(rome_b200_ctx* ctx, int family, uint32_t flags, uint64_t seed, uint32_t stream_id, int first,
-                        int count, const rome_b200_buffers* hb) {
+static int eval_host_impl(rome_b200_ctx* ctx, int family, uint32_t flags, uint64_t seed, uint32_t stream_id, int first,
+                          int count, const rome_b200_buffers* hb, bool sync) {
     if (int e = check_eval(ctx, family, flags, first, count, hb)) return e;
     if (ctx->capturing) return fail(ctx, ROME_B200_BAD_ARG, "eval_host during graph capture");
     if (count == 0) return ROME_B200_OK;
@@ -471,15 +471,15 @@ int rome_b200_eval_host(rome_b200_ctx* ctx, int family, uint32_t flags, uint64_t
     rome_b200_buffers db;
     std::memset(&db, 0, sizeof db);
     auto mirror = [&](int slot, size_t stride, float** out) -> int {
-        if (int e = grow_dev(ctx, ctx->out_dev[slot], (size_t)count * stride * sizeof(float))) return e;
+        if (int e = grow_dev(ctx, ctx->out_dev[family][slot], (size_t)count * stride * sizeof(float))) return e;
         // kernels index buffers by global factor id: bias the mirror base by -first
-        *out = static_cast<float*>(ctx->out_dev[slot].p) - (size_t)first * stride;
+        *out = static_cast<float*>(ctx->out_dev[family][slot].p) - (size_t)first * stride;
         return 0;
     };
     float* tmp = nullptr;
     if (!(flags & ROME_B200_SAMPLE)) {
         if (int e = mirror(0, sm, &tmp)) return e;
-        CK(cudaMemcpyAsync(ctx->out_dev[0].p, hb->meas + (size_t)first * sm, (size_t)count * sm * sizeof(float),
+        CK(cudaMemcpyAsync(ctx->out_dev[family][0].p, hb->meas + (size_t)first * sm, (size_t)count * sm * sizeof(float),
                            cudaMemcpyDefault, ctx->stream));
         db.meas = tmp;
     }
@@ -491,7 +491,7 @@ int rome_b200_eval_host(rome_b200_ctx* ctx, int family, uint32_t flags, uint64_t
     if (flags & ROME_B200_JACOBIAN) { if (int e = mirror(6, sj, &db.jac)) return e; }
     if (int e = rome_b200_eval(ctx, family, flags, seed, stream_id, first, count, &db)) return e;
     auto back = [&](int slot, size_t stride, float* host) -> int {
-        CK(cudaMemcpyAsync(host + (size_t)first * stride, ctx->out_dev[slot].p, (size_t)count * stride * sizeof(float),
+        CK(cudaMemcpyAsync(host + (size_t)first * stride, ctx->out_dev[family][slot].p, (size_t)count * stride * sizeof(float),
                            cudaMemcpyDefault, ctx->stream));
         return 0;
     };
@@ -501,8 +501,17 @@ int rome_b200_eval_host(rome_b200_ctx* ctx, int family, uint32_t flags, uint64_t
     if (flags & ROME_B200_PROPOSAL_BWD) { if (int e = back(4, sb, hb->prop_bwd)) return e; }
     if (flags & ROME_B200_STATS) { if (int e = back(5, ss, hb->stats)) return e; }
     if (flags & ROME_B200_JACOBIAN) { if (int e = back(6, sj, hb->jac)) return e; }
-    CK(cudaStreamSynchronize(ctx->stream));
+    if (sync) CK(cudaStreamSynchronize(ctx->stream));
     return ROME_B200_OK;
+}
+
+int rome_b200_eval_host(rome_b200_ctx* ctx, int family, uint32_t flags, uint64_t seed, uint32_t stream_id, int first,
+                        int count, const rome_b200_buffers* hb) {
+    return eval_host_impl(ctx, family, flags, seed, stream_id, first, count, hb, true);
+}
+int rome_b200_eval_host_async(rome_b200_ctx* ctx, int family, uint32_t flags, uint64_t seed, uint32_t stream_id,
+                              int first, int count, const rome_b200_buffers* hb) {
+    return eval_host_impl(ctx, family, flags, seed, stream_id, first, count, hb, false);
 }
 
 // ---------------------------------------------------------------------------------------------

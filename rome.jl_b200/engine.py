@@ -194,10 +194,12 @@ class Context:
         self._ck(self._lib.rome_b200_eval(self._h, family, flags, seed, stream_id, first, count, C.byref(b)))
 
     def eval_host(self, family, flags, *, seed=0, stream_id=0, first=0, count=-1, meas=None, meas_out=None,
-                  res=None, prop_fwd=None, prop_bwd=None, stats=None, jac=None):
-        """Synchronous call with HOST buffers (numpy float32 / pinned tensors)."""
+                  res=None, prop_fwd=None, prop_bwd=None, stats=None, jac=None, sync=True):
+        """Call with HOST buffers (numpy float32 / pinned tensors).  sync=False only enqueues (pinned buffers
+        required); call synchronize() before reading the outputs."""
         b = self._buffers(meas, meas_out, res, prop_fwd, prop_bwd, stats, jac)
-        self._ck(self._lib.rome_b200_eval_host(self._h, family, flags, seed, stream_id, first, count, C.byref(b)))
+        fn = self._lib.rome_b200_eval_host if sync else self._lib.rome_b200_eval_host_async
+        self._ck(fn(self._h, family, flags, seed, stream_id, first, count, C.byref(b)))
 
     def alloc_host_outputs(self, family, flags):
         """numpy float32 output arrays, shaped for all factors of the family, for eval_host."""
