@@ -35,7 +35,8 @@ namespace rome {
 struct Quat {
     double w, x, y, z;
 };
-__device__ __forceinline__ Quat quat_exp(double wx, double wy, double wz) {
+// general path: any rotation vector
+__device__ __noinline__ Quat quat_exp_general(double wx, double wy, double wz) {
     const double t2 = wx * wx + wy * wy + wz * wz;
     double k, c;
     if (t2 < 1e-8) {
@@ -49,16 +50,31 @@ __device__ __forceinline__ Quat quat_exp(double wx, double wy, double wz) {
     }
     return {c, k * wx, k * wy, k * wz};
 }
+// Exp of a rotation vector with |w| <= pi (the principal range) without sqrt, division or range reduction:
+// with y = theta/4 <= pi/4 the fdlibm kernels give cos y and sin(y)/y as polynomials in y^2 = |w|^2/16, and
+//   cos(theta/2) = 2 cos^2 y - 1,   sin(theta/2)/theta = (sin(y)/y) cos(y) / 2.
+__device__ __forceinline__ Quat quat_exp(double wx, double wy, double wz) {
+    const double t2 = wx * wx + wy * wy + wz * wz;
+    if (t2 > 9.8696) return quat_exp_general(wx, wy, wz);  // |w| > pi: non-principal rotation vector
+    const double z = t2 * 0.0625;
+    double ps = fma(z, kSinC[5], kSinC[4]);
+    double pc = fma(z, kCosC[5], kCosC[4]);
+    ps = fma(z, ps, kSinC[3]); pc = fma(z, pc, kCosC[3]);
+    ps = fma(z, ps, kSinC[2]); pc = fma(z, pc, kCosC[2]);
+    ps = fma(z, ps, kSinC[1]); pc = fma(z, pc, kCosC[1]);
+    ps = fma(z, ps, kSinC[0]); pc = fma(z, pc, kCosC[0]);
+    const double sy = fma(z, ps, 1.0);                       // sin(y)/y
+    const double cy = fma(z * z, pc, fma(z, -0.5, 1.0));     // cos(y)
+    const double k = 0.5 * sy * cy;
+    return {fma(2.0 * cy, cy, -1.0), k * wx, k * wy, k * wz};
+}
 __device__ __forceinline__ Quat qmul(const Quat& a, const Quat& b) {
     return {a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z, a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y,
             a.w * b.y - a.x * b.z + a.y * b.w + a.z * b.x, a.w * b.z + a.x * b.y - a.y * b.x + a.z * b.w};
 }
 __device__ __forceinline__ Quat qconj(const Quat& a) { return {a.w, -a.x, -a.y, -a.z}; }
-// rotation vector (angle in [0, pi]) of a unit quaternion
-__device__ __forceinline__ void quat_log(Quat q, double& x, double& y, double& z) {
-    if (q.w < 0.0) {
-        q.w = -q.w; q.x = -q.x; q.y = -q.y; q.z = -q.z;
-    }
+// rotation vector (angle in [0, pi]) of a unit quaternion: general path
+__device__ __noinline__ void quat_log_general(Quat q, double& x, double& y, double& z) {
     const double n2 = q.x * q.x + q.y * q.y + q.z * q.z;
     double k;
     if (n2 < 1e-16) {
@@ -67,6 +83,34 @@ __device__ __forceinline__ void quat_log(Quat q, double& x, double& y, double& z
         const double n = sqrt(n2);
         k = 2.0 * atan2(n, q.w) / n;
     }
+    x = k * q.x; y = k * q.y; z = k * q.z;
+}
+// Small rotations (the residual of a consistent factor): with u = |v|/w <= 0.1 (angle <= 0.2 rad),
+//   2 atan2(|v|, w)/|v| = (2/w) * atan(u)/u,  atan(u)/u = sum (-u^2)^k/(2k+1) (8 terms reach 1e-17),
+// 1/w by three Newton steps from 2 - w (w >= 0.995).  No sqrt, no division, no atan2.
+__device__ __forceinline__ void quat_log(Quat q, double& x, double& y, double& z) {
+    if (q.w < 0.0) {
+        q.w = -q.w; q.x = -q.x; q.y = -q.y; q.z = -q.z;
+    }
+    const double n2 = q.x * q.x + q.y * q.y + q.z * q.z;
+    if (n2 > 0.0099 * q.w * q.w) {
+        quat_log_general(q, x, y, z);
+        return;
+    }
+    double r = 2.0 - q.w;
+    r = r * fma(-q.w, r, 2.0);
+    r = r * fma(-q.w, r, 2.0);
+    r = r * fma(-q.w, r, 2.0);
+    const double u2 = -n2 * r * r;
+    double p = fma(u2, 1.0 / 17.0, 1.0 / 15.0);
+    p = fma(u2, p, 1.0 / 13.0);
+    p = fma(u2, p, 1.0 / 11.0);
+    p = fma(u2, p, 1.0 / 9.0);
+    p = fma(u2, p, 1.0 / 7.0);
+    p = fma(u2, p, 1.0 / 5.0);
+    p = fma(u2, p, 1.0 / 3.0);
+    p = fma(u2, p, 1.0);
+    const double k = 2.0 * r * p;
     x = k * q.x; y = k * q.y; z = k * q.z;
 }
 __device__ __forceinline__ void quat_rotate(const Quat& q, double vx, double vy, double vz, double& ox, double& oy,
