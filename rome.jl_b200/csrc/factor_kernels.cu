@@ -399,7 +399,12 @@ struct FamBearingRange {
         const float* Pp = reinterpret_cast<const float*>(V.b0 + var_header_bytes(3));
         const float* Lp = reinterpret_cast<const float*>(V.b1 + var_header_bytes(2));
         const double apt = ap[2];
-        const double dax = al[0] - ap[0], day = al[1] - ap[1];  // anchor(l) - anchor(p)
+        const double dax = al[0] - ap[0], day = al[1] - ap[1];  // D = anchor(l) - anchor(p)
+        // per factor: direction and inverse squared length of D; per particle the bearing is then
+        // atan(d) = atan(D) + atan(cross(D, delta) / (|D|^2 + D.delta)) with a small second term
+        const double D2 = dax * dax + day * day;
+        const double iD2 = 1.0 / D2;
+        const double phi0 = atan2(day, dax);
         const size_t fo = (size_t)f * 2 * Npad;
         const bool want_stats = flags & ROME_B200_STATS;
         float st[16];
@@ -420,11 +425,34 @@ struct FamBearingRange {
                     __stcs(reinterpret_cast<float2*>(P.meas_out + fo + 2 * n), make_float2(mb, mr));
             }
             const double b = row.mu_b + (double)mb, rho = row.mu_r + (double)mr;
-            const double dx = dax + (dlx - dpx), dy = day + (dly - dpy);
+            const double ex = dlx - dpx, ey = dly - dpy;  // delta: particle offsets (small against D)
+            const double dx = dax + ex, dy = day + ey;
             const double th = apt + dpt;
             const double d2 = dx * dx + dy * dy;
             const double rng = sqrt(d2);
-            double e1d = wrap_pi(b + th - atan2(dy, dx));
+            const double cr = dax * ey - day * ex;        // cross(D, delta)
+            const double dt = fma(dax, ex, fma(day, ey, D2));  // D.d = |D|^2 + D.delta
+            double phi;
+            if (fabs(dt * iD2 - 1.0) <= 0.1 && fabs(cr) <= 0.1 * dt) {
+                double r = iD2;  // 1/dt by Newton from 1/|D|^2 (relative start error <= 0.1 -> 1e-16 after 4 steps)
+                r = r * fma(-dt, r, 2.0);
+                r = r * fma(-dt, r, 2.0);
+                r = r * fma(-dt, r, 2.0);
+                r = r * fma(-dt, r, 2.0);
+                const double u = cr * r, u2 = -u * u;     // |u| <= 0.1: atan(u) = u * sum (-u^2)^k / (2k+1)
+                double p = fma(u2, 1.0 / 17.0, 1.0 / 15.0);
+                p = fma(u2, p, 1.0 / 13.0);
+                p = fma(u2, p, 1.0 / 11.0);
+                p = fma(u2, p, 1.0 / 9.0);
+                p = fma(u2, p, 1.0 / 7.0);
+                p = fma(u2, p, 1.0 / 5.0);
+                p = fma(u2, p, 1.0 / 3.0);
+                p = fma(u2, p, 1.0);
+                phi = fma(u, p, phi0);
+            } else {
+                phi = atan2(dy, dx);
+            }
+            double e1d = wrap_pi(b + th - phi);
             if (fabs(e1d - kPi) <= 1.4901161193847656e-08 * kPi) e1d = -kPi;  // sym_rem: +pi -> -pi
             const float e1 = (float)e1d, e2 = (float)(rho - rng);
             const float msk = (nn < N) ? 1.f : 0.f;
