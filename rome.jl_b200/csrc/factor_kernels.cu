@@ -238,7 +238,7 @@ __device__ __forceinline__ void normals_for_group(const EvalParams& P, int f, in
 
 struct FamPose2Pose2 {
     using Row = RowSE2;
-    static constexpr int D0 = 3, D1 = 3, DM = 3, DR = 3, DFWD = 3, kMinCtas = 3;
+    static constexpr int D0 = 3, D1 = 3, DM = 3, DR = 3, DFWD = 3, kMinCtas = 2;
     template <uint32_t kStatic, bool kSample>
     static __device__ __forceinline__ void factor(const Row& row, const EvalParams& P, const FactorView& V, int f,
                                                   int lane) {
@@ -857,14 +857,14 @@ int plan_launch(int family, uint32_t flags, int Npad, int smem_per_sm, int smem_
         const int out_warp = (fd.dr + (variant == 1 ? 0 : fd.dfwd)) * Npad * 4;
         const StageLayout L = stage_layout(ft, fd.row_bytes, fd.d0, fd.d1, fd.dm, sample, Npad);
         // prefer 2 CTAs/SM (register cap of the SE(2) kernels allows it) with >= 3 stages each, else 1 CTA/SM
-        for (int ctas = (se3 ? 1 : (family == ROME_B200_POSE2POSE2 ? 3 : 2)); ctas >= 1; --ctas) {
+        for (int ctas = (se3 ? 1 : 2); ctas >= 1; --ctas) {
             const int budget = (smem_per_sm / ctas) - 1024;  // 1 KB per CTA is reserved by the system
             const int cap = budget < smem_per_cta_max ? budget : smem_per_cta_max;
             int stages = (cap - kBarrierBytes - ft * out_warp) / L.bytes;
             if (stages > kMaxStages) stages = kMaxStages;
-            const int need = ctas >= 2 ? 3 : 2;
+            const int need = ctas == 2 ? 3 : 2;
             if (stages >= need) {
-                if (ctas >= 2 && stages > 4) stages = 4;
+                if (ctas == 2 && stages > 4) stages = 4;
                 plan->ft = ft; plan->variant = variant; plan->stages = stages;
                 plan->stage_bytes = L.bytes;
                 plan->out_warp_bytes = out_warp;
