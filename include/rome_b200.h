@@ -76,7 +76,14 @@ enum rome_b200_family {
     ROME_B200_BEARINGRANGE = 2,
     ROME_B200_POSE3POSE3 = 3,
     ROME_B200_PRIORPOSE3 = 4,
-    ROME_B200_NFAMILIES = 5
+    /* next-row families, same kernel template */
+    ROME_B200_PRIORPOINT2 = 5,        /* src/factors/Point2D.jl:8-18      r = m - x                       */
+    ROME_B200_POINT2POINT2 = 6,       /* src/factors/Point2D.jl:25-35     r = m - (xj - xi)               */
+    ROME_B200_POSE2POINT2 = 7,        /* src/factors/Pose2Point2.jl:9-40  r = l - (p.t + R_p m)           */
+    ROME_B200_POSE2POINT2RANGE = 8,   /* src/factors/Range2D.jl:43-54     r = rho - |l - p.t|             */
+    ROME_B200_POINT2POINT2RANGE = 9,  /* src/factors/Range2D.jl:5-18      r = rho - |xj - xi|             */
+    ROME_B200_POSE2POINT2BEARING = 10,/* src/factors/Bearing2D.jl:13-32   r = sym_rem(b - atan(R_p'(l-p.t))) */
+    ROME_B200_NFAMILIES = 11
 };
 
 /* eval flags */
@@ -150,6 +157,14 @@ ROME_B200_API int rome_b200_set_factors_pose3pose3(rome_b200_ctx* ctx, int nF, c
 /* PriorPose3(MvNormal(mu, cov)): src/factors/Pose3D.jl:9-11 */
 ROME_B200_API int rome_b200_set_factors_priorpose3(rome_b200_ctx* ctx, int nF, const int32_t* ip, const double* mu,
                                      const double* cov);
+/* 2-D Gaussian point factors: family in {PRIORPOINT2 (i1 = NULL), POINT2POINT2, POSE2POINT2};
+ * mu [nF][2], cov row-major [nF][2][2] */
+ROME_B200_API int rome_b200_set_factors_point2(rome_b200_ctx* ctx, int family, int nF, const int32_t* i0, const int32_t* i1,
+                                               const double* mu, const double* cov);
+/* scalar factors with a Normal belief: family in {POSE2POINT2RANGE, POINT2POINT2RANGE, POSE2POINT2BEARING};
+ * belief [nF][2] = (mean, standard deviation) */
+ROME_B200_API int rome_b200_set_factors_scalar(rome_b200_ctx* ctx, int family, int nF, const int32_t* i0, const int32_t* i1,
+                                               const double* belief);
 ROME_B200_API int rome_b200_num_factors(rome_b200_ctx* ctx, int family);
 
 /* ---- the hot path --------------------------------------------------------------------------- */

@@ -46,7 +46,8 @@ def lib() -> C.CDLL:
         for name, n in [("pose2pose2", 4), ("priorpose2", 3), ("bearingrange", 4), ("pose3pose3", 4),
                         ("priorpose3", 3), ("pose2pose2_fwd", 3), ("pose2pose2_bwd", 3),
                         ("bearingrange_fwd", 3), ("pose3pose3_fwd", 3), ("pose3pose3_bwd", 3),
-                        ("so3_exp", 2), ("so3_log", 2)]:
+                        ("so3_exp", 2), ("so3_log", 2), ("priorpoint2", 3), ("point2point2", 4), ("pose2point2", 4),
+                        ("range2", 4), ("pose2point2bearing", 4)]:
             fn = getattr(_lib, "rome_oracle_" + name)
             fn.restype = None
             fn.argtypes = [d] * n
@@ -108,6 +109,53 @@ def pose3pose3(X, p, q):
 
 def priorpose3(m, p):
     return _call("priorpose3", 6, m, p)
+
+
+def priorpoint2(m, x):
+    return _call("priorpoint2", 2, m, x)
+
+
+def point2point2(m, xi, xj):
+    return _call("point2point2", 2, m, xi, xj)
+
+
+def pose2point2(m, p, l):
+    return _call("pose2point2", 2, m, p, l)
+
+
+def range2(rho, xi, l):
+    return _call("range2", 1, np.atleast_1d(rho), np.asarray(xi, dtype=float)[:2], l)
+
+
+def pose2point2bearing(b, p, l):
+    return _call("pose2point2bearing", 1, np.atleast_1d(b), p, l)
+
+
+def np_priorpoint2(m, x):
+    return np.asarray(m, dtype=np.float64) - np.asarray(x, dtype=np.float64)
+
+
+def np_point2point2(m, xi, xj):
+    return np.asarray(m, dtype=np.float64) - (np.asarray(xj, dtype=np.float64) - np.asarray(xi, dtype=np.float64))
+
+
+def np_pose2point2(m, p, l):
+    m, p, l = (np.asarray(a, dtype=np.float64) for a in (m, p, l))
+    c, s = np.cos(p[..., 2]), np.sin(p[..., 2])
+    return np.stack([l[..., 0] - (p[..., 0] + c * m[..., 0] - s * m[..., 1]),
+                     l[..., 1] - (p[..., 1] + s * m[..., 0] + c * m[..., 1])], -1)
+
+
+def np_range2(rho, xi, l):
+    rho, xi, l = (np.asarray(a, dtype=np.float64) for a in (rho, xi, l))
+    return (rho[..., 0] - np.hypot(l[..., 0] - xi[..., 0], l[..., 1] - xi[..., 1]))[..., None]
+
+
+def np_pose2point2bearing(b, p, l):
+    b, p, l = (np.asarray(a, dtype=np.float64) for a in (b, p, l))
+    c, s = np.cos(p[..., 2]), np.sin(p[..., 2])
+    dx, dy = l[..., 0] - p[..., 0], l[..., 1] - p[..., 1]
+    return np_sym_rem(b[..., 0] - np.arctan2(-s * dx + c * dy, c * dx + s * dy))[..., None]
 
 
 def pose2pose2_fwd(X, p):

@@ -184,6 +184,35 @@ void rome_oracle_priorpose3(const double m[6], const double p[6], double r[6]) {
     rome_oracle_so3_log(U, r + 3);
 }
 
+/* ---- next-row families ---- */
+/* src/factors/Point2D.jl:14-18 */
+void rome_oracle_priorpoint2(const double m[2], const double x[2], double r[2]) {
+    r[0] = m[0] - x[0];
+    r[1] = m[1] - x[1];
+}
+/* src/factors/Point2D.jl:30-35 */
+void rome_oracle_point2point2(const double m[2], const double xi[2], const double xj[2], double r[2]) {
+    r[0] = m[0] - (xj[0] - xi[0]);
+    r[1] = m[1] - (xj[1] - xi[1]);
+}
+/* src/factors/Pose2Point2.jl:23-40: w_H_qhat = affine(w_T_p) * affine((m, I)); return l - w_H_qhat[1:2, end] */
+void rome_oracle_pose2point2(const double m[2], const double p[3], const double l[2], double r[2]) {
+    const double c = cos(p[2]), s = sin(p[2]);
+    r[0] = l[0] - (p[0] + c * m[0] - s * m[1]);
+    r[1] = l[1] - (p[1] + s * m[0] + c * m[1]);
+}
+/* src/factors/Range2D.jl:14-18, 51-54 */
+void rome_oracle_range2(const double rho[1], const double xi[2], const double l[2], double r[1]) {
+    const double dx = l[0] - xi[0], dy = l[1] - xi[1];
+    r[0] = rho[0] - sqrt(dx * dx + dy * dy);
+}
+/* src/factors/Bearing2D.jl:23-32 */
+void rome_oracle_pose2point2bearing(const double b[1], const double p[3], const double l[2], double r[1]) {
+    const double c = cos(p[2]), s = sin(p[2]);
+    const double dx = l[0] - p[0], dy = l[1] - p[1];
+    r[0] = rome_oracle_sym_rem(b[0] - atan2(-s * dx + c * dy, c * dx + s * dy));
+}
+
 /* ================================================================================== */
 /* closed-form roots                                                                  */
 /* ================================================================================== */

@@ -52,6 +52,18 @@ void rome_oracle_pose3pose3(const double X[6], const double p[6], const double q
 /* src/factors/Pose3D.jl:15-19 */
 void rome_oracle_priorpose3(const double m[6], const double p[6], double r[6]);
 
+/* ---- next-row families ---------------------------------------------------------- */
+/* src/factors/Point2D.jl:14-18  PriorPoint2: meas - x */
+void rome_oracle_priorpoint2(const double m[2], const double x[2], double r[2]);
+/* src/factors/Point2D.jl:30-35  Point2Point2: meas - (xj - xi) */
+void rome_oracle_point2point2(const double m[2], const double xi[2], const double xj[2], double r[2]);
+/* src/factors/Pose2Point2.jl:23-40  Pose2Point2: l - (p.t + R_p m) */
+void rome_oracle_pose2point2(const double m[2], const double p[3], const double l[2], double r[2]);
+/* src/factors/Range2D.jl:51-54 Pose2Point2Range and :14-18 Point2Point2Range: rho - |l - x| (xi: first two coords) */
+void rome_oracle_range2(const double rho[1], const double xi[2], const double l[2], double r[1]);
+/* src/factors/Bearing2D.jl:23-32 Pose2Point2Bearing: sym_rem(b - atan(R_p'(l - p.t))) */
+void rome_oracle_pose2point2bearing(const double b[1], const double p[3], const double l[2], double r[1]);
+
 /* ---- closed-form roots of the residual (what the per-particle solve converges to) */
 /* cf. src/services/OdometryUtils.jl:132-158 (addPose2Pose2 / odomKDE) */
 void rome_oracle_pose2pose2_fwd(const double X[3], const double p[3], double q[3]);

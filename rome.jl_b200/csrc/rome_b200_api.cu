@@ -44,6 +44,12 @@ const FamInfo kFam[ROME_B200_NFAMILIES] = {
     {ROME_B200_POSE2, ROME_B200_POINT2, 2, 2, 16, 4, (int)sizeof(RowBR), 2, 0},
     {ROME_B200_POSE3, ROME_B200_POSE3, 6, 6, 32, 0, (int)sizeof(RowSE3), 6, 6},
     {ROME_B200_POSE3, -1, 6, 6, 32, 0, (int)sizeof(RowSE3), 6, 0},
+    {ROME_B200_POINT2, -1, 2, 2, 16, 0, (int)sizeof(RowPT2), 2, 0},                // PriorPoint2
+    {ROME_B200_POINT2, ROME_B200_POINT2, 2, 2, 16, 0, (int)sizeof(RowPT2), 2, 0},  // Point2Point2
+    {ROME_B200_POSE2, ROME_B200_POINT2, 2, 2, 16, 0, (int)sizeof(RowPT2), 2, 0},   // Pose2Point2
+    {ROME_B200_POSE2, ROME_B200_POINT2, 1, 1, 16, 0, (int)sizeof(RowS1), 0, 0},    // Pose2Point2Range
+    {ROME_B200_POINT2, ROME_B200_POINT2, 1, 1, 16, 0, (int)sizeof(RowS1), 0, 0},   // Point2Point2Range
+    {ROME_B200_POSE2, ROME_B200_POINT2, 1, 1, 16, 0, (int)sizeof(RowS1), 0, 0},    // Pose2Point2Bearing
 };
 
 thread_local std::string g_create_error;
@@ -60,7 +66,7 @@ struct rome_b200_ctx {
     int smem_per_sm = 0, smem_per_cta_max = 0;
     Scratch stage_dev, stage_host;            // particle upload/download staging
     Scratch out_dev[ROME_B200_NFAMILIES][8];  // eval_host device mirrors per family: meas, meas_out, res, fwd, bwd, stats, jac
-    int n_peers[ROME_B200_NFAMILIES] = {0, 0, 0, 0, 0};
+    int n_peers[ROME_B200_NFAMILIES] = {};
     float* peers[ROME_B200_NFAMILIES][7] = {};
     std::vector<cudaGraphExec_t> graphs;
     std::vector<uint64_t> graph_kernels;
@@ -378,6 +384,50 @@ int rome_b200_set_factors_bearingrange(rome_b200_ctx* ctx, int nF, const int32_t
     }
     return upload_rows(ctx, ROME_B200_BEARINGRANGE, rows.data(), nF, m0, m1);
 }
+int rome_b200_set_factors_point2(rome_b200_ctx* ctx, int family, int nF, const int32_t* i0, const int32_t* i1,
+                                 const double* mu, const double* cov) {
+    if (!ctx) return ROME_B200_BAD_ARG;
+    if (family != ROME_B200_PRIORPOINT2 && family != ROME_B200_POINT2POINT2 && family != ROME_B200_POSE2POINT2)
+        return fail(ctx, ROME_B200_BAD_ARG, "family is not a 2-D Gaussian point factor");
+    const bool binary = family != ROME_B200_PRIORPOINT2;
+    if (nF < 0 || (nF > 0 && (!i0 || !mu || !cov || (binary && !i1)))) return fail(ctx, ROME_B200_BAD_ARG, "null factor arrays");
+    std::vector<RowPT2> rows((size_t)nF);
+    int m0 = -1, m1 = -1;
+    double L[4];
+    for (int f = 0; f < nF; ++f) {
+        RowPT2& r = rows[f];
+        std::memset(&r, 0, sizeof r);
+        r.ip = i0[f]; r.iq = binary ? i1[f] : -1;
+        if (r.ip < 0 || (binary && r.iq < 0)) return fail(ctx, ROME_B200_BAD_ARG, "negative variable index");
+        if (r.ip > m0) m0 = r.ip;
+        if (r.iq > m1) m1 = r.iq;
+        r.mu[0] = mu[2 * f]; r.mu[1] = mu[2 * f + 1];
+        if (!cholesky(cov + (size_t)f * 4, 2, L)) return fail(ctx, ROME_B200_BAD_ARG, "covariance is not positive definite");
+        r.L[0] = (float)L[0]; r.L[1] = (float)L[2]; r.L[2] = (float)L[3];
+    }
+    return upload_rows(ctx, family, rows.data(), nF, m0, m1);
+}
+int rome_b200_set_factors_scalar(rome_b200_ctx* ctx, int family, int nF, const int32_t* i0, const int32_t* i1,
+                                 const double* belief) {
+    if (!ctx) return ROME_B200_BAD_ARG;
+    if (family != ROME_B200_POSE2POINT2RANGE && family != ROME_B200_POINT2POINT2RANGE &&
+        family != ROME_B200_POSE2POINT2BEARING)
+        return fail(ctx, ROME_B200_BAD_ARG, "family is not a scalar factor");
+    if (nF < 0 || (nF > 0 && (!i0 || !i1 || !belief))) return fail(ctx, ROME_B200_BAD_ARG, "null factor arrays");
+    std::vector<RowS1> rows((size_t)nF);
+    int m0 = -1, m1 = -1;
+    for (int f = 0; f < nF; ++f) {
+        RowS1& r = rows[f];
+        std::memset(&r, 0, sizeof r);
+        r.ip = i0[f]; r.iq = i1[f];
+        if (r.ip < 0 || r.iq < 0) return fail(ctx, ROME_B200_BAD_ARG, "negative variable index");
+        if (!(belief[2 * f + 1] > 0.0)) return fail(ctx, ROME_B200_BAD_ARG, "standard deviation must be positive");
+        if (r.ip > m0) m0 = r.ip;
+        if (r.iq > m1) m1 = r.iq;
+        r.mu = belief[2 * f]; r.sigma = (float)belief[2 * f + 1];
+    }
+    return upload_rows(ctx, family, rows.data(), nF, m0, m1);
+}
 int rome_b200_num_factors(rome_b200_ctx* ctx, int family) {
     if (!ctx || family < 0 || family >= ROME_B200_NFAMILIES) return ROME_B200_BAD_ARG;
     return ctx->fac[family].nF;
@@ -407,6 +457,8 @@ static int check_eval(rome_b200_ctx* ctx, int family, uint32_t flags, int first,
     if ((flags & ROME_B200_WRITE_MEAS) && (!(flags & ROME_B200_SAMPLE) || !b->meas_out))
         return fail(ctx, ROME_B200_BAD_ARG, "WRITE_MEAS needs SAMPLE and meas_out");
     if ((flags & ROME_B200_RESIDUAL) && !b->res) return fail(ctx, ROME_B200_BAD_ARG, "res is NULL");
+    if ((flags & ROME_B200_PROPOSAL_FWD) && fi.dfwd == 0)
+        return fail(ctx, ROME_B200_BAD_ARG, "this family has no closed-form forward proposal");
     if ((flags & ROME_B200_PROPOSAL_FWD) && !b->prop_fwd) return fail(ctx, ROME_B200_BAD_ARG, "prop_fwd is NULL");
     // meas / res / prop_fwd rows move through 1-D TMA bulk copies: 16-byte alignment is required
     if (((flags & ROME_B200_RESIDUAL) && ((uintptr_t)b->res & 15)) ||

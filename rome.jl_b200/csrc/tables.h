@@ -35,6 +35,23 @@ struct alignas(32) RowSE3 {
 };
 static_assert(sizeof(RowSE3) == 160, "RowSE3 must be 160 B");
 
+// 2-D Gaussian point factors (PriorPoint2, Point2Point2, Pose2Point2): src/factors/Point2D.jl, Pose2Point2.jl
+struct alignas(16) RowPT2 {
+    int32_t ip, iq;
+    double mu[2];
+    float L[3];  // L00 L10 L11
+    float pad[3];
+};
+static_assert(sizeof(RowPT2) == 48, "RowPT2 must be 48 B");
+// scalar Normal factors (ranges, bearing): src/factors/Range2D.jl, Bearing2D.jl
+struct alignas(32) RowS1 {
+    int32_t ip, iq;
+    double mu;
+    float sigma;
+    float pad[3];
+};
+static_assert(sizeof(RowS1) == 32, "RowS1 must be 32 B");
+
 // Particle store: one contiguous BLOCK per variable so that a single 1-D TMA bulk copy brings a whole
 // variable (anchor + all particles) into shared memory:
 //     [ anchor header ][ Npad x d float32 offsets, particle-major ]

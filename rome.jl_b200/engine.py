@@ -10,8 +10,9 @@ import ctypes as C
 import numpy as np
 
 from . import _lib as L
-from ._lib import (BEARINGRANGE, JACOBIAN, POINT2, POSE2, POSE2POSE2, POSE3, POSE3POSE3, PRIORPOSE2, PRIORPOSE3,
-                   PROPOSAL_BWD, PROPOSAL_FWD, RESIDUAL, SAMPLE, STATS, WRITE_MEAS, Buffers, RomeB200Error)
+from ._lib import (BEARINGRANGE, JACOBIAN, POINT2, POINT2POINT2, POINT2POINT2RANGE, POSE2, POSE2POINT2,
+                   POSE2POINT2BEARING, POSE2POINT2RANGE, POSE2POSE2, POSE3, POSE3POSE3, PRIORPOINT2, PRIORPOSE2,
+                   PRIORPOSE3, PROPOSAL_BWD, PROPOSAL_FWD, RESIDUAL, SAMPLE, STATS, WRITE_MEAS, Buffers, RomeB200Error)
 
 VAR_DIM = {POSE2: 3, POINT2: 2, POSE3: 6}
 # family -> (vartype of first variable, vartype of second variable or None, dm, dr, nstats, dj, dfwd, dbwd)
@@ -21,11 +22,22 @@ FAMILY = {
     BEARINGRANGE: (POSE2, POINT2, 2, 2, 16, 4, 2, 0),
     POSE3POSE3: (POSE3, POSE3, 6, 6, 32, 0, 6, 6),
     PRIORPOSE3: (POSE3, None, 6, 6, 32, 0, 6, 0),
+    # next-row families
+    PRIORPOINT2: (POINT2, None, 2, 2, 16, 0, 2, 0),
+    POINT2POINT2: (POINT2, POINT2, 2, 2, 16, 0, 2, 0),
+    POSE2POINT2: (POSE2, POINT2, 2, 2, 16, 0, 2, 0),
+    POSE2POINT2RANGE: (POSE2, POINT2, 1, 1, 16, 0, 0, 0),
+    POINT2POINT2RANGE: (POINT2, POINT2, 1, 1, 16, 0, 0, 0),
+    POSE2POINT2BEARING: (POSE2, POINT2, 1, 1, 16, 0, 0, 0),
 }
 # algorithmic bytes per factor-particle eval with this layout (DESIGN.md "bytes per eval"):
 # read both variables' offsets + the measurement offsets, write the residual (float32 each)
-BYTES_PER_EVAL = {POSE2POSE2: 48, PRIORPOSE2: 36, BEARINGRANGE: 36, POSE3POSE3: 96, PRIORPOSE3: 72}
-BYTES_PER_EVAL_SAMPLED = {POSE2POSE2: 36, PRIORPOSE2: 24, BEARINGRANGE: 28, POSE3POSE3: 72, PRIORPOSE3: 48}
+BYTES_PER_EVAL = {POSE2POSE2: 48, PRIORPOSE2: 36, BEARINGRANGE: 36, POSE3POSE3: 96, PRIORPOSE3: 72,
+                  PRIORPOINT2: 24, POINT2POINT2: 32, POSE2POINT2: 36, POSE2POINT2RANGE: 28, POINT2POINT2RANGE: 24,
+                  POSE2POINT2BEARING: 28}
+BYTES_PER_EVAL_SAMPLED = {POSE2POSE2: 36, PRIORPOSE2: 24, BEARINGRANGE: 28, POSE3POSE3: 72, PRIORPOSE3: 48,
+                          PRIORPOINT2: 16, POINT2POINT2: 24, POSE2POINT2: 28, POSE2POINT2RANGE: 24,
+                          POINT2POINT2RANGE: 20, POSE2POINT2BEARING: 24}
 
 
 def npad(N: int) -> int:
@@ -178,6 +190,20 @@ class Context:
         ip, mu, cov = _i32(ip), _f64(mu), _f64(cov)
         self._ck(self._lib.rome_b200_set_factors_priorpose3(self._h, len(ip), self._ip(ip), self._dp(mu),
                                                             self._dp(cov)))
+
+    def set_factors_point2(self, family, i0, i1, mu, cov):
+        """PriorPoint2 (i1=None) / Point2Point2 / Pose2Point2: MvNormal(mu[2], cov[2][2])"""
+        i0, mu, cov = _i32(i0), _f64(mu), _f64(cov)
+        i1 = None if i1 is None else _i32(i1)
+        self._ck(self._lib.rome_b200_set_factors_point2(self._h, family, len(i0), self._ip(i0),
+                                                        None if i1 is None else self._ip(i1), self._dp(mu),
+                                                        self._dp(cov)))
+
+    def set_factors_scalar(self, family, i0, i1, belief):
+        """Pose2Point2Range / Point2Point2Range / Pose2Point2Bearing: Normal(mean, sigma) rows [nF][2]"""
+        i0, i1, belief = _i32(i0), _i32(i1), _f64(belief)
+        self._ck(self._lib.rome_b200_set_factors_scalar(self._h, family, len(i0), self._ip(i0), self._ip(i1),
+                                                        self._dp(belief)))
 
     def num_factors(self, family: int) -> int:
         return self._lib.rome_b200_num_factors(self._h, family)

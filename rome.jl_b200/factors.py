@@ -139,6 +139,53 @@ class PriorPose3(AbstractPrior):
             raise ValueError("PriorPose3 needs a 6-dimensional belief")
 
 
+# ---- next-row families --------------------------------------------------------------
+@dataclass
+class PriorPoint2(AbstractPrior):  # src/factors/Point2D.jl:8-10
+    Z: MvNormal = field(default_factory=lambda: _default_mv(2, [0.01, 0.01]))
+    family = L.PRIORPOINT2
+    variabletypes = (Point2,)
+
+
+@dataclass
+class Point2Point2(AbstractManifoldMinimize):  # src/factors/Point2D.jl:25-27
+    Z: MvNormal = field(default_factory=lambda: _default_mv(2, [0.1, 0.1]))
+    family = L.POINT2POINT2
+    variabletypes = (Point2, Point2)
+
+
+@dataclass
+class Pose2Point2(AbstractManifoldMinimize):  # src/factors/Pose2Point2.jl:9-12
+    Z: MvNormal = field(default_factory=lambda: _default_mv(2, [0.01, 0.01]))
+    family = L.POSE2POINT2
+    variabletypes = (Pose2, Point2)
+
+
+@dataclass
+class Pose2Point2Range(AbstractManifoldMinimize):  # src/factors/Range2D.jl:43-47
+    Z: Normal
+    family = L.POSE2POINT2RANGE
+    variabletypes = (Pose2, Point2)
+
+
+@dataclass
+class Point2Point2Range(AbstractManifoldMinimize):  # src/factors/Range2D.jl:5-7
+    Z: Normal
+    family = L.POINT2POINT2RANGE
+    variabletypes = (Point2, Point2)
+
+
+@dataclass
+class Pose2Point2Bearing(AbstractManifoldMinimize):  # src/factors/Bearing2D.jl:13-15
+    Z: Normal = field(default_factory=Normal)
+    family = L.POSE2POINT2BEARING
+    variabletypes = (Pose2, Point2)
+
+
+SCALAR_FACTORS = (Pose2Point2Range, Point2Point2Range, Pose2Point2Bearing)
+POINT2_FACTORS = (PriorPoint2, Point2Point2, Pose2Point2)
+
+
 def getManifold(x) -> str:
     """DFG.getManifold for the types of this path (returned as the reference's constructor text)."""
     if isinstance(x, type):
@@ -149,8 +196,12 @@ def getManifold(x) -> str:
         return Pose3.manifold  # src/factors/Pose3Pose3.jl:13, Pose3D.jl:13
     if isinstance(x, Pose2Point2BearingRange):  # src/factors/BearingRange2D.jl:15
         return "ProductGroup(ProductManifold(SpecialOrthogonal(2), TranslationGroup(1)), LeftInvariantRepresentation())"
-    if isinstance(x, Point2):
-        return Point2.manifold
+    if isinstance(x, (Point2, PriorPoint2, Point2Point2, Pose2Point2)):
+        return Point2.manifold  # Point2D.jl:12,29; Pose2Point2.jl:18
+    if isinstance(x, (Pose2Point2Range, Point2Point2Range)):
+        return "TranslationGroup(1)"  # Range2D.jl:9,49
+    if isinstance(x, Pose2Point2Bearing):
+        return "SpecialOrthogonal(2)"  # Bearing2D.jl:19
     raise TypeError(f"no manifold for {type(x)}")
 
 
@@ -159,11 +210,17 @@ def getMeasurementParametric(f):
     if isinstance(f, Pose2Point2BearingRange):
         return (np.array([f.bearing.mu, f.range.mu]),
                 np.diag([1.0 / f.bearing.sigma ** 2, 1.0 / f.range.sigma ** 2]))
+    if isinstance(f, SCALAR_FACTORS):
+        return np.array([f.Z.mu]), np.array([[1.0 / f.Z.sigma ** 2]])
     return f.Z.mu.copy(), np.linalg.inv(f.Z.Sigma)
 
 
 def factor_mean(f) -> np.ndarray:
-    return np.array([f.bearing.mu, f.range.mu]) if isinstance(f, Pose2Point2BearingRange) else f.Z.mu
+    if isinstance(f, Pose2Point2BearingRange):
+        return np.array([f.bearing.mu, f.range.mu])
+    if isinstance(f, SCALAR_FACTORS):
+        return np.array([f.Z.mu])
+    return f.Z.mu
 
 
 # ---- Packed* serialization types (Pose2D.jl:76-84, PriorPose2.jl:55-63, BearingRange2D.jl:76-87,
@@ -194,5 +251,8 @@ def unpack(d: dict):
     name = d["_type"][len("Packed"):]
     if name == "Pose2Point2BearingRange":
         return Pose2Point2BearingRange(_unpack_belief(d["bearstr"]), _unpack_belief(d["rangstr"]))
-    cls = {"Pose2Pose2": Pose2Pose2, "PriorPose2": PriorPose2, "Pose3Pose3": Pose3Pose3, "PriorPose3": PriorPose3}[name]
+    cls = {"Pose2Pose2": Pose2Pose2, "PriorPose2": PriorPose2, "Pose3Pose3": Pose3Pose3, "PriorPose3": PriorPose3,
+           "PriorPoint2": PriorPoint2, "Point2Point2": Point2Point2, "Pose2Point2": Pose2Point2,
+           "Pose2Point2Range": Pose2Point2Range, "Point2Point2Range": Point2Point2Range,
+           "Pose2Point2Bearing": Pose2Point2Bearing}[name]
     return cls(_unpack_belief(d["Z"]))

@@ -15,7 +15,8 @@ import numpy as np
 
 from . import _lib as L
 from .engine import FAMILY, VAR_DIM, Context, meas_to_offsets, offsets_to_meas, rows_to_particle_major
-from .factors import (AbstractFactor, InferenceVariable, Point2, Pose2, Pose2Point2BearingRange, Pose3, factor_mean)
+from .factors import (POINT2_FACTORS, SCALAR_FACTORS, AbstractFactor, InferenceVariable, Point2, Pose2,
+                      Pose2Point2BearingRange, Pose3, factor_mean)
 
 _VARCLASS = {L.POSE2: Pose2, L.POINT2: Point2, L.POSE3: Pose3}
 
@@ -151,6 +152,8 @@ def _factor_arrays(facs):
     if fam == L.BEARINGRANGE:
         return (np.array([[f.fnc.bearing.mu, f.fnc.bearing.sigma] for f in facs]),
                 np.array([[f.fnc.range.mu, f.fnc.range.sigma] for f in facs]))
+    if isinstance(facs[0].fnc, SCALAR_FACTORS):
+        return np.array([[f.fnc.Z.mu, f.fnc.Z.sigma] for f in facs]), None
     return np.stack([f.fnc.Z.mu for f in facs]), np.stack([f.fnc.Z.Sigma for f in facs])
 
 
@@ -199,6 +202,10 @@ class DeviceGraph:
                 c.set_factors_pose3pose3(i0, i1, a, b)
             elif fam == L.PRIORPOSE3:
                 c.set_factors_priorpose3(i0, a, b)
+            elif isinstance(facs[0].fnc, POINT2_FACTORS):
+                c.set_factors_point2(fam, i0, i1, a, b)
+            elif isinstance(facs[0].fnc, SCALAR_FACTORS):
+                c.set_factors_scalar(fam, i0, i1, a)
 
     def means(self, family) -> np.ndarray:
         return np.stack([factor_mean(f.fnc) for f in self.by_family[family]])
@@ -312,6 +319,12 @@ def approxConv(fg: FactorGraph, flabel, target, N: int | None = None, seed=0, ct
                 val = val[np.random.default_rng(seed).integers(0, val.shape[0], N)]
             pts.append(val)
     last = len(fnc.variabletypes) - 1
+    if isinstance(fnc, SCALAR_FACTORS):
+        # one equation for a 2- or 3-dimensional target: a 1-parameter family of roots, left to the optimiser's
+        # start point in the reference; no closed form is shipped
+        raise NotImplementedError(f"{type(fnc).__name__}: the convolution has no unique root")
+    if isinstance(fnc, POINT2_FACTORS) and not fnc.is_prior and slot != last:
+        raise NotImplementedError(f"{type(fnc).__name__}: only the convolution onto the last variable is closed-form here")
     if fnc.is_prior or slot == last:
         flag, key = L.PROPOSAL_FWD, "prop_fwd"
     elif isinstance(fnc, Pose2Point2BearingRange):

@@ -91,6 +91,16 @@ def known_answers():
     T.append(dict(src=src + ":162-167", X=[10., 0, 0, pi, pi, pi], p=[0] * 6, q=[10., 0, 0, pi, pi, pi],
                   expect_norm_below=1e-10))
 
+    # Pose2Point2Bearing (next row N1): test/testBearing2D.jl:13-47 (q = (5,5), measurement pi/4) and :59-66
+    Bg = ka.setdefault("pose2point2bearing", [])
+    ps = [[0., 0, 0], [5., 0, 0], [10., 0, 0], [10., 5, 0], [10., 10, 0], [5., 10, 0], [0., 10, 0], [0., 5, 0],
+          [0., 0, pi / 4], [0., 0, -pi / 4], [1., 2, 0]]
+    rs = [0, -pi / 4, -pi / 2, -3 * pi / 4, -pi, 3 * pi / 4, pi / 2, pi / 4, pi / 4, -pi / 4, pi / 4 - math.atan2(3, 4)]
+    for pp, rr in zip(ps, rs):
+        Bg.append(dict(src="test/testBearing2D.jl:13-47", b=pi / 4, p=pp, l=[5., 5.], expect=[rr], atol=1e-3,
+                       modulo_2pi=True))
+    Bg.append(dict(src="test/testBearing2D.jl:59-66", b=pi, p=[0., 0, 0], l=[-1., -0.001], expect=[-0.001], atol=1e-3))
+
     # parametric square loop: the posterior means the reference asserts are exact roots of the
     # chain x_{k+1} = x_k o Exp(m) (pins the Hybrid exp: translation NOT coupled through V(theta))
     ka["pose2pose2_parametric"].append(dict(

@@ -170,3 +170,26 @@ def test_philox_known_answer():
         [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
     z = np.array([O.normal4(5, 0, f, n) for f in range(40) for n in range(100)]).ravel()
     assert abs(z.mean()) < 0.03 and abs(z.std() - 1) < 0.03
+
+
+def test_next_row_families(ka):
+    """Pose2Point2Bearing known answers (test/testBearing2D.jl) and the closed-form point factors"""
+    for c in ka["pose2point2bearing"]:
+        r = O.pose2point2bearing(c["b"], c["p"], c["l"])
+        d = r - np.array(c["expect"])
+        if c.get("modulo_2pi"):
+            d = O.np_wrap(d)
+        assert np.all(np.abs(d) < c["atol"]), (c, r)
+        assert np.allclose(O.np_pose2point2bearing([c["b"]], c["p"], c["l"]), r, atol=1e-12)
+    rng = np.random.default_rng(4)
+    for _ in range(50):
+        m, xi, xj = rng.normal(size=2), rng.normal(size=2) * 10, rng.normal(size=2) * 10
+        p = np.append(xi, rng.uniform(-3, 3))
+        assert np.allclose(O.priorpoint2(m, xi), m - xi)
+        assert np.allclose(O.point2point2(m, xi, xj), m - (xj - xi))
+        assert np.allclose(O.point2point2(xj - xi, xi, xj), 0, atol=1e-12)
+        l = p[:2] + np.array([[np.cos(p[2]), -np.sin(p[2])], [np.sin(p[2]), np.cos(p[2])]]) @ m
+        assert np.allclose(O.pose2point2(m, p, l), 0, atol=1e-12)
+        assert np.allclose(O.pose2point2(m, p, xj), O.np_pose2point2(m, p, xj), atol=1e-12)
+        assert np.allclose(O.range2(7.0, xi, xj), 7.0 - np.linalg.norm(xj - xi))
+        assert np.allclose(O.range2(7.0, p, xj), O.np_range2([7.0], p, xj))
