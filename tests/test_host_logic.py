@@ -55,7 +55,7 @@ def test_dims_queries():
         a, b, c, d = (ctypes.c_int() for _ in range(4))
         assert lib.rome_b200_family_dims(fam, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c), ctypes.byref(d)) == 0
         assert (a.value, b.value, c.value, d.value) == (dm, dr, ns, dj)
-    assert lib.rome_b200_family_dims(9, None, None, None, None) == -1
+    assert lib.rome_b200_family_dims(99, None, None, None, None) == -1
     assert [lib.rome_b200_vartype_dim(t) for t in (0, 1, 2)] == [3, 2, 6]
     assert lib.rome_b200_npad(100) == 104 == rb.npad(100) and lib.rome_b200_npad(200) == 200 and lib.rome_b200_npad(1) == 8
 
