@@ -109,6 +109,9 @@ __constant__ double kSinC[6] = {-1.66666666666666324348e-01, 8.33333333332248946
                                 2.75573137070700676789e-06,  -2.50507602534068634195e-08, 1.58969099521155010221e-10};
 __constant__ double kCosC[6] = {4.16666666666666019037e-02,  -1.38888888888741095749e-03, 2.48015872894767294178e-05,
                                 -2.75573143513906633035e-07, 2.08757232129817482790e-09,  -1.13596475577881948265e-11};
+// atan(u)/u = sum (-u^2)^k / (2k+1): reciprocal odd numbers in constant memory (DFMA constant-bank operands)
+__constant__ double kOddInv[9] = {1.0,        1.0 / 3.0,  1.0 / 5.0,  1.0 / 7.0, 1.0 / 9.0,
+                                  1.0 / 11.0, 1.0 / 13.0, 1.0 / 15.0, 1.0 / 17.0};
 constexpr double kSmallAngle = 0.78;
 __device__ __forceinline__ void sincos_small(double x, double& s, double& c) {
     const double z = x * x;
@@ -120,6 +123,18 @@ __device__ __forceinline__ void sincos_small(double x, double& s, double& c) {
     ps = fma(z, ps, kSinC[0]); pc = fma(z, pc, kCosC[0]);
     s = fma(x * z, ps, x);
     c = fma(z * z, pc, fma(z, -0.5, 1.0));
+}
+// sqrt of a positive normal double in float32 range: MUFU.RSQ seed (relative error ~2^-22) followed by two
+// coupled Goldschmidt steps (error -> 1.5 e^2 each); result within ~1 ulp.  No branches, no division.
+__device__ __forceinline__ double sqrt_seeded(double a) {
+    float y0;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"((float)a));
+    double g = a * (double)y0, h = 0.5 * (double)y0;
+    double r = fma(-g, h, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    r = fma(-g, h, 0.5);
+    return fma(g, r, g);
 }
 // sin/cos of (anchor + x) given (ca, sa) = cos/sin(anchor): angle addition for small x, general path otherwise
 __device__ __forceinline__ void sincos_anchored(double anchor, double ca, double sa, double x, double& s, double& c) {

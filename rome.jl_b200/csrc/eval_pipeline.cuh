@@ -1,0 +1,316 @@
+// eval_pipeline.cuh -- the persistent TMA producer/consumer pipeline shared by every factor family:
+//   persistent CTAs = FT consumer warps (one factor each per tile of FT factors) + 1 producer warp;
+//   the producer stages, per tile and S tiles ahead, everything the consumers read into shared memory
+//   with 1-D TMA bulk copies (cp.async.bulk, completion on an mbarrier per stage): the tile's factor-table
+//   rows {var ids, mu (f64), chol(Sigma) (f32)}, its measurement block, and -- gathered by variable id --
+//   one contiguous particle block {anchor (f64), Npad x d float32 offsets} per factor slot;
+//   consumers never issue a global load: they wait on the stage's "full" barrier, compute in Float64 on
+//   the anchored float32 data (DESIGN.md "precision"), write residual / proposal rows into the warp's
+//   shared-memory slice, flush it with a warp-local TMA bulk store and release the stage through its
+//   "empty" barrier; statistics are reduced with a halving-butterfly of __shfl_xor_sync (device_utils.cuh).
+// A family (fam_*.cu) supplies `struct Fam { Row, D0, D1, DM, DR, DFWD, kMinCtas, factor<kStatic,kSample>() }`
+// and instantiates launch_family<Fam>.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../../include/rome_b200.h"
+#include "device_utils.cuh"
+#include "tables.h"
+
+namespace rome {
+
+// =============================================================================================
+// SE(2) statistics accumulator: 16 additive values per factor
+//   0..2 sum r | 3..8 sum r r' (11 12 13 22 23 33) | 9,10 sum proposal (dx,dy) | 11,12 sum cos/sin of the
+//   proposal heading offset | 13..15 sum dx^2, dx dy, dy^2     (offsets from the target anchor)
+// =============================================================================================
+__device__ __forceinline__ void acc_res3(float (&st)[16], float m, float r1, float r2, float r3) {
+    r1 *= m; r2 *= m; r3 *= m;
+    st[0] += r1; st[1] += r2; st[2] += r3;
+    st[3] = fmaf(r1, r1, st[3]); st[4] = fmaf(r1, r2, st[4]); st[5] = fmaf(r1, r3, st[5]);
+    st[6] = fmaf(r2, r2, st[6]); st[7] = fmaf(r2, r3, st[7]); st[8] = fmaf(r3, r3, st[8]);
+}
+__device__ __forceinline__ void acc_prop2(float (&st)[16], float m, float dx, float dy) {
+    dx *= m; dy *= m;
+    st[9] += dx; st[10] += dy;
+    st[13] = fmaf(dx, dx, st[13]); st[14] = fmaf(dx, dy, st[14]); st[15] = fmaf(dy, dy, st[15]);
+}
+__device__ __forceinline__ void acc_heading(float (&st)[16], float m, float dth) {
+    float s, c;
+    sincosf(dth, &s, &c);
+    st[11] = fmaf(m, c, st[11]);
+    st[12] = fmaf(m, s, st[12]);
+}
+__device__ __forceinline__ void write_stats16(float (&st)[16], float* stats, int f, int lane) {
+    const float tot = warp_reduce_scatter16(st, lane);
+    if ((lane & 1) == 0) stats[(size_t)f * 16 + (lane >> 1)] = tot;
+}
+// What a consumer warp sees of its factor: inputs already in shared memory, plus its private output slice.
+struct FactorView {
+    const unsigned char* b0;  // particle block of the first variable  {anchor, rows}
+    const unsigned char* b1;  // particle block of the second variable (nullptr for priors)
+    const float* meas;        // [dm][Npad] measurement offsets (nullptr with SAMPLE)
+    float* out_res;           // [dr][Npad] residual rows, flushed by a warp-local TMA bulk store
+    float* out_fwd;           // [dfwd][Npad] forward-proposal rows, same
+};
+constexpr uint32_t kHot1 = ROME_B200_RESIDUAL | ROME_B200_STATS;
+constexpr uint32_t kHot2 = ROME_B200_RESIDUAL | ROME_B200_STATS | ROME_B200_PROPOSAL_FWD;
+
+// =============================================================================================
+// SE(2) families.  Rows are particle-major ([Npad][d], the reference's own `vecval` order): lane l owns
+// particles l, l+32, l+64, ...; consecutive lanes read consecutive 12-B (8-B) records -> bank-conflict free.
+// The slot loop is unrolled by four: one Philox/Box-Muller batch serves four particles of a lane and the
+// Float64 chains of the four slots interleave.  kStatic != 0 fixes the output flags at compile time.
+// =============================================================================================
+// normals for the lane's slots [4g, 4g+4) of factor f: D normals per particle, 4 per Philox call
+template <int D>
+__device__ __forceinline__ void normals_for_group(const EvalParams& P, int f, int lane, int g, float (&z)[4 * D]) {
+#pragma unroll
+    for (int b = 0; b < D; ++b)
+        normal4(P.seed_lo, P.seed_hi, P.stream_id, (uint32_t)f, (uint32_t)lane, (uint32_t)(g * D + b), &z[4 * b]);
+}
+
+// Slot loop.  A group = the lane's 4 slots {n0, n0+32, n0+64, n0+96}.  A FULL group (its 4th slot still has live
+// particles) is evaluated as branch-free straight-line code: first the four slot BODIES (loads + arithmetic into
+// registers), then the four slot STORES -- no shared-memory store sits between the loads of different slots, so
+// the Float64 chains of the four particles may interleave.  Slots 0-2 are live for every lane; a lane whose 4th
+// particle is beyond Npad reads particle `lane` instead and has its stores/statistics masked.  FASTCOND
+// (warp-uniform) selects the variant whose body may assume kFast (e.g. small heading offsets -> polynomial
+// sin/cos without a fallback branch).  The trailing partial group is evaluated with warp-uniform guards.
+// The family defines ROME_SLOT_DECL (per-group register arrays) and ROME_SLOT_STORE (uses k, n, live).
+#define ROME_SLOT_LOOP(FASTCOND, ...)                                                          \
+    for (int g = 0, n0 = lane; n0 < Npad; ++g, n0 += 128) {                                    \
+        float z[4 * DZ];                                                                       \
+        if (kSample) normals_for_group<DZ>(P, f, lane, g, z);                                  \
+        ROME_SLOT_DECL                                                                         \
+        if (n0 - lane + 96 < Npad) {                                                           \
+            const int n3 = (n0 + 96 < Npad) ? n0 + 96 : lane;                                  \
+            if (FASTCOND) {                                                                    \
+                constexpr bool kFast = true; (void)kFast;                                      \
+                _Pragma("unroll") for (int k = 0; k < 4; ++k) {                                \
+                    const int nn = n0 + 32 * k;                                                \
+                    const bool live = (k < 3) || nn < Npad;                                    \
+                    const int n = (k < 3) ? nn : n3;                                           \
+                    __VA_ARGS__                                                                \
+                }                                                                              \
+            } else {                                                                           \
+                constexpr bool kFast = false; (void)kFast;                                     \
+                _Pragma("unroll") for (int k = 0; k < 4; ++k) {                                \
+                    const int nn = n0 + 32 * k;                                                \
+                    const bool live = (k < 3) || nn < Npad;                                    \
+                    const int n = (k < 3) ? nn : n3;                                           \
+                    __VA_ARGS__                                                                \
+                }                                                                              \
+            }                                                                                  \
+            _Pragma("unroll") for (int k = 0; k < 4; ++k) {                                    \
+                const int nn = n0 + 32 * k;                                                    \
+                const bool live = (k < 3) || nn < Npad;                                        \
+                const int n = (k < 3) ? nn : n3;                                               \
+                ROME_SLOT_STORE                                                                \
+            }                                                                                  \
+        } else {                                                                               \
+            constexpr bool kFast = false; (void)kFast;                                         \
+            _Pragma("unroll") for (int k = 0; k < 4; ++k) {                                    \
+                const int nn = n0 + 32 * k;                                                    \
+                if (n0 - lane + 32 * k < Npad) {                                               \
+                    const bool live = nn < Npad;                                               \
+                    const int n = live ? nn : lane;                                            \
+                    __VA_ARGS__                                                                \
+                    ROME_SLOT_STORE                                                            \
+                }                                                                              \
+            }                                                                                  \
+        }                                                                                      \
+    }
+
+// =============================================================================================
+// stage layout (shared by host planning and the kernel)
+// =============================================================================================
+struct StageLayout {
+    int rows_off, v0_off, v1_off, meas_off, bytes;
+    int b0, b1, mb;  // bytes of one slot-0 block, slot-1 block, one factor's measurement block
+};
+__host__ __device__ inline StageLayout stage_layout(int ft, int row_bytes, int d0, int d1, int dm, bool sample,
+                                                    int Npad) {
+    StageLayout L;
+    L.b0 = var_block_bytes(d0, Npad);
+    L.b1 = d1 ? var_block_bytes(d1, Npad) : 0;
+    L.mb = sample ? 0 : dm * Npad * 4;
+    L.rows_off = 0;
+    L.v0_off = (ft * row_bytes + 127) / 128 * 128;
+    L.v1_off = L.v0_off + ft * L.b0;
+    L.meas_off = L.v1_off + ft * L.b1;
+    L.bytes = (L.meas_off + ft * L.mb + 127) / 128 * 128;
+    return L;
+}
+constexpr int kBarrierBytes = 128;
+constexpr int kMaxStages = 6;
+
+// =============================================================================================
+// persistent producer/consumer pipeline
+//   smem: [full[], empty[] mbarriers | S input stages | FT per-warp output slices]
+// =============================================================================================
+template <class Fam, uint32_t kStatic, bool kSample, int FT>
+__global__ void __launch_bounds__((FT + 1) * 32, Fam::kMinCtas) eval_kernel(const __grid_constant__ EvalParams P) {
+    using Row = typename Fam::Row;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* empty = full + kMaxStages;
+    unsigned char* stage0 = smem + kBarrierBytes;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int S = P.stages;
+    const int nTiles = (P.count + FT - 1) / FT;
+    const StageLayout L = stage_layout(FT, (int)sizeof(Row), Fam::D0, Fam::D1, Fam::DM, kSample, P.Npad);
+    const Row* __restrict__ table = reinterpret_cast<const Row*>(P.rows) + P.first;
+    const uint32_t flags = kStatic ? kStatic : P.flags;
+
+    // The producer warp holds the variable ids of a CHUNK of 32/FT tiles at once (lane l <-> tile l/FT of the
+    // chunk, factor l%FT): one global-load latency per chunk instead of one per tile; the first chunk is
+    // requested before the barrier initialisation is published.
+    constexpr int TPC = 32 / FT;  // tiles per chunk
+    const int jl = lane / FT, fl_in_tile = lane % FT;
+    int2 ids_cur = make_int2(0, 0);
+    auto fetch_chunk = [&](int base_tile) {
+        const int t = base_tile + jl * (int)gridDim.x;
+        const int fl = t * FT + fl_in_tile;
+        int2 ids = make_int2(0, 0);
+        if (t < nTiles && fl < P.count) ids = __ldg(reinterpret_cast<const int2*>(table + fl));
+        return ids;
+    };
+    if (warp == FT) ids_cur = fetch_chunk(blockIdx.x);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], FT);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    // programmatic dependent launch: a following launch flagged ROME_B200_INDEPENDENT may begin as SMs free up
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+    if (warp == FT) {
+        // ---------------- producer warp ---------------------------------------------------------------------
+        int s = 0;
+        uint32_t phase = 1;  // parity of the previous round; the first pass over the ring does not wait
+        bool first_round = true;
+        for (int base = blockIdx.x; base < nTiles; base += TPC * gridDim.x) {
+            const int2 ids_next = fetch_chunk(base + TPC * gridDim.x);  // in flight while this chunk is issued
+#pragma unroll 1
+            for (int j = 0; j < TPC; ++j) {
+                const int tile = base + j * gridDim.x;
+                if (tile >= nTiles) break;
+                if (!first_round) mbar_wait(&empty[s], phase);
+                unsigned char* st = stage0 + (size_t)s * L.bytes;
+                const int nf = min(FT, P.count - tile * FT);
+                if (lane == j * FT) {
+                    fence_proxy_async();
+                    mbar_arrive_expect_tx(&full[s], (uint32_t)(nf * ((int)sizeof(Row) + L.b0 + L.b1 + L.mb)));
+                    tma_load_1d(st + L.rows_off, table + (size_t)tile * FT, (uint32_t)(nf * sizeof(Row)), &full[s]);
+                    if (!kSample)
+                        tma_load_1d(st + L.meas_off, P.meas + (size_t)(P.first + tile * FT) * Fam::DM * P.Npad,
+                                    (uint32_t)(nf * L.mb), &full[s]);
+                }
+                __syncwarp();
+                if (jl == j && fl_in_tile < nf) {
+                    tma_load_1d(st + L.v0_off + fl_in_tile * L.b0, P.v0 + (size_t)ids_cur.x * L.b0, (uint32_t)L.b0,
+                                &full[s]);
+                    if (Fam::D1)
+                        tma_load_1d(st + L.v1_off + fl_in_tile * L.b1, P.v1 + (size_t)ids_cur.y * L.b1,
+                                    (uint32_t)L.b1, &full[s]);
+                }
+                if (++s == S) { s = 0; phase ^= 1u; first_round = false; }
+            }
+            ids_cur = ids_next;
+        }
+    } else {
+        // ---------------- consumer warps: warp w owns the tile's w-th factor ----------------------------------
+        float* out = reinterpret_cast<float*>(stage0 + (size_t)S * L.bytes + (size_t)warp * P.out_warp_bytes);
+        const int res_floats = Fam::DR * P.Npad;
+        int s = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
+            mbar_wait(&full[s], phase);
+            const unsigned char* st = stage0 + (size_t)s * L.bytes;
+            const int fl = tile * FT + warp;
+            if (fl < P.count) {
+                const int f = P.first + fl;
+                const Row row = reinterpret_cast<const Row*>(st + L.rows_off)[warp];
+                FactorView V;
+                V.b0 = st + L.v0_off + warp * L.b0;
+                V.b1 = Fam::D1 ? st + L.v1_off + warp * L.b1 : nullptr;
+                V.meas = kSample ? nullptr : reinterpret_cast<const float*>(st + L.meas_off + (size_t)warp * L.mb);
+                V.out_res = out;
+                V.out_fwd = out + res_floats;
+                if (flags & (ROME_B200_RESIDUAL | ROME_B200_PROPOSAL_FWD)) {
+                    if (lane == 0) tma_store_wait_read();  // the previous tile's rows have left the slice
+                    __syncwarp();
+                }
+                Fam::template factor<kStatic, kSample>(row, P, V, f, lane);
+                if (flags & (ROME_B200_RESIDUAL | ROME_B200_PROPOSAL_FWD)) {
+                    fence_proxy_async();  // generic-proxy writes of the slice -> visible to the bulk-copy engine
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (flags & ROME_B200_RESIDUAL)
+                            tma_store_1d(P.res + (size_t)f * res_floats, V.out_res, (uint32_t)(res_floats * 4));
+                        if (flags & ROME_B200_PROPOSAL_FWD) {
+                            const size_t off = (size_t)f * Fam::DFWD * P.Npad;
+                            const uint32_t bytes = (uint32_t)(Fam::DFWD * P.Npad * 4);
+                            tma_store_1d(P.prop_fwd + off, V.out_fwd, bytes);
+                            // fused all-gather: the same slice goes to every peer GPU over NVLink
+                            for (int r = 0; r < P.n_peers; ++r) tma_store_1d(P.peer_fwd[r] + off, V.out_fwd, bytes);
+                        }
+                        tma_store_commit();
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+            if (++s == S) { s = 0; phase ^= 1u; }
+        }
+        if (lane == 0) tma_store_wait_all();
+    }
+    // a launch that overlapped its predecessor must not be seen as complete before the predecessor is
+    if (P.flags & ROME_B200_INDEPENDENT) asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <class Fam, uint32_t kStatic, bool kSample, int FT>
+int launch_ft(const EvalParams& p, const LaunchPlan& plan, int grid, cudaStream_t s) {
+    auto k = eval_kernel<Fam, kStatic, kSample, FT>;
+    static int configured[64] = {0};  // per-instantiation, per-device cache of the opt-in shared memory size
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || plan.smem_bytes > configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes);
+        if (e != cudaSuccess) return (int)e;
+        if (dev >= 0 && dev < 64) configured[dev] = plan.smem_bytes;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3((FT + 1) * 32);
+    cfg.dynamicSmemBytes = plan.smem_bytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (p.flags & ROME_B200_INDEPENDENT) ? 1 : 0;
+    return (int)cudaLaunchKernelEx(&cfg, k, p);
+}
+template <class Fam, bool kSample>
+int launch_sample(const EvalParams& p, const LaunchPlan& plan, int grid, cudaStream_t s) {
+    constexpr uint32_t smp = kSample ? ROME_B200_SAMPLE : 0u;
+    if (plan.ft == 8) {
+        if (plan.variant == 1) return launch_ft<Fam, kHot1 | smp, kSample, 8>(p, plan, grid, s);
+        if (plan.variant == 2) return launch_ft<Fam, kHot2 | smp, kSample, 8>(p, plan, grid, s);
+        return launch_ft<Fam, 0u, kSample, 8>(p, plan, grid, s);
+    }
+    if (plan.ft == 2) return launch_ft<Fam, 0u, kSample, 2>(p, plan, grid, s);
+    if (plan.ft == 1) return launch_ft<Fam, 0u, kSample, 1>(p, plan, grid, s);
+    return (int)cudaErrorInvalidValue;
+}
+template <class Fam>
+int launch_family(const EvalParams& p, const LaunchPlan& plan, int grid, cudaStream_t s) {
+    return (p.flags & ROME_B200_SAMPLE) ? launch_sample<Fam, true>(p, plan, grid, s)
+                                        : launch_sample<Fam, false>(p, plan, grid, s);
+}
+}  // namespace rome
