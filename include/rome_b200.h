@@ -28,7 +28,7 @@
  *     and staging scratch only.
  *   - variable coordinates use the reference's own layout: Float64, particle-major
  *     `[nvars][N][d]` (DFG `vecval`), d = 3 (Pose2: x,y,theta), 2 (Point2), 6 (Pose3: x,y,z,
- *     rotation vector) -- src/variables/VariableTypes.jl:13,35,47.
+ *     rotation vector), 3 (Point3) -- src/variables/VariableTypes.jl:13,23,35,47.
  *   - device layout ("anchored float32"): value = anchor(Float64, per variable / per factor
  *     mean) + offset(float32).  Every row set is PARTICLE-MAJOR like the reference's arrays:
  *     particles: one block per variable {anchor header, [Npad][d] float32 offsets};
@@ -68,7 +68,14 @@ enum rome_b200_status {
 };
 
 /* variable types: src/variables/VariableTypes.jl:35 (Pose2), :13 (Point2), :47 (Pose3) */
-enum rome_b200_vartype { ROME_B200_POSE2 = 0, ROME_B200_POINT2 = 1, ROME_B200_POSE3 = 2, ROME_B200_NVARTYPES = 3 };
+/* Point3: src/variables/VariableTypes.jl:23 */
+enum rome_b200_vartype {
+    ROME_B200_POSE2 = 0,
+    ROME_B200_POINT2 = 1,
+    ROME_B200_POSE3 = 2,
+    ROME_B200_POINT3 = 3,
+    ROME_B200_NVARTYPES = 4
+};
 
 enum rome_b200_family {
     ROME_B200_POSE2POSE2 = 0,
@@ -83,7 +90,12 @@ enum rome_b200_family {
     ROME_B200_POSE2POINT2RANGE = 8,   /* src/factors/Range2D.jl:43-54     r = rho - |l - p.t|             */
     ROME_B200_POINT2POINT2RANGE = 9,  /* src/factors/Range2D.jl:5-18      r = rho - |xj - xi|             */
     ROME_B200_POSE2POINT2BEARING = 10,/* src/factors/Bearing2D.jl:13-32   r = sym_rem(b - atan(R_p'(l-p.t))) */
-    ROME_B200_NFAMILIES = 11
+    ROME_B200_PRIORPOINT3 = 11,        /* src/factors/Point3D.jl:7-20         r = m - x                         */
+    ROME_B200_POINT3POINT3 = 12,       /* src/factors/Point3Point3.jl:4-15    r = m - (xj - xi)                 */
+    ROME_B200_POSE3POSE3XYYAW = 13,    /* src/factors/PartialPose3.jl:103-134 SE(2) residual of (x, y, yaw)     */
+    ROME_B200_POSE3POSE3ROTATION = 14, /* src/factors/PartialPose3.jl:198-226 r = m - Log(R_p' R_q)             */
+    ROME_B200_POSE3POSE3UNITTRANS = 15,/* src/factors/Pose3Pose3.jl:100-116   Pose3Pose3, unit translation part */
+    ROME_B200_NFAMILIES = 16
 };
 
 /* eval flags */
@@ -108,7 +120,7 @@ typedef struct rome_b200_buffers {
     float* res;        /* out: [nF][Npad][dr]                                                   */
     float* prop_fwd;   /* out: [nF][Npad][dv_last]  offsets from the last variable's anchor      */
     float* prop_bwd;   /* out: [nF][Npad][dv_first] offsets from the first variable's anchor     */
-    float* stats;      /* out: [nF][16] (SE(2) families) or [nF][32] (SE(3) families)            */
+    float* stats;      /* out: [nF][nstats], nstats = 16 or 32 (rome_b200_family_dims)          */
     float* jac;        /* out: [nF][Npad][dj] compact Jacobian entries                           */
 } rome_b200_buffers;
 
@@ -165,6 +177,10 @@ ROME_B200_API int rome_b200_set_factors_point2(rome_b200_ctx* ctx, int family, i
  * belief [nF][2] = (mean, standard deviation) */
 ROME_B200_API int rome_b200_set_factors_scalar(rome_b200_ctx* ctx, int family, int nF, const int32_t* i0, const int32_t* i1,
                                                const double* belief);
+/* Any family whose belief is ONE MvNormal(mu[dm], cov[dm][dm]) (every family except BEARINGRANGE and the scalar
+ * ones): i1 = NULL for priors.  The typed entry points above are thin wrappers of this one. */
+ROME_B200_API int rome_b200_set_factors_gaussian(rome_b200_ctx* ctx, int family, int nF, const int32_t* i0,
+                                                 const int32_t* i1, const double* mu, const double* cov);
 ROME_B200_API int rome_b200_num_factors(rome_b200_ctx* ctx, int family);
 
 /* ---- the hot path --------------------------------------------------------------------------- */

@@ -47,7 +47,9 @@ def lib() -> C.CDLL:
                         ("priorpose3", 3), ("pose2pose2_fwd", 3), ("pose2pose2_bwd", 3),
                         ("bearingrange_fwd", 3), ("pose3pose3_fwd", 3), ("pose3pose3_bwd", 3),
                         ("so3_exp", 2), ("so3_log", 2), ("priorpoint2", 3), ("point2point2", 4), ("pose2point2", 4),
-                        ("range2", 4), ("pose2point2bearing", 4)]:
+                        ("range2", 4), ("pose2point2bearing", 4), ("priorpoint3", 3), ("point3point3", 4),
+                        ("pose3pose3xyyaw", 4), ("pose3pose3rotation", 4), ("pose3pose3unittrans", 4),
+                        ("pose3_point", 3), ("pose3_coords", 3)]:
             fn = getattr(_lib, "rome_oracle_" + name)
             fn.restype = None
             fn.argtypes = [d] * n
@@ -129,6 +131,31 @@ def range2(rho, xi, l):
 
 def pose2point2bearing(b, p, l):
     return _call("pose2point2bearing", 1, np.atleast_1d(b), p, l)
+
+
+def priorpoint3(m, x):
+    return _call("priorpoint3", 3, m, x)
+
+
+def point3point3(m, xi, xj):
+    return _call("point3point3", 3, m, xi, xj)
+
+
+def pose3pose3xyyaw(X, p, q):
+    return _call("pose3pose3xyyaw", 3, X, p, q)
+
+
+def pose3pose3rotation(m, p, q):
+    return _call("pose3pose3rotation", 3, m, p, q)
+
+
+def pose3pose3unittrans(X, p, q):
+    return _call("pose3pose3unittrans", 6, X, p, q)
+
+
+def pose3_coords(t, R):
+    """coordinates (t, rotation vector) of the Pose3 point (t, R)"""
+    return _call("pose3_coords", 6, t, np.asarray(R, dtype=np.float64).reshape(9))
 
 
 def np_priorpoint2(m, x):
@@ -341,3 +368,25 @@ def np_priorpose3(m, p):
     m, p = np.asarray(m, dtype=np.float64), np.asarray(p, dtype=np.float64)
     U = np.swapaxes(np_so3_exp(p[..., 3:]), -1, -2) @ np_so3_exp(m[..., 3:])
     return np.concatenate([m[..., :3] - p[..., :3], np_so3_log(U)], -1)
+
+
+def np_pose3pose3xyyaw(X, p, q):
+    """src/factors/PartialPose3.jl:116-134 (vectorised twin)"""
+    X, p, q = (np.asarray(a, dtype=np.float64) for a in (X, p, q))
+    Rp, Rq = np_so3_exp(p[..., 3:]), np_so3_exp(q[..., 3:])
+    yp, yq = np.arctan2(Rp[..., 1, 0], Rp[..., 0, 0]), np.arctan2(Rq[..., 1, 0], Rq[..., 0, 0])
+    p2 = np.stack([p[..., 0], p[..., 1], yp], -1)
+    q2 = np.stack([q[..., 0], q[..., 1], yq], -1)
+    return np_pose2pose2(X, p2, q2)
+
+
+def np_pose3pose3rotation(m, p, q):
+    m, p, q = (np.asarray(a, dtype=np.float64) for a in (m, p, q))
+    U = np.swapaxes(np_so3_exp(p[..., 3:]), -1, -2) @ np_so3_exp(q[..., 3:])
+    return m - np_so3_log(U)
+
+
+def np_pose3pose3unittrans(X, p, q):
+    r = np_pose3pose3(X, p, q)
+    r[..., :3] /= np.linalg.norm(r[..., :3], axis=-1, keepdims=True)
+    return r

@@ -213,6 +213,46 @@ void rome_oracle_pose2point2bearing(const double b[1], const double p[3], const 
     r[0] = rome_oracle_sym_rem(b[0] - atan2(-s * dx + c * dy, c * dx + s * dy));
 }
 
+/* ---- next-row 3-D families ---- */
+/* src/factors/Point3D.jl:13-20 */
+void rome_oracle_priorpoint3(const double m[3], const double x[3], double r[3]) {
+    for (int i = 0; i < 3; ++i) r[i] = m[i] - x[i];
+}
+/* src/factors/Point3Point3.jl:11-15 */
+void rome_oracle_point3point3(const double m[3], const double xi[3], const double xj[3], double r[3]) {
+    for (int i = 0; i < 3; ++i) r[i] = m[i] - (xj[i] - xi[i]);
+}
+/* src/factors/PartialPose3.jl:116-134: p2 = (t_p[1:2], R from normalize(R_p[1:2,1])), q2 likewise;
+ *   qhat = compose(M2, p2, exp(M2, e, X)); Xc = vee(M2, q2, log(M2, q2, qhat))   (Hybrid SE(2): same reading as Pose2Pose2) */
+void rome_oracle_pose3pose3xyyaw(const double X[3], const double p[6], const double q[6], double r[3]) {
+    double tp[3], Rp[9], tq[3], Rq[9];
+    rome_oracle_pose3_point(p, tp, Rp);
+    rome_oracle_pose3_point(q, tq, Rq);
+    const double np_ = hypot(Rp[0], Rp[3]), nq = hypot(Rq[0], Rq[3]);
+    const double cp = Rp[0] / np_, sp = Rp[3] / np_, cq = Rq[0] / nq, sq = Rq[3] / nq;
+    const double cm = cos(X[2]), sm = sin(X[2]);
+    r[0] = tp[0] + cp * X[0] - sp * X[1] - tq[0];
+    r[1] = tp[1] + sp * X[0] + cp * X[1] - tq[1];
+    /* U = R_q2' R_p2 R(X.theta); angle = atan(U21, U11) */
+    const double ch = cp * cm - sp * sm, sh = sp * cm + cp * sm;
+    r[2] = atan2(sh * cq - ch * sq, ch * cq + sh * sq);
+}
+/* src/factors/PartialPose3.jl:212-226: Xc = vee(log(SO3, R_p, R_q)) = Log(R_p' R_q); return Xc_m - Xc */
+void rome_oracle_pose3pose3rotation(const double m[3], const double p[6], const double q[6], double r[3]) {
+    double tp[3], Rp[9], tq[3], Rq[9], U[9], w[3];
+    rome_oracle_pose3_point(p, tp, Rp);
+    rome_oracle_pose3_point(q, tq, Rq);
+    mat3_tmul(Rp, Rq, U);
+    rome_oracle_so3_log(U, w);
+    for (int i = 0; i < 3; ++i) r[i] = m[i] - w[i];
+}
+/* src/factors/Pose3Pose3.jl:107-116: Pose3Pose3 coordinates with normalize(Xc[1:3]) */
+void rome_oracle_pose3pose3unittrans(const double X[6], const double p[6], const double q[6], double r[6]) {
+    rome_oracle_pose3pose3(X, p, q, r);
+    const double n = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+    for (int i = 0; i < 3; ++i) r[i] /= n;
+}
+
 /* ================================================================================== */
 /* closed-form roots                                                                  */
 /* ================================================================================== */

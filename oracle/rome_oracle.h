@@ -64,6 +64,17 @@ void rome_oracle_range2(const double rho[1], const double xi[2], const double l[
 /* src/factors/Bearing2D.jl:23-32 Pose2Point2Bearing: sym_rem(b - atan(R_p'(l - p.t))) */
 void rome_oracle_pose2point2bearing(const double b[1], const double p[3], const double l[2], double r[1]);
 
+/* next-row 3-D families */
+/* src/factors/Point3D.jl:13-20 PriorPoint3: m - x ; src/factors/Point3Point3.jl:11-15: m - (xj - xi) */
+void rome_oracle_priorpoint3(const double m[3], const double x[3], double r[3]);
+void rome_oracle_point3point3(const double m[3], const double xi[3], const double xj[3], double r[3]);
+/* src/factors/PartialPose3.jl:116-134 Pose3Pose3XYYaw: SE(2) residual of the (x, y, yaw) projections */
+void rome_oracle_pose3pose3xyyaw(const double X[3], const double p[6], const double q[6], double r[3]);
+/* src/factors/PartialPose3.jl:212-226 Pose3Pose3Rotation: m - Log(R_p' R_q) */
+void rome_oracle_pose3pose3rotation(const double m[3], const double p[6], const double q[6], double r[3]);
+/* src/factors/Pose3Pose3.jl:107-116 Pose3Pose3UnitTrans */
+void rome_oracle_pose3pose3unittrans(const double X[6], const double p[6], const double q[6], double r[6]);
+
 /* ---- closed-form roots of the residual (what the per-particle solve converges to) */
 /* cf. src/services/OdometryUtils.jl:132-158 (addPose2Pose2 / odomKDE) */
 void rome_oracle_pose2pose2_fwd(const double X[3], const double p[3], double q[3]);

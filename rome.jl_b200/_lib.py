@@ -10,9 +10,10 @@ SO_PATH = os.path.join(HERE, "librome_b200.so")
 
 # enums of include/rome_b200.h
 OK, BAD_ARG, CUDA_ERROR, SHAPE_MISMATCH, NOT_SET, NO_DEVICE = 0, -1, -2, -3, -4, -5
-POSE2, POINT2, POSE3 = 0, 1, 2
+POSE2, POINT2, POSE3, POINT3 = 0, 1, 2, 3
 POSE2POSE2, PRIORPOSE2, BEARINGRANGE, POSE3POSE3, PRIORPOSE3 = 0, 1, 2, 3, 4
 PRIORPOINT2, POINT2POINT2, POSE2POINT2, POSE2POINT2RANGE, POINT2POINT2RANGE, POSE2POINT2BEARING = 5, 6, 7, 8, 9, 10
+PRIORPOINT3, POINT3POINT3, POSE3POSE3XYYAW, POSE3POSE3ROTATION, POSE3POSE3UNITTRANS = 11, 12, 13, 14, 15
 RESIDUAL, PROPOSAL_FWD, PROPOSAL_BWD, STATS, SAMPLE, WRITE_MEAS, JACOBIAN, INDEPENDENT = 1, 2, 4, 8, 16, 32, 64, 128
 
 # every symbol include/rome_b200.h declares (tests check the library exports each one)
@@ -22,7 +23,7 @@ SYMBOLS = [
     "rome_b200_set_particles", "rome_b200_get_particles", "rome_b200_particles_device", "rome_b200_adopt_proposal",
     "rome_b200_set_factors_pose2pose2", "rome_b200_set_factors_priorpose2", "rome_b200_set_factors_bearingrange",
     "rome_b200_set_factors_pose3pose3", "rome_b200_set_factors_priorpose3", "rome_b200_set_factors_point2",
-    "rome_b200_set_factors_scalar", "rome_b200_num_factors",
+    "rome_b200_set_factors_scalar", "rome_b200_set_factors_gaussian", "rome_b200_num_factors",
     "rome_b200_eval", "rome_b200_eval_host", "rome_b200_eval_host_async", "rome_b200_set_peer_proposals", "rome_b200_ipc_export",
     "rome_b200_ipc_import", "rome_b200_ipc_close", "rome_b200_graph_begin", "rome_b200_graph_end",
     "rome_b200_graph_launch", "rome_b200_malloc_device", "rome_b200_free_device", "rome_b200_malloc_host",
@@ -75,6 +76,7 @@ def load() -> C.CDLL:
     lib.rome_b200_set_factors_priorpose3.argtypes = [vp, i, ip32, dp, dp]
     lib.rome_b200_set_factors_point2.argtypes = [vp, i, i, ip32, ip32, dp, dp]
     lib.rome_b200_set_factors_scalar.argtypes = [vp, i, i, ip32, ip32, dp]
+    lib.rome_b200_set_factors_gaussian.argtypes = [vp, i, i, ip32, ip32, dp, dp]
     lib.rome_b200_num_factors.argtypes = [vp, i]
     lib.rome_b200_eval.argtypes = [vp, i, u32, u64, u32, i, i, C.POINTER(Buffers)]
     lib.rome_b200_eval_host.argtypes = [vp, i, u32, u64, u32, i, i, C.POINTER(Buffers)]

@@ -14,6 +14,8 @@ int launch_bearingrange(const EvalParams&, const LaunchPlan&, int, cudaStream_t)
 int launch_point2(int family, const EvalParams&, const LaunchPlan&, int, cudaStream_t);
 int launch_pose3pose3(const EvalParams&, const LaunchPlan&, int, cudaStream_t);
 int launch_priorpose3(const EvalParams&, const LaunchPlan&, int, cudaStream_t);
+int launch_point3(int family, const EvalParams&, const LaunchPlan&, int, cudaStream_t);
+int launch_pose3_partial(int family, const EvalParams&, const LaunchPlan&, int, cudaStream_t);
 
 // =============================================================================================
 // host side: launch planning + dispatch
@@ -33,6 +35,11 @@ static FamDims fam_dims(int family) {
         case ROME_B200_POSE2POINT2RANGE: return {(int)sizeof(RowS1), 3, 2, 1, 1, 0};
         case ROME_B200_POINT2POINT2RANGE: return {(int)sizeof(RowS1), 2, 2, 1, 1, 0};
         case ROME_B200_POSE2POINT2BEARING: return {(int)sizeof(RowS1), 3, 2, 1, 1, 0};
+        case ROME_B200_PRIORPOINT3: return {(int)sizeof(RowSE2), 3, 0, 3, 3, 3};
+        case ROME_B200_POINT3POINT3: return {(int)sizeof(RowSE2), 3, 3, 3, 3, 3};
+        case ROME_B200_POSE3POSE3XYYAW:
+        case ROME_B200_POSE3POSE3ROTATION: return {(int)sizeof(RowSE2), 6, 6, 3, 3, 0};
+        case ROME_B200_POSE3POSE3UNITTRANS: return {(int)sizeof(RowSE3), 6, 6, 6, 6, 0};
         default: return {(int)sizeof(RowSE3), 6, 0, 6, 6, 6};
     }
 }
@@ -52,7 +59,7 @@ static int min_stages_2cta() {
 int plan_launch(int family, uint32_t flags, int Npad, int smem_per_sm, int smem_per_cta_max, LaunchPlan* plan) {
     const FamDims fd = fam_dims(family);
     const bool sample = (flags & ROME_B200_SAMPLE) != 0;
-    const bool se3 = family == ROME_B200_POSE3POSE3 || family == ROME_B200_PRIORPOSE3;
+    const bool se3 = fd.d0 == 6;  // Pose3 families: one CTA per SM (register budget)
     if (fd.dfwd == 0) flags &= ~ROME_B200_PROPOSAL_FWD;
     const uint32_t out_flags = flags & ~(ROME_B200_SAMPLE | ROME_B200_INDEPENDENT);
     const int hot = out_flags == kHot1 ? 1 : out_flags == kHot2 ? 2 : 0;
@@ -98,6 +105,11 @@ int launch_eval(int family, const EvalParams& p, const LaunchPlan& plan, int gri
         case ROME_B200_POSE2POINT2RANGE:
         case ROME_B200_POINT2POINT2RANGE:
         case ROME_B200_POSE2POINT2BEARING: return launch_point2(family, p, plan, grid, s);
+        case ROME_B200_PRIORPOINT3:
+        case ROME_B200_POINT3POINT3: return launch_point3(family, p, plan, grid, s);
+        case ROME_B200_POSE3POSE3XYYAW:
+        case ROME_B200_POSE3POSE3ROTATION:
+        case ROME_B200_POSE3POSE3UNITTRANS: return launch_pose3_partial(family, p, plan, grid, s);
     }
     return (int)cudaErrorInvalidValue;
 }

@@ -32,8 +32,8 @@ struct Scratch {
     size_t cap = 0;
 };
 
-const int kVarDim[ROME_B200_NVARTYPES] = {3, 2, 6};
-const int kWrapDim[ROME_B200_NVARTYPES] = {2, -1, -1};
+const int kVarDim[ROME_B200_NVARTYPES] = {3, 2, 6, 3};
+const int kWrapDim[ROME_B200_NVARTYPES] = {2, -1, -1, -1};
 // family -> (first variable type, second variable type or -1, dm, dr, nstats, dj, row bytes, prop dims fwd/bwd)
 struct FamInfo {
     int vt0, vt1, dm, dr, nstats, dj, row_bytes, dfwd, dbwd;
@@ -50,6 +50,11 @@ const FamInfo kFam[ROME_B200_NFAMILIES] = {
     {ROME_B200_POSE2, ROME_B200_POINT2, 1, 1, 16, 0, (int)sizeof(RowS1), 0, 0},    // Pose2Point2Range
     {ROME_B200_POINT2, ROME_B200_POINT2, 1, 1, 16, 0, (int)sizeof(RowS1), 0, 0},   // Point2Point2Range
     {ROME_B200_POSE2, ROME_B200_POINT2, 1, 1, 16, 0, (int)sizeof(RowS1), 0, 0},    // Pose2Point2Bearing
+    {ROME_B200_POINT3, -1, 3, 3, 16, 0, (int)sizeof(RowSE2), 3, 0},                // PriorPoint3
+    {ROME_B200_POINT3, ROME_B200_POINT3, 3, 3, 16, 0, (int)sizeof(RowSE2), 3, 0},  // Point3Point3
+    {ROME_B200_POSE3, ROME_B200_POSE3, 3, 3, 16, 0, (int)sizeof(RowSE2), 0, 0},    // Pose3Pose3XYYaw
+    {ROME_B200_POSE3, ROME_B200_POSE3, 3, 3, 16, 0, (int)sizeof(RowSE2), 0, 0},    // Pose3Pose3Rotation
+    {ROME_B200_POSE3, ROME_B200_POSE3, 6, 6, 32, 0, (int)sizeof(RowSE3), 0, 0},    // Pose3Pose3UnitTrans
 };
 
 thread_local std::string g_create_error;
@@ -427,6 +432,20 @@ int rome_b200_set_factors_scalar(rome_b200_ctx* ctx, int family, int nF, const i
         r.mu = belief[2 * f]; r.sigma = (float)belief[2 * f + 1];
     }
     return upload_rows(ctx, family, rows.data(), nF, m0, m1);
+}
+int rome_b200_set_factors_gaussian(rome_b200_ctx* ctx, int family, int nF, const int32_t* i0, const int32_t* i1,
+                                   const double* mu, const double* cov) {
+    if (!ctx) return ROME_B200_BAD_ARG;
+    if (family < 0 || family >= ROME_B200_NFAMILIES) return fail(ctx, ROME_B200_BAD_ARG, "bad family");
+    const FamInfo& fi = kFam[family];
+    const bool binary = fi.vt1 >= 0;
+    if (binary && nF > 0 && !i1) return fail(ctx, ROME_B200_BAD_ARG, "second variable index array is NULL");
+    if (fi.row_bytes == (int)sizeof(RowSE3))
+        return set_gaussian_factors<RowSE3, 6>(ctx, family, nF, i0, binary ? i1 : nullptr, mu, cov);
+    if (fi.row_bytes == (int)sizeof(RowSE2) && fi.dm == 3)
+        return set_gaussian_factors<RowSE2, 3>(ctx, family, nF, i0, binary ? i1 : nullptr, mu, cov);
+    if (fi.row_bytes == (int)sizeof(RowPT2)) return rome_b200_set_factors_point2(ctx, family, nF, i0, i1, mu, cov);
+    return fail(ctx, ROME_B200_BAD_ARG, "family does not hold a single MvNormal belief");
 }
 int rome_b200_num_factors(rome_b200_ctx* ctx, int family) {
     if (!ctx || family < 0 || family >= ROME_B200_NFAMILIES) return ROME_B200_BAD_ARG;

@@ -10,11 +10,12 @@ import ctypes as C
 import numpy as np
 
 from . import _lib as L
-from ._lib import (BEARINGRANGE, JACOBIAN, POINT2, POINT2POINT2, POINT2POINT2RANGE, POSE2, POSE2POINT2,
-                   POSE2POINT2BEARING, POSE2POINT2RANGE, POSE2POSE2, POSE3, POSE3POSE3, PRIORPOINT2, PRIORPOSE2,
+from ._lib import (BEARINGRANGE, JACOBIAN, POINT2, POINT2POINT2, POINT2POINT2RANGE, POINT3, POINT3POINT3, POSE2,
+                   POSE2POINT2, POSE2POINT2BEARING, POSE2POINT2RANGE, POSE2POSE2, POSE3, POSE3POSE3,
+                   POSE3POSE3ROTATION, POSE3POSE3UNITTRANS, POSE3POSE3XYYAW, PRIORPOINT2, PRIORPOINT3, PRIORPOSE2,
                    PRIORPOSE3, PROPOSAL_BWD, PROPOSAL_FWD, RESIDUAL, SAMPLE, STATS, WRITE_MEAS, Buffers, RomeB200Error)
 
-VAR_DIM = {POSE2: 3, POINT2: 2, POSE3: 6}
+VAR_DIM = {POSE2: 3, POINT2: 2, POSE3: 6, POINT3: 3}
 # family -> (vartype of first variable, vartype of second variable or None, dm, dr, nstats, dj, dfwd, dbwd)
 FAMILY = {
     POSE2POSE2: (POSE2, POSE2, 3, 3, 16, 4, 3, 3),
@@ -29,15 +30,22 @@ FAMILY = {
     POSE2POINT2RANGE: (POSE2, POINT2, 1, 1, 16, 0, 0, 0),
     POINT2POINT2RANGE: (POINT2, POINT2, 1, 1, 16, 0, 0, 0),
     POSE2POINT2BEARING: (POSE2, POINT2, 1, 1, 16, 0, 0, 0),
+    PRIORPOINT3: (POINT3, None, 3, 3, 16, 0, 3, 0),
+    POINT3POINT3: (POINT3, POINT3, 3, 3, 16, 0, 3, 0),
+    POSE3POSE3XYYAW: (POSE3, POSE3, 3, 3, 16, 0, 0, 0),
+    POSE3POSE3ROTATION: (POSE3, POSE3, 3, 3, 16, 0, 0, 0),
+    POSE3POSE3UNITTRANS: (POSE3, POSE3, 6, 6, 32, 0, 0, 0),
 }
 # algorithmic bytes per factor-particle eval with this layout (DESIGN.md "bytes per eval"):
 # read both variables' offsets + the measurement offsets, write the residual (float32 each)
 BYTES_PER_EVAL = {POSE2POSE2: 48, PRIORPOSE2: 36, BEARINGRANGE: 36, POSE3POSE3: 96, PRIORPOSE3: 72,
                   PRIORPOINT2: 24, POINT2POINT2: 32, POSE2POINT2: 36, POSE2POINT2RANGE: 28, POINT2POINT2RANGE: 24,
-                  POSE2POINT2BEARING: 28}
+                  POSE2POINT2BEARING: 28, PRIORPOINT3: 36, POINT3POINT3: 48, POSE3POSE3XYYAW: 72,
+                  POSE3POSE3ROTATION: 72, POSE3POSE3UNITTRANS: 96}
 BYTES_PER_EVAL_SAMPLED = {POSE2POSE2: 36, PRIORPOSE2: 24, BEARINGRANGE: 28, POSE3POSE3: 72, PRIORPOSE3: 48,
                           PRIORPOINT2: 16, POINT2POINT2: 24, POSE2POINT2: 28, POSE2POINT2RANGE: 24,
-                          POINT2POINT2RANGE: 20, POSE2POINT2BEARING: 24}
+                          POINT2POINT2RANGE: 20, POSE2POINT2BEARING: 24, PRIORPOINT3: 24, POINT3POINT3: 36,
+                          POSE3POSE3XYYAW: 60, POSE3POSE3ROTATION: 60, POSE3POSE3UNITTRANS: 72}
 
 
 def npad(N: int) -> int:
@@ -198,6 +206,14 @@ class Context:
         self._ck(self._lib.rome_b200_set_factors_point2(self._h, family, len(i0), self._ip(i0),
                                                         None if i1 is None else self._ip(i1), self._dp(mu),
                                                         self._dp(cov)))
+
+    def set_factors_gaussian(self, family, i0, i1, mu, cov):
+        """any family with one MvNormal(mu[dm], cov[dm][dm]) belief; i1=None for priors"""
+        i0, mu, cov = _i32(i0), _f64(mu), _f64(cov)
+        i1 = None if i1 is None else _i32(i1)
+        self._ck(self._lib.rome_b200_set_factors_gaussian(self._h, family, len(i0), self._ip(i0),
+                                                          None if i1 is None else self._ip(i1), self._dp(mu),
+                                                          self._dp(cov)))
 
     def set_factors_scalar(self, family, i0, i1, belief):
         """Pose2Point2Range / Point2Point2Range / Pose2Point2Bearing: Normal(mean, sigma) rows [nF][2]"""

@@ -68,6 +68,10 @@ class Pose3(InferenceVariable):
     vartype, dim, manifold = L.POSE3, 6, "SpecialEuclidean(3; vectors=HybridTangentRepresentation())"
 
 
+class Point3(InferenceVariable):  # src/variables/VariableTypes.jl:23
+    vartype, dim, manifold = L.POINT3, 3, "TranslationGroup(3)"
+
+
 # ---- factors -----------------------------------------------------------------------------------------
 class AbstractFactor:
     family: int
@@ -182,8 +186,54 @@ class Pose2Point2Bearing(AbstractManifoldMinimize):  # src/factors/Bearing2D.jl:
     variabletypes = (Pose2, Point2)
 
 
+@dataclass
+class PriorPoint3(AbstractPrior):  # src/factors/Point3D.jl:7-9
+    Z: MvNormal = field(default_factory=lambda: _default_mv(3, [1.0, 1.0, 1.0]))
+    family = L.PRIORPOINT3
+    variabletypes = (Point3,)
+
+
+@dataclass
+class Point3Point3(AbstractManifoldMinimize):  # src/factors/Point3Point3.jl:4-6
+    Z: MvNormal = field(default_factory=lambda: _default_mv(3, [0.1, 0.1, 0.1]))
+    family = L.POINT3POINT3
+    variabletypes = (Point3, Point3)
+
+
+@dataclass
+class Pose3Pose3XYYaw(AbstractManifoldMinimize):  # src/factors/PartialPose3.jl:103-113, partial = (1, 2, 6)
+    Z: MvNormal
+    family = L.POSE3POSE3XYYAW
+    variabletypes = (Pose3, Pose3)
+    partial = (1, 2, 6)
+
+    def __post_init__(self):
+        if self.Z.mu.shape[0] != 3:
+            raise ValueError("Pose3Pose3XYYaw needs a 3-dimensional (x, y, yaw) belief")
+
+
+@dataclass
+class Pose3Pose3Rotation(AbstractManifoldMinimize):  # src/factors/PartialPose3.jl:198-204, partial = (4, 5, 6)
+    Z: MvNormal
+    family = L.POSE3POSE3ROTATION
+    variabletypes = (Pose3, Pose3)
+    partial = (4, 5, 6)
+
+    def __post_init__(self):
+        if self.Z.mu.shape[0] != 3:
+            raise ValueError("Pose3Pose3Rotation needs a 3-dimensional rotation-vector belief")
+
+
+@dataclass
+class Pose3Pose3UnitTrans(AbstractManifoldMinimize):  # src/factors/Pose3Pose3.jl:100-105
+    Z: MvNormal = field(default_factory=lambda: _default_mv(6, [0.01] * 3 + [0.0001] * 3))
+    family = L.POSE3POSE3UNITTRANS
+    variabletypes = (Pose3, Pose3)
+
+
 SCALAR_FACTORS = (Pose2Point2Range, Point2Point2Range, Pose2Point2Bearing)
 POINT2_FACTORS = (PriorPoint2, Point2Point2, Pose2Point2)
+PARTIAL_FACTORS = (Pose3Pose3XYYaw, Pose3Pose3Rotation, Pose3Pose3UnitTrans)  # no closed-form full proposal
 
 
 def getManifold(x) -> str:
@@ -192,12 +242,20 @@ def getManifold(x) -> str:
         x = x()
     if isinstance(x, (Pose2Pose2, PriorPose2, Pose2)):
         return Pose2.manifold  # src/factors/Pose2D.jl:34, PriorPose2.jl:17
-    if isinstance(x, (Pose3Pose3, PriorPose3, Pose3)):
+    if isinstance(x, (Pose3Pose3, PriorPose3)) or x is Pose3 or type(x) is Pose3:
         return Pose3.manifold  # src/factors/Pose3Pose3.jl:13, Pose3D.jl:13
     if isinstance(x, Pose2Point2BearingRange):  # src/factors/BearingRange2D.jl:15
         return "ProductGroup(ProductManifold(SpecialOrthogonal(2), TranslationGroup(1)), LeftInvariantRepresentation())"
     if isinstance(x, (Point2, PriorPoint2, Point2Point2, Pose2Point2)):
         return Point2.manifold  # Point2D.jl:12,29; Pose2Point2.jl:18
+    if isinstance(x, (Point3, PriorPoint3, Point3Point3)):
+        return Point3.manifold  # Point3D.jl:11, Point3Point3.jl:8
+    if isinstance(x, Pose3Pose3XYYaw):
+        return Pose2.manifold  # PartialPose3.jl:113
+    if isinstance(x, Pose3Pose3Rotation):
+        return "SpecialOrthogonal(3)"  # PartialPose3.jl:204
+    if isinstance(x, Pose3Pose3UnitTrans):
+        return Pose3.manifold  # Pose3Pose3.jl:105
     if isinstance(x, (Pose2Point2Range, Point2Point2Range)):
         return "TranslationGroup(1)"  # Range2D.jl:9,49
     if isinstance(x, Pose2Point2Bearing):
@@ -254,5 +312,7 @@ def unpack(d: dict):
     cls = {"Pose2Pose2": Pose2Pose2, "PriorPose2": PriorPose2, "Pose3Pose3": Pose3Pose3, "PriorPose3": PriorPose3,
            "PriorPoint2": PriorPoint2, "Point2Point2": Point2Point2, "Pose2Point2": Pose2Point2,
            "Pose2Point2Range": Pose2Point2Range, "Point2Point2Range": Point2Point2Range,
-           "Pose2Point2Bearing": Pose2Point2Bearing}[name]
+           "Pose2Point2Bearing": Pose2Point2Bearing, "PriorPoint3": PriorPoint3, "Point3Point3": Point3Point3,
+           "Pose3Pose3XYYaw": Pose3Pose3XYYaw, "Pose3Pose3Rotation": Pose3Pose3Rotation,
+           "Pose3Pose3UnitTrans": Pose3Pose3UnitTrans}[name]
     return cls(_unpack_belief(d["Z"]))

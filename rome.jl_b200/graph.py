@@ -15,10 +15,10 @@ import numpy as np
 
 from . import _lib as L
 from .engine import FAMILY, VAR_DIM, Context, meas_to_offsets, offsets_to_meas, rows_to_particle_major
-from .factors import (POINT2_FACTORS, SCALAR_FACTORS, AbstractFactor, InferenceVariable, Point2, Pose2,
-                      Pose2Point2BearingRange, Pose3, factor_mean)
+from .factors import (PARTIAL_FACTORS, POINT2_FACTORS, SCALAR_FACTORS, AbstractFactor, InferenceVariable, Point2, Point3,
+                      Pose2, Pose2Point2BearingRange, Pose3, factor_mean)
 
-_VARCLASS = {L.POSE2: Pose2, L.POINT2: Point2, L.POSE3: Pose3}
+_VARCLASS = {L.POSE2: Pose2, L.POINT2: Point2, L.POSE3: Pose3, L.POINT3: Point3}
 
 
 @dataclass
@@ -61,7 +61,7 @@ class FactorGraph:
         self.solverParams = solverParams or SolverParams()
         self.variables: dict[str, DFGVariable] = {}
         self.factors: dict[str, DFGFactor] = {}
-        self._nvar = {L.POSE2: 0, L.POINT2: 0, L.POSE3: 0}
+        self._nvar = {t: 0 for t in VAR_DIM}
         self._nfac = {f: 0 for f in FAMILY}
 
     def __getitem__(self, label):
@@ -83,7 +83,7 @@ def addVariable(fg: FactorGraph, label, variableType, tags=None, N=None) -> DFGV
     if label in fg.variables:
         raise KeyError(f"variable {label} already exists")
     if not (isinstance(variableType, type) and issubclass(variableType, InferenceVariable)):
-        raise TypeError("variableType must be Pose2, Point2 or Pose3")
+        raise TypeError("variableType must be Pose2, Point2, Pose3 or Point3")
     v = DFGVariable(label, variableType, fg._nvar[variableType.vartype], tags=list(tags or []))
     fg._nvar[variableType.vartype] += 1
     fg.variables[label] = v
@@ -206,6 +206,8 @@ class DeviceGraph:
                 c.set_factors_point2(fam, i0, i1, a, b)
             elif isinstance(facs[0].fnc, SCALAR_FACTORS):
                 c.set_factors_scalar(fam, i0, i1, a)
+            else:  # every other family holds one MvNormal belief
+                c.set_factors_gaussian(fam, i0, i1, a, b)
 
     def means(self, family) -> np.ndarray:
         return np.stack([factor_mean(f.fnc) for f in self.by_family[family]])
@@ -319,6 +321,8 @@ def approxConv(fg: FactorGraph, flabel, target, N: int | None = None, seed=0, ct
                 val = val[np.random.default_rng(seed).integers(0, val.shape[0], N)]
             pts.append(val)
     last = len(fnc.variabletypes) - 1
+    if isinstance(fnc, PARTIAL_FACTORS):
+        raise NotImplementedError(f"{type(fnc).__name__} is a partial constraint: the convolution has no unique root")
     if isinstance(fnc, SCALAR_FACTORS):
         # one equation for a 2- or 3-dimensional target: a 1-parameter family of roots, left to the optimiser's
         # start point in the reference; no closed form is shipped
@@ -331,6 +335,8 @@ def approxConv(fg: FactorGraph, flabel, target, N: int | None = None, seed=0, ct
         # pose from landmark is a 1-parameter family: the reference leaves it to the optimiser's start
         # point + inflation noise; no closed form is shipped for it.
         raise NotImplementedError("Pose2Point2BearingRange: convolution onto the pose has no unique root")
+    elif FAMILY[fnc.family][7] == 0:
+        raise NotImplementedError(f"{type(fnc).__name__}: only the convolution onto the last variable is closed-form here")
     else:
         flag, key = L.PROPOSAL_BWD, "prop_bwd"
     dg = DeviceGraph(_mini_graph(fnc, pts, N), ctx or default_context(), N=N)

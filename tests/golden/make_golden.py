@@ -101,6 +101,47 @@ def known_answers():
                        modulo_2pi=True))
     Bg.append(dict(src="test/testBearing2D.jl:59-66", b=pi, p=[0., 0, 0], l=[-1., -0.001], expect=[-0.001], atol=1e-3))
 
+    # ---- next-row 3-D families: test/testPartialPose3.jl ------------------------------------
+    # poses are given there as (t, R); coordinates = (t, rotation vector of R) computed with SciPy here
+    from scipy.spatial.transform import Rotation as Rot
+
+    def coords(t, R):
+        return [float(v) for v in t] + [float(v) for v in Rot.from_matrix(np.asarray(R, dtype=float)).as_rotvec()]
+
+    def RZ(a): return Rot.from_euler("z", a).as_matrix()
+    def RY(a): return Rot.from_euler("y", a).as_matrix()
+    def RX(a): return Rot.from_euler("x", a).as_matrix()
+    Y = ka.setdefault("pose3pose3xyyaw", [])
+    src = "test/testPartialPose3.jl"
+    mu2 = [20.0, 5.0, pi / 2]  # :91-92, evaluated at the belief mean (the reference samples: atol 0.15)
+    cases = [
+        (":172-177", ([0, 0, 0.], RZ(0)), ([20, 5, 0.], RZ(pi / 2))),
+        (":179-183", ([0, 0, 0.], RZ(pi / 2)), ([-5, 20, 0.], np.diag([-1., -1, 1]))),
+        (":185-189", ([0, 0, 100.], RZ(pi / 2)), ([-5, 20, -100.], np.diag([-1., -1, 1]))),
+        (":191-196", ([0, 0, 0.], RY(pi / 4)), ([20, 5, 0.], RZ(pi / 2) @ RY(pi / 4))),
+        (":198-202", ([0, 0, 10.], RY(pi / 4)), ([20, 5, -10.], RZ(pi / 2) @ RY(pi / 4))),
+        (":204-208", ([0, 0, 0.], RX(pi / 4)), ([20, 5, 0.], RZ(pi / 2) @ RX(pi / 4))),
+        (":210-214", ([0, 0, 10.], RX(pi / 4)), ([20, 5, -10.], RZ(pi / 2) @ RX(pi / 4))),
+        (":216-220", ([10, 0, 0.], RX(pi / 4)), ([30, 5, 0.], RZ(pi / 2) @ RX(pi / 4))),
+        (":222-226", ([0, 0, 0.], RY(pi / 4) @ RX(pi / 6)), ([20, 5, 0.], RZ(pi / 2) @ RY(pi / 4) @ RX(pi / 6))),
+        (":228-232", ([10, 0, 10.], RY(pi / 4) @ RX(pi / 6)), ([30, 5, -10.], RZ(pi / 2) @ RY(pi / 4) @ RX(pi / 6))),
+    ]
+    for ln, (tp, Rp), (tq, Rq) in cases:
+        Y.append(dict(src=src + ln, X=mu2, p=coords(tp, Rp), q=coords(tq, Rq), expect=[0, 0, 0], atol=0.15,
+                      exact_atol=1e-9))
+    # sign / frame checks :272-285 (RotZYX(0, -pi/4, pi/4) = Rz(0) Ry(-pi/4) Rx(pi/4))
+    Rj = RZ(0.0) @ RY(-pi / 4) @ RX(pi / 4)
+    Y.append(dict(src=src + ":272-277", X=[20.0, 5.0, 0.0], p=coords([10, 0, 10.], RZ(0.0)), q=coords([20, 10, -10.], Rj),
+                  expect=[10, -5, 0], atol=0.15, exact_atol=1e-9))
+    Y.append(dict(src=src + ":280-285", X=[20.0, 5.0, pi / 4], p=coords([10, 0, 10.], RZ(pi / 2)),
+                  q=coords([20, 10, -10.], Rj), expect=[-15, 10, 3 * pi / 4], atol=0.15, exact_atol=1e-9))
+    # Pose3Pose3Rotation :504-548: p = identity, q = (0, RotXYZ(rpy)) with one non-zero angle, measurement = rpy
+    Rr = ka.setdefault("pose3pose3rotation", [])
+    for rpy in [[0, 0, 0], [0.1, 0, 0], [0, 0.1, 0], [0, 0, 0.1], [-0.1, 0, 0], [0, -0.1, 0], [0, 0, -0.1]]:
+        Rq = RX(rpy[0]) @ RY(rpy[1]) @ RZ(rpy[2])  # Rotations.RotXYZ
+        Rr.append(dict(src=src + ":504-548", m=[float(v) for v in rpy], p=[0.0] * 6, q=coords([0, 0, 0.], Rq),
+                       expect_norm_below=1e-10))
+
     # parametric square loop: the posterior means the reference asserts are exact roots of the
     # chain x_{k+1} = x_k o Exp(m) (pins the Hybrid exp: translation NOT coupled through V(theta))
     ka["pose2pose2_parametric"].append(dict(

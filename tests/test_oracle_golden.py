@@ -193,3 +193,38 @@ def test_next_row_families(ka):
         assert np.allclose(O.pose2point2(m, p, xj), O.np_pose2point2(m, p, xj), atol=1e-12)
         assert np.allclose(O.range2(7.0, xi, xj), 7.0 - np.linalg.norm(xj - xi))
         assert np.allclose(O.range2(7.0, p, xj), O.np_range2([7.0], p, xj))
+
+
+def test_next_row_3d_families(ka):
+    """Pose3Pose3XYYaw / Pose3Pose3Rotation known answers of test/testPartialPose3.jl, C vs NumPy,
+    and the point factors"""
+    for c in ka["pose3pose3xyyaw"]:
+        r = O.pose3pose3xyyaw(c["X"], c["p"], c["q"])
+        d = r - np.array(c["expect"])
+        d[2] = O.np_wrap(d[2])
+        assert np.all(np.abs(d) < c["atol"]), (c["src"], r)          # the reference's own tolerance
+        assert np.all(np.abs(d) < c["exact_atol"]), (c["src"], r)    # the cases are exact at the belief mean
+        assert np.allclose(O.np_pose3pose3xyyaw(c["X"], c["p"], c["q"]), r, atol=1e-12)
+    for c in ka["pose3pose3rotation"]:
+        r = O.pose3pose3rotation(c["m"], c["p"], c["q"])
+        _check(r, c)
+        assert np.allclose(O.np_pose3pose3rotation(c["m"], c["p"], c["q"]), r, atol=1e-12)
+    rng = np.random.default_rng(8)
+    for _ in range(50):
+        m, xi, xj = rng.normal(size=3), rng.normal(size=3) * 10, rng.normal(size=3) * 10
+        assert np.allclose(O.priorpoint3(m, xi), m - xi)
+        assert np.allclose(O.point3point3(m, xi, xj), m - (xj - xi))
+        p, q = rng.normal(size=6), rng.normal(size=6)
+        X = rng.normal(size=6)
+        r6, ru = O.pose3pose3(X, p, q), O.pose3pose3unittrans(X, p, q)
+        assert np.allclose(ru[:3], r6[:3] / np.linalg.norm(r6[:3])) and np.allclose(ru[3:], r6[3:])
+        assert np.allclose(O.np_pose3pose3unittrans(X, p, q), ru, atol=1e-10)
+        X3 = rng.normal(size=3)
+        assert np.allclose(O.np_pose3pose3xyyaw(X3, p, q), O.pose3pose3xyyaw(X3, p, q), atol=1e-10)
+        assert np.allclose(O.np_pose3pose3rotation(X3, p, q), O.pose3pose3rotation(X3, p, q), atol=1e-10)
+        # a yaw-only pair reduces XYYaw to Pose2Pose2
+        p2, q2 = rng.normal(size=3), rng.normal(size=3)
+        P3, Q3 = [p2[0], p2[1], 3.0, 0, 0, p2[2]], [q2[0], q2[1], -1.0, 0, 0, q2[2]]
+        d = O.pose3pose3xyyaw(X3, P3, Q3) - O.pose2pose2(X3, p2, q2)
+        d[2] = O.np_wrap(d[2])
+        assert np.allclose(d, 0, atol=1e-12)
