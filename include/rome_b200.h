@@ -101,7 +101,8 @@ enum rome_b200_family {
 /* eval flags */
 #define ROME_B200_RESIDUAL 1u     /* write the residual coordinates                                  */
 #define ROME_B200_PROPOSAL_FWD 2u /* closed-form root for the LAST variable (q / landmark / prior var) */
-#define ROME_B200_PROPOSAL_BWD 4u /* closed-form root for the FIRST variable (Pose2Pose2, Pose3Pose3) */
+#define ROME_B200_PROPOSAL_BWD 4u /* closed-form root for the FIRST variable (Pose2Pose2, Pose3Pose3; BearingRange:
+                                     the root that keeps the pose particle's current heading)          */
 #define ROME_B200_STATS 8u        /* per-factor statistics (warp-shuffle reductions)                 */
 #define ROME_B200_SAMPLE 16u      /* getSample fused in-kernel (Philox4x32-10); `meas` is not read   */
 #define ROME_B200_WRITE_MEAS 32u  /* with SAMPLE: also store the drawn measurement offsets            */
@@ -201,6 +202,26 @@ ROME_B200_API int rome_b200_eval_host(rome_b200_ctx* ctx, int family, uint32_t f
 ROME_B200_API int rome_b200_eval_host_async(rome_b200_ctx* ctx, int family, uint32_t flags, uint64_t seed,
                                             uint32_t stream_id, int first, int count,
                                             const rome_b200_buffers* host_buffers);
+
+/* ---- the step after the path: belief update = product of the proposal densities -------------
+ * Replaces the host hop  proposals -> AMP.manifoldProduct / manikde! -> new particles  (IIF propagateBelief; callers
+ * test/testBearingRange2D.jl:275,296,342, test/testBasicPose2Conv.jl:25-34): every proposal row is a kernel density
+ * estimate (per-dimension rule-of-thumb bandwidth from its own particles, circular statistics for headings); N samples
+ * of the product of a variable's k proposal KDEs are drawn by Gibbs sampling over the component labels and written
+ * into the device particle store of that variable type, so particles stay on the GPU between sweeps.
+ * The plan lists, per variable (CSR `var_offsets[nvars+1]`), its sources: buffer index `src_buf` into the
+ * `d_prop_bufs` array given to rome_b200_product, and proposal row `src_row` (the factor index) inside that buffer.
+ * Rows must hold offsets from THAT variable's anchor (prop_fwd of factors whose last variable it is, prop_bwd of
+ * factors whose first variable it is).  Variables without sources keep their particles; one source is adopted as is. */
+#define ROME_B200_MAX_PRODUCT_SOURCES 32 /* proposals per variable */
+#define ROME_B200_MAX_PRODUCT_BUFFERS 16 /* distinct proposal buffers per call */
+#define ROME_B200_PRODUCT_REANCHOR 1u    /* afterwards move every anchor onto the variable's new first particle */
+ROME_B200_API int rome_b200_set_product_plan(rome_b200_ctx* ctx, int vartype, int nvars, const int32_t* var_offsets,
+                                             const int32_t* src_buf, const int32_t* src_row);
+/* gibbs_iters <= 0 selects the default (3).  d_bw_out: optional device [nsrc][d] bandwidths (diagnostics). */
+ROME_B200_API int rome_b200_product(rome_b200_ctx* ctx, int vartype, int n_bufs, const float* const* d_prop_bufs,
+                                    uint64_t seed, uint32_t stream_id, int gibbs_iters, uint32_t flags, float* d_bw_out);
+ROME_B200_API int rome_b200_reanchor(rome_b200_ctx* ctx, int vartype);
 
 /* ---- multi-GPU: proposals written straight into the peers' buffers (fused compute + all-gather) ------------
  * With peers set for a family, every evaluation with ROME_B200_PROPOSAL_FWD stores each factor's forward-proposal

@@ -390,3 +390,75 @@ def np_pose3pose3unittrans(X, p, q):
     r = np_pose3pose3(X, p, q)
     r[..., :3] /= np.linalg.norm(r[..., :3], axis=-1, keepdims=True)
     return r
+
+
+# ----------------------------------------------------------------------------------
+# product of proposal KDEs.  PARITY UNPINNED: the reference's product sampler lives in
+# ApproxManifoldProducts / KernelDensityEstimate (absent from /root/reference, versions Project.toml:51,67) and is
+# stochastic; this is a NumPy restatement of the algorithm the CUDA kernel implements (label Gibbs sampling over
+# Gaussian-kernel KDEs with rule-of-thumb bandwidths), checked statistically, never bit for bit.
+# ----------------------------------------------------------------------------------
+def kde_bandwidth(pts, wrap_dim=None):
+    """per-dimension rule-of-thumb bandwidth h = std * (4 / ((d + 2) N))^(1 / (d + 4)); circular std for wrap_dim"""
+    pts = np.asarray(pts, dtype=np.float64)
+    N, d = pts.shape
+    x = pts.copy()
+    if wrap_dim is not None:
+        m = np.arctan2(np.sin(x[:, wrap_dim]).sum(), np.cos(x[:, wrap_dim]).sum())
+        x[:, wrap_dim] = np_wrap(x[:, wrap_dim] - m)
+    std = np.sqrt(((x - x.mean(0) * (np.arange(d) != (wrap_dim if wrap_dim is not None else -1))) ** 2).sum(0) / max(N - 1, 1))
+    return np.maximum(std * (4.0 / ((d + 2.0) * N)) ** (1.0 / (d + 4.0)), 1e-6)
+
+
+def product_gibbs(props, n_out, iters=3, wrap_dim=None, seed=0):
+    """props: list of [N][d] particle sets (k >= 2).  Returns [n_out][d] samples of the product of their KDEs:
+    sources 0 and 1 are sampled exactly from the N^2-component pair mixture, further sources enter conditioned on the
+    components already chosen, then `iters` Gibbs sweeps over all labels (k > 2 only) -- the CUDA kernel's algorithm."""
+    rng = np.random.default_rng(seed)
+    props = [np.asarray(p, dtype=np.float64) for p in props]
+    k, (N, d) = len(props), props[0].shape
+    w = [1.0 / kde_bandwidth(p, wrap_dim) ** 2 for p in props]  # precisions per source and dimension
+    out = np.zeros((n_out, d))
+
+    def wrapdiff(dlt):
+        if wrap_dim is not None:
+            dlt[..., wrap_dim] = np_wrap(dlt[..., wrap_dim])
+        return dlt
+
+    def fuse(sel, upto, skip):
+        lam, s, ref = np.zeros(d), np.zeros(d), None
+        for j in range(upto):
+            if j == skip:
+                continue
+            x = props[j][sel[j]].copy()
+            if wrap_dim is not None:
+                if ref is None:
+                    ref = x[wrap_dim]
+                x[wrap_dim] = ref + np_wrap(x[wrap_dim] - ref)
+            lam += w[j]
+            s += w[j] * x
+        return s / lam, 1.0 / lam
+
+    def draw(j, mu, var):
+        q = -0.5 * (wrapdiff(props[j] - mu) ** 2 / (1.0 / w[j] + var)).sum(1)
+        return int(np.argmax(q + rng.gumbel(size=N)))
+
+    q01 = -0.5 * (wrapdiff(props[0][:, None, :] - props[1][None, :, :]) ** 2 / (1.0 / w[0] + 1.0 / w[1])).sum(-1)
+    lw = q01.max(1) + np.log(np.exp(q01 - q01.max(1, keepdims=True)).sum(1))
+    cdf = np.cumsum(np.exp(lw - lw.max()))
+    for c in range(n_out):
+        sel = np.zeros(k, dtype=int)
+        sel[0] = min(int(np.searchsorted(cdf, rng.random() * cdf[-1])), N - 1)
+        sel[1] = draw(1, *fuse(sel, 1, -1))
+        for j in range(2, k):
+            sel[j] = draw(j, *fuse(sel, j, -1))
+        if k > 2:
+            for _ in range(iters):
+                for j in range(k):
+                    sel[j] = draw(j, *fuse(sel, k, j))
+        mu, var = fuse(sel, k, -1)
+        x = mu + np.sqrt(var) * rng.normal(size=d)
+        if wrap_dim is not None:
+            x[wrap_dim] = np_wrap(x[wrap_dim])
+        out[c] = x
+    return out

@@ -22,6 +22,7 @@ from .canonical import (generateGraph_Beehive, generateGraph_Circle, generateGra
                         generateGraph_ManhattanShaped, generateGraph_Pose3Chain, generateGraph_ZeroPose,
                         seed_particles)
 from . import sharding
+from .solver import GibbsSolver, build_product_plans, solveGraphGibbs
 from .g2o import graphFromEdgeArrays, importG2o, loadG2o, parseG2oInstruction
 
 __version__ = "0.1.0"

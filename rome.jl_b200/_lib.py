@@ -15,6 +15,7 @@ POSE2POSE2, PRIORPOSE2, BEARINGRANGE, POSE3POSE3, PRIORPOSE3 = 0, 1, 2, 3, 4
 PRIORPOINT2, POINT2POINT2, POSE2POINT2, POSE2POINT2RANGE, POINT2POINT2RANGE, POSE2POINT2BEARING = 5, 6, 7, 8, 9, 10
 PRIORPOINT3, POINT3POINT3, POSE3POSE3XYYAW, POSE3POSE3ROTATION, POSE3POSE3UNITTRANS = 11, 12, 13, 14, 15
 RESIDUAL, PROPOSAL_FWD, PROPOSAL_BWD, STATS, SAMPLE, WRITE_MEAS, JACOBIAN, INDEPENDENT = 1, 2, 4, 8, 16, 32, 64, 128
+PRODUCT_REANCHOR, MAX_PRODUCT_SOURCES, MAX_PRODUCT_BUFFERS = 1, 32, 16
 
 # every symbol include/rome_b200.h declares (tests check the library exports each one)
 SYMBOLS = [
@@ -24,7 +25,8 @@ SYMBOLS = [
     "rome_b200_set_factors_pose2pose2", "rome_b200_set_factors_priorpose2", "rome_b200_set_factors_bearingrange",
     "rome_b200_set_factors_pose3pose3", "rome_b200_set_factors_priorpose3", "rome_b200_set_factors_point2",
     "rome_b200_set_factors_scalar", "rome_b200_set_factors_gaussian", "rome_b200_num_factors",
-    "rome_b200_eval", "rome_b200_eval_host", "rome_b200_eval_host_async", "rome_b200_set_peer_proposals", "rome_b200_ipc_export",
+    "rome_b200_eval", "rome_b200_eval_host", "rome_b200_eval_host_async", "rome_b200_set_product_plan", "rome_b200_product",
+    "rome_b200_reanchor", "rome_b200_set_peer_proposals", "rome_b200_ipc_export",
     "rome_b200_ipc_import", "rome_b200_ipc_close", "rome_b200_graph_begin", "rome_b200_graph_end",
     "rome_b200_graph_launch", "rome_b200_malloc_device", "rome_b200_free_device", "rome_b200_malloc_host",
     "rome_b200_free_host", "rome_b200_memcpy_h2d", "rome_b200_memcpy_d2h", "rome_b200_launch_count",
@@ -81,6 +83,9 @@ def load() -> C.CDLL:
     lib.rome_b200_eval.argtypes = [vp, i, u32, u64, u32, i, i, C.POINTER(Buffers)]
     lib.rome_b200_eval_host.argtypes = [vp, i, u32, u64, u32, i, i, C.POINTER(Buffers)]
     lib.rome_b200_eval_host_async.argtypes = [vp, i, u32, u64, u32, i, i, C.POINTER(Buffers)]
+    lib.rome_b200_set_product_plan.argtypes = [vp, i, i, ip32, ip32, ip32]
+    lib.rome_b200_product.argtypes = [vp, i, i, C.POINTER(vp), u64, u32, i, u32, vp]
+    lib.rome_b200_reanchor.argtypes = [vp, i]
     lib.rome_b200_set_peer_proposals.argtypes = [vp, i, i, C.POINTER(vp)]
     lib.rome_b200_ipc_export.argtypes = [vp, vp, C.c_char_p]
     lib.rome_b200_ipc_import.argtypes = [vp, C.c_char_p, C.POINTER(vp)]

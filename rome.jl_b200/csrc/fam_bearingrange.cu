@@ -39,7 +39,7 @@ struct FamBearingRange {
         for (int i = 0; i < 16; ++i) st[i] = 0.f;
         // proposal heading: sin/cos(theta_p + b) = angle addition from the per-factor sin/cos(anchor heading + mu_b)
         double sA = 0.0, cA = 1.0;
-        if (flags & ROME_B200_PROPOSAL_FWD) sincos(apt + row.mu_b, &sA, &cA);
+        if (flags & (ROME_B200_PROPOSAL_FWD | ROME_B200_PROPOSAL_BWD)) sincos(apt + row.mu_b, &sA, &cA);
         // Warp-uniform fast path: every particle pair of the group has |delta| <= 0.09 |D| (screened in float32), so
         //   |u| = |cross(D,delta)| / (D.d) <= 0.099 (series) and D.d / |D|^2 in [0.91, 1.09] (Newton start) hold for all
         //   lanes and the body is straight-line code: no atan2, no sqrt, no division, no per-particle branch.
@@ -102,12 +102,24 @@ struct FamBearingRange {
             const float msk = (nn < N) ? 1.f : 0.f;
             o_res[k] = make_float2(e1, e2);
             if (want_stats) acc_res3(st, msk, e1, e2, 0.f);
-            if (flags & ROME_B200_PROPOSAL_FWD) {  // l = t_p + rho R(theta_p)(cos b, sin b) - anchor(l)
+            if (flags & (ROME_B200_PROPOSAL_FWD | ROME_B200_PROPOSAL_BWD)) {
                 double s, c;
                 sincos_anchored(apt + row.mu_b, cA, sA, dpt + (double)mb, s, c);
-                const float ox = (float)((dpx - dax) + rho * c), oy = (float)((dpy - day) + rho * s);
-                o_fwd[k] = make_float2(ox, oy);
-                if (want_stats) acc_prop2(st, msk, ox, oy);
+                if (flags & ROME_B200_PROPOSAL_FWD) {  // l = t_p + rho R(theta_p)(cos b, sin b) - anchor(l)
+                    const float ox = (float)((dpx - dax) + rho * c), oy = (float)((dpy - day) + rho * s);
+                    o_fwd[k] = make_float2(ox, oy);
+                    if (want_stats) acc_prop2(st, msk, ox, oy);
+                }
+                if (flags & ROME_B200_PROPOSAL_BWD) {
+                    // pose from landmark: the residual has a 1-parameter family of roots; the member that keeps the
+                    // particle's current heading is t_p = l - rho R(theta_p)(cos b, sin b)   (offsets from anchor(p))
+                    const float ox = (float)((dlx + dax) - rho * c), oy = (float)((dly + day) - rho * s);
+                    if (live) {
+                        float* B = P.prop_bwd + (size_t)f * 3 * Npad + 3 * n;
+                        __stcs(B, ox); __stcs(B + 1, oy); __stcs(B + 2, (float)dpt);
+                    }
+                    if (want_stats && !(flags & ROME_B200_PROPOSAL_FWD)) acc_prop2(st, msk, ox, oy);
+                }
             }
             if ((flags & ROME_B200_JACOBIAN) && live) {  // d r1/d l = (dy,-dx)/rho^2 ; d r2/d l = -d/rho
                 const double i2 = 1.0 / d2, i1 = 1.0 / rng;

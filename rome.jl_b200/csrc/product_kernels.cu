@@ -1,0 +1,329 @@
+// product_kernels.cu -- the step AFTER the convolution path: the new belief of a variable is the
+// product of the proposal densities its factors produced.  Every proposal is a kernel density estimate over its N
+// proposal particles with a per-dimension rule-of-thumb bandwidth; N samples of the product of the k KDEs are drawn
+// with a Gibbs sampler over the component labels (the restated core of ApproxManifoldProducts.manifoldProduct /
+// KernelDensityEstimate's product sampler; callers: IIF propagateBelief, test/testBearingRange2D.jl:275,296,342,
+// test/testBasicPose2Conv.jl:25-34) and written straight into the device particle store, so particles never leave
+// the GPU between sweeps.
+//
+//   one warp per variable; lane = one chain = one output particle (blocks of 32 chains).
+//   k = 2 (the usual interior pose of a chain: forward + backward proposal) is sampled EXACTLY: the marginal weights
+//       W_a = sum_b Normal(x_0a - x_1b; 0, h_0^2 + h_1^2) of the N^2-component product mixture are computed once per
+//       variable (log-sum-exp), a chain draws a from their CDF and then b | a.
+//   k > 2: the remaining proposals enter one at a time conditioned on the components already chosen, followed by
+//       `iters` Gibbs sweeps; in a sweep, for every proposal j
+//       mu_-j, var_-j  <- precision-weighted mean / variance of the other proposals' selected components
+//       l_j            <- categorical draw over i = 1..N with log-weight -1/2 sum_dim (x_ji - mu_-j)^2 / (h_j^2 + var_-j),
+//                          taken in ONE pass with the Gumbel-max trick (no normalisation, no underflow)
+//   then x ~ Normal(mu_all, var_all).  Heading dimensions (Pose2 theta) use wrapped differences.
+// Proposal rows are read through the read-only path: all lanes of a warp read the same component in the categorical
+// scan (a broadcast), the k rows of a variable (k x Npad x d floats) stay L1-resident.
+#include <cuda_runtime.h>
+
+#include "../../include/rome_b200.h"
+#include "device_utils.cuh"
+#include "tables.h"
+
+namespace rome {
+
+constexpr int kProdWarps = 4;
+
+__device__ __forceinline__ float wrap_pi_f(float a) { return a - 6.283185307179586f * rintf(a * 0.15915494309189535f); }
+__device__ __forceinline__ uint32_t xorshift32(uint32_t& s) {
+    s ^= s << 13; s ^= s >> 17; s ^= s << 5;
+    return s;
+}
+// uniform in (0,1) with 23 random bits
+__device__ __forceinline__ float u01(uint32_t& s) {
+    return __uint_as_float(0x3f800000u | (xorshift32(s) >> 9)) - (1.0f - 5.9604644775390625e-08f);
+}
+__device__ __forceinline__ float lg2f(float x) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int b = 16; b >= 1; b >>= 1) v += __shfl_xor_sync(0xffffffffu, v, b);
+    return v;
+}
+
+// D = coordinate dimension, WRAP = index of the heading coordinate or -1
+template <int D, int WRAP>
+struct ProdOps {
+    // precision-weighted fusion of the selected components of sources [0, upto) except `skip`
+    static __device__ __forceinline__ void fuse(const ProductParams& P, const float (*bw)[D], const uint16_t (*lab)[32],
+                                                int s0, int upto, int skip, int lane, int row_floats, float (&mu)[D],
+                                                float (&vr)[D]) {
+        float lam[D], s[D], ref = 0.f;
+        bool have_ref = false;
+#pragma unroll
+        for (int c = 0; c < D; ++c) { lam[c] = 0.f; s[c] = 0.f; }
+        for (int jj = 0; jj < upto; ++jj) {
+            if (jj == skip) continue;
+            const float* row = P.bufs[P.src_buf[s0 + jj]] + (size_t)P.src_row[s0 + jj] * row_floats;
+            const int l = lab[jj][lane];
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+                float x = __ldg(row + l * D + c);
+                const float w = bw[jj][c];
+                if (c == WRAP) {  // unwrap every heading towards the first one so the weighted mean is well defined
+                    if (!have_ref) { ref = x; have_ref = true; }
+                    x = ref + wrap_pi_f(x - ref);
+                }
+                lam[c] += w;
+                s[c] = fmaf(w, x, s[c]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < D; ++c) { vr[c] = 1.0f / lam[c]; mu[c] = s[c] * vr[c]; }
+    }
+    // categorical draw over the N components of source j given (mu, vr) of the others:
+    //   argmax_i  q_i + Gumbel_i,  q_i = -1/2 sum (x_ji - mu)^2 / (h_j^2 + vr)      (one pass, no normalisation)
+    static __device__ __forceinline__ int draw(const ProductParams& P, const float (*bw)[D], int s0, int j, int row_floats,
+                                               const float (&mu)[D], const float (&vr)[D], uint32_t& rng) {
+        float c2[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) c2[c] = -0.5f / (1.0f / bw[j][c] + vr[c]);
+        const float* row = P.bufs[P.src_buf[s0 + j]] + (size_t)P.src_row[s0 + j] * row_floats;
+        float best = -3.0e38f;
+        int arg = 0;
+        for (int i = 0; i < P.N; ++i) {
+            float q = 0.f;
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+                float dlt = __ldg(row + i * D + c) - mu[c];
+                if (c == WRAP) dlt = wrap_pi_f(dlt);
+                q = fmaf(c2[c] * dlt, dlt, q);
+            }
+            const float key = q - 0.6931471805599453f * lg2f(-lg2f(u01(rng)));  // + Gumbel(0,1) up to a constant
+            if (key > best) { best = key; arg = i; }
+        }
+        return arg;
+    }
+};
+
+constexpr int kProdMaxN = 1024;  // components per proposal for which the exact pair stage is used
+
+template <int D, int WRAP>
+__global__ void __launch_bounds__(kProdWarps * 32) product_kernel(const __grid_constant__ ProductParams P) {
+    __shared__ float s_bw[kProdWarps][ROME_B200_MAX_PRODUCT_SOURCES][D];       // 1 / h^2 per source and dimension
+    __shared__ uint16_t s_lab[kProdWarps][ROME_B200_MAX_PRODUCT_SOURCES][32];  // labels of the lane's chain
+    __shared__ float s_cdf[kProdWarps][kProdMaxN];                             // pair stage: CDF over source-0 components
+    using Ops = ProdOps<D, WRAP>;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int blocks = (P.Npad + 31) / 32;
+    const int row_floats = D * P.Npad;
+    const float kLog2e = 1.4426950408889634f;
+    for (int v = blockIdx.x * kProdWarps + warp; v < P.nvars; v += gridDim.x * kProdWarps) {
+        const int s0 = P.var_off[v], k = P.var_off[v + 1] - s0;
+        if (k == 0) continue;  // no proposal: the belief is left as it is
+        float* dst = reinterpret_cast<float*>(P.store + (size_t)v * var_block_bytes(D, P.Npad) + var_header_bytes(D));
+        if (k == 1) {  // product of one density: adopt its particles
+            const float* row = P.bufs[P.src_buf[s0]] + (size_t)P.src_row[s0] * row_floats;
+            for (int n = lane; n < P.Npad; n += 32) {
+#pragma unroll
+                for (int c = 0; c < D; ++c) dst[n * D + c] = n < P.N ? __ldg(row + n * D + c) : 0.f;
+            }
+            continue;
+        }
+        // ---- per-source bandwidths: h = std * bw_scale (circular statistics for the heading) ------------------
+        for (int j = 0; j < k; ++j) {
+            const float* row = P.bufs[P.src_buf[s0 + j]] + (size_t)P.src_row[s0 + j] * row_floats;
+            float mean[D];
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+                float a = 0.f, b = 0.f;
+                for (int i = lane; i < P.N; i += 32) {
+                    const float x = __ldg(row + i * D + c);
+                    if (c == WRAP) { float sn, cs; __sincosf(x, &sn, &cs); a += cs; b += sn; }
+                    else a += x;
+                }
+                a = warp_sum(a);
+                if (c == WRAP) { b = warp_sum(b); mean[c] = atan2f(b, a); }
+                else mean[c] = a / (float)P.N;
+            }
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+                float a = 0.f;
+                for (int i = lane; i < P.N; i += 32) {
+                    float dlt = __ldg(row + i * D + c) - mean[c];
+                    if (c == WRAP) dlt = wrap_pi_f(dlt);
+                    a = fmaf(dlt, dlt, a);
+                }
+                const float var = warp_sum(a) / (float)max(P.N - 1, 1);
+                const float h = fmaxf(sqrtf(var) * P.bw_scale, 1e-6f);
+                if (lane == 0) {
+                    s_bw[warp][j][c] = 1.0f / (h * h);
+                    if (P.bw_out) P.bw_out[(size_t)(s0 + j) * D + c] = h;
+                }
+            }
+        }
+        __syncwarp();
+        // ---- exact pair stage for sources 0 and 1: the product of two KDEs is a mixture of N^2 Gaussians with weights
+        //      w_ab = Normal(x_0a - x_1b; 0, h_0^2 + h_1^2); marginal W_a = sum_b w_ab -> CDF over a (shared by all
+        //      chains of the variable); a chain draws a ~ W, then b | a.  log-sum-exp keeps far-apart proposals finite.
+        const bool pair = P.N <= kProdMaxN;
+        if (pair) {
+            const float* r0 = P.bufs[P.src_buf[s0]] + (size_t)P.src_row[s0] * row_floats;
+            const float* r1 = P.bufs[P.src_buf[s0 + 1]] + (size_t)P.src_row[s0 + 1] * row_floats;
+            float c2[D];
+#pragma unroll
+            for (int c = 0; c < D; ++c) c2[c] = -0.5f * kLog2e / (1.0f / s_bw[warp][0][c] + 1.0f / s_bw[warp][1][c]);
+            float wmax = -3.0e38f;
+            for (int a = lane; a < P.N; a += 32) {
+                float xa[D];
+#pragma unroll
+                for (int c = 0; c < D; ++c) xa[c] = __ldg(r0 + a * D + c);
+                float m = -3.0e38f, sum = 0.f;
+                for (int b = 0; b < P.N; ++b) {
+                    float q = 0.f;
+#pragma unroll
+                    for (int c = 0; c < D; ++c) {
+                        float dlt = __ldg(r1 + b * D + c) - xa[c];
+                        if (c == WRAP) dlt = wrap_pi_f(dlt);
+                        q = fmaf(c2[c] * dlt, dlt, q);
+                    }
+                    const float m2 = fmaxf(m, q);
+                    sum = fmaf(sum, exp2f(m - m2), exp2f(q - m2));
+                    m = m2;
+                }
+                const float lw = m + lg2f(sum);  // log2 W_a
+                s_cdf[warp][a] = lw;
+                wmax = fmaxf(wmax, lw);
+            }
+#pragma unroll
+            for (int b = 16; b >= 1; b >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, b));
+            __syncwarp();
+            // inclusive prefix sum of 2^(lw - wmax) over a (warp scan per chunk of 32 with a running carry)
+            float carry = 0.f;
+            for (int base = 0; base < P.N; base += 32) {
+                const int a = base + lane;
+                float x = a < P.N ? exp2f(s_cdf[warp][a] - wmax) : 0.f;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const float y = __shfl_up_sync(0xffffffffu, x, o);
+                    if (lane >= o) x += y;
+                }
+                x += carry;
+                if (a < P.N) s_cdf[warp][a] = x;
+                carry = __shfl_sync(0xffffffffu, x, 31);
+            }
+            __syncwarp();
+        }
+        // ---- chains: lane = chain n of the current block of 32 ------------------------------------------------------
+        for (int blk = 0; blk < blocks; ++blk) {
+            const int n = blk * 32 + lane;
+            uint32_t rng;
+            {
+                const uint4 x = philox4x32_10(make_uint4((uint32_t)n, (uint32_t)v, P.stream_id, 0x50524f44u), P.seed_lo, P.seed_hi);
+                rng = x.x | 1u;
+            }
+            float mu[D], vr[D];
+            if (pair) {
+                const float target = u01(rng) * s_cdf[warp][P.N - 1];
+                int lo = 0, hi = P.N - 1;  // first a with cdf[a] >= target
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (s_cdf[warp][mid] < target) lo = mid + 1; else hi = mid;
+                }
+                s_lab[warp][0][lane] = (uint16_t)lo;
+                Ops::fuse(P, s_bw[warp], s_lab[warp], s0, 1, -1, lane, row_floats, mu, vr);
+                s_lab[warp][1][lane] = (uint16_t)Ops::draw(P, s_bw[warp], s0, 1, row_floats, mu, vr, rng);
+            } else {
+                s_lab[warp][0][lane] = (uint16_t)(xorshift32(rng) % (uint32_t)P.N);
+                s_lab[warp][1][lane] = (uint16_t)(xorshift32(rng) % (uint32_t)P.N);
+            }
+            if (k > 2 || !pair) {
+                // further sources enter one at a time conditioned on the ones already chosen, then Gibbs sweeps over all
+                for (int j = 2; j < k; ++j) {
+                    Ops::fuse(P, s_bw[warp], s_lab[warp], s0, j, -1, lane, row_floats, mu, vr);
+                    s_lab[warp][j][lane] = (uint16_t)Ops::draw(P, s_bw[warp], s0, j, row_floats, mu, vr, rng);
+                }
+                for (int t = 0; t < P.iters; ++t)
+                    for (int j = 0; j < k; ++j) {
+                        Ops::fuse(P, s_bw[warp], s_lab[warp], s0, k, j, lane, row_floats, mu, vr);
+                        s_lab[warp][j][lane] = (uint16_t)Ops::draw(P, s_bw[warp], s0, j, row_floats, mu, vr, rng);
+                    }
+            }
+            // the sample: Normal(fused mean, fused variance) of the chosen components
+            Ops::fuse(P, s_bw[warp], s_lab[warp], s0, k, -1, lane, row_floats, mu, vr);
+            float z[8];
+            const uint4 a = philox4x32_10(make_uint4((uint32_t)n, (uint32_t)v, P.stream_id, 0x50524f45u), P.seed_lo, P.seed_hi);
+            box_muller(a.x, a.y, z[0], z[1]); box_muller(a.z, a.w, z[2], z[3]);
+            if (D > 4) {
+                const uint4 b = philox4x32_10(make_uint4((uint32_t)n, (uint32_t)v, P.stream_id, 0x50524f46u), P.seed_lo, P.seed_hi);
+                box_muller(b.x, b.y, z[4], z[5]); box_muller(b.z, b.w, z[6], z[7]);
+            }
+            if (n < P.Npad) {
+#pragma unroll
+                for (int c = 0; c < D; ++c) {
+                    float x = fmaf(sqrtf(vr[c]), z[c], mu[c]);
+                    if (c == WRAP) x = wrap_pi_f(x);
+                    dst[n * D + c] = n < P.N ? x : 0.f;
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// move every variable's anchor onto its first particle (offsets stay small after the belief has moved)
+template <int D, int WRAP>
+__global__ void reanchor_kernel(unsigned char* store, int nvars, int N, int Npad) {
+    const int v = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (v >= nvars) return;
+    unsigned char* blk = store + (size_t)v * var_block_bytes(D, Npad);
+    double* hdr = reinterpret_cast<double*>(blk);
+    float* off = reinterpret_cast<float*>(blk + var_header_bytes(D));
+    float o0[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) o0[c] = off[c];
+    __syncwarp();
+    for (int n = lane; n < N; n += 32) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            float x = off[n * D + c] - o0[c];
+            if (c == WRAP) x = wrap_pi_f(x);
+            off[n * D + c] = x;
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            double a = hdr[c] + (double)o0[c];
+            if (c == WRAP) a = wrap_pi(a);
+            hdr[c] = a;
+        }
+        if (WRAP >= 0) { hdr[D] = cos(hdr[WRAP]); hdr[D + 1] = sin(hdr[WRAP]); }
+    }
+}
+
+int launch_product(int d, int wrap_dim, const void* params, int num_sms, void* stream) {
+    const ProductParams& p = *static_cast<const ProductParams*>(params);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (p.nvars == 0) return 0;
+    int grid = (p.nvars + kProdWarps - 1) / kProdWarps;
+    const int cap = num_sms * 16;
+    if (grid > cap) grid = cap;
+    if (d == 3 && wrap_dim == 2) product_kernel<3, 2><<<grid, kProdWarps * 32, 0, s>>>(p);
+    else if (d == 3) product_kernel<3, -1><<<grid, kProdWarps * 32, 0, s>>>(p);
+    else if (d == 2) product_kernel<2, -1><<<grid, kProdWarps * 32, 0, s>>>(p);
+    else if (d == 6) product_kernel<6, -1><<<grid, kProdWarps * 32, 0, s>>>(p);
+    else return (int)cudaErrorInvalidValue;
+    return (int)cudaGetLastError();
+}
+int launch_reanchor(int d, int wrap_dim, unsigned char* store, int nvars, int N, int Npad, void* stream) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (nvars == 0) return 0;
+    const int grid = (nvars + 7) / 8;
+    if (d == 3 && wrap_dim == 2) reanchor_kernel<3, 2><<<grid, 256, 0, s>>>(store, nvars, N, Npad);
+    else if (d == 3) reanchor_kernel<3, -1><<<grid, 256, 0, s>>>(store, nvars, N, Npad);
+    else if (d == 2) reanchor_kernel<2, -1><<<grid, 256, 0, s>>>(store, nvars, N, Npad);
+    else if (d == 6) reanchor_kernel<6, -1><<<grid, 256, 0, s>>>(store, nvars, N, Npad);
+    else return (int)cudaErrorInvalidValue;
+    return (int)cudaGetLastError();
+}
+size_t product_params_size() { return sizeof(ProductParams); }
+
+}  // namespace rome

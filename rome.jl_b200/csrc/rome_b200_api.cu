@@ -31,6 +31,10 @@ struct Scratch {
     void* p = nullptr;
     size_t cap = 0;
 };
+struct ProductPlan {
+    int nvars = 0, nsrc = 0, max_buf = -1;
+    Scratch off, buf, row;  // device copies of the CSR arrays
+};
 
 const int kVarDim[ROME_B200_NVARTYPES] = {3, 2, 6, 3};
 const int kWrapDim[ROME_B200_NVARTYPES] = {2, -1, -1, -1};
@@ -41,7 +45,7 @@ struct FamInfo {
 const FamInfo kFam[ROME_B200_NFAMILIES] = {
     {ROME_B200_POSE2, ROME_B200_POSE2, 3, 3, 16, 4, (int)sizeof(RowSE2), 3, 3},
     {ROME_B200_POSE2, -1, 3, 3, 16, 0, (int)sizeof(RowSE2), 3, 0},
-    {ROME_B200_POSE2, ROME_B200_POINT2, 2, 2, 16, 4, (int)sizeof(RowBR), 2, 0},
+    {ROME_B200_POSE2, ROME_B200_POINT2, 2, 2, 16, 4, (int)sizeof(RowBR), 2, 3},
     {ROME_B200_POSE3, ROME_B200_POSE3, 6, 6, 32, 0, (int)sizeof(RowSE3), 6, 6},
     {ROME_B200_POSE3, -1, 6, 6, 32, 0, (int)sizeof(RowSE3), 6, 0},
     {ROME_B200_POINT2, -1, 2, 2, 16, 0, (int)sizeof(RowPT2), 2, 0},                // PriorPoint2
@@ -71,6 +75,7 @@ struct rome_b200_ctx {
     int smem_per_sm = 0, smem_per_cta_max = 0;
     Scratch stage_dev, stage_host;            // particle upload/download staging
     Scratch out_dev[ROME_B200_NFAMILIES][8];  // eval_host device mirrors per family: meas, meas_out, res, fwd, bwd, stats, jac
+    ProductPlan plan[ROME_B200_NVARTYPES];
     int n_peers[ROME_B200_NFAMILIES] = {};
     float* peers[ROME_B200_NFAMILIES][7] = {};
     std::vector<cudaGraphExec_t> graphs;
@@ -238,6 +243,7 @@ int rome_b200_destroy(rome_b200_ctx* ctx) {
     cudaFree(ctx->stage_dev.p);
     cudaFreeHost(ctx->stage_host.p);
     for (auto& f : ctx->out_dev) for (auto& s : f) cudaFree(s.p);
+    for (auto& pl : ctx->plan) { cudaFree(pl.off.p); cudaFree(pl.buf.p); cudaFree(pl.row.p); }
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return ROME_B200_OK;
@@ -583,6 +589,87 @@ int rome_b200_eval_host(rome_b200_ctx* ctx, int family, uint32_t flags, uint64_t
 int rome_b200_eval_host_async(rome_b200_ctx* ctx, int family, uint32_t flags, uint64_t seed, uint32_t stream_id,
                               int first, int count, const rome_b200_buffers* hb) {
     return eval_host_impl(ctx, family, flags, seed, stream_id, first, count, hb, false);
+}
+
+// ---------------------------------------------------------------------------------------------
+int rome_b200_set_product_plan(rome_b200_ctx* ctx, int vartype, int nvars, const int32_t* var_offsets,
+                               const int32_t* src_buf, const int32_t* src_row) {
+    if (!ctx) return ROME_B200_BAD_ARG;
+    if (vartype < 0 || vartype >= ROME_B200_NVARTYPES) return fail(ctx, ROME_B200_BAD_ARG, "bad vartype");
+    if (nvars < 0 || (nvars > 0 && !var_offsets)) return fail(ctx, ROME_B200_BAD_ARG, "bad plan arrays");
+    if (ctx->capturing) return fail(ctx, ROME_B200_BAD_ARG, "set_product_plan during graph capture");
+    const int nsrc = nvars ? var_offsets[nvars] : 0;
+    if (nvars && (var_offsets[0] != 0 || nsrc < 0 || (nsrc > 0 && (!src_buf || !src_row))))
+        return fail(ctx, ROME_B200_BAD_ARG, "bad plan arrays");
+    int max_buf = -1;
+    for (int v = 0; v < nvars; ++v) {
+        const int k = var_offsets[v + 1] - var_offsets[v];
+        if (k < 0) return fail(ctx, ROME_B200_BAD_ARG, "var_offsets must be non-decreasing");
+        if (k > ROME_B200_MAX_PRODUCT_SOURCES) return fail(ctx, ROME_B200_BAD_ARG, "too many proposals for one variable");
+    }
+    for (int i = 0; i < nsrc; ++i) {
+        if (src_buf[i] < 0 || src_buf[i] >= ROME_B200_MAX_PRODUCT_BUFFERS || src_row[i] < 0)
+            return fail(ctx, ROME_B200_BAD_ARG, "source buffer index / row out of range");
+        if (src_buf[i] > max_buf) max_buf = src_buf[i];
+    }
+    if (int e = bind(ctx)) return e;
+    ProductPlan& pl = ctx->plan[vartype];
+    if (int e = grow_dev(ctx, pl.off, (size_t)(nvars + 1) * 4)) return e;
+    if (int e = grow_dev(ctx, pl.buf, (size_t)(nsrc ? nsrc : 1) * 4)) return e;
+    if (int e = grow_dev(ctx, pl.row, (size_t)(nsrc ? nsrc : 1) * 4)) return e;
+    if (nvars) CK(cudaMemcpyAsync(pl.off.p, var_offsets, (size_t)(nvars + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (nsrc) {
+        CK(cudaMemcpyAsync(pl.buf.p, src_buf, (size_t)nsrc * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(pl.row.p, src_row, (size_t)nsrc * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));  // the caller's arrays may be temporaries
+    pl.nvars = nvars; pl.nsrc = nsrc; pl.max_buf = max_buf;
+    return ROME_B200_OK;
+}
+
+int rome_b200_product(rome_b200_ctx* ctx, int vartype, int n_bufs, const float* const* d_prop_bufs, uint64_t seed,
+                      uint32_t stream_id, int gibbs_iters, uint32_t flags, float* d_bw_out) {
+    if (!ctx) return ROME_B200_BAD_ARG;
+    if (vartype < 0 || vartype >= ROME_B200_NVARTYPES) return fail(ctx, ROME_B200_BAD_ARG, "bad vartype");
+    const ProductPlan& pl = ctx->plan[vartype];
+    VarStore& vs = ctx->vars[vartype];
+    if (vs.nvars == 0) return fail(ctx, ROME_B200_NOT_SET, "particles of this variable type are not set");
+    if (pl.nvars != vs.nvars) return fail(ctx, ROME_B200_NOT_SET, "no product plan for this variable type (or its size differs)");
+    if (n_bufs < 0 || n_bufs > ROME_B200_MAX_PRODUCT_BUFFERS || pl.max_buf >= n_bufs || (n_bufs > 0 && !d_prop_bufs))
+        return fail(ctx, ROME_B200_BAD_ARG, "the plan refers to more proposal buffers than were passed");
+    for (int b = 0; b <= pl.max_buf; ++b)
+        if (!d_prop_bufs[b]) return fail(ctx, ROME_B200_BAD_ARG, "proposal buffer is NULL");
+    if (int e = bind(ctx)) return e;
+    const int d = kVarDim[vartype];
+    ProductParams p;
+    std::memset(&p, 0, sizeof p);
+    p.store = vs.store;
+    p.var_off = static_cast<const int32_t*>(pl.off.p);
+    p.src_buf = static_cast<const int32_t*>(pl.buf.p);
+    p.src_row = static_cast<const int32_t*>(pl.row.p);
+    for (int b = 0; b < n_bufs; ++b) p.bufs[b] = d_prop_bufs[b];
+    p.bw_out = d_bw_out;
+    p.nvars = vs.nvars; p.N = vs.N; p.Npad = vs.Npad;
+    p.iters = gibbs_iters > 0 ? gibbs_iters : 3;
+    p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32); p.stream_id = stream_id;
+    p.bw_scale = (float)std::pow(4.0 / ((d + 2.0) * vs.N), 1.0 / (d + 4.0));
+    int e = launch_product(d, kWrapDim[vartype], &p, ctx->num_sms, ctx->stream);
+    if (e) return cuda_fail(ctx, (cudaError_t)e, "product kernel launch");
+    if (ctx->capturing) ctx->capture_kernels++; else ctx->launches++;
+    if (flags & ROME_B200_PRODUCT_REANCHOR) return rome_b200_reanchor(ctx, vartype);
+    return ROME_B200_OK;
+}
+
+int rome_b200_reanchor(rome_b200_ctx* ctx, int vartype) {
+    if (!ctx) return ROME_B200_BAD_ARG;
+    if (vartype < 0 || vartype >= ROME_B200_NVARTYPES) return fail(ctx, ROME_B200_BAD_ARG, "bad vartype");
+    VarStore& vs = ctx->vars[vartype];
+    if (vs.nvars == 0) return fail(ctx, ROME_B200_NOT_SET, "particles of this variable type are not set");
+    if (int e = bind(ctx)) return e;
+    int e = launch_reanchor(kVarDim[vartype], kWrapDim[vartype], vs.store, vs.nvars, vs.N, vs.Npad, ctx->stream);
+    if (e) return cuda_fail(ctx, (cudaError_t)e, "reanchor kernel launch");
+    if (ctx->capturing) ctx->capture_kernels++; else ctx->launches++;
+    return ROME_B200_OK;
 }
 
 // ---------------------------------------------------------------------------------------------

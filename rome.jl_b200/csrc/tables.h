@@ -6,6 +6,8 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include "../../include/rome_b200.h"
+
 namespace rome {
 
 // Pose2Pose2 / PriorPose2: MvNormal(mu, Sigma) -> mu (Float64) + lower Cholesky factor (float32).
@@ -83,6 +85,18 @@ struct EvalParams {
     float* peer_fwd[7];
 };
 
+struct ProductParams {
+    unsigned char* store;        // particle store of the variable type (updated in place)
+    const int32_t* var_off;      // [nvars + 1] CSR offsets into the source arrays
+    const int32_t* src_buf;      // [nsrc] index into bufs[]
+    const int32_t* src_row;      // [nsrc] proposal row (factor index) inside that buffer
+    const float* bufs[ROME_B200_MAX_PRODUCT_BUFFERS];
+    float* bw_out;               // optional [nsrc][D] bandwidths (diagnostics), may be null
+    int nvars, N, Npad, iters;
+    uint32_t seed_lo, seed_hi, stream_id;
+    float bw_scale;              // rule-of-thumb factor (4 / ((d + 2) N))^(1 / (d + 4))
+};
+
 // launch geometry chosen on the host for (family, sample, Npad)
 struct LaunchPlan {
     int ft;           // factors per tile == consumer warps per CTA (8, 2 or 1)
@@ -101,5 +115,7 @@ int launch_pack(int d, int wrap_dim, int nvars, int N, int Npad, const double* c
 int launch_unpack(int d, int wrap_dim, int nvars, int N, int Npad, const unsigned char* store, double* coords,
                   void* stream);
 int launch_adopt(int d, int Npad, unsigned char* store, int var, const float* prop, int factor, void* stream);
+int launch_product(int d, int wrap_dim, const void* params, int num_sms, void* stream);
+int launch_reanchor(int d, int wrap_dim, unsigned char* store, int nvars, int N, int Npad, void* stream);
 
 }  // namespace rome

@@ -20,7 +20,7 @@ VAR_DIM = {POSE2: 3, POINT2: 2, POSE3: 6, POINT3: 3}
 FAMILY = {
     POSE2POSE2: (POSE2, POSE2, 3, 3, 16, 4, 3, 3),
     PRIORPOSE2: (POSE2, None, 3, 3, 16, 0, 3, 0),
-    BEARINGRANGE: (POSE2, POINT2, 2, 2, 16, 4, 2, 0),
+    BEARINGRANGE: (POSE2, POINT2, 2, 2, 16, 4, 2, 3),
     POSE3POSE3: (POSE3, POSE3, 6, 6, 32, 0, 6, 6),
     PRIORPOSE3: (POSE3, None, 6, 6, 32, 0, 6, 0),
     # next-row families
@@ -263,6 +263,22 @@ class Context:
             out["jac"] = np.zeros((nF, Np, dj), np.float32)
         return out
 
+    # -- belief update: product of proposal densities -----------------------------
+    def set_product_plan(self, vartype: int, var_offsets, src_buf, src_row):
+        """CSR plan: variable v multiplies sources [var_offsets[v], var_offsets[v+1]); source = (buffer index, row)"""
+        off, sb, sr = _i32(var_offsets), _i32(src_buf), _i32(src_row)
+        self._ck(self._lib.rome_b200_set_product_plan(self._h, vartype, len(off) - 1, self._ip(off), self._ip(sb),
+                                                      self._ip(sr)))
+
+    def product(self, vartype: int, bufs, *, seed=0, stream_id=0, gibbs_iters=0, reanchor=True, bw_out=None):
+        """bufs: device pointers / CUDA tensors of the proposal buffers the plan indexes; updates the particle store"""
+        arr = (C.c_void_p * max(1, len(bufs)))(*[_ptr(b) for b in bufs])
+        self._ck(self._lib.rome_b200_product(self._h, vartype, len(bufs), arr, seed, stream_id, gibbs_iters,
+                                             L.PRODUCT_REANCHOR if reanchor else 0, _ptr(bw_out)))
+
+    def reanchor(self, vartype: int):
+        self._ck(self._lib.rome_b200_reanchor(self._h, vartype))
+
     # -- multi-GPU: fused all-gather of forward proposals ---------------------------------------
     def set_peer_proposals(self, family: int, peer_ptrs):
         """peer_ptrs: device pointers (ints) to the peers' identically shaped prop_fwd buffers; [] clears"""
@@ -286,6 +302,10 @@ class Context:
         p = C.c_void_p()
         self._ck(self._lib.rome_b200_ipc_import(self._h, handle, C.byref(p)))
         return p.value
+
+    def memcpy_h2d(self, dst_ptr: int, src: np.ndarray):
+        src = np.ascontiguousarray(src)
+        self._ck(self._lib.rome_b200_memcpy_h2d(self._h, dst_ptr, src.ctypes.data, src.nbytes))
 
     def memcpy_d2h(self, dst: np.ndarray, src_ptr: int):
         self._ck(self._lib.rome_b200_memcpy_d2h(self._h, dst.ctypes.data, src_ptr, dst.nbytes))

@@ -1,0 +1,144 @@
+"""The step after the path: product of proposal KDEs on the device and device-resident sweeps.
+The product sampler is stochastic (and the reference's lives in absent packages), so the checks are statistical:
+analytic Gaussian products, circular headings, multi-modal selection against the NumPy twin of the same algorithm, and
+the reference's own acceptance boxes for the Hexagonal graph (test/testHexagonal2D_CliqByCliq.jl:37-79)."""
+import numpy as np
+import pytest
+
+import rome_b200 as rb
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = rb.Context(0)
+    yield c
+    c.close()
+
+
+def _run_product(ctx, vartype, particles, rows, off, sb, sr, seed=1, iters=3, reanchor=False):
+    """rows: [nrows][N][d] Float64 proposal offsets (from the target's anchor); returns new particles [nvars][N][d]"""
+    nv, N, d = particles.shape
+    Np = rb.npad(N)
+    ctx.set_particles(vartype, particles)
+    buf = np.zeros((len(rows), Np, d), np.float32)
+    buf[:, :N] = rows
+    ptr = ctx.malloc_device(buf.nbytes)
+    ctx.memcpy_h2d(ptr, buf)
+    ctx.set_product_plan(vartype, off, sb, sr)
+    bw = ctx.malloc_device(max(1, len(sb)) * d * 4)
+    ctx.product(vartype, [ptr], seed=seed, gibbs_iters=iters, reanchor=reanchor, bw_out=bw)
+    out = ctx.get_particles(vartype)
+    h = np.zeros((max(1, len(sb)), d), np.float32)
+    ctx.memcpy_d2h(h, bw)
+    ctx.free_device(ptr); ctx.free_device(bw)
+    return out, h
+
+
+def test_product_of_gaussians_point2(ctx):
+    rng = np.random.default_rng(0)
+    N, nv = 200, 40
+    m1, m2, s1, s2 = np.array([1.0, -0.5]), np.array([-0.4, 0.7]), 0.5, 0.8
+    parts = np.zeros((nv + 2, N, 2))  # anchors at 0: proposal offsets are absolute coordinates
+    parts[nv] = 5.0 + rng.normal(size=(N, 2))      # one source -> adopted
+    parts[nv + 1] = -3.0 + rng.normal(size=(N, 2))  # no source -> unchanged
+    parts[nv, 0] = 0.0                              # anchor (= first particle) at the origin
+    rows = np.concatenate([m1 + s1 * rng.normal(size=(nv, N, 2)), m2 + s2 * rng.normal(size=(nv, N, 2)),
+                           7.0 + rng.normal(size=(1, N, 2))])
+    off = np.concatenate([2 * np.arange(nv + 1), [2 * nv + 1, 2 * nv + 1]]).astype(np.int32)
+    sb = np.zeros(2 * nv + 1, np.int32)
+    sr = np.concatenate([np.stack([np.arange(nv), nv + np.arange(nv)], 1).reshape(-1), [2 * nv]]).astype(np.int32)
+    before = parts.copy()
+    out, h = _run_product(ctx, rb.POINT2, parts, rows, off, sb, sr)
+    # bandwidths: rule of thumb from each proposal's own spread
+    scale = (4.0 / (4.0 * N)) ** (1.0 / 6.0)
+    assert np.allclose(h[0], rows[0].std(0, ddof=1) * scale, rtol=1e-3)
+    assert np.allclose(h[1], rows[nv].std(0, ddof=1) * scale, rtol=1e-3)
+    v1, v2 = s1 ** 2 * (1 + scale ** 2), s2 ** 2 * (1 + scale ** 2)
+    mean = (m1 / v1 + m2 / v2) / (1 / v1 + 1 / v2)
+    var = 1.0 / (1 / v1 + 1 / v2)
+    got = out[:nv].reshape(-1, 2)
+    assert np.allclose(got.mean(0), mean, atol=0.03), (got.mean(0), mean)
+    assert np.allclose(got.var(0), var, rtol=0.1), (got.var(0), var)
+    # per-variable means scatter like the finite-sample product does, not more
+    assert np.abs(out[:nv].mean(1) - mean).max() < 0.45
+    assert np.allclose(out[nv], rows[2 * nv], atol=1e-6)          # single proposal adopted
+    assert np.allclose(out[nv + 1], before[nv + 1], atol=1e-5)    # no proposal: untouched
+
+
+def test_product_heading_wraps(ctx):
+    """Pose2 headings straddling the +-pi cut relative to the anchor: the circular mean must come out near pi"""
+    rng = np.random.default_rng(1)
+    N, nv = 128, 16
+    parts = np.zeros((nv, N, 3))
+    a = np.concatenate([np.pi - 0.05 + 0.1 * rng.normal(size=(nv, N, 1))], 2)
+    b = np.concatenate([-np.pi + 0.08 + 0.1 * rng.normal(size=(nv, N, 1))], 2)
+    xy1, xy2 = 0.3 * rng.normal(size=(nv, N, 2)) + 1.0, 0.3 * rng.normal(size=(nv, N, 2)) + 1.2
+    rows = np.concatenate([np.concatenate([xy1, O.np_wrap(a)], 2), np.concatenate([xy2, O.np_wrap(b)], 2)])
+    off = (2 * np.arange(nv + 1)).astype(np.int32)
+    sr = np.stack([np.arange(nv), nv + np.arange(nv)], 1).reshape(-1).astype(np.int32)
+    out, h = _run_product(ctx, rb.POSE2, parts, rows, off, np.zeros(2 * nv, np.int32), sr)
+    th = out[..., 2].reshape(-1)
+    circ = np.arctan2(np.sin(th).mean(), np.cos(th).mean())
+    assert abs(O.np_wrap(circ - (np.pi + 0.015))) < 0.03, circ
+    assert np.abs(O.np_wrap(th - np.pi)).max() < 0.6        # nothing lands on the far side of the circle
+    assert np.allclose(out[..., :2].reshape(-1, 2).mean(0), [1.1, 1.1], atol=0.05)
+    assert h[:, 2].max() < 0.1                               # circular spread, not the +-pi jump
+
+
+def test_product_multimodal_matches_numpy_twin(ctx):
+    """a bimodal proposal times a unimodal one keeps the shared mode; same behaviour as the NumPy twin"""
+    rng = np.random.default_rng(2)
+    N, nv = 100, 24
+    bim = np.where(rng.random((nv, N, 1)) < 0.5, -2.0, 2.0) + 0.3 * rng.normal(size=(nv, N, 2))
+    uni = np.array([1.8, 1.9]) + 0.4 * rng.normal(size=(nv, N, 2))
+    rows = np.concatenate([bim, uni])
+    off = (2 * np.arange(nv + 1)).astype(np.int32)
+    sr = np.stack([np.arange(nv), nv + np.arange(nv)], 1).reshape(-1).astype(np.int32)
+    out, _ = _run_product(ctx, rb.POINT2, np.zeros((nv, N, 2)), rows, off, np.zeros(2 * nv, np.int32), sr)
+    twin = np.stack([O.product_gibbs([bim[v], uni[v]], N, iters=3, seed=v) for v in range(4)])
+    frac_gpu = (out[..., 0] > 0).mean()
+    frac_twin = (twin[..., 0] > 0).mean()
+    assert frac_gpu > 0.97 and frac_twin > 0.97, (frac_gpu, frac_twin)
+    g, t = out.reshape(-1, 2), twin.reshape(-1, 2)
+    assert np.allclose(g.mean(0), t.mean(0), atol=0.06), (g.mean(0), t.mean(0))
+    assert np.allclose(g.std(0), t.std(0), rtol=0.2), (g.std(0), t.std(0))
+
+
+def test_plan_errors(ctx):
+    ctx.set_particles(rb.POINT2, np.zeros((2, 16, 2)))
+    with pytest.raises(rb.RomeB200Error):  # more sources than ROME_B200_MAX_PRODUCT_SOURCES
+        ctx.set_product_plan(rb.POINT2, [0, 40, 40], np.zeros(40, np.int32), np.zeros(40, np.int32))
+    ctx.set_product_plan(rb.POINT2, [0, 1, 2], [0, 3], [0, 0])
+    p = ctx.malloc_device(4096)
+    with pytest.raises(rb.RomeB200Error):  # the plan indexes buffer 3, only one is passed
+        ctx.product(rb.POINT2, [p])
+    ctx.free_device(p)
+
+
+def test_hexagonal_solve_reference_boxes(ctx):
+    """generateGraph_Hexagonal + device-resident sweeps: the acceptance boxes of the reference's own solve test
+    (test/testHexagonal2D_CliqByCliq.jl:37-79: more than 35 of 100 particles inside each box)"""
+    fg = rb.generateGraph_Hexagonal()
+    rb.initAll(fg, seed=3, ctx=ctx)
+    rb.solveGraphGibbs(fg, sweeps=3, seed=5, ctx=ctx)
+    boxes = {
+        "x0": [(-3, 3), (-3, 3), (-0.3, 0.3)], "x1": [(7, 13), (-3, 3), (0.7, 1.3)],
+        "x2": [(12, 18), (6, 11), (1.8, 2.4)], "x4": [(-5, 5), (13, 22), (-2.8, -1.5)],
+        "x5": [(-8, -2), (6, 11), (-1.3, -0.7)], "x6": [(-3, 3), (-3, 3), (-0.3, 0.3)],
+        "l1": [(17, 23), (-5, 5)],
+    }
+    for label, bx in boxes.items():
+        v = rb.getVal(fg, label)
+        assert v.shape[0] == 100
+        for c, (lo, hi) in enumerate(bx):
+            x = O.np_wrap(v[:, c]) if c == 2 else v[:, c]
+            assert ((x > lo) & (x < hi)).sum() > 35, (label, c, x.mean())
+    v3 = rb.getVal(fg, "x3")  # :59-64: mean near (11, 17.5), heading near pi, bounded covariance
+    assert np.allclose(v3[:, :2].mean(0), [11, 17.5], atol=3.0)
+    assert abs(O.np_wrap(np.arctan2(np.sin(v3[:, 2]).mean(), np.cos(v3[:, 2]).mean()) - np.pi)) < 0.5
+    assert np.all(v3[:, :2].var(0) < 25)
+    # the loop closure through :l1 ties :x6 back to :x0
+    assert np.linalg.norm(rb.getVal(fg, "x6")[:, :2].mean(0)) < 1.5

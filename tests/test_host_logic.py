@@ -183,3 +183,22 @@ def test_layout_helpers():
     back = rb.offsets_to_meas(off, mu, 100)
     assert np.abs(back - meas).max() < 1e-6
     assert rb.rows_to_particle_major(off, 100).shape == (5, 100, 3)
+
+
+def test_product_plan_from_graph():
+    """host logic of the device-resident sweep: which proposal rows feed which variable"""
+    fg = rb.generateGraph_Hexagonal()
+    plans, buffers = rb.build_product_plans(fg)
+    fams = sorted({f for f, _ in buffers})
+    assert fams == [rb.POSE2POSE2, rb.PRIORPOSE2, rb.BEARINGRANGE]
+    off, sb, sr = plans[rb.POSE2]
+    assert len(off) == 8 and off[-1] == len(sb) == len(sr)
+    k = {f: i for i, f in enumerate(fams)}
+    # :x0 = prior (fwd) + bwd of x0x1f1 + bwd of the bearing-range sighting from x0
+    src0 = sorted(zip(sb[off[0]:off[1]], sr[off[0]:off[1]]))
+    assert src0 == sorted([(2 * k[rb.PRIORPOSE2], 0), (2 * k[rb.POSE2POSE2] + 1, 0), (2 * k[rb.BEARINGRANGE] + 1, 0)])
+    # :x3 = fwd of x2x3f1 + bwd of x3x4f1
+    src3 = sorted(zip(sb[off[3]:off[4]], sr[off[3]:off[4]]))
+    assert src3 == sorted([(2 * k[rb.POSE2POSE2], 2), (2 * k[rb.POSE2POSE2] + 1, 3)])
+    offl, sbl, srl = plans[rb.POINT2]  # :l1 = fwd of both sightings
+    assert list(offl) == [0, 2] and sorted(srl) == [0, 1] and set(sbl) == {2 * k[rb.BEARINGRANGE]}
