@@ -218,7 +218,7 @@ ROME_B200_API int rome_b200_eval_host_async(rome_b200_ctx* ctx, int family, uint
 #define ROME_B200_PRODUCT_REANCHOR 1u    /* afterwards move every anchor onto the variable's new first particle */
 ROME_B200_API int rome_b200_set_product_plan(rome_b200_ctx* ctx, int vartype, int nvars, const int32_t* var_offsets,
                                              const int32_t* src_buf, const int32_t* src_row);
-/* gibbs_iters <= 0 selects the default (3).  d_bw_out: optional device [nsrc][d] bandwidths (diagnostics). */
+/* gibbs_iters <= 0 selects the default (2; only variables with more than two proposals iterate).  d_bw_out: optional device [nsrc][d] bandwidths (diagnostics). */
 ROME_B200_API int rome_b200_product(rome_b200_ctx* ctx, int vartype, int n_bufs, const float* const* d_prop_bufs,
                                     uint64_t seed, uint32_t stream_id, int gibbs_iters, uint32_t flags, float* d_bw_out);
 ROME_B200_API int rome_b200_reanchor(rome_b200_ctx* ctx, int vartype);

@@ -6,7 +6,7 @@
 // test/testBasicPose2Conv.jl:25-34) and written straight into the device particle store, so particles never leave
 // the GPU between sweeps.
 //
-//   one warp per variable; lane = one chain = one output particle (blocks of 32 chains).
+//   one CTA per variable; lane = one chain = one output particle; the CTA's warps split the blocks of 32 chains.
 //   k = 2 (the usual interior pose of a chain: forward + backward proposal) is sampled EXACTLY: the marginal weights
 //       W_a = sum_b Normal(x_0a - x_1b; 0, h_0^2 + h_1^2) of the N^2-component product mixture are computed once per
 //       variable (log-sum-exp), a chain draws a from their CDF and then b | a.
@@ -107,28 +107,30 @@ constexpr int kProdMaxN = 1024;  // components per proposal for which the exact 
 
 template <int D, int WRAP>
 __global__ void __launch_bounds__(kProdWarps * 32) product_kernel(const __grid_constant__ ProductParams P) {
-    __shared__ float s_bw[kProdWarps][ROME_B200_MAX_PRODUCT_SOURCES][D];       // 1 / h^2 per source and dimension
+    // one CTA per variable (grid-stride); its warps share the bandwidths and the pair-stage CDF and split the chains
+    __shared__ float s_bw[ROME_B200_MAX_PRODUCT_SOURCES][D];                   // 1 / h^2 per source and dimension
     __shared__ uint16_t s_lab[kProdWarps][ROME_B200_MAX_PRODUCT_SOURCES][32];  // labels of the lane's chain
-    __shared__ float s_cdf[kProdWarps][kProdMaxN];                             // pair stage: CDF over source-0 components
+    __shared__ float s_cdf[kProdMaxN];                                         // pair stage: CDF over source-0 components
     using Ops = ProdOps<D, WRAP>;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int blocks = (P.Npad + 31) / 32;
     const int row_floats = D * P.Npad;
     const float kLog2e = 1.4426950408889634f;
-    for (int v = blockIdx.x * kProdWarps + warp; v < P.nvars; v += gridDim.x * kProdWarps) {
+    for (int v = blockIdx.x; v < P.nvars; v += gridDim.x) {
         const int s0 = P.var_off[v], k = P.var_off[v + 1] - s0;
         if (k == 0) continue;  // no proposal: the belief is left as it is
         float* dst = reinterpret_cast<float*>(P.store + (size_t)v * var_block_bytes(D, P.Npad) + var_header_bytes(D));
         if (k == 1) {  // product of one density: adopt its particles
             const float* row = P.bufs[P.src_buf[s0]] + (size_t)P.src_row[s0] * row_floats;
-            for (int n = lane; n < P.Npad; n += 32) {
+            for (int n = threadIdx.x; n < P.Npad; n += blockDim.x) {
 #pragma unroll
                 for (int c = 0; c < D; ++c) dst[n * D + c] = n < P.N ? __ldg(row + n * D + c) : 0.f;
             }
             continue;
         }
-        // ---- per-source bandwidths: h = std * bw_scale (circular statistics for the heading) ------------------
-        for (int j = 0; j < k; ++j) {
+        __syncthreads();  // the previous variable's shared state is no longer read
+        // ---- per-source bandwidths: h = std * bw_scale (circular statistics for the heading); sources split over warps
+        for (int j = warp; j < k; j += kProdWarps) {
             const float* row = P.bufs[P.src_buf[s0 + j]] + (size_t)P.src_row[s0 + j] * row_floats;
             float mean[D];
 #pragma unroll
@@ -154,12 +156,12 @@ __global__ void __launch_bounds__(kProdWarps * 32) product_kernel(const __grid_c
                 const float var = warp_sum(a) / (float)max(P.N - 1, 1);
                 const float h = fmaxf(sqrtf(var) * P.bw_scale, 1e-6f);
                 if (lane == 0) {
-                    s_bw[warp][j][c] = 1.0f / (h * h);
+                    s_bw[j][c] = 1.0f / (h * h);
                     if (P.bw_out) P.bw_out[(size_t)(s0 + j) * D + c] = h;
                 }
             }
         }
-        __syncwarp();
+        __syncthreads();
         // ---- exact pair stage for sources 0 and 1: the product of two KDEs is a mixture of N^2 Gaussians with weights
         //      w_ab = Normal(x_0a - x_1b; 0, h_0^2 + h_1^2); marginal W_a = sum_b w_ab -> CDF over a (shared by all
         //      chains of the variable); a chain draws a ~ W, then b | a.  log-sum-exp keeps far-apart proposals finite.
@@ -169,9 +171,8 @@ __global__ void __launch_bounds__(kProdWarps * 32) product_kernel(const __grid_c
             const float* r1 = P.bufs[P.src_buf[s0 + 1]] + (size_t)P.src_row[s0 + 1] * row_floats;
             float c2[D];
 #pragma unroll
-            for (int c = 0; c < D; ++c) c2[c] = -0.5f * kLog2e / (1.0f / s_bw[warp][0][c] + 1.0f / s_bw[warp][1][c]);
-            float wmax = -3.0e38f;
-            for (int a = lane; a < P.N; a += 32) {
+            for (int c = 0; c < D; ++c) c2[c] = -0.5f * kLog2e / (1.0f / s_bw[0][c] + 1.0f / s_bw[1][c]);
+            for (int a = threadIdx.x; a < P.N; a += blockDim.x) {
                 float xa[D];
 #pragma unroll
                 for (int c = 0; c < D; ++c) xa[c] = __ldg(r0 + a * D + c);
@@ -188,31 +189,33 @@ __global__ void __launch_bounds__(kProdWarps * 32) product_kernel(const __grid_c
                     sum = fmaf(sum, exp2f(m - m2), exp2f(q - m2));
                     m = m2;
                 }
-                const float lw = m + lg2f(sum);  // log2 W_a
-                s_cdf[warp][a] = lw;
-                wmax = fmaxf(wmax, lw);
+                s_cdf[a] = m + lg2f(sum);  // log2 W_a
             }
+            __syncthreads();
+            if (warp == 0) {
+                float wmax = -3.0e38f;
+                for (int a = lane; a < P.N; a += 32) wmax = fmaxf(wmax, s_cdf[a]);
 #pragma unroll
-            for (int b = 16; b >= 1; b >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, b));
-            __syncwarp();
-            // inclusive prefix sum of 2^(lw - wmax) over a (warp scan per chunk of 32 with a running carry)
-            float carry = 0.f;
-            for (int base = 0; base < P.N; base += 32) {
-                const int a = base + lane;
-                float x = a < P.N ? exp2f(s_cdf[warp][a] - wmax) : 0.f;
+                for (int b = 16; b >= 1; b >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, b));
+                // inclusive prefix sum of 2^(lw - wmax) over a (warp scan per chunk of 32 with a running carry)
+                float carry = 0.f;
+                for (int base = 0; base < P.N; base += 32) {
+                    const int a = base + lane;
+                    float x = a < P.N ? exp2f(s_cdf[a] - wmax) : 0.f;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const float y = __shfl_up_sync(0xffffffffu, x, o);
-                    if (lane >= o) x += y;
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const float y = __shfl_up_sync(0xffffffffu, x, o);
+                        if (lane >= o) x += y;
+                    }
+                    x += carry;
+                    if (a < P.N) s_cdf[a] = x;
+                    carry = __shfl_sync(0xffffffffu, x, 31);
                 }
-                x += carry;
-                if (a < P.N) s_cdf[warp][a] = x;
-                carry = __shfl_sync(0xffffffffu, x, 31);
             }
-            __syncwarp();
+            __syncthreads();
         }
-        // ---- chains: lane = chain n of the current block of 32 ------------------------------------------------------
-        for (int blk = 0; blk < blocks; ++blk) {
+        // ---- chains: lane = chain n; blocks of 32 chains are dealt to the warps round-robin -------------------------
+        for (int blk = warp; blk < blocks; blk += kProdWarps) {
             const int n = blk * 32 + lane;
             uint32_t rng;
             {
@@ -221,15 +224,15 @@ __global__ void __launch_bounds__(kProdWarps * 32) product_kernel(const __grid_c
             }
             float mu[D], vr[D];
             if (pair) {
-                const float target = u01(rng) * s_cdf[warp][P.N - 1];
+                const float target = u01(rng) * s_cdf[P.N - 1];
                 int lo = 0, hi = P.N - 1;  // first a with cdf[a] >= target
                 while (lo < hi) {
                     const int mid = (lo + hi) >> 1;
-                    if (s_cdf[warp][mid] < target) lo = mid + 1; else hi = mid;
+                    if (s_cdf[mid] < target) lo = mid + 1; else hi = mid;
                 }
                 s_lab[warp][0][lane] = (uint16_t)lo;
-                Ops::fuse(P, s_bw[warp], s_lab[warp], s0, 1, -1, lane, row_floats, mu, vr);
-                s_lab[warp][1][lane] = (uint16_t)Ops::draw(P, s_bw[warp], s0, 1, row_floats, mu, vr, rng);
+                Ops::fuse(P, s_bw, s_lab[warp], s0, 1, -1, lane, row_floats, mu, vr);
+                s_lab[warp][1][lane] = (uint16_t)Ops::draw(P, s_bw, s0, 1, row_floats, mu, vr, rng);
             } else {
                 s_lab[warp][0][lane] = (uint16_t)(xorshift32(rng) % (uint32_t)P.N);
                 s_lab[warp][1][lane] = (uint16_t)(xorshift32(rng) % (uint32_t)P.N);
@@ -237,17 +240,17 @@ __global__ void __launch_bounds__(kProdWarps * 32) product_kernel(const __grid_c
             if (k > 2 || !pair) {
                 // further sources enter one at a time conditioned on the ones already chosen, then Gibbs sweeps over all
                 for (int j = 2; j < k; ++j) {
-                    Ops::fuse(P, s_bw[warp], s_lab[warp], s0, j, -1, lane, row_floats, mu, vr);
-                    s_lab[warp][j][lane] = (uint16_t)Ops::draw(P, s_bw[warp], s0, j, row_floats, mu, vr, rng);
+                    Ops::fuse(P, s_bw, s_lab[warp], s0, j, -1, lane, row_floats, mu, vr);
+                    s_lab[warp][j][lane] = (uint16_t)Ops::draw(P, s_bw, s0, j, row_floats, mu, vr, rng);
                 }
                 for (int t = 0; t < P.iters; ++t)
                     for (int j = 0; j < k; ++j) {
-                        Ops::fuse(P, s_bw[warp], s_lab[warp], s0, k, j, lane, row_floats, mu, vr);
-                        s_lab[warp][j][lane] = (uint16_t)Ops::draw(P, s_bw[warp], s0, j, row_floats, mu, vr, rng);
+                        Ops::fuse(P, s_bw, s_lab[warp], s0, k, j, lane, row_floats, mu, vr);
+                        s_lab[warp][j][lane] = (uint16_t)Ops::draw(P, s_bw, s0, j, row_floats, mu, vr, rng);
                     }
             }
             // the sample: Normal(fused mean, fused variance) of the chosen components
-            Ops::fuse(P, s_bw[warp], s_lab[warp], s0, k, -1, lane, row_floats, mu, vr);
+            Ops::fuse(P, s_bw, s_lab[warp], s0, k, -1, lane, row_floats, mu, vr);
             float z[8];
             const uint4 a = philox4x32_10(make_uint4((uint32_t)n, (uint32_t)v, P.stream_id, 0x50524f45u), P.seed_lo, P.seed_hi);
             box_muller(a.x, a.y, z[0], z[1]); box_muller(a.z, a.w, z[2], z[3]);
@@ -303,7 +306,7 @@ int launch_product(int d, int wrap_dim, const void* params, int num_sms, void* s
     const ProductParams& p = *static_cast<const ProductParams*>(params);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (p.nvars == 0) return 0;
-    int grid = (p.nvars + kProdWarps - 1) / kProdWarps;
+    int grid = p.nvars;
     const int cap = num_sms * 16;
     if (grid > cap) grid = cap;
     if (d == 3 && wrap_dim == 2) product_kernel<3, 2><<<grid, kProdWarps * 32, 0, s>>>(p);

@@ -650,7 +650,7 @@ int rome_b200_product(rome_b200_ctx* ctx, int vartype, int n_bufs, const float* 
     for (int b = 0; b < n_bufs; ++b) p.bufs[b] = d_prop_bufs[b];
     p.bw_out = d_bw_out;
     p.nvars = vs.nvars; p.N = vs.N; p.Npad = vs.Npad;
-    p.iters = gibbs_iters > 0 ? gibbs_iters : 3;
+    p.iters = gibbs_iters > 0 ? gibbs_iters : 2;
     p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32); p.stream_id = stream_id;
     p.bw_scale = (float)std::pow(4.0 / ((d + 2.0) * vs.N), 1.0 / (d + 4.0));
     int e = launch_product(d, kWrapDim[vartype], &p, ctx->num_sms, ctx->stream);

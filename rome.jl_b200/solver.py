@@ -64,7 +64,7 @@ def build_product_plans(fg: FactorGraph, families=None):
 class GibbsSolver:
     """Device-resident sweeps over a DeviceGraph."""
 
-    def __init__(self, dg: DeviceGraph, gibbs_inner: int = 3):
+    def __init__(self, dg: DeviceGraph, gibbs_inner: int = 2):
         self.dg, self.ctx, self.N = dg, dg.ctx, dg.N
         self.gibbs_inner = gibbs_inner
         self.plans, self.buffers = build_product_plans(dg.fg)
