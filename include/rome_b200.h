@@ -112,6 +112,11 @@ enum rome_b200_family {
  * write different buffers).  It is then launched with programmatic dependent launch and may start on SMs the
  * preceding kernel has already vacated.  Results are identical; only the overlap changes. */
 #define ROME_B200_INDEPENDENT 128u
+/* Deconvolution (IIF approxDeconv, test/testBasicPose2Conv.jl:51-56): write to `meas_out` the measurement under which
+ * each particle pair (or prior particle) has ZERO residual, as offsets from the factor mean -- Pose2Pose2:
+ * (R_p'(t_q - t_p), wrap(th_q - th_p)); BearingRange: (bearing, range) of the landmark seen from the pose;
+ * Pose3Pose3: (R_p'(t_q - t_p), Log(R_p' R_q)); priors: the particle itself.  Excludes WRITE_MEAS. */
+#define ROME_B200_DECONV 256u
 
 /* Buffers of one eval call.  Unused members may be NULL.  `_host` entry points take host
  * pointers with the same shapes; plain entry points take device pointers. */

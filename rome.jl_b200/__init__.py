@@ -4,7 +4,7 @@ The directory is named `rome.jl_b200`; import it as `rome_b200` (see /rome_b200.
 Compute lives in librome_b200.so (csrc/, hand-written CUDA behind the C ABI of
 include/rome_b200.h); this package is the host-side mirror of the reference's factor API.
 """
-from ._lib import (BEARINGRANGE, INDEPENDENT, JACOBIAN, POINT2, POINT2POINT2, POINT2POINT2RANGE, POINT3, POINT3POINT3,
+from ._lib import (BEARINGRANGE, DECONV, INDEPENDENT, JACOBIAN, POINT2, POINT2POINT2, POINT2POINT2RANGE, POINT3, POINT3POINT3,
                    POSE2, POSE2POINT2, POSE2POINT2BEARING, POSE2POINT2RANGE, POSE2POSE2, POSE3, POSE3POSE3,
                    POSE3POSE3ROTATION, POSE3POSE3UNITTRANS, POSE3POSE3XYYAW, PRIORPOINT2, PRIORPOINT3, PRIORPOSE2, PRIORPOSE3,
                    PROPOSAL_BWD, PROPOSAL_FWD, RESIDUAL, SAMPLE, SO_PATH, STATS, SYMBOLS, WRITE_MEAS, RomeB200Error)
@@ -15,7 +15,7 @@ from .factors import (MvNormal, Normal, Point2, Point2Point2, Point2Point2Range,
                       Pose2Point2Bearing, Pose2Point2BearingRange, Pose2Point2Range, Pose2Pose2, Pose3, Pose3Pose3,
                       Pose3Pose3Rotation, Pose3Pose3UnitTrans, Pose3Pose3XYYaw, PriorPoint2, PriorPoint3, PriorPose2,
                       PriorPose3, getManifold, getMeasurementParametric, pack, unpack)
-from .graph import (DeviceGraph, FactorGraph, SolverParams, addFactor, addVariable, approxConv, approxConvBelief,
+from .graph import (DeviceGraph, FactorGraph, SolverParams, addFactor, addVariable, approxConv, approxConvBelief, approxDeconv,
                     calcFactorResidual, calcFactorResidualTemporary, default_context, getSample, getSolverParams,
                     getVal, initAll, initfg, ls, lsf, sampleFactor, setVal)
 from .canonical import (generateGraph_Beehive, generateGraph_Circle, generateGraph_Hexagonal,
@@ -23,6 +23,7 @@ from .canonical import (generateGraph_Beehive, generateGraph_Circle, generateGra
                         seed_particles)
 from . import sharding
 from .solver import GibbsSolver, build_product_plans, solveGraphGibbs
+from .parametric import color_variables, solveGraphParametric
 from .g2o import graphFromEdgeArrays, importG2o, loadG2o, parseG2oInstruction
 
 __version__ = "0.1.0"

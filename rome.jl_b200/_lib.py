@@ -15,6 +15,7 @@ POSE2POSE2, PRIORPOSE2, BEARINGRANGE, POSE3POSE3, PRIORPOSE3 = 0, 1, 2, 3, 4
 PRIORPOINT2, POINT2POINT2, POSE2POINT2, POSE2POINT2RANGE, POINT2POINT2RANGE, POSE2POINT2BEARING = 5, 6, 7, 8, 9, 10
 PRIORPOINT3, POINT3POINT3, POSE3POSE3XYYAW, POSE3POSE3ROTATION, POSE3POSE3UNITTRANS = 11, 12, 13, 14, 15
 RESIDUAL, PROPOSAL_FWD, PROPOSAL_BWD, STATS, SAMPLE, WRITE_MEAS, JACOBIAN, INDEPENDENT = 1, 2, 4, 8, 16, 32, 64, 128
+DECONV = 256
 PRODUCT_REANCHOR, MAX_PRODUCT_SOURCES, MAX_PRODUCT_BUFFERS = 1, 32, 16
 
 # every symbol include/rome_b200.h declares (tests check the library exports each one)

@@ -121,6 +121,9 @@ struct FamBearingRange {
                     if (want_stats && !(flags & ROME_B200_PROPOSAL_FWD)) acc_prop2(st, msk, ox, oy);
                 }
             }
+            if ((flags & ROME_B200_DECONV) && live)  // (bearing, range) of the landmark seen from the pose, minus the means
+                __stcs(reinterpret_cast<float2*>(P.meas_out + fo + 2 * n),
+                       make_float2((float)wrap_pi((phi - th) - row.mu_b), (float)(rng - row.mu_r)));
             if ((flags & ROME_B200_JACOBIAN) && live) {  // d r1/d l = (dy,-dx)/rho^2 ; d r2/d l = -d/rho
                 const double i2 = 1.0 / d2, i1 = 1.0 / rng;
                 float4* J = reinterpret_cast<float4*>(P.jac + ((size_t)f * Npad + n) * 4);

@@ -96,6 +96,13 @@ struct FamPose2Pose2 {
                     acc_prop2(st, msk, ox, oy); acc_heading(st, msk, ot);
                 }
             }
+            if ((flags & ROME_B200_DECONV) && live) {  // X = log(p^-1 q): (R_p'(t_q - t_p), wrap(th_q - th_p)) - mu
+                const double vx = (dqx - dpx) - dax, vy = (dqy - dpy) - day;
+                float* M = P.meas_out + fo + 3 * n;
+                __stcs(M, (float)((c * vx + s * vy) - mu0));
+                __stcs(M + 1, (float)((c * vy - s * vx) - mu1));
+                __stcs(M + 2, (float)wrap_pi(((dqt - dpt) - dat) - mu2));
+            }
             if ((flags & ROME_B200_JACOBIAN) && live) {  // d r/d theta_p = (-ry, rx, 1); d r/d m = R(theta_p) (+) 1
                 float4* J = reinterpret_cast<float4*>(P.jac + ((size_t)f * Npad + n) * 4);
                 __stcs(J, make_float4((float)(-ry), (float)rx, (float)c, (float)s));
@@ -148,6 +155,10 @@ struct FamPriorPose2 {
                 const float ox = (float)hx, oy = (float)hy, ot = (float)wrap_pi(ht);
                 o_fwd[k][0] = ox; o_fwd[k][1] = oy; o_fwd[k][2] = ot;
                 if (want_stats) { acc_prop2(st, msk, ox, oy); acc_heading(st, msk, ot); }
+            }
+            if ((flags & ROME_B200_DECONV) && live) {  // the measurement that explains the particle is the particle
+                float* M = P.meas_out + fo + 3 * n;
+                __stcs(M, (float)(dpx - mx0)); __stcs(M + 1, (float)(dpy - my0)); __stcs(M + 2, (float)wrap_pi(dpt - mt0));
             }
         })
         if (want_stats) write_stats16(st, P.stats, f, lane);

@@ -97,6 +97,16 @@ struct FamPose3Pose3 {
                 if (want_stats) acc_res6(st, msk, r);
                 if (kSample && (flags & ROME_B200_WRITE_MEAS) && live) store6_global(P.meas_out + fo + 6 * n, m[j]);
                 if ((flags & ROME_B200_RESIDUAL) && live) store6(V.out_res + 6 * n, r);
+                if ((flags & ROME_B200_DECONV) && live) {  // X = log(p^-1 q) = (R_p'(t_q - t_p), Log(R_p' R_q)) - mu
+                    const Quat Rpc = qconj(Rp[j]);
+                    double vx, vy, vz, ox, oy, oz;
+                    quat_rotate(Rpc, ((double)q[j][0] - (double)p[j][0]) - dax, ((double)q[j][1] - (double)p[j][1]) - day,
+                                ((double)q[j][2] - (double)p[j][2]) - daz, vx, vy, vz);
+                    quat_log_any(qmul(Rpc, Rq[j]), ox, oy, oz);
+                    const float o[6] = {(float)(vx - row.mu[0]), (float)(vy - row.mu[1]), (float)(vz - row.mu[2]),
+                                        (float)(ox - row.mu[3]), (float)(oy - row.mu[4]), (float)(oz - row.mu[5])};
+                    store6_global(P.meas_out + fo + 6 * n, o);
+                }
                 if (flags & ROME_B200_PROPOSAL_FWD) {  // q = p o Exp(X): coordinates as offsets from q's anchor
                     double ox, oy, oz;
                     quat_log_any(Rh[j], ox, oy, oz);
@@ -163,6 +173,12 @@ struct FamPriorPose3 {
                 if (want_stats) acc_res6(st, msk, r);
                 if (kSample && (flags & ROME_B200_WRITE_MEAS) && live) store6_global(P.meas_out + fo + 6 * n, m);
                 if ((flags & ROME_B200_RESIDUAL) && live) store6(V.out_res + 6 * n, r);
+                if ((flags & ROME_B200_DECONV) && live) {  // the measurement that explains the particle is the particle
+                    float o[6];
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) o[i] = (float)((ap[i] + (double)p[i]) - row.mu[i]);
+                    store6_global(P.meas_out + fo + 6 * n, o);
+                }
                 if (flags & ROME_B200_PROPOSAL_FWD) {  // proposal = the sampled point, offsets from the anchor
                     const float o[6] = {(float)hx,           (float)hy,           (float)hz,
                                         (float)(X[3] - ap[3]), (float)(X[4] - ap[4]), (float)(X[5] - ap[5])};

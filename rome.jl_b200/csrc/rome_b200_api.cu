@@ -481,6 +481,11 @@ static int check_eval(rome_b200_ctx* ctx, int family, uint32_t flags, int first,
     if (!(flags & ROME_B200_SAMPLE) && !b->meas) return fail(ctx, ROME_B200_BAD_ARG, "meas is NULL and SAMPLE is not set");
     if ((flags & ROME_B200_WRITE_MEAS) && (!(flags & ROME_B200_SAMPLE) || !b->meas_out))
         return fail(ctx, ROME_B200_BAD_ARG, "WRITE_MEAS needs SAMPLE and meas_out");
+    if (flags & ROME_B200_DECONV) {
+        if (family > ROME_B200_PRIORPOSE3) return fail(ctx, ROME_B200_BAD_ARG, "this family has no closed-form deconvolution");
+        if ((flags & ROME_B200_WRITE_MEAS) || !b->meas_out)
+            return fail(ctx, ROME_B200_BAD_ARG, "DECONV needs meas_out and excludes WRITE_MEAS");
+    }
     if ((flags & ROME_B200_RESIDUAL) && !b->res) return fail(ctx, ROME_B200_BAD_ARG, "res is NULL");
     if ((flags & ROME_B200_PROPOSAL_FWD) && fi.dfwd == 0)
         return fail(ctx, ROME_B200_BAD_ARG, "this family has no closed-form forward proposal");
@@ -560,7 +565,7 @@ static int eval_host_impl(rome_b200_ctx* ctx, int family, uint32_t flags, uint64
                            cudaMemcpyDefault, ctx->stream));
         db.meas = tmp;
     }
-    if (flags & ROME_B200_WRITE_MEAS) { if (int e = mirror(1, sm, &db.meas_out)) return e; }
+    if (flags & (ROME_B200_WRITE_MEAS | ROME_B200_DECONV)) { if (int e = mirror(1, sm, &db.meas_out)) return e; }
     if (flags & ROME_B200_RESIDUAL) { if (int e = mirror(2, sr, &db.res)) return e; }
     if (flags & ROME_B200_PROPOSAL_FWD) { if (int e = mirror(3, sf, &db.prop_fwd)) return e; }
     if (flags & ROME_B200_PROPOSAL_BWD) { if (int e = mirror(4, sb, &db.prop_bwd)) return e; }
@@ -572,7 +577,7 @@ static int eval_host_impl(rome_b200_ctx* ctx, int family, uint32_t flags, uint64
                            cudaMemcpyDefault, ctx->stream));
         return 0;
     };
-    if (flags & ROME_B200_WRITE_MEAS) { if (int e = back(1, sm, hb->meas_out)) return e; }
+    if (flags & (ROME_B200_WRITE_MEAS | ROME_B200_DECONV)) { if (int e = back(1, sm, hb->meas_out)) return e; }
     if (flags & ROME_B200_RESIDUAL) { if (int e = back(2, sr, hb->res)) return e; }
     if (flags & ROME_B200_PROPOSAL_FWD) { if (int e = back(3, sf, hb->prop_fwd)) return e; }
     if (flags & ROME_B200_PROPOSAL_BWD) { if (int e = back(4, sb, hb->prop_bwd)) return e; }

@@ -249,7 +249,7 @@ class Context:
         nF = self.num_factors(family)
         Np = self.particles_device(vt0)[5]
         out = {}
-        if flags & WRITE_MEAS:
+        if flags & (WRITE_MEAS | L.DECONV):
             out["meas_out"] = np.zeros((nF, Np, dm), np.float32)
         if flags & RESIDUAL:
             out["res"] = np.zeros((nF, Np, dr), np.float32)

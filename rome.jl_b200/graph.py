@@ -161,7 +161,7 @@ class DeviceGraph:
     """The whole graph resident on one GPU: particle stores per variable type + one factor table per
     family.  `eval(family, flags)` is the batched replacement of IIF's per-factor / per-particle loop."""
 
-    def __init__(self, fg: FactorGraph, ctx: Context | None = None, N: int | None = None):
+    def __init__(self, fg: FactorGraph, ctx: Context | None = None, N: int | None = None, upload_particles: bool = True):
         self.fg = fg
         self.ctx = ctx or Context(0)
         self.N = N or fg.solverParams.N
@@ -170,7 +170,8 @@ class DeviceGraph:
         self.by_family = {f: sorted((x for x in fg.factors.values() if x.fnc.family == f), key=lambda x: x.index)
                           for f in FAMILY}
         self.upload_factors()
-        self.upload_particles()
+        if upload_particles:
+            self.upload_particles()
 
     def upload_particles(self):
         for t, vs in self.by_type.items():
@@ -344,6 +345,28 @@ def approxConv(fg: FactorGraph, flabel, target, N: int | None = None, seed=0, ct
 
 
 approxConvBelief = approxConv
+
+
+def approxDeconv(fg: FactorGraph, flabel, N: int | None = None, seed=0, ctx: Context | None = None):
+    """IIF approxDeconv(fg, :x0x1f1) -> (pts, meas): `pts` = the measurement each particle pair implies (the residual
+    solved for the measurement, ROME_B200_DECONV), `meas` = N fresh samples of the factor's belief, both as [N][dm]
+    measurement coordinates (test/testBasicPose2Conv.jl:51-56 compares the two sets)."""
+    f = fg.factors[str(flabel)]
+    fnc = f.fnc
+    N = N or fg.solverParams.N
+    pts = []
+    for l in f.variableOrderSymbols:
+        v = fg.variables[l]
+        if v.val is None or v.val.shape[0] != N:
+            raise ValueError(f"variable {l} must hold {N} particles to deconvolve {flabel}")
+        pts.append(v.val)
+    dg = DeviceGraph(_mini_graph(fnc, pts, N), ctx or default_context(), N=N)
+    c, mu = dg.ctx, dg.means(fnc.family)
+    out = c.alloc_host_outputs(fnc.family, L.SAMPLE | L.DECONV)
+    c.eval_host(fnc.family, L.SAMPLE | L.DECONV, seed=seed, **out)
+    dec = offsets_to_meas(out["meas_out"], mu, N)[0]
+    meas = dg.eval(fnc.family, L.SAMPLE | L.WRITE_MEAS, seed=seed)["meas"][0]
+    return dec, meas
 
 
 def initAll(fg: FactorGraph, seed=0, ctx: Context | None = None):

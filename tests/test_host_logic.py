@@ -202,3 +202,13 @@ def test_product_plan_from_graph():
     assert src3 == sorted([(2 * k[rb.POSE2POSE2], 2), (2 * k[rb.POSE2POSE2] + 1, 3)])
     offl, sbl, srl = plans[rb.POINT2]  # :l1 = fwd of both sightings
     assert list(offl) == [0, 2] and sorted(srl) == [0, 1] and set(sbl) == {2 * k[rb.BEARINGRANGE]}
+
+
+def test_parametric_colouring_is_proper():
+    """host logic of the parametric solve: variables sharing a factor never share a colour"""
+    fg = rb.generateGraph_Hexagonal()
+    col = rb.color_variables(fg)
+    for f in fg.factors.values():
+        ls = f.variableOrderSymbols
+        assert len({col[l] for l in ls}) == len(ls)
+    assert max(col.values()) <= 3
