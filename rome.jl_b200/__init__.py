@@ -24,6 +24,6 @@ from .canonical import (generateGraph_Beehive, generateGraph_Circle, generateGra
 from . import sharding
 from .solver import GibbsSolver, build_product_plans, solveGraphGibbs
 from .parametric import color_variables, solveGraphParametric
-from .g2o import graphFromEdgeArrays, importG2o, loadG2o, parseG2oInstruction
+from .g2o import exportG2o, graphFromEdgeArrays, importG2o, loadG2o, parseG2oInstruction, stringG2o
 
 __version__ = "0.1.0"

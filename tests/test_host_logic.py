@@ -212,3 +212,46 @@ def test_parametric_colouring_is_proper():
         ls = f.variableOrderSymbols
         assert len({col[l] for l in ls}) == len(ls)
     assert max(col.values()) <= 3
+
+
+def test_g2o_import_export_text(golden_dir, tmp_path):
+    """test/testG2oParser.jl:8-17 (tokenised import) and :26-51 (exact exported text of the Hexagonal graph)"""
+    ins = rb.importG2o(os.path.join(golden_dir, "octagon.g2o"))
+    assert ins[0][0] == "EDGE_SE2" and ins[6][0] == "EDGE_SE2"
+    assert ins[5][11] == "6541.252776" and ins[2][6] == "1211.201664"
+    assert len(ins) == 8 and len(ins[1]) == 12
+    reflines = ["EDGE_SE2 0 1 10.0 0.0 1.0471975511965976 100.0 0.0 -0.0 100.0 -0.0 100.0",
+                "LANDMARK 0 2 0.0 20.0 99.99999999999999 0.0 1.0",
+                "EDGE_SE2 1 3 10.0 0.0 1.0471975511965976 100.0 0.0 -0.0 100.0 -0.0 100.0",
+                "EDGE_SE2 3 4 10.0 0.0 1.0471975511965976 100.0 0.0 -0.0 100.0 -0.0 100.0",
+                "EDGE_SE2 4 5 10.0 0.0 1.0471975511965976 100.0 0.0 -0.0 100.0 -0.0 100.0",
+                "EDGE_SE2 5 6 10.0 0.0 1.0471975511965976 100.0 0.0 -0.0 100.0 -0.0 100.0",
+                "EDGE_SE2 6 7 10.0 0.0 1.0471975511965976 100.0 0.0 -0.0 100.0 -0.0 100.0",
+                "LANDMARK 7 2 0.0 20.0 99.99999999999999 0.0 1.0"]
+    fg = rb.generateGraph_Hexagonal(graphinit=False)
+    path = rb.exportG2o(fg, filename=str(tmp_path / "hex.g2o"))
+    assert open(path).read().splitlines() == reflines
+    # round trip of the pose-pose edges through the importer
+    fg2 = rb.loadG2o(path.replace("hex.g2o", "hex2.g2o")) if False else rb.initfg()
+    for ln in reflines:
+        rb.parseG2oInstruction(fg2, ln.split())
+    assert len(rb.lsf(fg2, rb.Pose2Pose2)) == 6
+    f = fg2.factors["x0x1f1"].fnc
+    assert np.allclose(f.Z.mu, [10, 0, np.pi / 3]) and np.allclose(f.Z.Sigma, 0.01 * np.eye(3))
+    # SE(3): vertex + edge lines, quaternion order x y z w, 21 upper-triangular information entries
+    fg3 = rb.initfg()
+    rb.parseG2oInstruction(fg3, "VERTEX_SE3:QUAT 0 1 2 3 0 0 0.3826834323650898 0.9238795325112867".split())
+    rb.parseG2oInstruction(fg3, "VERTEX_SE2 5 1.5 -2 0.3".split())
+    assert np.allclose(fg3["x0"].parametric, [1, 2, 3, 0, 0, np.pi / 4]) and np.allclose(fg3["x5"].parametric, [1.5, -2, 0.3])
+    p3 = rb.generateGraph_Pose3Chain(4, loops=0)
+    path3 = rb.exportG2o(p3, filename=str(tmp_path / "p3.g2o"))
+    back = rb.loadG2o(path3)
+    for l, fa in p3.factors.items():
+        if isinstance(fa.fnc, rb.Pose3Pose3):
+            fb = back.factors[l].fnc
+            assert np.allclose(fa.fnc.Z.mu, fb.Z.mu, atol=1e-12) and np.allclose(fa.fnc.Z.Sigma, fb.Z.Sigma, rtol=1e-9)
+    # VERTEX lines from a solve key
+    for k, v in enumerate(fg.variables.values()):
+        v.parametric = np.arange(v.variableType.dim, dtype=float) + k
+    head = open(rb.exportG2o(fg, filename=str(tmp_path / "hexv.g2o"), solveKey="parametric")).read().splitlines()
+    assert head[0] == "VERTEX_SE2 0 0.0 1.0 2.0" and head[1] == "VERTEX_SE2 1 1.0 2.0 3.0" and len(head) == 7 + 8
