@@ -70,11 +70,11 @@ __device__ __forceinline__ void normals_for_group(const EvalParams& P, int f, in
         normal4(P.seed_lo, P.seed_hi, P.stream_id, (uint32_t)f, (uint32_t)lane, (uint32_t)(g * D + b), &z[4 * b]);
 }
 
-// Slot loop.  A group = the lane's 4 slots {n0, n0+32, n0+64, n0+96}.  A FULL group (its 4th slot still has live
-// particles) is evaluated as branch-free straight-line code: first the four slot BODIES (loads + arithmetic into
+// Slot loop.  A group = the lane's 4 slots {n0, n0+32, n0+64, n0+96}.  A group with at least three live slots
+// is evaluated as branch-free straight-line code: first the four slot BODIES (loads + arithmetic into
 // registers), then the four slot STORES -- no shared-memory store sits between the loads of different slots, so
-// the Float64 chains of the four particles may interleave.  Slots 0-2 are live for every lane; a lane whose 4th
-// particle is beyond Npad reads particle `lane` instead and has its stores/statistics masked.  FASTCOND
+// the Float64 chains of the four particles may interleave.  Slots 0-1 are live for every lane; a lane whose 3rd or
+// 4th particle is beyond Npad reads particle `lane` instead and has its stores/statistics masked.  FASTCOND
 // (warp-uniform) selects the variant whose body may assume kFast (e.g. small heading offsets -> polynomial
 // sin/cos without a fallback branch).  The trailing partial group is evaluated with warp-uniform guards.
 // The family defines ROME_SLOT_DECL (per-group register arrays) and ROME_SLOT_STORE (uses k, n, live).
@@ -83,34 +83,35 @@ __device__ __forceinline__ void normals_for_group(const EvalParams& P, int f, in
         float z[4 * DZ];                                                                       \
         if (kSample) normals_for_group<DZ>(P, f, lane, g, z);                                  \
         ROME_SLOT_DECL                                                                         \
-        if (n0 - lane + 96 < Npad) {                                                           \
+        if (n0 - lane + 64 < Npad) { /* at least three live slots: straight-line code for all four */ \
+            const int n2 = (n0 + 64 < Npad) ? n0 + 64 : lane;                                  \
             const int n3 = (n0 + 96 < Npad) ? n0 + 96 : lane;                                  \
             if (FASTCOND) {                                                                    \
                 constexpr bool kFast = true; (void)kFast;                                      \
                 _Pragma("unroll") for (int k = 0; k < 4; ++k) {                                \
                     const int nn = n0 + 32 * k;                                                \
-                    const bool live = (k < 3) || nn < Npad;                                    \
-                    const int n = (k < 3) ? nn : n3;                                           \
+                    const bool live = (k < 2) || nn < Npad;                                    \
+                    const int n = (k < 2) ? nn : (k == 2 ? n2 : n3);                           \
                     __VA_ARGS__                                                                \
                 }                                                                              \
             } else {                                                                           \
                 constexpr bool kFast = false; (void)kFast;                                     \
                 _Pragma("unroll") for (int k = 0; k < 4; ++k) {                                \
                     const int nn = n0 + 32 * k;                                                \
-                    const bool live = (k < 3) || nn < Npad;                                    \
-                    const int n = (k < 3) ? nn : n3;                                           \
+                    const bool live = (k < 2) || nn < Npad;                                    \
+                    const int n = (k < 2) ? nn : (k == 2 ? n2 : n3);                           \
                     __VA_ARGS__                                                                \
                 }                                                                              \
             }                                                                                  \
             _Pragma("unroll") for (int k = 0; k < 4; ++k) {                                    \
                 const int nn = n0 + 32 * k;                                                    \
-                const bool live = (k < 3) || nn < Npad;                                        \
-                const int n = (k < 3) ? nn : n3;                                               \
+                const bool live = (k < 2) || nn < Npad;                                        \
+                const int n = (k < 2) ? nn : (k == 2 ? n2 : n3);                               \
                 ROME_SLOT_STORE                                                                \
             }                                                                                  \
         } else {                                                                               \
             constexpr bool kFast = false; (void)kFast;                                         \
-            _Pragma("unroll") for (int k = 0; k < 4; ++k) {                                    \
+            _Pragma("unroll") for (int k = 0; k < 2; ++k) {                                    \
                 const int nn = n0 + 32 * k;                                                    \
                 if (n0 - lane + 32 * k < Npad) {                                               \
                     const bool live = nn < Npad;                                               \

@@ -49,7 +49,7 @@ struct FamBearingRange {
             return fmaf(ex, ex, ey * ey);
         };
 #define ROME_BR_FAST                                                                                       \
-    (!__any_sync(0xffffffffu, fmaxf(fmaxf(delta2(n0), delta2(n0 + 32)), fmaxf(delta2(n0 + 64), delta2(n3))) > fast_lim))
+    (!__any_sync(0xffffffffu, fmaxf(fmaxf(delta2(n0), delta2(n0 + 32)), fmaxf(delta2(n2), delta2(n3))) > fast_lim))
         ROME_SLOT_LOOP(ROME_BR_FAST, {
             const double dpx = Pp[3 * n], dpy = Pp[3 * n + 1], dpt = Pp[3 * n + 2];
             const float2 lxy = *reinterpret_cast<const float2*>(Lp + 2 * n);

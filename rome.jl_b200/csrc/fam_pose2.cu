@@ -40,7 +40,7 @@ struct FamPose2Pose2 {
         // warp-uniform: every heading offset of this group is small enough for the polynomial sin/cos
 #define ROME_P2P2_FAST                                                                                         \
     (!__any_sync(0xffffffffu, fmaxf(fmaxf(fabsf(Pp[3 * n0 + 2]), fabsf(Pp[3 * (n0 + 32) + 2])),               \
-                                    fmaxf(fabsf(Pp[3 * (n0 + 64) + 2]), fabsf(Pp[3 * n3 + 2]))) > (float)kSmallAngle))
+                                    fmaxf(fabsf(Pp[3 * n2 + 2]), fabsf(Pp[3 * n3 + 2]))) > (float)kSmallAngle))
         ROME_SLOT_LOOP(ROME_P2P2_FAST, {
             const double dpx = Pp[3 * n], dpy = Pp[3 * n + 1], dpt = Pp[3 * n + 2];
             const double dqx = Qp[3 * n], dqy = Qp[3 * n + 1], dqt = Qp[3 * n + 2];
