@@ -19,10 +19,16 @@ using RoME, DistributedFactorGraphs, IncrementalInference
 const LIB = get(ENV, "ROME_B200_LIB", joinpath(@__DIR__, "..", "librome_b200.so"))
 
 # enums of include/rome_b200.h
-const POSE2, POINT2, POSE3 = Cint(0), Cint(1), Cint(2)
+const POSE2, POINT2, POSE3, POINT3 = Cint(0), Cint(1), Cint(2), Cint(3)
 const POSE2POSE2, PRIORPOSE2, BEARINGRANGE, POSE3POSE3, PRIORPOSE3 = Cint(0), Cint(1), Cint(2), Cint(3), Cint(4)
-const RESIDUAL, PROPOSAL_FWD, PROPOSAL_BWD, STATS, SAMPLE, WRITE_MEAS, JACOBIAN =
-    UInt32(1), UInt32(2), UInt32(4), UInt32(8), UInt32(16), UInt32(32), UInt32(64)
+# next-row families (SURVEY.md 8f N1)
+const PRIORPOINT2, POINT2POINT2, POSE2POINT2, POSE2POINT2RANGE, POINT2POINT2RANGE, POSE2POINT2BEARING =
+    Cint(5), Cint(6), Cint(7), Cint(8), Cint(9), Cint(10)
+const PRIORPOINT3, POINT3POINT3, POSE3POSE3XYYAW, POSE3POSE3ROTATION, POSE3POSE3UNITTRANS =
+    Cint(11), Cint(12), Cint(13), Cint(14), Cint(15)
+const RESIDUAL, PROPOSAL_FWD, PROPOSAL_BWD, STATS, SAMPLE, WRITE_MEAS, JACOBIAN, INDEPENDENT, DECONV =
+    UInt32(1), UInt32(2), UInt32(4), UInt32(8), UInt32(16), UInt32(32), UInt32(64), UInt32(128), UInt32(256)
+const PRODUCT_REANCHOR = UInt32(1)
 
 struct Buffers            # struct rome_b200_buffers
     meas::Ptr{Cfloat}
@@ -94,6 +100,32 @@ function set_factors!(ctx::Context, ::Type{Pose3Pose3}, ip::Vector{Int32}, iq::V
     check(ctx, ccall((:rome_b200_set_factors_pose3pose3, LIB), Cint,
                      (Ptr{Cvoid}, Cint, Ptr{Int32}, Ptr{Int32}, Ptr{Cdouble}, Ptr{Cdouble}),
                      ctx.h, length(ip), ip, iq, mu, cv))
+end
+
+# every family whose belief is a single MvNormal (Point2Point2, Point3Point3, Pose3Pose3XYYaw, ...): iq = nothing for priors
+function set_factors!(ctx::Context, family::Cint, ip::Vector{Int32}, iq::Union{Nothing,Vector{Int32}}, Z::Vector{<:MvNormal})
+    mu = reduce(hcat, mean.(Z)); cv = reduce(hcat, vec.(Matrix.(cov.(Z))))
+    check(ctx, ccall((:rome_b200_set_factors_gaussian, LIB), Cint,
+                     (Ptr{Cvoid}, Cint, Cint, Ptr{Int32}, Ptr{Int32}, Ptr{Cdouble}, Ptr{Cdouble}),
+                     ctx.h, family, length(ip), ip, iq === nothing ? C_NULL : iq, mu, cv))
+end
+
+# ---- belief update on the device (SURVEY.md 8f N2): product of the proposal densities of every variable ---------
+# plan: CSR over variables of `vartype`; source = (index into `bufs`, proposal row = factor index)
+function set_product_plan!(ctx::Context, vartype::Cint, var_offsets::Vector{Int32}, src_buf::Vector{Int32}, src_row::Vector{Int32})
+    check(ctx, ccall((:rome_b200_set_product_plan, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}),
+                     ctx.h, vartype, length(var_offsets) - 1, var_offsets, src_buf, src_row))
+end
+# bufs: DEVICE pointers of the proposal buffers (rome_b200_malloc_device); replaces manifoldProduct / manikde! on the host
+function product!(ctx::Context, vartype::Cint, bufs::Vector{Ptr{Cfloat}}; seed=UInt64(0), sweep=UInt32(0), gibbs_iters=0)
+    check(ctx, ccall((:rome_b200_product, LIB), Cint,
+                     (Ptr{Cvoid}, Cint, Cint, Ptr{Ptr{Cfloat}}, UInt64, UInt32, Cint, UInt32, Ptr{Cfloat}),
+                     ctx.h, vartype, length(bufs), bufs, seed, sweep, gibbs_iters, PRODUCT_REANCHOR, C_NULL))
+end
+function get_particles(ctx::Context, vartype::Cint, d::Int, N::Int, nvars::Int)
+    out = Array{Float64,3}(undef, d, N, nvars)
+    check(ctx, ccall((:rome_b200_get_particles, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cdouble}), ctx.h, vartype, out))
+    return out
 end
 
 # ---- the hot path --------------------------------------------------------------------------------------------
