@@ -33,9 +33,12 @@ __device__ __forceinline__ uint32_t xorshift32(uint32_t& s) {
     s ^= s << 13; s ^= s >> 17; s ^= s << 5;
     return s;
 }
+// per-chain stream for the Gumbel noise: 32-bit LCG (Numerical Recipes constants), one IMAD per draw; only its top 23
+// bits are used and every chain is seeded by its own Philox block, which is ample for a categorical draw over N
 // uniform in (0,1) with 23 random bits
 __device__ __forceinline__ float u01(uint32_t& s) {
-    return __uint_as_float(0x3f800000u | (xorshift32(s) >> 9)) - (1.0f - 5.9604644775390625e-08f);
+    s = s * 1664525u + 1013904223u;
+    return __uint_as_float(0x3f800000u | (s >> 9)) - (1.0f - 5.9604644775390625e-08f);
 }
 __device__ __forceinline__ float lg2f(float x) {
     float r;
@@ -88,11 +91,12 @@ struct ProdOps {
         const float* row = P.bufs[P.src_buf[s0 + j]] + (size_t)P.src_row[s0 + j] * row_floats;
         float best = -3.0e38f;
         int arg = 0;
-        for (int i = 0; i < P.N; ++i) {
+        const float* x = row;
+        for (int i = 0; i < P.N; ++i, x += D) {  // running pointer: the D loads take immediate offsets
             float q = 0.f;
 #pragma unroll
             for (int c = 0; c < D; ++c) {
-                float dlt = __ldg(row + i * D + c) - mu[c];
+                float dlt = __ldg(x + c) - mu[c];
                 if (c == WRAP) dlt = wrap_pi_f(dlt);
                 q = fmaf(c2[c] * dlt, dlt, q);
             }
@@ -177,11 +181,12 @@ __global__ void __launch_bounds__(kProdWarps * 32) product_kernel(const __grid_c
 #pragma unroll
                 for (int c = 0; c < D; ++c) xa[c] = __ldg(r0 + a * D + c);
                 float m = -3.0e38f, sum = 0.f;
-                for (int b = 0; b < P.N; ++b) {
+                const float* xb = r1;
+                for (int b = 0; b < P.N; ++b, xb += D) {
                     float q = 0.f;
 #pragma unroll
                     for (int c = 0; c < D; ++c) {
-                        float dlt = __ldg(r1 + b * D + c) - xa[c];
+                        float dlt = __ldg(xb + c) - xa[c];
                         if (c == WRAP) dlt = wrap_pi_f(dlt);
                         q = fmaf(c2[c] * dlt, dlt, q);
                     }

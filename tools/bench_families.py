@@ -75,11 +75,74 @@ def time_family(name, fg, family, N, steps, sets_n):
     print(json.dumps(out), flush=True)
 
 
+def next_row_graph(family, poses, N, rng):
+    """synthetic workload for a next-row family: `poses` factors over `poses` + landmark variables laid
+    out like the Manhattan-shaped walk (unit steps), landmarks 5 m off the path"""
+    fg = rb.initfg(rb.SolverParams(N=N))
+    walk = np.cumsum(rng.choice([-1.0, 1.0], size=(poses, 2)), 0)
+    vt0, vt1 = rb.FAMILY[family][0], rb.FAMILY[family][1]
+    cls = {rb.POSE2: rb.Pose2, rb.POINT2: rb.Point2, rb.POSE3: rb.Pose3, rb.POINT3: rb.Point3}
+    sig = {rb.POSE2: [0.1, 0.12, 0.02], rb.POINT2: [0.3, 0.3], rb.POSE3: [0.1] * 3 + [0.02] * 3, rb.POINT3: [0.3] * 3}
+
+    def truth(t, i):
+        d = rb.VAR_DIM[t]
+        x = np.zeros(d)
+        x[:2] = walk[i]
+        if t in (rb.POINT2, rb.POINT3):
+            x[:2] += 5.0
+        if t == rb.POSE2:
+            x[2] = rng.uniform(-3, 3)
+        if t == rb.POSE3:
+            x[3:] = rng.normal(size=3) * 0.5
+        return x
+    names0 = [f"a{i}" for i in range(poses)]
+    for i, l in enumerate(names0):
+        v = rb.addVariable(fg, l, cls[vt0])
+        v.val = truth(vt0, i)[None] + rng.normal(size=(N, rb.VAR_DIM[vt0])) * sig[vt0]
+    if vt1 is not None and vt1 != vt0:
+        for i in range(poses):
+            v = rb.addVariable(fg, f"b{i}", cls[vt1])
+            v.val = truth(vt1, i)[None] + rng.normal(size=(N, rb.VAR_DIM[vt1])) * sig[vt1]
+    dm = rb.FAMILY[family][2]
+    mk = {rb.PRIORPOINT2: lambda: rb.PriorPoint2(rb.MvNormal(np.zeros(2), np.eye(2) * 0.01)),
+          rb.POINT2POINT2: lambda: rb.Point2Point2(rb.MvNormal(np.array([1.0, 1.0]), np.eye(2) * 0.01)),
+          rb.POSE2POINT2: lambda: rb.Pose2Point2(rb.MvNormal(np.array([5.0, 5.0]), np.eye(2) * 0.01)),
+          rb.POSE2POINT2RANGE: lambda: rb.Pose2Point2Range(rb.Normal(7.0, 0.1)),
+          rb.POINT2POINT2RANGE: lambda: rb.Point2Point2Range(rb.Normal(1.4, 0.1)),
+          rb.POSE2POINT2BEARING: lambda: rb.Pose2Point2Bearing(rb.Normal(0.7, 0.05)),
+          rb.PRIORPOINT3: lambda: rb.PriorPoint3(rb.MvNormal(np.zeros(3), np.eye(3) * 0.01)),
+          rb.POINT3POINT3: lambda: rb.Point3Point3(rb.MvNormal(np.array([1.0, 1.0, 0.0]), np.eye(3) * 0.01)),
+          rb.POSE3POSE3XYYAW: lambda: rb.Pose3Pose3XYYaw(rb.MvNormal(np.array([1.0, 1.0, 0.1]), np.eye(3) * 0.01)),
+          rb.POSE3POSE3ROTATION: lambda: rb.Pose3Pose3Rotation(rb.MvNormal(np.zeros(3), np.eye(3) * 1e-4)),
+          rb.POSE3POSE3UNITTRANS: lambda: rb.Pose3Pose3UnitTrans()}[family]
+    for i in range(poses):
+        if vt1 is None:
+            rb.addFactor(fg, [names0[i]], mk())
+        elif vt1 == vt0:
+            if i + 1 < poses:
+                rb.addFactor(fg, [names0[i], names0[i + 1]], mk())
+        else:
+            rb.addFactor(fg, [names0[i], f"b{i}"], mk())
+    return fg
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--poses", type=int, default=10000)
+    ap.add_argument("--next-rows", action="store_true", help="time the next-row families (SURVEY 8f N1) instead")
     args = ap.parse_args()
+    if args.next_rows:
+        rng = np.random.default_rng(6)
+        names = {rb.PRIORPOINT2: "PriorPoint2", rb.POINT2POINT2: "Point2Point2", rb.POSE2POINT2: "Pose2Point2",
+                 rb.POSE2POINT2RANGE: "Pose2Point2Range", rb.POINT2POINT2RANGE: "Point2Point2Range",
+                 rb.POSE2POINT2BEARING: "Pose2Point2Bearing", rb.PRIORPOINT3: "PriorPoint3", rb.POINT3POINT3: "Point3Point3",
+                 rb.POSE3POSE3XYYAW: "Pose3Pose3XYYaw", rb.POSE3POSE3ROTATION: "Pose3Pose3Rotation",
+                 rb.POSE3POSE3UNITTRANS: "Pose3Pose3UnitTrans"}
+        for fam, nm in names.items():
+            fg = next_row_graph(fam, args.poses, 100, rng)
+            time_family(f"N1 {nm} synthetic {args.poses}", fg, fam, 100, args.steps, 8)
+        return
     golden = os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "manhattan_g2o.npz")
     z = np.load(golden)
     fg = rb.graphFromEdgeArrays(z["ids"], z["mu"], z["info"])
