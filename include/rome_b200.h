@@ -136,7 +136,8 @@ ROME_B200_API int rome_b200_version(void);
 ROME_B200_API int rome_b200_create(int device, rome_b200_ctx** out);
 ROME_B200_API int rome_b200_destroy(rome_b200_ctx* ctx);
 ROME_B200_API const char* rome_b200_last_error(const rome_b200_ctx* ctx); /* ctx may be NULL (creation errors) */
-/* Use a caller-owned cudaStream_t for all work of this ctx (NULL -> the ctx's own stream). */
+/* Use a caller-owned cudaStream_t for all work of this ctx (NULL -> the ctx's own non-blocking stream; pass
+ * cudaStreamLegacy / cudaStreamPerThread explicitly to run on a default stream). */
 ROME_B200_API int rome_b200_set_stream(rome_b200_ctx* ctx, void* cuda_stream);
 ROME_B200_API int rome_b200_synchronize(rome_b200_ctx* ctx);
 /* family/vartype dimensions: dm (measurement), dr (residual), stats width, jacobian rows */

@@ -111,7 +111,8 @@ class Context:
 
     def use_torch_stream(self):
         import torch
-        self.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        # torch's default stream has handle 0, which the C ABI reads as "the ctx's own stream": pass cudaStreamLegacy
+        self.set_stream(torch.cuda.current_stream(self.device).cuda_stream or 1)
 
     def synchronize(self):
         self._ck(self._lib.rome_b200_synchronize(self._h))

@@ -62,28 +62,62 @@ def build_product_plans(fg: FactorGraph, families=None):
 
 
 class GibbsSolver:
-    """Device-resident sweeps over a DeviceGraph."""
+    """Device-resident sweeps over a DeviceGraph.
 
-    def __init__(self, dg: DeviceGraph, gibbs_inner: int = 2):
+    distributed=True (inside an initialised torch.distributed job, one rank per GPU, the same graph and particles on
+    every rank -- SURVEY.md 8e): every rank convolves only its contiguous share of each family's factor list, the proposal
+    rows are all-gathered (one collective per proposal buffer per sweep), and every rank takes the products of ALL
+    variables -- the product sampler is keyed by (seed, sweep, variable, particle), so the replicated particle stores
+    stay bit-identical without a second exchange."""
+
+    def __init__(self, dg: DeviceGraph, gibbs_inner: int = 2, distributed: bool = False, group=None):
         self.dg, self.ctx, self.N = dg, dg.ctx, dg.N
         self.gibbs_inner = gibbs_inner
         self.plans, self.buffers = build_product_plans(dg.fg)
+        self.distributed, self.group = distributed, group
+        self.world, self.rank = 1, 0
+        if distributed:
+            import torch.distributed as dist
+            self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+            import torch
+            # collectives and kernels must be ordered on ONE stream: a dedicated torch stream that the ctx adopts
+            # (torch's default stream is handle 0, which rome_b200_set_stream reads as "use the ctx's own stream")
+            self.ctx.synchronize()  # uploads issued on the ctx's own stream land before the stream changes
+            self._tstream = torch.cuda.Stream(device=self.ctx.device)
+            self.ctx.set_stream(self._tstream.cuda_stream)
         Np = npad(self.N)
-        self._dev = []
+        self._dev, self._tensors = [], []
         for fam, which in self.buffers:
             d = FAMILY[fam][6] if which == "fwd" else FAMILY[fam][7]
             nF = self.ctx.num_factors(fam)
-            self._dev.append(self.ctx.malloc_device(max(1, nF * Np * d * 4)) if d else 0)
+            if not d:
+                self._dev.append(0)
+            elif distributed:
+                import torch
+                from .sharding import shard_size
+                t = torch.zeros((self.world * shard_size(nF, self.world), Np, d), dtype=torch.float32,
+                                device=torch.device("cuda", self.ctx.device))
+                self._tensors.append((len(self._dev), t, nF))
+                self._dev.append(t.data_ptr())
+            else:
+                self._dev.append(self.ctx.malloc_device(max(1, nF * Np * d * 4)))
         for t, (off, sb, sr) in self.plans.items():
             self.ctx.set_product_plan(t, off, sb, sr)
         self.families = sorted({f for f, _ in self.buffers})
         self.sweeps_done = 0
+        if distributed:
+            import torch
+            torch.cuda.synchronize(self.ctx.device)  # the zero-fill of the proposal tensors ran on another stream
 
     def close(self):
-        for p in self._dev:
-            if p:
-                self.ctx.free_device(p)
-        self._dev = []
+        if not self.distributed:
+            for p in self._dev:
+                if p:
+                    self.ctx.free_device(p)
+        else:
+            self.ctx.synchronize()
+            self.ctx.set_stream(None)
+        self._dev, self._tensors = [], []
 
     def sweep(self, seed: int = 0):
         """one synchronous sweep: every factor convolves (fused getSample + closed-form roots), then every variable
@@ -96,8 +130,18 @@ class GibbsSolver:
                 continue
             if k > 0:
                 flags |= L.INDEPENDENT  # the family kernels of one sweep read the same particles, write different buffers
-            c.eval(fam, flags, seed=seed, stream_id=self.sweeps_done, prop_fwd=self._dev[2 * k] or None,
-                   prop_bwd=self._dev[2 * k + 1] or None)
+            first, count = 0, -1
+            if self.distributed:
+                from .sharding import shard_range
+                first, count = shard_range(c.num_factors(fam), self.rank, self.world)
+            c.eval(fam, flags, seed=seed, stream_id=self.sweeps_done, first=first, count=count,
+                   prop_fwd=self._dev[2 * k] or None, prop_bwd=self._dev[2 * k + 1] or None)
+        if self.distributed:
+            import torch
+            from .sharding import allgather_rows
+            with torch.cuda.stream(self._tstream):
+                for _, t, nF in self._tensors:  # the one exchange of the path: every rank ends up with all proposal rows
+                    allgather_rows(t, nF, self.group)
         some = next(p for p in self._dev if p)
         ptrs = [p or some for p in self._dev]  # placeholders for absent directions are never indexed by the plan
         for t in self.plans:

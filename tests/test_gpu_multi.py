@@ -94,3 +94,51 @@ def test_two_gpu_exchange_nccl_and_fused():
     for p in ps:
         p.join(timeout=120)
     assert res == [(0, True, True), (1, True, True)], res
+
+
+def _sweep_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    import rome_b200 as rb
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        def graph():
+            fg = rb.generateGraph_ManhattanShaped(400, seed=2, N=100)  # same graph and particles on every rank
+            rb.seed_particles(fg, seed=1)
+            return fg
+        # single-GPU reference on this rank
+        dg0 = rb.DeviceGraph(graph(), ctx=rb.Context(rank), N=100)
+        gs0 = rb.GibbsSolver(dg0)
+        gs0.solve(2, seed=7)
+        ref = dg0.ctx.get_particles(rb.POSE2)
+        gs0.close()
+        # factor list sharded over the ranks, proposals all-gathered, products replicated
+        dg = rb.DeviceGraph(graph(), ctx=rb.Context(rank), N=100)
+        gs = rb.GibbsSolver(dg, distributed=True)
+        gs.solve(2, seed=7)
+        torch.cuda.synchronize()
+        got = dg.ctx.get_particles(rb.POSE2)
+        gs.close()
+        dist.barrier()
+        q.put((rank, bool(np.array_equal(got, ref)), float(np.abs(got - ref).max())))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_device_resident_sweeps_match_single_gpu():
+    """SURVEY 8e + 8f N2: sharded convolutions + all-gather of the proposals + replicated products leave every rank
+    with exactly the particles a single GPU computes"""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_sweep_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in ps)
+    for p in ps:
+        p.join(timeout=120)
+    assert [(r[0], r[1]) for r in res] == [(0, True), (1, True)], res
