@@ -136,6 +136,18 @@ __device__ __forceinline__ double sqrt_seeded(double a) {
     r = fma(-g, h, 0.5);
     return fma(g, r, g);
 }
+// A rotation has the rotation vectors w (1 - 2 pi k / |w|), k integer.  Particle coordinates are stored as offsets from
+// the variable's anchor, so the representative CLOSEST to the anchor is the one to keep (near |w| = pi the principal
+// vector of a neighbouring rotation sits on the far side of the ball).  Replaces (x, y, z) by the better of k = 0, 1.
+__device__ __forceinline__ void closest_rotvec(double& x, double& y, double& z, double ax, double ay, double az) {
+    const double t2 = x * x + y * y + z * z;
+    if (t2 < 1e-12) return;
+    const double f = 1.0 - kTwoPi * rsqrt(t2);
+    const double bx = x * f, by = y * f, bz = z * f;
+    const double d0 = (x - ax) * (x - ax) + (y - ay) * (y - ay) + (z - az) * (z - az);
+    const double d1 = (bx - ax) * (bx - ax) + (by - ay) * (by - ay) + (bz - az) * (bz - az);
+    if (d1 < d0) { x = bx; y = by; z = bz; }
+}
 // sin/cos of (anchor + x) given (ca, sa) = cos/sin(anchor): angle addition for small x, general path otherwise
 __device__ __forceinline__ void sincos_anchored(double anchor, double ca, double sa, double x, double& s, double& c) {
     if (fabs(x) <= kSmallAngle) {

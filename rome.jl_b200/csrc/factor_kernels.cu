@@ -137,13 +137,14 @@ __global__ void pack_kernel(int nvars, int N, int Npad, int wrap_dim, const doub
     }
     float* dst = reinterpret_cast<float*>(blk + var_header_bytes(D));
     for (int n = lane; n < Npad; n += 32) {
+        double x[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) x[c] = n < N ? src[(size_t)n * D + c] : a[c];
+        if (D == 6) closest_rotvec(x[3], x[4], x[5], a[3], a[4], a[5]);  // Pose3: rotation vector nearest the anchor's
 #pragma unroll
         for (int c = 0; c < D; ++c) {
-            double o = 0.0;
-            if (n < N) {
-                o = src[(size_t)n * D + c] - a[c];
-                if (c == wrap_dim) o = wrap_pi(o);
-            }
+            double o = x[c] - a[c];
+            if (c == wrap_dim) o = wrap_pi(o);
             dst[(size_t)n * D + c] = (float)o;
         }
     }
@@ -158,12 +159,15 @@ __global__ void unpack_kernel(int nvars, int N, int Npad, int wrap_dim, const un
     const float* src = reinterpret_cast<const float*>(blk + var_header_bytes(D));
     double* dst = coords + (size_t)v * N * D;
     for (int n = lane; n < N; n += 32) {
+        double x[D];
 #pragma unroll
         for (int c = 0; c < D; ++c) {
-            double x = hdr[c] + (double)src[(size_t)n * D + c];
-            if (c == wrap_dim) x = wrap_pi(x);
-            dst[(size_t)n * D + c] = x;
+            x[c] = hdr[c] + (double)src[(size_t)n * D + c];
+            if (c == wrap_dim) x[c] = wrap_pi(x[c]);
         }
+        if (D == 6) closest_rotvec(x[3], x[4], x[5], 0.0, 0.0, 0.0);  // Pose3: report the principal rotation vector
+#pragma unroll
+        for (int c = 0; c < D; ++c) dst[(size_t)n * D + c] = x[c];
     }
 }
 __global__ void adopt_kernel(int d, int Npad, unsigned char* __restrict__ store, int var,

@@ -110,6 +110,7 @@ struct FamPose3Pose3 {
                 if (flags & ROME_B200_PROPOSAL_FWD) {  // q = p o Exp(X): coordinates as offsets from q's anchor
                     double ox, oy, oz;
                     quat_log_any(Rh[j], ox, oy, oz);
+                    closest_rotvec(ox, oy, oz, aq[3], aq[4], aq[5]);
                     const float o[6] = {(float)h[j][0],      (float)h[j][1],      (float)h[j][2],
                                         (float)(ox - aq[3]), (float)(oy - aq[4]), (float)(oz - aq[5])};
                     if (live) store6(V.out_fwd + 6 * n, o);
@@ -120,6 +121,7 @@ struct FamPose3Pose3 {
                     double bx, by, bz, ox, oy, oz;
                     quat_rotate(Rb, X[j][0], X[j][1], X[j][2], bx, by, bz);
                     quat_log_any(Rb, ox, oy, oz);
+                    closest_rotvec(ox, oy, oz, ap[3], ap[4], ap[5]);
                     const float o[6] = {(float)(((double)q[j][0] - dax) - bx), (float)(((double)q[j][1] - day) - by),
                                         (float)(((double)q[j][2] - daz) - bz), (float)(ox - ap[3]),
                                         (float)(oy - ap[4]),                   (float)(oz - ap[5])};

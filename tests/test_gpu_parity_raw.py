@@ -287,7 +287,10 @@ def test_particle_roundtrip(ctx):
     assert np.abs(d).max() < 1e-6
     p3 = make_pose3(rng, 9, 100)
     ctx.set_particles(rb.POSE3, p3)
-    assert np.abs(ctx.get_particles(rb.POSE3) - p3).max() < 1e-6
+    back3 = ctx.get_particles(rb.POSE3)
+    assert np.abs(back3[..., :3] - p3[..., :3]).max() < 1e-6
+    assert rot_close(back3[..., 3:], p3[..., 3:], 1e-6)                 # the same rotations ...
+    assert np.linalg.norm(back3[..., 3:], axis=-1).max() <= np.pi + 1e-9  # ... reported as principal rotation vectors
 
 
 @pytest.mark.parametrize("family", ["pose2pose2", "priorpose2", "bearingrange", "pose3pose3", "priorpose3"])

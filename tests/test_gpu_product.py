@@ -142,3 +142,31 @@ def test_hexagonal_solve_reference_boxes(ctx):
     assert np.all(v3[:, :2].var(0) < 25)
     # the loop closure through :l1 ties :x6 back to :x0
     assert np.linalg.norm(rb.getVal(fg, "x6")[:, :2].mean(0)) < 1.5
+
+
+def test_sweeps_on_pose3_chain_and_beehive(ctx):
+    """device-resident sweeps over the other BASELINE graph shapes: SE(3) chain with loop closures (rotation-vector
+    coordinates treated as Euclidean inside the product) and Beehive (Pose2Pose2 + bearing-range + landmarks):
+    beliefs stay centred on the simulated truth and contract instead of diffusing"""
+    p3 = rb.generateGraph_Pose3Chain(60, loops=6)
+    rb.seed_particles(p3, seed=4, N=100)
+    truth = {l: v.simulated.copy() for l, v in p3.variables.items()}
+    spread0 = np.mean([v.val[:, :3].std(0).mean() for v in p3.variables.values()])
+    rb.solveGraphGibbs(p3, sweeps=3, seed=2, ctx=ctx)
+    err = np.array([np.abs(v.val.mean(0)[:3] - truth[l][:3]).max() for l, v in p3.variables.items()])
+    # mean rotation error in the tangent space at the truth (rotation vectors do not average across |w| = pi)
+    rot = np.array([np.abs(O.np_so3_log(O.np_so3_exp(truth[l][3:]).T @ O.np_so3_exp(v.val[:, 3:])).mean(0)).max()
+                    for l, v in p3.variables.items()])
+    spread1 = np.mean([v.val[:, :3].std(0).mean() for v in p3.variables.values()])
+    assert err.max() < 0.5 and rot.max() < 0.1, (err.max(), rot.max())
+    assert spread1 < 1.5 * spread0
+    bh = rb.generateGraph_Beehive(30, N=100)
+    rb.seed_particles(bh, seed=3, N=100)
+    truth = {l: v.simulated.copy() for l, v in bh.variables.items()}
+    rb.solveGraphGibbs(bh, sweeps=3, seed=4, ctx=ctx)
+    for l, v in bh.variables.items():
+        m = v.val.mean(0)
+        assert np.abs(m[:2] - truth[l][:2]).max() < 1.5, (l, m, truth[l])
+        if v.variableType is rb.Pose2:
+            th = np.arctan2(np.sin(v.val[:, 2]).mean(), np.cos(v.val[:, 2]).mean())
+            assert abs(O.np_wrap(th - truth[l][2])) < 0.3, (l, th, truth[l][2])
