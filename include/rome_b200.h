@@ -218,7 +218,8 @@ ROME_B200_API int rome_b200_eval_host_async(rome_b200_ctx* ctx, int family, uint
  * The plan lists, per variable (CSR `var_offsets[nvars+1]`), its sources: buffer index `src_buf` into the
  * `d_prop_bufs` array given to rome_b200_product, and proposal row `src_row` (the factor index) inside that buffer.
  * Rows must hold offsets from THAT variable's anchor (prop_fwd of factors whose last variable it is, prop_bwd of
- * factors whose first variable it is).  Variables without sources keep their particles; one source is adopted as is. */
+ * factors whose first variable it is) and `src_row` must lie inside the buffer passed at that index (not checked: the
+ * library does not know the buffers' sizes).  Variables without sources keep their particles; one source is adopted as is. */
 #define ROME_B200_MAX_PRODUCT_SOURCES 32 /* proposals per variable */
 #define ROME_B200_MAX_PRODUCT_BUFFERS 16 /* distinct proposal buffers per call */
 #define ROME_B200_PRODUCT_REANCHOR 1u    /* afterwards move every anchor onto the variable's new first particle */

@@ -105,6 +105,8 @@ class GibbsSolver:
             self.ctx.set_product_plan(t, off, sb, sr)
         self.families = sorted({f for f, _ in self.buffers})
         self.sweeps_done = 0
+        if not any(self._dev):
+            raise ValueError("no factor of this graph has a closed-form proposal: nothing to sweep")
         if distributed:
             import torch
             torch.cuda.synchronize(self.ctx.device)  # the zero-fill of the proposal tensors ran on another stream
