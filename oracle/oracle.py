@@ -60,6 +60,8 @@ def lib() -> C.CDLL:
         _lib.rome_oracle_sweep_bearingrange.argtypes = [C.c_int, C.c_int, i32, i32, d, d, d, d, C.c_int]
         _lib.rome_oracle_conv_nm_pose2pose2.argtypes = [C.c_int, C.c_int, i32, i32, d, d, C.c_int, C.c_int,
                                                         C.c_double, u64, d, C.POINTER(u64), C.c_int]
+        _lib.rome_oracle_product.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(d), C.c_int, C.c_int, u64, d]
+        _lib.rome_oracle_product_sweep.argtypes = [C.c_int, i32, i32, d, C.c_int, C.c_int, C.c_int, C.c_int, u64, d, C.c_int]
         _lib.rome_oracle_philox4x32_10.restype = None
         _lib.rome_oracle_philox4x32_10.argtypes = [C.POINTER(C.c_uint32)] * 3
         _lib.rome_oracle_normal4.restype = None
@@ -462,3 +464,27 @@ def product_gibbs(props, n_out, iters=3, wrap_dim=None, seed=0):
             x[wrap_dim] = np_wrap(x[wrap_dim])
         out[c] = x
     return out
+
+
+def product_c(props, n_out, iters=2, wrap_dim=None, seed=0):
+    """C twin of product_gibbs (oracle/rome_oracle.c rome_oracle_product): same algorithm, own RNG"""
+    props = [_f64(p) for p in props]
+    k, (N, d) = len(props), props[0].shape
+    ptrs = (C.POINTER(C.c_double) * k)(*[_dp(p) for p in props])
+    out = np.zeros((n_out, d))
+    rc = lib().rome_oracle_product(k, N, d, -1 if wrap_dim is None else wrap_dim, ptrs, n_out, iters, seed, _dp(out))
+    if rc != 0:
+        raise ValueError("rome_oracle_product: bad arguments")
+    return out
+
+
+def product_sweep_c(var_off, src_row, rows, wrap_dim=None, iters=2, seed=0, nthreads=0):
+    """all variables of one type at once (OpenMP over variables): rows [nrows][N][d] -> [nvars][N][d]"""
+    var_off, src_row, rows = _i32(var_off), _i32(src_row), _f64(rows)
+    _, N, d = rows.shape
+    out = np.zeros((len(var_off) - 1, N, d))
+    rc = lib().rome_oracle_product_sweep(len(var_off) - 1, _ip(var_off), _ip(src_row), _dp(rows), N, d,
+                                         -1 if wrap_dim is None else wrap_dim, iters, seed, _dp(out), nthreads)
+    if rc < 0:
+        raise ValueError("rome_oracle_product_sweep: bad arguments")
+    return out, rc

@@ -537,3 +537,164 @@ int rome_oracle_conv_nm_pose2pose2(int nF, int N, const int32_t* ip, const int32
     if (n_evals) *n_evals = total;
     return nt;
 }
+
+
+/* ================================================================================== */
+/* product of proposal KDEs -- PARITY UNPINNED: the reference's     */
+/* sampler (ApproxManifoldProducts / KernelDensityEstimate) is absent and stochastic; */
+/* this restates the algorithm of csrc/product_kernels.cu in Float64 with its own RNG */
+/* and is compared statistically (tests/test_oracle_golden.py, tests/test_gpu_product) */
+/* ================================================================================== */
+static inline uint64_t splitmix64(uint64_t* s) {
+    uint64_t z = (*s += 0x9e3779b97f4a7c15ULL);
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    return z ^ (z >> 31);
+}
+static inline double unif01(uint64_t* s) { return ((double)(splitmix64(s) >> 11) + 0.5) * (1.0 / 9007199254740992.0); }
+static inline double wrapd(double a) { return a - 6.283185307179586476925 * nearbyint(a * 0.15915494309189533577); }
+
+/* rule-of-thumb bandwidth per dimension (circular spread for wrap_dim); out: 1/h^2 */
+static void kde_precision(const double* x, int N, int d, int wrap_dim, double* w) {
+    const double scale = pow(4.0 / ((d + 2.0) * N), 1.0 / (d + 4.0));
+    for (int c = 0; c < d; ++c) {
+        double mean = 0.0;
+        if (c == wrap_dim) {
+            double sc = 0.0, ss = 0.0;
+            for (int i = 0; i < N; ++i) { sc += cos(x[i * d + c]); ss += sin(x[i * d + c]); }
+            mean = atan2(ss, sc);
+        } else {
+            for (int i = 0; i < N; ++i) mean += x[i * d + c];
+            mean /= N;
+        }
+        double v = 0.0;
+        for (int i = 0; i < N; ++i) {
+            double dl = x[i * d + c] - mean;
+            if (c == wrap_dim) dl = wrapd(dl);
+            v += dl * dl;
+        }
+        double h = sqrt(v / (N > 1 ? N - 1 : 1)) * scale;
+        if (h < 1e-6) h = 1e-6;
+        w[c] = 1.0 / (h * h);
+    }
+}
+#define ROME_ORACLE_MAXD 6
+#define ROME_ORACLE_MAXK 32
+static void fuse_sel(int k, int d, int wrap_dim, const double* const* props, const double* w, const int* sel, int upto,
+                     int skip, double* mu, double* var) {
+    double lam[ROME_ORACLE_MAXD] = {0}, s[ROME_ORACLE_MAXD] = {0}, ref = 0.0;
+    int have_ref = 0;
+    (void)k;
+    for (int j = 0; j < upto; ++j) {
+        if (j == skip) continue;
+        const double* x = props[j] + (size_t)sel[j] * d;
+        for (int c = 0; c < d; ++c) {
+            double v = x[c];
+            if (c == wrap_dim) {
+                if (!have_ref) { ref = v; have_ref = 1; }
+                v = ref + wrapd(v - ref);
+            }
+            lam[c] += w[j * d + c];
+            s[c] += w[j * d + c] * v;
+        }
+    }
+    for (int c = 0; c < d; ++c) { var[c] = 1.0 / lam[c]; mu[c] = s[c] * var[c]; }
+}
+static int draw_label(int N, int d, int wrap_dim, const double* x, const double* wj, const double* mu, const double* var,
+                      uint64_t* rng) {
+    double best = -1e300;
+    int arg = 0;
+    for (int i = 0; i < N; ++i) {
+        double q = 0.0;
+        for (int c = 0; c < d; ++c) {
+            double dl = x[i * d + c] - mu[c];
+            if (c == wrap_dim) dl = wrapd(dl);
+            q += -0.5 * dl * dl / (1.0 / wj[c] + var[c]);
+        }
+        const double key = q - log(-log(unif01(rng)));
+        if (key > best) { best = key; arg = i; }
+    }
+    return arg;
+}
+/* props: k pointers to [N][d] particle sets; out: [n_out][d] samples of the product of their KDEs */
+int rome_oracle_product(int k, int N, int d, int wrap_dim, const double* const* props, int n_out, int iters,
+                        uint64_t seed, double* out) {
+    if (k < 2 || k > ROME_ORACLE_MAXK || d > ROME_ORACLE_MAXD || N < 1) return -1;
+    double w[ROME_ORACLE_MAXK * ROME_ORACLE_MAXD];
+    for (int j = 0; j < k; ++j) kde_precision(props[j], N, d, wrap_dim, w + j * d);
+    /* exact pair stage: marginal weights of source-0 components over source 1 (log-sum-exp), CDF */
+    double* cdf = (double*)malloc(sizeof(double) * N);
+    double wmax = -1e300;
+    for (int a = 0; a < N; ++a) {
+        double m = -1e300, sum = 0.0;
+        for (int b = 0; b < N; ++b) {
+            double q = 0.0;
+            for (int c = 0; c < d; ++c) {
+                double dl = props[1][b * d + c] - props[0][a * d + c];
+                if (c == wrap_dim) dl = wrapd(dl);
+                q += -0.5 * dl * dl / (1.0 / w[c] + 1.0 / w[d + c]);
+            }
+            const double m2 = q > m ? q : m;
+            sum = sum * exp(m - m2) + exp(q - m2);
+            m = m2;
+        }
+        cdf[a] = m + log(sum);
+        if (cdf[a] > wmax) wmax = cdf[a];
+    }
+    double acc = 0.0;
+    for (int a = 0; a < N; ++a) { acc += exp(cdf[a] - wmax); cdf[a] = acc; }
+    uint64_t rng = seed * 0x9e3779b97f4a7c15ULL + 12345;
+    int sel[ROME_ORACLE_MAXK];
+    double mu[ROME_ORACLE_MAXD], var[ROME_ORACLE_MAXD];
+    for (int n = 0; n < n_out; ++n) {
+        const double target = unif01(&rng) * cdf[N - 1];
+        int lo = 0, hi = N - 1;
+        while (lo < hi) { const int mid = (lo + hi) / 2; if (cdf[mid] < target) lo = mid + 1; else hi = mid; }
+        sel[0] = lo;
+        fuse_sel(k, d, wrap_dim, props, w, sel, 1, -1, mu, var);
+        sel[1] = draw_label(N, d, wrap_dim, props[1], w + d, mu, var, &rng);
+        for (int j = 2; j < k; ++j) {
+            fuse_sel(k, d, wrap_dim, props, w, sel, j, -1, mu, var);
+            sel[j] = draw_label(N, d, wrap_dim, props[j], w + j * d, mu, var, &rng);
+        }
+        if (k > 2)
+            for (int t = 0; t < iters; ++t)
+                for (int j = 0; j < k; ++j) {
+                    fuse_sel(k, d, wrap_dim, props, w, sel, k, j, mu, var);
+                    sel[j] = draw_label(N, d, wrap_dim, props[j], w + j * d, mu, var, &rng);
+                }
+        fuse_sel(k, d, wrap_dim, props, w, sel, k, -1, mu, var);
+        for (int c = 0; c < d; c += 2) {  /* Box-Muller */
+            const double r = sqrt(-2.0 * log(unif01(&rng))), t = 6.283185307179586476925 * unif01(&rng);
+            double x0 = mu[c] + sqrt(var[c]) * r * cos(t);
+            if (c == wrap_dim) x0 = wrapd(x0);
+            out[(size_t)n * d + c] = x0;
+            if (c + 1 < d) {
+                double x1 = mu[c + 1] + sqrt(var[c + 1]) * r * sin(t);
+                if (c + 1 == wrap_dim) x1 = wrapd(x1);
+                out[(size_t)n * d + c + 1] = x1;
+            }
+        }
+    }
+    free(cdf);
+    return 0;
+}
+/* one sweep's worth of products: variable v multiplies rows src_row[var_off[v] .. var_off[v+1]) of `rows`
+ * ([nrows][N][d]); out [nvars][N][d]; variables with fewer than two sources are copied / left zero */
+int rome_oracle_product_sweep(int nvars, const int32_t* var_off, const int32_t* src_row, const double* rows, int N, int d,
+                              int wrap_dim, int iters, uint64_t seed, double* out, int nthreads) {
+    const int nt = set_threads(nthreads);
+    int bad = 0;
+#pragma omp parallel for schedule(dynamic, 16) num_threads(nt)
+    for (int v = 0; v < nvars; ++v) {
+        const int k = var_off[v + 1] - var_off[v];
+        double* o = out + (size_t)v * N * d;
+        if (k == 0) continue;
+        if (k == 1) { memcpy(o, rows + (size_t)src_row[var_off[v]] * N * d, sizeof(double) * N * d); continue; }
+        const double* props[ROME_ORACLE_MAXK];
+        if (k > ROME_ORACLE_MAXK) { bad = 1; continue; }
+        for (int j = 0; j < k; ++j) props[j] = rows + (size_t)src_row[var_off[v] + j] * N * d;
+        if (rome_oracle_product(k, N, d, wrap_dim, props, N, iters, seed + (uint64_t)v, o)) bad = 1;
+    }
+    return bad ? -1 : nt;
+}

@@ -117,6 +117,12 @@ void rome_oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uin
 void rome_oracle_normal4(uint64_t seed, uint32_t stream, uint32_t factor, uint32_t particle,
                          uint32_t block, double z[4]);
 
+/* ---- product of proposal KDEs (PARITY UNPINNED, statistical checks only) ---- */
+int rome_oracle_product(int k, int N, int d, int wrap_dim, const double* const* props, int n_out, int iters,
+                        uint64_t seed, double* out);
+int rome_oracle_product_sweep(int nvars, const int32_t* var_off, const int32_t* src_row, const double* rows, int N, int d,
+                              int wrap_dim, int iters, uint64_t seed, double* out, int nthreads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -228,3 +228,49 @@ def test_next_row_3d_families(ka):
         d = O.pose3pose3xyyaw(X3, P3, Q3) - O.pose2pose2(X3, p2, q2)
         d[2] = O.np_wrap(d[2])
         assert np.allclose(d, 0, atol=1e-12)
+
+
+def test_product_twins_match_the_exact_mixture():
+    """SURVEY 8f N2 (parity unpinned, statistical): the C and NumPy product samplers reproduce the mean and variance of the
+    exact product mixture (N^2 resp. N^3 components enumerated) of two and three KDEs, and wrap headings correctly"""
+    rng = np.random.default_rng(0)
+    N = 80
+    a, b, c = 1.0 + 0.5 * rng.normal(size=(N, 2)), -0.4 + 0.8 * rng.normal(size=(N, 2)), 0.5 + 0.6 * rng.normal(size=(N, 2))
+    h2 = [O.kde_bandwidth(p) ** 2 for p in (a, b, c)]
+
+    def exact(props, hh):
+        k = len(props)
+        lam = sum(1.0 / h for h in hh)
+        if k == 2:
+            mu = (props[0][:, None] / hh[0] + props[1][None] / hh[1]) / lam
+            lw = -0.5 * ((props[0][:, None] - props[1][None]) ** 2 / (hh[0] + hh[1])).sum(-1)
+        else:
+            A, B, Cc = props
+            mu = (A[:, None, None] / hh[0] + B[None, :, None] / hh[1] + Cc[None, None, :] / hh[2]) / lam
+            lw = -0.5 * ((A ** 2 / hh[0]).sum(-1)[:, None, None] + (B ** 2 / hh[1]).sum(-1)[None, :, None]
+                         + (Cc ** 2 / hh[2]).sum(-1)[None, None, :] - (mu ** 2 * lam).sum(-1))
+        w = np.exp(lw - lw.max())
+        w /= w.sum()
+        ax = tuple(range(k))
+        m = (w[..., None] * mu).sum(ax)
+        return m, (w[..., None] * mu ** 2).sum(ax) - m ** 2 + 1.0 / lam
+
+    for props, hh in (([a, b], h2[:2]), ([a, b, c], h2)):
+        m, v = exact(props, hh)
+        xc = np.concatenate([O.product_c(props, 1500, seed=s) for s in range(2)])
+        xn = O.product_gibbs(props, 600, iters=2, seed=3)
+        for x, tol in ((xc, 0.035), (xn, 0.06)):
+            assert np.allclose(x.mean(0), m, atol=tol), (x.mean(0), m)
+            assert np.allclose(x.var(0), v, rtol=0.2), (x.var(0), v)
+    # headings on both sides of the cut
+    th1 = O.np_wrap(np.pi - 0.05 + 0.1 * rng.normal(size=(N, 1)))
+    th2 = O.np_wrap(-np.pi + 0.08 + 0.1 * rng.normal(size=(N, 1)))
+    p1, p2 = np.hstack([rng.normal(size=(N, 2)) * 0.3 + 1, th1]), np.hstack([rng.normal(size=(N, 2)) * 0.3 + 1.2, th2])
+    x = O.product_c([p1, p2], 800, wrap_dim=2, seed=1)
+    circ = np.arctan2(np.sin(x[:, 2]).mean(), np.cos(x[:, 2]).mean())
+    assert abs(O.np_wrap(circ - (np.pi + 0.015))) < 0.04 and np.abs(O.np_wrap(x[:, 2] - np.pi)).max() < 0.6
+    # the sweep entry point: CSR plan, variables with 0 / 1 / 2 sources
+    rows = np.stack([a, b, c])
+    out, nt = O.product_sweep_c([0, 2, 3, 3], [0, 1, 2], rows, seed=5)
+    assert nt >= 1 and np.array_equal(out[1], c) and not out[2].any()
+    assert np.allclose(out[0].mean(0), exact([a, b], h2[:2])[0], atol=0.15)
