@@ -274,10 +274,122 @@ __global__ void __launch_bounds__((FT + 1) * 32, Fam::kMinCtas) eval_kernel(cons
     // a launch that overlapped its predecessor must not be seen as complete before the predecessor is
     if (P.flags & ROME_B200_INDEPENDENT) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
+// =============================================================================================
+// per-warp pipeline ("warp pipeline"): no producer warp and no CTA-wide barrier.  Warp w of a CTA owns slot w of
+// every tile the CTA visits and runs its own S-deep ring: lane s keeps the variable ids of the factor destined for
+// stage s (fetched one factor ahead, behind the arithmetic) and issues that factor's four bulk copies (table row,
+// the two particle blocks, the measurement block) onto the (warp, stage) mbarrier as soon as the warp has finished
+// the factor that occupied the stage.  All registers of the CTA belong to consumer warps, so the SE(3) families run
+// 12 warps x 168 registers per SM instead of 8 + producer, and warps never wait for each other.  Built for the Pose3
+// families only (Fam::kWarpFT): measured 6 % faster there; for the SE(2) families (96 registers, two CTAs per SM) the
+// producer-warp pipeline with its CTA-wide stages is as fast at N = 100 and clearly faster at N = 200.
+//   smem: [bar[FT][kMaxStages] | FT x (S slots + output slice)]
+// =============================================================================================
+struct SlotLayout {
+    int row_off, v0_off, v1_off, meas_off, bytes, b0, b1, mb;
+};
+__host__ __device__ inline SlotLayout slot_layout(int row_bytes, int d0, int d1, int dm, bool sample, int Npad) {
+    SlotLayout L;
+    L.b0 = var_block_bytes(d0, Npad);
+    L.b1 = d1 ? var_block_bytes(d1, Npad) : 0;
+    L.mb = sample ? 0 : dm * Npad * 4;
+    L.row_off = 0;
+    L.v0_off = (row_bytes + 15) / 16 * 16;
+    L.v1_off = L.v0_off + L.b0;
+    L.meas_off = L.v1_off + L.b1;
+    L.bytes = (L.meas_off + L.mb + 127) / 128 * 128;
+    return L;
+}
 template <class Fam, uint32_t kStatic, bool kSample, int FT>
-int launch_ft(const EvalParams& p, const LaunchPlan& plan, int grid, cudaStream_t s) {
-    auto k = eval_kernel<Fam, kStatic, kSample, FT>;
-    static int configured[64] = {0};  // per-instantiation, per-device cache of the opt-in shared memory size
+__global__ void __launch_bounds__(FT * 32, Fam::kMinCtas) eval_kernel_w(const __grid_constant__ EvalParams P) {
+    using Row = typename Fam::Row;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int S = P.stages;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem) + warp * kMaxStages;
+    const SlotLayout L = slot_layout((int)sizeof(Row), Fam::D0, Fam::D1, Fam::DM, kSample, P.Npad);
+    const int warp_bytes = S * L.bytes + P.out_warp_bytes;
+    unsigned char* slots = smem + ((FT * kMaxStages * 8 + 127) / 128 * 128) + (size_t)warp * warp_bytes;
+    float* out = reinterpret_cast<float*>(slots + (size_t)S * L.bytes);
+    const Row* __restrict__ table = reinterpret_cast<const Row*>(P.rows) + P.first;
+    const uint32_t flags = kStatic ? kStatic : P.flags;
+    const int res_floats = Fam::DR * P.Npad;
+    // the i-th factor of this warp: tile blockIdx.x + i * gridDim.x, slot `warp`
+    auto factor_of = [&](int i) { return (blockIdx.x + i * (int)gridDim.x) * FT + warp; };
+    auto fetch_ids = [&](int i) {
+        const int fl = factor_of(i);
+        return fl < P.count ? __ldg(reinterpret_cast<const int2*>(table + fl)) : make_int2(0, 0);
+    };
+    auto issue = [&](int i, int s, int2 ids) {  // one lane: bulk copies of factor i into stage s
+        const int fl = factor_of(i);
+        if (fl >= P.count) return;
+        unsigned char* st = slots + (size_t)s * L.bytes;
+        fence_proxy_async();
+        mbar_arrive_expect_tx(&bar[s], (uint32_t)((int)sizeof(Row) + L.b0 + L.b1 + L.mb));
+        tma_load_1d(st + L.row_off, table + fl, (uint32_t)sizeof(Row), &bar[s]);
+        tma_load_1d(st + L.v0_off, P.v0 + (size_t)ids.x * L.b0, (uint32_t)L.b0, &bar[s]);
+        if (Fam::D1) tma_load_1d(st + L.v1_off, P.v1 + (size_t)ids.y * L.b1, (uint32_t)L.b1, &bar[s]);
+        if (!kSample)
+            tma_load_1d(st + L.meas_off, P.meas + (size_t)(P.first + fl) * Fam::DM * P.Npad, (uint32_t)L.mb, &bar[s]);
+    };
+    // prologue: lane s < S fetches the ids of factor s and fills stage s (all stages in flight after one load latency)
+    int2 ids = make_int2(0, 0);
+    if (lane < S) ids = fetch_ids(lane);
+    if (lane == 0) {
+        for (int s = 0; s < S; ++s) mbar_init(&bar[s], 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    if (lane < S) issue(lane, lane, ids);
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+    int s = 0;
+    uint32_t phase = 0;
+    for (int i = 0;; ++i) {
+        const int fl = factor_of(i);
+        if (fl >= P.count) break;
+        if (lane == s) ids = fetch_ids(i + S);  // consumed when this factor is done: hidden behind its arithmetic
+        mbar_wait(&bar[s], phase);
+        const unsigned char* st = slots + (size_t)s * L.bytes;
+        const int f = P.first + fl;
+        const Row row = *reinterpret_cast<const Row*>(st + L.row_off);
+        FactorView V;
+        V.b0 = st + L.v0_off;
+        V.b1 = Fam::D1 ? st + L.v1_off : nullptr;
+        V.meas = kSample ? nullptr : reinterpret_cast<const float*>(st + L.meas_off);
+        V.out_res = out;
+        V.out_fwd = out + res_floats;
+        if (flags & (ROME_B200_RESIDUAL | ROME_B200_PROPOSAL_FWD)) {
+            if (lane == 0) tma_store_wait_read();  // the previous factor's rows have left the slice
+            __syncwarp();
+        }
+        Fam::template factor<kStatic, kSample>(row, P, V, f, lane);
+        if (flags & (ROME_B200_RESIDUAL | ROME_B200_PROPOSAL_FWD)) {
+            fence_proxy_async();  // generic-proxy writes of the slice -> visible to the bulk-copy engine
+            __syncwarp();
+            if (lane == 0) {
+                if (flags & ROME_B200_RESIDUAL)
+                    tma_store_1d(P.res + (size_t)f * res_floats, V.out_res, (uint32_t)(res_floats * 4));
+                if (flags & ROME_B200_PROPOSAL_FWD) {
+                    const size_t off = (size_t)f * Fam::DFWD * P.Npad;
+                    const uint32_t bytes = (uint32_t)(Fam::DFWD * P.Npad * 4);
+                    tma_store_1d(P.prop_fwd + off, V.out_fwd, bytes);
+                    for (int r = 0; r < P.n_peers; ++r) tma_store_1d(P.peer_fwd[r] + off, V.out_fwd, bytes);
+                }
+                tma_store_commit();
+            }
+        }
+        __syncwarp();  // every lane has finished reading stage s
+        if (lane == s) issue(i + S, s, ids);
+        if (++s == S) { s = 0; phase ^= 1u; }
+    }
+    if (lane == 0) tma_store_wait_all();
+    if (P.flags & ROME_B200_INDEPENDENT) asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+template <class K>
+int launch_kernel_cfg(K k, int* configured, int threads, const EvalParams& p, const LaunchPlan& plan, int grid,
+                      cudaStream_t s) {
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || plan.smem_bytes > configured[dev]) {
@@ -287,7 +399,7 @@ int launch_ft(const EvalParams& p, const LaunchPlan& plan, int grid, cudaStream_
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3((FT + 1) * 32);
+    cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = plan.smem_bytes;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
@@ -297,9 +409,30 @@ int launch_ft(const EvalParams& p, const LaunchPlan& plan, int grid, cudaStream_
     cfg.numAttrs = (p.flags & ROME_B200_INDEPENDENT) ? 1 : 0;
     return (int)cudaLaunchKernelEx(&cfg, k, p);
 }
+template <class Fam, uint32_t kStatic, bool kSample, int FT>
+int launch_ft(const EvalParams& p, const LaunchPlan& plan, int grid, cudaStream_t s) {
+    static int configured[64] = {0};  // per-instantiation, per-device cache of the opt-in shared memory size
+    return launch_kernel_cfg(eval_kernel<Fam, kStatic, kSample, FT>, configured, (FT + 1) * 32, p, plan, grid, s);
+}
+template <class Fam, uint32_t kStatic, bool kSample, int FT>
+int launch_ft_w(const EvalParams& p, const LaunchPlan& plan, int grid, cudaStream_t s) {
+    static int configured[64] = {0};
+    return launch_kernel_cfg(eval_kernel_w<Fam, kStatic, kSample, FT>, configured, FT * 32, p, plan, grid, s);
+}
 template <class Fam, bool kSample>
 int launch_sample(const EvalParams& p, const LaunchPlan& plan, int grid, cudaStream_t s) {
     constexpr uint32_t smp = kSample ? ROME_B200_SAMPLE : 0u;
+    if constexpr (Fam::kWarpFT > 0) {  // families with a per-warp-pipeline build (Fam::kWarpFT warps per CTA)
+        if (plan.pipeline == 1) {
+            constexpr int W = Fam::kWarpFT;
+            if (plan.ft != W) return (int)cudaErrorInvalidValue;
+            if (plan.variant == 1) return launch_ft_w<Fam, kHot1 | smp, kSample, W>(p, plan, grid, s);
+            if (plan.variant == 2) return launch_ft_w<Fam, kHot2 | smp, kSample, W>(p, plan, grid, s);
+            return launch_ft_w<Fam, 0u, kSample, W>(p, plan, grid, s);
+        }
+    } else if (plan.pipeline == 1) {
+        return (int)cudaErrorInvalidValue;
+    }
     if (plan.ft == 8) {
         if (plan.variant == 1) return launch_ft<Fam, kHot1 | smp, kSample, 8>(p, plan, grid, s);
         if (plan.variant == 2) return launch_ft<Fam, kHot2 | smp, kSample, 8>(p, plan, grid, s);
@@ -314,4 +447,5 @@ int launch_family(const EvalParams& p, const LaunchPlan& plan, int grid, cudaStr
     return (p.flags & ROME_B200_SAMPLE) ? launch_sample<Fam, true>(p, plan, grid, s)
                                         : launch_sample<Fam, false>(p, plan, grid, s);
 }
+
 }  // namespace rome

@@ -56,6 +56,16 @@ static int min_stages_2cta() {
     return v;
 }
 
+// pipeline selection for the Pose3 families: per-warp pipelines unless ROME_B200_PIPELINE=cta
+static int pipeline_choice() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("ROME_B200_PIPELINE");
+        v = (e && e[0] == 'c') ? 0 : 1;
+    }
+    return v;
+}
+
 int plan_launch(int family, uint32_t flags, int Npad, int smem_per_sm, int smem_per_cta_max, LaunchPlan* plan) {
     const FamDims fd = fam_dims(family);
     const bool sample = (flags & ROME_B200_SAMPLE) != 0;
@@ -63,6 +73,27 @@ int plan_launch(int family, uint32_t flags, int Npad, int smem_per_sm, int smem_
     if (fd.dfwd == 0) flags &= ~ROME_B200_PROPOSAL_FWD;
     const uint32_t out_flags = flags & ~(ROME_B200_SAMPLE | ROME_B200_INDEPENDENT);
     const int hot = out_flags == kHot1 ? 1 : out_flags == kHot2 ? 2 : 0;
+    plan->pipeline = 0;
+    if (se3 && pipeline_choice() == 1) {
+        // per-warp pipelines: W warps per CTA, each with its own ring of `stages` slots + output slice
+        const int W = 12;
+        const int out_warp = (fd.dr + (hot == 1 ? 0 : fd.dfwd)) * Npad * 4;
+        const SlotLayout L = slot_layout(fd.row_bytes, fd.d0, fd.d1, fd.dm, sample, Npad);
+        const int bar_bytes = (W * kMaxStages * 8 + 127) / 128 * 128;
+        for (int ctas = (se3 ? 1 : 2); ctas >= 1; --ctas) {
+            const int budget = (smem_per_sm / ctas) - 1024;
+            const int cap = budget < smem_per_cta_max ? budget : smem_per_cta_max;
+            int stages = (cap - bar_bytes - W * out_warp) / (W * L.bytes);
+            if (stages > 4) stages = 4;
+            if (stages >= 2) {
+                plan->pipeline = 1; plan->ft = W; plan->variant = hot; plan->stages = stages;
+                plan->stage_bytes = L.bytes; plan->out_warp_bytes = out_warp;
+                plan->smem_bytes = bar_bytes + W * (stages * L.bytes + out_warp);
+                plan->ctas_per_sm = ctas;
+                return 0;
+            }
+        }
+    }
     static const int fts[3] = {8, 2, 1};
     for (int k = 0; k < 3; ++k) {
         const int ft = fts[k];

@@ -20,7 +20,7 @@ namespace rome {
 template <int KIND>  // 0 prior, 1 point-point, 2 pose-point
 struct FamPoint2Gauss {
     using Row = RowPT2;
-    static constexpr int D0 = KIND == 2 ? 3 : 2, D1 = KIND == 0 ? 0 : 2, DM = 2, DR = 2, DFWD = 2, kMinCtas = 2;
+    static constexpr int D0 = KIND == 2 ? 3 : 2, D1 = KIND == 0 ? 0 : 2, DM = 2, DR = 2, DFWD = 2, kMinCtas = 2, kWarpFT = 0;
     template <uint32_t kStatic, bool kSample>
     static __device__ __forceinline__ void factor(const Row& row, const EvalParams& P, const FactorView& V, int f,
                                                   int lane) {
@@ -97,7 +97,7 @@ struct FamPoint2Gauss {
 template <int KIND>
 struct FamScalar {
     using Row = RowS1;
-    static constexpr int D0 = KIND == 1 ? 2 : 3, D1 = 2, DM = 1, DR = 1, DFWD = 0, kMinCtas = 2;
+    static constexpr int D0 = KIND == 1 ? 2 : 3, D1 = 2, DM = 1, DR = 1, DFWD = 0, kMinCtas = 2, kWarpFT = 0;
     template <uint32_t kStatic, bool kSample>
     static __device__ __forceinline__ void factor(const Row& row, const EvalParams& P, const FactorView& V, int f,
                                                   int lane) {

@@ -19,7 +19,7 @@ namespace rome {
 template <int KIND>  // 0 prior, 1 point-point
 struct FamPoint3Gauss {
     using Row = RowSE2;
-    static constexpr int D0 = 3, D1 = KIND == 0 ? 0 : 3, DM = 3, DR = 3, DFWD = 3, kMinCtas = 2;
+    static constexpr int D0 = 3, D1 = KIND == 0 ? 0 : 3, DM = 3, DR = 3, DFWD = 3, kMinCtas = 2, kWarpFT = 0;
     template <uint32_t kStatic, bool kSample>
     static __device__ __forceinline__ void factor(const Row& row, const EvalParams& P, const FactorView& V, int f,
                                                   int lane) {

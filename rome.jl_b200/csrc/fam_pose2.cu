@@ -17,7 +17,7 @@ namespace rome {
 
 struct FamPose2Pose2 {
     using Row = RowSE2;
-    static constexpr int D0 = 3, D1 = 3, DM = 3, DR = 3, DFWD = 3, kMinCtas = 2;
+    static constexpr int D0 = 3, D1 = 3, DM = 3, DR = 3, DFWD = 3, kMinCtas = 2, kWarpFT = 0;
     template <uint32_t kStatic, bool kSample>
     static __device__ __forceinline__ void factor(const Row& row, const EvalParams& P, const FactorView& V, int f,
                                                   int lane) {
@@ -116,7 +116,7 @@ struct FamPose2Pose2 {
 // PriorPose2: r = (m.t - p.t, wrap(m.theta - p.theta)); proposal = the sampled point m
 struct FamPriorPose2 {
     using Row = RowSE2;
-    static constexpr int D0 = 3, D1 = 0, DM = 3, DR = 3, DFWD = 3, kMinCtas = 2;
+    static constexpr int D0 = 3, D1 = 0, DM = 3, DR = 3, DFWD = 3, kMinCtas = 2, kWarpFT = 0;
     template <uint32_t kStatic, bool kSample>
     static __device__ __forceinline__ void factor(const Row& row, const EvalParams& P, const FactorView& V, int f,
                                                   int lane) {

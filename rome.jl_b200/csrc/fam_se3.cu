@@ -7,7 +7,7 @@ namespace rome {
 
 struct FamPose3Pose3 {
     using Row = RowSE3;
-    static constexpr int D0 = 6, D1 = 6, DM = 6, DR = 6, DFWD = 6, kMinCtas = 1;
+    static constexpr int D0 = 6, D1 = 6, DM = 6, DR = 6, DFWD = 6, kMinCtas = 1, kWarpFT = 12;
     template <uint32_t kStatic, bool kSample>
     static __device__ __forceinline__ void factor(const Row& row, const EvalParams& P, const FactorView& V, int f,
                                                   int lane) {
@@ -139,7 +139,7 @@ struct FamPose3Pose3 {
 
 struct FamPriorPose3 {
     using Row = RowSE3;
-    static constexpr int D0 = 6, D1 = 0, DM = 6, DR = 6, DFWD = 6, kMinCtas = 1;
+    static constexpr int D0 = 6, D1 = 0, DM = 6, DR = 6, DFWD = 6, kMinCtas = 1, kWarpFT = 12;
     template <uint32_t kStatic, bool kSample>
     static __device__ __forceinline__ void factor(const Row& row, const EvalParams& P, const FactorView& V, int f,
                                                   int lane) {

@@ -34,7 +34,7 @@ __device__ __forceinline__ void yaw_dir(const Quat& q, double& c, double& s) {
 template <int KIND>  // 0 XYYaw, 1 Rotation
 struct FamPose3Partial {
     using Row = RowSE2;
-    static constexpr int D0 = 6, D1 = 6, DM = 3, DR = 3, DFWD = 0, kMinCtas = 1;
+    static constexpr int D0 = 6, D1 = 6, DM = 3, DR = 3, DFWD = 0, kMinCtas = 1, kWarpFT = 12;
     template <uint32_t kStatic, bool kSample>
     static __device__ __forceinline__ void factor(const Row& row, const EvalParams& P, const FactorView& V, int f,
                                                   int lane) {
@@ -92,7 +92,7 @@ struct FamPose3Partial {
 
 struct FamPose3Pose3UnitTrans {
     using Row = RowSE3;
-    static constexpr int D0 = 6, D1 = 6, DM = 6, DR = 6, DFWD = 0, kMinCtas = 1;
+    static constexpr int D0 = 6, D1 = 6, DM = 6, DR = 6, DFWD = 0, kMinCtas = 1, kWarpFT = 12;
     template <uint32_t kStatic, bool kSample>
     static __device__ __forceinline__ void factor(const Row& row, const EvalParams& P, const FactorView& V, int f,
                                                   int lane) {

@@ -106,6 +106,7 @@ struct LaunchPlan {
     int out_warp_bytes;
     int smem_bytes;   // dynamic shared memory per CTA
     int ctas_per_sm;
+    int pipeline;     // 0: producer warp + CTA-wide stages; 1: per-warp pipelines (no producer warp)
 };
 
 int plan_launch(int family, uint32_t flags, int Npad, int smem_per_sm, int smem_per_cta_max, LaunchPlan* plan);
