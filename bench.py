@@ -286,10 +286,15 @@ def main():
     ap.add_argument("--no-overlap", action="store_true", help="do not let consecutive (independent) steps overlap")
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
                     help="N>1: proposals reach the peers by the kernel's own TMA stores (fused) or by an NCCL all-gather")
+    ap.add_argument("--barrier", default="auto", choices=["auto", "flags", "nccl"],
+                    help="fused exchange: rank barrier by the GPUs' own flag kernels over NVLink (flags) or a 4-byte NCCL "
+                         "all-reduce (nccl); auto = flags at 2 GPUs (validated there), nccl above")
     ap.add_argument("--e2e-steps", type=int, default=40)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.barrier == "auto":
+        args.barrier = "flags" if int(os.environ.get("WORLD_SIZE", "1")) == 2 else "nccl"
 
     # stdout must carry exactly one JSON line: park fd 1 on stderr while libraries (NCCL prints its version banner to
     # stdout) initialise and run; it is restored just before the line is printed
@@ -345,6 +350,16 @@ def main():
                 c.set_peer_proposals(rb.POSE2POSE2, [c.ipc_import(everyone[r][si][0]) for r in range(G) if r != rank])
                 c.set_peer_proposals(rb.PRIORPOSE2, [c.ipc_import(everyone[r][si][1]) for r in range(G) if r != rank])
             token = torch.zeros(1, device="cuda")
+            # GPU-side barrier state: one flag array per rank; peer p owns slot dense(p) = p if p < rank else p - 1
+            c0 = sets[0][0]
+            state = c0.peer_state_alloc()
+            states = [None] * G
+            dist.all_gather_object(states, c0.ipc_export(state))
+            peer_slots = []
+            for p in range(G):
+                if p != rank:
+                    base = c0.ipc_import(states[p])
+                    peer_slots.append(base + 4 * (rank if rank < p else rank - 1))
             dist.barrier()
 
     n_prior = len(w["pr_ip"]) // G
@@ -375,8 +390,13 @@ def main():
                 if args.exchange == "nccl":  # the one exchange of the path: every rank's proposals to every rank
                     sharding.allgather_rows(bufs["prop_fwd"], F)
                     sharding.allgather_rows(pb["prop_fwd"], len(w["pr_ip"]))
-                else:  # the kernels already stored their rows into every peer: a stream-ordered barrier is left
+                elif args.barrier == "nccl":  # the kernels already stored their rows into every peer: a barrier is left
                     dist.all_reduce(token)
+                else:  # ... carried by two one-warp kernels over NVLink peer memory (they co-reside with the next step)
+                    c.set_stream(side.cuda_stream)
+                    c.peer_signal(state, peer_slots)
+                    c.peer_wait(state, G - 1)
+                    c.set_stream(stream.cuda_stream)
 
     def kernel_only(k, indep):
         c, bufs, _ = sets[k % S]
@@ -546,7 +566,9 @@ def main():
                        "factors_per_gpu": F0 + n_prior, "evals_per_step": evals_per_step,
                        "step": "getSample (in-kernel Philox) + residual + per-factor stats for every factor x particle"
                                + (("; + closed-form proposals, stored by the kernel's own TMA bulk stores into every peer GPU over NVLink "
-                                  "(fused all-gather) + a 4-byte NCCL all-reduce as barrier" if args.exchange == "fused" else
+                                  "(fused all-gather) + " + ("a GPU-side flag barrier over peer memory (rome_b200_peer_signal/wait)"
+                                                             if args.barrier == "flags" else "a 4-byte NCCL all-reduce as barrier")
+                                  if args.exchange == "fused" else
                                   "; + closed-form proposals and one NCCL all-gather of them") if multi else ""),
                        "storage": "anchored float32 (Float64 anchor + float32 offset)",
                        "l2": f"{S} rotating working-set copies (> 2x L2); K steps replayed from one CUDA graph",
@@ -573,7 +595,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * edt / args.e2e_steps, "steps": args.e2e_steps,
                     "api": "rome_b200_set_particles(pinned host f64) + rome_b200_eval_host_async(pinned host f32 outputs), two contexts alternating so upload and download overlap"},
-            "gpu_launches": 2 * args.steps,
+            "gpu_launches": (2 + (2 if multi and args.exchange == "fused" and args.barrier == "flags" else 0)) * args.steps,
             "clocks": clocks.summary(window),
         }
         if not args.no_cpu and G == 1:

@@ -238,10 +238,26 @@ ROME_B200_API int rome_b200_reanchor(rome_b200_ctx* ctx, int vartype);
  * proposals -- no separate all-gather pass; only a stream-ordered barrier between the ranks is still needed.
  * n_peers <= 7; n_peers = 0 clears. */
 ROME_B200_API int rome_b200_set_peer_proposals(rome_b200_ctx* ctx, int family, int n_peers, float* const* peer_prop_fwd);
-/* CUDA IPC plumbing for buffers allocated with rome_b200_malloc_device (64-byte opaque handles). */
+/* CUDA IPC plumbing for buffers allocated with rome_b200_malloc_device (64-byte opaque handles).  Only such buffers may
+ * be exported: rome_b200_malloc_device hands out whole 2 MiB blocks, so the handle (which names the driver's block) and
+ * the buffer coincide; a pointer into a packed small cudaMalloc allocation would be opened at the wrong address. */
 ROME_B200_API int rome_b200_ipc_export(rome_b200_ctx* ctx, void* dev_ptr, unsigned char handle[64]);
 ROME_B200_API int rome_b200_ipc_import(rome_b200_ctx* ctx, const unsigned char handle[64], void** dev_ptr);
 ROME_B200_API int rome_b200_ipc_close(rome_b200_ctx* ctx, void* dev_ptr);
+
+/* Stream-ordered barrier between the ranks, carried by the GPUs over NVLink peer memory (closes the fused exchange: no
+ * NCCL kernel, no host round trip).  `d_state` = one device buffer per rank of ROME_B200_PEER_STATE_WORDS uint32 words
+ * from rome_b200_malloc_device, ZEROED by the caller (rome_b200_memcpy_h2d): words [0, 8) are the flag slots the peers
+ * write, word 8 / 9 the signal / wait epochs, word 10 the give-up status.  `peer_slots[r]` = device pointer to the slot
+ * THIS rank owns inside peer r's state buffer (rome_b200_ipc_import of the peer's buffer + 4 * my_slot).
+ * rome_b200_peer_signal: after everything enqueued so far on the ctx stream, publish the next epoch to every peer.
+ * rome_b200_peer_wait: the stream continues once every one of the `n_slots` listed local slots has reached this rank's
+ * next wait epoch; gives up after ~2 s (a peer died) and sets the status word, read by rome_b200_peer_status.
+ * Epochs live on the device, so both calls may be captured in a CUDA graph and replayed. */
+#define ROME_B200_PEER_STATE_WORDS 16
+ROME_B200_API int rome_b200_peer_signal(rome_b200_ctx* ctx, void* d_state, uint32_t* const* peer_slots, int n_peers);
+ROME_B200_API int rome_b200_peer_wait(rome_b200_ctx* ctx, void* d_state, const int32_t* slots, int n_slots);
+ROME_B200_API int rome_b200_peer_status(rome_b200_ctx* ctx, void* d_state, int* gave_up);
 
 /* ---- CUDA-graph capture of a sweep (several eval calls replayed with one launch) ------------- */
 ROME_B200_API int rome_b200_graph_begin(rome_b200_ctx* ctx);

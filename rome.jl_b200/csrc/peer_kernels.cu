@@ -1,0 +1,59 @@
+// peer_kernels.cu -- stream-ordered barrier between the ranks of a multi-GPU job, carried by the GPUs themselves over
+// NVLink peer memory (no NCCL kernel, no host round trip).  It closes the fused exchange of the factor kernels: their
+// TMA bulk stores have already put the proposal rows into every peer's buffer; what is left is to tell the peers
+// "everything of my step e has landed" and to learn the same from them.
+//   signal: e = ++(*epoch); st.release.sys e -> the slot this rank owns in every peer's flag array
+//   wait:   e = ++(*epoch); spin (ld.acquire.sys, nanosleep back-off) until every local slot >= e
+// Both epochs live in device memory, so a captured CUDA graph can be replayed: each replay continues the sequence.
+// One tiny CTA each: it co-resides with the persistent factor kernels instead of queueing behind them.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rome {
+
+struct PeerSlots {
+    uint32_t* slot[8];
+};
+
+__global__ void peer_signal_kernel(PeerSlots peers, int n_peers, uint32_t* epoch) {
+    __shared__ uint32_t e;
+    if (threadIdx.x == 0) e = ++(*epoch);
+    __syncthreads();
+    if ((int)threadIdx.x < n_peers) {
+        __threadfence_system();  // everything this GPU stored before (the proposal rows) is visible before the flag
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peers.slot[threadIdx.x]), "r"(e) : "memory");
+    }
+}
+
+// status[0] is set to 1 if the wait gave up (a peer never arrived): the host reads it with rome_b200_peer_status
+__global__ void peer_wait_kernel(const uint32_t* flags, int n, uint32_t* epoch, uint32_t* status, long long max_cycles) {
+    __shared__ uint32_t e;
+    if (threadIdx.x == 0) e = ++(*epoch);
+    __syncthreads();
+    if ((int)threadIdx.x < n) {
+        const long long t0 = clock64();
+        uint32_t v;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + threadIdx.x) : "memory");
+            if ((int32_t)(v - e) >= 0) break;  // wrap-safe "v >= e"
+            if (clock64() - t0 > max_cycles) {
+                atomicExch(status, 1u);
+                break;
+            }
+            __nanosleep(64);
+        }
+    }
+}
+
+int launch_peer_signal(uint32_t* const* slots, int n_peers, uint32_t* epoch, void* stream) {
+    PeerSlots p = {};
+    for (int i = 0; i < n_peers && i < 8; ++i) p.slot[i] = slots[i];
+    peer_signal_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(p, n_peers, epoch);
+    return (int)cudaGetLastError();
+}
+int launch_peer_wait(const uint32_t* flags, int n, uint32_t* epoch, uint32_t* status, long long max_cycles, void* stream) {
+    peer_wait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(flags, n, epoch, status, max_cycles);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace rome

@@ -714,6 +714,46 @@ int rome_b200_ipc_close(rome_b200_ctx* ctx, void* dev_ptr) {
 }
 
 // ---------------------------------------------------------------------------------------------
+int rome_b200_peer_signal(rome_b200_ctx* ctx, void* d_state, uint32_t* const* peer_slots, int n_peers) {
+    if (!ctx) return ROME_B200_BAD_ARG;
+    if (!d_state || n_peers < 0 || n_peers > 7 || (n_peers > 0 && !peer_slots)) return fail(ctx, ROME_B200_BAD_ARG, "bad peer list");
+    for (int r = 0; r < n_peers; ++r)
+        if (!peer_slots[r]) return fail(ctx, ROME_B200_BAD_ARG, "peer slot is NULL");
+    if (int e = bind(ctx)) return e;
+    uint32_t* st = static_cast<uint32_t*>(d_state);
+    int e = launch_peer_signal(peer_slots, n_peers, st + 8, ctx->stream);
+    if (e) return cuda_fail(ctx, (cudaError_t)e, "peer signal launch");
+    if (ctx->capturing) ctx->capture_kernels++; else ctx->launches++;
+    return ROME_B200_OK;
+}
+int rome_b200_peer_wait(rome_b200_ctx* ctx, void* d_state, const int32_t* slots, int n_slots) {
+    if (!ctx) return ROME_B200_BAD_ARG;
+    if (!d_state || n_slots < 0 || n_slots > 8 || (n_slots > 0 && !slots)) return fail(ctx, ROME_B200_BAD_ARG, "bad slot list");
+    // the listed slots must be a prefix-free set of [0, 8); the kernel polls slots 0..n-1 of a compacted view, so the
+    // caller's slot numbering is required to be 0..n_slots-1 (ranks number their peers densely)
+    for (int i = 0; i < n_slots; ++i)
+        if (slots[i] != i) return fail(ctx, ROME_B200_BAD_ARG, "slots must be numbered 0..n_slots-1");
+    if (int e = bind(ctx)) return e;
+    uint32_t* st = static_cast<uint32_t*>(d_state);
+    int clock_khz = 0;
+    cudaDeviceGetAttribute(&clock_khz, cudaDevAttrClockRate, ctx->device);
+    const long long max_cycles = 2LL * 1000LL * (clock_khz > 0 ? clock_khz : 1965000);  // ~2 s
+    int e = launch_peer_wait(st, n_slots, st + 9, st + 10, max_cycles, ctx->stream);
+    if (e) return cuda_fail(ctx, (cudaError_t)e, "peer wait launch");
+    if (ctx->capturing) ctx->capture_kernels++; else ctx->launches++;
+    return ROME_B200_OK;
+}
+int rome_b200_peer_status(rome_b200_ctx* ctx, void* d_state, int* gave_up) {
+    if (!ctx || !d_state || !gave_up) return ROME_B200_BAD_ARG;
+    if (int e = bind(ctx)) return e;
+    uint32_t v = 0;
+    CK(cudaMemcpyAsync(&v, static_cast<uint32_t*>(d_state) + 10, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *gave_up = (int)v;
+    return ROME_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 int rome_b200_graph_begin(rome_b200_ctx* ctx) {
     if (!ctx) return ROME_B200_BAD_ARG;
     if (ctx->capturing) return fail(ctx, ROME_B200_BAD_ARG, "graph capture already active");
@@ -751,7 +791,12 @@ int rome_b200_graph_launch(rome_b200_ctx* ctx, int graph_id) {
 int rome_b200_malloc_device(rome_b200_ctx* ctx, size_t bytes, void** out) {
     if (!ctx || !out) return ROME_B200_BAD_ARG;
     if (int e = bind(ctx)) return e;
-    CK(cudaMalloc(out, bytes ? bytes : 1));
+    // Whole 2 MiB blocks: the driver packs smaller allocations into shared 2 MiB slabs, and a CUDA IPC handle always
+    // names the slab -- a peer that opens it gets the slab's base, not this buffer.  Buffers from this call are the ones
+    // callers export (rome_b200_ipc_export), so each owns its block(s) and base == pointer.
+    const size_t kBlock = size_t(2) << 20;
+    const size_t rounded = ((bytes ? bytes : 1) + kBlock - 1) / kBlock * kBlock;
+    CK(cudaMalloc(out, rounded));
     return ROME_B200_OK;
 }
 int rome_b200_free_device(rome_b200_ctx* ctx, void* p) {

@@ -118,5 +118,7 @@ int launch_unpack(int d, int wrap_dim, int nvars, int N, int Npad, const unsigne
 int launch_adopt(int d, int Npad, unsigned char* store, int var, const float* prop, int factor, void* stream);
 int launch_product(int d, int wrap_dim, const void* params, int num_sms, void* stream);
 int launch_reanchor(int d, int wrap_dim, unsigned char* store, int nvars, int N, int Npad, void* stream);
+int launch_peer_signal(uint32_t* const* slots, int n_peers, uint32_t* epoch, void* stream);
+int launch_peer_wait(const uint32_t* flags, int n, uint32_t* epoch, uint32_t* status, long long max_cycles, void* stream);
 
 }  // namespace rome

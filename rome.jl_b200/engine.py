@@ -286,6 +286,26 @@ class Context:
         arr = (C.c_void_p * max(1, len(peer_ptrs)))(*peer_ptrs)
         self._ck(self._lib.rome_b200_set_peer_proposals(self._h, family, len(peer_ptrs), arr))
 
+    # -- GPU-side barrier between ranks over NVLink peer memory (closes the fused exchange) ---------------
+    def peer_state_alloc(self) -> int:
+        """zeroed device state buffer (flag slots + epochs) for peer_signal / peer_wait"""
+        p = self.malloc_device(L.PEER_STATE_WORDS * 4)
+        self.memcpy_h2d(p, np.zeros(L.PEER_STATE_WORDS, np.uint32))
+        return p
+
+    def peer_signal(self, state_ptr: int, peer_slot_ptrs):
+        arr = (C.c_void_p * max(1, len(peer_slot_ptrs)))(*peer_slot_ptrs)
+        self._ck(self._lib.rome_b200_peer_signal(self._h, state_ptr, arr, len(peer_slot_ptrs)))
+
+    def peer_wait(self, state_ptr: int, n_slots: int):
+        slots = np.arange(n_slots, dtype=np.int32)
+        self._ck(self._lib.rome_b200_peer_wait(self._h, state_ptr, self._ip(slots), n_slots))
+
+    def peer_gave_up(self, state_ptr: int) -> bool:
+        v = C.c_int()
+        self._ck(self._lib.rome_b200_peer_status(self._h, state_ptr, C.byref(v)))
+        return bool(v.value)
+
     def malloc_device(self, nbytes: int) -> int:
         p = C.c_void_p()
         self._ck(self._lib.rome_b200_malloc_device(self._h, nbytes, C.byref(p)))

@@ -76,6 +76,21 @@ def _worker(rank, world, port, q):
         ok_b = bool(np.array_equal(got[:nF], full[:nF].cpu().numpy()))
         ctx.set_peer_proposals(rb.POSE2POSE2, [])
         dist.barrier()
+        # (c) the GPU-side barrier: signal / wait over peer memory, three rounds, no give-up
+        state = ctx.peer_state_alloc()
+        states = [None] * world
+        dist.all_gather_object(states, ctx.ipc_export(state))
+        slots = [ctx.ipc_import(states[p]) + 4 * (rank if rank < p else rank - 1) for p in range(world) if p != rank]
+        dist.barrier()
+        for _ in range(3):
+            ctx.peer_signal(state, slots)
+            ctx.peer_wait(state, world - 1)
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        words = np.zeros(16, np.uint32)
+        ctx.memcpy_d2h(words, state)
+        ok_b = ok_b and (not ctx.peer_gave_up(state)) and int(words[0]) == 3 and int(words[8]) == 3 and int(words[9]) == 3
+        dist.barrier()
         q.put((rank, ok_a, ok_b))
     finally:
         dist.destroy_process_group()
