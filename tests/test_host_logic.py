@@ -261,3 +261,20 @@ def test_g2o_import_export_text(golden_dir, tmp_path):
         v.parametric = np.arange(v.variableType.dim, dtype=float) + k
     head = open(rb.exportG2o(fg, filename=str(tmp_path / "hexv.g2o"), solveKey="parametric")).read().splitlines()
     assert head[0] == "VERTEX_SE2 0 0.0 1.0 2.0" and head[1] == "VERTEX_SE2 1 1.0 2.0 3.0" and len(head) == 7 + 8
+
+
+def test_bench_cpu_legs():
+    """the CPU legs of bench.py (cpu_baseline sweep, reference-shaped convolution, CPU product) run on the bench workload
+    and return sane rates -- they are what `--impl reference` and `cpu_baseline` report"""
+    import bench
+    w = bench.build_workload(1)
+    assert w["poses"].shape == (bench.NPOSES, bench.NPART, 3) and len(w["ip"]) == len(w["iq"]) == len(w["mu"])
+    assert len(w["ip"]) > bench.NPOSES and len(w["pr_ip"]) == 1
+    v, nt, reps, dt = bench.cpu_sweep_rate(w, 0.3)
+    assert v > 1e6 and nt >= 1 and reps >= 1
+    r = bench.cpu_reference_shaped(w, nfac=4)
+    assert r["residual_calls_per_particle"] > 50 and r["convolved_particles_per_s"] > 0
+    p = bench.cpu_product_shaped(w, nvars=40)
+    assert p["variables_per_s"] > 0 and p["s_per_sweep_extrapolated"] > 0
+    w2 = bench.build_workload(2)  # weak scaling: two graph copies with globally numbered variables
+    assert w2["poses"].shape[0] == 2 * bench.NPOSES and w2["ip"].max() >= bench.NPOSES
