@@ -144,6 +144,12 @@ ROME_B200_API int rome_b200_synchronize(rome_b200_ctx* ctx);
 ROME_B200_API int rome_b200_family_dims(int family, int* dm, int* dr, int* nstats, int* dj);
 ROME_B200_API int rome_b200_vartype_dim(int vartype);
 ROME_B200_API int rome_b200_npad(int N);
+/* Launch geometry the library would choose on a B200 for (family, flags, N) -- pure host arithmetic, no device needed:
+ * consumer warps per CTA (= factors per tile), pipeline stages, CTAs per SM, dynamic shared memory per CTA, and the
+ * pipeline kind (0 producer-warp, 1 per-warp).  ROME_B200_SHAPE_MISMATCH when N is too large for the shared-memory
+ * pipeline of that family. */
+ROME_B200_API int rome_b200_plan_query(int family, uint32_t flags, int N, int* warps, int* stages, int* ctas_per_sm,
+                                       int* smem_bytes, int* pipeline);
 
 /* ---- variables: replaces the per-variable `Vector{ArrayPartition}` particle storage -------- */
 /* Upload Float64 coordinates [nvars][N][d] (host); converts on device to anchored float32 SoA.

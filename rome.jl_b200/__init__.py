@@ -9,7 +9,7 @@ from ._lib import (BEARINGRANGE, DECONV, INDEPENDENT, JACOBIAN, POINT2, POINT2PO
                    POSE3POSE3ROTATION, POSE3POSE3UNITTRANS, POSE3POSE3XYYAW, PRIORPOINT2, PRIORPOINT3, PRIORPOSE2, PRIORPOSE3,
                    PROPOSAL_BWD, PROPOSAL_FWD, RESIDUAL, SAMPLE, SO_PATH, STATS, SYMBOLS, WRITE_MEAS, RomeB200Error)
 from .engine import (BYTES_PER_EVAL, BYTES_PER_EVAL_SAMPLED, FAMILY, VAR_DIM, Context, dequantized_particles,
-                     meas_to_offsets, npad, offsets_to_meas, rows_to_particle_major)
+                     meas_to_offsets, npad, offsets_to_meas, plan_query, rows_to_particle_major)
 
 from .factors import (MvNormal, Normal, Point2, Point2Point2, Point2Point2Range, Point3, Point3Point3, Pose2, Pose2Point2,
                       Pose2Point2Bearing, Pose2Point2BearingRange, Pose2Point2Range, Pose2Pose2, Pose3, Pose3Pose3,

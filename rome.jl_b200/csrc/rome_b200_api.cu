@@ -277,6 +277,19 @@ int rome_b200_vartype_dim(int vartype) {
     return (vartype < 0 || vartype >= ROME_B200_NVARTYPES) ? ROME_B200_BAD_ARG : kVarDim[vartype];
 }
 int rome_b200_npad(int N) { return N <= 0 ? ROME_B200_BAD_ARG : (N + 7) / 8 * 8; }
+int rome_b200_plan_query(int family, uint32_t flags, int N, int* warps, int* stages, int* ctas_per_sm, int* smem_bytes,
+                         int* pipeline) {
+    if (family < 0 || family >= ROME_B200_NFAMILIES || N <= 0) return ROME_B200_BAD_ARG;
+    LaunchPlan plan;
+    // B200 (sm_100): 228 KB shared memory per SM, 227 KB opt-in maximum per CTA
+    if (plan_launch(family, flags, rome_b200_npad(N), 233472, 232448, &plan)) return ROME_B200_SHAPE_MISMATCH;
+    if (warps) *warps = plan.ft;
+    if (stages) *stages = plan.stages;
+    if (ctas_per_sm) *ctas_per_sm = plan.ctas_per_sm;
+    if (smem_bytes) *smem_bytes = plan.smem_bytes;
+    if (pipeline) *pipeline = plan.pipeline;
+    return ROME_B200_OK;
+}
 
 // ---------------------------------------------------------------------------------------------
 int rome_b200_set_particles(rome_b200_ctx* ctx, int vartype, int nvars, int N, const double* coords_host) {

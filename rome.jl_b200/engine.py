@@ -48,6 +48,17 @@ BYTES_PER_EVAL_SAMPLED = {POSE2POSE2: 36, PRIORPOSE2: 24, BEARINGRANGE: 28, POSE
                           POSE3POSE3XYYAW: 60, POSE3POSE3ROTATION: 60, POSE3POSE3UNITTRANS: 72}
 
 
+def plan_query(family: int, flags: int, N: int):
+    """launch geometry on a B200 for (family, flags, N): dict(warps, stages, ctas_per_sm, smem_bytes, pipeline); no GPU needed"""
+    lib = L.load()
+    v = [C.c_int() for _ in range(5)]
+    rc = lib.rome_b200_plan_query(family, flags, N, *[C.byref(x) for x in v])
+    if rc != 0:
+        raise RomeB200Error(rc, "N is too large for the shared-memory pipeline of this family" if rc == L.SHAPE_MISMATCH
+                            else "bad family / N")
+    return dict(zip(("warps", "stages", "ctas_per_sm", "smem_bytes", "pipeline"), (x.value for x in v)))
+
+
 def npad(N: int) -> int:
     return (N + 7) // 8 * 8
 

@@ -278,3 +278,31 @@ def test_bench_cpu_legs():
     assert p["variables_per_s"] > 0 and p["s_per_sweep_extrapolated"] > 0
     w2 = bench.build_workload(2)  # weak scaling: two graph copies with globally numbered variables
     assert w2["poses"].shape[0] == 2 * bench.NPOSES and w2["ip"].max() >= bench.NPOSES
+
+
+def test_launch_plans_fit_the_sm():
+    """rome_b200_plan_query (pure host arithmetic): for every family, the flag sets the API distinguishes and particle
+    counts from 1 to 4000 the chosen geometry fits a B200 SM -- or the library says the N is too large"""
+    smem_sm, smem_cta = 233472, 232448
+    pose3 = {rb.POSE3POSE3, rb.PRIORPOSE3, rb.POSE3POSE3XYYAW, rb.POSE3POSE3ROTATION, rb.POSE3POSE3UNITTRANS}
+    flag_sets = [rb.RESIDUAL, rb.RESIDUAL | rb.STATS, rb.RESIDUAL | rb.STATS | rb.SAMPLE,
+                 rb.RESIDUAL | rb.STATS | rb.PROPOSAL_FWD, rb.RESIDUAL | rb.STATS | rb.PROPOSAL_FWD | rb.SAMPLE,
+                 rb.SAMPLE | rb.PROPOSAL_FWD | rb.PROPOSAL_BWD, rb.SAMPLE | rb.DECONV]
+    too_large = 0
+    for fam in rb.FAMILY:
+        for fl in flag_sets:
+            for N in (1, 7, 8, 37, 100, 104, 128, 200, 256, 400, 1000, 2000, 4000):
+                try:
+                    p = rb.plan_query(fam, fl, N)
+                except rb.RomeB200Error as e:
+                    assert e.code == -3 and N >= 400, (fam, fl, N)
+                    too_large += 1
+                    continue
+                assert p["stages"] >= 2 and p["warps"] in (1, 2, 8, 12), (fam, fl, N, p)
+                assert p["smem_bytes"] <= smem_cta and p["ctas_per_sm"] * (p["smem_bytes"] + 1024) <= smem_sm, (fam, fl, N, p)
+                assert (p["pipeline"] == 1) == (p["warps"] == 12) and (p["pipeline"] == 0 or fam in pose3), (fam, fl, N, p)
+                if N <= 104 and fam not in pose3:
+                    assert p["ctas_per_sm"] == 2 and p["warps"] == 8, (fam, fl, N, p)
+    assert too_large > 0  # the pipeline has a documented upper bound on N per family
+    with pytest.raises(rb.RomeB200Error):
+        rb.plan_query(99, rb.RESIDUAL, 100)
