@@ -18,7 +18,7 @@ from .factors import (MvNormal, Normal, Point2, Point2Point2, Point2Point2Range,
 from .graph import (DeviceGraph, FactorGraph, SolverParams, addFactor, addVariable, approxConv, approxConvBelief, approxDeconv,
                     calcFactorResidual, calcFactorResidualTemporary, default_context, getSample, getSolverParams,
                     getVal, initAll, initfg, ls, lsf, sampleFactor, setVal)
-from .canonical import (generateGraph_Beehive, generateGraph_Circle, generateGraph_Hexagonal,
+from .canonical import (generateGraph_Beehive, generateGraph_Circle, generateGraph_Hexagonal, generateGraph_Honeycomb,
                         generateGraph_ManhattanShaped, generateGraph_Pose3Chain, generateGraph_ZeroPose,
                         seed_particles)
 from . import sharding

@@ -107,6 +107,83 @@ def generateGraph_Hexagonal(fg: FactorGraph | None = None, landmark=True, loopCl
                                 loopClosure=landmark if loopClosure is None else loopClosure)
 
 
+class _LandmarkSighter:
+    """_addLandmarkBeehive! (GenerateHoneycomb.jl:59-100): every pose sights the lattice landmark 20 m ahead through
+    Pose2Point2BearingRange(Normal(0, 0.03), Normal(20, 0.5)); a landmark within `atol` of an existing one is that one
+    (the reference's `_checkVariableByReference` data association), otherwise a new Point2 is added."""
+
+    def __init__(self, fg, atol, label, association=None):
+        self.fg, self.atol, self.label, self.association = fg, atol, label, association
+        self.landmarks: list[tuple[str, np.ndarray]] = []
+        self.cells: dict[tuple[int, int], list[int]] = {}
+
+    def __call__(self, pose_label):
+        fg = self.fg
+        p = _truth(fg, pose_label)
+        pos = p[:2] + 20.0 * np.array([math.cos(p[2]), math.sin(p[2])])
+        key = (int(math.floor(pos[0] / 4.0)), int(math.floor(pos[1] / 4.0)))
+        found = None
+        if self.association is not None:
+            # `_doHoneycomb` (:73-83): the table decides, not the geometry
+            forced = self.association.get(self.label(pose_label, len(self.landmarks)))
+            found = None if forced is None else next(k for k, (lab, _) in enumerate(self.landmarks) if lab == forced)
+        else:
+            for dx in (-1, 0, 1):
+                for dy in (-1, 0, 1):
+                    for k in self.cells.get((key[0] + dx, key[1] + dy), []):
+                        if np.linalg.norm(self.landmarks[k][1] - pos) < self.atol:
+                            found = k
+        if found is None:
+            lab = self.label(pose_label, len(self.landmarks))
+            v = addVariable(fg, lab, Point2, tags=["LANDMARK"])
+            v.simulated = pos
+            self.landmarks.append((lab, pos))
+            self.cells.setdefault(key, []).append(len(self.landmarks) - 1)
+            found = len(self.landmarks) - 1
+        addFactor(fg, [pose_label, self.landmarks[found][0]], Pose2Point2BearingRange(Normal(0, 0.03), Normal(20, 0.5)),
+                  graphinit=False)
+        return self.landmarks[found][0]
+
+
+def generateGraph_Honeycomb(poseCountTarget=36, fg: FactorGraph | None = None, graphinit=False, direction="right",
+                            addLandmarks=True, atol=1.0, N=100, extraLeftLegs=(41, 63, 78), association=None):
+    """generateGraph_Honeycomb! (GenerateHoneycomb.jl:179-231): the predetermined honeycomb -- repeat { six hexagon legs
+    [10, 0, +pi/3] (`_driveHex!` :103-132), an extra left leg after poses 41, 63, 78 (the pose entries of
+    `_honeycombRecipe` :47-49), one offset leg [10, 0, -+pi/3] in `direction` (`_offsetHexLeg` :134-170) } until
+    poseCountTarget; every new pose sights the landmark 20 m ahead, named l<pose number> when new.  The reference forces
+    its landmark data association from a hard-coded table (`_honeycombRecipe` :3-46, `_doHoneycomb` :73-83): pass that
+    table as `association` ({"l6": "l0", ...}; tests/golden/known_answers.json holds it) to rebuild the reference's graph
+    label for label.  By default the association follows from the geometry (same landmark = within `atol`), which agrees
+    with the table wherever the table is consistent with the simulated poses (tests/test_host_logic.py)."""
+    fg = fg or initfg(SolverParams(N=N, graphinit=graphinit))
+    generateGraph_ZeroPose(fg, Pose2, graphinit=graphinit)
+    sight = _LandmarkSighter(fg, atol, label=lambda pose_label, count: "l" + pose_label[1:], association=association)
+    if addLandmarks:
+        sight("x0")
+    state = {"n": 0}
+
+    def leg(turn):
+        if poseCountTarget <= state["n"]:
+            return
+        i = state["n"]
+        X = np.array([10.0, 0.0, turn])
+        v = addVariable(fg, f"x{i + 1}", Pose2)
+        v.simulated = _se2_compose(_truth(fg, f"x{i}"), X)
+        addFactor(fg, [f"x{i}", f"x{i + 1}"], Pose2Pose2(MvNormal(X, np.diag([0.1, 0.1, 0.1]) ** 2)), graphinit=graphinit)
+        state["n"] = i + 1
+        if addLandmarks:
+            sight(f"x{i + 1}")
+
+    off = {"right": -math.pi / 3, "left": math.pi / 3}
+    while state["n"] < poseCountTarget:
+        for _ in range(6):
+            leg(math.pi / 3)
+        if state["n"] in extraLeftLegs:
+            leg(off["left"])
+        leg(off[direction])
+    return fg
+
+
 def generateGraph_Beehive(poseCountTarget=10, fg: FactorGraph | None = None, graphinit=True, addLandmarks=True,
                           yaw0=None, locality=1.0, atol=1.0, seed=3, N=200):
     """Honeycomb walk of GenerateBeehive.jl:20-72: legs [10, 0, +-pi/3] (GenerateHoneycomb.jl:134-170), direction
@@ -117,28 +194,7 @@ def generateGraph_Beehive(poseCountTarget=10, fg: FactorGraph | None = None, gra
     fg = fg or initfg(SolverParams(N=N, graphinit=graphinit))
     yaw0 = [0.0, -2 * math.pi / 3, 2 * math.pi / 3][rng.integers(0, 3)] if yaw0 is None else yaw0
     generateGraph_ZeroPose(fg, Pose2, mu0=[0.0, 0.0, yaw0], graphinit=graphinit)
-    landmarks: list[tuple[str, np.ndarray]] = []
-    cells: dict[tuple[int, int], list[int]] = {}
-
-    def sight(pose_label):
-        p = _truth(fg, pose_label)
-        pos = p[:2] + 20.0 * np.array([math.cos(p[2]), math.sin(p[2])])
-        key = (int(math.floor(pos[0] / 4.0)), int(math.floor(pos[1] / 4.0)))
-        found = None
-        for dx in (-1, 0, 1):
-            for dy in (-1, 0, 1):
-                for k in cells.get((key[0] + dx, key[1] + dy), []):
-                    if np.linalg.norm(landmarks[k][1] - pos) < atol:
-                        found = k
-        if found is None:
-            lab = f"l{len(landmarks) + 1}"
-            v = addVariable(fg, lab, Point2, tags=["LANDMARK"])
-            v.simulated = pos
-            landmarks.append((lab, pos))
-            cells.setdefault(key, []).append(len(landmarks) - 1)
-            found = len(landmarks) - 1
-        addFactor(fg, [pose_label, landmarks[found][0]], Pose2Point2BearingRange(Normal(0, 0.03), Normal(20, 0.5)),
-                  graphinit=False)
+    sight = _LandmarkSighter(fg, atol, label=lambda pose_label, count: f"l{count + 1}")
 
     if addLandmarks:
         sight("x0")

@@ -153,6 +153,12 @@ def known_answers():
         X=[10.0, 0.0, pi / 3],
         poses=[[0, 0, 0], [10, 0, pi / 3], [15, 8.66, 2 * pi / 3], [10, 17.32, pi], [0, 17.32, -2 * pi / 3],
                [-5, 8.66, -pi / 3], [0, 0, 0]], landmark=[20, 0], atol=0.01)
+    # data association + extra legs that generateGraph_Honeycomb! forces (parsed, not transcribed)
+    txt = open(os.path.join(REF, "src/canonical/GenerateHoneycomb.jl")).read()
+    ka["honeycomb_recipe"] = dict(
+        src="src/canonical/GenerateHoneycomb.jl:3-52",
+        landmarks=dict(re.findall(r":(l\d+)\s*=>\s*:(l\d+)", txt)),
+        legs={k: v for k, v in re.findall(r":(x\d+)\s*=>\s*:(left|right)", txt)})
     with open(os.path.join(OUT, "known_answers.json"), "w") as fh:
         json.dump(ka, fh, indent=1)
     return ka

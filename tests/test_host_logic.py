@@ -174,6 +174,45 @@ def test_generators_shapes():
     assert rb.getVal(p3, "x5").shape == (16, 6)
 
 
+def test_honeycomb_matches_reference_recipe():
+    """generateGraph_Honeycomb! (GenerateHoneycomb.jl:179-231).  With the reference's forced association table the graph
+    is the reference's label for label; the geometric association (default) agrees with the table on every entry except
+    :l42, where the table contradicts the simulated poses (x42 stands on x36's pose, whose sighting the table itself
+    resolves to :l3, yet it lists :l42 => :l0)."""
+    import json
+    rec = json.load(open(os.path.join(ROOT, "tests", "golden", "known_answers.json")))["honeycomb_recipe"]
+    table, legs = rec["landmarks"], rec["legs"]
+    assert sorted(int(k[1:]) for k in legs) == [41, 63, 78] and set(legs.values()) == {"left"}
+
+    def sightings(fg):
+        out = {}
+        for lab in rb.lsf(fg, rb.Pose2Point2BearingRange):
+            x, l = fg[lab].variableOrderSymbols
+            out["l" + x[1:]] = l
+        return out
+
+    last = max(int(k[1:]) for k in table)   # the table covers sightings up to :l70
+    forced = rb.generateGraph_Honeycomb(last, association=table)
+    geo = rb.generateGraph_Honeycomb(last)
+    sf, sg = sightings(forced), sightings(geo)
+    assert len(sf) == len(sg) == last + 1 and len(rb.ls(forced, rb.Pose2)) == last + 1
+    assert all(sf[k] == table.get(k, k) for k in sf)
+    differ = sorted(k for k in sf if sf[k] != sg[k])
+    # besides :l42, the table stops short of four re-sightings the geometry finds (it leaves them as new landmarks)
+    assert "l42" in differ and sg["l42"] == "l3"
+    assert all(k not in table for k in differ if k != "l42")
+    # every forced sighting except :l42 is geometrically exact: the landmark is 20 m dead ahead of the pose
+    for k, l in sf.items():
+        p, lm = forced["x" + k[1:]].simulated, forced[l].simulated
+        ahead = p[:2] + 20.0 * np.array([math.cos(p[2]), math.sin(p[2])])
+        assert (np.linalg.norm(ahead - lm) < 1e-6) == (k != "l42"), k
+    # default target (36 poses) + the `direction` switch
+    fg = rb.generateGraph_Honeycomb()
+    assert len(rb.ls(fg, rb.Pose2)) == 37 and len(rb.lsf(fg, rb.Pose2Pose2)) == 36 and len(rb.lsf(fg, rb.PriorPose2)) == 1
+    left = rb.generateGraph_Honeycomb(14, direction="left")
+    assert abs(left["x7"].simulated[2] - rb.generateGraph_Honeycomb(14)["x7"].simulated[2]) > 1.0
+
+
 def test_layout_helpers():
     rng = np.random.default_rng(0)
     meas = rng.normal(size=(5, 100, 3))
