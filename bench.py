@@ -348,16 +348,17 @@ def main():
                 c.set_peer_proposals(rb.POSE2POSE2, [c.ipc_import(everyone[r][si][0]) for r in range(G) if r != rank])
                 c.set_peer_proposals(rb.PRIORPOSE2, [c.ipc_import(everyone[r][si][1]) for r in range(G) if r != rank])
             token = torch.zeros(1, device="cuda")
-            # GPU-side barrier state: one flag array per rank; peer p owns slot dense(p) = p if p < rank else p - 1
-            c0 = sets[0][0]
-            state = c0.peer_state_alloc()
-            states = [None] * G
-            dist.all_gather_object(states, c0.ipc_export(state))
-            peer_slots = []
-            for p in range(G):
-                if p != rank:
-                    base = c0.ipc_import(states[p])
-                    peer_slots.append(base + 4 * (rank if rank < p else rank - 1))
+            if args.barrier == "flags":
+                # GPU-side barrier state: one flag array per rank; peer p owns slot dense(p) = p if p < rank else p - 1
+                c0 = sets[0][0]
+                state = c0.peer_state_alloc()
+                states = [None] * G
+                dist.all_gather_object(states, c0.ipc_export(state))
+                peer_slots = []
+                for p in range(G):
+                    if p != rank:
+                        base = c0.ipc_import(states[p])
+                        peer_slots.append(base + 4 * (rank if rank < p else rank - 1))
             dist.barrier()
 
     n_prior = len(w["pr_ip"]) // G
