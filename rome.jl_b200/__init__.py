@@ -24,6 +24,7 @@ from .canonical import (generateGraph_Beehive, generateGraph_Circle, generateGra
 from . import sharding
 from .solver import GibbsSolver, build_product_plans, solveGraphGibbs
 from .parametric import color_variables, solveGraphParametric
+from .dfg_io import loadDFG, saveDFG, setPPE
 from .g2o import exportG2o, graphFromEdgeArrays, importG2o, loadG2o, parseG2oInstruction, stringG2o
 
 __version__ = "0.1.0"

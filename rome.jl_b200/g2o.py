@@ -147,15 +147,20 @@ def stringG2o(fnc, varlist) -> str:
 
 
 def exportG2o(fg: FactorGraph, poseRegex: str = r"x\d", ignorePriors: bool = True, filename: str = "/tmp/test.txt",
-              solveKey=None) -> str:
-    """exportG2o(dfg; poseRegex, ignorePriors, filename, solveKey): factors in pose order, every factor once, variables
-    numbered in order of first appearance (landmarks interleave with poses exactly as in the reference); with a
-    solveKey the VERTEX_* lines of the numbered variables come first ("parametric": the parametric solution, anything
-    else: the particle mean)."""
+              solveKey=None, varIntLabel: dict | None = None) -> str:
+    """exportG2o(dfg; poseRegex, ignorePriors, filename, varIntLabel, solveKey) (g2oParser.jl:373-400): factors in pose
+    order, every factor once, variables numbered in order of first appearance (landmarks interleave with poses exactly
+    as in the reference), continuing after the numbers `varIntLabel` ({label: int}, ordered) already assigns.  With a
+    solveKey the VERTEX_* lines come first: for the entries of `varIntLabel` like the reference (`_writeG2oVertexes`
+    :323-339 -- it writes none when the mapping is empty), or, when no mapping is passed, for every numbered variable.
+    The estimate is the variable's PPE `suggested` for that key (`setPPE`), else the parametric solution
+    ("parametric"), else the particle mean."""
     pat = re.compile(poseRegex)
     poses = sorted((l for l in fg.variables if pat.match(l)), key=_natural_key)
     remaining = list(fg.factors)  # insertion order, like DFG's neighbour lists
-    ids, lines = {}, []
+    ids, lines = {str(k): int(v) for k, v in (varIntLabel or {}).items()}, []
+    vertex_labels = list(ids) if varIntLabel is not None else None
+    nxt = max(ids.values(), default=-1) + 1  # uniqVarInt: one past the largest number in use
     for vs in poses:
         for fl in [f for f in remaining if vs in fg.factors[f].variableOrderSymbols]:
             f = fg.factors[fl]
@@ -165,14 +170,17 @@ def exportG2o(fg: FactorGraph, poseRegex: str = r"x\d", ignorePriors: bool = Tru
             varlist = []
             for l in f.variableOrderSymbols:
                 if l not in ids:
-                    ids[l] = len(ids)
+                    ids[l] = nxt
+                    nxt += 1
                 varlist.append(ids[l])
             lines.append(stringG2o(f.fnc, varlist))
     head = []
     if solveKey is not None:
-        for l, i in ids.items():
-            v = fg.variables[l]
-            x = getattr(v, "parametric", None) if solveKey == "parametric" else None
+        for l in (ids if vertex_labels is None else vertex_labels):
+            v, i = fg.variables[l], ids[l]
+            x = getattr(v, "ppes", {}).get(solveKey, {}).get("suggested")
+            if x is None and solveKey == "parametric":
+                x = getattr(v, "parametric", None)
             if x is None:
                 if v.val is None:
                     raise ValueError(f"variable {l} has no estimate for solve key {solveKey}")

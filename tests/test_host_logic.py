@@ -345,3 +345,99 @@ def test_launch_plans_fit_the_sm():
     assert too_large > 0  # the pipeline has a documented upper bound on N per family
     with pytest.raises(rb.RomeB200Error):
         rb.plan_query(99, rb.RESIDUAL, 100)
+
+
+def _legacy_fullnormal(mu, S):
+    rows = "; ".join(" ".join(repr(float(v)) for v in r) for r in S)
+    return "FullNormal(\ndim: %d\nμ: [%s]\nΣ: [%s]\n)\n" % (len(mu), ", ".join(repr(float(v)) for v in mu), rows)
+
+
+def test_dfg_files_roundtrip_and_legacy_layout(tmp_path):
+    """saveDFG -> loadDFG keeps labels, order, beliefs, particles and solver parameters; the
+    2020 layout (solverDataDict / ppeDict strings, FullNormal text) is read too; the SE(3) export of
+    test/testG2oExportSE3.jl:13-29 (graph rebuilt from its commented recipe) produces VERTEX + EDGE lines."""
+    import json
+    import tarfile
+    fg = rb.generateGraph_Hexagonal(graphinit=False)
+    rb.seed_particles(fg, N=20, seed=3)
+    path = rb.saveDFG(fg, str(tmp_path / "hex"))
+    assert path.endswith("hex.tar.gz")
+    back = rb.loadDFG(str(tmp_path / "hex"))  # extension appended on load as well
+    assert rb.ls(back) == rb.ls(fg) and rb.lsf(back) == rb.lsf(fg)
+    assert back.solverParams == fg.solverParams
+    for l in rb.ls(fg):
+        assert back[l].variableType is fg[l].variableType and np.array_equal(back[l].val, fg[l].val)
+        assert back[l].tags == fg[l].tags
+    for l in rb.lsf(fg):
+        assert back[l].variableOrderSymbols == fg[l].variableOrderSymbols and rb.pack(back[l].fnc) == rb.pack(fg[l].fnc)
+    # ... so the exported g2o text is the reference's (test/testG2oParser.jl:28-35) after the round trip as well
+    a = open(rb.exportG2o(fg, filename=str(tmp_path / "a.g2o"))).read()
+    assert a == open(rb.exportG2o(back, filename=str(tmp_path / "b.g2o"))).read() and a.count("\n") == 8
+
+    # legacy 2020 layout, written by hand like examples/manhattan-batch-500-fg.tar.gz
+    root = tmp_path / "fg-after-solve"
+    (root / "variables").mkdir(parents=True)
+    (root / "factors").mkdir()
+    rng = np.random.default_rng(0)
+    pts = {"x0": rng.normal(size=(10, 3)), "x1": rng.normal(size=(10, 3)) + [1, 0, 0]}
+    for l, p in pts.items():
+        sd = {"default": {"vecval": p.reshape(-1).tolist(), "dimval": 3, "softtype": "Pose2(3, String[], (:Euclid, :Euclid, :Circular))",
+                          "initialized": True}}
+        ppe = {"default": {"solverKey": "default", "suggested": p.mean(0).tolist(), "max": p[0].tolist(), "mean": p.mean(0).tolist()}}
+        json.dump({"label": l, "solverDataDict": json.dumps(sd), "ppeDict": json.dumps(ppe), "tags": "[\"VARIABLE\"]",
+                   "timestamp": "2020-02-07T18:19:23.71", "solvable": 1}, open(root / "variables" / f"{l}.json", "w"))
+    S = np.array([[0.0225, 0.0008, 0.0], [0.0008, 0.0026, 0.0], [0.0, 0.0, 0.0007]])
+    for lab, vo, key, mu, cov, ts in (("x0x1f1", ["x0", "x1"], "datastr", [1.01983, 0.023016, -0.016479], S, "2020-02-07T18:21:46.664"),
+                                      ("x0f1", ["x0"], "str", [0.0, 0.0, 0.0], np.diag([0.01, 0.01, 0.0025]), "2020-02-07T18:13:01.361")):
+        data = {"fncargvID": vo, "fnc": {key: _legacy_fullnormal(mu, cov)}, "multihypo": "", "certainhypo": [1]}
+        json.dump({"label": lab, "_variableOrderSymbols": json.dumps(vo), "data": json.dumps(data), "tags": "[\"FACTOR\"]",
+                   "timestamp": ts, "fnctype": "Pose2Pose2" if len(vo) == 2 else "PriorPose2", "solvable": 1},
+                  open(root / "factors" / f"{lab}.json", "w"))
+    with tarfile.open(tmp_path / "legacy.tar.gz", "w:gz") as tf:
+        tf.add(root, arcname="fg-after-solve")
+    for src in (str(tmp_path / "legacy.tar.gz"), str(root)):  # archive or unpacked directory
+        lg = rb.loadDFG(src)
+        assert rb.ls(lg) == ["x0", "x1"] and rb.lsf(lg) == ["x0f1", "x0x1f1"]  # prior first: it is older
+        assert isinstance(lg["x0f1"].fnc, rb.PriorPose2) and np.array_equal(lg["x0x1f1"].fnc.Z.Sigma, S)
+        assert np.array_equal(lg["x0x1f1"].fnc.Z.mu, [1.01983, 0.023016, -0.016479])
+        assert np.array_equal(lg["x1"].val, pts["x1"]) and np.allclose(lg["x1"].ppes["default"]["suggested"], pts["x1"].mean(0))
+
+    # test/testG2oExportSE3.jl: four Pose3, a prior and three unit steps, saved, loaded, exported with fixed numbering
+    g3 = rb.initfg()
+    for l in ("x0", "x1", "x2", "x3"):
+        rb.addVariable(g3, l, rb.Pose3).parametric = np.zeros(6)
+    rb.addFactor(g3, ["x0"], rb.PriorPose3(rb.MvNormal(np.zeros(6), np.diag(0.1 * np.ones(6)))))
+    for a_, b_ in (("x0", "x1"), ("x1", "x2"), ("x2", "x3")):
+        rb.addFactor(g3, [a_, b_], rb.Pose3Pose3(rb.MvNormal([1, 0, 0, 0, 0, 0.], np.diag(0.1 * np.ones(6)))), graphinit=False)
+    g3 = rb.loadDFG(rb.saveDFG(g3, str(tmp_path / "g2otest.tar.gz")))
+    assert all(g3[l].val is None for l in rb.ls(g3))  # saved uninitialized, loaded uninitialized
+    rb.setPPE(g3, rb.ls(g3), "parametric")
+    out = open(rb.exportG2o(g3, filename=str(tmp_path / "se3.g2o"), solveKey="parametric",
+                            varIntLabel={l: i for i, l in enumerate(rb.ls(g3))})).read().splitlines()
+    assert out[:4] == [f"VERTEX_SE3:QUAT {i} 0.0 0.0 0.0 0.0 0.0 0.0 1.0" for i in range(4)]
+    assert [ln.split()[:10] for ln in out[4:]] == [["EDGE_SE3:QUAT", str(i), str(i + 1), "1.0", "0.0", "0.0", "0.0", "0.0", "0.0", "1.0"]
+                                                   for i in range(3)]
+    assert all(len(ln.split()) == 31 and abs(float(ln.split()[10]) - 10.0) < 1e-9 for ln in out[4:])
+    # the reference writes no VERTEX line when the mapping is empty (g2oParser.jl:323-339, 391-393)
+    none = open(rb.exportG2o(g3, filename=str(tmp_path / "n.g2o"), solveKey="parametric", varIntLabel={})).read()
+    assert "VERTEX" not in none and none.count("EDGE_SE3:QUAT") == 3
+    with pytest.raises(ValueError):  # families outside the path are refused, not skipped
+        bad = tmp_path / "bad"
+        (bad / "variables").mkdir(parents=True)
+        (bad / "factors").mkdir()
+        json.dump({"label": "x0", "variableType": "RoME.DynPose2", "solverData": [], "tags": []}, open(bad / "variables" / "x0.json", "w"))
+        rb.loadDFG(str(bad))
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/examples/manhattan-batch-500-fg.tar.gz"), reason="build container only")
+def test_dfg_reference_files_load():
+    """the reference's own files (not available on the GPU box): legacy Manhattan-500 solve and the v0.25 SE(3) chain"""
+    fg = rb.loadDFG("/root/reference/examples/manhattan-batch-500-fg.tar.gz")
+    assert len(rb.ls(fg)) == 361 and len(rb.lsf(fg, rb.Pose2Pose2)) == 500 and rb.lsf(fg)[0] == "x0f1"
+    d = np.load(os.path.join(ROOT, "tests", "golden", "manhattan500_fixture.npz"))
+    assert np.array_equal(np.stack([fg[f"x{i}"].val for i in range(120)]), d["particles"])
+    assert np.allclose(np.stack([fg[f"x{i}"].ppes["default"]["mean"] for i in range(120)]), d["ppe_mean"])
+    g3 = rb.loadDFG("/root/reference/test/testdata/g2otest.tar.gz")
+    assert rb.ls(g3) == ["x0", "x1", "x2", "x3"] and rb.lsf(g3) == ["x0f1", "x0x1f1", "x1x2f1", "x2x3f1"]
+    assert g3.solverParams.N == 100 and g3.solverParams.inflation == 5.0 and g3["x0"].val is None
+    assert np.array_equal(g3["x1x2f1"].fnc.Z.Sigma, 0.1 * np.eye(6)) and np.array_equal(g3["x2"].parametric, np.zeros(6))
