@@ -15,9 +15,9 @@ from .factors import (MvNormal, Normal, Point2, Point2Point2, Point2Point2Range,
                       Pose2Point2Bearing, Pose2Point2BearingRange, Pose2Point2Range, Pose2Pose2, Pose3, Pose3Pose3,
                       Pose3Pose3Rotation, Pose3Pose3UnitTrans, Pose3Pose3XYYaw, PriorPoint2, PriorPoint3, PriorPose2,
                       PriorPose3, getManifold, getMeasurementParametric, pack, unpack)
-from .graph import (DeviceGraph, FactorGraph, SolverParams, addFactor, addVariable, approxConv, approxConvBelief, approxDeconv,
+from .graph import (DeviceGraph, FactorGraph, SolverParams, accumulateFactorMeans, addFactor, addVariable, approxConv, approxConvBelief, approxDeconv,
                     calcFactorResidual, calcFactorResidualTemporary, default_context, getSample, getSolverParams,
-                    getVal, initAll, initfg, ls, lsf, sampleFactor, setVal)
+                    getVal, initAll, initfg, ls, lsf, sampleFactor, setVal, solveFactorParametric)
 from .canonical import (generateGraph_Beehive, generateGraph_Circle, generateGraph_Hexagonal, generateGraph_Honeycomb,
                         generateGraph_ManhattanShaped, generateGraph_Pose3Chain, generateGraph_ZeroPose,
                         seed_particles)

@@ -369,6 +369,57 @@ def approxDeconv(fg: FactorGraph, flabel, N: int | None = None, seed=0, ctx: Con
     return dec, meas
 
 
+def solveFactorParametric(fg: FactorGraph, flabel, src, target, ctx: Context | None = None) -> np.ndarray:
+    """IIF.solveFactorParametric(dfg, fct, [srcsym => val], trgsym): the target variable's coordinates that zero the
+    residual at the factor's MEAN measurement, given the other variable's coordinates -- the closed-form proposal
+    kernels evaluated on one particle with the measurement supplied (no sampling).  `src` = (label, coordinates)."""
+    f = fg.factors[str(flabel)]
+    fnc, target = f.fnc, str(target)
+    if fnc.is_prior or target not in f.variableOrderSymbols or len(f.variableOrderSymbols) != 2:
+        raise ValueError(f"{flabel} is not a two-variable factor connected to {target}")
+    slot = f.variableOrderSymbols.index(target)
+    if str(src[0]) != f.variableOrderSymbols[1 - slot]:
+        raise KeyError(f"{src[0]} is not the other variable of {flabel}")
+    if isinstance(fnc, PARTIAL_FACTORS) or isinstance(fnc, SCALAR_FACTORS) or FAMILY[fnc.family][7 if slot == 0 else 6] == 0:
+        raise NotImplementedError(f"{type(fnc).__name__}: no closed-form solve onto {'the first' if slot == 0 else 'the last'} variable")
+    pts = [None, None]
+    pts[1 - slot] = np.asarray(src[1], dtype=np.float64).reshape(1, -1)
+    pts[slot] = np.zeros((1, fnc.variabletypes[slot].dim))
+    dg = DeviceGraph(_mini_graph(fnc, pts, 1), ctx or default_context(), N=1)
+    flag, key = (L.PROPOSAL_FWD, "prop_fwd") if slot == 1 else (L.PROPOSAL_BWD, "prop_bwd")
+    return dg.eval(fnc.family, L.RESIDUAL | flag, meas=factor_mean(fnc).reshape(1, 1, -1))[key][0, 0]
+
+
+def accumulateFactorMeans(fg: FactorGraph, fctsyms, ctx: Context | None = None) -> np.ndarray:
+    """IIF.accumulateFactorMeans(dfg, [:x0f1; :x0x1f1; ...]) (test/testAccumulateFactors.jl:19-30): start from the
+    first factor's mean when it is a prior (else from the mean of the chain's first variable's particles) and carry
+    the value along the chain of relative factors through `solveFactorParametric`."""
+    fctsyms = [str(s) for s in fctsyms]
+    if not fctsyms:
+        raise ValueError("accumulateFactorMeans needs at least one factor")
+    f0 = fg.factors[fctsyms[0]]
+    if f0.fnc.is_prior:
+        val, cur, rest = factor_mean(f0.fnc).astype(np.float64), f0.variableOrderSymbols[0], fctsyms[1:]
+    else:
+        vs = f0.variableOrderSymbols
+        nxt = [v for v in vs if len(fctsyms) > 1 and v in fg.factors[fctsyms[1]].variableOrderSymbols]
+        cur = next(v for v in vs if v not in nxt[:1]) if nxt else vs[0]
+        v = fg.variables[cur]
+        if v.val is None:
+            raise ValueError(f"variable {cur} has no estimate to start the chain from")
+        val = v.val.mean(0)
+        if v.variableType is Pose2:
+            val[2] = np.arctan2(np.sin(v.val[:, 2]).mean(), np.cos(v.val[:, 2]).mean())
+        rest = fctsyms
+    for fl in rest:
+        others = [v for v in fg.factors[fl].variableOrderSymbols if v != cur]
+        if len(others) != 1:
+            raise ValueError(f"{fl} does not continue the chain from {cur}")
+        val = solveFactorParametric(fg, fl, (cur, val), others[0], ctx=ctx)
+        cur = others[0]
+    return val
+
+
 def initAll(fg: FactorGraph, seed=0, ctx: Context | None = None):
     """graphinit: initialise every variable by propagating priors through the factors in insertion order
     (IIF initAll!/doautoinit! uses the same approxConv path)."""

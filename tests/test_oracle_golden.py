@@ -126,6 +126,12 @@ def test_closed_forms_are_roots():
         assert np.linalg.norm(O.pose3pose3(X6, O.pose3pose3_bwd(X6, p6), p6)) < 1e-10
 
 
+def test_accumulated_factor_means_known_answer():
+    """test/testAccumulateFactors.jl:19-30: prior mean zeros, then the odometry mean [10, 0, 0] -> [10, 0, 0] (atol 1e-3)"""
+    val = O.pose2pose2_fwd([10.0, 0.0, 0.0], np.zeros(3))
+    assert np.allclose(val, [10, 0, 0], atol=1e-3) and np.allclose(val, [10, 0, 0], atol=1e-14)
+
+
 def test_pose3_coordinate_roundtrip(golden_dir):
     """test/testPose3.jl:9-23 and the golden Pose3 clouds (test/X1ptst.csv, X2ptst.csv)."""
     rng = np.random.default_rng(2)
