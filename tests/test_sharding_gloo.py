@@ -66,3 +66,43 @@ def test_shard_ranges_cover_everything():
                 assert c <= sharding.shard_size(n, w)
                 seen += list(range(f, f + c))
             assert seen == list(range(n))
+
+
+def test_owner_plan_covers_and_cuts():
+    """owner partition (planned replacement of the all-gather): every factor on exactly one rank, ranges contiguous in
+    the permuted order, cut edges = owner(first) != owner(last), halo = their first variables; on the bench graph the
+    owner exchange moves two orders of magnitude fewer bytes than the all-gather"""
+    import numpy as np
+    from rome_b200 import sharding as S
+    rng = np.random.default_rng(0)
+    V, F, G = 1000, 3000, 4
+    i0 = rng.integers(0, V - 1, F)
+    i1 = np.where(rng.random(F) < 0.9, i0 + 1, rng.integers(0, V, F))
+    plan = S.owner_plan(i0, i1, V, V, G)
+    assert sorted(plan["order"].tolist()) == list(range(F))
+    assert sum(c for _, c in plan["ranges"]) == F
+    for r, (a, c) in enumerate(plan["ranges"]):
+        ids = plan["order"][a:a + c]
+        assert np.all(S.owner_of(i1[ids], V, G) == r)
+    own0, own1 = S.owner_of(i0, V, G), S.owner_of(i1, V, G)
+    assert np.array_equal(plan["cut"], own0 != own1)
+    assert sum(len(v) for v in plan["send_bwd"].values()) == int(plan["cut"].sum())
+    for (src, dst), ids in plan["send_bwd"].items():
+        assert src != dst and np.all(own1[ids] == src) and np.all(own0[ids] == dst)
+    for r in range(G):
+        assert np.all(S.owner_of(plan["halo"][r], V, G) != r)
+        assert set(plan["halo"][r]) == set(i0[plan["cut"] & (own1 == r)])
+    pri = S.owner_plan(np.array([0, V - 1]), None, V, None, G)
+    assert not pri["cut"].any() and [c for _, c in pri["ranges"]] == [1, 0, 0, 1]
+    # the bench graph (10 000 Pose2, 11 999 Pose2Pose2, N = 100 -> 1248-B rows, 1296-B particle blocks)
+    import rome_b200 as rb
+    fg = rb.generateGraph_ManhattanShaped(10000, seed=2, N=100)
+    idx = {l: v.index for l, v in fg.variables.items()}
+    fs = [f for f in fg.factors.values() if isinstance(f.fnc, rb.Pose2Pose2)]
+    a = np.array([idx[f.variableOrderSymbols[0]] for f in fs])
+    b = np.array([idx[f.variableOrderSymbols[1]] for f in fs])
+    for world, most in ((2, 0.04), (8, 0.10)):
+        p = S.owner_plan(a, b, 10000, 10000, world)
+        assert 0 < p["cut"].mean() < most
+        ag, ow = S.exchange_bytes(p, len(fs), world, 1248, 1296)
+        assert ow * 20 < ag
