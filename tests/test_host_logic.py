@@ -49,6 +49,34 @@ def test_no_cpu_fallback_without_gpu():
     assert ei.value.code == -5
 
 
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """the drop-in boundary is a C ABI: include/rome_b200.h compiles as pedantic C99, a C program links against the
+    library, and without a device rome_b200_create reports ROME_B200_NO_DEVICE with a message (no CPU fallback)"""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "abi.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <string.h>\n#include "rome_b200.h"\n'
+        "int main(void) {\n"
+        "  rome_b200_ctx* c = 0; int dm = 0, dr = 0, ns = 0, dj = 0;\n"
+        "  if (rome_b200_version() != ROME_B200_VERSION) return 2;\n"
+        "  if (rome_b200_family_dims(ROME_B200_POSE3POSE3, &dm, &dr, &ns, &dj) != ROME_B200_OK || dm != 6 || dr != 6) return 3;\n"
+        "  if (rome_b200_npad(100) != 104 || rome_b200_vartype_dim(ROME_B200_POSE2) != 3) return 4;\n"
+        "  if (rome_b200_set_particles(0, 0, 0, 1, 0) != ROME_B200_BAD_ARG) return 5;\n"
+        "  int rc = rome_b200_create(0, &c);\n"
+        '  printf("%d %s\\n", rc, rome_b200_last_error(c));\n'
+        "  if (rc == ROME_B200_OK) return rome_b200_destroy(c);\n"
+        "  return (rc == ROME_B200_NO_DEVICE && c == 0 && strlen(rome_b200_last_error(0)) > 0) ? 0 : 6;\n}\n")
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(rb.SO_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src),
+                    "-o", str(exe), "-L", libdir, "-lrome_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+
+
 def test_dims_queries():
     lib = ctypes.CDLL(rb.SO_PATH)
     for fam, (vt0, vt1, dm, dr, ns, dj, dfwd, dbwd) in rb.FAMILY.items():
