@@ -75,6 +75,14 @@ def test_header_is_plain_c_and_links_from_c(tmp_path):
                     "-o", str(exe), "-L", libdir, "-lrome_b200", f"-Wl,-rpath,{libdir}"], check=True)
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    # the C example of INTEGRATION.md builds the same way; without a device it stops at rome_b200_create (exit 77)
+    ex = tmp_path / "hexagonal"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "hexagonal.c"), "-o", str(ex), "-L", libdir, "-lrome_b200",
+                    f"-Wl,-rpath,{libdir}", "-lm"], check=True)
+    import torch
+    if not torch.cuda.is_available():
+        assert subprocess.run([str(ex)], capture_output=True, text=True).returncode == 77
 
 
 def test_dims_queries():
