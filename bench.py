@@ -479,27 +479,6 @@ def main():
         pms = timed(gp) / args.steps
         pms_serial = timed(capture(kernel_only_supplied, False)) / args.steps if overlap else pms
         del meas_sets
-        # solveTree!-shaped proxy: gibbsIters = 3 sweeps, each convolving every Pose2Pose2 factor in both directions
-        # (closed-form proposals + residual check + stats, in-kernel sampling) and the prior -- what IIF's
-        # approxConvBelief loop does with a Nelder-Mead solve per particle (tree + KDE products excluded on both sides)
-        conv_ms = None
-        if not multi:
-            cf = rb.SAMPLE | rb.RESIDUAL | rb.STATS
-            c0, b0, p0 = sets[0]
-            fwd = torch.zeros((F, Np, 3), device="cuda")
-            bwd = torch.zeros((F, Np, 3), device="cuda")
-            pfw = torch.zeros((len(w["pr_ip"]), Np, 3), device="cuda")
-
-            def conv_sweeps(k, indep):
-                for it in range(3):
-                    c0.eval(rb.PRIORPOSE2, cf | rb.PROPOSAL_FWD, seed=11, stream_id=6 * k + 2 * it, prop_fwd=pfw, **p0)
-                    c0.eval(rb.POSE2POSE2, cf | rb.PROPOSAL_FWD | rb.INDEPENDENT, seed=11, stream_id=6 * k + 2 * it,
-                            prop_fwd=fwd, **b0)
-                    c0.eval(rb.POSE2POSE2, cf | rb.PROPOSAL_BWD | rb.INDEPENDENT, seed=11, stream_id=6 * k + 2 * it + 1,
-                            prop_bwd=bwd, **b0)
-            saved_steps, args.steps = args.steps, 20
-            conv_ms = timed(capture(conv_sweeps, True)) / 20
-            args.steps = saved_steps
 
     t = torch.tensor([ms], device="cuda", dtype=torch.float64)
     if multi:
@@ -612,24 +591,28 @@ def main():
             v, nt, reps, dt = cpu_sweep_rate(w, args.cpu_seconds)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": nt, "kind": "port",
                                     "sample": f"{reps} full residual sweeps ({F0 + n_prior} factors x {N} particles) in {dt:.1f} s"}
-            line["cpu_reference_shaped"] = cpu_reference_shaped(w)
-            cps = line["cpu_reference_shaped"]["convolved_particles_per_s"]
-            n_conv = 3 * (2 * F0 + n_prior) * N  # convolved particles in the 3 sweeps
-            sw = device_sweeps(3)
-            cpp = cpu_product_shaped(w)
-            line["cpu_product_shaped"] = cpp
-            line["solve_shaped"] = {
-                "definition": "gibbsIters=3 device-resident sweeps over the whole graph, N=100: every factor convolves forward and "
-                              "backward (fused getSample + closed-form roots), then every variable takes the product of its "
-                              "proposal KDEs on the GPU (rome_b200_product) -- particles never leave the device; measured wall "
-                              "clock around the 3 sweeps.  CPU (all host cores): Nelder-Mead per particle x 3 inflation cycles "
-                              "(IIF-shaped) for the convolutions + the C port of the same product sampler, both extrapolated "
-                              "from measured sample rates; Bayes tree excluded on both sides",
-                "convolved_particles": n_conv, "gpu_ms": sw["ms"], "gpu_ms_convolutions": sw["ms_conv"],
-                "gpu_ms_products": sw["ms_prod"], "cpu_s_convolutions_extrapolated": n_conv / cps,
-                "cpu_s_products_extrapolated": 3 * cpp["s_per_sweep_extrapolated"],
-                "cpu_s_extrapolated": n_conv / cps + 3 * cpp["s_per_sweep_extrapolated"],
-                "speedup": (n_conv / cps + 3 * cpp["s_per_sweep_extrapolated"]) / (sw["ms"] * 1e-3)}
+            # secondary comparison (solveTree!-shaped): never allowed to take the headline line down with it
+            try:
+                line["cpu_reference_shaped"] = cpu_reference_shaped(w)
+                cps = line["cpu_reference_shaped"]["convolved_particles_per_s"]
+                n_conv = 3 * (2 * F0 + n_prior) * N  # convolved particles in the 3 sweeps
+                sw = device_sweeps(3)
+                cpp = cpu_product_shaped(w)
+                line["cpu_product_shaped"] = cpp
+                line["solve_shaped"] = {
+                    "definition": "gibbsIters=3 device-resident sweeps over the whole graph, N=100: every factor convolves forward and "
+                                  "backward (fused getSample + closed-form roots), then every variable takes the product of its "
+                                  "proposal KDEs on the GPU (rome_b200_product) -- particles never leave the device; measured wall "
+                                  "clock around the 3 sweeps.  CPU (all host cores): Nelder-Mead per particle x 3 inflation cycles "
+                                  "(IIF-shaped) for the convolutions + the C port of the same product sampler, both extrapolated "
+                                  "from measured sample rates; Bayes tree excluded on both sides",
+                    "convolved_particles": n_conv, "gpu_ms": sw["ms"], "gpu_ms_convolutions": sw["ms_conv"],
+                    "gpu_ms_products": sw["ms_prod"], "cpu_s_convolutions_extrapolated": n_conv / cps,
+                    "cpu_s_products_extrapolated": 3 * cpp["s_per_sweep_extrapolated"],
+                    "cpu_s_extrapolated": n_conv / cps + 3 * cpp["s_per_sweep_extrapolated"],
+                    "speedup": (n_conv / cps + 3 * cpp["s_per_sweep_extrapolated"]) / (sw["ms"] * 1e-3)}
+            except Exception as e:  # noqa: BLE001
+                line["solve_shaped"] = {"error": f"{type(e).__name__}: {e}"}
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
