@@ -178,6 +178,30 @@ def test_philox_known_answer():
     assert abs(z.mean()) < 0.03 and abs(z.std() - 1) < 0.03
 
 
+def test_sampler_twin_is_standard_normal_and_uncorrelated():
+    """statistics of the host twin of the in-kernel sampler (Philox4x32-10 + Box-Muller, counter = (particle, factor,
+    stream, block); the device draws equal it to ~1e-4 sigma, tests/test_gpu_parity_raw.py): Kolmogorov-Smirnov against
+    N(0, 1), no correlation between the four normals of a block, between neighbouring particles, factors, sweeps
+    (stream ids) and seeds"""
+    from scipy import stats
+    z = np.array([[O.normal4(7, 0, f, n) for n in range(128)] for f in range(48)])  # [factor][particle][4]
+    assert stats.kstest(z.ravel(), "norm").pvalue > 1e-3
+    assert abs(stats.skew(z.ravel())) < 0.06 and abs(stats.kurtosis(z.ravel())) < 0.12
+    flat = z.reshape(-1, 4)
+    c = np.corrcoef(flat.T)
+    assert np.abs(c - np.eye(4)).max() < 0.04                      # within a block
+    bound = 4.5 / math.sqrt(flat.shape[0] * 4)                      # 4.5 sigma of a sample correlation
+
+    def corr(a, b):
+        return abs(np.corrcoef(a.ravel(), b.ravel())[0, 1])
+    assert corr(z[:, :-1], z[:, 1:]) < bound                        # particle n vs n + 1
+    assert corr(z[:-1], z[1:]) < bound                              # factor f vs f + 1
+    z1 = np.array([[O.normal4(7, 1, f, n) for n in range(128)] for f in range(48)])
+    z2 = np.array([[O.normal4(8, 0, f, n) for n in range(128)] for f in range(48)])
+    assert corr(z, z1) < bound and corr(z, z2) < bound              # sweep s vs s + 1, seed vs seed + 1
+    assert not np.array_equal(z, z1) and not np.array_equal(z, z2)
+
+
 def test_next_row_families(ka):
     """Pose2Point2Bearing known answers (test/testBearing2D.jl) and the closed-form point factors"""
     for c in ka["pose2point2bearing"]:
