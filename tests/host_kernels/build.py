@@ -1,0 +1,79 @@
+"""Builds tests/host_kernels' emulation library: the factor-family kernel SOURCES (text regions of csrc/*.cu / *.cuh)
+compiled as host C++ behind hk_shim.h.  TEST INFRASTRUCTURE for the CPU suite -- nothing under rome.jl_b200/ knows about
+it, and it is never used when a GPU test runs."""
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+CSRC = os.path.join(ROOT, "rome.jl_b200", "csrc")
+BANNER = "// ==="
+DASHES = "// ---"
+
+
+def _read(name):
+    return open(os.path.join(CSRC, name)).read()
+
+
+def _between(src, start_marker, end_marker, back_to_banner=True):
+    a = src.index(start_marker)
+    if back_to_banner:  # include the comment banner the marker sits in
+        a = src.rfind("\n", 0, src.rfind("// ", 0, a) if False else a) + 1
+        while True:  # walk back over the comment lines above
+            prev = src.rfind("\n", 0, a - 1) + 1
+            if src[prev:a].lstrip().startswith("//"):
+                a = prev
+            else:
+                break
+    b = src.index(end_marker, a) if end_marker else len(src)
+    if end_marker and back_to_banner:
+        while True:
+            prev = src.rfind("\n", 0, b - 1) + 1
+            if src[prev:b].lstrip().startswith("//"):
+                b = prev
+            else:
+                break
+    return src[a:b]
+
+
+def family_region(name):
+    s = _read(name)
+    a = s.index("namespace rome {") + len("namespace rome {")
+    b = s.index("\nint launch_", a)
+    return f"\n// ===== {name} =====\n" + s[a:b] + "\n"
+
+
+def source_text():
+    du, ep, se, fk = _read("device_utils.cuh"), _read("eval_pipeline.cuh"), _read("se3_common.cuh"), _read("factor_kernels.cu")
+    parts = ['#include "hk_shim.h"\n#include <vector>\n', f'#include "{os.path.join(CSRC, "tables.h")}"\n', "namespace rome {\n"]
+    parts.append(_between(du, "constexpr double kPi", "// mbarrier + TMA"))
+    parts.append(_between(du, "// Float64 angle helpers", "}  // namespace rome", back_to_banner=True))
+    parts.append(_between(ep, "// SE(2) statistics accumulator", "// stage layout (shared by host planning and the kernel)"))
+    parts.append(_between(fk, "// layout conversion: reference layout", "__global__ void adopt_kernel"))
+    parts.append(family_region("fam_pose2.cu"))
+    parts.append(family_region("fam_bearingrange.cu"))
+    parts.append(family_region("fam_point2.cu"))
+    parts.append(family_region("fam_point3.cu"))
+    se_body = se[se.index("namespace rome {") + len("namespace rome {"):se.rindex("}  // namespace rome")]
+    parts.append("\n// ===== se3_common.cuh =====\n" + se_body)
+    parts.append(family_region("fam_se3.cu"))
+    parts.append(family_region("fam_se3_partial.cu"))
+    parts.append(open(os.path.join(HERE, "hk_main.inc")).read())
+    return "".join(parts)
+
+
+def build(outdir):
+    os.makedirs(outdir, exist_ok=True)
+    src = os.path.join(outdir, "host_kernels.cpp")
+    so = os.path.join(outdir, "libhost_kernels.so")
+    open(src, "w").write(source_text())
+    cmd = ["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-I", HERE, src, "-o", so, "-lm"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("host build of the kernel sources failed:\n" + r.stderr[-6000:])
+    return so
+
+
+if __name__ == "__main__":
+    import sys
+    print(build(sys.argv[1] if len(sys.argv) > 1 else "/tmp/host_kernels"))

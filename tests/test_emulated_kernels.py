@@ -1,0 +1,140 @@
+"""The factor-family kernel SOURCES run on the CPU (tests/host_kernels: host build of the source text of csrc/fam_*.cu,
+se3_common.cuh and the pack / unpack kernels behind a 32-lane warp emulator) through the very parity tests the GPU
+suite runs -- same inputs, same oracle, same tolerances -- by handing those test functions an emulated context.
+What this covers without a GPU: the families' arithmetic with its warp-uniform fast-path votes, masking of padding
+lanes, the halving-butterfly statistics, closed-form proposals, Jacobians, the in-kernel sampler's counters, the
+particle-store layout kernels and every particle-count regime (N = 1 ... 2000).  What only the GPU suite covers: the
+TMA/mbarrier pipeline, streams and graphs, the product kernel, the C ABI's argument checking, MUFU approximations."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests", "host_kernels"))
+
+
+@pytest.fixture(scope="module")
+def ectx(tmp_path_factory):
+    import shutil
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    import build as hk_build
+    from emu import EmulatedContext
+    return EmulatedContext(hk_build.build(str(tmp_path_factory.mktemp("host_kernels"))))
+
+
+def _raw():
+    import test_gpu_parity_raw as T
+    return T
+
+
+@pytest.mark.parametrize("N", [100, 37, 200])
+def test_pose2pose2(ectx, N):
+    _raw().test_pose2pose2_parity(ectx, N)
+
+
+def test_priorpose2_bearingrange_priorpose3(ectx):
+    T = _raw()
+    T.test_priorpose2_parity(ectx)
+    T.test_bearingrange_parity(ectx)
+    T.test_priorpose3_parity(ectx)
+
+
+@pytest.mark.parametrize("N", [100, 64])
+def test_pose3pose3(ectx, N):
+    _raw().test_pose3pose3_parity(ectx, N)
+
+
+def test_layout_roundtrip_nan_and_wide_headings(ectx):
+    T = _raw()
+    T.test_particle_roundtrip(ectx)
+    T.test_nan_propagates(ectx)
+    T.test_wide_heading_spread_takes_general_sincos_path(ectx)
+
+
+@pytest.mark.parametrize("family", ["pose2pose2", "priorpose2", "bearingrange", "pose3pose3", "priorpose3"])
+def test_fused_sampling(ectx, family):
+    _raw().test_fused_sampling_matches_supplied_and_host_twin(ectx, family)
+
+
+@pytest.mark.parametrize("N", [1, 8, 33, 129, 500, 2000])
+def test_particle_counts(ectx, N):
+    _raw().test_particle_count_edge_cases(ectx, N)
+
+
+# ---- the remaining families and the reference-named host API, on the same emulated device ---------------------------
+@pytest.fixture()
+def emulated_api(ectx, monkeypatch):
+    """route every context the host API creates to the emulated device (Context(0), DeviceGraph's default, default_context)"""
+    import rome_b200 as rb
+    from rome_b200 import graph as G
+    make = lambda device=0: ectx  # noqa: E731 -- one shared emulated device, like default_context()
+    monkeypatch.setattr(rb, "Context", make)
+    monkeypatch.setattr(G, "Context", make)
+    monkeypatch.setattr(G, "default_context", make)
+    monkeypatch.setattr(rb, "default_context", make)
+    return ectx
+
+
+@pytest.mark.parametrize("N", [100, 37])
+def test_next_families_2d(ectx, N):
+    import test_gpu_next_families as T
+    T.test_point2_gaussian_families(ectx, N)
+    T.test_scalar_families(ectx, N)
+
+
+@pytest.mark.parametrize("N", [100, 37])
+def test_next_families_3d(ectx, N, golden_dir):
+    import test_gpu_next_families_3d as T
+    T.test_point3_families(ectx, N)
+    T.test_pose3_partial_families(ectx, N)
+    T.test_known_answers_3d(ectx, golden_dir)
+
+
+def test_next_families_through_the_graph_api(emulated_api, golden_dir):
+    import test_gpu_next_families as T
+    T.test_bearing_known_answers(golden_dir)
+    T.test_graph_api_with_point_factors()
+
+
+def test_deconvolution(emulated_api):
+    import test_gpu_deconv as T
+    T.test_deconv_pose2_families(emulated_api)
+    T.test_deconv_pose3_families(emulated_api)
+    T.test_approxdeconv_reproduces_the_measurement_belief(emulated_api)
+
+
+def test_reference_known_answers_through_the_host_api(emulated_api, golden_dir):
+    import json
+    import test_gpu_graph_api as T
+    ka = json.load(open(os.path.join(golden_dir, "known_answers.json")))
+    T.test_known_answers_pose2pose2(ka)
+    T.test_known_answers_bearingrange(ka)
+    T.test_known_answers_pose3pose3(ka)
+    T.test_priors_zero_at_measurement()
+
+
+def test_canonical_graphs_and_fixtures(emulated_api, golden_dir):
+    import test_gpu_graph_api as T
+    T.test_hexagonal_graph_all_families()
+    T.test_manhattan500_fixture_parity(golden_dir)
+    T.test_manhattan_g2o_full_graph(golden_dir)
+    T.test_approxconv_and_samplefactor()
+    T.test_beehive_and_pose3_chain_parity()
+
+
+def test_parametric_solves(emulated_api):
+    import test_gpu_parametric as T
+    T.test_square_loop(emulated_api)
+    T.test_information_weighting(emulated_api)
+    T.test_bearing_range_triangulation(emulated_api)
+    T.test_pose3_loop(emulated_api)
+
+
+def test_accumulated_factor_means(emulated_api):
+    import test_gpu_zz_accumulate as T
+    T.test_accumulate_factor_means_reference_case()
+    T.test_accumulate_along_hexagon_and_back()
