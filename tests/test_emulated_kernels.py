@@ -138,3 +138,69 @@ def test_accumulated_factor_means(emulated_api):
     import test_gpu_zz_accumulate as T
     T.test_accumulate_factor_means_reference_case()
     T.test_accumulate_along_hexagon_and_back()
+
+
+def test_full_size_baseline_workloads(emulated_api):
+    """BASELINE configs at FULL size on the emulated device (the oracle sweeps them in milliseconds, the emulator in
+    seconds): T = 10 000 Pose2 / 11 999 Pose2Pose2 + prior, N = 100 (the bench workload); C4 = Beehive-shaped 3 000 poses
+    with bearing-range sightings, N = 200; C5 = SE(3) chain of 3 000 poses + 300 loops, N = 100.  Per config: residuals
+    against the oracle on the written-back samples (1e-5 relative, floor 1e-2 as in the GPU suite), forward proposals
+    are roots of the residual, statistics equal the sums over the live particles."""
+    import bench
+    import rome_b200 as rb
+    from oracle import oracle as O
+    c, N = emulated_api, 100
+    w = bench.build_workload(1)
+    c.set_particles(rb.POSE2, w["poses"])
+    c.set_factors_pose2pose2(w["ip"], w["iq"], w["mu"], w["cov"])
+    fl = rb.SAMPLE | rb.RESIDUAL | rb.STATS | rb.PROPOSAL_FWD | rb.WRITE_MEAS
+    out = c.alloc_host_outputs(rb.POSE2POSE2, fl)
+    c.eval_host(rb.POSE2POSE2, fl, seed=7, **out)
+    seen = rb.dequantized_particles(c.get_anchors(rb.POSE2), c.get_offsets(rb.POSE2), N)
+    meas = rb.offsets_to_meas(out["meas_out"], w["mu"], N)
+    res = rb.rows_to_particle_major(out["res"], N)
+    ref = O.sweep_pose2pose2(w["ip"], w["iq"], seen, meas)
+    d = res - ref
+    d[..., 2] = O.np_wrap(d[..., 2])
+    assert (np.abs(d) / np.maximum(np.abs(ref), 1e-7)).max() < 1e-5   # same inputs: pure relative down to 1e-7
+    prop = rb.rows_to_particle_major(out["prop_fwd"], N) + c.get_anchors(rb.POSE2)[w["iq"]][:, None, :]
+    # the proposal zeroes the residual: evaluate the oracle with q := proposal (one factor at a time would be slow; stack)
+    stacked = np.concatenate([seen, prop])
+    r0 = O.sweep_pose2pose2(w["ip"], np.arange(len(w["ip"]), dtype=np.int32) + len(seen), stacked, meas)
+    r0[..., 2] = O.np_wrap(r0[..., 2])
+    assert np.abs(r0).max() < 2e-5   # float32 rounding of proposal coordinates of magnitude <= ~150 m
+    assert np.allclose(out["stats"][:, 0:3], res.sum(1), rtol=1e-3, atol=2e-3)
+    # the bench's second family
+    c.set_factors_priorpose2(w["pr_ip"], w["pr_mu"], w["pr_cov"])
+    o = c.alloc_host_outputs(rb.PRIORPOSE2, rb.SAMPLE | rb.RESIDUAL | rb.STATS | rb.WRITE_MEAS)
+    c.eval_host(rb.PRIORPOSE2, rb.SAMPLE | rb.RESIDUAL | rb.STATS | rb.WRITE_MEAS, seed=7, **o)
+    rp = O.sweep_priorpose2(w["pr_ip"], seen, rb.offsets_to_meas(o["meas_out"], w["pr_mu"], N))
+    assert np.abs(rb.rows_to_particle_major(o["res"], N) - rp).max() < 1e-6
+
+    # C4 / C5 through the graph API, like tests/test_gpu_graph_api.py but at thousands of poses
+    fl = rb.RESIDUAL | rb.SAMPLE | rb.WRITE_MEAS
+    bh = rb.generateGraph_Beehive(3000, N=200)
+    rb.seed_particles(bh, N=200, seed=3)
+    dg = rb.DeviceGraph(bh)
+    poses = np.stack([v.val for v in dg.by_type[rb.POSE2]])
+    points = np.stack([v.val for v in dg.by_type[rb.POINT2]])
+    o = dg.eval(rb.BEARINGRANGE, fl, seed=1)
+    facs = dg.by_family[rb.BEARINGRANGE]
+    ip = [bh[f.variableOrderSymbols[0]].index for f in facs]
+    il = [bh[f.variableOrderSymbols[1]].index for f in facs]
+    assert len(facs) == 3001
+    ref = O.sweep_bearingrange(ip, il, poses, points, o["meas"])
+    d = o["res"] - ref
+    d[..., 0] = O.np_wrap(d[..., 0])
+    assert (np.abs(d) / np.maximum(np.abs(ref), 1e-2)).max() < 1e-5
+    p3 = rb.generateGraph_Pose3Chain(3000, loops=300)
+    rb.seed_particles(p3, seed=4)
+    dg3 = rb.DeviceGraph(p3)
+    o = dg3.eval(rb.POSE3POSE3, fl, seed=1)
+    facs = dg3.by_family[rb.POSE3POSE3]
+    assert len(facs) >= 3200
+    ip = [p3[f.variableOrderSymbols[0]].index for f in facs]
+    iq = [p3[f.variableOrderSymbols[1]].index for f in facs]
+    poses3 = np.stack([v.val for v in dg3.by_type[rb.POSE3]])
+    ref = O.sweep_pose3pose3(ip, iq, poses3, o["meas"])
+    assert (np.abs(o["res"] - ref) / np.maximum(np.abs(ref), 1e-2)).max() < 1e-5
