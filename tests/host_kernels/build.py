@@ -2,6 +2,7 @@
 compiled as host C++ behind hk_shim.h.  TEST INFRASTRUCTURE for the CPU suite -- nothing under rome.jl_b200/ knows about
 it, and it is never used when a GPU test runs."""
 import os
+import re
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -58,8 +59,16 @@ def source_text():
     parts.append("\n// ===== se3_common.cuh =====\n" + se_body)
     parts.append(family_region("fam_se3.cu"))
     parts.append(family_region("fam_se3_partial.cu"))
+    pk = _read("product_kernels.cu")
+    parts.append("\n// ===== product_kernels.cu =====\n" + pk[pk.index("constexpr int kProdWarps"):pk.index("\nint launch_product")] + "\n")
     parts.append(open(os.path.join(HERE, "hk_main.inc")).read())
-    return "".join(parts)
+    text = "".join(parts)
+    # the few PTX statements of the compiled regions are MUFU approximations: substitute the exact functions
+    exact = {"rsqrt": "1.0f / std::sqrt", "lg2": "std::log2"}
+    text, n = re.subn(r'asm\("(\w+)\.approx\.ftz\.f32 %0, %1;"\s*:\s*"=f"\((\w+)\)\s*:\s*"f"\((.+?)\)\);',
+                      lambda m: f"{m.group(2)} = {exact[m.group(1)]}({m.group(3)});", text)
+    assert n >= 2 and "asm(" not in text and "asm volatile" not in text
+    return text
 
 
 def build(outdir):

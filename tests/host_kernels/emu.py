@@ -170,6 +170,75 @@ class EmulatedContext:
         assert rc == 0
         self.launch_count += 1
 
+    # the device-pointer entry point: "device memory" of the emulated device is host memory (malloc_device below)
+    def eval(self, family, flags, *, seed=0, stream_id=0, first=0, count=-1, meas=None, meas_out=None, res=None,
+             prop_fwd=None, prop_bwd=None, stats=None, jac=None):
+        def view(p, d):
+            if p is None or isinstance(p, np.ndarray):
+                return p
+            nF, Np = len(self._rows[family]), self._shape[FAMILY[family][0]][2]
+            n = nF * (Np * d if d > 0 else -d)
+            return np.ctypeslib.as_array(C.cast(int(p), C.POINTER(C.c_float)), shape=(n,))
+        _, _, dm, dr, ns, dj, dfwd, dbwd = FAMILY[family]
+        self.eval_host(family, flags & ~L.INDEPENDENT, seed=seed, stream_id=stream_id, first=first, count=count,
+                       meas=view(meas, dm), meas_out=view(meas_out, dm), res=view(res, dr), prop_fwd=view(prop_fwd, dfwd),
+                       prop_bwd=view(prop_bwd, dbwd), stats=view(stats, -ns), jac=view(jac, dj))
+
+    # -- "device" memory ------------------------------------------------------------------------------------------------
+    def malloc_device(self, nbytes):
+        a = np.zeros(max(1, (int(nbytes) + 3) // 4), np.float32)
+        self._mem = getattr(self, "_mem", {})
+        self._mem[a.ctypes.data] = a
+        return a.ctypes.data
+
+    def free_device(self, ptr):
+        self._mem.pop(int(ptr), None)
+
+    def memcpy_h2d(self, dst_ptr, src):
+        src = np.ascontiguousarray(src)
+        C.memmove(int(dst_ptr), src.ctypes.data, src.nbytes)
+
+    def memcpy_d2h(self, dst, src_ptr):
+        C.memmove(dst.ctypes.data, int(src_ptr), dst.nbytes)
+
+    # -- belief update (product of proposal densities) --------------------------------------------------------------------
+    def set_product_plan(self, vartype, var_offsets, src_buf, src_row):
+        off, sb, sr = (np.ascontiguousarray(a, dtype=np.int32) for a in (var_offsets, src_buf, src_row))
+        if len(off) < 1 or off[0] != 0 or np.any(np.diff(off) < 0) or off[-1] != len(sb) or len(sb) != len(sr):
+            raise rb.RomeB200Error(L.BAD_ARG, "bad plan arrays")
+        if np.any(np.diff(off) > L.MAX_PRODUCT_SOURCES):
+            raise rb.RomeB200Error(L.BAD_ARG, "too many proposals for one variable")
+        if len(sb) and (sb.min() < 0 or sb.max() >= 16 or sr.min() < 0):
+            raise rb.RomeB200Error(L.BAD_ARG, "source buffer index / row out of range")
+        self._plan = getattr(self, "_plan", {})
+        self._plan[vartype] = (off, sb, sr)
+
+    def product(self, vartype, bufs, *, seed=0, stream_id=0, gibbs_iters=0, reanchor=True, bw_out=None):
+        off, sb, sr = self._plan[vartype]
+        nvars, N, Np = self._shape[vartype]
+        if len(off) - 1 != nvars:
+            raise rb.RomeB200Error(L.NOT_SET, "no product plan for this variable type (or its size differs)")
+        if len(sb) and sb.max() >= len(bufs):
+            raise rb.RomeB200Error(L.BAD_ARG, "the plan refers to more proposal buffers than were passed")
+        d = VAR_DIM[vartype]
+        arr = (C.c_void_p * max(1, len(bufs)))(*[int(b) for b in bufs])
+        self._hk.hk_product.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                        C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint32, C.c_float]
+        rc = self._hk.hk_product(d, _WRAP[vartype], self._store[vartype].ctypes.data, off.ctypes.data, sb.ctypes.data,
+                                 sr.ctypes.data, len(bufs), arr, None if bw_out is None else int(bw_out), nvars, N, Np,
+                                 gibbs_iters if gibbs_iters > 0 else 2, seed, stream_id,
+                                 float((4.0 / ((d + 2.0) * N)) ** (1.0 / (d + 4.0))))
+        assert rc == 0
+        self.launch_count += 1
+        if reanchor:
+            self.reanchor(vartype)
+
+    def reanchor(self, vartype):
+        nvars, N, Np = self._shape[vartype]
+        self._hk.hk_reanchor.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        assert self._hk.hk_reanchor(VAR_DIM[vartype], _WRAP[vartype], self._store[vartype].ctypes.data, nvars, N, Np) == 0
+        self.launch_count += 1
+
     def synchronize(self):
         pass
 

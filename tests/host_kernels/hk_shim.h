@@ -1,10 +1,10 @@
 // hk_shim.h -- TEST INFRASTRUCTURE (CPU suite only; never part of the product path).
 // Lets the SOURCE TEXT of the factor-family kernels (csrc/fam_*.cu, se3_common.cuh, the arithmetic parts of
 // device_utils.cuh / eval_pipeline.cuh, the pack/unpack kernels) compile as host C++: CUDA vocabulary as no-ops, the few
-// intrinsics the families use, and a 32-lane warp emulator (one fiber per lane, switched at every warp collective) so
-// that __any_sync / __all_sync / __shfl_xor_sync behave as on the device.  What is NOT emulated: the TMA/mbarrier
+// intrinsics the kernels use, and a thread emulator (one fiber per CUDA thread of a block, switched at every warp or block
+// collective) so that __any_sync / __all_sync / __shfl_*_sync / __syncwarp / __syncthreads behave as on the device.  What is NOT emulated: the TMA/mbarrier
 // pipeline (the harness hands every factor its inputs directly) and the MUFU approximations (the accurate sampler
-// branch is compiled; sqrt_seeded's seed is the exact reciprocal square root).
+// branch is compiled; the `*.approx.ftz.f32` PTX statements are replaced by the exact functions in build.py).
 #pragma once
 #include <ucontext.h>
 
@@ -28,7 +28,6 @@ struct float2 { float x, y; };
 struct float4 { float x, y, z, w; };
 struct double2 { double x, y; };
 struct int2 { int x, y; };
-struct uint3 { unsigned x, y, z; };
 struct uint4 { uint32_t x, y, z, w; };
 static inline float2 make_float2(float x, float y) { return {x, y}; }
 static inline float4 make_float4(float x, float y, float z, float w) { return {x, y, z, w}; }
@@ -53,80 +52,111 @@ static inline double __hiloint2double(int hi, int lo) {
     const uint64_t b = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo;
     double v; std::memcpy(&v, &b, 8); return v;
 }
-// the one PTX statement in the compiled regions: sqrt_seeded's `rsqrt.approx.ftz.f32` seed
-#define asm(...) (y0 = 1.0f / std::sqrt((float)a))
 
-// kernels launched as grids (pack / unpack): the harness sets these before calling the kernel body per lane
-static uint3 threadIdx, blockIdx, blockDim;
-
-// ---- warp emulator: 32 fibers, round-robin, switched at collectives ------------------------------------------------
+// ---- thread emulator: one fiber per CUDA thread of ONE block, round-robin, switched at every collective --------------
+// Warp collectives (__any_sync, __all_sync, __shfl_*_sync, __syncwarp) rendezvous the 32 fibers of a warp, __syncthreads
+// all fibers of the block; a fiber that arrives early keeps yielding until its rendezvous is complete, so warps may
+// run ahead of each other exactly as far as the barriers of the kernel allow.
+struct dim3_ { unsigned x, y, z; };
+static dim3_ blockIdx = {0, 1, 1}, blockDim = {32, 1, 1}, gridDim = {1, 1, 1};
 namespace hk {
-constexpr int kLanes = 32;
+constexpr int kMaxThreads = 128;
 constexpr size_t kStack = 256 * 1024;
-static ucontext_t g_sched, g_lane[kLanes];
-static char* g_stack[kLanes];
-static bool g_done[kLanes];
-static int g_cur = 0;
-static uint32_t g_x[2][kLanes];
-static unsigned g_phase[kLanes];
+static ucontext_t g_sched, g_fiber[kMaxThreads];
+static char* g_stack[kMaxThreads];
+static bool g_done[kMaxThreads];
+static int g_cur = 0, g_nthreads = 32;
+static uint32_t g_x[2][kMaxThreads];
+static unsigned g_warp_phase[kMaxThreads], g_warp_deposits[kMaxThreads / 32];
+static unsigned g_block_phase[kMaxThreads], g_block_arrivals;
 static std::function<void(int)> g_body;
 
+static inline dim3_ tid3() { return {(unsigned)g_cur, 0, 0}; }
 static void trampoline() {
     g_body(g_cur);
     g_done[g_cur] = true;
-    swapcontext(&g_lane[g_cur], &g_sched);
+    swapcontext(&g_fiber[g_cur], &g_sched);
 }
-// every lane deposits a word, then reads the words of ALL lanes of the same collective (double-buffered by parity)
+static inline void yield_() {
+    const int t = g_cur;
+    swapcontext(&g_fiber[t], &g_sched);
+    g_cur = t;
+}
+// every lane of the warp deposits a word, then reads the words of the warp's 32 lanes (double-buffered by parity)
 static inline const uint32_t* collective(uint32_t v) {
-    const int lane = g_cur;
-    const unsigned k = g_phase[lane]++;
-    g_x[k & 1][lane] = v;
-    swapcontext(&g_lane[lane], &g_sched);  // resumed once every lane has deposited
-    g_cur = lane;
-    return g_x[k & 1];
+    const int t = g_cur, w = t >> 5;
+    const unsigned k = g_warp_phase[t]++;
+    g_x[k & 1][t] = v;
+    ++g_warp_deposits[w];
+    while (g_warp_deposits[w] < 32u * (k + 1)) yield_();
+    return &g_x[k & 1][w << 5];
+}
+static inline void block_barrier() {
+    const int t = g_cur;
+    const unsigned k = g_block_phase[t]++;
+    ++g_block_arrivals;
+    while (g_block_arrivals < (unsigned)g_nthreads * (k + 1)) yield_();
 }
 template <class F>
-static void run_warp(F&& f) {
+static void run_block(int nthreads, F&& f) {
     g_body = f;
-    for (int l = 0; l < kLanes; ++l) {
-        if (!g_stack[l]) g_stack[l] = (char*)std::malloc(kStack);
-        g_done[l] = false;
-        g_phase[l] = 0;
-        getcontext(&g_lane[l]);
-        g_lane[l].uc_stack.ss_sp = g_stack[l];
-        g_lane[l].uc_stack.ss_size = kStack;
-        g_lane[l].uc_link = nullptr;
-        makecontext(&g_lane[l], trampoline, 0);
+    g_nthreads = nthreads;
+    g_block_arrivals = 0;
+    for (int w = 0; w < kMaxThreads / 32; ++w) g_warp_deposits[w] = 0;
+    for (int t = 0; t < nthreads; ++t) {
+        if (!g_stack[t]) g_stack[t] = (char*)std::malloc(kStack);
+        g_done[t] = false;
+        g_warp_phase[t] = g_block_phase[t] = 0;
+        getcontext(&g_fiber[t]);
+        g_fiber[t].uc_stack.ss_sp = g_stack[t];
+        g_fiber[t].uc_stack.ss_size = kStack;
+        g_fiber[t].uc_link = nullptr;
+        makecontext(&g_fiber[t], trampoline, 0);
     }
     for (bool any = true; any;) {
         any = false;
-        for (int l = 0; l < kLanes; ++l)
-            if (!g_done[l]) {
-                g_cur = l;
-                swapcontext(&g_sched, &g_lane[l]);
-                any = any || !g_done[l];
+        for (int t = 0; t < nthreads; ++t)
+            if (!g_done[t]) {
+                g_cur = t;
+                swapcontext(&g_sched, &g_fiber[t]);
+                any = any || !g_done[t];
             }
     }
 }
+template <class F>
+static void run_warp(F&& f) { run_block(32, f); }
 }  // namespace hk
+#define threadIdx (hk::tid3())
 
 static inline int __any_sync(unsigned, int pred) {
     const uint32_t* x = hk::collective(pred ? 1u : 0u);
     uint32_t r = 0;
-    for (int l = 0; l < hk::kLanes; ++l) r |= x[l];
+    for (int l = 0; l < 32; ++l) r |= x[l];
     return (int)r;
 }
 static inline int __all_sync(unsigned, int pred) {
     const uint32_t* x = hk::collective(pred ? 1u : 0u);
     uint32_t r = 1;
-    for (int l = 0; l < hk::kLanes; ++l) r &= x[l];
+    for (int l = 0; l < 32; ++l) r &= x[l];
     return (int)r;
 }
-static inline float __shfl_xor_sync(unsigned, float v, int bit) {
+static inline float hk_shfl(float v, int src_lane_fn(int lane, int arg), int arg) {
     uint32_t u; std::memcpy(&u, &v, 4);
-    const int lane = hk::g_cur;
+    const int lane = hk::g_cur & 31;
     const uint32_t* x = hk::collective(u);
-    float r; std::memcpy(&r, &x[lane ^ bit], 4);
+    const int src = src_lane_fn(lane, arg);
+    float r; std::memcpy(&r, &x[(src < 0 || src > 31) ? lane : src], 4);
     return r;
 }
+static inline float __shfl_xor_sync(unsigned, float v, int bit) { return hk_shfl(v, [](int l, int a) { return l ^ a; }, bit); }
+static inline float __shfl_up_sync(unsigned, float v, int d) { return hk_shfl(v, [](int l, int a) { return l - a; }, d); }
+static inline float __shfl_sync(unsigned, float v, int src) { return hk_shfl(v, [](int, int a) { return a & 31; }, src); }
+static inline void __syncwarp(unsigned = 0xffffffffu) { hk::collective(0u); }
+static inline void __syncthreads() { hk::block_barrier(); }
+template <class T> static inline T __ldg(const T* p) { return *p; }
+#define __sincosf(x, s, c) sincosf((x), (s), (c))
+static inline int max(int a, int b) { return a > b ? a : b; }
+#define __shared__ static
+#define __launch_bounds__(...)
+#define __grid_constant__
 using std::fabs; using std::fmax; using std::fma; using std::rint; using std::sqrt; using std::atan2; using std::sin; using std::cos;

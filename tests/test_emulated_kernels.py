@@ -204,3 +204,17 @@ def test_full_size_baseline_workloads(emulated_api):
     poses3 = np.stack([v.val for v in dg3.by_type[rb.POSE3]])
     ref = O.sweep_pose3pose3(ip, iq, poses3, o["meas"])
     assert (np.abs(o["res"] - ref) / np.maximum(np.abs(ref), 1e-2)).max() < 1e-5
+
+
+def test_product_kernel_and_device_resident_sweeps(emulated_api):
+    """the belief-update kernel (csrc/product_kernels.cu: one block of 4 warps per variable, shared bandwidths and pair
+    CDF, __syncthreads / warp scans) under the block-level thread emulator, through the GPU suite's statistical tests:
+    analytic Gaussian products, heading wrap, multi-modal selection against the NumPy twin, plan errors, and the
+    reference's Hexagonal acceptance boxes after three device-resident sweeps"""
+    import test_gpu_product as T
+    T.test_product_of_gaussians_point2(emulated_api)
+    T.test_product_heading_wraps(emulated_api)
+    T.test_product_multimodal_matches_numpy_twin(emulated_api)
+    T.test_plan_errors(emulated_api)
+    T.test_hexagonal_solve_reference_boxes(emulated_api)
+    T.test_sweeps_on_pose3_chain_and_beehive(emulated_api)
