@@ -26,8 +26,18 @@ def _fp(a):
 
 
 class EmulatedContext:
-    def __init__(self, so_path):
+    """pipeline=False: every factor's inputs are handed to the family arithmetic directly (fast: a warp of fibers per
+    factor).  pipeline=True: the library's OWN kernels run -- eval_kernel / eval_kernel_w with their persistent blocks,
+    producer warp, TMA bulk copies and mbarrier rings (host semantics in hk_shim.h), planned by the library's plan_launch
+    and dispatched by its launch_family -- on at most `grid_cap` blocks."""
+
+    def __init__(self, so_path, pipeline=False, grid_cap=3):
+        self.pipeline, self.grid_cap, self.last_plan = pipeline, grid_cap, None
         self._hk = C.CDLL(so_path)
+        self._hk.hk_eval_pipeline.argtypes = [C.c_int, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                              C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                              C.POINTER(C.c_float), C.c_uint64, C.c_uint32, C.c_int, C.POINTER(C.c_int)]
         self._hk.hk_eval.argtypes = [C.c_int, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float),
                                      C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_uint64, C.c_uint32,
@@ -164,10 +174,22 @@ class EmulatedContext:
                         ("stats", stats), ("jac", jac)):
             assert a is None or (isinstance(a, np.ndarray) and a.dtype == np.float32 and a.flags.c_contiguous), name
         v1 = self._store[vt1] if vt1 is not None else self._store[vt0]
-        rc = self._hk.hk_eval(family, flags, first, count, N, Np, rows.ctypes.data, self._store[vt0].ctypes.data, v1.ctypes.data,
-                              _fp(meas), _fp(meas_out), _fp(res), _fp(prop_fwd), _fp(prop_bwd), _fp(stats), _fp(jac), seed,
-                              stream_id, variant)
-        assert rc == 0
+        if self.pipeline:
+            info = (C.c_int * 6)()
+            rc = self._hk.hk_eval_pipeline(family, flags, first, count, N, Np, rows.ctypes.data, self._store[vt0].ctypes.data,
+                                           v1.ctypes.data, _fp(meas), _fp(meas_out), _fp(res), _fp(prop_fwd), _fp(prop_bwd),
+                                           _fp(stats), _fp(jac), seed, stream_id, self.grid_cap, info)
+            if rc == -3:
+                raise rb.RomeB200Error(L.SHAPE_MISMATCH, "N is too large for the shared-memory pipeline of this family")
+            self.last_plan = dict(zip(("ft", "variant", "stages", "pipeline", "grid", "threads"), info))
+            assert rc == 0, f"emulated kernel failed: {rc} (700 = stopped making progress), plan {self.last_plan}"
+            assert (self.last_plan["ft"], self.last_plan["stages"], self.last_plan["pipeline"]) == \
+                (plan["warps"], plan["stages"], plan["pipeline"])   # the same plan the shipped library reports
+        else:
+            rc = self._hk.hk_eval(family, flags, first, count, N, Np, rows.ctypes.data, self._store[vt0].ctypes.data,
+                                  v1.ctypes.data, _fp(meas), _fp(meas_out), _fp(res), _fp(prop_fwd), _fp(prop_bwd), _fp(stats),
+                                  _fp(jac), seed, stream_id, variant)
+            assert rc == 0
         self.launch_count += 1
 
     # the device-pointer entry point: "device memory" of the emulated device is host memory (malloc_device below)

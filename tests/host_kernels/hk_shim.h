@@ -32,6 +32,7 @@ struct uint4 { uint32_t x, y, z, w; };
 static inline float2 make_float2(float x, float y) { return {x, y}; }
 static inline float4 make_float4(float x, float y, float z, float w) { return {x, y, z, w}; }
 static inline double2 make_double2(double x, double y) { return {x, y}; }
+static inline int2 make_int2(int x, int y) { return {x, y}; }
 static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return {x, y, z, w}; }
 typedef void* cudaStream_t;
 
@@ -60,7 +61,7 @@ static inline double __hiloint2double(int hi, int lo) {
 struct dim3_ { unsigned x, y, z; };
 static dim3_ blockIdx = {0, 1, 1}, blockDim = {32, 1, 1}, gridDim = {1, 1, 1};
 namespace hk {
-constexpr int kMaxThreads = 128;
+constexpr int kMaxThreads = 416;  // eval_kernel: 8 + 1 warps, eval_kernel_w: 12 warps, product_kernel: 4 warps
 constexpr size_t kStack = 256 * 1024;
 static ucontext_t g_sched, g_fiber[kMaxThreads];
 static char* g_stack[kMaxThreads];
@@ -70,6 +71,8 @@ static uint32_t g_x[2][kMaxThreads];
 static unsigned g_warp_phase[kMaxThreads], g_warp_deposits[kMaxThreads / 32];
 static unsigned g_block_phase[kMaxThreads], g_block_arrivals;
 static std::function<void(int)> g_body;
+static unsigned long long g_progress = 0;  // bumped by everything that can unblock a waiting fiber
+static bool g_deadlock = false;
 
 static inline dim3_ tid3() { return {(unsigned)g_cur, 0, 0}; }
 static void trampoline() {
@@ -88,6 +91,7 @@ static inline const uint32_t* collective(uint32_t v) {
     const unsigned k = g_warp_phase[t]++;
     g_x[k & 1][t] = v;
     ++g_warp_deposits[w];
+    ++g_progress;
     while (g_warp_deposits[w] < 32u * (k + 1)) yield_();
     return &g_x[k & 1][w << 5];
 }
@@ -95,6 +99,7 @@ static inline void block_barrier() {
     const int t = g_cur;
     const unsigned k = g_block_phase[t]++;
     ++g_block_arrivals;
+    ++g_progress;
     while (g_block_arrivals < (unsigned)g_nthreads * (k + 1)) yield_();
 }
 template <class F>
@@ -113,14 +118,22 @@ static void run_block(int nthreads, F&& f) {
         g_fiber[t].uc_link = nullptr;
         makecontext(&g_fiber[t], trampoline, 0);
     }
+    g_deadlock = false;
+    unsigned long long idle_rounds = 0;
     for (bool any = true; any;) {
         any = false;
+        const unsigned long long before = g_progress;
         for (int t = 0; t < nthreads; ++t)
             if (!g_done[t]) {
                 g_cur = t;
                 swapcontext(&g_sched, &g_fiber[t]);
                 any = any || !g_done[t];
+                if (g_done[t]) ++g_progress;
             }
+        // a round in which no fiber finished, no rendezvous completed and no barrier word changed is a deadlock of the
+        // emulated kernel (e.g. an mbarrier whose expected byte count never arrives): give up instead of spinning
+        idle_rounds = (g_progress == before) ? idle_rounds + 1 : 0;
+        if (idle_rounds > 4) { g_deadlock = true; return; }
     }
 }
 template <class F>
@@ -154,6 +167,56 @@ static inline float __shfl_sync(unsigned, float v, int src) { return hk_shfl(v, 
 static inline void __syncwarp(unsigned = 0xffffffffu) { hk::collective(0u); }
 static inline void __syncthreads() { hk::block_barrier(); }
 template <class T> static inline T __ldg(const T* p) { return *p; }
+static inline int min(int a, int b) { return a < b ? a : b; }
+#define __align__(n) __attribute__((aligned(n)))
+
+// ---- mbarrier + 1-D bulk copies (device_utils.cuh's PTX wrappers, host semantics) -----------------------------------
+// The 64-bit barrier word holds {phase bit, pending arrivals, pending transaction bytes, arrival count of a phase}; a
+// bulk load is performed at once (one legal schedule of the asynchronous copy) and completes its bytes on the barrier;
+// a phase completes when both pending counts reach zero.  try_wait.parity(p) succeeds once the phase of parity p is over.
+namespace rome {
+struct HkBar { uint8_t phase, expected; int16_t pending; int32_t tx; };
+static_assert(sizeof(HkBar) <= 8, "an emulated mbarrier must fit the kernel's 8-byte barrier slot");
+static inline void hk_bar_check(HkBar* b) {
+    if (b->pending == 0 && b->tx == 0) { b->phase ^= 1; b->pending = (int16_t)b->expected; }
+    ++hk::g_progress;
+}
+static inline void mbar_init(uint64_t* bar, uint32_t count) {
+    HkBar* b = reinterpret_cast<HkBar*>(bar);
+    b->phase = 0; b->expected = (uint8_t)count; b->pending = (int16_t)count; b->tx = 0;
+}
+static inline void fence_mbar_init() {}
+static inline void fence_proxy_async() {}
+static inline void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    HkBar* b = reinterpret_cast<HkBar*>(bar);
+    b->tx += (int32_t)bytes; b->pending -= 1;
+    hk_bar_check(b);
+}
+static inline void mbar_arrive(uint64_t* bar) {
+    HkBar* b = reinterpret_cast<HkBar*>(bar);
+    b->pending -= 1;
+    hk_bar_check(b);
+}
+static inline void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const HkBar* b = reinterpret_cast<const HkBar*>(bar);
+    while (b->phase == parity) hk::yield_();
+}
+static inline void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    if ((bytes & 15u) || (reinterpret_cast<uintptr_t>(smem_dst) & 15u) || (reinterpret_cast<uintptr_t>(gmem_src) & 15u)) std::abort();
+    std::memcpy(smem_dst, gmem_src, bytes);
+    HkBar* b = reinterpret_cast<HkBar*>(bar);
+    b->tx -= (int32_t)bytes;
+    hk_bar_check(b);
+}
+static inline void tma_store_1d(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+    if ((bytes & 15u) || (reinterpret_cast<uintptr_t>(gmem_dst) & 15u) || (reinterpret_cast<uintptr_t>(smem_src) & 15u)) std::abort();
+    std::memcpy(gmem_dst, smem_src, bytes);
+}
+static inline void tma_store_commit() {}
+static inline void tma_store_wait_read() {}
+static inline void tma_store_wait_all() {}
+}  // namespace rome
+enum { cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorInvalidConfiguration = 9 };
 #define __sincosf(x, s, c) sincosf((x), (s), (c))
 static inline int max(int a, int b) { return a > b ? a : b; }
 #define __shared__ static

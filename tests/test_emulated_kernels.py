@@ -17,13 +17,19 @@ sys.path.insert(0, os.path.join(ROOT, "tests", "host_kernels"))
 
 
 @pytest.fixture(scope="module")
-def ectx(tmp_path_factory):
+def hk_so(tmp_path_factory):
+    """one host build of the kernel sources per test session (about half a minute of g++)"""
     import shutil
     if shutil.which("g++") is None:
         pytest.skip("g++ not available")
     import build as hk_build
+    return hk_build.build(str(tmp_path_factory.mktemp("host_kernels")))
+
+
+@pytest.fixture(scope="module")
+def ectx(hk_so):
     from emu import EmulatedContext
-    return EmulatedContext(hk_build.build(str(tmp_path_factory.mktemp("host_kernels"))))
+    return EmulatedContext(hk_so)
 
 
 def _raw():
@@ -218,3 +224,50 @@ def test_product_kernel_and_device_resident_sweeps(emulated_api):
     T.test_plan_errors(emulated_api)
     T.test_hexagonal_solve_reference_boxes(emulated_api)
     T.test_sweeps_on_pose3_chain_and_beehive(emulated_api)
+
+
+# ---- the library's OWN kernels under the emulator: persistent blocks, producer warp, TMA bulk copies, mbarrier rings ---
+@pytest.fixture(scope="module", params=[1, 3, 7], ids=lambda g: f"grid{g}")
+def pctx(request, hk_so):
+    """eval_kernel / eval_kernel_w themselves (csrc/eval_pipeline.cuh), planned by plan_launch and dispatched by
+    launch_family, on 1, 3 or 7 blocks: few blocks mean many tiles per block, i.e. the stage rings wrap many times"""
+    from emu import EmulatedContext
+    return EmulatedContext(hk_so, pipeline=True, grid_cap=request.param)
+
+
+def test_pipeline_kernels_parity(pctx):
+    T = _raw()
+    T.test_pose2pose2_parity(pctx, 100)
+    assert pctx.last_plan["threads"] == 288 and pctx.last_plan["pipeline"] == 0     # 8 consumer warps + producer warp
+    T.test_pose2pose2_parity(pctx, 37)
+    T.test_priorpose2_parity(pctx)
+    T.test_bearingrange_parity(pctx)
+    T.test_pose3pose3_parity(pctx, 64)
+    T.test_priorpose3_parity(pctx)
+    T.test_wide_heading_spread_takes_general_sincos_path(pctx)
+
+
+@pytest.mark.parametrize("family", ["pose2pose2", "bearingrange", "pose3pose3", "priorpose3"])
+def test_pipeline_kernels_fused_sampling(pctx, family):
+    _raw().test_fused_sampling_matches_supplied_and_host_twin(pctx, family)
+    if family in ("pose3pose3", "priorpose3"):   # sampled SE(3): the per-warp pipeline (12 warps, no producer warp)
+        assert pctx.last_plan["pipeline"] in (0, 1)
+
+
+@pytest.mark.parametrize("N", [1, 33, 500, 2000])
+def test_pipeline_kernels_tile_variants(pctx, N):
+    """N = 500 switches to the 2-factor tile, N = 2000 to the 1-factor tile (shared-memory budget)"""
+    _raw().test_particle_count_edge_cases(pctx, N)
+    assert pctx.last_plan["ft"] == {1: 8, 33: 8, 500: 2, 2000: 1}[N]
+
+
+def test_pipeline_kernels_ranges_and_next_families(pctx):
+    T = _raw()
+    T.test_empty_range_and_zero_factors(pctx)
+    T.test_too_many_particles_is_an_error(pctx)
+    import test_gpu_next_families as T2
+    import test_gpu_next_families_3d as T3
+    T2.test_point2_gaussian_families(pctx, 37)
+    T2.test_scalar_families(pctx, 100)
+    T3.test_point3_families(pctx, 37)
+    T3.test_pose3_partial_families(pctx, 100)
