@@ -74,7 +74,9 @@ __device__ __forceinline__ void normals_for_group(const EvalParams& P, int f, in
 // is evaluated as branch-free straight-line code: first the four slot BODIES (loads + arithmetic into
 // registers), then the four slot STORES -- no shared-memory store sits between the loads of different slots, so
 // the Float64 chains of the four particles may interleave.  Slots 0-1 are live for every lane; a lane whose 3rd or
-// 4th particle is beyond Npad reads particle `lane` instead and has its stores/statistics masked.  FASTCOND
+// 4th particle is beyond Npad reads particle `lane` instead (in range: this path needs Npad > 64) and has its
+// stores/statistics masked; in the trailing partial group dead lanes read particle 0 -- with Npad < 32 particle `lane`
+// would lie beyond the block, and a NaN/Inf found there survives the multiplication by the zero mask.  FASTCOND
 // (warp-uniform) selects the variant whose body may assume kFast (e.g. small heading offsets -> polynomial
 // sin/cos without a fallback branch).  The trailing partial group is evaluated with warp-uniform guards.
 // The family defines ROME_SLOT_DECL (per-group register arrays) and ROME_SLOT_STORE (uses k, n, live).
@@ -115,7 +117,7 @@ __device__ __forceinline__ void normals_for_group(const EvalParams& P, int f, in
                 const int nn = n0 + 32 * k;                                                    \
                 if (n0 - lane + 32 * k < Npad) {                                               \
                     const bool live = nn < Npad;                                               \
-                    const int n = live ? nn : lane;                                            \
+                    const int n = live ? nn : 0;  /* dead lanes re-read particle 0 (always in range) */ \
                     __VA_ARGS__                                                                \
                     ROME_SLOT_STORE                                                            \
                 }                                                                              \

@@ -174,7 +174,9 @@ __device__ __forceinline__ Pair pair_of(int it, int lane, int Npad) {
     for (int j = 0; j < 2; ++j) {
         const int nn = lane + 32 * (2 * it + j);
         pr.live[j] = nn < Npad;
-        pr.n[j] = pr.live[j] ? nn : lane;  // dead slots re-read particle `lane`; their outputs are masked
+        // dead slots re-read a particle that exists (lane, or 0 when Npad < 32); their outputs are masked, but a NaN/Inf
+        // picked up beyond the block would survive the zero mask of the statistics
+        pr.n[j] = pr.live[j] ? nn : (lane < Npad ? lane : 0);
     }
     return pr;
 }

@@ -37,7 +37,9 @@ class EmulatedContext:
         self._hk.hk_eval_pipeline.argtypes = [C.c_int, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                               C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float),
                                               C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float),
-                                              C.POINTER(C.c_float), C.c_uint64, C.c_uint32, C.c_int, C.POINTER(C.c_int)]
+                                              C.POINTER(C.c_float), C.c_uint64, C.c_uint32, C.c_int, C.POINTER(C.c_int), C.c_int,
+                                              C.c_void_p]
+        self._peers = {}
         self._hk.hk_eval.argtypes = [C.c_int, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float),
                                      C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_uint64, C.c_uint32,
@@ -176,9 +178,11 @@ class EmulatedContext:
         v1 = self._store[vt1] if vt1 is not None else self._store[vt0]
         if self.pipeline:
             info = (C.c_int * 6)()
+            peers = self._peers.get(family, [])
+            parr = (C.c_void_p * max(1, len(peers)))(*peers)
             rc = self._hk.hk_eval_pipeline(family, flags, first, count, N, Np, rows.ctypes.data, self._store[vt0].ctypes.data,
                                            v1.ctypes.data, _fp(meas), _fp(meas_out), _fp(res), _fp(prop_fwd), _fp(prop_bwd),
-                                           _fp(stats), _fp(jac), seed, stream_id, self.grid_cap, info)
+                                           _fp(stats), _fp(jac), seed, stream_id, self.grid_cap, info, len(peers), parr)
             if rc == -3:
                 raise rb.RomeB200Error(L.SHAPE_MISMATCH, "N is too large for the shared-memory pipeline of this family")
             self.last_plan = dict(zip(("ft", "variant", "stages", "pipeline", "grid", "threads"), info))
@@ -205,6 +209,11 @@ class EmulatedContext:
         self.eval_host(family, flags & ~L.INDEPENDENT, seed=seed, stream_id=stream_id, first=first, count=count,
                        meas=view(meas, dm), meas_out=view(meas_out, dm), res=view(res, dr), prop_fwd=view(prop_fwd, dfwd),
                        prop_bwd=view(prop_bwd, dbwd), stats=view(stats, -ns), jac=view(jac, dj))
+
+    def set_peer_proposals(self, family, peer_ptrs):
+        """fused all-gather: forward-proposal rows are also stored into these buffers (pipeline mode only)"""
+        assert self.pipeline and len(peer_ptrs) <= 7
+        self._peers[family] = [int(p) for p in peer_ptrs]
 
     # -- "device" memory ------------------------------------------------------------------------------------------------
     def malloc_device(self, nbytes):

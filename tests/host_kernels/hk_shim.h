@@ -71,6 +71,7 @@ static uint32_t g_x[2][kMaxThreads];
 static unsigned g_warp_phase[kMaxThreads], g_warp_deposits[kMaxThreads / 32];
 static unsigned g_block_phase[kMaxThreads], g_block_arrivals;
 static std::function<void(int)> g_body;
+alignas(128) static unsigned char g_smem[240 * 1024];  // the running block's dynamic shared memory
 static unsigned long long g_progress = 0;  // bumped by everything that can unblock a waiting fiber
 static bool g_deadlock = false;
 

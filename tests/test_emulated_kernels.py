@@ -335,3 +335,77 @@ def test_pipeline_fuzz_against_direct_family_arithmetic(hk_so):
             live = slice(first, first + count)
             assert np.array_equal(a[live], b[live], equal_nan=True), (what, key)
             assert np.all(b[:first] == -777.0) and np.all(b[first + count:] == -777.0), (what, key, "wrote outside the range")
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_fused_all_gather_indexing_on_emulated_ranks(hk_so, world):
+    """SURVEY 8e on emulated ranks: the factor list is split into `world` contiguous ranges (sharding.shard_range), every
+    rank evaluates its range with the other ranks' proposal buffers set as peers (rome_b200_set_peer_proposals), the
+    kernels' bulk stores deliver each row to every buffer -- afterwards EVERY rank must hold the proposals of ALL
+    factors, identical to a single-rank evaluation (the real 2-GPU run is tests/test_gpu_multi.py; 8 ranks were only
+    ever timed on the device, never compared)."""
+    import rome_b200 as rb
+    from rome_b200 import sharding
+    from emu import EmulatedContext
+    rng = np.random.default_rng(9)
+    N, nv, nF = 100, 40, 203
+    poses = rng.normal(size=(nv, 1, 3)) * [20, 20, 1] + rng.normal(size=(nv, N, 3)) * [0.1, 0.1, 0.02]
+    ip = rng.integers(0, nv - 1, nF).astype(np.int32)
+    iq = (ip + 1).astype(np.int32)
+    mu = rng.normal(size=(nF, 3)) * [5, 1, 0.5]
+    cov = np.tile(np.diag([0.01, 0.01, 0.001]), (nF, 1, 1))
+    Np, c = rb.npad(N), sharding.shard_size(nF, world)
+    flags = rb.SAMPLE | rb.RESIDUAL | rb.STATS | rb.PROPOSAL_FWD
+    ranks = [EmulatedContext(hk_so, pipeline=True, grid_cap=2) for _ in range(world)]
+    bufs = [np.zeros((world * c, Np, 3), np.float32) for _ in range(world)]
+    for r, ctx in enumerate(ranks):
+        ctx.set_particles(rb.POSE2, poses)
+        ctx.set_factors_pose2pose2(ip, iq, mu, cov)
+        ctx.set_peer_proposals(rb.POSE2POSE2, [bufs[p].ctypes.data for p in range(world) if p != r])
+    full = np.zeros((world * c, Np, 3), np.float32)
+    single = EmulatedContext(hk_so, pipeline=True, grid_cap=2)
+    single.set_particles(rb.POSE2, poses)
+    single.set_factors_pose2pose2(ip, iq, mu, cov)
+    res, st = np.zeros((nF, Np, 3), np.float32), np.zeros((nF, 16), np.float32)
+    single.eval_host(rb.POSE2POSE2, flags, seed=5, res=res, stats=st, prop_fwd=full)
+    for r, ctx in enumerate(ranks):
+        first, count = sharding.shard_range(nF, r, world)
+        ctx.eval_host(rb.POSE2POSE2, flags, seed=5, first=first, count=count, res=res, stats=st, prop_fwd=bufs[r])
+    for r in range(world):
+        assert np.array_equal(bufs[r][:nF], full[:nF]), r
+        assert not bufs[r][nF:].any()
+
+
+@pytest.mark.parametrize("N", [1, 3, 8, 17, 24])
+def test_small_particle_counts_do_not_read_beyond_their_blocks(hk_so, N):
+    """Npad < 32: the dead lanes of the (only) slot group must not pick up whatever lies behind the particle block -- with
+    shared memory poisoned by NaN patterns, statistics (zero-masked sums: NaN * 0 = NaN) and every live output stay finite
+    and the statistics equal the sums over the live particles.  Found by the fuzz above; all families share the slot loop
+    (eval_pipeline.cuh ROME_SLOT_LOOP) or the SE(3) pair iterator (se3_common.cuh pair_of)."""
+    import ctypes
+    import rome_b200 as rb
+    from emu import EmulatedContext
+    rng = np.random.default_rng(N)
+    c = EmulatedContext(hk_so, pipeline=True, grid_cap=2)
+    nv, nF = 6, 19
+    for fam in (rb.POSE2POSE2, rb.PRIORPOSE2, rb.BEARINGRANGE, rb.POSE3POSE3, rb.PRIORPOSE3, rb.POINT2POINT2, rb.POSE2POINT2RANGE,
+                rb.POINT3POINT3, rb.POSE3POSE3XYYAW, rb.POSE3POSE3UNITTRANS):
+        vt0, vt1, dm, dr, ns, dj, dfwd, dbwd = rb.FAMILY[fam]
+        for t in {vt0, vt1} - {None}:
+            c.set_particles(t, rng.normal(size=(nv, N, rb.VAR_DIM[t])) * 0.2 + rng.normal(size=(nv, 1, rb.VAR_DIM[t])) * 3)
+        i0, i1 = rng.integers(0, nv, nF).astype(np.int32), rng.integers(0, nv, nF).astype(np.int32)
+        if fam == rb.BEARINGRANGE:
+            c.set_factors_bearingrange(i0, i1, np.column_stack([np.zeros(nF), np.full(nF, 0.1)]), np.column_stack([np.full(nF, 5.0), np.full(nF, 0.5)]))
+        elif fam == rb.POSE2POINT2RANGE:
+            c.set_factors_scalar(fam, i0, i1, np.column_stack([np.full(nF, 5.0), np.full(nF, 0.3)]))
+        else:
+            c.set_factors_gaussian(fam, i0, None if vt1 is None else i1, rng.normal(size=(nF, dm)), np.tile(0.01 * np.eye(dm), (nF, 1, 1)))
+        for sample in (False, True):
+            flags = rb.RESIDUAL | rb.STATS | (rb.PROPOSAL_FWD if dfwd else 0) | (rb.SAMPLE if sample else 0)
+            out = c.alloc_host_outputs(fam, flags)
+            meas = None if sample else (rng.normal(size=(nF, rb.npad(N), dm)) * 0.05).astype(np.float32)
+            c._hk.hk_poison_smem(0xFF)
+            c.eval_host(fam, flags, seed=2, meas=meas, **out)
+            res = out["res"][:, :N].astype(np.float64)
+            assert np.isfinite(res).all() and np.isfinite(out["stats"]).all(), (fam, sample, c.last_plan)
+            assert np.allclose(out["stats"][:, :dr], res.sum(1), rtol=1e-4, atol=1e-5), (fam, sample)
