@@ -409,3 +409,35 @@ def test_small_particle_counts_do_not_read_beyond_their_blocks(hk_so, N):
             res = out["res"][:, :N].astype(np.float64)
             assert np.isfinite(res).all() and np.isfinite(out["stats"]).all(), (fam, sample, c.last_plan)
             assert np.allclose(out["stats"][:, :dr], res.sum(1), rtol=1e-4, atol=1e-5), (fam, sample)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_gpu_side_rank_barrier_on_emulated_ranks(tmp_path_factory, world):
+    """rome_b200_peer_signal / rome_b200_peer_wait (csrc/peer_kernels.cu) with `world` emulated ranks, 60 rounds, ranks
+    delayed at random (some fall several kernels behind, others run ahead): no rank leaves wait k before every peer has
+    issued signal k, nobody gives up, every epoch and every flag slot ends at the round count.  On the device this was
+    validated at 2 GPUs only."""
+    import ctypes as C
+    import shutil
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    import build as hk_build
+    lib = C.CDLL(hk_build.build_peer(str(tmp_path_factory.mktemp("host_peer"))))
+    rounds = 60
+    rng = np.random.default_rng(world)
+    for pattern in range(4):
+        lag = np.zeros((world, rounds), np.int32)
+        if pattern == 1:
+            lag = rng.integers(0, 4, (world, rounds)).astype(np.int32)
+        elif pattern == 2:   # one straggler: everybody else has to wait for it every round
+            lag[world - 1] = 25
+        elif pattern == 3:   # bursts: a rank stalls for a long time once in a while
+            lag = (rng.random((world, rounds)) < 0.1).astype(np.int32) * 200
+        lag = np.ascontiguousarray(lag)
+        viol = C.c_int(-1)
+        state = np.zeros((world, 16), np.uint32)
+        rc = lib.hk_peer_barrier_rounds(world, rounds, lag.ctypes.data_as(C.POINTER(C.c_int)), C.byref(viol),
+                                        state.ctypes.data_as(C.POINTER(C.c_uint32)))
+        assert rc == 0 and viol.value == 0, (pattern, rc, viol.value)
+        assert np.all(state[:, :world - 1] == rounds) and np.all(state[:, world - 1:8] == 0)   # one slot per peer
+        assert np.all(state[:, 8] == rounds) and np.all(state[:, 9] == rounds) and np.all(state[:, 10] == 0)
