@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <vector>
 
 #define __device__
 #define __host__
@@ -73,6 +74,30 @@ static unsigned g_block_phase[kMaxThreads], g_block_arrivals;
 static std::function<void(int)> g_body;
 alignas(128) static unsigned char g_smem[240 * 1024];  // the running block's dynamic shared memory
 static unsigned long long g_progress = 0;  // bumped by everything that can unblock a waiting fiber
+// Asynchronous bulk copies: with g_async_max > 0 a copy is not performed when it is issued but a pseudo-random number of
+// scheduler rounds later (1 .. g_async_max), like the copy engine working behind the issuing thread's back; loads
+// complete their bytes on the mbarrier only then, stores read shared memory only then -- unless the issuing thread waits
+// for its bulk group first.  g_async_max = 0: copies are instantaneous.
+struct PendingCopy { void* dst; const void* src; uint32_t bytes; uint64_t* bar; int owner; unsigned long long due; };
+static std::vector<PendingCopy> g_pending;
+static unsigned long long g_round = 0;
+static unsigned g_async_max = 0, g_async_state = 12345u;
+static inline unsigned async_delay() {
+    g_async_state = g_async_state * 1664525u + 1013904223u;
+    return 1u + (g_async_state >> 8) % g_async_max;
+}
+static void complete_copy(const PendingCopy& c);   // defined with the mbarrier emulation below
+static inline void run_due_copies(bool all_of_owner = false, int owner = -1) {
+    for (size_t i = 0; i < g_pending.size();) {
+        const PendingCopy c = g_pending[i];
+        if (all_of_owner ? (c.owner == owner && c.bar == nullptr) : c.due <= g_round) {
+            g_pending.erase(g_pending.begin() + i);
+            complete_copy(c);
+        } else {
+            ++i;
+        }
+    }
+}
 static bool g_deadlock = false;
 
 static inline dim3_ tid3() { return {(unsigned)g_cur, 0, 0}; }
@@ -120,10 +145,14 @@ static void run_block(int nthreads, F&& f) {
         makecontext(&g_fiber[t], trampoline, 0);
     }
     g_deadlock = false;
+    g_pending.clear();
     unsigned long long idle_rounds = 0;
     for (bool any = true; any;) {
         any = false;
         const unsigned long long before = g_progress;
+        ++g_round;
+        run_due_copies();
+        if (!g_pending.empty()) ++g_progress;   // a copy still in flight will unblock somebody
         for (int t = 0; t < nthreads; ++t)
             if (!g_done[t]) {
                 g_cur = t;
@@ -136,6 +165,7 @@ static void run_block(int nthreads, F&& f) {
         idle_rounds = (g_progress == before) ? idle_rounds + 1 : 0;
         if (idle_rounds > 4) { g_deadlock = true; return; }
     }
+    if (!g_pending.empty()) g_deadlock = true;   // the block exited with bulk copies in flight (no wait on their group)
 }
 template <class F>
 static void run_warp(F&& f) { run_block(32, f); }
@@ -204,19 +234,31 @@ static inline void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 static inline void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
     if ((bytes & 15u) || (reinterpret_cast<uintptr_t>(smem_dst) & 15u) || (reinterpret_cast<uintptr_t>(gmem_src) & 15u)) std::abort();
-    std::memcpy(smem_dst, gmem_src, bytes);
-    HkBar* b = reinterpret_cast<HkBar*>(bar);
-    b->tx -= (int32_t)bytes;
-    hk_bar_check(b);
+    const hk::PendingCopy c = {smem_dst, gmem_src, bytes, bar, hk::g_cur, hk::g_round + (hk::g_async_max ? hk::async_delay() : 0)};
+    if (hk::g_async_max) hk::g_pending.push_back(c); else hk::complete_copy(c);
 }
 static inline void tma_store_1d(void* gmem_dst, const void* smem_src, uint32_t bytes) {
     if ((bytes & 15u) || (reinterpret_cast<uintptr_t>(gmem_dst) & 15u) || (reinterpret_cast<uintptr_t>(smem_src) & 15u)) std::abort();
-    std::memcpy(gmem_dst, smem_src, bytes);
+    const hk::PendingCopy c = {gmem_dst, smem_src, bytes, nullptr, hk::g_cur, hk::g_round + (hk::g_async_max ? hk::async_delay() : 0)};
+    if (hk::g_async_max) hk::g_pending.push_back(c); else hk::complete_copy(c);
 }
 static inline void tma_store_commit() {}
-static inline void tma_store_wait_read() {}
-static inline void tma_store_wait_all() {}
+// waiting for the thread's bulk groups: its stores in flight are carried out now (they have read their source, and --
+// for wait_all -- written their destination; the emulation does not distinguish the two)
+static inline void tma_store_wait_read() { hk::run_due_copies(true, hk::g_cur); }
+static inline void tma_store_wait_all() { hk::run_due_copies(true, hk::g_cur); }
 }  // namespace rome
+namespace hk {
+static void complete_copy(const PendingCopy& c) {
+    std::memcpy(c.dst, c.src, c.bytes);
+    if (c.bar) {
+        rome::HkBar* b = reinterpret_cast<rome::HkBar*>(c.bar);
+        b->tx -= (int32_t)c.bytes;
+        rome::hk_bar_check(b);
+    }
+    ++g_progress;
+}
+}  // namespace hk
 enum { cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorInvalidConfiguration = 9 };
 #define __sincosf(x, s, c) sincosf((x), (s), (c))
 static inline int max(int a, int b) { return a > b ? a : b; }

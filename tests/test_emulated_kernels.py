@@ -441,3 +441,59 @@ def test_gpu_side_rank_barrier_on_emulated_ranks(tmp_path_factory, world):
         assert rc == 0 and viol.value == 0, (pattern, rc, viol.value)
         assert np.all(state[:, :world - 1] == rounds) and np.all(state[:, world - 1:8] == 0)   # one slot per peer
         assert np.all(state[:, 8] == rounds) and np.all(state[:, 9] == rounds) and np.all(state[:, 10] == 0)
+
+
+@pytest.mark.parametrize("max_delay", [1, 3, 17, 60])
+def test_pipeline_with_asynchronous_copies(hk_so, max_delay):
+    """the pipeline kernels with bulk copies that are NOT instantaneous: every load / store is carried out a pseudo-random
+    1 .. max_delay scheduler rounds after it was issued (loads complete their mbarrier bytes only then, stores read their
+    shared-memory source only then unless the issuing thread waits for its bulk group).  Results must still be exactly
+    those of the directly fed family arithmetic: the `full` / `empty` hand-over, the wait that protects a warp's output
+    slice before it is rewritten and the final wait before the block exits are what this exercises (a kernel without
+    the slice wait passes with instantaneous copies and fails here)."""
+    import rome_b200 as rb
+    from emu import EmulatedContext
+    rng = np.random.default_rng(max_delay)
+    direct = EmulatedContext(hk_so)
+    fams = list(rb.FAMILY)
+    for trial in range(96):
+        fam = fams[trial % len(fams)]
+        vt0, vt1, dm, dr, ns, dj, dfwd, dbwd = rb.FAMILY[fam]
+        N = int(rng.choice([1, 8, 31, 33, 100, 104, 200, 333, 700]))
+        nv, nF = int(rng.integers(1, 7)), int(rng.integers(1, 70))
+        first = int(rng.integers(0, nF))
+        count = int(rng.integers(1, nF - first + 1))
+        pipe = EmulatedContext(hk_so, pipeline=True, grid_cap=int(rng.integers(1, 5)))
+        parts = {t: rng.normal(size=(nv, N, rb.VAR_DIM[t])) * 0.3 + rng.normal(size=(nv, 1, rb.VAR_DIM[t])) * 3 for t in {vt0, vt1} - {None}}
+        i0, i1 = rng.integers(0, nv, nF).astype(np.int32), rng.integers(0, nv, nF).astype(np.int32)
+        for c in (direct, pipe):
+            for t, p in parts.items():
+                c.set_particles(t, p)
+            if fam == rb.BEARINGRANGE:
+                c.set_factors_bearingrange(i0, i1, np.column_stack([np.linspace(-1, 1, nF), np.full(nF, 0.1)]),
+                                           np.column_stack([np.linspace(3, 9, nF), np.full(nF, 0.5)]))
+            elif fam in (rb.POSE2POINT2RANGE, rb.POINT2POINT2RANGE, rb.POSE2POINT2BEARING):
+                c.set_factors_scalar(fam, i0, i1, np.column_stack([np.linspace(1, 3, nF), np.full(nF, 0.3)]))
+            else:
+                A = np.random.default_rng(trial).normal(size=(nF, dm, dm)) * 0.1
+                c.set_factors_gaussian(fam, i0, None if vt1 is None else i1, np.random.default_rng(trial).normal(size=(nF, dm)),
+                                       A @ np.swapaxes(A, 1, 2) + 0.01 * np.eye(dm))
+        flags = rb.RESIDUAL | (rb.STATS if rng.random() < 0.6 else 0) | (rb.PROPOSAL_FWD if dfwd and rng.random() < 0.7 else 0)
+        sample = rng.random() < 0.5
+        flags |= rb.SAMPLE if sample else 0
+        meas = None if sample else (rng.normal(size=(nF, rb.npad(N), dm)) * 0.05).astype(np.float32)
+        outs = []
+        for c in (direct, pipe):
+            out = c.alloc_host_outputs(fam, flags)
+            for a in out.values():
+                a.fill(-777.0)
+            if c is pipe:
+                c._hk.hk_poison_smem(0xFF)
+                c._hk.hk_set_async(max_delay, trial)
+            try:
+                c.eval_host(fam, flags, seed=trial, stream_id=3, first=first, count=count, meas=meas, **out)
+            finally:
+                c._hk.hk_set_async(0, 0)
+            outs.append(out)
+        for key in outs[0]:
+            assert np.array_equal(outs[0][key], outs[1][key], equal_nan=True), (trial, fam, N, nF, first, count, flags, key, pipe.last_plan)
