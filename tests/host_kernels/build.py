@@ -19,7 +19,7 @@ def _read(name):
 def _between(src, start_marker, end_marker, back_to_banner=True):
     a = src.index(start_marker)
     if back_to_banner:  # include the comment banner the marker sits in
-        a = src.rfind("\n", 0, src.rfind("// ", 0, a) if False else a) + 1
+        a = src.rfind("\n", 0, a) + 1
         while True:  # walk back over the comment lines above
             prev = src.rfind("\n", 0, a - 1) + 1
             if src[prev:a].lstrip().startswith("//"):
