@@ -144,6 +144,8 @@ def test_accumulated_factor_means(emulated_api):
     import test_gpu_zz_accumulate as T
     T.test_accumulate_factor_means_reference_case()
     T.test_accumulate_along_hexagon_and_back()
+    for N in (1, 5, 17):
+        T.test_statistics_with_fewer_particles_than_lanes(N, nF=250)
 
 
 def test_full_size_baseline_workloads(emulated_api):

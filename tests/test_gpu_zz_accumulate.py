@@ -51,3 +51,28 @@ def test_accumulate_along_hexagon_and_back():
         rb.addVariable(gr, "l1", rb.Point2)
         rb.addFactor(gr, ["x0", "l1"], rb.Pose2Point2Range(rb.Normal(5.0, 0.1)), graphinit=False)
         rb.solveFactorParametric(gr, "x0l1f1", ("x0", np.zeros(3)), "l1")
+
+
+@pytest.mark.parametrize("N", [1, 5, 17])
+def test_statistics_with_fewer_particles_than_lanes(N, nF=4000):
+    """Npad < 32: the dead lanes of the slot group must read a particle that exists -- whatever lies behind the block in
+    shared memory (possibly a NaN bit pattern) would otherwise enter the zero-masked statistics as NaN * 0.  Thousands of
+    factors so that, were the defect back, some factor would meet such a pattern (found by tests/test_emulated_kernels.py)."""
+    rng = np.random.default_rng(N)
+    ctx = rb.default_context()
+    nv = 300
+    poses = rng.normal(size=(nv, 1, 3)) * [30, 30, 1] + rng.normal(size=(nv, N, 3)) * [0.1, 0.1, 0.02]
+    p3 = rng.normal(size=(nv, 1, 6)) * [5, 5, 5, 0.5, 0.5, 0.5] + rng.normal(size=(nv, N, 6)) * 0.05
+    ip = rng.integers(0, nv, nF).astype(np.int32)
+    iq = rng.integers(0, nv, nF).astype(np.int32)
+    ctx.set_particles(rb.POSE2, poses)
+    ctx.set_particles(rb.POSE3, p3)
+    ctx.set_factors_pose2pose2(ip, iq, rng.normal(size=(nF, 3)), np.tile(0.01 * np.eye(3), (nF, 1, 1)))
+    ctx.set_factors_pose3pose3(ip, iq, rng.normal(size=(nF, 6)) * 0.3, np.tile(0.01 * np.eye(6), (nF, 1, 1)))
+    for fam, dr in ((rb.POSE2POSE2, 3), (rb.POSE3POSE3, 6)):
+        for flags in (rb.RESIDUAL | rb.STATS | rb.SAMPLE, rb.RESIDUAL | rb.STATS | rb.PROPOSAL_FWD | rb.SAMPLE):
+            out = ctx.alloc_host_outputs(fam, flags)
+            ctx.eval_host(fam, flags, seed=3, **out)
+            res = out["res"][:, :N].astype(np.float64)
+            assert np.isfinite(out["stats"]).all() and np.isfinite(res).all(), (fam, flags)
+            assert np.allclose(out["stats"][:, :dr], res.sum(1), rtol=1e-4, atol=1e-4), (fam, flags)
