@@ -36,7 +36,8 @@
  *     proposals [nF][Npad][dv] offsets from the TARGET variable's anchor; jac [nF][Npad][dj].
  *     Npad = N rounded up to a multiple of 8; padding particles hold 0 on input and are ignored.
  *     meas, res and prop_fwd must be 16-byte aligned (they move through 1-D TMA bulk copies).
- *     Arithmetic inside the kernels is Float64.
+ *     Arithmetic: Float64 per factor, float32 per particle on the (small) offsets; ROME_B200_PRECISE selects
+ *     Float64 throughout.
  */
 #ifndef ROME_B200_H
 #define ROME_B200_H
@@ -117,6 +118,13 @@ enum rome_b200_family {
  * (R_p'(t_q - t_p), wrap(th_q - th_p)); BearingRange: (bearing, range) of the landmark seen from the pose;
  * Pose3Pose3: (R_p'(t_q - t_p), Log(R_p' R_q)); priors: the particle itself.  Excludes WRITE_MEAS. */
 #define ROME_B200_DECONV 256u
+/* Per-particle arithmetic in Float64.  Default (flag absent): everything LARGE -- anchors, factor means, the lever arm
+ * R(anchor) mu_t, the anchors' own residual -- is folded per factor in Float64, and the per-particle part, which then
+ * only involves small offsets, runs in float32 (|error| ~ 2^-24 x the offsets' magnitude, i.e. ~1e-8 on SLAM-sized
+ * spreads; tests/test_gpu_parity_raw.py states the bar).  With this flag the whole chain is Float64 on
+ * anchor + offset and the only rounding is that of the float32 output.  Jacobian and deconvolution outputs always take
+ * the Float64 chain. */
+#define ROME_B200_PRECISE 512u
 
 /* Buffers of one eval call.  Unused members may be NULL.  `_host` entry points take host
  * pointers with the same shapes; plain entry points take device pointers. */

@@ -6,7 +6,7 @@ include/rome_b200.h); this package is the host-side mirror of the reference's fa
 """
 from ._lib import (BEARINGRANGE, DECONV, INDEPENDENT, JACOBIAN, POINT2, POINT2POINT2, POINT2POINT2RANGE, POINT3, POINT3POINT3,
                    POSE2, POSE2POINT2, POSE2POINT2BEARING, POSE2POINT2RANGE, POSE2POSE2, POSE3, POSE3POSE3,
-                   POSE3POSE3ROTATION, POSE3POSE3UNITTRANS, POSE3POSE3XYYAW, PRIORPOINT2, PRIORPOINT3, PRIORPOSE2, PRIORPOSE3,
+                   POSE3POSE3ROTATION, POSE3POSE3UNITTRANS, POSE3POSE3XYYAW, PRECISE, PRIORPOINT2, PRIORPOINT3, PRIORPOSE2, PRIORPOSE3,
                    PROPOSAL_BWD, PROPOSAL_FWD, RESIDUAL, SAMPLE, SO_PATH, STATS, SYMBOLS, WRITE_MEAS, RomeB200Error)
 from .engine import (BYTES_PER_EVAL, BYTES_PER_EVAL_SAMPLED, FAMILY, VAR_DIM, Context, dequantized_particles,
                      meas_to_offsets, npad, offsets_to_meas, plan_query, rows_to_particle_major)

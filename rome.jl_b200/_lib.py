@@ -16,6 +16,7 @@ PRIORPOINT2, POINT2POINT2, POSE2POINT2, POSE2POINT2RANGE, POINT2POINT2RANGE, POS
 PRIORPOINT3, POINT3POINT3, POSE3POSE3XYYAW, POSE3POSE3ROTATION, POSE3POSE3UNITTRANS = 11, 12, 13, 14, 15
 RESIDUAL, PROPOSAL_FWD, PROPOSAL_BWD, STATS, SAMPLE, WRITE_MEAS, JACOBIAN, INDEPENDENT = 1, 2, 4, 8, 16, 32, 64, 128
 DECONV = 256
+PRECISE = 512
 PRODUCT_REANCHOR, MAX_PRODUCT_SOURCES, MAX_PRODUCT_BUFFERS = 1, 32, 16
 PEER_STATE_WORDS = 16
 

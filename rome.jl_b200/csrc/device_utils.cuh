@@ -124,6 +124,47 @@ __device__ __forceinline__ void sincos_small(double x, double& s, double& c) {
     s = fma(x * z, ps, x);
     c = fma(z * z, pc, fma(z, -0.5, 1.0));
 }
+// ---------------------------------------------------------------------------------------------
+// float32 per-particle helpers (the default arithmetic of the per-particle path: every per-particle
+// quantity is a SMALL offset, so float32 keeps ~1e-8 absolute; the large parts are per-factor Float64)
+// ---------------------------------------------------------------------------------------------
+// sin(x) and cos(x) - 1 for |x| <= 0.78, Taylor to x^9 / x^10: truncation < 2e-9 relative
+__device__ __forceinline__ void sincosm1_small_f(float x, float& s, float& cm1) {
+    const float z = x * x;
+    float ps = fmaf(z, 2.7557319224e-6f, -1.9841269841e-4f);
+    float pc = fmaf(z, -2.7557319224e-7f, 2.4801587302e-5f);
+    ps = fmaf(z, ps, 8.3333333333e-3f);
+    pc = fmaf(z, pc, -1.3888888889e-3f);
+    ps = fmaf(z, ps, -1.6666666667e-1f);
+    pc = fmaf(z, pc, 4.1666666667e-2f);
+    s = fmaf(x * z, ps, x);
+    pc = fmaf(z, pc, -0.5f);
+    cm1 = z * pc;
+}
+// a - 2 pi rint(a / 2 pi) in float32; rint by the 1.5 * 2^23 magic constant (two full-rate FADDs instead of FRND),
+// 2 pi split into float(2 pi) + remainder so that the reduction of a small multiple is exact to ~1e-8
+__device__ __forceinline__ float wrap_pi_f(float a) {
+    const float k = __fadd_rn(__fmaf_rn(a, 0.15915494309f, 12582912.f), -12582912.f);
+    return fmaf(-k, -1.7484555e-7f, fmaf(-k, 6.2831854820f, a));
+}
+// split a Float64 into float32 hi + lo (hi = the value with its low 29 mantissa bits cleared, exactly a float32 for
+// magnitudes in float32's normal range): one widening conversion less than (float)(x - (double)(float)x)
+__device__ __forceinline__ void split_f64(double x, float& hi, float& lo) {
+    const double h = __hiloint2double(__double2hiint(x), __double2loint(x) & (int)0xE0000000);
+    hi = (float)h;
+    lo = (float)(x - h);
+}
+// sin/cos of any float32 angle with full float32 accuracy: polynomial for small angles, libdevice otherwise
+__device__ __forceinline__ void sincos_any_f(float x, float& s, float& c) {
+    if (fabsf(x) <= 0.78f) {
+        float cm1;
+        sincosm1_small_f(x, s, cm1);
+        c = 1.f + cm1;
+    } else {
+        sincosf(x, &s, &c);
+    }
+}
+
 // sqrt of a positive normal double in float32 range: MUFU.RSQ seed (relative error ~2^-22) followed by two
 // coupled Goldschmidt steps (error -> 1.5 e^2 each); result within ~1 ulp.  No branches, no division.
 __device__ __forceinline__ double sqrt_seeded(double a) {

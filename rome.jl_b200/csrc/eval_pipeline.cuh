@@ -37,7 +37,7 @@ __device__ __forceinline__ void acc_prop2(float (&st)[16], float m, float dx, fl
 }
 __device__ __forceinline__ void acc_heading(float (&st)[16], float m, float dth) {
     float s, c;
-    sincosf(dth, &s, &c);
+    sincos_any_f(dth, s, c);
     st[11] = fmaf(m, c, st[11]);
     st[12] = fmaf(m, s, st[12]);
 }

@@ -165,6 +165,9 @@ __global__ void pack_kernel(int nvars, int N, int Npad, int wrap_dim, const doub
         if (wrap_dim >= 0 && lane == D) h = cos(src[wrap_dim]);      // Pose2 header: {x, y, theta, cos, sin, 0}
         if (wrap_dim >= 0 && lane == D + 1) h = sin(src[wrap_dim]);
         hdr[lane] = h;
+        // last header slot of a Pose2 block: float32 copies of (cos, sin) for the float32 per-particle path
+        if (wrap_dim >= 0 && lane == D + 2)
+            *reinterpret_cast<float2*>(hdr + lane) = make_float2((float)cos(src[wrap_dim]), (float)sin(src[wrap_dim]));
     }
     float* dst = reinterpret_cast<float*>(blk + var_header_bytes(D));
     for (int n = lane; n < Npad; n += 32) {

@@ -48,12 +48,24 @@ struct FamBearingRange {
             const float ex = Lp[2 * n_] - Pp[3 * n_], ey = Lp[2 * n_ + 1] - Pp[3 * n_ + 1];
             return fmaf(ex, ex, ey * ey);
         };
+        // ---- per-factor Float64 part of the float32 path (warp-uniform) ----------------------------------------------
+        //   u = D/|D|, beta0 = wrap(mu_b + anchor heading - atan(D)), rho0 = mu_rho - |D|; per particle, with
+        //   e = dl - dp (small), (along, cross) = (u.e, u x e):  atan(d) - atan(D) = atan(cross / (|D| + along)) and
+        //   |d| - |D| = along + cross * x * (1/2 - x^2/8 + ...), x = cross / (|D| + along)  -- all small quantities
+        const bool f32ok = !(flags & (ROME_B200_PRECISE | ROME_B200_JACOBIAN | ROME_B200_DECONV));
+        const double Dn = sqrt(D2), iDn = 1.0 / Dn;
+        const float ux = (float)(dax * iDn), uy = (float)(day * iDn), Dnf = (float)Dn;
+        const float beta0 = (float)wrap_pi((row.mu_b + apt) - phi0);
+        const float rho0 = (float)(row.mu_r - Dn), murf = (float)row.mu_r;
+        // proposals: rho dir - D = (mu_rho dir0 - D) + m_rho dir0 + rho (R(zeta) - I) dir0, dir0 = (cA, sA)
+        const float cAf = (float)cA, sAf = (float)sA;
+        float g0x, g0xl, g0y, g0yl;
+        split_f64(row.mu_r * cA - dax, g0x, g0xl);
+        split_f64(row.mu_r * sA - day, g0y, g0yl);
 #define ROME_BR_FAST                                                                                       \
-    (!__any_sync(0xffffffffu, fmaxf(fmaxf(delta2(n0), delta2(n0 + 32)), fmaxf(delta2(n2), delta2(n3))) > fast_lim))
+    (f32ok && !__any_sync(0xffffffffu, fmaxf(fmaxf(delta2(n0), delta2(n0 + 32)), fmaxf(delta2(n2), delta2(n3))) > fast_lim))
         ROME_SLOT_LOOP(ROME_BR_FAST, {
-            const double dpx = Pp[3 * n], dpy = Pp[3 * n + 1], dpt = Pp[3 * n + 2];
             const float2 lxy = *reinterpret_cast<const float2*>(Lp + 2 * n);
-            const double dlx = lxy.x, dly = lxy.y;
             float mb, mr;
             if (!kSample) {
                 const float2 m2 = *reinterpret_cast<const float2*>(V.meas + 2 * n);
@@ -64,6 +76,56 @@ struct FamBearingRange {
                 if ((flags & ROME_B200_WRITE_MEAS) && live)
                     __stcs(reinterpret_cast<float2*>(P.meas_out + fo + 2 * n), make_float2(mb, mr));
             }
+            const float msk = (nn < N) ? 1.f : 0.f;
+            if (kFast) {
+                // ---------------- float32 per-particle arithmetic (default) -----------------------------------------
+                const float px = Pp[3 * n], py = Pp[3 * n + 1], pt = Pp[3 * n + 2];
+                const float exf = lxy.x - px, eyf = lxy.y - py;
+                const float al = fmaf(ux, exf, uy * eyf), cr = fmaf(ux, eyf, -uy * exf);
+                const float x = __fdividef(cr, Dnf + al), q = x * x;  // |x| <= 0.1 under the fast condition
+                float pa = fmaf(q, 1.f / 9.f, -1.f / 7.f);
+                pa = fmaf(q, pa, 1.f / 5.f);
+                pa = fmaf(q, pa, -1.f / 3.f);
+                const float dphi = fmaf(x * q, pa, x);                                        // atan(x)
+                const float ps = fmaf(q, fmaf(q, fmaf(q, -5.f / 128.f, 1.f / 16.f), -0.125f), 0.5f);
+                const float dr = fmaf(cr * x, ps, al);                                        // |d| - |D|
+                float e1 = wrap_pi_f(((beta0 + pt) + mb) - dphi);
+                if (fabsf(e1 - 3.14159274f) <= 2.4e-7f) e1 = -3.14159274f;                    // sym_rem: +pi -> -pi
+                const float e2 = (rho0 + mr) - dr;
+                o_res[k] = make_float2(e1, e2);
+                if (want_stats) acc_res3(st, msk, e1, e2, 0.f);
+                if (flags & (ROME_B200_PROPOSAL_FWD | ROME_B200_PROPOSAL_BWD)) {
+                    float sz, cz1;
+                    const float zeta = pt + mb;
+                    if (fabsf(zeta) <= 0.78f) {
+                        sincosm1_small_f(zeta, sz, cz1);
+                    } else {
+                        float cz;
+                        sincosf(zeta, &sz, &cz);
+                        cz1 = cz - 1.f;
+                    }
+                    const float rho = murf + mr;
+                    const float gx = (g0xl + mr * cAf) + rho * fmaf(cz1, cAf, -sz * sAf);   // small part of rho dir - D
+                    const float gy = (g0yl + mr * sAf) + rho * fmaf(cz1, sAf, sz * cAf);
+                    if (flags & ROME_B200_PROPOSAL_FWD) {
+                        const float ox = (px + g0x) + gx, oy = (py + g0y) + gy;
+                        o_fwd[k] = make_float2(ox, oy);
+                        if (want_stats) acc_prop2(st, msk, ox, oy);
+                    }
+                    if (flags & ROME_B200_PROPOSAL_BWD) {
+                        const float ox = (lxy.x - g0x) - gx, oy = (lxy.y - g0y) - gy;
+                        if (live) {
+                            float* B = P.prop_bwd + (size_t)f * 3 * Npad + 3 * n;
+                            __stcs(B, ox); __stcs(B + 1, oy); __stcs(B + 2, pt);
+                        }
+                        if (want_stats && !(flags & ROME_B200_PROPOSAL_FWD)) acc_prop2(st, msk, ox, oy);
+                    }
+                }
+            } else {
+            // ---------------- Float64 per-particle arithmetic (ROME_B200_PRECISE, landmark close to the pose,
+            // Jacobian, deconvolution, trailing partial groups) ------------------------------------------------------
+            const double dpx = Pp[3 * n], dpy = Pp[3 * n + 1], dpt = Pp[3 * n + 2];
+            const double dlx = lxy.x, dly = lxy.y;
             const double b = row.mu_b + (double)mb, rho = row.mu_r + (double)mr;
             const double ex = dlx - dpx, ey = dly - dpy;  // delta: particle offsets (small against D)
             const double dx = dax + ex, dy = day + ey;
@@ -72,7 +134,7 @@ struct FamBearingRange {
             const double cr = dax * ey - day * ex;             // cross(D, delta)
             const double dt = fma(dax, ex, fma(day, ey, D2));  // D.d = |D|^2 + D.delta
             double phi, rng;
-            if (kFast || (fabs(dt * iD2 - 1.0) <= 0.1 && fabs(cr) <= 0.1 * dt)) {
+            if (fabs(dt * iD2 - 1.0) <= 0.1 && fabs(cr) <= 0.1 * dt) {
                 double r = iD2;  // 1/dt by Newton from 1/|D|^2 (relative start error <= 0.1 -> 1e-16 after 4 steps)
                 r = r * fma(-dt, r, 2.0);
                 r = r * fma(-dt, r, 2.0);
@@ -91,15 +153,10 @@ struct FamBearingRange {
             } else {
                 phi = atan2(dy, dx);
             }
-            if (kFast) {  // sqrt(d2): MUFU.RSQ seed (2^-22) + two Goldschmidt steps (1.5 e^2 each) -> < 1e-16 relative
-                rng = sqrt_seeded(d2);
-            } else {
-                rng = sqrt(d2);
-            }
+            rng = sqrt(d2);
             double e1d = wrap_pi(b + th - phi);
             if (fabs(e1d - kPi) <= 1.4901161193847656e-08 * kPi) e1d = -kPi;  // sym_rem: +pi -> -pi
             const float e1 = (float)e1d, e2 = (float)(rho - rng);
-            const float msk = (nn < N) ? 1.f : 0.f;
             o_res[k] = make_float2(e1, e2);
             if (want_stats) acc_res3(st, msk, e1, e2, 0.f);
             if (flags & (ROME_B200_PROPOSAL_FWD | ROME_B200_PROPOSAL_BWD)) {
@@ -128,6 +185,7 @@ struct FamBearingRange {
                 const double i2 = 1.0 / d2, i1 = 1.0 / rng;
                 float4* J = reinterpret_cast<float4*>(P.jac + ((size_t)f * Npad + n) * 4);
                 __stcs(J, make_float4((float)(dy * i2), (float)(-dx * i2), (float)(-dx * i1), (float)(-dy * i1)));
+            }
             }
         })
 #undef ROME_BR_FAST

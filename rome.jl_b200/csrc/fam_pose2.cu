@@ -37,13 +37,26 @@ struct FamPose2Pose2 {
 #pragma unroll
         for (int i = 0; i < 16; ++i) st[i] = 0.f;
 
+        // ---- per-factor Float64 part of the float32 path (warp-uniform): everything LARGE is folded here -----------
+        //   A   = R(anchor heading of p) mu_t                      (the lever arm; float32 copy for the small rotation)
+        //   c0  = (anchor_p - anchor_q).t + A                      (translation residual of the anchors, hi + lo)
+        //   th0 = wrap(anchor_p.theta + mu_theta - anchor_q.theta)
+        // per particle everything left is a small offset: r_t = c0 + (dp - dq) + (R(d) - I) A + R(theta_p) m
+        const bool f32ok = !(flags & (ROME_B200_PRECISE | ROME_B200_JACOBIAN | ROME_B200_DECONV));
+        const double Axd = ca * mu0 - sa * mu1, Ayd = sa * mu0 + ca * mu1;
+        const float Ax = (float)Axd, Ay = (float)Ayd;
+        float c0x, c0xl, c0y, c0yl;
+        split_f64(dax + Axd, c0x, c0xl);
+        split_f64(day + Ayd, c0y, c0yl);
+        const float th0 = (float)wrap_pi(dat + mu2);
+        const float2 csf = *reinterpret_cast<const float2*>(ap + 5);  // float32 copies of (cos, sin) of the anchor heading
+        const float caf = csf.x, saf = csf.y;
+
         // warp-uniform: every heading offset of this group is small enough for the polynomial sin/cos
 #define ROME_P2P2_FAST                                                                                         \
-    (!__any_sync(0xffffffffu, fmaxf(fmaxf(fabsf(Pp[3 * n0 + 2]), fabsf(Pp[3 * (n0 + 32) + 2])),               \
-                                    fmaxf(fabsf(Pp[3 * n2 + 2]), fabsf(Pp[3 * n3 + 2]))) > (float)kSmallAngle))
+    (f32ok && !__any_sync(0xffffffffu, fmaxf(fmaxf(fabsf(Pp[3 * n0 + 2]), fabsf(Pp[3 * (n0 + 32) + 2])),      \
+                                             fmaxf(fabsf(Pp[3 * n2 + 2]), fabsf(Pp[3 * n3 + 2]))) > (float)kSmallAngle))
         ROME_SLOT_LOOP(ROME_P2P2_FAST, {
-            const double dpx = Pp[3 * n], dpy = Pp[3 * n + 1], dpt = Pp[3 * n + 2];
-            const double dqx = Qp[3 * n], dqy = Qp[3 * n + 1], dqt = Qp[3 * n + 2];
             float mx, my, mt;
             if (!kSample) {
                 mx = V.meas[3 * n]; my = V.meas[3 * n + 1]; mt = V.meas[3 * n + 2];
@@ -56,23 +69,65 @@ struct FamPose2Pose2 {
                     __stcs(M, mx); __stcs(M + 1, my); __stcs(M + 2, mt);
                 }
             }
+            const float msk = (nn < N) ? 1.f : 0.f;
+            if (kFast) {
+                // ---------------- float32 per-particle arithmetic (default) -----------------------------------------
+                const float px = Pp[3 * n], py = Pp[3 * n + 1], pt = Pp[3 * n + 2];
+                const float qx = Qp[3 * n], qy = Qp[3 * n + 1], qt = Qp[3 * n + 2];
+                float sd, cm1;
+                sincosm1_small_f(pt, sd, cm1);
+                const float lx = fmaf(cm1, Ax, -sd * Ay), ly = fmaf(cm1, Ay, sd * Ax);       // (R(d) - I) A
+                const float c = fmaf(caf, cm1, fmaf(-saf, sd, caf)), s = fmaf(saf, cm1, fmaf(caf, sd, saf));
+                const float rmx = fmaf(c, mx, -s * my), rmy = fmaf(s, mx, c * my);           // R(theta_p) m
+                const float smx = (c0xl + lx) + rmx, smy = (c0yl + ly) + rmy;                // all the small terms
+                const float ht = (pt + th0) + mt;
+                const float e1 = ((px - qx) + c0x) + smx, e2 = ((py - qy) + c0y) + smy, e3 = wrap_pi_f(ht - qt);
+                o_res[k][0] = e1; o_res[k][1] = e2; o_res[k][2] = e3;
+                if (want_stats) acc_res3(st, msk, e1, e2, e3);
+                if (flags & ROME_B200_PROPOSAL_FWD) {  // qhat as offsets from q's anchor
+                    const float ox = (px + c0x) + smx, oy = (py + c0y) + smy, ot = wrap_pi_f(ht);
+                    o_fwd[k][0] = ox; o_fwd[k][1] = oy; o_fwd[k][2] = ot;
+                    if (want_stats) { acc_prop2(st, msk, ox, oy); acc_heading(st, msk, ot); }
+                }
+                if (flags & ROME_B200_PROPOSAL_BWD) {
+                    // theta_p = theta_q - X_theta = anchor_p.theta + tb ; t_p = t_q - R(tb) (A + R(anchor) m)
+                    // R(theta_p) X_t = R(tb) B, B = A + R(anchor) m;  t_p - anchor_p = (dq - c0) - R(anchor) m - (R(tb) - I) B
+                    const float tb = (qt - th0) - mt;
+                    float sb, cb1;
+                    if (fabsf(tb) <= 0.78f) {
+                        sincosm1_small_f(tb, sb, cb1);
+                    } else {
+                        float cb;
+                        sincosf(tb, &sb, &cb);
+                        cb1 = cb - 1.f;
+                    }
+                    const float r0x = fmaf(caf, mx, -saf * my), r0y = fmaf(saf, mx, caf * my);
+                    const float bx = Ax + r0x, by = Ay + r0y;
+                    const float ox = ((qx - c0x) - (c0xl + r0x)) - fmaf(cb1, bx, -sb * by);
+                    const float oy = ((qy - c0y) - (c0yl + r0y)) - fmaf(cb1, by, sb * bx);
+                    const float ot = wrap_pi_f(tb);
+                    if (live) {
+                        float* B = P.prop_bwd + fo + 3 * n;
+                        __stcs(B, ox); __stcs(B + 1, oy); __stcs(B + 2, ot);
+                    }
+                    if (want_stats && !(flags & ROME_B200_PROPOSAL_FWD)) {
+                        acc_prop2(st, msk, ox, oy); acc_heading(st, msk, ot);
+                    }
+                }
+            } else {
+            // ---------------- Float64 per-particle arithmetic (ROME_B200_PRECISE, wide heading spreads, Jacobian,
+            // deconvolution, trailing partial groups) -------------------------------------------------------------
+            const double dpx = Pp[3 * n], dpy = Pp[3 * n + 1], dpt = Pp[3 * n + 2];
+            const double dqx = Qp[3 * n], dqy = Qp[3 * n + 1], dqt = Qp[3 * n + 2];
             const double Xx = mu0 + (double)mx, Xy = mu1 + (double)my, Xt = mu2 + (double)mt;
             double s, c;
-            if (kFast) {  // sin/cos(anchor + small offset) by angle addition, no fallback branch
-                double sx, cx;
-                sincos_small(dpt, sx, cx);
-                s = fma(sa, cx, ca * sx);
-                c = fma(ca, cx, -sa * sx);
-            } else {
-                sincos_anchored(apt, ca, sa, dpt, s, c);
-            }
+            sincos_anchored(apt, ca, sa, dpt, s, c);
             const double rx = c * Xx - s * Xy;  // R(theta_p) X.t
             const double ry = s * Xx + c * Xy;
             // qhat - q, Pose2D.jl:62-65 ; qhat offsets are relative to q's anchor
             const double hx = (dax + dpx) + rx, hy = (day + dpy) + ry;
             const double ht = (dat + dpt) + Xt;
             const float e1 = (float)(hx - dqx), e2 = (float)(hy - dqy), e3 = (float)wrap_pi(ht - dqt);
-            const float msk = (nn < N) ? 1.f : 0.f;
             o_res[k][0] = e1; o_res[k][1] = e2; o_res[k][2] = e3;
             if (want_stats) acc_res3(st, msk, e1, e2, e3);
             if (flags & ROME_B200_PROPOSAL_FWD) {
@@ -107,6 +162,7 @@ struct FamPose2Pose2 {
                 float4* J = reinterpret_cast<float4*>(P.jac + ((size_t)f * Npad + n) * 4);
                 __stcs(J, make_float4((float)(-ry), (float)rx, (float)c, (float)s));
             }
+            }
         })
 #undef ROME_P2P2_FAST
         if (want_stats) write_stats16(st, P.stats, f, lane);
@@ -132,8 +188,13 @@ struct FamPriorPose2 {
         float st[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) st[i] = 0.f;
-        ROME_SLOT_LOOP(true, {
-            const double dpx = Pp[3 * n], dpy = Pp[3 * n + 1], dpt = Pp[3 * n + 2];
+        // float32 path: the mean relative to the anchor is the only large quantity (per factor, Float64 -> hi + lo)
+        const bool f32ok = !(flags & (ROME_B200_PRECISE | ROME_B200_DECONV));
+        float m0x, m0xl, m0y, m0yl;
+        split_f64(mx0, m0x, m0xl);
+        split_f64(my0, m0y, m0yl);
+        const float m0t = (float)wrap_pi(mt0);
+        ROME_SLOT_LOOP(f32ok, {
             float mx, my, mt;
             if (!kSample) {
                 mx = V.meas[3 * n]; my = V.meas[3 * n + 1]; mt = V.meas[3 * n + 2];
@@ -146,9 +207,22 @@ struct FamPriorPose2 {
                     __stcs(M, mx); __stcs(M + 1, my); __stcs(M + 2, mt);
                 }
             }
+            const float msk = (nn < N) ? 1.f : 0.f;
+            if (kFast) {
+                const float px = Pp[3 * n], py = Pp[3 * n + 1], pt = Pp[3 * n + 2];
+                const float hxs = m0xl + mx, hys = m0yl + my, ht = m0t + mt;  // m - anchor = m0 (hi) + small
+                const float e1 = (m0x - px) + hxs, e2 = (m0y - py) + hys, e3 = wrap_pi_f(ht - pt);
+                o_res[k][0] = e1; o_res[k][1] = e2; o_res[k][2] = e3;
+                if (want_stats) acc_res3(st, msk, e1, e2, e3);
+                if (flags & ROME_B200_PROPOSAL_FWD) {
+                    const float ox = m0x + hxs, oy = m0y + hys, ot = wrap_pi_f(ht);
+                    o_fwd[k][0] = ox; o_fwd[k][1] = oy; o_fwd[k][2] = ot;
+                    if (want_stats) { acc_prop2(st, msk, ox, oy); acc_heading(st, msk, ot); }
+                }
+            } else {
+            const double dpx = Pp[3 * n], dpy = Pp[3 * n + 1], dpt = Pp[3 * n + 2];
             const double hx = mx0 + (double)mx, hy = my0 + (double)my, ht = mt0 + (double)mt;  // m - anchor
             const float e1 = (float)(hx - dpx), e2 = (float)(hy - dpy), e3 = (float)wrap_pi(ht - dpt);
-            const float msk = (nn < N) ? 1.f : 0.f;
             o_res[k][0] = e1; o_res[k][1] = e2; o_res[k][2] = e3;
             if (want_stats) acc_res3(st, msk, e1, e2, e3);
             if (flags & ROME_B200_PROPOSAL_FWD) {
@@ -159,6 +233,7 @@ struct FamPriorPose2 {
             if ((flags & ROME_B200_DECONV) && live) {  // the measurement that explains the particle is the particle
                 float* M = P.meas_out + fo + 3 * n;
                 __stcs(M, (float)(dpx - mx0)); __stcs(M + 1, (float)(dpy - my0)); __stcs(M + 2, (float)wrap_pi(dpt - mt0));
+            }
             }
         })
         if (want_stats) write_stats16(st, P.stats, f, lane);

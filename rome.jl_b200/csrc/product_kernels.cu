@@ -28,7 +28,6 @@ namespace rome {
 
 constexpr int kProdWarps = 4;
 
-__device__ __forceinline__ float wrap_pi_f(float a) { return a - 6.283185307179586f * rintf(a * 0.15915494309189535f); }
 __device__ __forceinline__ uint32_t xorshift32(uint32_t& s) {
     s ^= s << 13; s ^= s >> 17; s ^= s << 5;
     return s;
@@ -303,7 +302,10 @@ __global__ void reanchor_kernel(unsigned char* store, int nvars, int N, int Npad
             if (c == WRAP) a = wrap_pi(a);
             hdr[c] = a;
         }
-        if (WRAP >= 0) { hdr[D] = cos(hdr[WRAP]); hdr[D + 1] = sin(hdr[WRAP]); }
+        if (WRAP >= 0) {
+            hdr[D] = cos(hdr[WRAP]); hdr[D + 1] = sin(hdr[WRAP]);
+            *reinterpret_cast<float2*>(hdr + D + 2) = make_float2((float)hdr[D], (float)hdr[D + 1]);
+        }
     }
 }
 

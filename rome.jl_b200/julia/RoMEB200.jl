@@ -26,8 +26,8 @@ const PRIORPOINT2, POINT2POINT2, POSE2POINT2, POSE2POINT2RANGE, POINT2POINT2RANG
     Cint(5), Cint(6), Cint(7), Cint(8), Cint(9), Cint(10)
 const PRIORPOINT3, POINT3POINT3, POSE3POSE3XYYAW, POSE3POSE3ROTATION, POSE3POSE3UNITTRANS =
     Cint(11), Cint(12), Cint(13), Cint(14), Cint(15)
-const RESIDUAL, PROPOSAL_FWD, PROPOSAL_BWD, STATS, SAMPLE, WRITE_MEAS, JACOBIAN, INDEPENDENT, DECONV =
-    UInt32(1), UInt32(2), UInt32(4), UInt32(8), UInt32(16), UInt32(32), UInt32(64), UInt32(128), UInt32(256)
+const RESIDUAL, PROPOSAL_FWD, PROPOSAL_BWD, STATS, SAMPLE, WRITE_MEAS, JACOBIAN, INDEPENDENT, DECONV, PRECISE =
+    UInt32(1), UInt32(2), UInt32(4), UInt32(8), UInt32(16), UInt32(32), UInt32(64), UInt32(128), UInt32(256), UInt32(512)
 const PRODUCT_REANCHOR = UInt32(1)
 
 struct Buffers            # struct rome_b200_buffers

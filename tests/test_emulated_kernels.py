@@ -170,7 +170,14 @@ def test_full_size_baseline_workloads(emulated_api):
     ref = O.sweep_pose2pose2(w["ip"], w["iq"], seen, meas)
     d = res - ref
     d[..., 2] = O.np_wrap(d[..., 2])
-    assert (np.abs(d) / np.maximum(np.abs(ref), 1e-7)).max() < 1e-5   # same inputs: pure relative down to 1e-7
+    # default arithmetic (float32 per particle): 1e-5 relative with floor 0.1 -- and on this workload the error itself
+    # stays below 3e-7 (unit steps: lever arm 1 m, offsets of ~0.1 m; measured 1.2e-7 over 3.6e6 components)
+    assert (np.abs(d) / np.maximum(np.abs(ref), 1e-1)).max() < 1e-5 and np.abs(d).max() < 3e-7, np.abs(d).max()
+    o64 = c.alloc_host_outputs(rb.POSE2POSE2, rb.RESIDUAL | rb.PRECISE)
+    c.eval_host(rb.POSE2POSE2, rb.RESIDUAL | rb.PRECISE, meas=out["meas_out"], **o64)
+    d64 = rb.rows_to_particle_major(o64["res"], N) - ref
+    d64[..., 2] = O.np_wrap(d64[..., 2])
+    assert (np.abs(d64) / np.maximum(np.abs(ref), 1e-7)).max() < 1e-5   # Float64 chain: pure relative down to 1e-7
     prop = rb.rows_to_particle_major(out["prop_fwd"], N) + c.get_anchors(rb.POSE2)[w["iq"]][:, None, :]
     # the proposal zeroes the residual: evaluate the oracle with q := proposal (one factor at a time would be slow; stack)
     stacked = np.concatenate([seen, prop])
@@ -200,7 +207,7 @@ def test_full_size_baseline_workloads(emulated_api):
     ref = O.sweep_bearingrange(ip, il, poses, points, o["meas"])
     d = o["res"] - ref
     d[..., 0] = O.np_wrap(d[..., 0])
-    assert (np.abs(d) / np.maximum(np.abs(ref), 1e-2)).max() < 1e-5
+    assert (np.abs(d) / np.maximum(np.abs(ref), 1e-1)).max() < 1e-5   # default arithmetic: floor 0.1
     p3 = rb.generateGraph_Pose3Chain(3000, loops=300)
     rb.seed_particles(p3, seed=4)
     dg3 = rb.DeviceGraph(p3)

@@ -189,14 +189,16 @@ def test_beehive_and_pose3_chain_parity():
     fl = rb.RESIDUAL | rb.SAMPLE | rb.WRITE_MEAS
     poses = np.stack([v.val for v in dg.by_type[rb.POSE2]])
     points = np.stack([v.val for v in dg.by_type[rb.POINT2]])
-    out = dg.eval(rb.BEARINGRANGE, fl, seed=1)
     facs = dg.by_family[rb.BEARINGRANGE]
     ip = [bh[f.variableOrderSymbols[0]].index for f in facs]
     il = [bh[f.variableOrderSymbols[1]].index for f in facs]
-    ref = O.sweep_bearingrange(ip, il, poses, points, out["meas"])
-    d = out["res"] - ref
-    d[..., 0] = O.np_wrap(d[..., 0])
-    assert (np.abs(d) / np.maximum(np.abs(ref), 1e-2)).max() < 1e-5
+    # default arithmetic (float32 per particle; ranges of 20 m +- 0.5 m): floor 0.1; Float64 chain (PRECISE): floor 0.01
+    for flags, floor in ((fl, 1e-1), (fl | rb.PRECISE, 1e-2)):
+        out = dg.eval(rb.BEARINGRANGE, flags, seed=1)
+        ref = O.sweep_bearingrange(ip, il, poses, points, out["meas"])
+        d = out["res"] - ref
+        d[..., 0] = O.np_wrap(d[..., 0])
+        assert (np.abs(d) / np.maximum(np.abs(ref), floor)).max() < 1e-5
     p3 = rb.generateGraph_Pose3Chain(400, loops=40)
     rb.seed_particles(p3, seed=4)
     dg3 = rb.DeviceGraph(p3)
