@@ -252,6 +252,24 @@ ROME_B200_API int rome_b200_reanchor(rome_b200_ctx* ctx, int vartype);
  * proposals -- no separate all-gather pass; only a stream-ordered barrier between the ranks is still needed.
  * n_peers <= 7; n_peers = 0 clears. */
 ROME_B200_API int rome_b200_set_peer_proposals(rome_b200_ctx* ctx, int family, int n_peers, float* const* peer_prop_fwd);
+/* ---- multi-GPU, owner-sharded (the exchange of a sweep whose variables AND factors are partitioned) ---------------
+ * Every rank owns a contiguous range of variables and evaluates the factors placed on it; only what a cut edge needs
+ * crosses NVLink: the proposal row of a factor whose target variable lives on another rank, and the particle blocks of
+ * the foreign ("halo") variables its factors read.
+ * rome_b200_set_proposal_destinations: rows[f] = device address the forward (direction 0) / backward (direction 1)
+ * proposal row of factor f is written to INSTEAD of row f of prop_fwd / prop_bwd, or NULL for that default; typically
+ * a row of a receive buffer in the owner's memory (rome_b200_ipc_import).  Forward rows leave through the kernel's own
+ * TMA bulk stores, backward rows through its streaming stores -- the transfer rides on the evaluation, tile by tile.
+ * nF must equal the number of factors of the family; nF = 0 clears.
+ * rome_b200_set_halo_plan / rome_b200_push_halo: copy the particle blocks (anchor header + offsets) of the listed local
+ * variables to the given device addresses (slots in the peers' particle stores, rome_b200_particles_device of the peer
+ * + slot * block_bytes, imported through CUDA IPC); run it after the belief update of a sweep.
+ * Order both against the peers with rome_b200_peer_signal / rome_b200_peer_wait. */
+ROME_B200_API int rome_b200_set_proposal_destinations(rome_b200_ctx* ctx, int family, int direction, int nF,
+                                                      void* const* rows);
+ROME_B200_API int rome_b200_set_halo_plan(rome_b200_ctx* ctx, int vartype, int n, const int32_t* src_var,
+                                          void* const* dst_blocks);
+ROME_B200_API int rome_b200_push_halo(rome_b200_ctx* ctx, int vartype);
 /* CUDA IPC plumbing for buffers allocated with rome_b200_malloc_device (64-byte opaque handles).  Only such buffers may
  * be exported: rome_b200_malloc_device hands out whole 2 MiB blocks, so the handle (which names the driver's block) and
  * the buffer coincide; a pointer into a packed small cudaMalloc allocation would be opened at the wrong address. */

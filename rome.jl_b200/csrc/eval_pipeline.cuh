@@ -189,8 +189,14 @@ __global__ void __launch_bounds__((FT + 1) * 32, Fam::kMinCtas) eval_kernel(cons
         fence_mbar_init();
     }
     __syncthreads();
-    // programmatic dependent launch: a following launch flagged ROME_B200_INDEPENDENT may begin as SMs free up
+    // Programmatic dependent launch.  Every launch lets its successor start on SMs this grid has vacated
+    // (launch_dependents), and every launch is itself started that way: what it has done so far -- barrier
+    // initialisation and the first variable ids, read from the factor table, which no kernel writes -- overlaps the
+    // predecessor's tail and the launch latency.  Before the first access to data a predecessor may have written
+    // (particle blocks) or may still read (the output buffers) it waits for the predecessor grid to complete; a launch
+    // flagged ROME_B200_INDEPENDENT touches no such data and defers that wait to its end.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (!(P.flags & ROME_B200_INDEPENDENT)) asm volatile("griddepcontrol.wait;" ::: "memory");
 
     if (warp == FT) {
         // ---------------- producer warp ---------------------------------------------------------------------
@@ -245,6 +251,10 @@ __global__ void __launch_bounds__((FT + 1) * 32, Fam::kMinCtas) eval_kernel(cons
                 V.meas = kSample ? nullptr : reinterpret_cast<const float*>(st + L.meas_off + (size_t)warp * L.mb);
                 V.out_res = out;
                 V.out_fwd = out + res_floats;
+                // owner-sharded exchange: this factor's forward row may have its own destination (a peer GPU); requested
+                // before the arithmetic so that the load's latency hides behind it
+                unsigned long long fdst = 0;
+                if ((flags & ROME_B200_PROPOSAL_FWD) && P.fwd_dst && lane == 0) fdst = __ldg(P.fwd_dst + f);
                 if (flags & (ROME_B200_RESIDUAL | ROME_B200_PROPOSAL_FWD)) {
                     if (lane == 0) tma_store_wait_read();  // the previous tile's rows have left the slice
                     __syncwarp();
@@ -259,7 +269,7 @@ __global__ void __launch_bounds__((FT + 1) * 32, Fam::kMinCtas) eval_kernel(cons
                         if (flags & ROME_B200_PROPOSAL_FWD) {
                             const size_t off = (size_t)f * Fam::DFWD * P.Npad;
                             const uint32_t bytes = (uint32_t)(Fam::DFWD * P.Npad * 4);
-                            tma_store_1d(P.prop_fwd + off, V.out_fwd, bytes);
+                            tma_store_1d(fdst ? reinterpret_cast<float*>(fdst) : P.prop_fwd + off, V.out_fwd, bytes);
                             // fused all-gather: the same slice goes to every peer GPU over NVLink
                             for (int r = 0; r < P.n_peers; ++r) tma_store_1d(P.peer_fwd[r] + off, V.out_fwd, bytes);
                         }
@@ -342,8 +352,9 @@ __global__ void __launch_bounds__(FT * 32, Fam::kMinCtas) eval_kernel_w(const __
         fence_mbar_init();
     }
     __syncwarp();
-    if (lane < S) issue(lane, lane, ids);
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (!(P.flags & ROME_B200_INDEPENDENT)) asm volatile("griddepcontrol.wait;" ::: "memory");  // see eval_kernel
+    if (lane < S) issue(lane, lane, ids);
 
     int s = 0;
     uint32_t phase = 0;
@@ -361,6 +372,8 @@ __global__ void __launch_bounds__(FT * 32, Fam::kMinCtas) eval_kernel_w(const __
         V.meas = kSample ? nullptr : reinterpret_cast<const float*>(st + L.meas_off);
         V.out_res = out;
         V.out_fwd = out + res_floats;
+        unsigned long long fdst = 0;  // owner-sharded exchange: per-factor destination of the forward row
+        if ((flags & ROME_B200_PROPOSAL_FWD) && P.fwd_dst && lane == 0) fdst = __ldg(P.fwd_dst + f);
         if (flags & (ROME_B200_RESIDUAL | ROME_B200_PROPOSAL_FWD)) {
             if (lane == 0) tma_store_wait_read();  // the previous factor's rows have left the slice
             __syncwarp();
@@ -375,7 +388,7 @@ __global__ void __launch_bounds__(FT * 32, Fam::kMinCtas) eval_kernel_w(const __
                 if (flags & ROME_B200_PROPOSAL_FWD) {
                     const size_t off = (size_t)f * Fam::DFWD * P.Npad;
                     const uint32_t bytes = (uint32_t)(Fam::DFWD * P.Npad * 4);
-                    tma_store_1d(P.prop_fwd + off, V.out_fwd, bytes);
+                    tma_store_1d(fdst ? reinterpret_cast<float*>(fdst) : P.prop_fwd + off, V.out_fwd, bytes);
                     for (int r = 0; r < P.n_peers; ++r) tma_store_1d(P.peer_fwd[r] + off, V.out_fwd, bytes);
                 }
                 tma_store_commit();
@@ -408,7 +421,7 @@ int launch_kernel_cfg(K k, int* configured, int threads, const EvalParams& p, co
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = (p.flags & ROME_B200_INDEPENDENT) ? 1 : 0;
+    cfg.numAttrs = 1;
     return (int)cudaLaunchKernelEx(&cfg, k, p);
 }
 template <class Fam, uint32_t kStatic, bool kSample, int FT>

@@ -33,6 +33,7 @@ struct FamBearingRange {
         const double iD2 = 1.0 / D2;
         const double phi0 = atan2(day, dax);
         const size_t fo = (size_t)f * 2 * Npad;
+        float* const bwd = (flags & ROME_B200_PROPOSAL_BWD) ? bwd_row(P, f, (size_t)3 * Npad) : nullptr;
         const bool want_stats = flags & ROME_B200_STATS;
         float st[16];
 #pragma unroll
@@ -115,7 +116,7 @@ struct FamBearingRange {
                     if (flags & ROME_B200_PROPOSAL_BWD) {
                         const float ox = (lxy.x - g0x) - gx, oy = (lxy.y - g0y) - gy;
                         if (live) {
-                            float* B = P.prop_bwd + (size_t)f * 3 * Npad + 3 * n;
+                            float* B = bwd + 3 * n;
                             __stcs(B, ox); __stcs(B + 1, oy); __stcs(B + 2, pt);
                         }
                         if (want_stats && !(flags & ROME_B200_PROPOSAL_FWD)) acc_prop2(st, msk, ox, oy);
@@ -172,7 +173,7 @@ struct FamBearingRange {
                     // particle's current heading is t_p = l - rho R(theta_p)(cos b, sin b)   (offsets from anchor(p))
                     const float ox = (float)((dlx + dax) - rho * c), oy = (float)((dly + day) - rho * s);
                     if (live) {
-                        float* B = P.prop_bwd + (size_t)f * 3 * Npad + 3 * n;
+                        float* B = bwd + 3 * n;
                         __stcs(B, ox); __stcs(B + 1, oy); __stcs(B + 2, (float)dpt);
                     }
                     if (want_stats && !(flags & ROME_B200_PROPOSAL_FWD)) acc_prop2(st, msk, ox, oy);

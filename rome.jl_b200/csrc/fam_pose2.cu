@@ -32,6 +32,7 @@ struct FamPose2Pose2 {
         const double dax = ap[0] - aq[0], day = ap[1] - aq[1], dat = apt - aq[2];  // anchor deltas (exact Float64)
         const double mu0 = row.mu[0], mu1 = row.mu[1], mu2 = row.mu[2];
         const size_t fo = (size_t)f * 3 * Npad;
+        float* const bwd = (flags & ROME_B200_PROPOSAL_BWD) ? bwd_row(P, f, (size_t)3 * Npad) : nullptr;
         const bool want_stats = flags & ROME_B200_STATS;
         float st[16];
 #pragma unroll
@@ -107,7 +108,7 @@ struct FamPose2Pose2 {
                     const float oy = ((qy - c0y) - (c0yl + r0y)) - fmaf(cb1, by, sb * bx);
                     const float ot = wrap_pi_f(tb);
                     if (live) {
-                        float* B = P.prop_bwd + fo + 3 * n;
+                        float* B = bwd + 3 * n;
                         __stcs(B, ox); __stcs(B + 1, oy); __stcs(B + 2, ot);
                     }
                     if (want_stats && !(flags & ROME_B200_PROPOSAL_FWD)) {
@@ -144,7 +145,7 @@ struct FamPose2Pose2 {
                 const float oy = (float)((dqy - day) - (sb * Xx + cb * Xy));
                 const float ot = (float)wrap_pi(tb);
                 if (live) {
-                    float* B = P.prop_bwd + fo + 3 * n;
+                    float* B = bwd + 3 * n;
                     __stcs(B, ox); __stcs(B + 1, oy); __stcs(B + 2, ot);
                 }
                 if (want_stats && !(flags & ROME_B200_PROPOSAL_FWD)) {

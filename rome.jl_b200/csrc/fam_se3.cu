@@ -18,6 +18,7 @@ struct FamPose3Pose3 {
         const float* Pp = reinterpret_cast<const float*>(V.b0 + var_header_bytes(6));
         const float* Qp = reinterpret_cast<const float*>(V.b1 + var_header_bytes(6));
         const size_t fo = (size_t)f * 6 * Npad;
+        float* const bwd = (flags & ROME_B200_PROPOSAL_BWD) ? bwd_row(P, f, (size_t)6 * Npad) : nullptr;
         const bool want_stats = flags & ROME_B200_STATS;
         const double dax = ap[0] - aq[0], day = ap[1] - aq[1], daz = ap[2] - aq[2];  // anchor delta (exact Float64)
         float st[32];
@@ -125,7 +126,7 @@ struct FamPose3Pose3 {
                     const float o[6] = {(float)(((double)q[j][0] - dax) - bx), (float)(((double)q[j][1] - day) - by),
                                         (float)(((double)q[j][2] - daz) - bz), (float)(ox - ap[3]),
                                         (float)(oy - ap[4]),                   (float)(oz - ap[5])};
-                    if (live) store6_global(P.prop_bwd + fo + 6 * n, o);
+                    if (live) store6_global(bwd + 6 * n, o);
                     if (want_stats && !(flags & ROME_B200_PROPOSAL_FWD)) acc_prop3(st, msk, o[0], o[1], o[2]);
                 }
             }

@@ -56,4 +56,21 @@ int launch_peer_wait(const uint32_t* flags, int n, uint32_t* epoch, uint32_t* st
     return (int)cudaGetLastError();
 }
 
+// Halo push (owner-sharded sweeps): copy whole particle blocks of variables this rank owns into the particle stores of
+// the peers that read them -- one warp per block, 16-byte stores over NVLink peer memory.
+__global__ void halo_push_kernel(const unsigned char* __restrict__ store, int block_bytes, int n,
+                                 const int32_t* __restrict__ src_var, const unsigned long long* __restrict__ dst_blocks) {
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= n) return;
+    const uint4* src = reinterpret_cast<const uint4*>(store + (size_t)src_var[i] * block_bytes);
+    uint4* dst = reinterpret_cast<uint4*>(dst_blocks[i]);
+    for (int k = lane; k < block_bytes / 16; k += 32) dst[k] = src[k];
+}
+int launch_halo_push(const unsigned char* store, int block_bytes, int n, const int32_t* src_var,
+                     const unsigned long long* dst_blocks, void* stream) {
+    if (n <= 0) return 0;
+    halo_push_kernel<<<(n + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(store, block_bytes, n, src_var, dst_blocks);
+    return (int)cudaGetLastError();
+}
+
 }  // namespace rome

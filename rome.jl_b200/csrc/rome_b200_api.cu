@@ -78,6 +78,10 @@ struct rome_b200_ctx {
     ProductPlan plan[ROME_B200_NVARTYPES];
     int n_peers[ROME_B200_NFAMILIES] = {};
     float* peers[ROME_B200_NFAMILIES][7] = {};
+    Scratch row_dst[ROME_B200_NFAMILIES][2];     // per-factor proposal row destinations (fwd, bwd), device arrays
+    int row_dst_n[ROME_B200_NFAMILIES][2] = {};  // number of factors they cover (0 = not set)
+    Scratch halo_src[ROME_B200_NVARTYPES], halo_dst[ROME_B200_NVARTYPES];
+    int halo_n[ROME_B200_NVARTYPES] = {};
     std::vector<cudaGraphExec_t> graphs;
     std::vector<uint64_t> graph_kernels;
     bool capturing = false;
@@ -244,6 +248,9 @@ int rome_b200_destroy(rome_b200_ctx* ctx) {
     cudaFreeHost(ctx->stage_host.p);
     for (auto& f : ctx->out_dev) for (auto& s : f) cudaFree(s.p);
     for (auto& pl : ctx->plan) { cudaFree(pl.off.p); cudaFree(pl.buf.p); cudaFree(pl.row.p); }
+    for (auto& f : ctx->row_dst) for (auto& s : f) cudaFree(s.p);
+    for (auto& s : ctx->halo_src) cudaFree(s.p);
+    for (auto& s : ctx->halo_dst) cudaFree(s.p);
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return ROME_B200_OK;
@@ -304,8 +311,12 @@ int rome_b200_set_particles(rome_b200_ctx* ctx, int vartype, int nvars, int N, c
     if (store_bytes > vs.cap) {
         if (vs.store) CK(cudaFree(vs.store));
         vs.store = nullptr; vs.cap = 0;
-        CK(cudaMalloc(&vs.store, store_bytes));
-        vs.cap = store_bytes;
+        // whole 2 MiB blocks: the store may be exported through CUDA IPC (halo blocks pushed by peer GPUs), and an IPC
+        // handle names the driver's allocation block, see rome_b200_malloc_device
+        const size_t kBlock = size_t(2) << 20;
+        const size_t rounded = (store_bytes + kBlock - 1) / kBlock * kBlock;
+        CK(cudaMalloc(&vs.store, rounded));
+        vs.cap = rounded;
     }
     vs.nvars = nvars; vs.N = N; vs.Npad = Npad;
     if (nvars == 0) return ROME_B200_OK;
@@ -537,6 +548,14 @@ int rome_b200_eval(rome_b200_ctx* ctx, int family, uint32_t flags, uint64_t seed
     p.stats = b->stats; p.jac = b->jac;
     p.n_peers = (flags & ROME_B200_PROPOSAL_FWD) ? ctx->n_peers[family] : 0;
     for (int r = 0; r < 7; ++r) p.peer_fwd[r] = ctx->peers[family][r];
+    p.fwd_dst = p.bwd_dst = nullptr;
+    for (int dir = 0; dir < 2; ++dir) {
+        const int n = ctx->row_dst_n[family][dir];
+        if (!n) continue;
+        if (n != ctx->fac[family].nF)
+            return fail(ctx, ROME_B200_SHAPE_MISMATCH, "proposal destinations were set for a different number of factors");
+        (dir ? p.bwd_dst : p.fwd_dst) = static_cast<const unsigned long long*>(ctx->row_dst[family][dir].p);
+    }
     p.flags = flags;
     p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32); p.stream_id = stream_id;
     LaunchPlan plan;
@@ -700,6 +719,62 @@ int rome_b200_set_peer_proposals(rome_b200_ctx* ctx, int family, int n_peers, fl
             return fail(ctx, ROME_B200_BAD_ARG, "peer buffers must be non-NULL and 16-byte aligned");
     ctx->n_peers[family] = n_peers;
     for (int r = 0; r < 7; ++r) ctx->peers[family][r] = r < n_peers ? peer_prop_fwd[r] : nullptr;
+    return ROME_B200_OK;
+}
+int rome_b200_set_proposal_destinations(rome_b200_ctx* ctx, int family, int direction, int nF, void* const* rows) {
+    if (!ctx) return ROME_B200_BAD_ARG;
+    if (family < 0 || family >= ROME_B200_NFAMILIES || (direction != 0 && direction != 1))
+        return fail(ctx, ROME_B200_BAD_ARG, "bad family / direction");
+    if (ctx->capturing) return fail(ctx, ROME_B200_BAD_ARG, "set_proposal_destinations during graph capture");
+    if (nF == 0) { ctx->row_dst_n[family][direction] = 0; return ROME_B200_OK; }
+    if (nF < 0 || !rows) return fail(ctx, ROME_B200_BAD_ARG, "bad destination array");
+    if (nF != ctx->fac[family].nF) return fail(ctx, ROME_B200_SHAPE_MISMATCH, "one destination per factor of the family is required");
+    const FamInfo& fi = kFam[family];
+    if ((direction == 0 ? fi.dfwd : fi.dbwd) == 0) return fail(ctx, ROME_B200_BAD_ARG, "this family has no proposal in that direction");
+    for (int f = 0; f < nF; ++f)
+        if ((uintptr_t)rows[f] & 15) return fail(ctx, ROME_B200_BAD_ARG, "destination rows must be 16-byte aligned");
+    if (int e = bind(ctx)) return e;
+    Scratch& sc = ctx->row_dst[family][direction];
+    if (int e = grow_dev(ctx, sc, (size_t)nF * 8)) return e;
+    static_assert(sizeof(void*) == 8, "64-bit pointers");
+    CK(cudaMemcpyAsync(sc.p, rows, (size_t)nF * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));  // the caller's array may be a temporary
+    ctx->row_dst_n[family][direction] = nF;
+    return ROME_B200_OK;
+}
+int rome_b200_set_halo_plan(rome_b200_ctx* ctx, int vartype, int n, const int32_t* src_var, void* const* dst_blocks) {
+    if (!ctx) return ROME_B200_BAD_ARG;
+    if (vartype < 0 || vartype >= ROME_B200_NVARTYPES) return fail(ctx, ROME_B200_BAD_ARG, "bad vartype");
+    if (ctx->capturing) return fail(ctx, ROME_B200_BAD_ARG, "set_halo_plan during graph capture");
+    if (n == 0) { ctx->halo_n[vartype] = 0; return ROME_B200_OK; }
+    if (n < 0 || !src_var || !dst_blocks) return fail(ctx, ROME_B200_BAD_ARG, "bad halo arrays");
+    const VarStore& vs = ctx->vars[vartype];
+    for (int i = 0; i < n; ++i) {
+        if (src_var[i] < 0 || src_var[i] >= vs.nvars) return fail(ctx, ROME_B200_BAD_ARG, "halo source variable out of range");
+        if (!dst_blocks[i] || ((uintptr_t)dst_blocks[i] & 15)) return fail(ctx, ROME_B200_BAD_ARG, "halo destinations must be non-NULL and 16-byte aligned");
+    }
+    if (int e = bind(ctx)) return e;
+    if (int e = grow_dev(ctx, ctx->halo_src[vartype], (size_t)n * 4)) return e;
+    if (int e = grow_dev(ctx, ctx->halo_dst[vartype], (size_t)n * 8)) return e;
+    CK(cudaMemcpyAsync(ctx->halo_src[vartype].p, src_var, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->halo_dst[vartype].p, dst_blocks, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->halo_n[vartype] = n;
+    return ROME_B200_OK;
+}
+int rome_b200_push_halo(rome_b200_ctx* ctx, int vartype) {
+    if (!ctx) return ROME_B200_BAD_ARG;
+    if (vartype < 0 || vartype >= ROME_B200_NVARTYPES) return fail(ctx, ROME_B200_BAD_ARG, "bad vartype");
+    const int n = ctx->halo_n[vartype];
+    if (n == 0) return ROME_B200_OK;
+    const VarStore& vs = ctx->vars[vartype];
+    if (vs.nvars == 0) return fail(ctx, ROME_B200_NOT_SET, "particles of this variable type are not set");
+    if (int e = bind(ctx)) return e;
+    int e = launch_halo_push(vs.store, var_block_bytes(kVarDim[vartype], vs.Npad), n,
+                             static_cast<const int32_t*>(ctx->halo_src[vartype].p),
+                             static_cast<const unsigned long long*>(ctx->halo_dst[vartype].p), ctx->stream);
+    if (e) return cuda_fail(ctx, (cudaError_t)e, "halo push launch");
+    if (ctx->capturing) ctx->capture_kernels++; else ctx->launches++;
     return ROME_B200_OK;
 }
 int rome_b200_ipc_export(rome_b200_ctx* ctx, void* dev_ptr, unsigned char handle[64]) {

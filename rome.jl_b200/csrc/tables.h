@@ -83,7 +83,19 @@ struct EvalParams {
     int out_warp_bytes;  // shared-memory output staging per consumer warp (residual rows [+ forward proposal rows])
     int n_peers;         // forward proposals are also stored to these peer-GPU buffers (fused all-gather)
     float* peer_fwd[7];
+    // owner-sharded exchange: per-factor destination of the forward / backward proposal row (device pointers, possibly
+    // into a peer GPU's memory; 0 = the default row of prop_fwd / prop_bwd); arrays indexed by factor id, or null
+    const unsigned long long* fwd_dst;
+    const unsigned long long* bwd_dst;
 };
+// row of the backward proposal of factor f (row_floats = dbwd * Npad)
+__host__ __device__ inline float* bwd_row(const EvalParams& P, int f, size_t row_floats) {
+    if (P.bwd_dst) {
+        const unsigned long long d = P.bwd_dst[f];
+        if (d) return reinterpret_cast<float*>(d);
+    }
+    return P.prop_bwd + (size_t)f * row_floats;
+}
 
 struct ProductParams {
     unsigned char* store;        // particle store of the variable type (updated in place)
@@ -118,6 +130,8 @@ int launch_unpack(int d, int wrap_dim, int nvars, int N, int Npad, const unsigne
 int launch_adopt(int d, int Npad, unsigned char* store, int var, const float* prop, int factor, void* stream);
 int launch_product(int d, int wrap_dim, const void* params, int num_sms, void* stream);
 int launch_reanchor(int d, int wrap_dim, unsigned char* store, int nvars, int N, int Npad, void* stream);
+int launch_halo_push(const unsigned char* store, int block_bytes, int n, const int32_t* src_var,
+                     const unsigned long long* dst_blocks, void* stream);
 int launch_peer_signal(uint32_t* const* slots, int n_peers, uint32_t* epoch, void* stream);
 int launch_peer_wait(const uint32_t* flags, int n, uint32_t* epoch, uint32_t* status, long long max_cycles, void* stream);
 

@@ -297,6 +297,22 @@ class Context:
         arr = (C.c_void_p * max(1, len(peer_ptrs)))(*peer_ptrs)
         self._ck(self._lib.rome_b200_set_peer_proposals(self._h, family, len(peer_ptrs), arr))
 
+    # -- multi-GPU, owner-sharded: per-factor proposal destinations + halo particle blocks ---------------
+    def set_proposal_destinations(self, family: int, direction: int, row_ptrs):
+        """row_ptrs[f]: device address (int, 0 = default row) the forward (0) / backward (1) proposal row of factor f
+        is written to; [] clears"""
+        n = len(row_ptrs)
+        arr = (C.c_void_p * max(1, n))(*[int(p) or None for p in row_ptrs])
+        self._ck(self._lib.rome_b200_set_proposal_destinations(self._h, family, direction, n, arr))
+
+    def set_halo_plan(self, vartype: int, src_vars, dst_block_ptrs):
+        src = _i32(src_vars)
+        arr = (C.c_void_p * max(1, len(src)))(*[int(p) for p in dst_block_ptrs])
+        self._ck(self._lib.rome_b200_set_halo_plan(self._h, vartype, len(src), self._ip(src), arr))
+
+    def push_halo(self, vartype: int):
+        self._ck(self._lib.rome_b200_push_halo(self._h, vartype))
+
     # -- GPU-side barrier between ranks over NVLink peer memory (closes the fused exchange) ---------------
     def peer_state_alloc(self) -> int:
         """zeroed device state buffer (flag slots + epochs) for peer_signal / peer_wait"""

@@ -82,3 +82,149 @@ def exchange_bytes(plan, n_factors: int, world: int, row_bytes: int, block_bytes
         recv_rows[dst] += len(ids)
     owner = max(r * row_bytes + len(h) * block_bytes for r, h in zip(recv_rows, plan["halo"]))
     return allgather, owner
+
+
+# ---- owner-sharded sweeps: variables AND factors partitioned, only cut edges cross ------------------------------------
+def balanced_bounds(i0_lists, nvars: int, world: int):
+    """contiguous variable ranges [b[r], b[r+1]) such that the factors placed by their first variable (i0 of every
+    family given) are spread evenly over the ranks (a rank's work is its factor count, not its variable count)"""
+    import numpy as np
+    load = np.zeros(nvars, dtype=np.int64)
+    for i0 in i0_lists:
+        load += np.bincount(np.asarray(i0, dtype=np.int64), minlength=nvars)
+    cum = np.concatenate([[0], np.cumsum(load)])
+    total = cum[-1]
+    b = [0]
+    for r in range(1, world):
+        b.append(int(np.searchsorted(cum, total * r / world, side="left")))
+    b.append(nvars)
+    b = np.maximum.accumulate(np.asarray(b, dtype=np.int64))
+    return b
+
+
+class OwnerSharding:
+    """Plan of an owner-sharded sweep.
+
+    Every variable type is split into contiguous ranges, one per rank (`bounds[vt]`, world + 1 entries).  A factor is
+    evaluated on the owner of its FIRST variable; if its LAST variable belongs to another rank it is a CUT factor: that
+    rank's copy of the last variable is a HALO block (pushed by the owner after every belief update) and the factor's
+    forward proposal row is written straight into a receive buffer of the owner (rome_b200_set_proposal_destinations).
+    Everything is derived from the global index arrays, identically on every rank, so no plan has to be exchanged.
+
+    families: {family id: (vt0, vt1 or None, i0 array, i1 array or None)}    nvars: {vt: count}"""
+
+    def __init__(self, world: int, nvars: dict, families: dict, bounds: dict | None = None):
+        import numpy as np
+        self.world, self.nvars, self.families = world, dict(nvars), {}
+        self.bounds = {}
+        for vt, n in nvars.items():
+            if bounds and vt in bounds:
+                b = np.asarray(bounds[vt], dtype=np.int64)
+            else:
+                c = shard_size(n, world)
+                b = np.minimum(np.arange(world + 1, dtype=np.int64) * c, n)
+            assert len(b) == world + 1 and b[0] == 0 and b[-1] == n and (np.diff(b) >= 0).all()
+            self.bounds[vt] = b
+        for fam, (vt0, vt1, i0, i1) in families.items():
+            i0 = np.asarray(i0, dtype=np.int64)
+            r0 = self.owner(vt0, i0)
+            if vt1 is None or i1 is None:
+                i1, r1 = None, r0
+            else:
+                i1 = np.asarray(i1, dtype=np.int64)
+                r1 = self.owner(vt1, i1)
+            self.families[fam] = dict(vt0=vt0, vt1=vt1 if i1 is not None else None, i0=i0, i1=i1, rank=r0, dst=r1)
+        self._local = {}
+
+    def owner(self, vt, index):
+        import numpy as np
+        return np.searchsorted(self.bounds[vt], np.asarray(index), side="right") - 1
+
+    def recv_layout(self, fam, rank):
+        """global ids of the cut factors whose forward rows land on `rank`, in receive-buffer row order (by source
+        rank, then by global id), and the row offset of every source rank"""
+        import numpy as np
+        F = self.families[fam]
+        ids = np.nonzero((F["dst"] == rank) & (F["rank"] != rank))[0]
+        order = np.lexsort((ids, F["rank"][ids]))
+        return ids[order]
+
+    def local(self, rank: int):
+        """everything rank `rank` needs: its variables (owned, then halo), its factors (interior, then cut) with local
+        indices, the destination (rank, row) of every cut factor's forward row, and the halo blocks it must push"""
+        import numpy as np
+        if rank in self._local:
+            return self._local[rank]
+        own = {vt: (int(b[rank]), int(b[rank + 1])) for vt, b in self.bounds.items()}
+        halo = {vt: [] for vt in self.bounds}
+        for fam, F in self.families.items():
+            if F["i1"] is None:
+                continue
+            cut = (F["rank"] == rank) & (F["dst"] != rank)
+            halo[F["vt1"]].append(F["i1"][cut])
+        halo = {vt: (np.unique(np.concatenate(v)) if v else np.zeros(0, np.int64)) for vt, v in halo.items()}
+        var_global = {vt: np.concatenate([np.arange(*own[vt], dtype=np.int64), halo[vt]]) for vt in self.bounds}
+
+        def to_local(vt, gid):
+            lo, hi = own[vt]
+            inside = (gid >= lo) & (gid < hi)
+            pos = np.searchsorted(halo[vt], gid)
+            pos = np.minimum(pos, max(len(halo[vt]) - 1, 0))
+            if len(halo[vt]):
+                assert (inside | (halo[vt][pos] == gid)).all()
+            else:
+                assert inside.all()
+            return np.where(inside, gid - lo, (hi - lo) + pos).astype(np.int32)
+
+        fams = {}
+        for fam, F in self.families.items():
+            mine = np.nonzero(F["rank"] == rank)[0]
+            is_cut = F["dst"][mine] != rank
+            interior, cutf = mine[~is_cut], mine[is_cut]
+            cutf = cutf[np.lexsort((cutf, F["dst"][cutf]))]  # grouped by destination rank
+            order = np.concatenate([interior, cutf])
+            dst_rank = F["dst"][cutf]
+            dst_row = np.zeros(len(cutf), dtype=np.int64)
+            for d in np.unique(dst_rank):
+                lay = self.recv_layout(fam, int(d))
+                sel = dst_rank == d
+                pos = {int(g): k for k, g in enumerate(lay)}
+                dst_row[sel] = [pos[int(g)] for g in cutf[sel]]
+            fams[fam] = dict(order=order, n_interior=len(interior), n_cut=len(cutf),
+                             i0=to_local(F["vt0"], F["i0"][order]),
+                             i1=to_local(F["vt1"], F["i1"][order]) if F["i1"] is not None else None,
+                             dst_rank=dst_rank, dst_row=dst_row, recv=self.recv_layout(fam, rank))
+        # halo blocks this rank owns and must push: (reader rank, local variable id here, slot in the reader's store)
+        push = {vt: [] for vt in self.bounds}
+        for other in range(self.world):
+            if other == rank:
+                continue
+            oown = {vt: (int(b[other]), int(b[other + 1])) for vt, b in self.bounds.items()}
+            for vt in self.bounds:
+                need = []
+                for fam, F in self.families.items():
+                    if F["i1"] is None or F["vt1"] != vt:
+                        continue
+                    cut = (F["rank"] == other) & (F["dst"] == rank)
+                    need.append(F["i1"][cut])
+                need = np.unique(np.concatenate(need)) if need else np.zeros(0, np.int64)
+                if len(need) == 0:
+                    continue
+                # the reader's halo list is the sorted unique set of ALL its foreign last variables of this type
+                ohalo = []
+                for fam, F in self.families.items():
+                    if F["i1"] is None or F["vt1"] != vt:
+                        continue
+                    ohalo.append(F["i1"][(F["rank"] == other) & (F["dst"] != other)])
+                ohalo = np.unique(np.concatenate(ohalo))
+                slot = (oown[vt][1] - oown[vt][0]) + np.searchsorted(ohalo, need)
+                push[vt].append((other, (need - own[vt][0]).astype(np.int32), slot.astype(np.int64)))
+        out = dict(own=own, halo=halo, var_global=var_global, fam=fams, push=push)
+        self._local[rank] = out
+        return out
+
+    def exchange_bytes(self, rank, row_bytes: dict, block_bytes: dict):
+        """bytes RECEIVED by `rank` per sweep: forward rows of cut factors targeting it + halo blocks it reads"""
+        L = self.local(rank)
+        return sum(len(f["recv"]) * row_bytes[fam] for fam, f in L["fam"].items()) + \
+            sum(len(h) * block_bytes[vt] for vt, h in L["halo"].items())

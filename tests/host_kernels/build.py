@@ -55,7 +55,7 @@ def source_text():
     pipe = pipe.replace("extern __shared__ __align__(128) unsigned char smem[];",
                         "unsigned char* const smem = hk::g_smem;  /* one block at a time: its dynamic shared memory */")
     pipe, n = re.subn(r'asm volatile\("griddepcontrol\.[a-z_]+;" ::: "memory"\);', "/* griddepcontrol: scheduling hint, no effect on results */;", pipe)
-    assert n == 4 and pipe.count("unsigned char* const smem = hk::g_smem") == 2
+    assert n == 6 and pipe.count("unsigned char* const smem = hk::g_smem") == 2
     parts.append(pipe)
     parts.append(open(os.path.join(HERE, "hk_launch.inc")).read())   # launch_kernel_cfg: run the grid under the emulator
     parts.append(ep[ep.index("template <class Fam, uint32_t kStatic, bool kSample, int FT>\nint launch_ft("):ep.rindex("}  // namespace rome")])
