@@ -3,26 +3,39 @@
 
 Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON line.
 
-Workload (config.workload = "manhattan_shaped_10k_se2_N100"): the configuration BASELINE.json's target is
-quoted on -- a synthetic Manhattan-world SE(2) graph of 10 000 Pose2 x N=100 particles with 9 999 odometry +
-2 000 loop-closure Pose2Pose2 factors and one PriorPose2 (rome_b200.generateGraph_ManhattanShaped, seed 2;
-particles = simulated truth + sigma (0.1, 0.12, 0.02), seed 1).
-A STEP is one pass of the hot path over the whole graph: for every factor x every particle, getSample
-(in-kernel Philox) + residual + per-factor statistics -- one launch of the fused Pose2Pose2 kernel and one of
-the PriorPose2 kernel.  With --gpus N > 1 the graph is replicated N times (weak scaling: one 10k-pose graph's
-factors per rank, particles of all N graphs resident on every GPU), each rank also writes the closed-form
-proposals of its factors and one NCCL all-gather per step exchanges them.
+Workloads (BASELINE.json configs; --workload):
+  manhattan_shaped_10k_se2_N100 (default, the configuration the north-star target is quoted on): synthetic
+      Manhattan-world SE(2) graph, 10 000 Pose2 PER GPU x N=100 particles, 9 999 odometry + 2 000 loop-closure Pose2Pose2
+      per 10 000 poses and one PriorPose2 (rome_b200.workloads.manhattan_arrays, seeds 2 / 1) -- WEAK scaling: with
+      --gpus G the graph has G x 10 000 poses.
+  beehive_N200  (config 4): Beehive2D, 10 000 Pose2 + lattice landmarks, Pose2Pose2 + Pose2Point2BearingRange +
+      PriorPose2, N=200 -- STRONG scaling (the one graph is split over the GPUs).
+  se3_chain_10k (config 5): SE(3) helix chain, 10 000 Pose3, 9 999 + 1 000 Pose3Pose3 + PriorPose3, N=100 -- STRONG.
 
-Timing: W warm-up steps, then EXACTLY K steps inside one CUDA-event pair on the launch stream, bracketed by a
-barrier + torch.cuda.synchronize(); max over ranks.  L2: the K steps rotate through `sets` independent copies
-of the whole working set (particles + tables + outputs; > 2x the 126 MB L2), so no step finds its inputs in L2.
-The K steps are replayed from one CUDA graph (launch latency is otherwise comparable to the 10-20 us kernel).
+A STEP is one pass of the hot path over the whole graph: for every factor x every particle, getSample (in-kernel Philox)
++ residual + per-factor statistics, one fused kernel launch per factor family.  Steps are DEPENDENT (as Gibbs sweeps
+are): the first launch of a step waits for the previous step to complete; the other family kernels of the same sweep
+read the same particles and write other buffers, so they carry ROME_B200_INDEPENDENT and overlap it.
 
-`e2e`: the same metric through the public host API with HOST buffers every step: pinned Float64 particles in
-the reference layout -> rome_b200_set_particles (H2D + layout kernel) -> rome_b200_eval_host (kernels + D2H of
-residuals and statistics).
-`cpu_baseline` / `--impl reference`: the float64 C restatement (oracle/) of the same residual sweep on the
-host cores (kind "port": the Julia reference cannot run in this image).
+--gpus G > 1 (one process per GPU): owner-sharded.  Variables are split into contiguous ranges (bounds chosen so that
+every rank evaluates the same number of factors), a factor lives on the owner of its first variable, and only what cut
+edges need crosses NVLink: the forward-proposal rows of cut factors are written by the evaluating kernel's own TMA bulk
+stores straight into a receive buffer of the target variable's owner (rome_b200_set_proposal_destinations), halo
+particle blocks are pushed once (rome_b200_push_halo; in a solve: after every belief update), and a GPU-side flag
+barrier over peer memory (rome_b200_peer_signal / _wait) closes every step.  After the timed region every rank
+recomputes, from the same seeds, the rows its peers should have delivered and compares them bit for bit
+(`exchange_verified`).
+
+Timing: W warm-up steps, then EXACTLY K steps replayed from one CUDA graph inside one CUDA-event pair on the launch
+stream, bracketed by a barrier + torch.cuda.synchronize(); max over ranks.  L2: the K steps rotate through `sets`
+independent copies of the whole working set (> 2x the 126 MB L2), so no step finds its inputs in L2.
+
+`e2e`: the same step through the public host API with HOST buffers every step: pinned Float64 particles in the
+reference layout -> rome_b200_set_particles (H2D + layout kernel) -> rome_b200_eval_host_async (kernels + D2H of
+residual rows and statistics).  `e2e_compact`: anchored float32 upload (rome_b200_set_particles_anchored) and only the
+statistics downloaded.
+`cpu_baseline` / `--impl reference`: the float64 C restatement (oracle/) of the SAME step (getSample + residual +
+statistics) on all host cores (kind "port": the Julia reference cannot run in this image).
 """
 from __future__ import annotations
 
@@ -42,64 +55,46 @@ METRIC = "factor_particle_residual_evals_per_sec"
 UNIT = "evals/s"
 WORKLOAD = "manhattan_shaped_10k_se2_N100"
 NPOSES, NPART = 10000, 100
+STEP_TEXT = "getSample + residual + per-factor statistics for every factor x particle of every family of the graph"
 
 
 # --------------------------------------------------------------------------------------------------------
+def make_workload(name, G=1):
+    """global workload arrays (rome_b200.workloads) + scaling kind + the dominant family"""
+    import rome_b200 as rb
+    from rome_b200 import workloads as W
+    if name == WORKLOAD:
+        return W.manhattan_arrays(NPOSES * G, seed=2, N=NPART, particle_seed=1), "weak"
+    if name == "beehive_N200":
+        fg = rb.generateGraph_Beehive(10000, N=200)
+        rb.seed_particles(fg, N=200, seed=3)
+        return W.graph_arrays(fg, 200), "strong"
+    if name == "se3_chain_10k":
+        fg = rb.generateGraph_Pose3Chain(10000, loops=1000)
+        rb.seed_particles(fg, N=100, seed=4)
+        return W.graph_arrays(fg, 100), "strong"
+    raise SystemExit(f"unknown workload {name}")
+
+
 def build_workload(copies=1):
-    """arrays of `copies` independent 10k-pose graphs with globally numbered variables"""
+    """round-1 layout of the default workload (kept for tests/tools): dict(poses, ip, iq, mu, cov, pr_ip, pr_mu, pr_cov)"""
     import rome_b200 as rb
-    fg = rb.generateGraph_ManhattanShaped(NPOSES, seed=2, N=NPART)
-    rb.seed_particles(fg, seed=1)
-    idx = {l: v.index for l, v in fg.variables.items()}
-    p2 = [f for f in fg.factors.values() if isinstance(f.fnc, rb.Pose2Pose2)]
-    pr = [f for f in fg.factors.values() if isinstance(f.fnc, rb.PriorPose2)]
-    base = dict(
-        poses=np.stack([v.val for v in fg.variables.values()]),
-        ip=np.array([idx[f.variableOrderSymbols[0]] for f in p2], np.int32),
-        iq=np.array([idx[f.variableOrderSymbols[1]] for f in p2], np.int32),
-        mu=np.stack([f.fnc.Z.mu for f in p2]), cov=np.stack([f.fnc.Z.Sigma for f in p2]),
-        pr_ip=np.array([idx[f.variableOrderSymbols[0]] for f in pr], np.int32),
-        pr_mu=np.stack([f.fnc.Z.mu for f in pr]), pr_cov=np.stack([f.fnc.Z.Sigma for f in pr]))
-    if copies == 1:
-        return base
-    rng = np.random.default_rng(11)
-    V = base["poses"].shape[0]
-    out = {k: [] for k in base}
-    for c in range(copies):
-        out["poses"].append(base["poses"] + (rng.normal(size=base["poses"].shape) * 1e-3 if c else 0.0))
-        for k in ("ip", "iq", "pr_ip"):
-            out[k].append(base[k] + c * V)
-        for k in ("mu", "cov", "pr_mu", "pr_cov"):
-            out[k].append(base[k])
-    return {k: np.concatenate(v) for k, v in out.items()}
+    from rome_b200 import workloads as W
+    w = W.manhattan_arrays(NPOSES * copies, seed=2, N=NPART, particle_seed=1)
+    p2, pr = w["families"][rb.POSE2POSE2], w["families"][rb.PRIORPOSE2]
+    return dict(poses=w["particles"][rb.POSE2], ip=p2["i0"], iq=p2["i1"], mu=p2["a"], cov=p2["b"],
+                pr_ip=pr["i0"], pr_mu=pr["a"], pr_cov=pr["b"])
 
 
-def device_sweeps(sweeps):
-    """wall clock of `sweeps` device-resident sweeps (convolutions + products) on the bench graph"""
+def cholesky_of(fam, f):
+    """[nF][dm][dm] lower Cholesky factors of a family's beliefs (BearingRange: diag(sig_b, sig_r)) and the means"""
     import rome_b200 as rb
-    fg = rb.generateGraph_ManhattanShaped(NPOSES, seed=2, N=NPART)
-    rb.seed_particles(fg, seed=1)
-    dg = rb.DeviceGraph(fg, ctx=rb.Context(0), N=NPART)
-    gs = rb.GibbsSolver(dg)
-    c = dg.ctx
-    gs.sweep(0)
-    c.synchronize()
-    t0 = time.perf_counter()
-    for k in range(sweeps):
-        gs.sweep(1 + k)
-    c.synchronize()
-    dt = time.perf_counter() - t0
-    some = next(p for p in gs._dev if p)
-    ptrs = [p or some for p in gs._dev]
-    t1 = time.perf_counter()
-    for k in range(sweeps):
-        for t in gs.plans:
-            c.product(t, ptrs, seed=k, stream_id=k, gibbs_iters=gs.gibbs_inner, reanchor=True)
-    c.synchronize()
-    dp = time.perf_counter() - t1
-    gs.close()
-    c.close()
-    return dict(ms=1e3 * dt, ms_prod=1e3 * dp, ms_conv=1e3 * (dt - dp))
+    if fam == rb.BEARINGRANGE:
+        a, b = np.asarray(f["a"]), np.asarray(f["b"])
+        Lc = np.zeros((len(a), 2, 2))
+        Lc[:, 0, 0], Lc[:, 1, 1] = a[:, 1], b[:, 1]
+        return np.column_stack([a[:, 0], b[:, 0]]), Lc
+    return np.asarray(f["a"]), np.linalg.cholesky(np.asarray(f["b"]))
 
 
 class ClockSampler:
@@ -157,10 +152,10 @@ class ClockSampler:
 
 
 def ncu_traffic(kernel_substr):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu summary (profiles/), or None"""
+    """DRAM bytes per launch of the dominant kernel from the newest committed ncu summary (profiles/), or None"""
     import csv
     import glob
-    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_pose2pose2_metrics.csv")), reverse=True):
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_metrics.csv")), reverse=True):
         rows = list(csv.reader(open(path)))
         hdr, units = rows[0], rows[1]
         try:
@@ -170,41 +165,49 @@ def ncu_traffic(kernel_substr):
         scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         for r in rows[2:]:
             if kernel_substr in r[1]:
-                return float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]]
-    return None
+                return float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]], os.path.basename(path)
+    return None, None
 
 
-# --------------------------------------------------------------------------------------------------------
-def cpu_sweep_prepare(w, nthreads=0):
-    """bare residual sweep of the oracle port over the workload's Pose2Pose2 + PriorPose2 factors: inputs converted and
-    outputs allocated once, so a call is the C loop (OpenMP over factors) and nothing else.  Returns (sweep, evals)
-    where sweep() -> threads used"""
+# ---- CPU legs (oracle port; the only places bench.py executes oracle/) ------------------------------------------
+FAM_ORACLE = {0: 0, 1: 1, 2: 2, 3: 3, 4: 4}  # rome_b200 family id -> rome_oracle_step family id (same numbering)
+
+
+def cpu_step_prepare(w, max_factors=None, nthreads=0):
+    """the GPU step on the CPU: rome_oracle_step (getSample + residual + statistics) for every family of the workload.
+    Returns (step, evals, sample_text); step(seed) -> threads used.  max_factors bounds the sample (first factors of
+    every family, proportionally)."""
     from oracle import oracle as O
-    rng = np.random.default_rng(5)
-    F, N = len(w["ip"]), w["poses"].shape[1]
-    L = np.linalg.cholesky(w["cov"])
-    meas = w["mu"][:, None, :] + np.einsum("fij,fnj->fni", L, rng.normal(size=(F, N, 3)))
-    pm = w["pr_mu"][:, None, :] + rng.normal(size=(len(w["pr_ip"]), N, 3)) * 0.1
-    lib = O.lib()
-    ip, iq, poses, meas = O._i32(w["ip"]), O._i32(w["iq"]), O._f64(w["poses"]), O._f64(meas)
-    pip, pm = O._i32(w["pr_ip"]), O._f64(pm)
-    res = np.empty((F, N, 3))
-    pres = np.empty((len(pip), N, 3))
+    import rome_b200 as rb
+    O.build()
+    total = sum(len(f["i0"]) for f in w["families"].values())
+    frac = 1.0 if not max_factors or max_factors >= total else max_factors / total
+    calls, evals, parts = [], 0, []
+    for fam, f in w["families"].items():
+        vt0, vt1 = rb.FAMILY[fam][0], rb.FAMILY[fam][1]
+        n = len(f["i0"]) if frac == 1.0 else max(1, int(len(f["i0"]) * frac))
+        mu, Lc = cholesky_of(fam, f)
+        call, _, _ = O.step_prepare(FAM_ORACLE[fam], f["i0"][:n], None if f["i1"] is None else f["i1"][:n],
+                                    w["particles"][vt0], None if vt1 is None else w["particles"][vt1], mu[:n], Lc[:n],
+                                    nthreads)
+        calls.append(call)
+        evals += n * w["N"]
+        parts.append(f"{n} of {len(f['i0'])} family-{fam} factors")
 
-    def sweep():
-        nt = lib.rome_oracle_sweep_pose2pose2(F, N, O._ip(ip), O._ip(iq), O._dp(poses), O._dp(meas), O._dp(res), nthreads)
-        lib.rome_oracle_sweep_priorpose2(len(pip), N, O._ip(pip), O._dp(poses), O._dp(pm), O._dp(pres), nthreads)
+    def step(seed=0):
+        nt = 1
+        for c in calls:
+            nt = c(seed)
         return nt
 
-    sweep()  # warm-up: pages of the outputs touched, threads started
-    return sweep, (F + len(pip)) * N
+    step(0)  # warm-up: output pages touched, threads started
+    return step, evals, " + ".join(parts) + f" x {w['N']} particles"
 
 
-def cpu_sweep_rate(w, seconds=12.0, nthreads=0):
-    sweep, evals = cpu_sweep_prepare(w, nthreads)
+def cpu_rate(step, evals, seconds):
     reps, t0, nt = 0, time.perf_counter(), 1
     while True:
-        nt = sweep()
+        nt = step(reps)
         reps += 1
         dt = time.perf_counter() - t0
         if dt >= seconds:
@@ -212,68 +215,75 @@ def cpu_sweep_rate(w, seconds=12.0, nthreads=0):
     return reps * evals / dt, nt, reps, dt
 
 
-def cpu_reference_shaped(w, nfac=96, nthreads=0):
-    """Nelder-Mead per particle x inflateCycles (IIF-shaped convolution) on the first `nfac` factors"""
+def cpu_bare_sweep_rate(w, seconds=3.0):
+    """round-1's figure, kept as a secondary: the bare Pose2Pose2 residual loop on prepared samples (no sampling, no
+    statistics)"""
     from oracle import oracle as O
-    rng = np.random.default_rng(6)
-    N = w["poses"].shape[1]
-    L = np.linalg.cholesky(w["cov"][:nfac])
-    meas = w["mu"][:nfac, None, :] + np.einsum("fij,fnj->fni", L, rng.normal(size=(nfac, N, 3)))
-    t0 = time.perf_counter()
-    _, nev, nt = O.conv_nm_pose2pose2(w["ip"][:nfac], w["iq"][:nfac], w["poses"], meas, fwd=True, inflate_cycles=3,
-                                      inflation=5.0, seed=1, nthreads=nthreads)
-    dt = time.perf_counter() - t0
-    return dict(residual_evals_per_s=nev / dt, convolved_particles_per_s=nfac * N / dt, residual_calls_per_particle=nev / (nfac * N),
-                cores=nt, sample=f"{nfac} Pose2Pose2 factors x {N} particles, NelderMead x 3 inflation cycles")
+    import rome_b200 as rb
+    f = w["families"].get(rb.POSE2POSE2)
+    if f is None:
+        return None
+    rng = np.random.default_rng(5)
+    F, N = len(f["i0"]), w["N"]
+    mu, Lc = cholesky_of(rb.POSE2POSE2, f)
+    meas = O._f64(mu[:, None, :] + np.einsum("fij,fnj->fni", Lc, rng.normal(size=(F, N, 3))))
+    ip, iq, poses = O._i32(f["i0"]), O._i32(f["i1"]), O._f64(w["particles"][rb.POSE2])
+    res = np.empty((F, N, 3))
+    lib = O.lib()
+    nt = os.cpu_count() or 1
 
-
-def cpu_product_shaped(w, nvars=1500, nthreads=0):
-    """the belief-update half of a sweep on the CPU: the C port of the product of proposal KDEs (oracle/, OpenMP) on the
-    first `nvars` variables of the bench graph, each with the number of proposals the graph gives it"""
-    from oracle import oracle as O
-    rng = np.random.default_rng(8)
-    V, N, _ = w["poses"].shape
-    deg = np.bincount(w["iq"], minlength=V) + np.bincount(w["ip"], minlength=V) + np.bincount(w["pr_ip"], minlength=V)
-    deg = deg[:nvars]
-    off = np.concatenate([[0], np.cumsum(deg)]).astype(np.int32)
-    rows = np.concatenate([w["poses"][v][None] - w["poses"][v, :1][None] + rng.normal(size=(int(deg[v]), N, 3)) * [0.1, 0.1, 0.02]
-                           for v in range(nvars)])
-    t0 = time.perf_counter()
-    _, nt = O.product_sweep_c(off, np.arange(len(rows), dtype=np.int32), rows, wrap_dim=2, iters=2, seed=1, nthreads=nthreads)
-    dt = time.perf_counter() - t0
-    return dict(variables_per_s=nvars / dt, s_per_sweep_extrapolated=V / (nvars / dt), cores=nt,
-                sample=f"{nvars} variables x {N} particles, {deg.mean():.2f} proposals per variable")
+    def sweep(_=0):
+        return lib.rome_oracle_sweep_pose2pose2(F, N, O._ip(ip), O._ip(iq), O._dp(poses), O._dp(meas), O._dp(res), nt)
+    sweep()
+    v, nt, reps, dt = cpu_rate(sweep, F * N, seconds)
+    return {"value": v, "unit": UNIT, "cores": nt, "sample": f"{reps} bare Pose2Pose2 residual sweeps ({F} x {N}) in {dt:.1f} s"}
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU path (oracle port) on this box's host cores"""
+    """--impl reference: the reference's CPU path (oracle port of the same step) on this box's host cores"""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import oracle as O
-    O.build()
-    w = build_workload(1)
-    F, N = len(w["ip"]) + len(w["pr_ip"]), w["poses"].shape[1]
-    step, evals = cpu_sweep_prepare(w)
-    nt = 1
-    for _ in range(args.warmup):
-        step()
+    w, scaling = make_workload(args.workload, args.gpus)
+    nt = os.cpu_count() or 1  # explicit: torch.distributed.run exports OMP_NUM_THREADS=1
+    total = sum(len(f["i0"]) for f in w["families"].values())
+    step, evals, sample = cpu_step_prepare(w, nthreads=nt)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        nt = step()
+    step(1)
+    one = time.perf_counter() - t0
+    budget = 100.0  # seconds for warm-up + timed steps
+    if one * (args.steps + args.warmup) > budget:  # bound the per-step sample so that the run ends within minutes
+        keep = max(256, int(total * budget / (one * (args.steps + args.warmup))))
+        step, evals, sample = cpu_step_prepare(w, max_factors=keep, nthreads=nt)
+    for k in range(args.warmup):
+        step(k)
+    n_timed, used = 0, 1
+    t0 = time.perf_counter()
+    while n_timed < args.steps or time.perf_counter() - t0 < 2.0:  # at least K steps and at least 2 s
+        used = step(100 + n_timed)
+        n_timed += 1
     dt = time.perf_counter() - t0
-    value = args.steps * evals / dt
+    value = n_timed * evals / dt
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / n_timed, "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "poses": NPOSES, "particles": N, "factors": F,
-                       "step": "one bare residual sweep over all factors x particles (no optimiser, no sampling)"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": nt, "kind": "port",
-                             "sample": f"{args.steps} full sweeps of {F} factors x {N} particles"},
+            "config": config_of(args.workload, w, args.gpus, scaling),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "port",
+                             "sample": f"{n_timed} steps of [{sample}] in {dt:.2f} s (Xoshiro256++ / polar-method getSample "
+                                       f"+ residual + statistics, OpenMP over factors)"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
-            "note": "Julia reference cannot run here (no julia, unvendored deps); this is the float64 C restatement"}
+            "note": "Julia reference cannot run here (no julia, unvendored deps); this is the float64 C restatement of the same step"}
     print(json.dumps(line))
+
+
+def config_of(name, w, G, scaling):
+    import rome_b200 as rb
+    fams = {str(fam): len(f["i0"]) for fam, f in w["families"].items()}
+    return {"workload": name, "variables": {str(vt): int(p.shape[0]) for vt, p in w["particles"].items()},
+            "particles": w["N"], "npad": rb.npad(w["N"]), "factors": fams,
+            "evals_per_step": int(sum(fams.values()) * w["N"]), "step": STEP_TEXT,
+            "gpus": G, "scaling": scaling}
 
 
 # --------------------------------------------------------------------------------------------------------
@@ -283,15 +293,12 @@ def main():
     ap.add_argument("--steps", type=int, default=600)
     ap.add_argument("--warmup", type=int, default=60)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--sets", type=int, default=12, help="independent working-set copies rotated through (L2 defeat)")
+    ap.add_argument("--workload", default=WORKLOAD, choices=[WORKLOAD, "beehive_N200", "se3_chain_10k"])
+    ap.add_argument("--sets", type=int, default=0, help="independent working-set copies rotated through (0: enough for > 2x L2)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-overlap", action="store_true", help="do not let consecutive (independent) steps overlap")
-    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
-                    help="N>1: proposals reach the peers by the kernel's own TMA stores (fused) or by an NCCL all-gather")
-    ap.add_argument("--barrier", default="nccl", choices=["flags", "nccl"],
-                    help="fused exchange: rank barrier by a 4-byte NCCL all-reduce (default; validated at 2, 4 and 8 GPUs) or by "
-                         "the GPUs' own flag kernels over NVLink peer memory (flags; validated at 2 GPUs: 31.6 vs 34.1 us/step)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU legs (cpu_baseline, parity check)")
+    ap.add_argument("--barrier", default="flags", choices=["flags", "nccl"],
+                    help="G>1: rank barrier by the GPUs' own flag kernels over NVLink peer memory (default) or a 4-byte NCCL all-reduce")
     ap.add_argument("--e2e-steps", type=int, default=40)
     args = ap.parse_args()
     if args.impl == "reference":
@@ -305,7 +312,7 @@ def main():
     import torch
     import torch.distributed as dist
     import rome_b200 as rb
-    from rome_b200 import sharding
+    from rome_b200 import workloads as W
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -315,115 +322,165 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    G = world
-    w = build_workload(G)
-    F0 = len(w["ip"]) // G  # Pose2Pose2 factors per graph copy == per rank
-    F, N, Np, V = len(w["ip"]), NPART, rb.npad(NPART), w["poses"].shape[0]
-    first = rank * F0
-    multi = G > 1
-    flags = rb.SAMPLE | rb.RESIDUAL | rb.STATS | (rb.PROPOSAL_FWD if multi else 0)
+    G, multi = world, world > 1
+    wg, scaling = make_workload(args.workload, G)       # the GLOBAL graph (every rank builds the same arrays)
+    N, Np = wg["N"], rb.npad(wg["N"])
+    sh = W.sharding_of(wg, G)
+    lv = W.local_view(wg, sh, rank)                     # what this rank holds: owned + halo variables, its factors
+    fam_order = sorted(lv["families"], key=lambda f: -len(lv["families"][f]["i0"]))
+    dom = max(wg["families"], key=lambda f: len(wg["families"][f]["i0"]) * rb.BYTES_PER_EVAL_SAMPLED[f])
+    evals_per_step = sum(len(f["i0"]) for f in wg["families"].values()) * N
+    evals_rank = sum(len(f["i0"]) for f in lv["families"].values()) * N
+    F0 = rb.SAMPLE | rb.RESIDUAL | rb.STATS
+
+    def set_bytes():
+        b = 0
+        for vt, p in lv["particles"].items():
+            b += p.shape[0] * (48 + Np * rb.VAR_DIM[vt] * 4)
+        for fam, f in lv["families"].items():
+            b += len(f["i0"]) * (Np * rb.FAMILY[fam][3] * 4 + rb.FAMILY[fam][4] * 4 + 64)
+        return b
+    S = args.sets or int(min(64, max(12, -(-300e6 // max(set_bytes(), 1)))))
     stream = torch.cuda.Stream()
-    S = args.sets
+
+    # ---- working sets ---------------------------------------------------------------------------------------------
     sets = []
     with torch.cuda.stream(stream):
         for s in range(S):
             c = rb.Context(local)
             c.use_torch_stream()
-            c.set_particles(rb.POSE2, w["poses"] + (1e-4 * s))
-            c.set_factors_pose2pose2(w["ip"], w["iq"], w["mu"], w["cov"])
-            c.set_factors_priorpose2(w["pr_ip"], w["pr_mu"], w["pr_cov"])
-            bufs = dict(res=torch.zeros((F, Np, 3), device="cuda"), stats=torch.zeros((F, 16), device="cuda"))
-            pb = dict(res=torch.zeros((len(w["pr_ip"]), Np, 3), device="cuda"),
-                      stats=torch.zeros((len(w["pr_ip"]), 16), device="cuda"))
-            if multi and args.exchange == "nccl":
-                bufs["prop_fwd"] = torch.zeros((F, Np, 3), device="cuda")
-                pb["prop_fwd"] = torch.zeros((len(w["pr_ip"]), Np, 3), device="cuda")
-            elif multi:  # fused exchange: plain cudaMalloc buffers that the peers map through CUDA IPC
-                bufs["prop_fwd"] = c.malloc_device(F * Np * 3 * 4)
-                pb["prop_fwd"] = c.malloc_device(len(w["pr_ip"]) * Np * 3 * 4)
-            sets.append((c, bufs, pb))
+            for vt, p in lv["particles"].items():
+                q = p + 1e-4 * s
+                n_own = lv["loc"]["own"][vt][1] - lv["loc"]["own"][vt][0]
+                q[n_own:] = 0.0   # halo slots: filled by their owners' rome_b200_push_halo
+                c.set_particles(vt, q)
+            bufs = {}
+            for fam, f in lv["families"].items():
+                W.upload_family(c, fam, f["i0"], f["i1"], f["a"], f["b"])
+                nF, dr, ns, dfwd = len(f["i0"]), rb.FAMILY[fam][3], rb.FAMILY[fam][4], rb.FAMILY[fam][6]
+                bufs[fam] = dict(res=torch.zeros((nF, Np, dr), device="cuda"), stats=torch.zeros((nF, ns), device="cuda"))
+                if multi and dfwd:
+                    bufs[fam]["recv"] = c.malloc_device(max(1, len(f["recv"])) * Np * dfwd * 4)
+            sets.append((c, bufs))
         stream.synchronize()
-        if multi and args.exchange == "fused":
-            mine = [(c.ipc_export(b["prop_fwd"]), c.ipc_export(p["prop_fwd"])) for c, b, p in sets]
-            everyone = [None] * G
-            dist.all_gather_object(everyone, mine)
-            for si, (c, b, p) in enumerate(sets):
-                c.set_peer_proposals(rb.POSE2POSE2, [c.ipc_import(everyone[r][si][0]) for r in range(G) if r != rank])
-                c.set_peer_proposals(rb.PRIORPOSE2, [c.ipc_import(everyone[r][si][1]) for r in range(G) if r != rank])
-            token = torch.zeros(1, device="cuda")
-            if args.barrier == "flags":
-                # GPU-side barrier state: one flag array per rank; peer p owns slot dense(p) = p if p < rank else p - 1
-                c0 = sets[0][0]
-                state = c0.peer_state_alloc()
-                states = [None] * G
-                dist.all_gather_object(states, c0.ipc_export(state))
-                peer_slots = []
-                for p in range(G):
-                    if p != rank:
-                        base = c0.ipc_import(states[p])
-                        peer_slots.append(base + 4 * (rank if rank < p else rank - 1))
-            dist.barrier()
 
-    n_prior = len(w["pr_ip"]) // G
-    evals_per_step_rank = (F0 + n_prior) * N
-    evals_per_step = evals_per_step_rank * G
+    # ---- owner-sharded exchange plumbing: CUDA IPC handles of every receive buffer and particle store --------------
+    state = peer_slots = None
+    dummy_fwd = {}
+    if multi:
+        c0 = sets[0][0]
+        mine = []
+        for c, bufs in sets:
+            mine.append({"recv": {fam: c.ipc_export(b["recv"]) for fam, b in bufs.items() if "recv" in b},
+                         "store": {vt: c.ipc_export(c.particles_device(vt)[0]) for vt in lv["particles"]}})
+        state = c0.peer_state_alloc()
+        everyone = [None] * G
+        dist.all_gather_object(everyone, {"sets": mine, "state": c0.ipc_export(state)})
+        peer_slots = []
+        for p in range(G):
+            if p != rank:
+                peer_slots.append(c0.ipc_import(everyone[p]["state"]) + 4 * (rank if rank < p else rank - 1))
+        for si, (c, bufs) in enumerate(sets):
+            recv_ptr = {p: {fam: c.ipc_import(h) for fam, h in everyone[p]["sets"][si]["recv"].items()}
+                        for p in range(G) if p != rank}
+            store_ptr = {p: {vt: c.ipc_import(h) for vt, h in everyone[p]["sets"][si]["store"].items()}
+                         for p in range(G) if p != rank}
+            for fam, f in lv["families"].items():
+                dfwd = rb.FAMILY[fam][6]
+                if not dfwd or f["n_cut"] == 0:
+                    continue
+                rowb = Np * dfwd * 4
+                ptrs = [0] * f["n_interior"] + [recv_ptr[int(d)][fam] + int(r) * rowb
+                                                for d, r in zip(f["dst_rank"], f["dst_row"])]
+                c.set_proposal_destinations(fam, 0, ptrs)
+                if fam not in dummy_fwd:  # default rows of prop_fwd are never written for the cut range; one shared buffer
+                    dummy_fwd[fam] = torch.zeros((len(f["i0"]), Np, dfwd), device="cuda")
+            for vt, pushes in lv["loc"]["push"].items():
+                src, dst = [], []
+                bb = c.particles_device(vt)[1]
+                for reader, local_vars, slots in pushes:
+                    src += [int(v) for v in local_vars]
+                    dst += [store_ptr[reader][vt] + int(sl) * bb for sl in slots]
+                if src:
+                    c.set_halo_plan(vt, src, dst)
+        dist.barrier()
+        token = torch.zeros(1, device="cuda")
 
-    side = torch.cuda.Stream()
-    pflags = rb.RESIDUAL | rb.STATS
+    def rank_barrier(c):
+        """stream-ordered barrier between the ranks (after everything enqueued so far on the launch stream)"""
+        if args.barrier == "flags":
+            c.peer_signal(state, peer_slots)
+            c.peer_wait(state, G - 1)
+        else:
+            dist.all_reduce(token)
 
-    def step(k, indep):
-        """one pass of the hot path over the graph.  The two family kernels have no mutual dependency: PriorPose2 runs on a
-        side stream (a parallel branch of the captured graph).  With `indep` the Pose2Pose2 launch carries
-        ROME_B200_INDEPENDENT: consecutive steps work on different working-set copies, so a step may start on SMs the
-        previous step has already vacated (programmatic dependent launch).  N>1: the exchange of step k (NCCL
-        all-gather, or -- fused -- only the barrier that follows the kernels' own peer stores) is issued on the side
-        stream after both kernels of the step, and overlaps the kernels of step k+1."""
-        c, bufs, pb = sets[k % S]
-        c.set_stream(side.cuda_stream)
-        c.eval(rb.PRIORPOSE2, flags, seed=7, stream_id=k, first=rank * n_prior, count=n_prior, **pb)
-        c.set_stream(stream.cuda_stream)
-        c.eval(rb.POSE2POSE2, flags | (rb.INDEPENDENT if indep else 0), seed=7, stream_id=k, first=first, count=F0,
-               **bufs)
-        if multi:
-            ev = torch.cuda.Event()
-            ev.record(stream)
-            side.wait_event(ev)
-            with torch.cuda.stream(side):
-                if args.exchange == "nccl":  # the one exchange of the path: every rank's proposals to every rank
-                    sharding.allgather_rows(bufs["prop_fwd"], F)
-                    sharding.allgather_rows(pb["prop_fwd"], len(w["pr_ip"]))
-                elif args.barrier == "nccl":  # the kernels already stored their rows into every peer: a barrier is left
-                    dist.all_reduce(token)
-                else:  # ... carried by two one-warp kernels over NVLink peer memory (they co-reside with the next step)
-                    c.set_stream(side.cuda_stream)
-                    c.peer_signal(state, peer_slots)
-                    c.peer_wait(state, G - 1)
-                    c.set_stream(stream.cuda_stream)
-
-    def kernel_only(k, indep):
-        c, bufs, _ = sets[k % S]
-        c.eval(rb.POSE2POSE2, flags | (rb.INDEPENDENT if indep else 0), seed=7, stream_id=k, first=first, count=F0,
-               **bufs)
-
-    def kernel_only_supplied(k, indep):
-        c, bufs, _ = sets[k % S]
-        c.eval(rb.POSE2POSE2, pflags | (rb.INDEPENDENT if indep else 0), first=first, count=F0, meas=meas_sets[k % S],
-               res=bufs["res"], stats=bufs["stats"])
-
-    def capture(fn, indep):
-        gr = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(gr, stream=stream):
-            for c, _, _ in sets:
+    halo_checked = 0
+    if multi:
+        with torch.cuda.stream(stream):
+            for c, _ in sets:
                 c.use_torch_stream()
-            side.wait_stream(stream)  # fork the side branch
+                for vt in lv["particles"]:
+                    c.push_halo(vt)
+            rank_barrier(sets[0][0])
+            stream.synchronize()
+        dist.barrier()
+        # the halo blocks that arrived are, byte for byte, the blocks their owners hold
+        halo_ok = True
+        with torch.cuda.stream(stream):
+            for si in (0, S - 1):
+                c = sets[si][0]
+                for vt, p in wg["particles"].items():
+                    hal = lv["loc"]["halo"][vt]
+                    if len(hal) == 0:
+                        continue
+                    chk = rb.Context(local)
+                    chk.use_torch_stream()
+                    chk.set_particles(vt, p[hal] + 1e-4 * si)
+                    ptr, bb, _, nv, _, _ = c.particles_device(vt)
+                    n_own = lv["loc"]["own"][vt][1] - lv["loc"]["own"][vt][0]
+                    got = np.empty(len(hal) * bb, np.uint8)
+                    want = np.empty(len(hal) * bb, np.uint8)
+                    c.memcpy_d2h(got, ptr + n_own * bb)
+                    chk.memcpy_d2h(want, chk.particles_device(vt)[0])
+                    halo_ok = halo_ok and bool(np.array_equal(got, want))
+                    halo_checked += len(hal)
+                    chk.close()
+
+    # ---- the step ---------------------------------------------------------------------------------------------------
+    def step(k, fams=None, barrier=True, indep_all=False):
+        c, bufs = sets[k % S]
+        first = True
+        for fam in (fams or fam_order):
+            f = lv["families"][fam]
+            b = bufs[fam]
+            dfwd = rb.FAMILY[fam][6]
+            n_int = f["n_interior"] + (0 if (multi and dfwd) else f["n_cut"])  # families without a forward proposal: all local
+            n_cut = len(f["i0"]) - n_int
+            if n_int:
+                c.eval(fam, F0 | (0 if (first and not indep_all) else rb.INDEPENDENT), seed=7, stream_id=k, first=0,
+                       count=n_int, res=b["res"], stats=b["stats"])
+                first = False
+            if n_cut:  # cut factors: the forward proposal rows go straight to the owners of their target variables
+                c.eval(fam, F0 | rb.PROPOSAL_FWD | (0 if (first and not indep_all) else rb.INDEPENDENT), seed=7,
+                       stream_id=k, first=n_int, count=n_cut, res=b["res"], stats=b["stats"], prop_fwd=dummy_fwd[fam])
+                first = False
+        if multi and barrier:
+            rank_barrier(c)
+
+    def capture(fn, **kw):
+        gr = torch.cuda.CUDAGraph()
+        before = sum(c.launch_count for c, _ in sets)
+        with torch.cuda.graph(gr, stream=stream):
+            for c, _ in sets:
+                c.use_torch_stream()
             for k in range(args.steps):
-                fn(args.warmup + k, indep)
-            stream.wait_stream(side)  # join
-        for c, _, _ in sets:
+                fn(args.warmup + k, **kw)
+        launches = sum(c.launch_count for c, _ in sets) - before
+        for c, _ in sets:
             c.use_torch_stream()
         gr.replay()  # untimed replay: graph upload + warm instruction caches
         stream.synchronize()
-        return gr
+        return gr, launches
 
     def timed(gr, sample_clocks=False):
         if multi:
@@ -443,20 +500,24 @@ def main():
         torch.cuda.synchronize()
         return e0.elapsed_time(e1)
 
+    def allmax(x):
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        if multi:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     clocks = ClockSampler(local)
-    overlap = not args.no_overlap
     with torch.cuda.stream(stream):
-        side.wait_stream(stream)
+        for c, _ in sets:
+            c.use_torch_stream()
         for k in range(args.warmup):
-            step(k, False)
-        stream.wait_stream(side)
+            step(k)
         stream.synchronize()
-        g = capture(step, overlap)
+        g, launches_per_replay = capture(step)
         ms = timed(g, sample_clocks=True)
         window = "timed"
         # timed region too short to sample the clocks: keep sampling under identical replays.  Whether and how often is
-        # decided COLLECTIVELY (same replay count on every rank): every replay carries the ranks' barrier, so ranks that
-        # replayed different numbers of times would leave each other waiting
+        # decided COLLECTIVELY (every replay carries the ranks' barrier: same replay count on every rank)
         need = torch.tensor([1.0 if len(clocks.samples) < 5 else 0.0, ms], device="cuda", dtype=torch.float64)
         if multi:
             dist.all_reduce(need, op=dist.ReduceOp.MAX)
@@ -468,71 +529,164 @@ def main():
                 stream.synchronize()
             clocks.stop()
             window = "timed+identical replays"
-        ms_serial = timed(capture(step, False)) if overlap else ms
-        # dominant kernel alone (Pose2Pose2 fused kernel): live CUDA-event timing over K launches
-        gk = capture(kernel_only, overlap)
-        kms = timed(gk) / args.steps
-        kms_serial = timed(capture(kernel_only, False)) / args.steps if overlap else kms
-        # same kernel with the measurement supplied from HBM (48 B/eval)
-        meas_sets = [torch.randn((F, Np, 3), device="cuda") * 0.05 for _ in range(S)]
-        gp = capture(kernel_only_supplied, overlap)
-        pms = timed(gp) / args.steps
-        pms_serial = timed(capture(kernel_only_supplied, False)) / args.steps if overlap else pms
-        del meas_sets
-
-    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-    if multi:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    ms = allmax(ms)
     value = evals_per_step * args.steps / (ms * 1e-3)
 
+    # ---- exchange verification (untimed): recompute what every peer should have delivered ---------------------------
+    verify = None
+    if multi:
+        k_last = args.warmup + args.steps - 1
+        si = k_last % S
+        c, bufs = sets[si]
+        ok, rows_checked, worst = True, 0, 0.0
+        with torch.cuda.stream(stream):
+            for fam, f in lv["families"].items():
+                dfwd = rb.FAMILY[fam][6]
+                if not dfwd or len(f["recv"]) == 0:
+                    continue
+                got = np.empty((len(f["recv"]), Np, dfwd), np.float32)
+                c.memcpy_d2h(got, bufs[fam]["recv"])
+                pos = 0
+                F = sh.families[fam]
+                for src in range(G):
+                    if src == rank:
+                        continue
+                    rows = f["recv"][F["rank"][f["recv"]] == src]
+                    if len(rows) == 0:
+                        continue
+                    lsrc = W.local_view(wg, sh, src, fill_halo=True)   # the source rank's local problem, rebuilt here
+                    chk = rb.Context(local)
+                    chk.use_torch_stream()
+                    for vt, p in lsrc["particles"].items():
+                        q = p.copy()
+                        n_own = lsrc["loc"]["own"][vt][1] - lsrc["loc"]["own"][vt][0]
+                        q[:n_own] += 1e-4 * si
+                        # halo slots of the source hold what their owners pushed: the owners' own values of set si
+                        q[n_own:] += 1e-4 * si
+                        chk.set_particles(vt, q)
+                    fs = lsrc["families"][fam]
+                    W.upload_family(chk, fam, fs["i0"], fs["i1"], fs["a"], fs["b"])
+                    nFs = len(fs["i0"])
+                    out = dict(res=torch.zeros((nFs, Np, rb.FAMILY[fam][3]), device="cuda"),
+                               stats=torch.zeros((nFs, rb.FAMILY[fam][4]), device="cuda"),
+                               prop_fwd=torch.zeros((nFs, Np, dfwd), device="cuda"))
+                    chk.eval(fam, F0 | rb.PROPOSAL_FWD, seed=7, stream_id=k_last, first=fs["n_interior"], count=fs["n_cut"],
+                             **out)
+                    stream.synchronize()
+                    mine_rows = fs["n_interior"] + np.nonzero(fs["dst_rank"] == rank)[0]
+                    want = out["prop_fwd"][torch.as_tensor(mine_rows, device="cuda")].cpu().numpy()
+                    # rows arrive in (source rank, global id) order; the source's cut factors to one destination are
+                    # sorted by global id too
+                    seg = got[pos:pos + len(rows)]
+                    pos += len(rows)
+                    same = np.array_equal(seg[:, :N], want[:, :N])
+                    ok = ok and same and len(want) == len(rows)
+                    if not same and seg.shape == want.shape:
+                        worst = max(worst, float(np.nanmax(np.abs(seg[:, :N] - want[:, :N]))))
+                    rows_checked += len(rows)
+                    chk.close()
+        gave_up = bool(sets[0][0].peer_gave_up(state)) if args.barrier == "flags" else False
+        flag = torch.tensor([1.0 if (ok and halo_ok and not gave_up) else 0.0, float(rows_checked), worst, float(halo_checked)],
+                            device="cuda", dtype=torch.float64)
+        mn = flag.clone()
+        dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+        sm = flag.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        mx = flag.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        verify = {"exchange_verified": bool(mn[0].item() > 0.5), "rows_checked_all_ranks": int(sm[1].item()),
+                  "max_abs_diff": float(mx[2].item()), "halo_blocks_checked_all_ranks": int(sm[3].item()),
+                  "how": "after the timed replay every rank rebuilds each peer's local problem from the seeds, recomputes the "
+                         "forward-proposal rows that peer's cut factors address to it (same seed / stream id as the last timed "
+                         "step on that working set) and compares them bit for bit with its receive buffer; halo particle "
+                         "blocks are compared byte for byte with a fresh pack of their owners' particles"}
+
+    # ---- the dominant kernel alone (roofline): K dependent launches, live CUDA-event timing ------------------------
+    def kernel_only(k, indep=False):
+        step(k, fams=[dom], barrier=False, indep_all=indep)
+
+    with torch.cuda.stream(stream):
+        gk, _ = capture(kernel_only)
+        kms = allmax(timed(gk)) / args.steps
+        gko, _ = capture(kernel_only, indep=True)
+        kms_over = allmax(timed(gko)) / args.steps
+        pms = None
+        if not multi and dom == rb.POSE2POSE2:  # same kernel with the measurement supplied from HBM (48 B/eval)
+            nFd = len(lv["families"][dom]["i0"])
+            meas_sets = [torch.randn((nFd, Np, 3), device="cuda") * 0.05 for _ in range(S)]
+
+            def kernel_supplied(k):
+                c, bufs = sets[k % S]
+                c.eval(dom, rb.RESIDUAL | rb.STATS, meas=meas_sets[k % S], res=bufs[dom]["res"], stats=bufs[dom]["stats"])
+            gp, _ = capture(kernel_supplied)
+            pms = timed(gp) / args.steps
+            del meas_sets, gp
+
     # ---- e2e through the host API (per rank, host buffers, copies inside the timed region) ----
-    # Two contexts on their own streams alternate, so the H2D upload of step k+1 overlaps the D2H download of
-    # step k (PCIe is full duplex); every step still uploads all particles and downloads all residuals + stats.
-    eflags = rb.SAMPLE | rb.RESIDUAL | rb.STATS
+    # Two contexts on their own streams alternate, so the H2D upload of step k+1 overlaps the D2H download of step k
+    # (PCIe is full duplex); every step uploads this rank's particles and downloads its residual rows + statistics.
     lanes = []
+    host_parts = W.local_view(wg, sh, rank, fill_halo=True)["particles"]  # the host holds its halo variables' values too
     for j in range(2):
         c = sets[j][0]
         c.set_stream(None)
-        lanes.append(dict(
-            c=c, poses=torch.from_numpy(w["poses"] + 1e-4 * j).pin_memory(),
-            res=torch.zeros((F, Np, 3), dtype=torch.float32).pin_memory(),
-            stats=torch.zeros((F, 16), dtype=torch.float32).pin_memory(),
-            pres=torch.zeros((len(w["pr_ip"]), Np, 3), dtype=torch.float32).pin_memory(),
-            pstats=torch.zeros((len(w["pr_ip"]), 16), dtype=torch.float32).pin_memory()))
+        ln = dict(c=c, parts={vt: torch.from_numpy(p + 1e-4 * j).pin_memory() for vt, p in host_parts.items()}, out={})
+        ln["anch"] = {vt: torch.from_numpy(np.ascontiguousarray(p[:, 0, :])).pin_memory() for vt, p in host_parts.items()}
+        ln["offs"] = {vt: torch.from_numpy((p - p[:, :1, :]).astype(np.float32)).pin_memory() for vt, p in host_parts.items()}
+        for fam, f in lv["families"].items():
+            nF = max(1, len(f["i0"]))
+            ln["out"][fam] = dict(res=torch.zeros((nF, Np, rb.FAMILY[fam][3]), dtype=torch.float32).pin_memory(),
+                                  stats=torch.zeros((nF, rb.FAMILY[fam][4]), dtype=torch.float32).pin_memory())
+        lanes.append(ln)
 
-    def e2e_step(k):
+    def e2e_step(k, compact=False):
         ln = lanes[k % 2]
         c = ln["c"]
         c.synchronize()  # results of this lane's previous step (two steps ago) are complete and readable
-        c.set_particles(rb.POSE2, ln["poses"])
-        c.eval_host(rb.POSE2POSE2, eflags, seed=9, stream_id=k, first=first, count=F0, res=ln["res"],
-                    stats=ln["stats"], sync=False)
-        c.eval_host(rb.PRIORPOSE2, eflags, seed=9, stream_id=k, first=rank * n_prior, count=n_prior, res=ln["pres"],
-                    stats=ln["pstats"], sync=False)
+        for vt in ln["parts"]:
+            if compact:
+                c.set_particles_anchored(vt, ln["anch"][vt], ln["offs"][vt])
+            else:
+                c.set_particles(vt, ln["parts"][vt])
+        for fam in fam_order:
+            o = ln["out"][fam]
+            if len(lv["families"][fam]["i0"]) == 0:
+                continue
+            if compact:
+                c.eval_host(fam, rb.SAMPLE | rb.STATS, seed=9, stream_id=k, stats=o["stats"], sync=False)
+            else:
+                c.eval_host(fam, F0, seed=9, stream_id=k, res=o["res"], stats=o["stats"], sync=False)
 
-    for k in range(4):
-        e2e_step(k)
-    for ln in lanes:
-        ln["c"].synchronize()
+    def e2e_run(compact):
+        for k in range(4):
+            e2e_step(k, compact)
+        for ln in lanes:
+            ln["c"].synchronize()
+        if multi:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for k in range(args.e2e_steps):
+            e2e_step(k, compact)
+        for ln in lanes:
+            ln["c"].synchronize()
+        torch.cuda.synchronize()
+        return allmax(time.perf_counter() - t0)
+
+    # destinations off for the host-API legs (no exchange there: the device-resident exchange is not a host-buffer path)
     if multi:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for k in range(args.e2e_steps):
-        e2e_step(k)
-    for ln in lanes:
-        ln["c"].synchronize()
-    torch.cuda.synchronize()
-    edt = time.perf_counter() - t0
-    assert float(lanes[0]["stats"].abs().sum()) > 0 and float(lanes[1]["res"].abs().sum()) > 0
-    et = torch.tensor([edt], device="cuda", dtype=torch.float64)
-    if multi:
-        dist.all_reduce(et, op=dist.ReduceOp.MAX)
-    edt = float(et.item())
-    e2e_value = evals_per_step * args.e2e_steps / edt
-    h2d = V * N * 3 * 8
-    d2h = (F0 * 3 * Np + F0 * 16 + n_prior * 3 * Np + n_prior * 16) * 4
+        for c, _ in sets[:2]:
+            for fam in lv["families"]:
+                if rb.FAMILY[fam][6]:
+                    c.set_proposal_destinations(fam, 0, [])
+    edt = e2e_run(False)
+    assert all(float(ln["out"][dom]["stats"].abs().sum()) > 0 and float(ln["out"][dom]["res"].abs().sum()) > 0 for ln in lanes)
+    edt_c = e2e_run(True)
+    assert all(float(ln["out"][dom]["stats"].abs().sum()) > 0 for ln in lanes)
+    h2d = sum(p.shape[0] * N * rb.VAR_DIM[vt] * 8 for vt, p in lv["particles"].items())
+    d2h = sum(len(f["i0"]) * (Np * rb.FAMILY[fam][3] + rb.FAMILY[fam][4]) * 4 for fam, f in lv["families"].items())
+    h2d_c = sum(p.shape[0] * (N * 4 + 8) * rb.VAR_DIM[vt] for vt, p in lv["particles"].items())
+    d2h_c = sum(len(f["i0"]) * rb.FAMILY[fam][4] * 4 for fam, f in lv["families"].items())
 
     if rank == 0:
         peaks = {}
@@ -541,90 +695,121 @@ def main():
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        traffic = ncu_traffic("FamPose2Pose2, 25, 1, 8")
-        bpe = rb.BYTES_PER_EVAL_SAMPLED[rb.POSE2POSE2] + (12 if multi else 0)
-        ach = F0 * N * bpe / (kms * 1e-3) / 1e9
-        pach = F0 * N * rb.BYTES_PER_EVAL[rb.POSE2POSE2] / (pms * 1e-3) / 1e9
+        names = {rb.POSE2POSE2: "FamPose2Pose2", rb.BEARINGRANGE: "FamBearingRange", rb.POSE3POSE3: "FamPose3Pose3"}
+        traffic, traffic_src = ncu_traffic(names.get(dom, "eval_kernel"))
+        bpe = rb.BYTES_PER_EVAL_SAMPLED[dom]
+        fd = lv["families"][dom]
+        n_dom = fd["n_interior"] + (fd["n_cut"] if not (multi and rb.FAMILY[dom][6]) else 0)
+        n_dom_cut = len(fd["i0"]) - n_dom
+        alg_bytes = (n_dom * bpe + n_dom_cut * (bpe + 4 * rb.FAMILY[dom][6])) * N
+        ach = alg_bytes / (kms * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": G, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "poses_per_gpu": NPOSES, "particles": N, "npad": Np,
-                       "factors_per_gpu": F0 + n_prior, "evals_per_step": evals_per_step,
-                       "step": "getSample (in-kernel Philox) + residual + per-factor stats for every factor x particle"
-                               + (("; + closed-form proposals, stored by the kernel's own TMA bulk stores into every peer GPU over NVLink "
-                                  "(fused all-gather) + " + ("a GPU-side flag barrier over peer memory (rome_b200_peer_signal/wait)"
-                                                             if args.barrier == "flags" else "a 4-byte NCCL all-reduce as barrier")
-                                  if args.exchange == "fused" else
-                                  "; + closed-form proposals and one NCCL all-gather of them") if multi else ""),
-                       "storage": "anchored float32 (Float64 anchor + float32 offset)",
-                       "l2": f"{S} rotating working-set copies (> 2x L2); K steps replayed from one CUDA graph",
-                       "overlap": ("consecutive steps are independent (different working-set copies) and launched with "
-                                   "ROME_B200_INDEPENDENT (programmatic dependent launch): a step may start on SMs the "
-                                   "previous one vacated; serialized figures alongside") if overlap else "none",
-                       "parallelism": f"factor-list sharding x{G}" if multi else "single GPU"},
-            "roofline": {"bound": "hbm", "kernel": "eval_kernel<FamPose2Pose2, sample=true>", "achieved": ach, "peak": peak,
-                         "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu "
-                                         "--set full capture (profiles/); below the algorithmic bytes because neighbouring "
-                                         "factors share particle blocks in L2 and written rows are still L2-resident when "
-                                         "the replayed launch ends",
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+            "dtype": "f64 per factor / f32 per particle arithmetic on anchored float32 I/O (Float64 anchor + float32 offset)",
+            "data": "synthetic",
+            "config": dict(config_of(args.workload, wg, G, scaling),
+                           sets=S, l2=f"{S} rotating working-set copies (> 2x L2); K steps replayed from one CUDA graph",
+                           steps_are="dependent (each step's first launch waits for the previous step, like Gibbs sweeps); "
+                                     "only the family kernels WITHIN a step overlap",
+                           factors_this_rank={str(f): len(v["i0"]) for f, v in lv["families"].items()},
+                           parallelism=(f"owner-sharded x{G}: variables in contiguous ranges, factors on the owner of their "
+                                        f"first variable; rank 0 holds {sum(v['n_cut'] for v in lv['families'].values())} cut "
+                                        f"factors; exchange = cut factors' proposal rows by the kernel's own TMA stores into "
+                                        f"the owners' receive buffers + {args.barrier} barrier per step") if multi else "single GPU"),
+            "roofline": {"bound": "hbm", "kernel": f"eval_kernel<{names.get(dom, dom)}, sample=true>", "achieved": ach,
+                         "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                         "traffic_note": f"dram__bytes_read.sum + dram__bytes_write.sum per launch from profiles/{traffic_src}; "
+                                         "below the algorithmic bytes: neighbouring factors share particle blocks in L2 and "
+                                         "written rows are still L2-resident when the launch ends",
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
-                         "bytes_per_eval": bpe, "evals_per_launch": F0 * N, "us_per_launch": kms * 1e3,
-                         "us_per_launch_serialized": kms_serial * 1e3,
-                         "frac_serialized": F0 * N * bpe / (kms_serial * 1e-3) / 1e9 / peak},
-            "roofline_supplied_meas": {"kernel": "eval_kernel<FamPose2Pose2, sample=false>", "achieved": pach, "peak": peak,
-                                       "unit": "GB/s", "frac": pach / peak, "bytes_per_eval": rb.BYTES_PER_EVAL[rb.POSE2POSE2],
-                                       "us_per_launch": pms * 1e3, "evals_per_s": F0 * N / (pms * 1e-3),
-                                       "us_per_launch_serialized": pms_serial * 1e3,
-                                       "frac_serialized": F0 * N * rb.BYTES_PER_EVAL[rb.POSE2POSE2] / (pms_serial * 1e-3) / 1e9 / peak},
-            "ms_per_step_serialized": ms_serial / args.steps,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": 1e3 * edt / args.e2e_steps, "steps": args.e2e_steps,
-                    "api": "rome_b200_set_particles(pinned host f64) + rome_b200_eval_host_async(pinned host f32 outputs), two contexts alternating so upload and download overlap"},
-            "gpu_launches": (2 + (2 if multi and args.exchange == "fused" and args.barrier == "flags" else 0)) * args.steps,
+                         "bytes_per_eval": bpe, "evals_per_launch": len(fd["i0"]) * N if not multi else (n_dom + n_dom_cut) * N,
+                         "us_per_launch": kms * 1e3, "launches": "dependent (serialized): every launch waits for its predecessor",
+                         "us_per_launch_overlapped": kms_over * 1e3, "frac_overlapped": alg_bytes / (kms_over * 1e-3) / 1e9 / peak},
+            "e2e": {"value": evals_per_step * args.e2e_steps / edt, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * edt / args.e2e_steps, "steps": args.e2e_steps,
+                    "api": "rome_b200_set_particles(pinned host f64, reference layout) + rome_b200_eval_host_async(pinned host "
+                           "f32 residual rows + statistics), two contexts alternating so upload and download overlap"
+                           + ("; bytes are per rank" if multi else "")},
+            "e2e_compact": {"value": evals_per_step * args.e2e_steps / edt_c, "unit": UNIT, "h2d_bytes_per_step": h2d_c,
+                            "d2h_bytes_per_step": d2h_c, "ms_per_step": 1e3 * edt_c / args.e2e_steps,
+                            "api": "rome_b200_set_particles_anchored(f64 anchors + f32 offsets) + rome_b200_eval_host_async("
+                                   "SAMPLE|STATS): same evaluations, only the per-factor statistics come back"},
+            "gpu_launches": launches_per_replay,
             "clocks": clocks.summary(window),
         }
-        if not args.no_cpu and G == 1:
-            from oracle import oracle as O
-            O.build()
-            v, nt, reps, dt = cpu_sweep_rate(w, args.cpu_seconds)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": nt, "kind": "port",
-                                    "sample": f"{reps} full residual sweeps ({F0 + n_prior} factors x {N} particles) in {dt:.1f} s"}
-            # secondary comparison (solveTree!-shaped): never allowed to take the headline line down with it
+        if pms is not None:
+            pach = len(fd["i0"]) * N * rb.BYTES_PER_EVAL[dom] / (pms * 1e-3) / 1e9
+            line["roofline_supplied_meas"] = {"kernel": f"eval_kernel<{names.get(dom, dom)}, sample=false>", "achieved": pach,
+                                              "peak": peak, "unit": "GB/s", "frac": pach / peak,
+                                              "bytes_per_eval": rb.BYTES_PER_EVAL[dom], "us_per_launch": pms * 1e3,
+                                              "launches": "dependent (serialized)"}
+        if verify:
+            line.update(verify)
+        if not args.no_cpu:
             try:
-                line["cpu_reference_shaped"] = cpu_reference_shaped(w)
-                cps = line["cpu_reference_shaped"]["convolved_particles_per_s"]
-                n_conv = 3 * (2 * F0 + n_prior) * N  # convolved particles in the 3 sweeps
-                sw = device_sweeps(3)
-                cpp = cpu_product_shaped(w)
-                line["cpu_product_shaped"] = cpp
-                line["solve_shaped"] = {
-                    "definition": "gibbsIters=3 device-resident sweeps over the whole graph, N=100: every factor convolves forward and "
-                                  "backward (fused getSample + closed-form roots), then every variable takes the product of its "
-                                  "proposal KDEs on the GPU (rome_b200_product) -- particles never leave the device; measured wall "
-                                  "clock around the 3 sweeps.  CPU (all host cores): Nelder-Mead per particle x 3 inflation cycles "
-                                  "(IIF-shaped) for the convolutions + the C port of the same product sampler, both extrapolated "
-                                  "from measured sample rates; Bayes tree excluded on both sides",
-                    "convolved_particles": n_conv, "gpu_ms": sw["ms"], "gpu_ms_convolutions": sw["ms_conv"],
-                    "gpu_ms_products": sw["ms_prod"], "cpu_s_convolutions_extrapolated": n_conv / cps,
-                    "cpu_s_products_extrapolated": 3 * cpp["s_per_sweep_extrapolated"],
-                    "cpu_s_extrapolated": n_conv / cps + 3 * cpp["s_per_sweep_extrapolated"],
-                    "speedup": (n_conv / cps + 3 * cpp["s_per_sweep_extrapolated"]) / (sw["ms"] * 1e-3)}
+                line["parity"] = parity_check(rb, sets[2 % S][0], lv, wg, sh, rank, dom, N)
             except Exception as e:  # noqa: BLE001
-                line["solve_shaped"] = {"error": f"{type(e).__name__}: {e}"}
+                line["parity"] = {"error": f"{type(e).__name__}: {e}"}
+        if not args.no_cpu and G == 1:
+            stepc, evc, sample = cpu_step_prepare(wg, nthreads=os.cpu_count() or 1)
+            v, nt, reps, dt = cpu_rate(stepc, evc, args.cpu_seconds)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": nt, "kind": "port",
+                                    "sample": f"{reps} steps of [{sample}] in {dt:.1f} s (the same step: getSample + residual + "
+                                              f"statistics; float64 C port of the reference arithmetic, OpenMP)"}
+            try:
+                line["cpu_bare_residual_sweep"] = cpu_bare_sweep_rate(wg)
+            except Exception as e:  # noqa: BLE001
+                line["cpu_bare_residual_sweep"] = {"error": f"{type(e).__name__}: {e}"}
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
     if multi:
-        # CUDA graphs that captured NCCL work must die before the communicator; then leave without the
-        # (occasionally hanging) communicator teardown -- every rank has finished its work at the barrier.
-        del g, gk, gp
+        # CUDA graphs must die before the process group; then leave without the (occasionally hanging) communicator
+        # teardown -- every rank has finished its work at the barrier.
+        del g, gk, gko
         torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()
         sys.stdout.flush()
         os._exit(0)
+
+
+def parity_check(rb, c, lv, wg, sh, rank, dom, N, nfac=256):
+    """in-run parity of a sampled subset (oracle as the CHECKER, untimed): the dominant family's first `nfac` local
+    factors, fused getSample with the samples written back, residuals against the float64 oracle on the caller's
+    original Float64 particles: |gpu - ref| <= 1e-5 max(|ref|, 0.1)"""
+    from oracle import oracle as O
+    from rome_b200 import workloads as W
+    full = W.local_view(wg, sh, rank, fill_halo=True)
+    c.set_stream(None)
+    for vt, p in full["particles"].items():
+        c.set_particles(vt, p)
+    f = full["families"][dom]
+    m = min(nfac, len(f["i0"]))
+    fl = rb.SAMPLE | rb.WRITE_MEAS | rb.RESIDUAL
+    out = c.alloc_host_outputs(dom, fl)
+    c.set_proposal_destinations(dom, 0, []) if rb.FAMILY[dom][6] else None
+    c.eval_host(dom, fl, seed=11, stream_id=3, first=0, count=m, **out)
+    mu, _ = cholesky_of(dom, f)
+    meas = rb.offsets_to_meas(out["meas_out"][:m], mu[:m], N)
+    res = rb.rows_to_particle_major(out["res"][:m], N)
+    vt0, vt1 = rb.FAMILY[dom][0], rb.FAMILY[dom][1]
+    P0 = full["particles"][vt0]
+    if dom == rb.POSE2POSE2:
+        ref, ang = O.sweep_pose2pose2(f["i0"][:m], f["i1"][:m], P0, meas), (2,)
+    elif dom == rb.BEARINGRANGE:
+        ref, ang = O.sweep_bearingrange(f["i0"][:m], f["i1"][:m], P0, full["particles"][vt1], meas), (0,)
+    elif dom == rb.POSE3POSE3:
+        ref, ang = O.sweep_pose3pose3(f["i0"][:m], f["i1"][:m], P0, meas), ()
+    else:
+        return {"skipped": f"no oracle sweep wired for family {dom}"}
+    d = res - ref
+    for a in ang:
+        d[..., a] = O.np_wrap(d[..., a])
+    rel = float((np.abs(d) / np.maximum(np.abs(ref), 0.1)).max())
+    return {"checked_evals": int(m * N), "family": int(dom), "max_abs_err": float(np.abs(d).max()),
+            "max_rel_err_floor_0.1": rel, "ok": bool(rel < 1e-5), "checker": "oracle (float64 C port), original Float64 inputs"}
 
 
 if __name__ == "__main__":

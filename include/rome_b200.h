@@ -164,6 +164,11 @@ ROME_B200_API int rome_b200_plan_query(int family, uint32_t flags, int N, int* w
  * anchor of a variable = its first particle.  The variable types a factor family touches must
  * hold the same N when that family is evaluated (checked by rome_b200_eval). */
 ROME_B200_API int rome_b200_set_particles(rome_b200_ctx* ctx, int vartype, int nvars, int N, const double* coords_host);
+/* Same in the anchored form the device keeps: Float64 anchors [nvars][d] + float32 offsets [nvars][N][d] (offset =
+ * coordinate - anchor, heading offsets wrapped to [-pi, pi], Pose3 rotation vectors taken nearest the anchor's) -- half
+ * the bytes over PCIe for a host that already holds its particles relative to a per-variable reference point. */
+ROME_B200_API int rome_b200_set_particles_anchored(rome_b200_ctx* ctx, int vartype, int nvars, int N,
+                                                   const double* anchors_host, const float* offsets_host);
 ROME_B200_API int rome_b200_get_particles(rome_b200_ctx* ctx, int vartype, double* coords_host);
 /* Device view of the particle store (zero-copy interop): nvars contiguous blocks of `block_bytes`, each
  * { anchor header of `header_bytes` (Pose2: x,y,theta,cos,sin) }{ [Npad][d] float32 offsets }. */

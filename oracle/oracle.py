@@ -54,6 +54,7 @@ def lib() -> C.CDLL:
             fn.restype = None
             fn.argtypes = [d] * n
         _lib.rome_oracle_sweep_pose2pose2.argtypes = [C.c_int, C.c_int, i32, i32, d, d, d, C.c_int]
+        _lib.rome_oracle_step.argtypes = [C.c_int, C.c_int, C.c_int, i32, i32, d, d, d, d, u64, d, d, C.c_int]
         _lib.rome_oracle_sweep_pose3pose3.argtypes = [C.c_int, C.c_int, i32, i32, d, d, d, C.c_int]
         _lib.rome_oracle_sweep_priorpose2.argtypes = [C.c_int, C.c_int, i32, d, d, d, C.c_int]
         _lib.rome_oracle_sweep_priorpose3.argtypes = [C.c_int, C.c_int, i32, d, d, d, C.c_int]
@@ -223,6 +224,22 @@ def sym_rem(x):
 # batched sweeps; arrays in the reference's particle-major layout
 #   vars [nvars][N][d], meas [nF][N][dm] -> res [nF][N][dr]
 # ----------------------------------------------------------------------------------
+def step_prepare(family, i0, i1, v0, v1, mu, Lc, nthreads=0):
+    """one STEP of the hot path on the CPU (rome_oracle_step: getSample + residual + per-factor statistics for every
+    factor x particle of `family`, 0..4): inputs converted and outputs allocated once; returns (call, res, stats) where
+    call(seed) -> threads used"""
+    i0, v0, mu, Lc = _i32(i0), _f64(v0), _f64(mu), _f64(Lc)
+    i1 = _i32(i1) if i1 is not None else i0
+    v1 = _f64(v1) if v1 is not None else v0
+    nF, N, dr = len(i0), v0.shape[1], mu.shape[1]
+    res, stats = np.empty((nF, N, dr)), np.empty((nF, dr + dr * (dr + 1) // 2))
+
+    def call(seed=0):
+        return lib().rome_oracle_step(family, nF, N, _ip(i0), _ip(i1), _dp(v0), _dp(v1), _dp(mu), _dp(Lc), seed, _dp(res),
+                                      _dp(stats), nthreads)
+    return call, res, stats
+
+
 def sweep_pose2pose2(ip, iq, poses, meas, nthreads=0):
     ip, iq, poses, meas = _i32(ip), _i32(iq), _f64(poses), _f64(meas)
     nF, N = meas.shape[0], meas.shape[1]

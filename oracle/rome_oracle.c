@@ -315,6 +315,88 @@ static int set_threads(int nthreads) {
 #endif
 }
 
+/* ---- one STEP of the hot path on the CPU, as bench.py's GPU step defines it: for every factor x particle getSample
+ * (rand(MvNormal) = mu + L z, IIF's default sampler on the `.Z` field; BearingRange2D.jl:17-27 for the two scalar
+ * beliefs), the residual functor, and the per-factor statistics (sum r, sum r r').  The reference draws from Julia's
+ * Xoshiro256++ stream with a ziggurat randn; this restatement uses Xoshiro256++ with the Marsaglia polar method, one
+ * generator per factor seeded from (seed, factor) so the result does not depend on the thread count.
+ * family: 0 Pose2Pose2, 1 PriorPose2, 2 BearingRange, 3 Pose3Pose3, 4 PriorPose3 (include/rome_b200.h numbering).
+ * mu [nF][dm], Lc [nF][dm][dm] lower Cholesky factor row-major (BearingRange: diag(sig_b, sig_r)),
+ * res [nF][N][dr], stats [nF][dr + dr(dr+1)/2]. */
+typedef struct { uint64_t s[4]; int have; double spare; } xo_t;
+static inline uint64_t xo_rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+static inline uint64_t xo_next(xo_t* g) {
+    uint64_t* s = g->s;
+    const uint64_t r = xo_rotl(s[0] + s[3], 23) + s[0], t = s[1] << 17;
+    s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3]; s[2] ^= t; s[3] = xo_rotl(s[3], 45);
+    return r;
+}
+static inline void xo_seed(xo_t* g, uint64_t seed, uint64_t stream) {
+    uint64_t z = seed ^ (stream * 0x9E3779B97F4A7C15ull);
+    for (int i = 0; i < 4; ++i) {  /* splitmix64 */
+        z += 0x9E3779B97F4A7C15ull;
+        uint64_t x = z;
+        x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+        x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+        g->s[i] = x ^ (x >> 31);
+    }
+    g->have = 0;
+}
+static inline double xo_normal(xo_t* g) {
+    if (g->have) { g->have = 0; return g->spare; }
+    double u, v, q;
+    do {
+        u = (double)(xo_next(g) >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+        v = (double)(xo_next(g) >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+        q = u * u + v * v;
+    } while (q >= 1.0 || q == 0.0);
+    const double m = sqrt(-2.0 * log(q) / q);
+    g->spare = v * m; g->have = 1;
+    return u * m;
+}
+int rome_oracle_step(int family, int nF, int N, const int32_t* i0, const int32_t* i1, const double* v0, const double* v1,
+                     const double* mu, const double* Lc, uint64_t seed, double* res, double* stats, int nthreads) {
+    static const int DM[5] = {3, 3, 2, 6, 6}, D0[5] = {3, 3, 3, 6, 6}, D1[5] = {3, 0, 2, 6, 0};
+    if (family < 0 || family > 4) return -1;
+    const int dm = DM[family], dr = dm, d0 = D0[family], d1 = D1[family], ns = dr + dr * (dr + 1) / 2;
+    const int nt = set_threads(nthreads);
+#pragma omp parallel for schedule(static) num_threads(nt)
+    for (int f = 0; f < nF; ++f) {
+        xo_t g;
+        xo_seed(&g, seed, (uint64_t)f);
+        const double* P = v0 + (size_t)i0[f] * N * d0;
+        const double* Q = d1 ? v1 + (size_t)i1[f] * N * d1 : 0;
+        const double *m0 = mu + (size_t)f * dm, *L = Lc + (size_t)f * dm * dm;
+        double* R = res + (size_t)f * N * dr;
+        double st[27];
+        for (int i = 0; i < ns; ++i) st[i] = 0.0;
+        for (int n = 0; n < N; ++n) {
+            double z[6], X[6], r[6];
+            for (int i = 0; i < dm; ++i) z[i] = xo_normal(&g);
+            for (int i = 0; i < dm; ++i) {
+                double a = m0[i];
+                for (int j = 0; j <= i; ++j) a += L[i * dm + j] * z[j];
+                X[i] = a;
+            }
+            switch (family) {
+                case 0: rome_oracle_pose2pose2(X, P + 3 * n, Q + 3 * n, r); break;
+                case 1: rome_oracle_priorpose2(X, P + 3 * n, r); break;
+                case 2: rome_oracle_bearingrange(X, P + 3 * n, Q + 2 * n, r); break;
+                case 3: rome_oracle_pose3pose3(X, P + 6 * n, Q + 6 * n, r); break;
+                default: rome_oracle_priorpose3(X, P + 6 * n, r); break;
+            }
+            int k = dr;
+            for (int i = 0; i < dr; ++i) {
+                R[(size_t)n * dr + i] = r[i];
+                st[i] += r[i];
+                for (int j = i; j < dr; ++j) st[k++] += r[i] * r[j];
+            }
+        }
+        for (int i = 0; i < ns; ++i) stats[(size_t)f * ns + i] = st[i];
+    }
+    return nt;
+}
+
 int rome_oracle_sweep_pose2pose2(int nF, int N, const int32_t* ip, const int32_t* iq,
                                  const double* poses, const double* meas, double* res, int nthreads) {
     const int nt = set_threads(nthreads);

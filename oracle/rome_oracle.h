@@ -99,6 +99,11 @@ int rome_oracle_sweep_pose3pose3(int nF, int N, const int32_t* ip, const int32_t
 int rome_oracle_sweep_priorpose3(int nF, int N, const int32_t* ip,
                                  const double* poses, const double* meas, double* res, int nthreads);
 
+/* One STEP of the hot path as bench.py's GPU step defines it (getSample + residual + per-factor statistics for every
+ * factor x particle of one family); see rome_oracle.c.  Returns the thread count used, -1 for an unknown family. */
+int rome_oracle_step(int family, int nF, int N, const int32_t* i0, const int32_t* i1, const double* v0, const double* v1,
+                     const double* mu, const double* Lc, uint64_t seed, double* res, double* stats, int nthreads);
+
 /* ---- "reference-shaped" convolution: per particle, Nelder-Mead over the target's
  * tangent coordinates wrapping the residual, inflateCycles restarts with inflation
  * noise (IIF 0.35 defaults N=100, inflateCycles=3, inflation=5.0 as serialized in

@@ -24,7 +24,7 @@ PEER_STATE_WORDS = 16
 SYMBOLS = [
     "rome_b200_version", "rome_b200_create", "rome_b200_destroy", "rome_b200_last_error", "rome_b200_set_stream",
     "rome_b200_synchronize", "rome_b200_family_dims", "rome_b200_vartype_dim", "rome_b200_npad", "rome_b200_plan_query",
-    "rome_b200_set_particles", "rome_b200_get_particles", "rome_b200_particles_device", "rome_b200_adopt_proposal",
+    "rome_b200_set_particles", "rome_b200_set_particles_anchored", "rome_b200_get_particles", "rome_b200_particles_device", "rome_b200_adopt_proposal",
     "rome_b200_set_factors_pose2pose2", "rome_b200_set_factors_priorpose2", "rome_b200_set_factors_bearingrange",
     "rome_b200_set_factors_pose3pose3", "rome_b200_set_factors_priorpose3", "rome_b200_set_factors_point2",
     "rome_b200_set_factors_scalar", "rome_b200_set_factors_gaussian", "rome_b200_num_factors",
@@ -73,6 +73,7 @@ def load() -> C.CDLL:
     lib.rome_b200_npad.argtypes = [i]
     lib.rome_b200_plan_query.argtypes = [i, u32, i] + [C.POINTER(i)] * 5
     lib.rome_b200_set_particles.argtypes = [vp, i, i, i, vp]
+    lib.rome_b200_set_particles_anchored.argtypes = [vp, i, i, i, vp, vp]
     lib.rome_b200_get_particles.argtypes = [vp, i, vp]
     lib.rome_b200_particles_device.argtypes = [vp, i, C.POINTER(vp)] + [C.POINTER(i)] * 5
     lib.rome_b200_adopt_proposal.argtypes = [vp, i, i, vp, i]

@@ -183,6 +183,28 @@ __global__ void pack_kernel(int nvars, int N, int Npad, int wrap_dim, const doub
         }
     }
 }
+// anchored upload: the caller supplies the Float64 anchors [nvars][D] and float32 offsets [nvars][N][D] (half the bytes
+// of the Float64 coordinates); this kernel only lays them out as blocks {header, [Npad][D] offsets}
+template <int D>
+__global__ void pack_anchored_kernel(int nvars, int N, int Npad, int wrap_dim, const double* __restrict__ anchors,
+                                     const float* __restrict__ offs, unsigned char* __restrict__ store) {
+    const int v = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (v >= nvars) return;
+    const double* a = anchors + (size_t)v * D;
+    unsigned char* blk = store + (size_t)v * var_block_bytes(D, Npad);
+    double* hdr = reinterpret_cast<double*>(blk);
+    if (lane < var_header_bytes(D) / 8) {
+        double h = lane < D ? a[lane] : 0.0;
+        if (wrap_dim >= 0 && lane == D) h = cos(a[wrap_dim]);
+        if (wrap_dim >= 0 && lane == D + 1) h = sin(a[wrap_dim]);
+        hdr[lane] = h;
+        if (wrap_dim >= 0 && lane == D + 2)
+            *reinterpret_cast<float2*>(hdr + lane) = make_float2((float)cos(a[wrap_dim]), (float)sin(a[wrap_dim]));
+    }
+    const float* src = offs + (size_t)v * N * D;
+    float* dst = reinterpret_cast<float*>(blk + var_header_bytes(D));
+    for (int i = lane; i < Npad * D; i += 32) dst[i] = i < N * D ? src[i] : 0.f;
+}
 template <int D>
 __global__ void unpack_kernel(int nvars, int N, int Npad, int wrap_dim, const unsigned char* __restrict__ store,
                               double* __restrict__ coords) {
@@ -219,6 +241,17 @@ int launch_pack(int d, int wrap_dim, int nvars, int N, int Npad, const double* c
     if (d == 3) pack_kernel<3><<<grid, 256, 0, s>>>(nvars, N, Npad, wrap_dim, coords, store);
     else if (d == 2) pack_kernel<2><<<grid, 256, 0, s>>>(nvars, N, Npad, wrap_dim, coords, store);
     else if (d == 6) pack_kernel<6><<<grid, 256, 0, s>>>(nvars, N, Npad, wrap_dim, coords, store);
+    else return (int)cudaErrorInvalidValue;
+    return (int)cudaGetLastError();
+}
+int launch_pack_anchored(int d, int wrap_dim, int nvars, int N, int Npad, const double* anchors, const float* offs,
+                         unsigned char* store, void* stream) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int grid = (nvars + 7) / 8;
+    if (nvars == 0) return 0;
+    if (d == 3) pack_anchored_kernel<3><<<grid, 256, 0, s>>>(nvars, N, Npad, wrap_dim, anchors, offs, store);
+    else if (d == 2) pack_anchored_kernel<2><<<grid, 256, 0, s>>>(nvars, N, Npad, wrap_dim, anchors, offs, store);
+    else if (d == 6) pack_anchored_kernel<6><<<grid, 256, 0, s>>>(nvars, N, Npad, wrap_dim, anchors, offs, store);
     else return (int)cudaErrorInvalidValue;
     return (int)cudaGetLastError();
 }

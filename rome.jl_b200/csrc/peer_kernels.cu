@@ -15,8 +15,13 @@ struct PeerSlots {
     uint32_t* slot[8];
 };
 
+// Both kernels are launched with programmatic dependent launch: they are resident (one warp) while their predecessor
+// drains, wait for its COMPLETION (griddepcontrol.wait: all its stores, peer stores included, are performed) and only
+// then publish / poll; their own successor may be set up meanwhile (launch_dependents).
 __global__ void peer_signal_kernel(PeerSlots peers, int n_peers, uint32_t* epoch) {
     __shared__ uint32_t e;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (threadIdx.x == 0) e = ++(*epoch);
     __syncthreads();
     if ((int)threadIdx.x < n_peers) {
@@ -28,6 +33,8 @@ __global__ void peer_signal_kernel(PeerSlots peers, int n_peers, uint32_t* epoch
 // status[0] is set to 1 if the wait gave up (a peer never arrived): the host reads it with rome_b200_peer_status
 __global__ void peer_wait_kernel(const uint32_t* flags, int n, uint32_t* epoch, uint32_t* status, long long max_cycles) {
     __shared__ uint32_t e;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (threadIdx.x == 0) e = ++(*epoch);
     __syncthreads();
     if ((int)threadIdx.x < n) {
@@ -45,15 +52,26 @@ __global__ void peer_wait_kernel(const uint32_t* flags, int n, uint32_t* epoch, 
     }
 }
 
+template <class K, class... A>
+static int launch_one_warp_pdl(K k, void* stream, A... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(1);
+    cfg.blockDim = dim3(32);
+    cfg.stream = static_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return (int)cudaLaunchKernelEx(&cfg, k, args...);
+}
 int launch_peer_signal(uint32_t* const* slots, int n_peers, uint32_t* epoch, void* stream) {
     PeerSlots p = {};
     for (int i = 0; i < n_peers && i < 8; ++i) p.slot[i] = slots[i];
-    peer_signal_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(p, n_peers, epoch);
-    return (int)cudaGetLastError();
+    return launch_one_warp_pdl(peer_signal_kernel, stream, p, n_peers, epoch);
 }
 int launch_peer_wait(const uint32_t* flags, int n, uint32_t* epoch, uint32_t* status, long long max_cycles, void* stream) {
-    peer_wait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(flags, n, epoch, status, max_cycles);
-    return (int)cudaGetLastError();
+    return launch_one_warp_pdl(peer_wait_kernel, stream, flags, n, epoch, status, max_cycles);
 }
 
 // Halo push (owner-sharded sweeps): copy whole particle blocks of variables this rank owns into the particle stores of

@@ -336,6 +336,47 @@ int rome_b200_set_particles(rome_b200_ctx* ctx, int vartype, int nvars, int N, c
     return ROME_B200_OK;
 }
 
+int rome_b200_set_particles_anchored(rome_b200_ctx* ctx, int vartype, int nvars, int N, const double* anchors_host,
+                                     const float* offsets_host) {
+    if (!ctx) return ROME_B200_BAD_ARG;
+    if (vartype < 0 || vartype >= ROME_B200_NVARTYPES) return fail(ctx, ROME_B200_BAD_ARG, "bad vartype");
+    if (nvars < 0 || N <= 0 || (nvars > 0 && (!anchors_host || !offsets_host))) return fail(ctx, ROME_B200_BAD_ARG, "bad particle shape");
+    if (ctx->capturing) return fail(ctx, ROME_B200_BAD_ARG, "set_particles during graph capture");
+    if (int e = bind(ctx)) return e;
+    const int d = kVarDim[vartype], Npad = rome_b200_npad(N);
+    VarStore& vs = ctx->vars[vartype];
+    const size_t store_bytes = (size_t)nvars * var_block_bytes(d, Npad);
+    if (store_bytes > vs.cap) {
+        if (vs.store) CK(cudaFree(vs.store));
+        vs.store = nullptr; vs.cap = 0;
+        const size_t kBlock = size_t(2) << 20;
+        const size_t rounded = (store_bytes + kBlock - 1) / kBlock * kBlock;
+        CK(cudaMalloc(&vs.store, rounded));
+        vs.cap = rounded;
+    }
+    vs.nvars = nvars; vs.N = N; vs.Npad = Npad;
+    if (nvars == 0) return ROME_B200_OK;
+    const size_t a_bytes = ((size_t)nvars * d * sizeof(double) + 255) / 256 * 256;
+    const size_t o_bytes = (size_t)nvars * N * d * sizeof(float);
+    if (int e = grow_dev(ctx, ctx->stage_dev, a_bytes + o_bytes)) return e;
+    unsigned char* sd = static_cast<unsigned char*>(ctx->stage_dev.p);
+    const void *sa = anchors_host, *so = offsets_host;
+    if (!is_pinned_or_device(anchors_host) || !is_pinned_or_device(offsets_host)) {  // pageable: stage through pinned memory
+        if (int e = grow_host(ctx, ctx->stage_host, a_bytes + o_bytes)) return e;
+        CK(cudaStreamSynchronize(ctx->stream));
+        unsigned char* sh = static_cast<unsigned char*>(ctx->stage_host.p);
+        std::memcpy(sh, anchors_host, (size_t)nvars * d * sizeof(double));
+        std::memcpy(sh + a_bytes, offsets_host, o_bytes);
+        sa = sh; so = sh + a_bytes;
+    }
+    CK(cudaMemcpyAsync(sd, sa, (size_t)nvars * d * sizeof(double), cudaMemcpyDefault, ctx->stream));
+    CK(cudaMemcpyAsync(sd + a_bytes, so, o_bytes, cudaMemcpyDefault, ctx->stream));
+    int e = launch_pack_anchored(d, kWrapDim[vartype], nvars, N, Npad, reinterpret_cast<const double*>(sd),
+                                 reinterpret_cast<const float*>(sd + a_bytes), vs.store, ctx->stream);
+    if (e) return cuda_fail(ctx, (cudaError_t)e, "pack kernel");
+    return ROME_B200_OK;
+}
+
 int rome_b200_get_particles(rome_b200_ctx* ctx, int vartype, double* coords_host) {
     if (!ctx) return ROME_B200_BAD_ARG;
     if (vartype < 0 || vartype >= ROME_B200_NVARTYPES || !coords_host) return fail(ctx, ROME_B200_BAD_ARG, "bad argument");

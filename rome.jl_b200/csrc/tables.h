@@ -125,6 +125,8 @@ int plan_launch(int family, uint32_t flags, int Npad, int smem_per_sm, int smem_
 int launch_eval(int family, const EvalParams& p, const LaunchPlan& plan, int grid, void* stream);
 int launch_pack(int d, int wrap_dim, int nvars, int N, int Npad, const double* coords, unsigned char* store,
                 void* stream);
+int launch_pack_anchored(int d, int wrap_dim, int nvars, int N, int Npad, const double* anchors, const float* offs,
+                         unsigned char* store, void* stream);
 int launch_unpack(int d, int wrap_dim, int nvars, int N, int Npad, const unsigned char* store, double* coords,
                   void* stream);
 int launch_adopt(int d, int Npad, unsigned char* store, int var, const float* prop, int factor, void* stream);

@@ -143,6 +143,19 @@ class Context:
         self._ck(self._lib.rome_b200_set_particles(self._h, vartype, nvars, N, _ptr(coords)))
         self._keep = coords  # keep alive until the async copy is consumed
 
+    def set_particles_anchored(self, vartype: int, anchors, offsets):
+        """anchors Float64 [nvars][d], offsets float32 [nvars][N][d] (numpy arrays or pinned torch tensors): the
+        device's own representation, half the upload bytes of set_particles"""
+        if isinstance(anchors, np.ndarray):
+            anchors = _f64(anchors)
+        if isinstance(offsets, np.ndarray):
+            offsets = np.ascontiguousarray(offsets, dtype=np.float32)
+        nvars, N, d = offsets.shape
+        if d != VAR_DIM[vartype] or tuple(anchors.shape) != (nvars, d):
+            raise ValueError("anchor / offset shapes do not match the variable type")
+        self._ck(self._lib.rome_b200_set_particles_anchored(self._h, vartype, nvars, N, _ptr(anchors), _ptr(offsets)))
+        self._keep = (anchors, offsets)
+
     def get_particles(self, vartype: int) -> np.ndarray:
         nvars, N = self.particles_device(vartype)[3:5]
         out = np.empty((nvars, N, VAR_DIM[vartype]))

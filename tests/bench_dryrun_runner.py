@@ -45,10 +45,9 @@ class _Graph:
 
 class _Ctx:
     """inert stand-in for rome_b200.Context: accepts every call bench.py makes, fills host outputs with ones"""
-    launch_count = 0
-
     def __init__(self, device=0):
         self.device = device
+        self.launch_count = 0
 
     def __getattr__(self, name):
         def call(*a, **k):
@@ -56,8 +55,17 @@ class _Ctx:
                 for key in ("res", "stats"):
                     if isinstance(k.get(key), torch.Tensor):
                         k[key].fill_(1.0)
+            if name in ("eval", "peer_signal", "peer_wait", "push_halo"):
+                self.launch_count += 1
             if name == "ipc_export":
                 return b"\0" * 64
+            if name == "particles_device":
+                return (1 << 21, 1296, 48, 0, 100, 104)
+            if name == "memcpy_d2h":
+                a[0][...] = 0
+                return None
+            if name == "peer_gave_up":
+                return False
             return 1 << 21 if name in ("malloc_device", "peer_state_alloc", "ipc_import") else None
         return call
 
@@ -73,7 +81,7 @@ def install():
             return fn(*a, **k)
         return wrapped
 
-    for name in ("zeros", "randn", "tensor"):
+    for name in ("zeros", "randn", "tensor", "as_tensor"):
         setattr(torch, name, on_cpu(getattr(torch, name)))
     torch.Tensor.pin_memory = lambda self: self
     torch.cuda.is_available = lambda: True
@@ -86,12 +94,6 @@ def install():
     dist.init_process_group = lambda backend=None, **k: real_init("gloo")
     rb.Context = _Ctx
 
-    def no_device(sweeps):
-        raise RuntimeError("no device in the dry run")
-
-    bench.device_sweeps = no_device
-    bench.cpu_reference_shaped = lambda w, nfac=4, nthreads=0: dict(
-        residual_evals_per_s=1.0, convolved_particles_per_s=1.0, residual_calls_per_particle=1.0, cores=1, sample="stub")
     return bench
 
 

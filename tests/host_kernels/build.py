@@ -103,7 +103,8 @@ def build_peer(outdir):
                        r"*(volatile uint32_t*)(\1) = \2; ++hk::g_progress;", body)
     body, n2 = re.subn(r'asm volatile\("ld\.acquire\.sys\.global\.u32 %0, \[%1\];" : "=r"\((\w+)\) : "l"\((.+?)\) : "memory"\);',
                        r"\1 = *(volatile const uint32_t*)(\2);", body)
-    assert n1 == 1 and n2 == 1 and "asm" not in body
+    body, n3 = re.subn(r'asm volatile\("griddepcontrol\.[a-z_]+;" ::: "memory"\);', "", body)
+    assert n1 == 1 and n2 == 1 and n3 == 4 and "asm" not in body
     text = ('#include "hk_shim.h"\n#undef threadIdx\n#define threadIdx (dim3_{(unsigned)(hk::g_cur & 31), 0, 0})\n'
             "#define __syncthreads() hk::collective(0u)\n#define __threadfence_system()\n#define __nanosleep(ns) hk::yield_()\n"
             "static long long hk_clock = 0;\n#define clock64() (++hk_clock)\n"
