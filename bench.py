@@ -296,9 +296,12 @@ def main():
     ap.add_argument("--workload", default=WORKLOAD, choices=[WORKLOAD, "beehive_N200", "se3_chain_10k"])
     ap.add_argument("--sets", type=int, default=0, help="independent working-set copies rotated through (0: enough for > 2x L2)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU legs (cpu_baseline, parity check)")
-    ap.add_argument("--barrier", default="flags", choices=["flags", "nccl"],
-                    help="G>1: rank barrier by the GPUs' own flag kernels over NVLink peer memory (default) or a 4-byte NCCL all-reduce")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline legs")
+    ap.add_argument("--no-parity", action="store_true", help="skip the in-run parity check of a sampled subset against the oracle")
+    ap.add_argument("--barrier", default="fused", choices=["fused", "flags", "nccl"],
+                    help="G>1: rank barrier fused into the evaluation kernels (default: the step's first launch waits for the "
+                         "peers' flags, its last launch publishes this rank's), by two one-warp flag kernels, or by a 4-byte "
+                         "NCCL all-reduce")
     ap.add_argument("--e2e-steps", type=int, default=40)
     args = ap.parse_args()
     if args.impl == "reference":
@@ -403,12 +406,13 @@ def main():
                     dst += [store_ptr[reader][vt] + int(sl) * bb for sl in slots]
                 if src:
                     c.set_halo_plan(vt, src, dst)
+            c.set_step_barrier(state, peer_slots)
         dist.barrier()
         token = torch.zeros(1, device="cuda")
 
     def rank_barrier(c):
         """stream-ordered barrier between the ranks (after everything enqueued so far on the launch stream)"""
-        if args.barrier == "flags":
+        if args.barrier in ("flags", "fused"):
             c.peer_signal(state, peer_slots)
             c.peer_wait(state, G - 1)
         else:
@@ -448,23 +452,25 @@ def main():
 
     # ---- the step ---------------------------------------------------------------------------------------------------
     def step(k, fams=None, barrier=True, indep_all=False):
+        """one pass of the hot path over this rank's factors: ONE launch per family.  The first launch is dependent (it
+        waits for the previous step), the others read the same particles and write other buffers: INDEPENDENT.  G > 1:
+        families with cut factors run with PROPOSAL_FWD | ROUTED_ONLY -- only the cut factors produce forward rows, and
+        those go straight into the owners' receive buffers; the rank barrier rides on the step's first / last launch."""
         c, bufs = sets[k % S]
-        first = True
-        for fam in (fams or fam_order):
-            f = lv["families"][fam]
-            b = bufs[fam]
-            dfwd = rb.FAMILY[fam][6]
-            n_int = f["n_interior"] + (0 if (multi and dfwd) else f["n_cut"])  # families without a forward proposal: all local
-            n_cut = len(f["i0"]) - n_int
-            if n_int:
-                c.eval(fam, F0 | (0 if (first and not indep_all) else rb.INDEPENDENT), seed=7, stream_id=k, first=0,
-                       count=n_int, res=b["res"], stats=b["stats"])
-                first = False
-            if n_cut:  # cut factors: the forward proposal rows go straight to the owners of their target variables
-                c.eval(fam, F0 | rb.PROPOSAL_FWD | (0 if (first and not indep_all) else rb.INDEPENDENT), seed=7,
-                       stream_id=k, first=n_int, count=n_cut, res=b["res"], stats=b["stats"], prop_fwd=dummy_fwd[fam])
-                first = False
-        if multi and barrier:
+        todo = [fam for fam in (fams or fam_order) if len(lv["families"][fam]["i0"]) > 0]
+        for idx, fam in enumerate(todo):
+            f, b = lv["families"][fam], bufs[fam]
+            fl = F0
+            kw = dict(res=b["res"], stats=b["stats"])
+            if multi and rb.FAMILY[fam][6] and f["n_cut"] > 0:
+                fl |= rb.PROPOSAL_FWD | rb.ROUTED_ONLY
+                kw["prop_fwd"] = dummy_fwd[fam]  # default rows are never written: every cut factor has a destination
+            if idx > 0 or indep_all:
+                fl |= rb.INDEPENDENT
+            if multi and barrier and args.barrier == "fused":
+                fl |= (rb.BARRIER_WAIT if idx == 0 else 0) | (rb.BARRIER_SIGNAL if idx == len(todo) - 1 else 0)
+            c.eval(fam, fl, seed=7, stream_id=k, **kw)
+        if multi and barrier and args.barrier != "fused":
             rank_barrier(c)
 
     def capture(fn, **kw):
@@ -585,7 +591,7 @@ def main():
                         worst = max(worst, float(np.nanmax(np.abs(seg[:, :N] - want[:, :N]))))
                     rows_checked += len(rows)
                     chk.close()
-        gave_up = bool(sets[0][0].peer_gave_up(state)) if args.barrier == "flags" else False
+        gave_up = bool(sets[0][0].peer_gave_up(state)) if args.barrier != "nccl" else False
         flag = torch.tensor([1.0 if (ok and halo_ok and not gave_up) else 0.0, float(rows_checked), worst, float(halo_checked)],
                             device="cuda", dtype=torch.float64)
         mn = flag.clone()
@@ -700,7 +706,7 @@ def main():
         bpe = rb.BYTES_PER_EVAL_SAMPLED[dom]
         fd = lv["families"][dom]
         n_dom = fd["n_interior"] + (fd["n_cut"] if not (multi and rb.FAMILY[dom][6]) else 0)
-        n_dom_cut = len(fd["i0"]) - n_dom
+        n_dom_cut = len(fd["i0"]) - n_dom   # cut factors also write a forward-proposal row (+4 dfwd bytes per eval)
         alg_bytes = (n_dom * bpe + n_dom_cut * (bpe + 4 * rb.FAMILY[dom][6])) * N
         ach = alg_bytes / (kms * 1e-3) / 1e9
         line = {
@@ -746,7 +752,7 @@ def main():
                                               "launches": "dependent (serialized)"}
         if verify:
             line.update(verify)
-        if not args.no_cpu:
+        if not args.no_parity:
             try:
                 line["parity"] = parity_check(rb, sets[2 % S][0], lv, wg, sh, rank, dom, N)
             except Exception as e:  # noqa: BLE001

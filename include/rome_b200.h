@@ -125,6 +125,17 @@ enum rome_b200_family {
  * anchor + offset and the only rounding is that of the float32 output.  Jacobian and deconvolution outputs always take
  * the Float64 chain. */
 #define ROME_B200_PRECISE 512u
+/* Owner-sharded multi-GPU sweeps (see rome_b200_set_proposal_destinations / rome_b200_set_step_barrier below):
+ * ROUTED_ONLY    with PROPOSAL_FWD: only factors that HAVE a destination write their forward row (and accumulate
+ *                proposal statistics); the others behave as if PROPOSAL_FWD were absent -- one launch covers a rank's
+ *                interior and cut factors.
+ * BARRIER_WAIT   this launch is the first of a step: before it fetches particle blocks it waits (on the device) until
+ *                every peer has signalled the end of its previous step.
+ * BARRIER_SIGNAL this launch is the last of a step: when its grid has finished, the next epoch is published to every
+ *                peer. */
+#define ROME_B200_ROUTED_ONLY 1024u
+#define ROME_B200_BARRIER_WAIT 2048u
+#define ROME_B200_BARRIER_SIGNAL 4096u
 
 /* Buffers of one eval call.  Unused members may be NULL.  `_host` entry points take host
  * pointers with the same shapes; plain entry points take device pointers. */
@@ -272,9 +283,20 @@ ROME_B200_API int rome_b200_set_peer_proposals(rome_b200_ctx* ctx, int family, i
  * Order both against the peers with rome_b200_peer_signal / rome_b200_peer_wait. */
 ROME_B200_API int rome_b200_set_proposal_destinations(rome_b200_ctx* ctx, int family, int direction, int nF,
                                                       void* const* rows);
+/* Variables [0, n_owned) of the type are this rank's own: rome_b200_product / rome_b200_reanchor update only those (the
+ * product plan then covers n_owned variables); the slots behind them are halo copies written by their owners' pushes.
+ * n_owned < 0: all variables (default). */
+ROME_B200_API int rome_b200_set_owned_variables(rome_b200_ctx* ctx, int vartype, int n_owned);
 ROME_B200_API int rome_b200_set_halo_plan(rome_b200_ctx* ctx, int vartype, int n, const int32_t* src_var,
                                           void* const* dst_blocks);
 ROME_B200_API int rome_b200_push_halo(rome_b200_ctx* ctx, int vartype);
+/* Rank barrier FUSED into the evaluation kernels (flags ROME_B200_BARRIER_WAIT / ROME_B200_BARRIER_SIGNAL): `d_state`
+ * and `peer_slots` as for rome_b200_peer_signal.  Protocol per step and rank: the FIRST launch carries BARRIER_WAIT, the
+ * LAST launch (one that is not empty) carries BARRIER_SIGNAL; a single launch may carry both.  Every rank must execute
+ * the same number of steps.  The wait target is this rank's own signal count, so rome_b200_peer_signal / _wait and the
+ * fused flags must not be interleaved on one state buffer except that a completed signal + wait PAIR of the kernels may
+ * precede the first fused step (set-up barrier).  n_peers = 0 clears. */
+ROME_B200_API int rome_b200_set_step_barrier(rome_b200_ctx* ctx, void* d_state, uint32_t* const* peer_slots, int n_peers);
 /* CUDA IPC plumbing for buffers allocated with rome_b200_malloc_device (64-byte opaque handles).  Only such buffers may
  * be exported: rome_b200_malloc_device hands out whole 2 MiB blocks, so the handle (which names the driver's block) and
  * the buffer coincide; a pointer into a packed small cudaMalloc allocation would be opened at the wrong address. */

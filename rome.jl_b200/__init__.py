@@ -4,10 +4,10 @@ The directory is named `rome.jl_b200`; import it as `rome_b200` (see /rome_b200.
 Compute lives in librome_b200.so (csrc/, hand-written CUDA behind the C ABI of
 include/rome_b200.h); this package is the host-side mirror of the reference's factor API.
 """
-from ._lib import (BEARINGRANGE, DECONV, INDEPENDENT, JACOBIAN, POINT2, POINT2POINT2, POINT2POINT2RANGE, POINT3, POINT3POINT3,
+from ._lib import (BARRIER_SIGNAL, BARRIER_WAIT, BEARINGRANGE, DECONV, INDEPENDENT, JACOBIAN, POINT2, POINT2POINT2, POINT2POINT2RANGE, POINT3, POINT3POINT3,
                    POSE2, POSE2POINT2, POSE2POINT2BEARING, POSE2POINT2RANGE, POSE2POSE2, POSE3, POSE3POSE3,
                    POSE3POSE3ROTATION, POSE3POSE3UNITTRANS, POSE3POSE3XYYAW, PRECISE, PRIORPOINT2, PRIORPOINT3, PRIORPOSE2, PRIORPOSE3,
-                   PROPOSAL_BWD, PROPOSAL_FWD, RESIDUAL, SAMPLE, SO_PATH, STATS, SYMBOLS, WRITE_MEAS, RomeB200Error)
+                   PROPOSAL_BWD, PROPOSAL_FWD, RESIDUAL, ROUTED_ONLY, SAMPLE, SO_PATH, STATS, SYMBOLS, WRITE_MEAS, RomeB200Error)
 from .engine import (BYTES_PER_EVAL, BYTES_PER_EVAL_SAMPLED, FAMILY, VAR_DIM, Context, dequantized_particles,
                      meas_to_offsets, npad, offsets_to_meas, plan_query, rows_to_particle_major)
 

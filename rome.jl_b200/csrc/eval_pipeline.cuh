@@ -52,6 +52,7 @@ struct FactorView {
     const float* meas;        // [dm][Npad] measurement offsets (nullptr with SAMPLE)
     float* out_res;           // [dr][Npad] residual rows, flushed by a warp-local TMA bulk store
     float* out_fwd;           // [dfwd][Npad] forward-proposal rows, same
+    bool fwd_on;              // false: this factor writes no forward row (ROME_B200_ROUTED_ONLY and no destination)
 };
 constexpr uint32_t kHot1 = ROME_B200_RESIDUAL | ROME_B200_STATS;
 constexpr uint32_t kHot2 = ROME_B200_RESIDUAL | ROME_B200_STATS | ROME_B200_PROPOSAL_FWD;
@@ -149,6 +150,71 @@ constexpr int kBarrierBytes = 128;
 constexpr int kMaxStages = 6;
 
 // =============================================================================================
+// tile schedule of a persistent grid: `rounds` rounds in which EVERY CTA takes a full tile of FT factors (static round
+// robin), then ONE tail round in which the remaining factors are split evenly over the CTAs (m <= FT each) -- instead of
+// a last round of full tiles on a few CTAs while the others idle (12 000 factors on 296 CTAs: 5 rounds + 1 factor on
+// 160 CTAs instead of a 6th round on 20 CTAs).  Tile i of CTA b covers factors [first, first + nf) of the launch range.
+// =============================================================================================
+struct TileSched {
+    int rounds, tail_base, tail_m, rem, n;  // n = tiles of THIS CTA
+    __device__ __forceinline__ void init(int count, int ft, int grid, int b) {
+        rounds = (count / ft) / grid;
+        tail_base = rounds * grid * ft;
+        rem = count - tail_base;
+        tail_m = (rem + grid - 1) / grid;
+        n = rounds + ((tail_m > 0 && b * tail_m < rem) ? 1 : 0);
+    }
+    __device__ __forceinline__ int first(int i, int ft, int grid, int b) const {
+        return i < rounds ? (b + i * grid) * ft : tail_base + b * tail_m;
+    }
+    __device__ __forceinline__ int nf(int i, int ft, int b) const {
+        return i < rounds ? ft : min(tail_m, rem - b * tail_m);
+    }
+};
+
+// =============================================================================================
+// rank barrier fused into the evaluation kernels (owner-sharded multi-GPU sweeps; the state buffer is the one of
+// rome_b200_peer_signal / _wait: words [0, 8) flag slots written by the peers, word 8 this rank's signal epoch, word 10
+// give-up status, word 12 the CTA counter of the signalling launch).
+//   ROME_B200_BARRIER_WAIT   (first launch of a step): before the first particle block is fetched, every CTA polls the
+//       local flag slots until each peer has signalled as often as this rank has (word 8) -- the peers' previous step,
+//       with its stores into this GPU's memory, is complete.
+//   ROME_B200_BARRIER_SIGNAL (last launch of a step): the CTA that finishes last publishes the next epoch to the slot
+//       this rank owns in every peer's state (st.release.sys after a system-scope fence: the rows this grid stored into
+//       peer memory are visible before the flag).
+// No extra kernel, no host round trip: the barrier costs the NVLink latency of a 4-byte store.
+// =============================================================================================
+__device__ __forceinline__ void fused_barrier_wait(const EvalParams& P) {
+    if (threadIdx.x < (unsigned)P.bar_n) {
+        const uint32_t target = *reinterpret_cast<volatile const uint32_t*>(P.bar_state + 8);
+        const long long t0 = clock64();
+        for (;;) {
+            const uint32_t v = ld_acquire_sys_u32(P.bar_state + threadIdx.x);
+            if ((int32_t)(v - target) >= 0) break;  // wrap-safe "v >= target"
+            if (clock64() - t0 > P.bar_timeout) {    // a peer died: give up instead of hanging the GPU
+                atomicExch(P.bar_state + 10, 1u);
+                break;
+            }
+        }
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void fused_barrier_signal(const EvalParams& P) {
+    __syncthreads();  // every warp of this CTA has waited for its bulk stores
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        const uint32_t done = atomicAdd(P.bar_state + 12, 1u);
+        if (done == gridDim.x - 1) {  // the last CTA of the grid
+            __threadfence_system();
+            P.bar_state[12] = 0;
+            const uint32_t e = P.bar_state[8] + 1;
+            P.bar_state[8] = e;
+            for (int r = 0; r < P.bar_n; ++r) st_release_sys_u32(P.bar_peer[r], e);
+        }
+    }
+}
+
+// =============================================================================================
 // persistent producer/consumer pipeline
 //   smem: [full[], empty[] mbarriers | S input stages | FT per-warp output slices]
 // =============================================================================================
@@ -161,7 +227,9 @@ __global__ void __launch_bounds__((FT + 1) * 32, Fam::kMinCtas) eval_kernel(cons
     unsigned char* stage0 = smem + kBarrierBytes;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = P.stages;
-    const int nTiles = (P.count + FT - 1) / FT;
+    const int grid = (int)gridDim.x, cta = (int)blockIdx.x;
+    TileSched T;
+    T.init(P.count, FT, grid, cta);
     const StageLayout L = stage_layout(FT, (int)sizeof(Row), Fam::D0, Fam::D1, Fam::DM, kSample, P.Npad);
     const Row* __restrict__ table = reinterpret_cast<const Row*>(P.rows) + P.first;
     const uint32_t flags = kStatic ? kStatic : P.flags;
@@ -172,14 +240,14 @@ __global__ void __launch_bounds__((FT + 1) * 32, Fam::kMinCtas) eval_kernel(cons
     constexpr int TPC = 32 / FT;  // tiles per chunk
     const int jl = lane / FT, fl_in_tile = lane % FT;
     int2 ids_cur = make_int2(0, 0);
-    auto fetch_chunk = [&](int base_tile) {
-        const int t = base_tile + jl * (int)gridDim.x;
-        const int fl = t * FT + fl_in_tile;
+    auto fetch_chunk = [&](int base_i) {
+        const int i = base_i + jl;
         int2 ids = make_int2(0, 0);
-        if (t < nTiles && fl < P.count) ids = __ldg(reinterpret_cast<const int2*>(table + fl));
+        if (i < T.n && fl_in_tile < T.nf(i, FT, cta))
+            ids = __ldg(reinterpret_cast<const int2*>(table + T.first(i, FT, grid, cta) + fl_in_tile));
         return ids;
     };
-    if (warp == FT) ids_cur = fetch_chunk(blockIdx.x);
+    if (warp == FT) ids_cur = fetch_chunk(0);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
@@ -197,27 +265,28 @@ __global__ void __launch_bounds__((FT + 1) * 32, Fam::kMinCtas) eval_kernel(cons
     // flagged ROME_B200_INDEPENDENT touches no such data and defers that wait to its end.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (!(P.flags & ROME_B200_INDEPENDENT)) asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (P.flags & ROME_B200_BARRIER_WAIT) fused_barrier_wait(P);  // the peers' previous step has landed in this GPU's memory
 
     if (warp == FT) {
         // ---------------- producer warp ---------------------------------------------------------------------
         int s = 0;
         uint32_t phase = 1;  // parity of the previous round; the first pass over the ring does not wait
         bool first_round = true;
-        for (int base = blockIdx.x; base < nTiles; base += TPC * gridDim.x) {
-            const int2 ids_next = fetch_chunk(base + TPC * gridDim.x);  // in flight while this chunk is issued
+        for (int base = 0; base < T.n; base += TPC) {
+            const int2 ids_next = fetch_chunk(base + TPC);  // in flight while this chunk is issued
 #pragma unroll 1
             for (int j = 0; j < TPC; ++j) {
-                const int tile = base + j * gridDim.x;
-                if (tile >= nTiles) break;
+                const int i = base + j;
+                if (i >= T.n) break;
                 if (!first_round) mbar_wait(&empty[s], phase);
                 unsigned char* st = stage0 + (size_t)s * L.bytes;
-                const int nf = min(FT, P.count - tile * FT);
+                const int t0 = T.first(i, FT, grid, cta), nf = T.nf(i, FT, cta);
                 if (lane == j * FT) {
                     fence_proxy_async();
                     mbar_arrive_expect_tx(&full[s], (uint32_t)(nf * ((int)sizeof(Row) + L.b0 + L.b1 + L.mb)));
-                    tma_load_1d(st + L.rows_off, table + (size_t)tile * FT, (uint32_t)(nf * sizeof(Row)), &full[s]);
+                    tma_load_1d(st + L.rows_off, table + t0, (uint32_t)(nf * sizeof(Row)), &full[s]);
                     if (!kSample)
-                        tma_load_1d(st + L.meas_off, P.meas + (size_t)(P.first + tile * FT) * Fam::DM * P.Npad,
+                        tma_load_1d(st + L.meas_off, P.meas + (size_t)(P.first + t0) * Fam::DM * P.Npad,
                                     (uint32_t)(nf * L.mb), &full[s]);
                 }
                 __syncwarp();
@@ -238,12 +307,16 @@ __global__ void __launch_bounds__((FT + 1) * 32, Fam::kMinCtas) eval_kernel(cons
         const int res_floats = Fam::DR * P.Npad;
         int s = 0;
         uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
+        for (int i = 0; i < T.n; ++i) {
+            const bool mine = warp < T.nf(i, FT, cta);
+            const int f = P.first + T.first(i, FT, grid, cta) + warp;
+            // owner-sharded exchange: this factor's forward row may have its own destination (a peer GPU); requested
+            // before the wait for the stage so that the load's latency hides behind it (warp-uniform address)
+            unsigned long long fdst = 0;
+            if (mine && (flags & ROME_B200_PROPOSAL_FWD) && P.fwd_dst) fdst = __ldg(P.fwd_dst + f);
             mbar_wait(&full[s], phase);
             const unsigned char* st = stage0 + (size_t)s * L.bytes;
-            const int fl = tile * FT + warp;
-            if (fl < P.count) {
-                const int f = P.first + fl;
+            if (mine) {
                 const Row row = reinterpret_cast<const Row*>(st + L.rows_off)[warp];
                 FactorView V;
                 V.b0 = st + L.v0_off + warp * L.b0;
@@ -251,10 +324,7 @@ __global__ void __launch_bounds__((FT + 1) * 32, Fam::kMinCtas) eval_kernel(cons
                 V.meas = kSample ? nullptr : reinterpret_cast<const float*>(st + L.meas_off + (size_t)warp * L.mb);
                 V.out_res = out;
                 V.out_fwd = out + res_floats;
-                // owner-sharded exchange: this factor's forward row may have its own destination (a peer GPU); requested
-                // before the arithmetic so that the load's latency hides behind it
-                unsigned long long fdst = 0;
-                if ((flags & ROME_B200_PROPOSAL_FWD) && P.fwd_dst && lane == 0) fdst = __ldg(P.fwd_dst + f);
+                V.fwd_on = !(P.flags & ROME_B200_ROUTED_ONLY) || fdst != 0;
                 if (flags & (ROME_B200_RESIDUAL | ROME_B200_PROPOSAL_FWD)) {
                     if (lane == 0) tma_store_wait_read();  // the previous tile's rows have left the slice
                     __syncwarp();
@@ -266,7 +336,7 @@ __global__ void __launch_bounds__((FT + 1) * 32, Fam::kMinCtas) eval_kernel(cons
                     if (lane == 0) {
                         if (flags & ROME_B200_RESIDUAL)
                             tma_store_1d(P.res + (size_t)f * res_floats, V.out_res, (uint32_t)(res_floats * 4));
-                        if (flags & ROME_B200_PROPOSAL_FWD) {
+                        if ((flags & ROME_B200_PROPOSAL_FWD) && V.fwd_on) {
                             const size_t off = (size_t)f * Fam::DFWD * P.Npad;
                             const uint32_t bytes = (uint32_t)(Fam::DFWD * P.Npad * 4);
                             tma_store_1d(fdst ? reinterpret_cast<float*>(fdst) : P.prop_fwd + off, V.out_fwd, bytes);
@@ -285,6 +355,7 @@ __global__ void __launch_bounds__((FT + 1) * 32, Fam::kMinCtas) eval_kernel(cons
     }
     // a launch that overlapped its predecessor must not be seen as complete before the predecessor is
     if (P.flags & ROME_B200_INDEPENDENT) asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (P.flags & ROME_B200_BARRIER_SIGNAL) fused_barrier_signal(P);
 }
 // =============================================================================================
 // per-warp pipeline ("warp pipeline"): no producer warp and no CTA-wide barrier.  Warp w of a CTA owns slot w of
@@ -318,6 +389,9 @@ __global__ void __launch_bounds__(FT * 32, Fam::kMinCtas) eval_kernel_w(const __
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = P.stages;
+    const int grid = (int)gridDim.x, cta = (int)blockIdx.x;
+    TileSched T;
+    T.init(P.count, FT, grid, cta);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem) + warp * kMaxStages;
     const SlotLayout L = slot_layout((int)sizeof(Row), Fam::D0, Fam::D1, Fam::DM, kSample, P.Npad);
     const int warp_bytes = S * L.bytes + P.out_warp_bytes;
@@ -326,15 +400,15 @@ __global__ void __launch_bounds__(FT * 32, Fam::kMinCtas) eval_kernel_w(const __
     const Row* __restrict__ table = reinterpret_cast<const Row*>(P.rows) + P.first;
     const uint32_t flags = kStatic ? kStatic : P.flags;
     const int res_floats = Fam::DR * P.Npad;
-    // the i-th factor of this warp: tile blockIdx.x + i * gridDim.x, slot `warp`
-    auto factor_of = [&](int i) { return (blockIdx.x + i * (int)gridDim.x) * FT + warp; };
+    // the i-th factor of this warp: slot `warp` of the CTA's i-th tile (-1: none)
+    auto factor_of = [&](int i) { return (i < T.n && warp < T.nf(i, FT, cta)) ? T.first(i, FT, grid, cta) + warp : -1; };
     auto fetch_ids = [&](int i) {
         const int fl = factor_of(i);
-        return fl < P.count ? __ldg(reinterpret_cast<const int2*>(table + fl)) : make_int2(0, 0);
+        return fl >= 0 ? __ldg(reinterpret_cast<const int2*>(table + fl)) : make_int2(0, 0);
     };
     auto issue = [&](int i, int s, int2 ids) {  // one lane: bulk copies of factor i into stage s
         const int fl = factor_of(i);
-        if (fl >= P.count) return;
+        if (fl < 0) return;
         unsigned char* st = slots + (size_t)s * L.bytes;
         fence_proxy_async();
         mbar_arrive_expect_tx(&bar[s], (uint32_t)((int)sizeof(Row) + L.b0 + L.b1 + L.mb));
@@ -354,17 +428,20 @@ __global__ void __launch_bounds__(FT * 32, Fam::kMinCtas) eval_kernel_w(const __
     __syncwarp();
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (!(P.flags & ROME_B200_INDEPENDENT)) asm volatile("griddepcontrol.wait;" ::: "memory");  // see eval_kernel
+    if (P.flags & ROME_B200_BARRIER_WAIT) fused_barrier_wait(P);
     if (lane < S) issue(lane, lane, ids);
 
     int s = 0;
     uint32_t phase = 0;
     for (int i = 0;; ++i) {
         const int fl = factor_of(i);
-        if (fl >= P.count) break;
+        if (fl < 0) break;
+        const int f = P.first + fl;
+        unsigned long long fdst = 0;  // owner-sharded exchange: per-factor destination of the forward row
+        if ((flags & ROME_B200_PROPOSAL_FWD) && P.fwd_dst) fdst = __ldg(P.fwd_dst + f);
         if (lane == s) ids = fetch_ids(i + S);  // consumed when this factor is done: hidden behind its arithmetic
         mbar_wait(&bar[s], phase);
         const unsigned char* st = slots + (size_t)s * L.bytes;
-        const int f = P.first + fl;
         const Row row = *reinterpret_cast<const Row*>(st + L.row_off);
         FactorView V;
         V.b0 = st + L.v0_off;
@@ -372,8 +449,7 @@ __global__ void __launch_bounds__(FT * 32, Fam::kMinCtas) eval_kernel_w(const __
         V.meas = kSample ? nullptr : reinterpret_cast<const float*>(st + L.meas_off);
         V.out_res = out;
         V.out_fwd = out + res_floats;
-        unsigned long long fdst = 0;  // owner-sharded exchange: per-factor destination of the forward row
-        if ((flags & ROME_B200_PROPOSAL_FWD) && P.fwd_dst && lane == 0) fdst = __ldg(P.fwd_dst + f);
+        V.fwd_on = !(P.flags & ROME_B200_ROUTED_ONLY) || fdst != 0;
         if (flags & (ROME_B200_RESIDUAL | ROME_B200_PROPOSAL_FWD)) {
             if (lane == 0) tma_store_wait_read();  // the previous factor's rows have left the slice
             __syncwarp();
@@ -385,7 +461,7 @@ __global__ void __launch_bounds__(FT * 32, Fam::kMinCtas) eval_kernel_w(const __
             if (lane == 0) {
                 if (flags & ROME_B200_RESIDUAL)
                     tma_store_1d(P.res + (size_t)f * res_floats, V.out_res, (uint32_t)(res_floats * 4));
-                if (flags & ROME_B200_PROPOSAL_FWD) {
+                if ((flags & ROME_B200_PROPOSAL_FWD) && V.fwd_on) {
                     const size_t off = (size_t)f * Fam::DFWD * P.Npad;
                     const uint32_t bytes = (uint32_t)(Fam::DFWD * P.Npad * 4);
                     tma_store_1d(fdst ? reinterpret_cast<float*>(fdst) : P.prop_fwd + off, V.out_fwd, bytes);
@@ -400,6 +476,7 @@ __global__ void __launch_bounds__(FT * 32, Fam::kMinCtas) eval_kernel_w(const __
     }
     if (lane == 0) tma_store_wait_all();
     if (P.flags & ROME_B200_INDEPENDENT) asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (P.flags & ROME_B200_BARRIER_SIGNAL) fused_barrier_signal(P);
 }
 
 template <class K>

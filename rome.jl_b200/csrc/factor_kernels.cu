@@ -71,7 +71,7 @@ int plan_launch(int family, uint32_t flags, int Npad, int smem_per_sm, int smem_
     const bool sample = (flags & ROME_B200_SAMPLE) != 0;
     const bool se3 = fd.d0 == 6;  // Pose3 families: one CTA per SM (register budget)
     if (fd.dfwd == 0) flags &= ~ROME_B200_PROPOSAL_FWD;
-    const uint32_t out_flags = flags & ~(ROME_B200_SAMPLE | ROME_B200_INDEPENDENT);
+    const uint32_t out_flags = flags & ~kSchedFlags;
     const int hot = out_flags == kHot1 ? 1 : out_flags == kHot2 ? 2 : 0;
     plan->pipeline = 0;
     if (se3 && pipeline_choice() == 1) {

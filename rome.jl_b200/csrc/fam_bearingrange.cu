@@ -20,7 +20,7 @@ struct FamBearingRange {
                                                   int lane) {
         constexpr int DZ = 2;
         const int Npad = P.Npad, N = P.N;
-        const uint32_t flags = kStatic ? kStatic : P.flags;
+        const uint32_t flags = (kStatic ? kStatic : P.flags) & (V.fwd_on ? ~0u : ~ROME_B200_PROPOSAL_FWD);
         const double* ap = reinterpret_cast<const double*>(V.b0);
         const double* al = reinterpret_cast<const double*>(V.b1);
         const float* Pp = reinterpret_cast<const float*>(V.b0 + var_header_bytes(3));

@@ -26,7 +26,7 @@ struct FamPoint2Gauss {
                                                   int lane) {
         constexpr int DZ = 2;
         const int Npad = P.Npad, N = P.N;
-        const uint32_t flags = kStatic ? kStatic : P.flags;
+        const uint32_t flags = (kStatic ? kStatic : P.flags) & (V.fwd_on ? ~0u : ~ROME_B200_PROPOSAL_FWD);
         const double* a0 = reinterpret_cast<const double*>(V.b0);
         const double* a1 = reinterpret_cast<const double*>(KIND == 0 ? V.b0 : V.b1);
         const float* X0 = reinterpret_cast<const float*>(V.b0 + var_header_bytes(D0));
@@ -103,7 +103,7 @@ struct FamScalar {
                                                   int lane) {
         constexpr int DZ = 1;
         const int Npad = P.Npad, N = P.N;
-        const uint32_t flags = kStatic ? kStatic : P.flags;
+        const uint32_t flags = (kStatic ? kStatic : P.flags) & (V.fwd_on ? ~0u : ~ROME_B200_PROPOSAL_FWD);
         const double* a0 = reinterpret_cast<const double*>(V.b0);
         const double* a1 = reinterpret_cast<const double*>(V.b1);
         const float* X0 = reinterpret_cast<const float*>(V.b0 + var_header_bytes(D0));

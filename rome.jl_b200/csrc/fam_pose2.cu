@@ -23,7 +23,7 @@ struct FamPose2Pose2 {
                                                   int lane) {
         constexpr int DZ = 3;
         const int Npad = P.Npad, N = P.N;
-        const uint32_t flags = kStatic ? kStatic : P.flags;
+        const uint32_t flags = (kStatic ? kStatic : P.flags) & (V.fwd_on ? ~0u : ~ROME_B200_PROPOSAL_FWD);
         const double* ap = reinterpret_cast<const double*>(V.b0);  // {x, y, theta, cos, sin}
         const double* aq = reinterpret_cast<const double*>(V.b1);
         const float* Pp = reinterpret_cast<const float*>(V.b0 + var_header_bytes(3));
@@ -179,7 +179,7 @@ struct FamPriorPose2 {
                                                   int lane) {
         constexpr int DZ = 3;
         const int Npad = P.Npad, N = P.N;
-        const uint32_t flags = kStatic ? kStatic : P.flags;
+        const uint32_t flags = (kStatic ? kStatic : P.flags) & (V.fwd_on ? ~0u : ~ROME_B200_PROPOSAL_FWD);
         const double* ap = reinterpret_cast<const double*>(V.b0);
         const float* Pp = reinterpret_cast<const float*>(V.b0 + var_header_bytes(3));
         // mean relative to the variable's anchor

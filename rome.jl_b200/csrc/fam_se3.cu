@@ -12,7 +12,7 @@ struct FamPose3Pose3 {
     static __device__ __forceinline__ void factor(const Row& row, const EvalParams& P, const FactorView& V, int f,
                                                   int lane) {
         const int Npad = P.Npad, N = P.N;
-        const uint32_t flags = kStatic ? kStatic : P.flags;
+        const uint32_t flags = (kStatic ? kStatic : P.flags) & (V.fwd_on ? ~0u : ~ROME_B200_PROPOSAL_FWD);
         const double* ap = reinterpret_cast<const double*>(V.b0);
         const double* aq = reinterpret_cast<const double*>(V.b1);
         const float* Pp = reinterpret_cast<const float*>(V.b0 + var_header_bytes(6));
@@ -145,7 +145,7 @@ struct FamPriorPose3 {
     static __device__ __forceinline__ void factor(const Row& row, const EvalParams& P, const FactorView& V, int f,
                                                   int lane) {
         const int Npad = P.Npad, N = P.N;
-        const uint32_t flags = kStatic ? kStatic : P.flags;
+        const uint32_t flags = (kStatic ? kStatic : P.flags) & (V.fwd_on ? ~0u : ~ROME_B200_PROPOSAL_FWD);
         const double* ap = reinterpret_cast<const double*>(V.b0);
         const float* Pp = reinterpret_cast<const float*>(V.b0 + var_header_bytes(6));
         const size_t fo = (size_t)f * 6 * Npad;

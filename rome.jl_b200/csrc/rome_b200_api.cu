@@ -82,6 +82,10 @@ struct rome_b200_ctx {
     int row_dst_n[ROME_B200_NFAMILIES][2] = {};  // number of factors they cover (0 = not set)
     Scratch halo_src[ROME_B200_NVARTYPES], halo_dst[ROME_B200_NVARTYPES];
     int halo_n[ROME_B200_NVARTYPES] = {};
+    uint32_t* bar_state = nullptr;   // fused step barrier (rome_b200_set_step_barrier)
+    uint32_t* bar_peer[7] = {};
+    int bar_n = 0;
+    int owned[ROME_B200_NVARTYPES] = {-1, -1, -1, -1};  // variables [0, owned) are updated by product / reanchor (-1: all)
     std::vector<cudaGraphExec_t> graphs;
     std::vector<uint64_t> graph_kernels;
     bool capturing = false;
@@ -597,6 +601,15 @@ int rome_b200_eval(rome_b200_ctx* ctx, int family, uint32_t flags, uint64_t seed
             return fail(ctx, ROME_B200_SHAPE_MISMATCH, "proposal destinations were set for a different number of factors");
         (dir ? p.bwd_dst : p.fwd_dst) = static_cast<const unsigned long long*>(ctx->row_dst[family][dir].p);
     }
+    p.bar_state = ctx->bar_state; p.bar_n = ctx->bar_n; p.bar_timeout = 0;
+    for (int r = 0; r < 7; ++r) p.bar_peer[r] = ctx->bar_peer[r];
+    if (flags & (ROME_B200_BARRIER_WAIT | ROME_B200_BARRIER_SIGNAL)) {
+        if (!ctx->bar_state || ctx->bar_n == 0)
+            return fail(ctx, ROME_B200_NOT_SET, "BARRIER_WAIT / BARRIER_SIGNAL need rome_b200_set_step_barrier");
+        int clock_khz = 0;
+        cudaDeviceGetAttribute(&clock_khz, cudaDevAttrClockRate, ctx->device);
+        p.bar_timeout = 2LL * 1000LL * (clock_khz > 0 ? clock_khz : 1965000);  // ~2 s
+    }
     p.flags = flags;
     p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32); p.stream_id = stream_id;
     LaunchPlan plan;
@@ -712,7 +725,8 @@ int rome_b200_product(rome_b200_ctx* ctx, int vartype, int n_bufs, const float* 
     const ProductPlan& pl = ctx->plan[vartype];
     VarStore& vs = ctx->vars[vartype];
     if (vs.nvars == 0) return fail(ctx, ROME_B200_NOT_SET, "particles of this variable type are not set");
-    if (pl.nvars != vs.nvars) return fail(ctx, ROME_B200_NOT_SET, "no product plan for this variable type (or its size differs)");
+    const int nown = (ctx->owned[vartype] >= 0 && ctx->owned[vartype] < vs.nvars) ? ctx->owned[vartype] : vs.nvars;
+    if (pl.nvars != nown) return fail(ctx, ROME_B200_NOT_SET, "no product plan for this variable type (or its size differs)");
     if (n_bufs < 0 || n_bufs > ROME_B200_MAX_PRODUCT_BUFFERS || pl.max_buf >= n_bufs || (n_bufs > 0 && !d_prop_bufs))
         return fail(ctx, ROME_B200_BAD_ARG, "the plan refers to more proposal buffers than were passed");
     for (int b = 0; b <= pl.max_buf; ++b)
@@ -727,7 +741,7 @@ int rome_b200_product(rome_b200_ctx* ctx, int vartype, int n_bufs, const float* 
     p.src_row = static_cast<const int32_t*>(pl.row.p);
     for (int b = 0; b < n_bufs; ++b) p.bufs[b] = d_prop_bufs[b];
     p.bw_out = d_bw_out;
-    p.nvars = vs.nvars; p.N = vs.N; p.Npad = vs.Npad;
+    p.nvars = nown; p.N = vs.N; p.Npad = vs.Npad;
     p.iters = gibbs_iters > 0 ? gibbs_iters : 2;
     p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32); p.stream_id = stream_id;
     p.bw_scale = (float)std::pow(4.0 / ((d + 2.0) * vs.N), 1.0 / (d + 4.0));
@@ -744,7 +758,8 @@ int rome_b200_reanchor(rome_b200_ctx* ctx, int vartype) {
     VarStore& vs = ctx->vars[vartype];
     if (vs.nvars == 0) return fail(ctx, ROME_B200_NOT_SET, "particles of this variable type are not set");
     if (int e = bind(ctx)) return e;
-    int e = launch_reanchor(kVarDim[vartype], kWrapDim[vartype], vs.store, vs.nvars, vs.N, vs.Npad, ctx->stream);
+    const int nown = (ctx->owned[vartype] >= 0 && ctx->owned[vartype] < vs.nvars) ? ctx->owned[vartype] : vs.nvars;
+    int e = launch_reanchor(kVarDim[vartype], kWrapDim[vartype], vs.store, nown, vs.N, vs.Npad, ctx->stream);
     if (e) return cuda_fail(ctx, (cudaError_t)e, "reanchor kernel launch");
     if (ctx->capturing) ctx->capture_kernels++; else ctx->launches++;
     return ROME_B200_OK;
@@ -781,6 +796,23 @@ int rome_b200_set_proposal_destinations(rome_b200_ctx* ctx, int family, int dire
     CK(cudaMemcpyAsync(sc.p, rows, (size_t)nF * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));  // the caller's array may be a temporary
     ctx->row_dst_n[family][direction] = nF;
+    return ROME_B200_OK;
+}
+int rome_b200_set_step_barrier(rome_b200_ctx* ctx, void* d_state, uint32_t* const* peer_slots, int n_peers) {
+    if (!ctx) return ROME_B200_BAD_ARG;
+    if (n_peers == 0) { ctx->bar_state = nullptr; ctx->bar_n = 0; return ROME_B200_OK; }
+    if (!d_state || n_peers < 0 || n_peers > 7 || !peer_slots) return fail(ctx, ROME_B200_BAD_ARG, "bad peer list");
+    for (int r = 0; r < n_peers; ++r)
+        if (!peer_slots[r]) return fail(ctx, ROME_B200_BAD_ARG, "peer slot is NULL");
+    ctx->bar_state = static_cast<uint32_t*>(d_state);
+    ctx->bar_n = n_peers;
+    for (int r = 0; r < 7; ++r) ctx->bar_peer[r] = r < n_peers ? peer_slots[r] : nullptr;
+    return ROME_B200_OK;
+}
+int rome_b200_set_owned_variables(rome_b200_ctx* ctx, int vartype, int n_owned) {
+    if (!ctx) return ROME_B200_BAD_ARG;
+    if (vartype < 0 || vartype >= ROME_B200_NVARTYPES) return fail(ctx, ROME_B200_BAD_ARG, "bad vartype");
+    ctx->owned[vartype] = n_owned < 0 ? -1 : n_owned;
     return ROME_B200_OK;
 }
 int rome_b200_set_halo_plan(rome_b200_ctx* ctx, int vartype, int n, const int32_t* src_var, void* const* dst_blocks) {

@@ -87,7 +87,17 @@ struct EvalParams {
     // into a peer GPU's memory; 0 = the default row of prop_fwd / prop_bwd); arrays indexed by factor id, or null
     const unsigned long long* fwd_dst;
     const unsigned long long* bwd_dst;
+    // rank barrier fused into the launch (ROME_B200_BARRIER_WAIT / _SIGNAL): this rank's state words, the slot it owns
+    // in every peer's state, the number of peers, and the give-up limit of the wait in clock cycles
+    uint32_t* bar_state;
+    uint32_t* bar_peer[7];
+    int bar_n;
+    long long bar_timeout;
 };
+// flags that change scheduling / routing only, never which outputs a launch computes (ignored when a compile-time
+// flag variant is selected)
+constexpr uint32_t kSchedFlags = ROME_B200_SAMPLE | ROME_B200_INDEPENDENT | ROME_B200_ROUTED_ONLY |
+                                 ROME_B200_BARRIER_WAIT | ROME_B200_BARRIER_SIGNAL;
 // row of the backward proposal of factor f (row_floats = dbwd * Npad)
 __host__ __device__ inline float* bwd_row(const EvalParams& P, int f, size_t row_floats) {
     if (P.bwd_dst) {

@@ -318,6 +318,15 @@ class Context:
         arr = (C.c_void_p * max(1, n))(*[int(p) or None for p in row_ptrs])
         self._ck(self._lib.rome_b200_set_proposal_destinations(self._h, family, direction, n, arr))
 
+    def set_step_barrier(self, state_ptr: int, peer_slot_ptrs):
+        """rank barrier fused into eval launches flagged BARRIER_WAIT / BARRIER_SIGNAL; [] clears"""
+        arr = (C.c_void_p * max(1, len(peer_slot_ptrs)))(*peer_slot_ptrs)
+        self._ck(self._lib.rome_b200_set_step_barrier(self._h, state_ptr or None, arr, len(peer_slot_ptrs)))
+
+    def set_owned_variables(self, vartype: int, n_owned: int):
+        """product / reanchor update only variables [0, n_owned) (the rest are halo copies); -1: all"""
+        self._ck(self._lib.rome_b200_set_owned_variables(self._h, vartype, n_owned))
+
     def set_halo_plan(self, vartype: int, src_vars, dst_block_ptrs):
         src = _i32(src_vars)
         arr = (C.c_void_p * max(1, len(src)))(*[int(p) for p in dst_block_ptrs])

@@ -434,9 +434,15 @@ def initAll(fg: FactorGraph, seed=0, ctx: Context | None = None):
                     vs[0].val = approxConv(fg, f.label, vs[0].label, seed=seed + k, ctx=ctx)
                     progress, k = True, k + 1
             elif vs[0].initialized and not vs[1].initialized:
+                if FAMILY[f.fnc.family][6] == 0:
+                    continue  # no closed-form root toward the last variable (ranges, bearing, partial Pose3): defer it
                 vs[1].val = approxConv(fg, f.label, vs[1].label, seed=seed + k, ctx=ctx)
                 progress, k = True, k + 1
-            elif vs[1].initialized and not vs[0].initialized and not isinstance(f.fnc, Pose2Point2BearingRange):
+            elif vs[1].initialized and not vs[0].initialized:
+                # a backward root that needs no starting point exists for Pose2Pose2 / Pose3Pose3 only (BearingRange's
+                # keeps the pose's current heading, the point / scalar families have none): defer the variable otherwise
+                if FAMILY[f.fnc.family][7] == 0 or isinstance(f.fnc, Pose2Point2BearingRange):
+                    continue
                 vs[0].val = approxConv(fg, f.label, vs[0].label, seed=seed + k, ctx=ctx)
                 progress, k = True, k + 1
     return fg

@@ -28,6 +28,7 @@ const PRIORPOINT3, POINT3POINT3, POSE3POSE3XYYAW, POSE3POSE3ROTATION, POSE3POSE3
     Cint(11), Cint(12), Cint(13), Cint(14), Cint(15)
 const RESIDUAL, PROPOSAL_FWD, PROPOSAL_BWD, STATS, SAMPLE, WRITE_MEAS, JACOBIAN, INDEPENDENT, DECONV, PRECISE =
     UInt32(1), UInt32(2), UInt32(4), UInt32(8), UInt32(16), UInt32(32), UInt32(64), UInt32(128), UInt32(256), UInt32(512)
+const ROUTED_ONLY, BARRIER_WAIT, BARRIER_SIGNAL = UInt32(1024), UInt32(2048), UInt32(4096)
 const PRODUCT_REANCHOR = UInt32(1)
 
 struct Buffers            # struct rome_b200_buffers

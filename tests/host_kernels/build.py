@@ -98,7 +98,7 @@ def build_peer(outdir):
     __syncthreads is the warp rendezvous and threadIdx the lane; release / acquire accesses become volatile accesses"""
     os.makedirs(outdir, exist_ok=True)
     pk = _read("peer_kernels.cu")
-    body = pk[pk.index("struct PeerSlots {"):pk.index("int launch_peer_signal(")]
+    body = pk[pk.index("struct PeerSlots {"):pk.index("template <class K, class... A>\nstatic int launch_one_warp_pdl")]
     body, n1 = re.subn(r'asm volatile\("st\.release\.sys\.global\.u32 \[%0\], %1;" ::"l"\((.+?)\), "r"\((\w+)\) : "memory"\);',
                        r"*(volatile uint32_t*)(\1) = \2; ++hk::g_progress;", body)
     body, n2 = re.subn(r'asm volatile\("ld\.acquire\.sys\.global\.u32 %0, \[%1\];" : "=r"\((\w+)\) : "l"\((.+?)\) : "memory"\);',
@@ -106,9 +106,7 @@ def build_peer(outdir):
     body, n3 = re.subn(r'asm volatile\("griddepcontrol\.[a-z_]+;" ::: "memory"\);', "", body)
     assert n1 == 1 and n2 == 1 and n3 == 4 and "asm" not in body
     text = ('#include "hk_shim.h"\n#undef threadIdx\n#define threadIdx (dim3_{(unsigned)(hk::g_cur & 31), 0, 0})\n'
-            "#define __syncthreads() hk::collective(0u)\n#define __threadfence_system()\n#define __nanosleep(ns) hk::yield_()\n"
-            "static long long hk_clock = 0;\n#define clock64() (++hk_clock)\n"
-            "static inline uint32_t atomicExch(uint32_t* p, uint32_t v) { const uint32_t o = *p; *p = v; return o; }\n"
+            "#define __syncthreads() hk::collective(0u)\n#define __nanosleep(ns) hk::yield_()\n"
             "namespace rome {\n" + body + open(os.path.join(HERE, "hk_peer_main.inc")).read() + "}\n")
     src, so = os.path.join(outdir, "host_peer.cpp"), os.path.join(outdir, "libhost_peer.so")
     open(src, "w").write(text)

@@ -168,7 +168,8 @@ class EmulatedContext:
         assert rows["ip"].max() < nvars and (vt1 is None or (rows["iq"].max() < self._shape[vt1][0] and self._shape[vt1][1] == N))
         # compile-time flag variants exist where the planner picks the 8-factor tile (or the per-warp pipeline), as in
         # plan_launch / launch_sample of the library
-        out_flags = (flags if dfwd else flags & ~L.PROPOSAL_FWD) & ~(L.SAMPLE | L.INDEPENDENT)
+        out_flags = (flags if dfwd else flags & ~L.PROPOSAL_FWD) & ~(L.SAMPLE | L.INDEPENDENT | L.ROUTED_ONLY |
+                                                                       L.BARRIER_WAIT | L.BARRIER_SIGNAL)
         hot = 1 if out_flags == (L.RESIDUAL | L.STATS) else 2 if out_flags == (L.RESIDUAL | L.STATS | L.PROPOSAL_FWD) else 0
         plan = rb.plan_query(family, flags, N)
         variant = hot if (plan["warps"] == 8 or plan["pipeline"] == 1) else 0

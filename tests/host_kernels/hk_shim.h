@@ -208,7 +208,14 @@ static inline int min(int a, int b) { return a < b ? a : b; }
 // The 64-bit barrier word holds {phase bit, pending arrivals, pending transaction bytes, arrival count of a phase}; a
 // bulk load is performed at once (one legal schedule of the asynchronous copy) and completes its bytes on the barrier;
 // a phase completes when both pending counts reach zero.  try_wait.parity(p) succeeds once the phase of parity p is over.
+static long long hk_clock_ticks = 0;
+static inline long long clock64() { return ++hk_clock_ticks; }
+static inline void __threadfence_system() {}
+static inline uint32_t atomicAdd(uint32_t* p, uint32_t v) { const uint32_t o = *p; *p = o + v; return o; }
+static inline uint32_t atomicExch(uint32_t* p, uint32_t v) { const uint32_t o = *p; *p = v; return o; }
 namespace rome {
+static inline void st_release_sys_u32(uint32_t* p, uint32_t v) { *(volatile uint32_t*)p = v; ++hk::g_progress; }
+static inline uint32_t ld_acquire_sys_u32(const uint32_t* p) { hk::yield_(); return *(volatile const uint32_t*)p; }
 struct HkBar { uint8_t phase, expected; int16_t pending; int32_t tx; };
 static_assert(sizeof(HkBar) <= 8, "an emulated mbarrier must fit the kernel's 8-byte barrier slot");
 static inline void hk_bar_check(HkBar* b) {
