@@ -396,6 +396,7 @@ def main():
                 ptrs = [0] * f["n_interior"] + [recv_ptr[int(d)][fam] + int(r) * rowb
                                                 for d, r in zip(f["dst_rank"], f["dst_row"])]
                 c.set_proposal_destinations(fam, 0, ptrs)
+                c.set_interior_count(fam, f["n_interior"])   # the rank barrier is only passed before the first cut factor
                 if fam not in dummy_fwd:  # default rows of prop_fwd are never written for the cut range; one shared buffer
                     dummy_fwd[fam] = torch.zeros((len(f["i0"]), Np, dfwd), device="cuda")
             for vt, pushes in lv["loc"]["push"].items():

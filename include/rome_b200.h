@@ -107,7 +107,14 @@ enum rome_b200_family {
 #define ROME_B200_STATS 8u        /* per-factor statistics (warp-shuffle reductions)                 */
 #define ROME_B200_SAMPLE 16u      /* getSample fused in-kernel (Philox4x32-10); `meas` is not read   */
 #define ROME_B200_WRITE_MEAS 32u  /* with SAMPLE: also store the drawn measurement offsets            */
-#define ROME_B200_JACOBIAN 64u    /* compact analytic Jacobian blocks                */
+#define ROME_B200_JACOBIAN 64u    /* compact analytic Jacobian blocks, dj floats per particle (rome_b200_family_dims):
+                                     Pose2Pose2 (4): d r_t/d theta_p = (-ry, rx), (cos, sin) of theta_p [d r/d m = R(theta_p) (+) 1];
+                                     BearingRange (4): d r1/d l, d r2/d l;
+                                     Pose3Pose3 (36), perturbations t <- t + dt, R <- R Exp(delta), four row-major 3x3 blocks
+                                       A = d r_t/d delta_p = -R_p [m_t]x, B = d r_w/d delta_p = Jr^-1(r_w) M',
+                                       C = d r_w/d delta_q = -Jl^-1(r_w), R_p = d r_t/d m_t
+                                       (d r_t/d t_p = I, d r_t/d t_q = -I, d r_t/d delta_q = 0, d r_w/d m_w = B M);
+                                     PriorPose3 (9): d r_w/d delta_p = -Jl^-1(r_w) (d r_t/d t_p = -I)          */
 /* Scheduling hint: this launch reads nothing that was written by launches issued on the same ctx stream since the
  * last launch WITHOUT this flag (e.g. the family kernels of one Gibbs sweep: all read the same particle state and
  * write different buffers).  It is then launched with programmatic dependent launch and may start on SMs the
@@ -297,6 +304,11 @@ ROME_B200_API int rome_b200_push_halo(rome_b200_ctx* ctx, int vartype);
  * fused flags must not be interleaved on one state buffer except that a completed signal + wait PAIR of the kernels may
  * precede the first fused step (set-up barrier).  n_peers = 0 clears. */
 ROME_B200_API int rome_b200_set_step_barrier(rome_b200_ctx* ctx, void* d_state, uint32_t* const* peer_slots, int n_peers);
+/* Factors [0, n_interior) of the family read only variables this rank owns and write only local buffers (upload the
+ * table with the interior factors first): a launch flagged BARRIER_WAIT evaluates them right away and passes the barrier
+ * only before it fetches the first factor >= n_interior, so the barrier's latency hides behind the interior work.
+ * Default 0: the barrier is passed before anything is fetched. */
+ROME_B200_API int rome_b200_set_interior_count(rome_b200_ctx* ctx, int family, int n_interior);
 /* CUDA IPC plumbing for buffers allocated with rome_b200_malloc_device (64-byte opaque handles).  Only such buffers may
  * be exported: rome_b200_malloc_device hands out whole 2 MiB blocks, so the handle (which names the driver's block) and
  * the buffer coincide; a pointer into a packed small cudaMalloc allocation would be opened at the wrong address. */

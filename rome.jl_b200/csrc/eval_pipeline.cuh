@@ -150,46 +150,26 @@ constexpr int kBarrierBytes = 128;
 constexpr int kMaxStages = 6;
 
 // =============================================================================================
-// tile schedule of a persistent grid: `rounds` rounds in which EVERY CTA takes a full tile of FT factors (static round
-// robin), then ONE tail round in which the remaining factors are split evenly over the CTAs (m <= FT each) -- instead of
-// a last round of full tiles on a few CTAs while the others idle (12 000 factors on 296 CTAs: 5 rounds + 1 factor on
-// 160 CTAs instead of a 6th round on 20 CTAs).  Tile i of CTA b covers factors [first, first + nf) of the launch range.
-// =============================================================================================
-struct TileSched {
-    int rounds, tail_base, tail_m, rem, n;  // n = tiles of THIS CTA
-    __device__ __forceinline__ void init(int count, int ft, int grid, int b) {
-        rounds = (count / ft) / grid;
-        tail_base = rounds * grid * ft;
-        rem = count - tail_base;
-        tail_m = (rem + grid - 1) / grid;
-        n = rounds + ((tail_m > 0 && b * tail_m < rem) ? 1 : 0);
-    }
-    __device__ __forceinline__ int first(int i, int ft, int grid, int b) const {
-        return i < rounds ? (b + i * grid) * ft : tail_base + b * tail_m;
-    }
-    __device__ __forceinline__ int nf(int i, int ft, int b) const {
-        return i < rounds ? ft : min(tail_m, rem - b * tail_m);
-    }
-};
-
-// =============================================================================================
 // rank barrier fused into the evaluation kernels (owner-sharded multi-GPU sweeps; the state buffer is the one of
 // rome_b200_peer_signal / _wait: words [0, 8) flag slots written by the peers, word 8 this rank's signal epoch, word 10
 // give-up status, word 12 the CTA counter of the signalling launch).
-//   ROME_B200_BARRIER_WAIT   (first launch of a step): before the first particle block is fetched, every CTA polls the
-//       local flag slots until each peer has signalled as often as this rank has (word 8) -- the peers' previous step,
-//       with its stores into this GPU's memory, is complete.
+//   ROME_B200_BARRIER_WAIT   (first launch of a step): before the first factor >= bar_from (the first cut factor; 0 = every
+//       factor) is fetched, the fetching warp polls the local flag slots until each peer has signalled as often as this
+//       rank has (word 8) -- the peers' previous step, with its stores into this GPU's memory, is complete.
 //   ROME_B200_BARRIER_SIGNAL (last launch of a step): the CTA that finishes last publishes the next epoch to the slot
 //       this rank owns in every peer's state (st.release.sys after a system-scope fence: the rows this grid stored into
 //       peer memory are visible before the flag).
 // No extra kernel, no host round trip: the barrier costs the NVLink latency of a 4-byte store.
 // =============================================================================================
-__device__ __forceinline__ void fused_barrier_wait(const EvalParams& P) {
-    if (threadIdx.x < (unsigned)P.bar_n) {
+// executed by ONE WARP (the warp that fetches particle blocks), right before the first factor >= P.bar_from is fetched:
+// the factors in front of it -- a rank's interior factors -- neither read halo blocks nor write into peer memory, so
+// their evaluation overlaps the barrier's latency
+__device__ __forceinline__ void fused_barrier_wait(const EvalParams& P, int lane) {
+    if (lane < P.bar_n) {
         const uint32_t target = *reinterpret_cast<volatile const uint32_t*>(P.bar_state + 8);
         const long long t0 = clock64();
         for (;;) {
-            const uint32_t v = ld_acquire_sys_u32(P.bar_state + threadIdx.x);
+            const uint32_t v = ld_acquire_sys_u32(P.bar_state + lane);
             if ((int32_t)(v - target) >= 0) break;  // wrap-safe "v >= target"
             if (clock64() - t0 > P.bar_timeout) {    // a peer died: give up instead of hanging the GPU
                 atomicExch(P.bar_state + 10, 1u);
@@ -197,7 +177,7 @@ __device__ __forceinline__ void fused_barrier_wait(const EvalParams& P) {
             }
         }
     }
-    __syncthreads();
+    __syncwarp();
 }
 __device__ __forceinline__ void fused_barrier_signal(const EvalParams& P) {
     __syncthreads();  // every warp of this CTA has waited for its bulk stores
@@ -218,8 +198,13 @@ __device__ __forceinline__ void fused_barrier_signal(const EvalParams& P) {
 // persistent producer/consumer pipeline
 //   smem: [full[], empty[] mbarriers | S input stages | FT per-warp output slices]
 // =============================================================================================
+// (A warpgroup register re-allocation -- 384 threads, setmaxnreg.inc 104 for the two consumer warpgroups, .dec 24 for the
+// producer's -- was measured on B200 and is SLOWER than this 288-thread form at 96 registers: 16.6 vs 15.8 us per
+// launch of the bench workload; requesting more registers than the CTA was launched with hangs.  profiles/r02_analysis.md)
+template <int FT>
+constexpr int eval_threads() { return (FT + 1) * 32; }
 template <class Fam, uint32_t kStatic, bool kSample, int FT>
-__global__ void __launch_bounds__((FT + 1) * 32, Fam::kMinCtas) eval_kernel(const __grid_constant__ EvalParams P) {
+__global__ void __launch_bounds__(eval_threads<FT>(), Fam::kMinCtas) eval_kernel(const __grid_constant__ EvalParams P) {
     using Row = typename Fam::Row;
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
@@ -227,9 +212,7 @@ __global__ void __launch_bounds__((FT + 1) * 32, Fam::kMinCtas) eval_kernel(cons
     unsigned char* stage0 = smem + kBarrierBytes;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = P.stages;
-    const int grid = (int)gridDim.x, cta = (int)blockIdx.x;
-    TileSched T;
-    T.init(P.count, FT, grid, cta);
+    const int nTiles = (P.count + FT - 1) / FT;
     const StageLayout L = stage_layout(FT, (int)sizeof(Row), Fam::D0, Fam::D1, Fam::DM, kSample, P.Npad);
     const Row* __restrict__ table = reinterpret_cast<const Row*>(P.rows) + P.first;
     const uint32_t flags = kStatic ? kStatic : P.flags;
@@ -240,14 +223,14 @@ __global__ void __launch_bounds__((FT + 1) * 32, Fam::kMinCtas) eval_kernel(cons
     constexpr int TPC = 32 / FT;  // tiles per chunk
     const int jl = lane / FT, fl_in_tile = lane % FT;
     int2 ids_cur = make_int2(0, 0);
-    auto fetch_chunk = [&](int base_i) {
-        const int i = base_i + jl;
+    auto fetch_chunk = [&](int base_tile) {
+        const int t = base_tile + jl * (int)gridDim.x;
+        const int fl = t * FT + fl_in_tile;
         int2 ids = make_int2(0, 0);
-        if (i < T.n && fl_in_tile < T.nf(i, FT, cta))
-            ids = __ldg(reinterpret_cast<const int2*>(table + T.first(i, FT, grid, cta) + fl_in_tile));
+        if (t < nTiles && fl < P.count) ids = __ldg(reinterpret_cast<const int2*>(table + fl));
         return ids;
     };
-    if (warp == FT) ids_cur = fetch_chunk(0);
+    if (warp == FT) ids_cur = fetch_chunk(blockIdx.x);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
@@ -265,22 +248,26 @@ __global__ void __launch_bounds__((FT + 1) * 32, Fam::kMinCtas) eval_kernel(cons
     // flagged ROME_B200_INDEPENDENT touches no such data and defers that wait to its end.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (!(P.flags & ROME_B200_INDEPENDENT)) asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (P.flags & ROME_B200_BARRIER_WAIT) fused_barrier_wait(P);  // the peers' previous step has landed in this GPU's memory
 
     if (warp == FT) {
         // ---------------- producer warp ---------------------------------------------------------------------
         int s = 0;
         uint32_t phase = 1;  // parity of the previous round; the first pass over the ring does not wait
         bool first_round = true;
-        for (int base = 0; base < T.n; base += TPC) {
-            const int2 ids_next = fetch_chunk(base + TPC);  // in flight while this chunk is issued
+        bool synced = !(P.flags & ROME_B200_BARRIER_WAIT);  // rank barrier still to be passed?
+        for (int base = blockIdx.x; base < nTiles; base += TPC * gridDim.x) {
+            const int2 ids_next = fetch_chunk(base + TPC * gridDim.x);  // in flight while this chunk is issued
 #pragma unroll 1
             for (int j = 0; j < TPC; ++j) {
-                const int i = base + j;
-                if (i >= T.n) break;
+                const int tile = base + j * gridDim.x;
+                if (tile >= nTiles) break;
                 if (!first_round) mbar_wait(&empty[s], phase);
                 unsigned char* st = stage0 + (size_t)s * L.bytes;
-                const int t0 = T.first(i, FT, grid, cta), nf = T.nf(i, FT, cta);
+                const int t0 = tile * FT, nf = min(FT, P.count - tile * FT);
+                if (!synced && P.first + t0 + nf > P.bar_from) {  // the peers' previous step must have landed from here on
+                    fused_barrier_wait(P, lane);
+                    synced = true;
+                }
                 if (lane == j * FT) {
                     fence_proxy_async();
                     mbar_arrive_expect_tx(&full[s], (uint32_t)(nf * ((int)sizeof(Row) + L.b0 + L.b1 + L.mb)));
@@ -307,9 +294,10 @@ __global__ void __launch_bounds__((FT + 1) * 32, Fam::kMinCtas) eval_kernel(cons
         const int res_floats = Fam::DR * P.Npad;
         int s = 0;
         uint32_t phase = 0;
-        for (int i = 0; i < T.n; ++i) {
-            const bool mine = warp < T.nf(i, FT, cta);
-            const int f = P.first + T.first(i, FT, grid, cta) + warp;
+        for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
+            const int fl = tile * FT + warp;
+            const bool mine = fl < P.count;
+            const int f = P.first + fl;
             // owner-sharded exchange: this factor's forward row may have its own destination (a peer GPU); requested
             // before the wait for the stage so that the load's latency hides behind it (warp-uniform address)
             unsigned long long fdst = 0;
@@ -389,9 +377,6 @@ __global__ void __launch_bounds__(FT * 32, Fam::kMinCtas) eval_kernel_w(const __
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = P.stages;
-    const int grid = (int)gridDim.x, cta = (int)blockIdx.x;
-    TileSched T;
-    T.init(P.count, FT, grid, cta);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem) + warp * kMaxStages;
     const SlotLayout L = slot_layout((int)sizeof(Row), Fam::D0, Fam::D1, Fam::DM, kSample, P.Npad);
     const int warp_bytes = S * L.bytes + P.out_warp_bytes;
@@ -400,8 +385,11 @@ __global__ void __launch_bounds__(FT * 32, Fam::kMinCtas) eval_kernel_w(const __
     const Row* __restrict__ table = reinterpret_cast<const Row*>(P.rows) + P.first;
     const uint32_t flags = kStatic ? kStatic : P.flags;
     const int res_floats = Fam::DR * P.Npad;
-    // the i-th factor of this warp: slot `warp` of the CTA's i-th tile (-1: none)
-    auto factor_of = [&](int i) { return (i < T.n && warp < T.nf(i, FT, cta)) ? T.first(i, FT, grid, cta) + warp : -1; };
+    // the i-th factor of this warp: tile blockIdx.x + i * gridDim.x, slot `warp` (-1: none)
+    auto factor_of = [&](int i) {
+        const int fl = (blockIdx.x + i * (int)gridDim.x) * FT + warp;
+        return fl < P.count ? fl : -1;
+    };
     auto fetch_ids = [&](int i) {
         const int fl = factor_of(i);
         return fl >= 0 ? __ldg(reinterpret_cast<const int2*>(table + fl)) : make_int2(0, 0);
@@ -428,7 +416,15 @@ __global__ void __launch_bounds__(FT * 32, Fam::kMinCtas) eval_kernel_w(const __
     __syncwarp();
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (!(P.flags & ROME_B200_INDEPENDENT)) asm volatile("griddepcontrol.wait;" ::: "memory");  // see eval_kernel
-    if (P.flags & ROME_B200_BARRIER_WAIT) fused_barrier_wait(P);
+    bool synced = !(P.flags & ROME_B200_BARRIER_WAIT);  // rank barrier still to be passed (every warp fetches for itself)
+    auto sync_before = [&](int i) {
+        const int fl = factor_of(i);
+        if (!synced && fl >= 0 && P.first + fl >= P.bar_from) {
+            fused_barrier_wait(P, lane);
+            synced = true;
+        }
+    };
+    for (int i = 0; i < S; ++i) sync_before(i);
     if (lane < S) issue(lane, lane, ids);
 
     int s = 0;
@@ -471,6 +467,7 @@ __global__ void __launch_bounds__(FT * 32, Fam::kMinCtas) eval_kernel_w(const __
             }
         }
         __syncwarp();  // every lane has finished reading stage s
+        sync_before(i + S);
         if (lane == s) issue(i + S, s, ids);
         if (++s == S) { s = 0; phase ^= 1u; }
     }
@@ -504,7 +501,7 @@ int launch_kernel_cfg(K k, int* configured, int threads, const EvalParams& p, co
 template <class Fam, uint32_t kStatic, bool kSample, int FT>
 int launch_ft(const EvalParams& p, const LaunchPlan& plan, int grid, cudaStream_t s) {
     static int configured[64] = {0};  // per-instantiation, per-device cache of the opt-in shared memory size
-    return launch_kernel_cfg(eval_kernel<Fam, kStatic, kSample, FT>, configured, (FT + 1) * 32, p, plan, grid, s);
+    return launch_kernel_cfg(eval_kernel<Fam, kStatic, kSample, FT>, configured, eval_threads<FT>(), p, plan, grid, s);
 }
 template <class Fam, uint32_t kStatic, bool kSample, int FT>
 int launch_ft_w(const EvalParams& p, const LaunchPlan& plan, int grid, cudaStream_t s) {

@@ -108,6 +108,32 @@ struct FamPose3Pose3 {
                                         (float)(ox - row.mu[3]), (float)(oy - row.mu[4]), (float)(oz - row.mu[5])};
                     store6_global(P.meas_out + fo + 6 * n, o);
                 }
+                if ((flags & ROME_B200_JACOBIAN) && live) {
+                    // 36 floats per particle, four row-major 3x3 blocks (perturbations t <- t + dt, R <- R Exp(delta)):
+                    //   A = d r_t / d delta_p = -R_p [m_t]x      B = d r_w / d delta_p = Jr^-1(r_w) M'
+                    //   C = d r_w / d delta_q = -Jl^-1(r_w)      R_p = d r_t / d m_t
+                    // (d r_t / d t_p = I, d r_t / d t_q = -I, d r_t / d delta_q = 0, d r_w / d m_w = B M)
+                    double Rm[9], Mm[9], Jr[9], Jl[9], A[9], B[9];
+                    quat_to_rot(Rp[j], Rm);
+                    quat_to_rot(M[j], Mm);
+                    const double rx = kl[j] * E[j].x, ry = kl[j] * E[j].y, rz = kl[j] * E[j].z;
+                    so3_jinv(rx, ry, rz, 1.0, Jr);
+                    so3_jinv(rx, ry, rz, -1.0, Jl);
+                    const double mx = X[j][0], my = X[j][1], mz = X[j][2];
+                    const double K[9] = {0.0, -mz, my, mz, 0.0, -mx, -my, mx, 0.0};  // [m_t]x
+#pragma unroll
+                    for (int a = 0; a < 3; ++a)
+#pragma unroll
+                        for (int b = 0; b < 3; ++b) {
+                            A[3 * a + b] = -(Rm[3 * a] * K[b] + Rm[3 * a + 1] * K[3 + b] + Rm[3 * a + 2] * K[6 + b]);
+                            B[3 * a + b] = Jr[3 * a] * Mm[3 * b] + Jr[3 * a + 1] * Mm[3 * b + 1] + Jr[3 * a + 2] * Mm[3 * b + 2];
+                        }
+                    float* J = P.jac + ((size_t)f * Npad + n) * 36;
+                    store9_global(J, A, 1.0);
+                    store9_global(J + 9, B, 1.0);
+                    store9_global(J + 18, Jl, -1.0);
+                    store9_global(J + 27, Rm, 1.0);
+                }
                 if (flags & ROME_B200_PROPOSAL_FWD) {  // q = p o Exp(X): coordinates as offsets from q's anchor
                     double ox, oy, oz;
                     quat_log_any(Rh[j], ox, oy, oz);
@@ -181,6 +207,11 @@ struct FamPriorPose3 {
 #pragma unroll
                     for (int i = 0; i < 6; ++i) o[i] = (float)((ap[i] + (double)p[i]) - row.mu[i]);
                     store6_global(P.meas_out + fo + 6 * n, o);
+                }
+                if ((flags & ROME_B200_JACOBIAN) && live) {  // 9 floats: d r_w / d delta_p = -Jl^-1(r_w); d r_t / d t_p = -I
+                    double Jl[9];
+                    so3_jinv(wx, wy, wz, -1.0, Jl);
+                    store9_global(P.jac + ((size_t)f * Npad + n) * 9, Jl, -1.0);
                 }
                 if (flags & ROME_B200_PROPOSAL_FWD) {  // proposal = the sampled point, offsets from the anchor
                     const float o[6] = {(float)hx,           (float)hy,           (float)hz,

@@ -46,8 +46,8 @@ const FamInfo kFam[ROME_B200_NFAMILIES] = {
     {ROME_B200_POSE2, ROME_B200_POSE2, 3, 3, 16, 4, (int)sizeof(RowSE2), 3, 3},
     {ROME_B200_POSE2, -1, 3, 3, 16, 0, (int)sizeof(RowSE2), 3, 0},
     {ROME_B200_POSE2, ROME_B200_POINT2, 2, 2, 16, 4, (int)sizeof(RowBR), 2, 3},
-    {ROME_B200_POSE3, ROME_B200_POSE3, 6, 6, 32, 0, (int)sizeof(RowSE3), 6, 6},
-    {ROME_B200_POSE3, -1, 6, 6, 32, 0, (int)sizeof(RowSE3), 6, 0},
+    {ROME_B200_POSE3, ROME_B200_POSE3, 6, 6, 32, 36, (int)sizeof(RowSE3), 6, 6},
+    {ROME_B200_POSE3, -1, 6, 6, 32, 9, (int)sizeof(RowSE3), 6, 0},
     {ROME_B200_POINT2, -1, 2, 2, 16, 0, (int)sizeof(RowPT2), 2, 0},                // PriorPoint2
     {ROME_B200_POINT2, ROME_B200_POINT2, 2, 2, 16, 0, (int)sizeof(RowPT2), 2, 0},  // Point2Point2
     {ROME_B200_POSE2, ROME_B200_POINT2, 2, 2, 16, 0, (int)sizeof(RowPT2), 2, 0},   // Pose2Point2
@@ -85,6 +85,7 @@ struct rome_b200_ctx {
     uint32_t* bar_state = nullptr;   // fused step barrier (rome_b200_set_step_barrier)
     uint32_t* bar_peer[7] = {};
     int bar_n = 0;
+    int bar_from[ROME_B200_NFAMILIES] = {};  // first factor of a family that depends on the peers (rome_b200_set_interior_count)
     int owned[ROME_B200_NVARTYPES] = {-1, -1, -1, -1};  // variables [0, owned) are updated by product / reanchor (-1: all)
     std::vector<cudaGraphExec_t> graphs;
     std::vector<uint64_t> graph_kernels;
@@ -601,7 +602,7 @@ int rome_b200_eval(rome_b200_ctx* ctx, int family, uint32_t flags, uint64_t seed
             return fail(ctx, ROME_B200_SHAPE_MISMATCH, "proposal destinations were set for a different number of factors");
         (dir ? p.bwd_dst : p.fwd_dst) = static_cast<const unsigned long long*>(ctx->row_dst[family][dir].p);
     }
-    p.bar_state = ctx->bar_state; p.bar_n = ctx->bar_n; p.bar_timeout = 0;
+    p.bar_state = ctx->bar_state; p.bar_n = ctx->bar_n; p.bar_timeout = 0; p.bar_from = ctx->bar_from[family];
     for (int r = 0; r < 7; ++r) p.bar_peer[r] = ctx->bar_peer[r];
     if (flags & (ROME_B200_BARRIER_WAIT | ROME_B200_BARRIER_SIGNAL)) {
         if (!ctx->bar_state || ctx->bar_n == 0)
@@ -807,6 +808,12 @@ int rome_b200_set_step_barrier(rome_b200_ctx* ctx, void* d_state, uint32_t* cons
     ctx->bar_state = static_cast<uint32_t*>(d_state);
     ctx->bar_n = n_peers;
     for (int r = 0; r < 7; ++r) ctx->bar_peer[r] = r < n_peers ? peer_slots[r] : nullptr;
+    return ROME_B200_OK;
+}
+int rome_b200_set_interior_count(rome_b200_ctx* ctx, int family, int n_interior) {
+    if (!ctx) return ROME_B200_BAD_ARG;
+    if (family < 0 || family >= ROME_B200_NFAMILIES || n_interior < 0) return fail(ctx, ROME_B200_BAD_ARG, "bad family / count");
+    ctx->bar_from[family] = n_interior;
     return ROME_B200_OK;
 }
 int rome_b200_set_owned_variables(rome_b200_ctx* ctx, int vartype, int n_owned) {

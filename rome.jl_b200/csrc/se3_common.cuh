@@ -109,6 +109,38 @@ __device__ __forceinline__ void quat_rotate(const Quat& q, double vx, double vy,
     oz = vz + q.w * tz + (q.x * ty - q.y * tx);
 }
 
+// ---- analytic Jacobian blocks (perturbations t <- t + dt, R <- R Exp(delta)) -----------------
+__device__ __forceinline__ void quat_to_rot(const Quat& q, double (&R)[9]) {
+    const double xx = q.x * q.x, yy = q.y * q.y, zz = q.z * q.z, xy = q.x * q.y, xz = q.x * q.z, yz = q.y * q.z,
+                 wx = q.w * q.x, wy = q.w * q.y, wz = q.w * q.z;
+    R[0] = 1.0 - 2.0 * (yy + zz); R[1] = 2.0 * (xy - wz);       R[2] = 2.0 * (xz + wy);
+    R[3] = 2.0 * (xy + wz);       R[4] = 1.0 - 2.0 * (xx + zz); R[5] = 2.0 * (yz - wx);
+    R[6] = 2.0 * (xz - wy);       R[7] = 2.0 * (yz + wx);       R[8] = 1.0 - 2.0 * (xx + yy);
+}
+// inverse right Jacobian of SO(3) at the rotation vector w, sgn = +1;  sgn = -1 gives the inverse LEFT Jacobian
+//   Jr^-1(w) = I + 1/2 [w]x + c [w]x^2,  c = 1/t^2 - (1 + cos t) / (2 t sin t)  (series below t = 0.05),  Jl^-1(w) = Jr^-1(-w)
+__device__ __forceinline__ void so3_jinv(double wx, double wy, double wz, double sgn, double (&J)[9]) {
+    const double t2 = wx * wx + wy * wy + wz * wz;
+    double c;
+    if (t2 < 2.5e-3) {
+        c = 1.0 / 12.0 + t2 * (1.0 / 720.0 + t2 * (1.0 / 30240.0));
+    } else {
+        const double t = sqrt(t2);
+        double st, ct;
+        sincos(t, &st, &ct);
+        c = 1.0 / t2 - (1.0 + ct) / (2.0 * t * st);
+    }
+    const double h = 0.5 * sgn;
+    // [w]x^2 = w w' - |w|^2 I
+    J[0] = 1.0 + c * (wx * wx - t2); J[1] = -h * wz + c * wx * wy;     J[2] = h * wy + c * wx * wz;
+    J[3] = h * wz + c * wx * wy;     J[4] = 1.0 + c * (wy * wy - t2); J[5] = -h * wx + c * wy * wz;
+    J[6] = -h * wy + c * wx * wz;    J[7] = h * wx + c * wy * wz;     J[8] = 1.0 + c * (wz * wz - t2);
+}
+__device__ __forceinline__ void store9_global(float* p, const double (&M)[9], double scale) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) __stcs(p + i, (float)(scale * M[i]));
+}
+
 // =============================================================================================
 // SE(3) families.  A lane evaluates TWO particles per iteration (n, n+32): the exponentials of both are
 // taken on the polynomial path when every rotation vector of the warp's 64 particles is principal

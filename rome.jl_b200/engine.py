@@ -21,8 +21,8 @@ FAMILY = {
     POSE2POSE2: (POSE2, POSE2, 3, 3, 16, 4, 3, 3),
     PRIORPOSE2: (POSE2, None, 3, 3, 16, 0, 3, 0),
     BEARINGRANGE: (POSE2, POINT2, 2, 2, 16, 4, 2, 3),
-    POSE3POSE3: (POSE3, POSE3, 6, 6, 32, 0, 6, 6),
-    PRIORPOSE3: (POSE3, None, 6, 6, 32, 0, 6, 0),
+    POSE3POSE3: (POSE3, POSE3, 6, 6, 32, 36, 6, 6),
+    PRIORPOSE3: (POSE3, None, 6, 6, 32, 9, 6, 0),
     # next-row families
     PRIORPOINT2: (POINT2, None, 2, 2, 16, 0, 2, 0),
     POINT2POINT2: (POINT2, POINT2, 2, 2, 16, 0, 2, 0),
@@ -322,6 +322,10 @@ class Context:
         """rank barrier fused into eval launches flagged BARRIER_WAIT / BARRIER_SIGNAL; [] clears"""
         arr = (C.c_void_p * max(1, len(peer_slot_ptrs)))(*peer_slot_ptrs)
         self._ck(self._lib.rome_b200_set_step_barrier(self._h, state_ptr or None, arr, len(peer_slot_ptrs)))
+
+    def set_interior_count(self, family: int, n_interior: int):
+        """factors [0, n_interior) do not depend on the peers: BARRIER_WAIT is passed only before the first later factor"""
+        self._ck(self._lib.rome_b200_set_interior_count(self._h, family, n_interior))
 
     def set_owned_variables(self, vartype: int, n_owned: int):
         """product / reanchor update only variables [0, n_owned) (the rest are halo copies); -1: all"""

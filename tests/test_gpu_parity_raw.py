@@ -575,3 +575,68 @@ def test_independent_flag_gives_identical_results(ctx):
             assert torch.equal(b["res"], bufs[0]["res"]) and torch.equal(b["stats"], bufs[0]["stats"])
     finally:
         ctx.set_stream(None)
+
+
+def _right_perturb(poses, delta):
+    """coordinates of (t, R Exp(delta)) for Pose3 coordinates (t, rotation vector)"""
+    R = O.np_so3_exp(poses[..., 3:]) @ O.np_so3_exp(np.broadcast_to(delta, poses[..., 3:].shape))
+    return np.concatenate([poses[..., :3], O.np_so3_log(R)], -1)
+
+
+def test_se3_jacobians_match_finite_differences_of_the_oracle(ctx):
+    """analytic Jacobian blocks of Pose3Pose3 / PriorPose3 (right perturbations R <- R Exp(delta))
+    against central finite differences of the float64 oracle"""
+    rng = np.random.default_rng(15)
+    nvars, nF, N = 12, 30, 16
+    poses = make_pose3(rng, nvars, N)
+    ip = rng.integers(0, nvars - 2, nF).astype(np.int32)
+    iq = (ip + rng.integers(1, 3, nF)).astype(np.int32)
+    mu = np.zeros((nF, 6))
+    for f in range(nF):
+        p, q = poses[ip[f], 0], poses[iq[f], 0]
+        Rp = O.so3_exp(p[3:])
+        mu[f, :3] = Rp.T @ (q[:3] - p[:3])
+        mu[f, 3:] = O.so3_log(Rp.T @ O.so3_exp(q[3:])) + rng.normal(size=3) * 0.3   # residual rotations up to ~1 rad
+    cov = rand_cov(rng, nF, 6, [0.1, 0.1, 0.1, 0.01, 0.01, 0.01])
+    meas = mu[:, None, :] + np.einsum("fij,fnj->fni", np.linalg.cholesky(cov), rng.normal(size=(nF, N, 6)))
+    ctx.set_particles(rb.POSE3, poses)
+    ctx.set_factors_pose3pose3(ip, iq, mu, cov)
+    flags = rb.RESIDUAL | rb.JACOBIAN
+    out = ctx.alloc_host_outputs(rb.POSE3POSE3, flags)
+    assert out["jac"].shape[-1] == 36
+    moff = rb.meas_to_offsets(meas, mu)
+    ctx.eval_host(rb.POSE3POSE3, flags, meas=moff, **out)
+    P, Q = seen(ctx, rb.POSE3, N)[ip], seen(ctx, rb.POSE3, N)[iq]
+    M = seen_meas(moff, mu, N)
+    J = out["jac"][:, :N].reshape(nF, N, 4, 3, 3).astype(np.float64)
+    h = 1e-6
+    for k in range(3):
+        d = np.zeros(3)
+        d[k] = h
+        fd_p = (O.np_pose3pose3(M, _right_perturb(P, d), Q) - O.np_pose3pose3(M, _right_perturb(P, -d), Q)) / (2 * h)
+        fd_q = (O.np_pose3pose3(M, P, _right_perturb(Q, d)) - O.np_pose3pose3(M, P, _right_perturb(Q, -d))) / (2 * h)
+        assert np.abs(fd_p[..., :3] - J[:, :, 0, :, k]).max() < 2e-5      # A = d r_t / d delta_p
+        assert np.abs(fd_p[..., 3:] - J[:, :, 1, :, k]).max() < 2e-5      # B = d r_w / d delta_p
+        assert np.abs(fd_q[..., 3:] - J[:, :, 2, :, k]).max() < 2e-5      # C = d r_w / d delta_q
+        assert np.abs(fd_q[..., :3]).max() < 1e-6                          # d r_t / d delta_q = 0
+        Mp, Mm_ = M.copy(), M.copy()
+        Mp[..., k] += h
+        Mm_[..., k] -= h
+        fd_m = (O.np_pose3pose3(Mp, P, Q) - O.np_pose3pose3(Mm_, P, Q)) / (2 * h)
+        assert np.abs(fd_m[..., :3] - J[:, :, 3, :, k]).max() < 2e-5      # R_p = d r_t / d m_t
+    # PriorPose3
+    ctx.set_factors_priorpose3(ip, poses[ip, 0] + rng.normal(size=(nF, 6)) * [0.1, 0.1, 0.1, 0.3, 0.3, 0.3], cov)
+    mu_p = poses[ip, 0]
+    outp = ctx.alloc_host_outputs(rb.PRIORPOSE3, flags)
+    assert outp["jac"].shape[-1] == 9
+    measp = mu_p[:, None, :] + rng.normal(size=(nF, N, 6)) * [0.1, 0.1, 0.1, 0.3, 0.3, 0.3]
+    ctx.set_factors_priorpose3(ip, mu_p, cov)
+    moffp = rb.meas_to_offsets(measp, mu_p)
+    ctx.eval_host(rb.PRIORPOSE3, flags, meas=moffp, **outp)
+    Mp_ = seen_meas(moffp, mu_p, N)
+    Jp = outp["jac"][:, :N].reshape(nF, N, 3, 3).astype(np.float64)
+    for k in range(3):
+        d = np.zeros(3)
+        d[k] = h
+        fd = (O.np_priorpose3(Mp_, _right_perturb(P, d)) - O.np_priorpose3(Mp_, _right_perturb(P, -d))) / (2 * h)
+        assert np.abs(fd[..., 3:] - Jp[:, :, :, k]).max() < 2e-5
