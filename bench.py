@@ -586,10 +586,16 @@ def main():
                     # sorted by global id too
                     seg = got[pos:pos + len(rows)]
                     pos += len(rows)
-                    same = np.array_equal(seg[:, :N], want[:, :N])
-                    ok = ok and same and len(want) == len(rows)
-                    if not same and seg.shape == want.shape:
-                        worst = max(worst, float(np.nanmax(np.abs(seg[:, :N] - want[:, :N]))))
+                    same = seg.shape == want.shape and np.array_equal(seg[:, :N], want[:, :N])
+                    ok = ok and same
+                    if not same:
+                        bad = np.inf
+                        if seg.shape == want.shape:
+                            dd = np.abs(seg[:, :N].astype(np.float64) - want[:, :N])
+                            bad = float(np.nanmax(dd)) if np.isfinite(dd).any() else np.inf
+                            print(f"[rank {rank}] exchange mismatch from rank {src}: {int((dd > 0).any(axis=(1, 2)).sum())} of "
+                                  f"{len(rows)} rows differ, {int(np.isnan(seg).sum())} NaN received, worst {bad}", file=sys.stderr)
+                        worst = max(worst, bad)
                     rows_checked += len(rows)
                     chk.close()
         gave_up = bool(sets[0][0].peer_gave_up(state)) if args.barrier != "nccl" else False
@@ -601,7 +607,10 @@ def main():
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         mx = flag.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        verify = {"exchange_verified": bool(mn[0].item() > 0.5), "rows_checked_all_ranks": int(sm[1].item()),
+        gu = torch.tensor([1.0 if gave_up else 0.0, 0.0 if halo_ok else 1.0], device="cuda", dtype=torch.float64)
+        dist.all_reduce(gu, op=dist.ReduceOp.MAX)
+        verify = {"exchange_verified": bool(mn[0].item() > 0.5), "barrier_gave_up": bool(gu[0].item() > 0),
+                  "halo_mismatch": bool(gu[1].item() > 0), "rows_checked_all_ranks": int(sm[1].item()),
                   "max_abs_diff": float(mx[2].item()), "halo_blocks_checked_all_ranks": int(sm[3].item()),
                   "how": "after the timed replay every rank rebuilds each peer's local problem from the seeds, recomputes the "
                          "forward-proposal rows that peer's cut factors address to it (same seed / stream id as the last timed "

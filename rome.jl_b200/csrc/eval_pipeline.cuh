@@ -182,7 +182,7 @@ __device__ __forceinline__ void fused_barrier_wait(const EvalParams& P, int lane
 __device__ __forceinline__ void fused_barrier_signal(const EvalParams& P) {
     __syncthreads();  // every warp of this CTA has waited for its bulk stores
     if (threadIdx.x == 0) {
-        __threadfence_system();
+        __threadfence();
         const uint32_t done = atomicAdd(P.bar_state + 12, 1u);
         if (done == gridDim.x - 1) {  // the last CTA of the grid
             __threadfence_system();
@@ -203,7 +203,17 @@ __device__ __forceinline__ void fused_barrier_signal(const EvalParams& P) {
 // launch of the bench workload; requesting more registers than the CTA was launched with hangs.  profiles/r02_analysis.md)
 template <int FT>
 constexpr int eval_threads() { return (FT + 1) * 32; }
-template <class Fam, uint32_t kStatic, bool kSample, int FT>
+// out-of-line run-time-flag body for the rare routed factors of a kRouted kernel: its own register allocation, so the
+// common path's is not disturbed
+template <class Fam, bool kSample>
+__device__ __noinline__ void factor_runtime_flags(const typename Fam::Row& row, const EvalParams& P, const FactorView& V,
+                                                  int f, int lane) {
+    Fam::template factor<0u, kSample>(row, P, V, f, lane);
+}
+// kRouted (the compile-time RESIDUAL|STATS variant of a ROUTED_ONLY launch): factors without a destination run the
+// compile-time body; the few factors WITH one (a rank's cut factors) take the run-time-flag body, which also writes
+// their forward row -- the common path keeps the register allocation and instruction count of the plain variant.
+template <class Fam, uint32_t kStatic, bool kSample, int FT, bool kRouted = false>
 __global__ void __launch_bounds__(eval_threads<FT>(), Fam::kMinCtas) eval_kernel(const __grid_constant__ EvalParams P) {
     using Row = typename Fam::Row;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -294,6 +304,7 @@ __global__ void __launch_bounds__(eval_threads<FT>(), Fam::kMinCtas) eval_kernel
         const int res_floats = Fam::DR * P.Npad;
         int s = 0;
         uint32_t phase = 0;
+        bool wrote_peer = false;  // did this warp store rows into another GPU's memory?
         for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
             const int fl = tile * FT + warp;
             const bool mine = fl < P.count;
@@ -301,7 +312,7 @@ __global__ void __launch_bounds__(eval_threads<FT>(), Fam::kMinCtas) eval_kernel
             // owner-sharded exchange: this factor's forward row may have its own destination (a peer GPU); requested
             // before the wait for the stage so that the load's latency hides behind it (warp-uniform address)
             unsigned long long fdst = 0;
-            if (mine && (flags & ROME_B200_PROPOSAL_FWD) && P.fwd_dst) fdst = __ldg(P.fwd_dst + f);
+            if (mine && ((flags & ROME_B200_PROPOSAL_FWD) || kRouted) && P.fwd_dst) fdst = __ldg(P.fwd_dst + f);
             mbar_wait(&full[s], phase);
             const unsigned char* st = stage0 + (size_t)s * L.bytes;
             if (mine) {
@@ -313,18 +324,21 @@ __global__ void __launch_bounds__(eval_threads<FT>(), Fam::kMinCtas) eval_kernel
                 V.out_res = out;
                 V.out_fwd = out + res_floats;
                 V.fwd_on = !(P.flags & ROME_B200_ROUTED_ONLY) || fdst != 0;
+                wrote_peer = wrote_peer || fdst != 0 || P.n_peers > 0;
                 if (flags & (ROME_B200_RESIDUAL | ROME_B200_PROPOSAL_FWD)) {
                     if (lane == 0) tma_store_wait_read();  // the previous tile's rows have left the slice
                     __syncwarp();
                 }
-                Fam::template factor<kStatic, kSample>(row, P, V, f, lane);
+                const bool routed = kRouted && fdst != 0;  // warp-uniform
+                if (routed) factor_runtime_flags<Fam, kSample>(row, P, V, f, lane);   // + forward row
+                else Fam::template factor<kStatic, kSample>(row, P, V, f, lane);
                 if (flags & (ROME_B200_RESIDUAL | ROME_B200_PROPOSAL_FWD)) {
                     fence_proxy_async();  // generic-proxy writes of the slice -> visible to the bulk-copy engine
                     __syncwarp();
                     if (lane == 0) {
                         if (flags & ROME_B200_RESIDUAL)
                             tma_store_1d(P.res + (size_t)f * res_floats, V.out_res, (uint32_t)(res_floats * 4));
-                        if ((flags & ROME_B200_PROPOSAL_FWD) && V.fwd_on) {
+                        if (((flags & ROME_B200_PROPOSAL_FWD) && V.fwd_on) || routed) {
                             const size_t off = (size_t)f * Fam::DFWD * P.Npad;
                             const uint32_t bytes = (uint32_t)(Fam::DFWD * P.Npad * 4);
                             tma_store_1d(fdst ? reinterpret_cast<float*>(fdst) : P.prop_fwd + off, V.out_fwd, bytes);
@@ -339,7 +353,12 @@ __global__ void __launch_bounds__(eval_threads<FT>(), Fam::kMinCtas) eval_kernel
             if (lane == 0) mbar_arrive(&empty[s]);
             if (++s == S) { s = 0; phase ^= 1u; }
         }
-        if (lane == 0) tma_store_wait_all();
+        if (lane == 0) {
+            tma_store_wait_all();
+            // rows stored into peer memory are performed system-wide before this CTA reports completion (only the
+            // warps that have such rows pay for the system-scope fence)
+            if ((P.flags & ROME_B200_BARRIER_SIGNAL) && wrote_peer) __threadfence_system();
+        }
     }
     // a launch that overlapped its predecessor must not be seen as complete before the predecessor is
     if (P.flags & ROME_B200_INDEPENDENT) asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -371,7 +390,7 @@ __host__ __device__ inline SlotLayout slot_layout(int row_bytes, int d0, int d1,
     L.bytes = (L.meas_off + L.mb + 127) / 128 * 128;
     return L;
 }
-template <class Fam, uint32_t kStatic, bool kSample, int FT>
+template <class Fam, uint32_t kStatic, bool kSample, int FT, bool kRouted = false>
 __global__ void __launch_bounds__(FT * 32, Fam::kMinCtas) eval_kernel_w(const __grid_constant__ EvalParams P) {
     using Row = typename Fam::Row;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -429,12 +448,13 @@ __global__ void __launch_bounds__(FT * 32, Fam::kMinCtas) eval_kernel_w(const __
 
     int s = 0;
     uint32_t phase = 0;
+    bool wrote_peer = false;
     for (int i = 0;; ++i) {
         const int fl = factor_of(i);
         if (fl < 0) break;
         const int f = P.first + fl;
         unsigned long long fdst = 0;  // owner-sharded exchange: per-factor destination of the forward row
-        if ((flags & ROME_B200_PROPOSAL_FWD) && P.fwd_dst) fdst = __ldg(P.fwd_dst + f);
+        if (((flags & ROME_B200_PROPOSAL_FWD) || kRouted) && P.fwd_dst) fdst = __ldg(P.fwd_dst + f);
         if (lane == s) ids = fetch_ids(i + S);  // consumed when this factor is done: hidden behind its arithmetic
         mbar_wait(&bar[s], phase);
         const unsigned char* st = slots + (size_t)s * L.bytes;
@@ -446,18 +466,21 @@ __global__ void __launch_bounds__(FT * 32, Fam::kMinCtas) eval_kernel_w(const __
         V.out_res = out;
         V.out_fwd = out + res_floats;
         V.fwd_on = !(P.flags & ROME_B200_ROUTED_ONLY) || fdst != 0;
+        wrote_peer = wrote_peer || fdst != 0 || P.n_peers > 0;
         if (flags & (ROME_B200_RESIDUAL | ROME_B200_PROPOSAL_FWD)) {
             if (lane == 0) tma_store_wait_read();  // the previous factor's rows have left the slice
             __syncwarp();
         }
-        Fam::template factor<kStatic, kSample>(row, P, V, f, lane);
+        const bool routed = kRouted && fdst != 0;  // warp-uniform
+        if (routed) factor_runtime_flags<Fam, kSample>(row, P, V, f, lane);   // + forward row
+        else Fam::template factor<kStatic, kSample>(row, P, V, f, lane);
         if (flags & (ROME_B200_RESIDUAL | ROME_B200_PROPOSAL_FWD)) {
             fence_proxy_async();  // generic-proxy writes of the slice -> visible to the bulk-copy engine
             __syncwarp();
             if (lane == 0) {
                 if (flags & ROME_B200_RESIDUAL)
                     tma_store_1d(P.res + (size_t)f * res_floats, V.out_res, (uint32_t)(res_floats * 4));
-                if ((flags & ROME_B200_PROPOSAL_FWD) && V.fwd_on) {
+                if (((flags & ROME_B200_PROPOSAL_FWD) && V.fwd_on) || routed) {
                     const size_t off = (size_t)f * Fam::DFWD * P.Npad;
                     const uint32_t bytes = (uint32_t)(Fam::DFWD * P.Npad * 4);
                     tma_store_1d(fdst ? reinterpret_cast<float*>(fdst) : P.prop_fwd + off, V.out_fwd, bytes);
@@ -471,7 +494,10 @@ __global__ void __launch_bounds__(FT * 32, Fam::kMinCtas) eval_kernel_w(const __
         if (lane == s) issue(i + S, s, ids);
         if (++s == S) { s = 0; phase ^= 1u; }
     }
-    if (lane == 0) tma_store_wait_all();
+    if (lane == 0) {
+        tma_store_wait_all();
+        if ((P.flags & ROME_B200_BARRIER_SIGNAL) && wrote_peer) __threadfence_system();
+    }
     if (P.flags & ROME_B200_INDEPENDENT) asm volatile("griddepcontrol.wait;" ::: "memory");
     if (P.flags & ROME_B200_BARRIER_SIGNAL) fused_barrier_signal(P);
 }
@@ -498,15 +524,15 @@ int launch_kernel_cfg(K k, int* configured, int threads, const EvalParams& p, co
     cfg.numAttrs = 1;
     return (int)cudaLaunchKernelEx(&cfg, k, p);
 }
-template <class Fam, uint32_t kStatic, bool kSample, int FT>
+template <class Fam, uint32_t kStatic, bool kSample, int FT, bool kRouted = false>
 int launch_ft(const EvalParams& p, const LaunchPlan& plan, int grid, cudaStream_t s) {
     static int configured[64] = {0};  // per-instantiation, per-device cache of the opt-in shared memory size
-    return launch_kernel_cfg(eval_kernel<Fam, kStatic, kSample, FT>, configured, eval_threads<FT>(), p, plan, grid, s);
+    return launch_kernel_cfg(eval_kernel<Fam, kStatic, kSample, FT, kRouted>, configured, eval_threads<FT>(), p, plan, grid, s);
 }
-template <class Fam, uint32_t kStatic, bool kSample, int FT>
+template <class Fam, uint32_t kStatic, bool kSample, int FT, bool kRouted = false>
 int launch_ft_w(const EvalParams& p, const LaunchPlan& plan, int grid, cudaStream_t s) {
     static int configured[64] = {0};
-    return launch_kernel_cfg(eval_kernel_w<Fam, kStatic, kSample, FT>, configured, FT * 32, p, plan, grid, s);
+    return launch_kernel_cfg(eval_kernel_w<Fam, kStatic, kSample, FT, kRouted>, configured, FT * 32, p, plan, grid, s);
 }
 template <class Fam, bool kSample>
 int launch_sample(const EvalParams& p, const LaunchPlan& plan, int grid, cudaStream_t s) {
@@ -517,6 +543,9 @@ int launch_sample(const EvalParams& p, const LaunchPlan& plan, int grid, cudaStr
             if (plan.ft != W) return (int)cudaErrorInvalidValue;
             if (plan.variant == 1) return launch_ft_w<Fam, kHot1 | smp, kSample, W>(p, plan, grid, s);
             if (plan.variant == 2) return launch_ft_w<Fam, kHot2 | smp, kSample, W>(p, plan, grid, s);
+            if constexpr (Fam::DFWD > 0) {
+                if (plan.variant == 3) return launch_ft_w<Fam, kHot1 | smp, kSample, W, true>(p, plan, grid, s);
+            }
             return launch_ft_w<Fam, 0u, kSample, W>(p, plan, grid, s);
         }
     } else if (plan.pipeline == 1) {
@@ -525,6 +554,9 @@ int launch_sample(const EvalParams& p, const LaunchPlan& plan, int grid, cudaStr
     if (plan.ft == 8) {
         if (plan.variant == 1) return launch_ft<Fam, kHot1 | smp, kSample, 8>(p, plan, grid, s);
         if (plan.variant == 2) return launch_ft<Fam, kHot2 | smp, kSample, 8>(p, plan, grid, s);
+        if constexpr (Fam::DFWD > 0) {
+            if (plan.variant == 3) return launch_ft<Fam, kHot1 | smp, kSample, 8, true>(p, plan, grid, s);
+        }
         return launch_ft<Fam, 0u, kSample, 8>(p, plan, grid, s);
     }
     if (plan.ft == 2) return launch_ft<Fam, 0u, kSample, 2>(p, plan, grid, s);

@@ -72,7 +72,8 @@ int plan_launch(int family, uint32_t flags, int Npad, int smem_per_sm, int smem_
     const bool se3 = fd.d0 == 6;  // Pose3 families: one CTA per SM (register budget)
     if (fd.dfwd == 0) flags &= ~ROME_B200_PROPOSAL_FWD;
     const uint32_t out_flags = flags & ~kSchedFlags;
-    const int hot = out_flags == kHot1 ? 1 : out_flags == kHot2 ? 2 : 0;
+    // 3: RESIDUAL|STATS compiled in, forward rows only for the factors that have a destination (ROUTED_ONLY)
+    const int hot = out_flags == kHot1 ? 1 : out_flags == kHot2 ? ((flags & ROME_B200_ROUTED_ONLY) ? 3 : 2) : 0;
     plan->pipeline = 0;
     if (se3 && pipeline_choice() == 1) {
         // per-warp pipelines: W warps per CTA, each with its own ring of `stages` slots + output slice

@@ -123,7 +123,8 @@ struct ProductParams {
 // launch geometry chosen on the host for (family, sample, Npad)
 struct LaunchPlan {
     int ft;           // factors per tile == consumer warps per CTA (8, 2 or 1)
-    int variant;      // 0: runtime flags; 1: RESIDUAL|STATS; 2: RESIDUAL|STATS|PROPOSAL_FWD (compile-time flags)
+    int variant;      // 0: runtime flags; 1: RESIDUAL|STATS; 2: RESIDUAL|STATS|PROPOSAL_FWD (compile-time flags);
+                      // 3: RESIDUAL|STATS compile-time + forward rows of the routed factors (ROUTED_ONLY launches)
     int stages;
     int stage_bytes;
     int out_warp_bytes;

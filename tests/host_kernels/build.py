@@ -58,7 +58,7 @@ def source_text():
     assert n == 6 and pipe.count("unsigned char* const smem = hk::g_smem") == 2
     parts.append(pipe)
     parts.append(open(os.path.join(HERE, "hk_launch.inc")).read())   # launch_kernel_cfg: run the grid under the emulator
-    parts.append(ep[ep.index("template <class Fam, uint32_t kStatic, bool kSample, int FT>\nint launch_ft("):ep.rindex("}  // namespace rome")])
+    parts.append(ep[ep.index("template <class Fam, uint32_t kStatic, bool kSample, int FT, bool kRouted = false>\nint launch_ft("):ep.rindex("}  // namespace rome")])
     parts.append(fk[fk.index("struct FamDims {"):fk.index("int launch_eval(")])
     parts.append(_between(fk, "// layout conversion: reference layout", "__global__ void adopt_kernel"))
     parts.append(family_region("fam_pose2.cu"))

@@ -211,6 +211,7 @@ static inline int min(int a, int b) { return a < b ? a : b; }
 static long long hk_clock_ticks = 0;
 static inline long long clock64() { return ++hk_clock_ticks; }
 static inline void __threadfence_system() {}
+static inline void __threadfence() {}
 static inline uint32_t atomicAdd(uint32_t* p, uint32_t v) { const uint32_t o = *p; *p = o + v; return o; }
 static inline uint32_t atomicExch(uint32_t* p, uint32_t v) { const uint32_t o = *p; *p = v; return o; }
 namespace rome {
