@@ -393,10 +393,11 @@ def main():
                 if not dfwd or f["n_cut"] == 0:
                     continue
                 rowb = Np * dfwd * 4
-                ptrs = [0] * f["n_interior"] + [recv_ptr[int(d)][fam] + int(r) * rowb
-                                                for d, r in zip(f["dst_rank"], f["dst_row"])]
+                ptrs = [0] * f["cut_first"] + [recv_ptr[int(d)][fam] + int(r) * rowb
+                                               for d, r in zip(f["dst_rank"], f["dst_row"])]
+                ptrs += [0] * (len(f["i0"]) - len(ptrs))
                 c.set_proposal_destinations(fam, 0, ptrs)
-                c.set_interior_count(fam, f["n_interior"])   # the rank barrier is only passed before the first cut factor
+                c.set_barrier_range(fam, f["cut_first"], f["n_cut"])   # the rank barrier is only passed before the cut block
                 if fam not in dummy_fwd:  # default rows of prop_fwd are never written for the cut range; one shared buffer
                     dummy_fwd[fam] = torch.zeros((len(f["i0"]), Np, dfwd), device="cuda")
             for vt, pushes in lv["loc"]["push"].items():
@@ -469,7 +470,9 @@ def main():
             if idx > 0 or indep_all:
                 fl |= rb.INDEPENDENT
             if multi and barrier and args.barrier == "fused":
-                fl |= (rb.BARRIER_WAIT if idx == 0 else 0) | (rb.BARRIER_SIGNAL if idx == len(todo) - 1 else 0)
+                # every launch with cut factors passes the barrier before its cut block; the step's LAST launch (its
+                # epilogue runs after all launches of the step have completed) publishes this rank's epoch
+                fl |= (rb.BARRIER_WAIT if (fl & rb.ROUTED_ONLY) else 0) | (rb.BARRIER_SIGNAL if idx == len(todo) - 1 else 0)
             c.eval(fam, fl, seed=7, stream_id=k, **kw)
         if multi and barrier and args.barrier != "fused":
             rank_barrier(c)
@@ -577,11 +580,17 @@ def main():
                     out = dict(res=torch.zeros((nFs, Np, rb.FAMILY[fam][3]), device="cuda"),
                                stats=torch.zeros((nFs, rb.FAMILY[fam][4]), device="cuda"),
                                prop_fwd=torch.zeros((nFs, Np, dfwd), device="cuda"))
-                    chk.eval(fam, F0 | rb.PROPOSAL_FWD, seed=7, stream_id=k_last, first=fs["n_interior"], count=fs["n_cut"],
-                             **out)
+                    # the same launch the source rank issued (same kernel variant, same factor numbering), its cut rows
+                    # routed into a local buffer instead of the peers' memory
+                    routed = torch.zeros((max(1, fs["n_cut"]), Np, dfwd), device="cuda")
+                    rowb = Np * dfwd * 4
+                    lp = [0] * fs["cut_first"] + [routed.data_ptr() + j * rowb for j in range(fs["n_cut"])]
+                    lp += [0] * (nFs - len(lp))
+                    chk.set_proposal_destinations(fam, 0, lp)
+                    chk.eval(fam, F0 | rb.PROPOSAL_FWD | rb.ROUTED_ONLY, seed=7, stream_id=k_last, **out)
                     stream.synchronize()
-                    mine_rows = fs["n_interior"] + np.nonzero(fs["dst_rank"] == rank)[0]
-                    want = out["prop_fwd"][torch.as_tensor(mine_rows, device="cuda")].cpu().numpy()
+                    mine_rows = np.nonzero(fs["dst_rank"] == rank)[0]
+                    want = routed[torch.as_tensor(mine_rows, device="cuda")].cpu().numpy()
                     # rows arrive in (source rank, global id) order; the source's cut factors to one destination are
                     # sorted by global id too
                     seg = got[pos:pos + len(rows)]

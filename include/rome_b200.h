@@ -304,11 +304,11 @@ ROME_B200_API int rome_b200_push_halo(rome_b200_ctx* ctx, int vartype);
  * fused flags must not be interleaved on one state buffer except that a completed signal + wait PAIR of the kernels may
  * precede the first fused step (set-up barrier).  n_peers = 0 clears. */
 ROME_B200_API int rome_b200_set_step_barrier(rome_b200_ctx* ctx, void* d_state, uint32_t* const* peer_slots, int n_peers);
-/* Factors [0, n_interior) of the family read only variables this rank owns and write only local buffers (upload the
- * table with the interior factors first): a launch flagged BARRIER_WAIT evaluates them right away and passes the barrier
- * only before it fetches the first factor >= n_interior, so the barrier's latency hides behind the interior work.
- * Default 0: the barrier is passed before anything is fetched. */
-ROME_B200_API int rome_b200_set_interior_count(rome_b200_ctx* ctx, int family, int n_interior);
+/* Only factors [first, first + count) of the family depend on the peers (they read halo blocks / write into peer memory:
+ * a rank's cut factors, uploaded as one block of the table): a launch flagged BARRIER_WAIT evaluates everything else
+ * without waiting and passes the barrier only before it fetches the first factor of that range, so the barrier's latency
+ * hides behind the interior work.  count < 0 restores the default: every factor depends on the peers. */
+ROME_B200_API int rome_b200_set_barrier_range(rome_b200_ctx* ctx, int family, int first, int count);
 /* CUDA IPC plumbing for buffers allocated with rome_b200_malloc_device (64-byte opaque handles).  Only such buffers may
  * be exported: rome_b200_malloc_device hands out whole 2 MiB blocks, so the handle (which names the driver's block) and
  * the buffer coincide; a pointer into a packed small cudaMalloc allocation would be opened at the wrong address. */

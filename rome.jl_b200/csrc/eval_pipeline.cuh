@@ -153,16 +153,17 @@ constexpr int kMaxStages = 6;
 // rank barrier fused into the evaluation kernels (owner-sharded multi-GPU sweeps; the state buffer is the one of
 // rome_b200_peer_signal / _wait: words [0, 8) flag slots written by the peers, word 8 this rank's signal epoch, word 10
 // give-up status, word 12 the CTA counter of the signalling launch).
-//   ROME_B200_BARRIER_WAIT   (first launch of a step): before the first factor >= bar_from (the first cut factor; 0 = every
-//       factor) is fetched, the fetching warp polls the local flag slots until each peer has signalled as often as this
-//       rank has (word 8) -- the peers' previous step, with its stores into this GPU's memory, is complete.
+//   ROME_B200_BARRIER_WAIT   (a launch of the next step): before the first factor of [bar_lo, bar_hi) -- the family's cut
+//       factors; default: every factor -- is fetched, the fetching warp polls the local flag slots until each peer has
+//       signalled as often as this rank has (word 8): the peers' previous step, with its stores into this GPU's memory,
+//       is complete.
 //   ROME_B200_BARRIER_SIGNAL (last launch of a step): the CTA that finishes last publishes the next epoch to the slot
 //       this rank owns in every peer's state (st.release.sys after a system-scope fence: the rows this grid stored into
 //       peer memory are visible before the flag).
 // No extra kernel, no host round trip: the barrier costs the NVLink latency of a 4-byte store.
 // =============================================================================================
-// executed by ONE WARP (the warp that fetches particle blocks), right before the first factor >= P.bar_from is fetched:
-// the factors in front of it -- a rank's interior factors -- neither read halo blocks nor write into peer memory, so
+// executed by ONE WARP (the warp that fetches particle blocks), right before the first factor of [P.bar_lo, P.bar_hi) is
+// fetched: the other factors -- a rank's interior factors -- neither read halo blocks nor write into peer memory, so
 // their evaluation overlaps the barrier's latency
 __device__ __forceinline__ void fused_barrier_wait(const EvalParams& P, int lane) {
     if (lane < P.bar_n) {
@@ -203,16 +204,11 @@ __device__ __forceinline__ void fused_barrier_signal(const EvalParams& P) {
 // launch of the bench workload; requesting more registers than the CTA was launched with hangs.  profiles/r02_analysis.md)
 template <int FT>
 constexpr int eval_threads() { return (FT + 1) * 32; }
-// out-of-line run-time-flag body for the rare routed factors of a kRouted kernel: its own register allocation, so the
-// common path's is not disturbed
-template <class Fam, bool kSample>
-__device__ __noinline__ void factor_runtime_flags(const typename Fam::Row& row, const EvalParams& P, const FactorView& V,
-                                                  int f, int lane) {
-    Fam::template factor<0u, kSample>(row, P, V, f, lane);
-}
 // kRouted (the compile-time RESIDUAL|STATS variant of a ROUTED_ONLY launch): factors without a destination run the
-// compile-time body; the few factors WITH one (a rank's cut factors) take the run-time-flag body, which also writes
-// their forward row -- the common path keeps the register allocation and instruction count of the plain variant.
+// compile-time RESIDUAL|STATS body; the few factors WITH one (a rank's cut factors) run the compile-time
+// RESIDUAL|STATS|PROPOSAL_FWD body, which also writes their forward row -- the common path keeps the instruction count
+// of the plain variant.  (An out-of-line run-time-flag body for the routed factors was measured: 6x slower per factor,
+// and the cut factors sit in the last tiles, i.e. on the kernel's critical path.)
 template <class Fam, uint32_t kStatic, bool kSample, int FT, bool kRouted = false>
 __global__ void __launch_bounds__(eval_threads<FT>(), Fam::kMinCtas) eval_kernel(const __grid_constant__ EvalParams P) {
     using Row = typename Fam::Row;
@@ -255,9 +251,11 @@ __global__ void __launch_bounds__(eval_threads<FT>(), Fam::kMinCtas) eval_kernel
     // initialisation and the first variable ids, read from the factor table, which no kernel writes -- overlaps the
     // predecessor's tail and the launch latency.  Before the first access to data a predecessor may have written
     // (particle blocks) or may still read (the output buffers) it waits for the predecessor grid to complete; a launch
-    // flagged ROME_B200_INDEPENDENT touches no such data and defers that wait to its end.
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // flagged ROME_B200_INDEPENDENT touches no such data and defers that wait to its end.  A dependent launch releases
+    // ITS successors only after its own wait: an INDEPENDENT successor starts without waiting, so it must not be able to
+    // start before the sweep's first launch has seen the previous sweep complete.
     if (!(P.flags & ROME_B200_INDEPENDENT)) asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (warp == FT) {
         // ---------------- producer warp ---------------------------------------------------------------------
@@ -274,7 +272,7 @@ __global__ void __launch_bounds__(eval_threads<FT>(), Fam::kMinCtas) eval_kernel
                 if (!first_round) mbar_wait(&empty[s], phase);
                 unsigned char* st = stage0 + (size_t)s * L.bytes;
                 const int t0 = tile * FT, nf = min(FT, P.count - tile * FT);
-                if (!synced && P.first + t0 + nf > P.bar_from) {  // the peers' previous step must have landed from here on
+                if (!synced && P.first + t0 + nf > P.bar_lo && P.first + t0 < P.bar_hi) {  // a tile with peer-dependent factors
                     fused_barrier_wait(P, lane);
                     synced = true;
                 }
@@ -330,7 +328,7 @@ __global__ void __launch_bounds__(eval_threads<FT>(), Fam::kMinCtas) eval_kernel
                     __syncwarp();
                 }
                 const bool routed = kRouted && fdst != 0;  // warp-uniform
-                if (routed) factor_runtime_flags<Fam, kSample>(row, P, V, f, lane);   // + forward row
+                if (routed) Fam::template factor<kHot2 | (kStatic & ROME_B200_SAMPLE), kSample>(row, P, V, f, lane);
                 else Fam::template factor<kStatic, kSample>(row, P, V, f, lane);
                 if (flags & (ROME_B200_RESIDUAL | ROME_B200_PROPOSAL_FWD)) {
                     fence_proxy_async();  // generic-proxy writes of the slice -> visible to the bulk-copy engine
@@ -433,12 +431,12 @@ __global__ void __launch_bounds__(FT * 32, Fam::kMinCtas) eval_kernel_w(const __
         fence_mbar_init();
     }
     __syncwarp();
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (!(P.flags & ROME_B200_INDEPENDENT)) asm volatile("griddepcontrol.wait;" ::: "memory");  // see eval_kernel
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     bool synced = !(P.flags & ROME_B200_BARRIER_WAIT);  // rank barrier still to be passed (every warp fetches for itself)
     auto sync_before = [&](int i) {
         const int fl = factor_of(i);
-        if (!synced && fl >= 0 && P.first + fl >= P.bar_from) {
+        if (!synced && fl >= 0 && P.first + fl >= P.bar_lo && P.first + fl < P.bar_hi) {
             fused_barrier_wait(P, lane);
             synced = true;
         }
@@ -472,7 +470,7 @@ __global__ void __launch_bounds__(FT * 32, Fam::kMinCtas) eval_kernel_w(const __
             __syncwarp();
         }
         const bool routed = kRouted && fdst != 0;  // warp-uniform
-        if (routed) factor_runtime_flags<Fam, kSample>(row, P, V, f, lane);   // + forward row
+        if (routed) Fam::template factor<kHot2 | (kStatic & ROME_B200_SAMPLE), kSample>(row, P, V, f, lane);
         else Fam::template factor<kStatic, kSample>(row, P, V, f, lane);
         if (flags & (ROME_B200_RESIDUAL | ROME_B200_PROPOSAL_FWD)) {
             fence_proxy_async();  // generic-proxy writes of the slice -> visible to the bulk-copy engine

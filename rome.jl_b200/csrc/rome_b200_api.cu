@@ -85,7 +85,8 @@ struct rome_b200_ctx {
     uint32_t* bar_state = nullptr;   // fused step barrier (rome_b200_set_step_barrier)
     uint32_t* bar_peer[7] = {};
     int bar_n = 0;
-    int bar_from[ROME_B200_NFAMILIES] = {};  // first factor of a family that depends on the peers (rome_b200_set_interior_count)
+    int bar_lo[ROME_B200_NFAMILIES] = {};    // factors of a family that depend on the peers (rome_b200_set_barrier_range);
+    int bar_hi[ROME_B200_NFAMILIES];         // default [0, INT_MAX): all
     int owned[ROME_B200_NVARTYPES] = {-1, -1, -1, -1};  // variables [0, owned) are updated by product / reanchor (-1: all)
     std::vector<cudaGraphExec_t> graphs;
     std::vector<uint64_t> graph_kernels;
@@ -222,6 +223,7 @@ int rome_b200_create(int device, rome_b200_ctx** out) {
     rome_b200_ctx* ctx = new (std::nothrow) rome_b200_ctx();
     if (!ctx) return fail(nullptr, ROME_B200_BAD_ARG, "out of host memory");
     ctx->device = device;
+    for (int& h : ctx->bar_hi) h = 0x7fffffff;
     if ((e = cudaSetDevice(device)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) {
@@ -602,7 +604,7 @@ int rome_b200_eval(rome_b200_ctx* ctx, int family, uint32_t flags, uint64_t seed
             return fail(ctx, ROME_B200_SHAPE_MISMATCH, "proposal destinations were set for a different number of factors");
         (dir ? p.bwd_dst : p.fwd_dst) = static_cast<const unsigned long long*>(ctx->row_dst[family][dir].p);
     }
-    p.bar_state = ctx->bar_state; p.bar_n = ctx->bar_n; p.bar_timeout = 0; p.bar_from = ctx->bar_from[family];
+    p.bar_state = ctx->bar_state; p.bar_n = ctx->bar_n; p.bar_timeout = 0; p.bar_lo = ctx->bar_lo[family]; p.bar_hi = ctx->bar_hi[family];
     for (int r = 0; r < 7; ++r) p.bar_peer[r] = ctx->bar_peer[r];
     if (flags & (ROME_B200_BARRIER_WAIT | ROME_B200_BARRIER_SIGNAL)) {
         if (!ctx->bar_state || ctx->bar_n == 0)
@@ -810,10 +812,11 @@ int rome_b200_set_step_barrier(rome_b200_ctx* ctx, void* d_state, uint32_t* cons
     for (int r = 0; r < 7; ++r) ctx->bar_peer[r] = r < n_peers ? peer_slots[r] : nullptr;
     return ROME_B200_OK;
 }
-int rome_b200_set_interior_count(rome_b200_ctx* ctx, int family, int n_interior) {
+int rome_b200_set_barrier_range(rome_b200_ctx* ctx, int family, int first, int count) {
     if (!ctx) return ROME_B200_BAD_ARG;
-    if (family < 0 || family >= ROME_B200_NFAMILIES || n_interior < 0) return fail(ctx, ROME_B200_BAD_ARG, "bad family / count");
-    ctx->bar_from[family] = n_interior;
+    if (family < 0 || family >= ROME_B200_NFAMILIES || first < 0) return fail(ctx, ROME_B200_BAD_ARG, "bad family / range");
+    ctx->bar_lo[family] = count < 0 ? 0 : first;
+    ctx->bar_hi[family] = count < 0 ? 0x7fffffff : first + count;
     return ROME_B200_OK;
 }
 int rome_b200_set_owned_variables(rome_b200_ctx* ctx, int vartype, int n_owned) {

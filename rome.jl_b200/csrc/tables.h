@@ -92,7 +92,7 @@ struct EvalParams {
     uint32_t* bar_state;
     uint32_t* bar_peer[7];
     int bar_n;
-    int bar_from;  // BARRIER_WAIT is passed right before the first factor >= bar_from is fetched
+    int bar_lo, bar_hi;  // BARRIER_WAIT is passed right before the first factor of [bar_lo, bar_hi) is fetched
     long long bar_timeout;
 };
 // flags that change scheduling / routing only, never which outputs a launch computes (ignored when a compile-time

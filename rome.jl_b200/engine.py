@@ -323,9 +323,10 @@ class Context:
         arr = (C.c_void_p * max(1, len(peer_slot_ptrs)))(*peer_slot_ptrs)
         self._ck(self._lib.rome_b200_set_step_barrier(self._h, state_ptr or None, arr, len(peer_slot_ptrs)))
 
-    def set_interior_count(self, family: int, n_interior: int):
-        """factors [0, n_interior) do not depend on the peers: BARRIER_WAIT is passed only before the first later factor"""
-        self._ck(self._lib.rome_b200_set_interior_count(self._h, family, n_interior))
+    def set_barrier_range(self, family: int, first: int, count: int):
+        """only factors [first, first + count) depend on the peers: BARRIER_WAIT is passed right before the first of them
+        is fetched (count < 0: every factor, the default)"""
+        self._ck(self._lib.rome_b200_set_barrier_range(self._h, family, first, count))
 
     def set_owned_variables(self, vartype: int, n_owned: int):
         """product / reanchor update only variables [0, n_owned) (the rest are halo copies); -1: all"""

@@ -242,8 +242,9 @@ class OwnerShardedSolver:
             tgt = f["i1"] if f["i1"] is not None else f["i0"]
             if (fam, "fwd") in self.bufs:
                 b = names.index((fam, "fwd"))
-                for fl in range(f["n_interior"]):
-                    per_var[tgt_vt][int(tgt[fl])].append((b, fl))
+                for fl in range(len(f["i0"])):
+                    if not (f["cut_first"] <= fl < f["cut_first"] + f["n_cut"]):   # interior: the target is owned here
+                        per_var[tgt_vt][int(tgt[fl])].append((b, fl))
                 b = names.index((fam, "recv"))
                 F = self.sh.families[fam]
                 lo = lv["loc"]["own"][tgt_vt][0]
@@ -282,8 +283,9 @@ class OwnerShardedSolver:
             f = lv["families"][fam]
             if (fam, "recv") in self.bufs and f["n_cut"]:
                 rowb = Np * FAMILY[fam][6] * 4
-                c.set_proposal_destinations(fam, 0, [0] * f["n_interior"] + [recv_ptr[int(d)][fam] + int(r) * rowb
-                                                                              for d, r in zip(f["dst_rank"], f["dst_row"])])
+                c.set_proposal_destinations(fam, 0, [0] * f["cut_first"] +
+                                            [recv_ptr[int(d)][fam] + int(r) * rowb for d, r in zip(f["dst_rank"], f["dst_row"])] +
+                                            [0] * (len(f["i0"]) - f["cut_first"] - f["n_cut"]))
         for vt, pushes in lv["loc"]["push"].items():
             src, dst, bb = [], [], c.particles_device(vt)[1]
             for reader, local_vars, slots in pushes:

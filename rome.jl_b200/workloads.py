@@ -125,8 +125,8 @@ def sharding_of(w, world, balance=True):
 
 def local_view(w, sh, rank, fill_halo=False):
     """rank-local arrays of workload `w` under sharding `sh`: particles of the owned variables followed by the halo
-    slots (zeros unless fill_halo: the owners push them), every family's factors in local order (interior, then cut)
-    with local variable indices"""
+    slots (zeros unless fill_halo: the owners push them), every family's factors in local table order (cut factors at
+    local indices [cut_first, cut_first + n_cut)) with local variable indices"""
     loc = sh.local(rank)
     particles = {}
     for vt, p in w["particles"].items():
@@ -142,6 +142,6 @@ def local_view(w, sh, rank, fill_halo=False):
         o = lf["order"]
         families[fam] = dict(i0=lf["i0"], i1=lf["i1"], a=np.asarray(f["a"])[o],
                              b=None if f["b"] is None else np.asarray(f["b"])[o],
-                             n_interior=lf["n_interior"], n_cut=lf["n_cut"], order=o,
+                             n_interior=lf["n_interior"], n_cut=lf["n_cut"], cut_first=lf["cut_first"], order=o,
                              dst_rank=lf["dst_rank"], dst_row=lf["dst_row"], recv=lf["recv"])
     return dict(N=w["N"], particles=particles, families=families, loc=loc)

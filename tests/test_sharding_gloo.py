@@ -126,7 +126,8 @@ def _owner_worker(rank, world, port, q):
         f = lv["families"][0]
         # "evaluate": interior rows stay local; every cut row is addressed (destination rank, row) -- gather what every
         # rank sends and let each rank apply the rows addressed to it (the GPUs do this with peer stores)
-        sends = [(int(d), int(r), _row_of(int(g))) for d, r, g in zip(f["dst_rank"], f["dst_row"], f["order"][f["n_interior"]:])]
+        cut_ids = f["order"][f["cut_first"]:f["cut_first"] + f["n_cut"]]
+        sends = [(int(d), int(r), _row_of(int(g))) for d, r, g in zip(f["dst_rank"], f["dst_row"], cut_ids)]
         halo_sends = []
         for vt, pushes in lv["loc"]["push"].items():
             for reader, local_vars, slots in pushes:
@@ -190,8 +191,11 @@ def test_owner_sharding_plan_properties():
         assert np.all((i0[f["order"]] >= lo) & (i0[f["order"]] < hi))
         gid1 = L["var_global"][1]
         assert np.array_equal(gid1[f["i1"]], i1[f["order"]])
-        cut_ids = f["order"][f["n_interior"]:]
-        assert np.all(sh.owner(1, i1[cut_ids]) != r) and np.all(sh.owner(1, i1[f["order"][:f["n_interior"]]]) == r)
+        cf = f["cut_first"]
+        cut_ids = f["order"][cf:cf + f["n_cut"]]
+        interior_ids = np.concatenate([f["order"][:cf], f["order"][cf + f["n_cut"]:]])
+        assert cf % 24 == 0 or f["n_cut"] == 0
+        assert np.all(sh.owner(1, i1[cut_ids]) != r) and np.all(sh.owner(1, i1[interior_ids]) == r)
         for d, row, g in zip(f["dst_rank"], f["dst_row"], cut_ids):
             assert sh.local(int(d))["fam"][2]["recv"][row] == g
         total_cut += f["n_cut"]
