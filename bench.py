@@ -488,6 +488,8 @@ def main():
         launches = sum(c.launch_count for c, _ in sets) - before
         for c, _ in sets:
             c.use_torch_stream()
+        if multi:
+            dist.barrier()  # replays carry the ranks' device-side barrier: start them together
         gr.replay()  # untimed replay: graph upload + warm instruction caches
         stream.synchronize()
         return gr, launches
@@ -517,12 +519,16 @@ def main():
         return float(t.item())
 
     clocks = ClockSampler(local)
+    if multi:
+        dist.barrier()   # the ranks enter the first fused-barrier step together (the device-side wait gives up after ~2 s)
     with torch.cuda.stream(stream):
         for c, _ in sets:
             c.use_torch_stream()
         for k in range(args.warmup):
             step(k)
         stream.synchronize()
+        if multi:
+            dist.barrier()
         g, launches_per_replay = capture(step)
         ms = timed(g, sample_clocks=True)
         window = "timed"

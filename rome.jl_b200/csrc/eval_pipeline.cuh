@@ -204,13 +204,16 @@ __device__ __forceinline__ void fused_barrier_signal(const EvalParams& P) {
 // launch of the bench workload; requesting more registers than the CTA was launched with hangs.  profiles/r02_analysis.md)
 template <int FT>
 constexpr int eval_threads() { return (FT + 1) * 32; }
+// resident CTAs per SM the kernel is compiled for: the 4-factor tile runs twice as many CTAs as the 8-factor tile
+template <class Fam, int FT>
+constexpr int eval_min_ctas() { return FT == 4 ? 2 * Fam::kMinCtas : Fam::kMinCtas; }
 // kRouted (the compile-time RESIDUAL|STATS variant of a ROUTED_ONLY launch): factors without a destination run the
 // compile-time RESIDUAL|STATS body; the few factors WITH one (a rank's cut factors) run the compile-time
 // RESIDUAL|STATS|PROPOSAL_FWD body, which also writes their forward row -- the common path keeps the instruction count
 // of the plain variant.  (An out-of-line run-time-flag body for the routed factors was measured: 6x slower per factor,
 // and the cut factors sit in the last tiles, i.e. on the kernel's critical path.)
 template <class Fam, uint32_t kStatic, bool kSample, int FT, bool kRouted = false>
-__global__ void __launch_bounds__(eval_threads<FT>(), Fam::kMinCtas) eval_kernel(const __grid_constant__ EvalParams P) {
+__global__ void __launch_bounds__(eval_threads<FT>(), eval_min_ctas<Fam, FT>()) eval_kernel(const __grid_constant__ EvalParams P) {
     using Row = typename Fam::Row;
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
@@ -556,6 +559,16 @@ int launch_sample(const EvalParams& p, const LaunchPlan& plan, int grid, cudaStr
             if (plan.variant == 3) return launch_ft<Fam, kHot1 | smp, kSample, 8, true>(p, plan, grid, s);
         }
         return launch_ft<Fam, 0u, kSample, 8>(p, plan, grid, s);
+    }
+    if constexpr (Fam::kMinCtas == 2) {
+        if (plan.ft == 4) {
+            if (plan.variant == 1) return launch_ft<Fam, kHot1 | smp, kSample, 4>(p, plan, grid, s);
+            if (plan.variant == 2) return launch_ft<Fam, kHot2 | smp, kSample, 4>(p, plan, grid, s);
+            if constexpr (Fam::DFWD > 0) {
+                if (plan.variant == 3) return launch_ft<Fam, kHot1 | smp, kSample, 4, true>(p, plan, grid, s);
+            }
+            return (int)cudaErrorInvalidValue;
+        }
     }
     if (plan.ft == 2) return launch_ft<Fam, 0u, kSample, 2>(p, plan, grid, s);
     if (plan.ft == 1) return launch_ft<Fam, 0u, kSample, 1>(p, plan, grid, s);

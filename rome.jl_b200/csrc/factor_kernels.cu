@@ -56,6 +56,18 @@ static int min_stages_2cta() {
     return v;
 }
 
+// tile size of the hot variants: 8 factors x 2 CTAs per SM; ROME_B200_TILE=4 selects 4 factors x 4 CTAs per SM (measured on
+// the bench workload: the kernel alone is 1 us faster -- its last, partly filled round costs half as much -- but a step
+// with a second, tiny family kernel is 0.8 us slower; profiles/r02_analysis.md)
+static int tile_choice() {
+    static int v = 0;
+    if (!v) {
+        const char* e = getenv("ROME_B200_TILE");
+        v = (e && atoi(e) == 4) ? 4 : 8;
+    }
+    return v;
+}
+
 // pipeline selection for the Pose3 families: per-warp pipelines unless ROME_B200_PIPELINE=cta
 static int pipeline_choice() {
     static int v = -1;
@@ -95,10 +107,29 @@ int plan_launch(int family, uint32_t flags, int Npad, int smem_per_sm, int smem_
             }
         }
     }
+    // Optional (ROME_B200_TILE=4) for the hot flag sets of the SE(2)-sized families: 4-factor tiles, FOUR CTAs (4 consumer
+    // warps + producer) per SM -- the same 16 consumer warps per SM as two 8-factor CTAs, but a persistent grid's last,
+    // partly filled round costs half as much (12 000 factors: 3 000 tiles on 592 CTAs instead of 1 500 on 296).
+    if (!se3 && hot != 0 && tile_choice() == 4) {
+        const int ft = 4, ctas = 4;
+        const int out_warp = (fd.dr + (hot == 1 ? 0 : fd.dfwd)) * Npad * 4;
+        const StageLayout L = stage_layout(ft, fd.row_bytes, fd.d0, fd.d1, fd.dm, sample, Npad);
+        const int budget = (smem_per_sm / ctas) - 1024;
+        const int cap = budget < smem_per_cta_max ? budget : smem_per_cta_max;
+        int stages = (cap - kBarrierBytes - ft * out_warp) / L.bytes;
+        if (stages > 4) stages = 4;
+        if (stages >= 3) {
+            plan->ft = ft; plan->variant = hot; plan->stages = stages; plan->stage_bytes = L.bytes;
+            plan->out_warp_bytes = out_warp;
+            plan->smem_bytes = kBarrierBytes + stages * L.bytes + ft * out_warp;
+            plan->ctas_per_sm = ctas;
+            return 0;
+        }
+    }
     static const int fts[3] = {8, 2, 1};
     for (int k = 0; k < 3; ++k) {
         const int ft = fts[k];
-        const int variant = ft == 8 ? hot : 0;  // compile-time flag variants exist for the 8-factor tile only
+        const int variant = ft == 8 ? hot : 0;  // compile-time flag variants exist for the 8- and 4-factor tiles only
         // per-warp output slice: residual rows, then forward-proposal rows (the generic variant reserves both)
         const int out_warp = (fd.dr + (variant == 1 ? 0 : fd.dfwd)) * Npad * 4;
         const StageLayout L = stage_layout(ft, fd.row_bytes, fd.d0, fd.d1, fd.dm, sample, Npad);

@@ -620,6 +620,8 @@ int rome_b200_eval(rome_b200_ctx* ctx, int family, uint32_t flags, uint64_t seed
         return fail(ctx, ROME_B200_SHAPE_MISMATCH, "N is too large for the shared-memory pipeline of this family");
     p.stages = plan.stages; p.stage_bytes = plan.stage_bytes; p.out_warp_bytes = plan.out_warp_bytes;
     const int nTiles = (count + plan.ft - 1) / plan.ft;
+    // (leaving one SM free for the small INDEPENDENT kernels launched next to a full persistent grid was measured: the
+    // dependent launches that follow get 1.5-2 us slower, profiles/r02_analysis.md)
     const int resident = ctx->num_sms * plan.ctas_per_sm;
     const int grid = nTiles < resident ? nTiles : resident;
     int e = launch_eval(family, p, plan, grid, ctx->stream);

@@ -172,7 +172,7 @@ class EmulatedContext:
                                                                        L.BARRIER_WAIT | L.BARRIER_SIGNAL)
         hot = 1 if out_flags == (L.RESIDUAL | L.STATS) else 2 if out_flags == (L.RESIDUAL | L.STATS | L.PROPOSAL_FWD) else 0
         plan = rb.plan_query(family, flags, N)
-        variant = hot if (plan["warps"] == 8 or plan["pipeline"] == 1) else 0
+        variant = hot if (plan["warps"] in (8, 4) or plan["pipeline"] == 1) else 0
         for name, a in (("meas", meas), ("meas_out", meas_out), ("res", res), ("prop_fwd", prop_fwd), ("prop_bwd", prop_bwd),
                         ("stats", stats), ("jac", jac)):
             assert a is None or (isinstance(a, np.ndarray) and a.dtype == np.float32 and a.flags.c_contiguous), name
