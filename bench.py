@@ -344,6 +344,10 @@ def main():
             b += len(f["i0"]) * (Np * rb.FAMILY[fam][3] * 4 + rb.FAMILY[fam][4] * 4 + 64)
         return b
     S = args.sets or int(min(64, max(12, -(-300e6 // max(set_bytes(), 1)))))
+    if multi:  # the same number of working sets on every rank (their handles are exchanged set by set)
+        t = torch.tensor([S], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        S = int(t.item())
     stream = torch.cuda.Stream()
 
     # ---- working sets ---------------------------------------------------------------------------------------------

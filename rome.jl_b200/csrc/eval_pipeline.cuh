@@ -182,15 +182,21 @@ __device__ __forceinline__ void fused_barrier_wait(const EvalParams& P, int lane
 }
 __device__ __forceinline__ void fused_barrier_signal(const EvalParams& P) {
     __syncthreads();  // every warp of this CTA has waited for its bulk stores
-    if (threadIdx.x == 0) {
-        __threadfence();
-        const uint32_t done = atomicAdd(P.bar_state + 12, 1u);
-        if (done == gridDim.x - 1) {  // the last CTA of the grid
-            __threadfence_system();
-            P.bar_state[12] = 0;
-            const uint32_t e = P.bar_state[8] + 1;
-            P.bar_state[8] = e;
-            for (int r = 0; r < P.bar_n; ++r) st_release_sys_u32(P.bar_peer[r], e);
+    if (threadIdx.x < 32) {
+        uint32_t done = 0;
+        if (threadIdx.x == 0) {
+            __threadfence();
+            done = atomicAdd(P.bar_state + 12, 1u);
+        }
+        done = __shfl_sync(0xffffffffu, done, 0);
+        if (done == gridDim.x - 1) {  // the last CTA of the grid: lane r publishes the epoch to peer r, all in parallel
+            const uint32_t e = *reinterpret_cast<volatile uint32_t*>(P.bar_state + 8) + 1;
+            __syncwarp();
+            if (threadIdx.x == 0) {
+                P.bar_state[12] = 0;
+                P.bar_state[8] = e;
+            }
+            if (threadIdx.x < (unsigned)P.bar_n) st_release_sys_u32(P.bar_peer[threadIdx.x], e);  // fence.sys + store each
         }
     }
 }
