@@ -298,7 +298,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline legs")
     ap.add_argument("--no-parity", action="store_true", help="skip the in-run parity check of a sampled subset against the oracle")
-    ap.add_argument("--barrier", default="fused", choices=["fused", "flags", "nccl"],
+    ap.add_argument("--barrier", default="fused", choices=["fused", "flags", "nccl", "none"],
                     help="G>1: rank barrier fused into the evaluation kernels (default: the step's first launch waits for the "
                          "peers' flags, its last launch publishes this rank's), by two one-warp flag kernels, or by a 4-byte "
                          "NCCL all-reduce")
@@ -418,7 +418,7 @@ def main():
 
     def rank_barrier(c):
         """stream-ordered barrier between the ranks (after everything enqueued so far on the launch stream)"""
-        if args.barrier in ("flags", "fused"):
+        if args.barrier in ("flags", "fused", "none"):
             c.peer_signal(state, peer_slots)
             c.peer_wait(state, G - 1)
         else:
@@ -478,7 +478,7 @@ def main():
                 # epilogue runs after all launches of the step have completed) publishes this rank's epoch
                 fl |= (rb.BARRIER_WAIT if (fl & rb.ROUTED_ONLY) else 0) | (rb.BARRIER_SIGNAL if idx == len(todo) - 1 else 0)
             c.eval(fam, fl, seed=7, stream_id=k, **kw)
-        if multi and barrier and args.barrier != "fused":
+        if multi and barrier and args.barrier in ("flags", "nccl"):   # "none": experiment only -- steps of the ranks uncoupled
             rank_barrier(c)
 
     def capture(fn, **kw):

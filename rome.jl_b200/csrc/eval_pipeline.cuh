@@ -150,6 +150,29 @@ constexpr int kBarrierBytes = 128;
 constexpr int kMaxStages = 6;
 
 // =============================================================================================
+// Order in which a persistent CTA visits its tiles (tile b + i * grid, i = 0 .. n-1).  A launch that has to pass the rank
+// barrier visits the tiles holding peer-dependent factors (a contiguous range of tile indices) LAST: the fetching warp
+// runs several tiles ahead of the arithmetic, so in table order it would meet the barrier at the very start of the
+// kernel, before the peers' signals of the previous step can have arrived.
+// =============================================================================================
+struct TileOrder {
+    int n, i0, nc;  // tiles of this CTA; its peer-dependent tiles are i0 .. i0 + nc - 1
+    __device__ __forceinline__ void init(int nTiles, int grid, int b, bool defer, int c0, int c1 /* tile range */) {
+        n = nTiles > b ? (nTiles - b + grid - 1) / grid : 0;
+        i0 = n; nc = 0;
+        if (defer && c1 >= c0 && n > 0) {
+            int lo = c0 <= b ? 0 : (c0 - b + grid - 1) / grid;        // first i with b + i grid >= c0
+            int hi = c1 < b ? -1 : (c1 - b) / grid;                    // last i with b + i grid <= c1
+            if (hi > n - 1) hi = n - 1;
+            if (hi >= lo) { i0 = lo; nc = hi - lo + 1; }
+        }
+    }
+    __device__ __forceinline__ int at(int j) const {  // position j of the visiting order -> i
+        return j < i0 ? j : (j < n - nc ? j + nc : i0 + (j - (n - nc)));
+    }
+};
+
+// =============================================================================================
 // rank barrier fused into the evaluation kernels (owner-sharded multi-GPU sweeps; the state buffer is the one of
 // rome_b200_peer_signal / _wait: words [0, 8) flag slots written by the peers, word 8 this rank's signal epoch, word 10
 // give-up status, word 12 the CTA counter of the signalling launch).
@@ -238,14 +261,22 @@ __global__ void __launch_bounds__(eval_threads<FT>(), eval_min_ctas<Fam, FT>()) 
     constexpr int TPC = 32 / FT;  // tiles per chunk
     const int jl = lane / FT, fl_in_tile = lane % FT;
     int2 ids_cur = make_int2(0, 0);
-    auto fetch_chunk = [&](int base_tile) {
-        const int t = base_tile + jl * (int)gridDim.x;
-        const int fl = t * FT + fl_in_tile;
+    TileOrder ord;  // visiting order of this CTA's tiles (peer-dependent tiles last when the launch passes the rank barrier)
+    {
+        const int lo = P.bar_lo - P.first, hi = P.bar_hi - P.first;  // peer-dependent factors, relative to the launch range
+        ord.init(nTiles, (int)gridDim.x, (int)blockIdx.x, (P.flags & ROME_B200_BARRIER_WAIT) != 0 && hi > 0 && lo < P.count,
+                 (lo > 0 ? lo : 0) / FT, ((hi < P.count ? hi : P.count) - 1) / FT);
+    }
+    auto fetch_chunk = [&](int base_j) {  // ids of visiting positions base_j .. base_j + TPC - 1
+        const int j = base_j + jl;
         int2 ids = make_int2(0, 0);
-        if (t < nTiles && fl < P.count) ids = __ldg(reinterpret_cast<const int2*>(table + fl));
+        if (j < ord.n) {
+            const int fl = ((int)blockIdx.x + ord.at(j) * (int)gridDim.x) * FT + fl_in_tile;
+            if (fl < P.count) ids = __ldg(reinterpret_cast<const int2*>(table + fl));
+        }
         return ids;
     };
-    if (warp == FT) ids_cur = fetch_chunk(blockIdx.x);
+    if (warp == FT) ids_cur = fetch_chunk(0);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
@@ -272,12 +303,12 @@ __global__ void __launch_bounds__(eval_threads<FT>(), eval_min_ctas<Fam, FT>()) 
         uint32_t phase = 1;  // parity of the previous round; the first pass over the ring does not wait
         bool first_round = true;
         bool synced = !(P.flags & ROME_B200_BARRIER_WAIT);  // rank barrier still to be passed?
-        for (int base = blockIdx.x; base < nTiles; base += TPC * gridDim.x) {
-            const int2 ids_next = fetch_chunk(base + TPC * gridDim.x);  // in flight while this chunk is issued
+        for (int base = 0; base < ord.n; base += TPC) {
+            const int2 ids_next = fetch_chunk(base + TPC);  // in flight while this chunk is issued
 #pragma unroll 1
             for (int j = 0; j < TPC; ++j) {
-                const int tile = base + j * gridDim.x;
-                if (tile >= nTiles) break;
+                if (base + j >= ord.n) break;
+                const int tile = (int)blockIdx.x + ord.at(base + j) * (int)gridDim.x;
                 if (!first_round) mbar_wait(&empty[s], phase);
                 unsigned char* st = stage0 + (size_t)s * L.bytes;
                 const int t0 = tile * FT, nf = min(FT, P.count - tile * FT);
@@ -312,7 +343,8 @@ __global__ void __launch_bounds__(eval_threads<FT>(), eval_min_ctas<Fam, FT>()) 
         int s = 0;
         uint32_t phase = 0;
         bool wrote_peer = false;  // did this warp store rows into another GPU's memory?
-        for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
+        for (int j = 0; j < ord.n; ++j) {
+            const int tile = (int)blockIdx.x + ord.at(j) * (int)gridDim.x;
             const int fl = tile * FT + warp;
             const bool mine = fl < P.count;
             const int f = P.first + fl;
@@ -412,17 +444,29 @@ __global__ void __launch_bounds__(FT * 32, Fam::kMinCtas) eval_kernel_w(const __
     const uint32_t flags = kStatic ? kStatic : P.flags;
     const int res_floats = Fam::DR * P.Npad;
     // the i-th factor of this warp: tile blockIdx.x + i * gridDim.x, slot `warp` (-1: none)
-    auto factor_of = [&](int i) {
-        const int fl = (blockIdx.x + i * (int)gridDim.x) * FT + warp;
+    TileOrder ord;
+    {
+        const int nTiles = (P.count + FT - 1) / FT;
+        const int lo = P.bar_lo - P.first, hi = P.bar_hi - P.first;
+        ord.init(nTiles, (int)gridDim.x, (int)blockIdx.x, (P.flags & ROME_B200_BARRIER_WAIT) != 0 && hi > 0 && lo < P.count,
+                 (lo > 0 ? lo : 0) / FT, ((hi < P.count ? hi : P.count) - 1) / FT);
+    }
+    auto factor_of = [&](int j) {  // the factor this warp evaluates at visiting position j
+        if (j >= ord.n) return -1;
+        const int fl = ((int)blockIdx.x + ord.at(j) * (int)gridDim.x) * FT + warp;
         return fl < P.count ? fl : -1;
     };
     auto fetch_ids = [&](int i) {
         const int fl = factor_of(i);
         return fl >= 0 ? __ldg(reinterpret_cast<const int2*>(table + fl)) : make_int2(0, 0);
     };
-    auto issue = [&](int i, int s, int2 ids) {  // one lane: bulk copies of factor i into stage s
+    auto issue = [&](int i, int s, int2 ids) {  // one lane: bulk copies of the factor of position i into stage s
+        if (i >= ord.n) return;
         const int fl = factor_of(i);
-        if (fl < 0) return;
+        if (fl < 0) {  // this warp has no factor in that tile (the partial last tile): complete the stage's phase as is
+            mbar_arrive(&bar[s]);
+            return;
+        }
         unsigned char* st = slots + (size_t)s * L.bytes;
         fence_proxy_async();
         mbar_arrive_expect_tx(&bar[s], (uint32_t)((int)sizeof(Row) + L.b0 + L.b1 + L.mb));
@@ -456,14 +500,14 @@ __global__ void __launch_bounds__(FT * 32, Fam::kMinCtas) eval_kernel_w(const __
     int s = 0;
     uint32_t phase = 0;
     bool wrote_peer = false;
-    for (int i = 0;; ++i) {
+    for (int i = 0; i < ord.n; ++i) {
         const int fl = factor_of(i);
-        if (fl < 0) break;
         const int f = P.first + fl;
         unsigned long long fdst = 0;  // owner-sharded exchange: per-factor destination of the forward row
-        if (((flags & ROME_B200_PROPOSAL_FWD) || kRouted) && P.fwd_dst) fdst = __ldg(P.fwd_dst + f);
+        if (fl >= 0 && ((flags & ROME_B200_PROPOSAL_FWD) || kRouted) && P.fwd_dst) fdst = __ldg(P.fwd_dst + f);
         if (lane == s) ids = fetch_ids(i + S);  // consumed when this factor is done: hidden behind its arithmetic
         mbar_wait(&bar[s], phase);
+        if (fl >= 0) {
         const unsigned char* st = slots + (size_t)s * L.bytes;
         const Row row = *reinterpret_cast<const Row*>(st + L.row_off);
         FactorView V;
@@ -495,6 +539,7 @@ __global__ void __launch_bounds__(FT * 32, Fam::kMinCtas) eval_kernel_w(const __
                 }
                 tma_store_commit();
             }
+        }
         }
         __syncwarp();  // every lane has finished reading stage s
         sync_before(i + S);

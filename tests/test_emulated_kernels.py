@@ -506,3 +506,40 @@ def test_pipeline_with_asynchronous_copies(hk_so, max_delay):
             outs.append(out)
         for key in outs[0]:
             assert np.array_equal(outs[0][key], outs[1][key], equal_nan=True), (trial, fam, N, nF, first, count, flags, key, pipe.last_plan)
+
+
+@pytest.mark.parametrize("grid", [1, 3, 7])
+def test_deferred_tiles_do_not_change_results(hk_so, grid):
+    """A launch that passes the rank barrier (BARRIER_WAIT) visits the tiles of its peer-dependent factor range LAST
+    (TileOrder, csrc/eval_pipeline.cuh): every factor is still evaluated exactly once with the same result -- both
+    pipelines (producer warp: Pose2Pose2 / BearingRange, per-warp rings: Pose3Pose3), ranges at the start, in the middle,
+    at the end, covering everything, empty, and a partial last tile"""
+    import ctypes as C
+    import rome_b200 as rb
+    from emu import EmulatedContext
+    T = _raw()
+    c = EmulatedContext(hk_so, pipeline=True, grid_cap=grid)
+    rng = np.random.default_rng(50 + grid)
+    N, nvars, nF = 40, 60, 203   # 203 = 25 tiles of 8 + 3, 16 tiles of 12 + 11
+    poses, ip, iq = T.make_pose2_graph(rng, nvars, nF, N)
+    c.set_particles(rb.POSE2, poses)
+    c.set_factors_pose2pose2(ip, iq, rng.normal(size=(nF, 3)), T.rand_cov(rng, nF, 3, [0.1, 0.1, 0.02]))
+    p3 = T.make_pose3(rng, nvars, N)
+    c.set_particles(rb.POSE3, p3)
+    c.set_factors_pose3pose3(ip, iq, rng.normal(size=(nF, 6)) * 0.2, T.rand_cov(rng, nF, 6, [0.1] * 3 + [0.01] * 3))
+    hk = c._hk
+    hk.hk_set_barrier_range.argtypes = [C.c_int, C.c_int]
+    for fam in (rb.POSE2POSE2, rb.POSE3POSE3):
+        fl = rb.SAMPLE | rb.RESIDUAL | rb.STATS
+        hk.hk_set_barrier_range(0, 2 ** 31 - 1)
+        ref = c.alloc_host_outputs(fam, fl)
+        c.eval_host(fam, fl, seed=3, **ref)
+        for lo, hi in ((0, 16), (72, 131), (96, 97), (180, 203), (0, 203), (50, 50), (199, 400)):
+            for first, count in ((0, -1), (24, 150)):
+                hk.hk_set_barrier_range(lo, hi)
+                out = c.alloc_host_outputs(fam, fl)
+                c.eval_host(fam, fl | rb.BARRIER_WAIT, seed=3, first=first, count=count, **out)
+                a, b = first, nF if count < 0 else first + count
+                assert np.array_equal(out["res"][a:b], ref["res"][a:b]) and np.array_equal(out["stats"][a:b], ref["stats"][a:b]), (fam, lo, hi, first)
+                assert not out["res"][:a].any() and not out["res"][b:].any()
+    hk.hk_set_barrier_range(0, 2 ** 31 - 1)
