@@ -464,19 +464,23 @@ def main():
         those go straight into the owners' receive buffers; the rank barrier rides on the step's first / last launch."""
         c, bufs = sets[k % S]
         todo = [fam for fam in (fams or fam_order) if len(lv["families"][fam]["i0"]) > 0]
+        is_routed = [bool(multi and rb.FAMILY[fam][6] and lv["families"][fam]["n_cut"] > 0) for fam in todo]
+        # every launch with cut factors passes the barrier before its cut tiles; the LAST of them publishes this rank's
+        # epoch when its grid has finished (its epilogue runs after the launches before it have completed, so none of
+        # them is still polling; launches behind it touch nothing a peer can see).  A rank without cut factors signals
+        # from its first launch.
+        signal_idx = max([i for i, r in enumerate(is_routed) if r], default=0)
         for idx, fam in enumerate(todo):
             f, b = lv["families"][fam], bufs[fam]
             fl = F0
             kw = dict(res=b["res"], stats=b["stats"])
-            if multi and rb.FAMILY[fam][6] and f["n_cut"] > 0:
+            if is_routed[idx]:
                 fl |= rb.PROPOSAL_FWD | rb.ROUTED_ONLY
                 kw["prop_fwd"] = dummy_fwd[fam]  # default rows are never written: every cut factor has a destination
             if idx > 0 or indep_all:
                 fl |= rb.INDEPENDENT
             if multi and barrier and args.barrier == "fused":
-                # every launch with cut factors passes the barrier before its cut block; the step's LAST launch (its
-                # epilogue runs after all launches of the step have completed) publishes this rank's epoch
-                fl |= (rb.BARRIER_WAIT if (fl & rb.ROUTED_ONLY) else 0) | (rb.BARRIER_SIGNAL if idx == len(todo) - 1 else 0)
+                fl |= (rb.BARRIER_WAIT if is_routed[idx] else 0) | (rb.BARRIER_SIGNAL if idx == signal_idx else 0)
             c.eval(fam, fl, seed=7, stream_id=k, **kw)
         if multi and barrier and args.barrier in ("flags", "nccl"):   # "none": experiment only -- steps of the ranks uncoupled
             rank_barrier(c)
@@ -618,6 +622,11 @@ def main():
                     rows_checked += len(rows)
                     chk.close()
         gave_up = bool(sets[0][0].peer_gave_up(state)) if args.barrier != "nccl" else False
+        words = np.zeros(16, np.uint32)
+        sets[0][0].memcpy_d2h(words, state)
+        print(f"[rank {rank}] barrier state: signals {words[8]}, passes {words[14]}, mean cycles per pass "
+              f"{words[13] / max(1, words[14]):.0f}, publish cycles per signal {words[15] / max(1, words[8]):.0f} "
+              f"(wrapping 32-bit sums)", file=sys.stderr)
         flag = torch.tensor([1.0 if (ok and halo_ok and not gave_up) else 0.0, float(rows_checked), worst, float(halo_checked)],
                             device="cuda", dtype=torch.float64)
         mn = flag.clone()

@@ -67,6 +67,12 @@ __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk
 // all of this thread's bulk stores have finished READING shared memory (the source may be overwritten)
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// all but the newest n (0..2) of this thread's bulk-store groups are complete (written, not merely read)
+__device__ __forceinline__ void tma_store_wait_pending(int n) {
+    if (n <= 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    else if (n == 1) asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
+    else asm volatile("cp.async.bulk.wait_group 2;" ::: "memory");
+}
 
 // system-scope release store / acquire load (flags in peer-GPU memory over NVLink)
 __device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {

@@ -150,27 +150,47 @@ constexpr int kBarrierBytes = 128;
 constexpr int kMaxStages = 6;
 
 // =============================================================================================
-// Order in which a persistent CTA visits its tiles (tile b + i * grid, i = 0 .. n-1).  A launch that has to pass the rank
-// barrier visits the tiles holding peer-dependent factors (a contiguous range of tile indices) LAST: the fetching warp
-// runs several tiles ahead of the arithmetic, so in table order it would meet the barrier at the very start of the
-// kernel, before the peers' signals of the previous step can have arrived.
+// Order in which a persistent CTA visits its tiles (tile b + i * grid, i = 0 .. n-1).  A launch that takes part in the
+// rank barrier visits the tiles holding peer-dependent factors (a contiguous range of tile indices) FIRST:
+//   * they are the only tiles that must wait for the peers (BARRIER_WAIT) -- and what they wait for, the peers' signal of
+//     the PREVIOUS step, was published early in that step (next point), i.e. long ago;
+//   * once the rows they store into peer memory have landed, this rank's signal can go out (BARRIER_SIGNAL) while the
+//     interior tiles, the bulk of the launch, are still being evaluated: the latency of the NVLink stores, of the
+//     system-scope fence and of the flag's flight all hide behind interior work instead of following the kernel.
 // =============================================================================================
 struct TileOrder {
-    int n, i0, nc;  // tiles of this CTA; its peer-dependent tiles are i0 .. i0 + nc - 1
-    __device__ __forceinline__ void init(int nTiles, int grid, int b, bool defer, int c0, int c1 /* tile range */) {
+    int n, i0, nc;     // tiles of this CTA; its peer-dependent tiles are i0 .. i0 + nc - 1
+    int cut_ctas;      // CTAs of the grid that hold peer-dependent tiles
+    __device__ __forceinline__ void init(int nTiles, int grid, int b, bool front, int c0, int c1 /* tile range */) {
         n = nTiles > b ? (nTiles - b + grid - 1) / grid : 0;
-        i0 = n; nc = 0;
-        if (defer && c1 >= c0 && n > 0) {
-            int lo = c0 <= b ? 0 : (c0 - b + grid - 1) / grid;        // first i with b + i grid >= c0
-            int hi = c1 < b ? -1 : (c1 - b) / grid;                    // last i with b + i grid <= c1
-            if (hi > n - 1) hi = n - 1;
-            if (hi >= lo) { i0 = lo; nc = hi - lo + 1; }
+        i0 = 0; nc = 0; cut_ctas = 0;
+        if (c1 > nTiles - 1) c1 = nTiles - 1;
+        if (front && c1 >= c0) {
+            cut_ctas = (c1 - c0 + 1) < grid ? (c1 - c0 + 1) : grid;
+            if (n > 0) {
+                int lo = c0 <= b ? 0 : (c0 - b + grid - 1) / grid;        // first i with b + i grid >= c0
+                int hi = c1 < b ? -1 : (c1 - b) / grid;                    // last i with b + i grid <= c1
+                if (hi > n - 1) hi = n - 1;
+                if (hi >= lo) { i0 = lo; nc = hi - lo + 1; }
+            }
         }
     }
     __device__ __forceinline__ int at(int j) const {  // position j of the visiting order -> i
-        return j < i0 ? j : (j < n - nc ? j + nc : i0 + (j - (n - nc)));
+        if (j < nc) return i0 + j;
+        const int k = j - nc;
+        return k < i0 ? k : k + nc;
     }
 };
+// owner of the barrier range of a launch, relative to its factor range: tile range [c0, c1] (c1 < c0: none)
+__device__ __forceinline__ void barrier_tiles(const EvalParams& P, int ft, int& c0, int& c1) {
+    const int lo = P.bar_lo - P.first, hi = P.bar_hi - P.first;
+    if (!(P.flags & (ROME_B200_BARRIER_WAIT | ROME_B200_BARRIER_SIGNAL)) || hi <= 0 || lo >= P.count || hi <= lo) {
+        c0 = 0; c1 = -1;
+        return;
+    }
+    c0 = (lo > 0 ? lo : 0) / ft;
+    c1 = ((hi < P.count ? hi : P.count) - 1) / ft;
+}
 
 // =============================================================================================
 // rank barrier fused into the evaluation kernels (owner-sharded multi-GPU sweeps; the state buffer is the one of
@@ -180,7 +200,8 @@ struct TileOrder {
 //       factors; default: every factor -- is fetched, the fetching warp polls the local flag slots until each peer has
 //       signalled as often as this rank has (word 8): the peers' previous step, with its stores into this GPU's memory,
 //       is complete.
-//   ROME_B200_BARRIER_SIGNAL (last launch of a step): the CTA that finishes last publishes the next epoch to the slot
+//   ROME_B200_BARRIER_SIGNAL: as soon as the launch's peer-dependent tiles have landed (they are visited first, see
+//       TileOrder) -- or, for a launch without any, when its grid has finished -- the next epoch is published to the slot
 //       this rank owns in every peer's state (st.release.sys after a system-scope fence: the rows this grid stored into
 //       peer memory are visible before the flag).
 // No extra kernel, no host round trip: the barrier costs the NVLink latency of a 4-byte store.
@@ -189,9 +210,9 @@ struct TileOrder {
 // fetched: the other factors -- a rank's interior factors -- neither read halo blocks nor write into peer memory, so
 // their evaluation overlaps the barrier's latency
 __device__ __forceinline__ void fused_barrier_wait(const EvalParams& P, int lane) {
+    const long long t0 = clock64();
     if (lane < P.bar_n) {
         const uint32_t target = *reinterpret_cast<volatile const uint32_t*>(P.bar_state + 8);
-        const long long t0 = clock64();
         for (;;) {
             const uint32_t v = ld_acquire_sys_u32(P.bar_state + lane);
             if ((int32_t)(v - target) >= 0) break;  // wrap-safe "v >= target"
@@ -202,6 +223,10 @@ __device__ __forceinline__ void fused_barrier_wait(const EvalParams& P, int lane
         }
     }
     __syncwarp();
+    if (lane == 0) {  // instrumentation (words 13 / 14 of the state): cycles spent at the barrier, number of passes
+        atomicAdd(P.bar_state + 13, (uint32_t)(clock64() - t0));
+        atomicAdd(P.bar_state + 14, 1u);
+    }
 }
 __device__ __forceinline__ void fused_barrier_signal(const EvalParams& P) {
     __syncthreads();  // every warp of this CTA has waited for its bulk stores
@@ -213,6 +238,7 @@ __device__ __forceinline__ void fused_barrier_signal(const EvalParams& P) {
         }
         done = __shfl_sync(0xffffffffu, done, 0);
         if (done == gridDim.x - 1) {  // the last CTA of the grid: lane r publishes the epoch to peer r, all in parallel
+            const long long t0 = clock64();
             const uint32_t e = *reinterpret_cast<volatile uint32_t*>(P.bar_state + 8) + 1;
             __syncwarp();
             if (threadIdx.x == 0) {
@@ -220,13 +246,41 @@ __device__ __forceinline__ void fused_barrier_signal(const EvalParams& P) {
                 P.bar_state[8] = e;
             }
             if (threadIdx.x < (unsigned)P.bar_n) st_release_sys_u32(P.bar_peer[threadIdx.x], e);  // fence.sys + store each
+            __syncwarp();
+            if (threadIdx.x == 0) atomicAdd(P.bar_state + 15, (uint32_t)(clock64() - t0));  // instrumentation: publish cycles
         }
+    }
+}
+
+// Early signal (see TileOrder): executed by every consumer warp of a CTA that holds peer-dependent tiles, one or two
+// tiles after the last of them.  `pending` = bulk-store groups the warp has committed since its peer-dependent tiles (0..2):
+// all older groups -- the rows in peer memory -- are waited for, made visible system-wide, and the warp is counted;
+// the last warp of the last such CTA publishes the epoch.  `expected` = arrivals that complete the count.
+__device__ __forceinline__ void early_signal(const EvalParams& P, int lane, int pending, uint32_t expected, int* cta_count,
+                                             int cta_warps) {
+    uint32_t pub = 0;
+    if (lane == 0) {
+        tma_store_wait_pending(pending);
+        __threadfence_system();
+        bool cta_last = true;
+        if (cta_count) cta_last = atomicAdd(cta_count, 1) == cta_warps - 1;  // CTA-level count first (shared memory)
+        if (cta_last) pub = (atomicAdd(P.bar_state + 12, 1u) == expected - 1) ? 1u : 0u;
+    }
+    pub = __shfl_sync(0xffffffffu, pub, 0);
+    if (pub) {
+        const uint32_t e = *reinterpret_cast<volatile uint32_t*>(P.bar_state + 8) + 1;
+        __syncwarp();
+        if (lane == 0) {
+            P.bar_state[12] = 0;
+            P.bar_state[8] = e;
+        }
+        if (lane < P.bar_n) st_release_sys_u32(P.bar_peer[lane], e);
     }
 }
 
 // =============================================================================================
 // persistent producer/consumer pipeline
-//   smem: [full[], empty[] mbarriers | S input stages | FT per-warp output slices]
+//   smem: [full[], empty[] mbarriers, early-signal counter | S input stages | FT per-warp output slices]
 // =============================================================================================
 // (A warpgroup register re-allocation -- 384 threads, setmaxnreg.inc 104 for the two consumer warpgroups, .dec 24 for the
 // producer's -- was measured on B200 and is SLOWER than this 288-thread form at 96 registers: 16.6 vs 15.8 us per
@@ -261,12 +315,16 @@ __global__ void __launch_bounds__(eval_threads<FT>(), eval_min_ctas<Fam, FT>()) 
     constexpr int TPC = 32 / FT;  // tiles per chunk
     const int jl = lane / FT, fl_in_tile = lane % FT;
     int2 ids_cur = make_int2(0, 0);
-    TileOrder ord;  // visiting order of this CTA's tiles (peer-dependent tiles last when the launch passes the rank barrier)
+    TileOrder ord;  // visiting order of this CTA's tiles (peer-dependent tiles first when the launch takes part in the barrier)
     {
-        const int lo = P.bar_lo - P.first, hi = P.bar_hi - P.first;  // peer-dependent factors, relative to the launch range
-        ord.init(nTiles, (int)gridDim.x, (int)blockIdx.x, (P.flags & ROME_B200_BARRIER_WAIT) != 0 && hi > 0 && lo < P.count,
-                 (lo > 0 ? lo : 0) / FT, ((hi < P.count ? hi : P.count) - 1) / FT);
+        int c0, c1;
+        barrier_tiles(P, FT, c0, c1);
+        ord.init(nTiles, (int)gridDim.x, (int)blockIdx.x, c1 >= c0, c0, c1);
     }
+    // the signal goes out as soon as the peer-dependent tiles have landed (early), or -- a launch without such tiles, or
+    // one that replicates its rows to every peer -- when the whole grid has finished
+    const bool sig_early = (P.flags & ROME_B200_BARRIER_SIGNAL) && ord.cut_ctas > 0 && P.n_peers == 0;
+    int* sig_count = reinterpret_cast<int*>(smem + 2 * kMaxStages * 8);
     auto fetch_chunk = [&](int base_j) {  // ids of visiting positions base_j .. base_j + TPC - 1
         const int j = base_j + jl;
         int2 ids = make_int2(0, 0);
@@ -283,6 +341,7 @@ __global__ void __launch_bounds__(eval_threads<FT>(), eval_min_ctas<Fam, FT>()) 
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], FT);
         }
+        *sig_count = 0;
         fence_mbar_init();
     }
     __syncthreads();
@@ -343,6 +402,8 @@ __global__ void __launch_bounds__(eval_threads<FT>(), eval_min_ctas<Fam, FT>()) 
         int s = 0;
         uint32_t phase = 0;
         bool wrote_peer = false;  // did this warp store rows into another GPU's memory?
+        int after_cut = 0;        // bulk-store groups committed since the peer-dependent tiles
+        const int sig_pos = sig_early && ord.nc > 0 ? (ord.nc + 1 < ord.n ? ord.nc + 1 : ord.n - 1) : -1;
         for (int j = 0; j < ord.n; ++j) {
             const int tile = (int)blockIdx.x + ord.at(j) * (int)gridDim.x;
             const int fl = tile * FT + warp;
@@ -385,23 +446,25 @@ __global__ void __launch_bounds__(eval_threads<FT>(), eval_min_ctas<Fam, FT>()) 
                             for (int r = 0; r < P.n_peers; ++r) tma_store_1d(P.peer_fwd[r] + off, V.out_fwd, bytes);
                         }
                         tma_store_commit();
+                        if (j >= ord.nc) ++after_cut;
                     }
                 }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
             if (++s == S) { s = 0; phase ^= 1u; }
+            if (j == sig_pos) early_signal(P, lane, after_cut, (uint32_t)ord.cut_ctas, sig_count, FT);
         }
         if (lane == 0) {
             tma_store_wait_all();
-            // rows stored into peer memory are performed system-wide before this CTA reports completion (only the
-            // warps that have such rows pay for the system-scope fence)
-            if ((P.flags & ROME_B200_BARRIER_SIGNAL) && wrote_peer) __threadfence_system();
+            // end-of-grid signal: rows stored into peer memory are performed system-wide before this CTA reports
+            // completion (only the warps that have such rows pay for the system-scope fence)
+            if ((P.flags & ROME_B200_BARRIER_SIGNAL) && !sig_early && wrote_peer) __threadfence_system();
         }
     }
     // a launch that overlapped its predecessor must not be seen as complete before the predecessor is
     if (P.flags & ROME_B200_INDEPENDENT) asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (P.flags & ROME_B200_BARRIER_SIGNAL) fused_barrier_signal(P);
+    if ((P.flags & ROME_B200_BARRIER_SIGNAL) && !sig_early) fused_barrier_signal(P);
 }
 // =============================================================================================
 // per-warp pipeline ("warp pipeline"): no producer warp and no CTA-wide barrier.  Warp w of a CTA owns slot w of
@@ -446,11 +509,11 @@ __global__ void __launch_bounds__(FT * 32, Fam::kMinCtas) eval_kernel_w(const __
     // the i-th factor of this warp: tile blockIdx.x + i * gridDim.x, slot `warp` (-1: none)
     TileOrder ord;
     {
-        const int nTiles = (P.count + FT - 1) / FT;
-        const int lo = P.bar_lo - P.first, hi = P.bar_hi - P.first;
-        ord.init(nTiles, (int)gridDim.x, (int)blockIdx.x, (P.flags & ROME_B200_BARRIER_WAIT) != 0 && hi > 0 && lo < P.count,
-                 (lo > 0 ? lo : 0) / FT, ((hi < P.count ? hi : P.count) - 1) / FT);
+        int c0, c1;
+        barrier_tiles(P, FT, c0, c1);
+        ord.init((P.count + FT - 1) / FT, (int)gridDim.x, (int)blockIdx.x, c1 >= c0, c0, c1);
     }
+    const bool sig_early = (P.flags & ROME_B200_BARRIER_SIGNAL) && ord.cut_ctas > 0 && P.n_peers == 0;
     auto factor_of = [&](int j) {  // the factor this warp evaluates at visiting position j
         if (j >= ord.n) return -1;
         const int fl = ((int)blockIdx.x + ord.at(j) * (int)gridDim.x) * FT + warp;
@@ -500,6 +563,8 @@ __global__ void __launch_bounds__(FT * 32, Fam::kMinCtas) eval_kernel_w(const __
     int s = 0;
     uint32_t phase = 0;
     bool wrote_peer = false;
+    int after_cut = 0;
+    const int sig_pos = sig_early && ord.nc > 0 ? (ord.nc + 1 < ord.n ? ord.nc + 1 : ord.n - 1) : -1;
     for (int i = 0; i < ord.n; ++i) {
         const int fl = factor_of(i);
         const int f = P.first + fl;
@@ -538,20 +603,23 @@ __global__ void __launch_bounds__(FT * 32, Fam::kMinCtas) eval_kernel_w(const __
                     for (int r = 0; r < P.n_peers; ++r) tma_store_1d(P.peer_fwd[r] + off, V.out_fwd, bytes);
                 }
                 tma_store_commit();
+                if (i >= ord.nc) ++after_cut;
             }
         }
         }
         __syncwarp();  // every lane has finished reading stage s
+        // early signal: every warp of a CTA with peer-dependent tiles is counted (FT warps per such CTA)
+        if (i == sig_pos) early_signal(P, lane, after_cut, (uint32_t)(ord.cut_ctas * FT), nullptr, 0);
         sync_before(i + S);
         if (lane == s) issue(i + S, s, ids);
         if (++s == S) { s = 0; phase ^= 1u; }
     }
     if (lane == 0) {
         tma_store_wait_all();
-        if ((P.flags & ROME_B200_BARRIER_SIGNAL) && wrote_peer) __threadfence_system();
+        if ((P.flags & ROME_B200_BARRIER_SIGNAL) && !sig_early && wrote_peer) __threadfence_system();
     }
     if (P.flags & ROME_B200_INDEPENDENT) asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (P.flags & ROME_B200_BARRIER_SIGNAL) fused_barrier_signal(P);
+    if ((P.flags & ROME_B200_BARRIER_SIGNAL) && !sig_early) fused_barrier_signal(P);
 }
 
 template <class K>

@@ -198,6 +198,7 @@ static inline float hk_shfl(float v, int src_lane_fn(int lane, int arg), int arg
 static inline float __shfl_xor_sync(unsigned, float v, int bit) { return hk_shfl(v, [](int l, int a) { return l ^ a; }, bit); }
 static inline float __shfl_up_sync(unsigned, float v, int d) { return hk_shfl(v, [](int l, int a) { return l - a; }, d); }
 static inline float __shfl_sync(unsigned, float v, int src) { return hk_shfl(v, [](int, int a) { return a & 31; }, src); }
+static inline uint32_t __shfl_sync(unsigned, uint32_t v, int src) { return hk::collective(v)[src & 31]; }
 static inline void __syncwarp(unsigned = 0xffffffffu) { hk::collective(0u); }
 static inline void __syncthreads() { hk::block_barrier(); }
 template <class T> static inline T __ldg(const T* p) { return *p; }
@@ -213,6 +214,7 @@ static inline long long clock64() { return ++hk_clock_ticks; }
 static inline void __threadfence_system() {}
 static inline void __threadfence() {}
 static inline uint32_t atomicAdd(uint32_t* p, uint32_t v) { const uint32_t o = *p; *p = o + v; return o; }
+static inline int atomicAdd(int* p, int v) { const int o = *p; *p = o + v; return o; }
 static inline uint32_t atomicExch(uint32_t* p, uint32_t v) { const uint32_t o = *p; *p = v; return o; }
 namespace rome {
 static inline void st_release_sys_u32(uint32_t* p, uint32_t v) { *(volatile uint32_t*)p = v; ++hk::g_progress; }
@@ -258,6 +260,7 @@ static inline void tma_store_commit() {}
 // for wait_all -- written their destination; the emulation does not distinguish the two)
 static inline void tma_store_wait_read() { hk::run_due_copies(true, hk::g_cur); }
 static inline void tma_store_wait_all() { hk::run_due_copies(true, hk::g_cur); }
+static inline void tma_store_wait_pending(int) { hk::run_due_copies(true, hk::g_cur); }
 }  // namespace rome
 namespace hk {
 static void complete_copy(const PendingCopy& c) {

@@ -510,8 +510,9 @@ def test_pipeline_with_asynchronous_copies(hk_so, max_delay):
 
 @pytest.mark.parametrize("grid", [1, 3, 7])
 def test_deferred_tiles_do_not_change_results(hk_so, grid):
-    """A launch that passes the rank barrier (BARRIER_WAIT) visits the tiles of its peer-dependent factor range LAST
-    (TileOrder, csrc/eval_pipeline.cuh): every factor is still evaluated exactly once with the same result -- both
+    """A launch that takes part in the rank barrier visits the tiles of its peer-dependent factor range FIRST and signals
+    as soon as they have landed (TileOrder / early_signal, csrc/eval_pipeline.cuh; no peers here, so only the counting
+    runs): every factor is still evaluated exactly once with the same result, every launch signals exactly once -- both
     pipelines (producer warp: Pose2Pose2 / BearingRange, per-warp rings: Pose3Pose3), ranges at the start, in the middle,
     at the end, covering everything, empty, and a partial last tile"""
     import ctypes as C
@@ -529,6 +530,8 @@ def test_deferred_tiles_do_not_change_results(hk_so, grid):
     c.set_factors_pose3pose3(ip, iq, rng.normal(size=(nF, 6)) * 0.2, T.rand_cov(rng, nF, 6, [0.1] * 3 + [0.01] * 3))
     hk = c._hk
     hk.hk_set_barrier_range.argtypes = [C.c_int, C.c_int]
+    hk.hk_barrier_state.restype = C.POINTER(C.c_uint32)
+    signals_before = hk.hk_barrier_state()[8]
     for fam in (rb.POSE2POSE2, rb.POSE3POSE3):
         fl = rb.SAMPLE | rb.RESIDUAL | rb.STATS
         hk.hk_set_barrier_range(0, 2 ** 31 - 1)
@@ -538,8 +541,10 @@ def test_deferred_tiles_do_not_change_results(hk_so, grid):
             for first, count in ((0, -1), (24, 150)):
                 hk.hk_set_barrier_range(lo, hi)
                 out = c.alloc_host_outputs(fam, fl)
-                c.eval_host(fam, fl | rb.BARRIER_WAIT, seed=3, first=first, count=count, **out)
+                c.eval_host(fam, fl | rb.BARRIER_WAIT | rb.BARRIER_SIGNAL, seed=3, first=first, count=count, **out)
                 a, b = first, nF if count < 0 else first + count
                 assert np.array_equal(out["res"][a:b], ref["res"][a:b]) and np.array_equal(out["stats"][a:b], ref["stats"][a:b]), (fam, lo, hi, first)
                 assert not out["res"][:a].any() and not out["res"][b:].any()
     hk.hk_set_barrier_range(0, 2 ** 31 - 1)
+    st = hk.hk_barrier_state()
+    assert st[8] - signals_before == 2 * 7 * 2 and st[12] == 0 and st[10] == 0   # one signal per launch, counter back at zero, no give-up
