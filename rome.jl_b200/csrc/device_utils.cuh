@@ -74,6 +74,8 @@ __device__ __forceinline__ void tma_store_wait_pending(int n) {
     else asm volatile("cp.async.bulk.wait_group 2;" ::: "memory");
 }
 
+// back-off inside a spin loop on shared / global memory
+__device__ __forceinline__ void spin_pause() { __nanosleep(32); }
 // system-scope release store / acquire load (flags in peer-GPU memory over NVLink)
 __device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");

@@ -175,10 +175,21 @@ struct TileOrder {
             }
         }
     }
+    // visiting order: ONE interior tile, then the peer-dependent tiles, then the other interior tiles (the wait for the
+    // peers' flags, issued by the fetching warp before the first peer-dependent tile, overlaps that first interior tile)
+    __device__ __forceinline__ int lead() const { return (nc > 0 && n > nc) ? 1 : 0; }
+    __device__ __forceinline__ int interior(int m) const { return m < i0 ? m : m + nc; }
     __device__ __forceinline__ int at(int j) const {  // position j of the visiting order -> i
-        if (j < nc) return i0 + j;
-        const int k = j - nc;
-        return k < i0 ? k : k + nc;
+        const int ld = lead();
+        if (j < ld) return interior(0);
+        if (j < ld + nc) return i0 + (j - ld);
+        return interior(j - nc);
+    }
+    // position at which the early signal is prepared: two tiles after the last peer-dependent one (its rows have had
+    // two tile times to land), or the CTA's last position
+    __device__ __forceinline__ int signal_pos() const {
+        const int p = lead() + nc + 1;
+        return p < n ? p : n - 1;
     }
 };
 // owner of the barrier range of a launch, relative to its factor range: tile range [c0, c1] (c1 < c0: none)
@@ -252,19 +263,25 @@ __device__ __forceinline__ void fused_barrier_signal(const EvalParams& P) {
     }
 }
 
-// Early signal (see TileOrder): executed by every consumer warp of a CTA that holds peer-dependent tiles, one or two
-// tiles after the last of them.  `pending` = bulk-store groups the warp has committed since its peer-dependent tiles (0..2):
-// all older groups -- the rows in peer memory -- are waited for, made visible system-wide, and the warp is counted;
-// the last warp of the last such CTA publishes the epoch.  `expected` = arrivals that complete the count.
-__device__ __forceinline__ void early_signal(const EvalParams& P, int lane, int pending, uint32_t expected, int* cta_count,
-                                             int cta_warps) {
-    uint32_t pub = 0;
+// Early signal (see TileOrder), in two halves.
+//  (1) every consumer warp of a CTA that holds peer-dependent tiles, two tiles after the last of them: wait until the
+//      bulk-store groups of those tiles are complete (`pending` = groups committed since: they may still be in flight) and
+//      count the warp in the CTA's shared-memory counter.  Nothing else: the arithmetic warps never pay for a fence.
+//  (2) the warp that has time -- the producer warp, once it has issued the CTA's last tile; in the per-warp pipeline the
+//      warp itself -- makes those rows visible system-wide (fence.sys is cumulative over what it observed through the
+//      counter), counts the CTA in the grid's counter, and the last one publishes the epoch to every peer in parallel.
+__device__ __forceinline__ void early_signal_arrive(int lane, int pending, int* cta_count) {
     if (lane == 0) {
         tma_store_wait_pending(pending);
+        __threadfence_block();
+        atomicAdd(cta_count, 1);
+    }
+}
+__device__ __forceinline__ void early_signal_publish(const EvalParams& P, int lane, uint32_t expected) {
+    uint32_t pub = 0;
+    if (lane == 0) {
         __threadfence_system();
-        bool cta_last = true;
-        if (cta_count) cta_last = atomicAdd(cta_count, 1) == cta_warps - 1;  // CTA-level count first (shared memory)
-        if (cta_last) pub = (atomicAdd(P.bar_state + 12, 1u) == expected - 1) ? 1u : 0u;
+        pub = (atomicAdd(P.bar_state + 12, 1u) == expected - 1) ? 1u : 0u;
     }
     pub = __shfl_sync(0xffffffffu, pub, 0);
     if (pub) {
@@ -395,6 +412,12 @@ __global__ void __launch_bounds__(eval_threads<FT>(), eval_min_ctas<Fam, FT>()) 
             }
             ids_cur = ids_next;
         }
+        if (sig_early && ord.nc > 0) {  // early signal, second half: when all consumer warps have reported their rows landed
+            if (lane == 0)
+                while (*reinterpret_cast<volatile int*>(sig_count) < FT) spin_pause();
+            __syncwarp();
+            early_signal_publish(P, lane, (uint32_t)ord.cut_ctas);
+        }
     } else {
         // ---------------- consumer warps: warp w owns the tile's w-th factor ----------------------------------
         float* out = reinterpret_cast<float*>(stage0 + (size_t)S * L.bytes + (size_t)warp * P.out_warp_bytes);
@@ -403,7 +426,8 @@ __global__ void __launch_bounds__(eval_threads<FT>(), eval_min_ctas<Fam, FT>()) 
         uint32_t phase = 0;
         bool wrote_peer = false;  // did this warp store rows into another GPU's memory?
         int after_cut = 0;        // bulk-store groups committed since the peer-dependent tiles
-        const int sig_pos = sig_early && ord.nc > 0 ? (ord.nc + 1 < ord.n ? ord.nc + 1 : ord.n - 1) : -1;
+        const int sig_pos = sig_early && ord.nc > 0 ? ord.signal_pos() : -1;
+        const int cut_end = ord.lead() + ord.nc;  // first position behind the peer-dependent tiles
         for (int j = 0; j < ord.n; ++j) {
             const int tile = (int)blockIdx.x + ord.at(j) * (int)gridDim.x;
             const int fl = tile * FT + warp;
@@ -446,14 +470,14 @@ __global__ void __launch_bounds__(eval_threads<FT>(), eval_min_ctas<Fam, FT>()) 
                             for (int r = 0; r < P.n_peers; ++r) tma_store_1d(P.peer_fwd[r] + off, V.out_fwd, bytes);
                         }
                         tma_store_commit();
-                        if (j >= ord.nc) ++after_cut;
+                        if (j >= cut_end) ++after_cut;
                     }
                 }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
             if (++s == S) { s = 0; phase ^= 1u; }
-            if (j == sig_pos) early_signal(P, lane, after_cut, (uint32_t)ord.cut_ctas, sig_count, FT);
+            if (j == sig_pos) early_signal_arrive(lane, after_cut, sig_count);
         }
         if (lane == 0) {
             tma_store_wait_all();
@@ -564,7 +588,8 @@ __global__ void __launch_bounds__(FT * 32, Fam::kMinCtas) eval_kernel_w(const __
     uint32_t phase = 0;
     bool wrote_peer = false;
     int after_cut = 0;
-    const int sig_pos = sig_early && ord.nc > 0 ? (ord.nc + 1 < ord.n ? ord.nc + 1 : ord.n - 1) : -1;
+    const int sig_pos = sig_early && ord.nc > 0 ? ord.signal_pos() : -1;
+    const int cut_end = ord.lead() + ord.nc;
     for (int i = 0; i < ord.n; ++i) {
         const int fl = factor_of(i);
         const int f = P.first + fl;
@@ -603,13 +628,16 @@ __global__ void __launch_bounds__(FT * 32, Fam::kMinCtas) eval_kernel_w(const __
                     for (int r = 0; r < P.n_peers; ++r) tma_store_1d(P.peer_fwd[r] + off, V.out_fwd, bytes);
                 }
                 tma_store_commit();
-                if (i >= ord.nc) ++after_cut;
+                if (i >= cut_end) ++after_cut;
             }
         }
         }
         __syncwarp();  // every lane has finished reading stage s
         // early signal: every warp of a CTA with peer-dependent tiles is counted (FT warps per such CTA)
-        if (i == sig_pos) early_signal(P, lane, after_cut, (uint32_t)(ord.cut_ctas * FT), nullptr, 0);
+        if (i == sig_pos) {
+            if (lane == 0) tma_store_wait_pending(after_cut);
+            early_signal_publish(P, lane, (uint32_t)(ord.cut_ctas * FT));
+        }
         sync_before(i + S);
         if (lane == s) issue(i + S, s, ids);
         if (++s == S) { s = 0; phase ^= 1u; }

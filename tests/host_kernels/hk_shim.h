@@ -213,10 +213,12 @@ static long long hk_clock_ticks = 0;
 static inline long long clock64() { return ++hk_clock_ticks; }
 static inline void __threadfence_system() {}
 static inline void __threadfence() {}
+static inline void __threadfence_block() {}
 static inline uint32_t atomicAdd(uint32_t* p, uint32_t v) { const uint32_t o = *p; *p = o + v; return o; }
 static inline int atomicAdd(int* p, int v) { const int o = *p; *p = o + v; return o; }
 static inline uint32_t atomicExch(uint32_t* p, uint32_t v) { const uint32_t o = *p; *p = v; return o; }
 namespace rome {
+static inline void spin_pause() { hk::yield_(); }
 static inline void st_release_sys_u32(uint32_t* p, uint32_t v) { *(volatile uint32_t*)p = v; ++hk::g_progress; }
 static inline uint32_t ld_acquire_sys_u32(const uint32_t* p) { hk::yield_(); return *(volatile const uint32_t*)p; }
 struct HkBar { uint8_t phase, expected; int16_t pending; int32_t tx; };
