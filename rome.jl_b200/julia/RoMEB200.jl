@@ -149,29 +149,132 @@ function eval_host(ctx::Context, family::Cint, nF::Int, N::Int, dm::Int, dr::Int
     return res, prop, stats
 end
 
-# ---- drop-in: batched replacement of `approxConvBelief` for all Pose2Pose2 factors of a graph ----------------
+# ---- drop-in: batched replacement of `approxConvBelief` for the five hot families ------------------------------
 # [IIF-knowledge, unverified here] IIF reaches the factor functor through
 #   approxConvBelief -> evalFactor -> evalPotentialSpecific -> _solveCCWNumeric! (per particle, Optim NelderMead).
-# A maintainer overrides at `approxConvBelief` level for the factor types below: gather every factor of the type,
-# one library call per (type, sweep), then hand the N proposal points per factor back as the convolution result.
-function approxConvBatch(ctx::Context, fg::AbstractDFG, ::Type{Pose2Pose2}; N::Int=getSolverParams(fg).N, seed=UInt64(0))
-    flabels = [l for l in lsf(fg) if getFactorType(fg, l) isa Pose2Pose2]
-    vlabels = ls(fg, Pose2) |> sortDFG
-    vidx = Dict(l => Int32(i - 1) for (i, l) in enumerate(vlabels))
-    ip = Int32[vidx[getVariableOrder(fg, l)[1]] for l in flabels]
-    iq = Int32[vidx[getVariableOrder(fg, l)[2]] for l in flabels]
-    set_particles!(ctx, POSE2, coordinates(fg, vlabels, Pose2, N))
-    set_factors!(ctx, Pose2Pose2, ip, iq, [getFactorType(fg, l).Z for l in flabels])
-    res, prop, stats = eval_host(ctx, POSE2POSE2, length(flabels), N, 3, 3, 3, 16; seed=seed)
-    # proposals are offsets from the target variable's anchor == its first particle's coordinates
+# The replacement works one level up: ONE library call per (factor type, sweep) evaluates getSample + the closed-form
+# root for every factor of the type x every particle; the N proposal points of a factor are what approxConvBelief returns.
+#
+# `DeviceGraph` keeps the context, the variable numbering and the factor tables ACROSS calls: tables are uploaded when the
+# graph is mirrored (or a factor is added), particles only when they changed on the host (`upload_particles!`).
+
+const FAMILY_OF = Dict{DataType,Cint}(Pose2Pose2 => POSE2POSE2, PriorPose2 => PRIORPOSE2,
+                                      Pose2Point2BearingRange => BEARINGRANGE, Pose3Pose3 => POSE3POSE3,
+                                      PriorPose3 => PRIORPOSE3)
+# family -> (first variable type, last variable type or nothing, dm, dr, d of the forward proposal, nstats)
+const FAMILY_DIMS = Dict{Cint,Tuple}(POSE2POSE2 => (Pose2, Pose2, 3, 3, 3, 16), PRIORPOSE2 => (Pose2, nothing, 3, 3, 3, 16),
+                                     BEARINGRANGE => (Pose2, Point2, 2, 2, 2, 16), POSE3POSE3 => (Pose3, Pose3, 6, 6, 6, 32),
+                                     PRIORPOSE3 => (Pose3, nothing, 6, 6, 6, 32))
+const VARTYPE_OF = Dict{DataType,Cint}(Pose2 => POSE2, Point2 => POINT2, Pose3 => POSE3)
+
+mutable struct DeviceGraph
+    ctx::Context
+    fg::AbstractDFG
+    N::Int
+    vlabels::Dict{DataType,Vector{Symbol}}          # variable type -> labels in device order
+    vindex::Dict{Symbol,Int32}                      # label -> index inside its type's particle store
+    flabels::Dict{Cint,Vector{Symbol}}              # family -> factor labels in table order
+    sweep::UInt32
+end
+
+function DeviceGraph(fg::AbstractDFG; device::Integer=0, N::Int=getSolverParams(fg).N)
+    ctx = Context(device)
+    vlabels = Dict{DataType,Vector{Symbol}}(T => sortDFG(ls(fg, T)) for T in (Pose2, Point2, Pose3))
+    vindex = Dict{Symbol,Int32}()
+    for (T, ls_) in vlabels, (i, l) in enumerate(ls_)
+        vindex[l] = Int32(i - 1)
+    end
+    dg = DeviceGraph(ctx, fg, N, vlabels, vindex, Dict{Cint,Vector{Symbol}}(), UInt32(0))
+    upload_factors!(dg)
+    upload_particles!(dg)
+    return dg
+end
+
+"upload the particles of every variable type (call after the host changed them)"
+function upload_particles!(dg::DeviceGraph)
+    for (T, labels) in dg.vlabels
+        isempty(labels) && continue
+        set_particles!(dg.ctx, VARTYPE_OF[T], coordinates(dg.fg, labels, T, dg.N))
+    end
+end
+
+"(re)build the factor tables of the five hot families from the graph"
+function upload_factors!(dg::DeviceGraph)
+    fg = dg.fg
+    for (FT, fam) in FAMILY_OF
+        labels = Symbol[l for l in lsf(fg) if getFactorType(fg, l) isa FT]
+        dg.flabels[fam] = labels
+        isempty(labels) && continue
+        i0 = Int32[dg.vindex[getVariableOrder(fg, l)[1]] for l in labels]
+        fcts = [getFactorType(fg, l) for l in labels]
+        if FT === Pose2Pose2 || FT === Pose3Pose3
+            i1 = Int32[dg.vindex[getVariableOrder(fg, l)[2]] for l in labels]
+            set_factors!(dg.ctx, FT, i0, i1, [f.Z for f in fcts])
+        elseif FT === Pose2Point2BearingRange
+            i1 = Int32[dg.vindex[getVariableOrder(fg, l)[2]] for l in labels]
+            set_factors!(dg.ctx, FT, i0, i1, fcts)
+        elseif FT === PriorPose2
+            set_factors!(dg.ctx, FT, i0, [f.Z for f in fcts])
+        else  # PriorPose3
+            set_factors!(dg.ctx, PRIORPOSE3, i0, nothing, [f.Z for f in fcts])
+        end
+    end
+end
+
+"""
+    approxConvBatch(dg, F) -> (proposals::Dict{Symbol,Vector}, res, stats)
+
+Convolve EVERY factor of type `F` (Pose2Pose2, PriorPose2, Pose2Point2BearingRange, Pose3Pose3, PriorPose3) toward its
+last variable (the prior's variable): fused getSample + closed-form root on the device, N proposal points per factor.
+`proposals[factor label]` is what `approxConvBelief(fg, factor, target)` returns for that factor.
+"""
+function approxConvBatch(dg::DeviceGraph, ::Type{F}; seed::UInt64=UInt64(0)) where {F}
+    fam = FAMILY_OF[F]
+    T0, T1, dm, dr, dfwd, nstats = FAMILY_DIMS[fam]
+    labels = dg.flabels[fam]
     out = Dict{Symbol,Vector}()
-    M = getManifold(Pose2)
-    for (k, l) in enumerate(flabels)
-        tgt = getVariableOrder(fg, l)[2]
-        a = vee(M, getPointIdentity(M), log(M, getPointIdentity(M), getVal(fg, tgt)[1]))
-        out[l] = [getPoint(Pose2, a .+ Float64.(prop[:, n, k])) for n in 1:N]
+    isempty(labels) && return out, zeros(Float32, dr, npad(dg.N), 0), zeros(Float32, nstats, 0)
+    res, prop, stats = eval_host(dg.ctx, fam, length(labels), dg.N, dm, dr, dfwd, nstats; seed=seed, stream_id=dg.sweep)
+    dg.sweep += UInt32(1)
+    TT = T1 === nothing ? T0 : T1                      # type of the target variable
+    M = getManifold(TT)
+    e = getPointIdentity(M)
+    for (k, l) in enumerate(labels)
+        tgt = getVariableOrder(dg.fg, l)[end]
+        # proposals are offsets from the target variable's anchor == the coordinates of its first particle
+        a = vee(M, e, log(M, e, getVal(dg.fg, tgt)[1]))
+        out[l] = [getPoint(TT, a .+ Float64.(prop[:, n, k])) for n in 1:dg.N]
     end
     return out, res, stats
 end
+
+# one-shot convenience (mirrors the graph, convolves, drops the mirror) -- the cached form above is the one a solver uses
+approxConvBatch(fg::AbstractDFG, ::Type{F}; device::Integer=0, N::Int=getSolverParams(fg).N, seed::UInt64=UInt64(0)) where {F} =
+    approxConvBatch(DeviceGraph(fg; device=device, N=N), F; seed=seed)
+
+# ---- the method a maintainer adds to IIF / RoME so that canonical graphs drop in unchanged ---------------------------
+# [IIF-knowledge, unverified here: IncrementalInference 0.35 is not vendored]  `approxConvBelief(dfg, fc, target, ...)`
+# is IIF's per-factor convolution; specialising it on the factor TYPE keeps `generateGraph_Hexagonal`, the g2o loader,
+# `solveTree!` etc. untouched while every convolution of a hot family is served from a per-graph cache that is refreshed
+# once per (family, sweep):
+#
+#   const _MIRROR = IdDict{AbstractDFG,DeviceGraph}()                       # one device mirror per graph
+#   const _CACHE  = Dict{Tuple{UInt,Cint,UInt32},Dict{Symbol,Vector}}()     # (graph id, family, sweep) -> proposals
+#
+#   function IncrementalInference.approxConvBelief(dfg::AbstractDFG, fc::DFGFactor{<:CommonConvWrapper{<:F}},
+#                                                  target::Symbol, args...; kw...) where
+#            {F<:Union{Pose2Pose2,PriorPose2,Pose2Point2BearingRange,Pose3Pose3,PriorPose3}}
+#       getVariableOrder(fc)[end] == target || return invoke(approxConvBelief, Tuple{AbstractDFG,DFGFactor,Symbol}, dfg, fc, target, args...; kw...)
+#       dg = get!(() -> RoMEB200.DeviceGraph(dfg), _MIRROR, dfg)
+#       key = (objectid(dfg), RoMEB200.FAMILY_OF[F], dg.sweep)
+#       props = get!(_CACHE, key) do
+#           RoMEB200.upload_particles!(dg)                                   # particles changed since the last sweep
+#           first(RoMEB200.approxConvBatch(dg, F))
+#       end
+#       return manikde!(getManifold(getVariable(dfg, target)), props[getLabel(fc)])
+#   end
+#
+# Backward convolutions (toward the first variable) take the same route with ROME_B200_PROPOSAL_BWD; the numeric
+# (Nelder-Mead) path remains for every other factor type and for multihypo / nullhypo factors.
 
 end # module

@@ -138,6 +138,7 @@ def test_parametric_solves(emulated_api):
     T.test_information_weighting(emulated_api)
     T.test_bearing_range_triangulation(emulated_api)
     T.test_pose3_loop(emulated_api)
+    T.test_analytic_and_finite_difference_jacobians_give_the_same_solution(emulated_api)
 
 
 def test_accumulated_factor_means(emulated_api):
@@ -548,3 +549,10 @@ def test_deferred_tiles_do_not_change_results(hk_so, grid):
     hk.hk_set_barrier_range(0, 2 ** 31 - 1)
     st = hk.hk_barrier_state()
     assert st[8] - signals_before == 2 * 7 * 2 and st[12] == 0 and st[10] == 0   # one signal per launch, counter back at zero, no give-up
+
+
+def test_fullsize_gpu_tests_logic_on_the_emulated_device(ectx):
+    """tests/test_gpu_fullsize.py's heading-across-the-cut case and its checker, run against the emulated device (the
+    10 000-pose cases themselves are covered by test_full_size_baseline_workloads above)"""
+    import test_gpu_fullsize as T
+    T.test_heading_spread_across_the_branch_cut(ectx)

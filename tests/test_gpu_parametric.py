@@ -88,3 +88,27 @@ def test_pose3_loop(ctx):
     # every odometry residual vanishes at the solution (float64 oracle on the solved coordinates)
     for i in range(1, 5):
         assert np.abs(O.pose3pose3(odo.mu, x[f"x{i - 1}"], x[f"x{i}"])).max() < 1e-4
+
+
+def test_analytic_and_finite_difference_jacobians_give_the_same_solution(ctx):
+    """the kernels' analytic Jacobian blocks (default for the hot families) against the finite-difference path on a graph
+    with all five hot families' 2-D members and on the Pose3 loop"""
+    fg = rb.generateGraph_Hexagonal()
+    rb.initAll(fg, seed=1, ctx=ctx)
+    start = {l: (v.val.mean(0) if v.val is not None else np.zeros(v.variableType.dim)) for l, v in fg.variables.items()}
+
+    def solve(analytic):
+        for l, v in fg.variables.items():
+            v.parametric = start[l].copy()
+        return rb.solveGraphParametric(fg, ctx=ctx, analytic=analytic)
+    _, xa, ca, Sa = solve(True)
+    _, xf, cf, Sf = solve(False)
+    for l in xa:
+        d = xa[l] - xf[l]
+        if fg[l].variableType is rb.Pose2:
+            d[2] = O.np_wrap(d[2])
+        assert np.abs(d).max() < 2e-4, (l, d)
+    assert abs(ca - cf) < 1e-6 * max(1.0, cf)
+    assert np.allclose(Sa, Sf, rtol=2e-2, atol=1e-6)
+    # known answer of the Hexagonal graph (test/testHexagonal2D_CliqByCliq.jl:37-79 ground truth)
+    assert np.allclose(xa["x1"][:2], [10, 0], atol=0.5) and np.allclose(xa["l1"], [20, 0], atol=1.0)

@@ -115,3 +115,27 @@ def test_buffers_struct_and_constants_mirror_the_header():
     assert {"POSE2", "POSE3POSE3", "POSE3POSE3UNITTRANS", "RESIDUAL", "SAMPLE", "DECONV", "PRODUCT_REANCHOR"} <= checked
     # the flag word quoted in INTEGRATION.md
     assert "0x1b #=RESIDUAL|PROPOSAL_FWD|STATS|SAMPLE=#" in MD and (flags["RESIDUAL"] | flags["PROPOSAL_FWD"] | flags["STATS"] | flags["SAMPLE"]) == 0x1b
+
+
+def test_julia_shim_covers_the_five_hot_families():
+    """the batched drop-in (`DeviceGraph` + `approxConvBatch`) exists for all five hot families, and the per-family
+    dimensions it hands to the library are the library's own (rome_b200_family_dims / engine.FAMILY)"""
+    import rome_b200 as rb
+    fam_of = re.search(r"const FAMILY_OF = Dict\{DataType,Cint\}\((.*?)\)\n", JL, re.S).group(1)
+    pairs = dict(re.findall(r"(\w+) => (\w+)", fam_of))
+    assert pairs == {"Pose2Pose2": "POSE2POSE2", "PriorPose2": "PRIORPOSE2", "Pose2Point2BearingRange": "BEARINGRANGE",
+                     "Pose3Pose3": "POSE3POSE3", "PriorPose3": "PRIORPOSE3"}
+    dims = re.search(r"const FAMILY_DIMS = Dict\{Cint,Tuple\}\((.*?)\)\nconst", JL, re.S).group(1)
+    got = {m[0]: (m[1], m[2], int(m[3]), int(m[4]), int(m[5]), int(m[6]))
+           for m in re.findall(r"(\w+) => \((\w+), (\w+), (\d+), (\d+), (\d+), (\d+)\)", dims)}
+    vt = {rb.POSE2: "Pose2", rb.POINT2: "Point2", rb.POSE3: "Pose3", None: "nothing"}
+    for name, fam in (("POSE2POSE2", rb.POSE2POSE2), ("PRIORPOSE2", rb.PRIORPOSE2), ("BEARINGRANGE", rb.BEARINGRANGE),
+                      ("POSE3POSE3", rb.POSE3POSE3), ("PRIORPOSE3", rb.PRIORPOSE3)):
+        v0, v1, dm, dr, ns, _, dfwd, _ = rb.FAMILY[fam]
+        assert got[name] == (vt[v0], vt[v1], dm, dr, dfwd, ns), name
+    assert "function approxConvBatch(dg::DeviceGraph, ::Type{F}; seed::UInt64=UInt64(0)) where {F}" in JL
+    assert "function upload_factors!(dg::DeviceGraph)" in JL and "function upload_particles!(dg::DeviceGraph)" in JL
+    assert "IncrementalInference.approxConvBelief(dfg::AbstractDFG, fc::DFGFactor{<:CommonConvWrapper{<:F}}" in JL
+    # every flag constant of the header is mirrored (the regex of the test above walks them; the newest ones by name)
+    for name in ("PRECISE", "ROUTED_ONLY", "BARRIER_WAIT", "BARRIER_SIGNAL"):
+        assert re.search(rf"\b{name}\b", JL), name
