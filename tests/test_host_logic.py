@@ -35,9 +35,10 @@ def test_library_is_sm100a_only_and_uses_tma():
     assert "SHFL" in body    # warp-shuffle statistics
     assert "DFMA" in body    # Float64 arithmetic
     # consumers never load particle/measurement data from global memory: the only LDGs are the producer's
-    # variable-id reads (LDG.E.64.CONSTANT) and the 2/pi table of sincos' huge-argument slow path
+    # variable-id reads (LDG.E.64.CONSTANT), the 2/pi table of sincos' huge-argument slow path, and the fused rank
+    # barrier's state words (the flag polls are system-scope strong loads, LD/LDG.E.STRONG.SYS)
     import re
-    assert set(re.findall(r"LDG[.\w]*", body)) <= {"LDG.E.64.CONSTANT", "LDG.E.CONSTANT"}
+    assert set(re.findall(r"LDG[.\w]*", body)) <= {"LDG.E.64.CONSTANT", "LDG.E.CONSTANT", "LDG.E.STRONG.SYS", "LDG.E.STRONG.GPU"}
 
 
 def test_no_cpu_fallback_without_gpu():
@@ -268,15 +269,23 @@ def test_product_plan_from_graph():
     assert fams == [rb.POSE2POSE2, rb.PRIORPOSE2, rb.BEARINGRANGE]
     off, sb, sr = plans[rb.POSE2]
     assert len(off) == 8 and off[-1] == len(sb) == len(sr)
-    k = {f: i for i, f in enumerate(fams)}
+    # dense numbering: one buffer per (family, direction) that HAS a closed-form proposal -- the prior has no backward one
+    assert buffers == [(rb.POSE2POSE2, "fwd"), (rb.POSE2POSE2, "bwd"), (rb.PRIORPOSE2, "fwd"), (rb.BEARINGRANGE, "fwd"),
+                       (rb.BEARINGRANGE, "bwd")]
+    k = {b: i for i, b in enumerate(buffers)}
     # :x0 = prior (fwd) + bwd of x0x1f1 + bwd of the bearing-range sighting from x0
     src0 = sorted(zip(sb[off[0]:off[1]], sr[off[0]:off[1]]))
-    assert src0 == sorted([(2 * k[rb.PRIORPOSE2], 0), (2 * k[rb.POSE2POSE2] + 1, 0), (2 * k[rb.BEARINGRANGE] + 1, 0)])
+    assert src0 == sorted([(k[(rb.PRIORPOSE2, "fwd")], 0), (k[(rb.POSE2POSE2, "bwd")], 0), (k[(rb.BEARINGRANGE, "bwd")], 0)])
     # :x3 = fwd of x2x3f1 + bwd of x3x4f1
     src3 = sorted(zip(sb[off[3]:off[4]], sr[off[3]:off[4]]))
-    assert src3 == sorted([(2 * k[rb.POSE2POSE2], 2), (2 * k[rb.POSE2POSE2] + 1, 3)])
+    assert src3 == sorted([(k[(rb.POSE2POSE2, "fwd")], 2), (k[(rb.POSE2POSE2, "bwd")], 3)])
     offl, sbl, srl = plans[rb.POINT2]  # :l1 = fwd of both sightings
-    assert list(offl) == [0, 2] and sorted(srl) == [0, 1] and set(sbl) == {2 * k[rb.BEARINGRANGE]}
+    assert list(offl) == [0, 2] and sorted(srl) == [0, 1] and set(sbl) == {k[(rb.BEARINGRANGE, "fwd")]}
+    # a 2-D graph with every family present stays below the library's limit of 16 proposal buffers (advisor finding r1)
+    import rome_b200.solver as S
+    fams_2d = [f for f, v in rb.FAMILY.items() if v[0] in (rb.POSE2, rb.POINT2)]
+    nbuf = sum(bool(rb.FAMILY[f][6]) + bool(rb.FAMILY[f][7] and rb.FAMILY[f][1] is not None) for f in fams_2d)
+    assert nbuf <= 16 and S.L.MAX_PRODUCT_BUFFERS == 16
 
 
 def test_parametric_colouring_is_proper():
@@ -339,20 +348,37 @@ def test_g2o_import_export_text(golden_dir, tmp_path):
 
 
 def test_bench_cpu_legs():
-    """the CPU legs of bench.py (cpu_baseline sweep, reference-shaped convolution, CPU product) run on the bench workload
-    and return sane rates -- they are what `--impl reference` and `cpu_baseline` report"""
+    """the CPU legs of bench.py run on the bench workloads and return sane rates -- they are what `--impl reference` and
+    `cpu_baseline` report: the float64 port of the SAME step as the GPU arm (getSample + residual + statistics)"""
     import bench
     w = bench.build_workload(1)
     assert w["poses"].shape == (bench.NPOSES, bench.NPART, 3) and len(w["ip"]) == len(w["iq"]) == len(w["mu"])
     assert len(w["ip"]) > bench.NPOSES and len(w["pr_ip"]) == 1
-    v, nt, reps, dt = bench.cpu_sweep_rate(w, 0.3)
-    assert v > 1e6 and nt >= 1 and reps >= 1
-    r = bench.cpu_reference_shaped(w, nfac=4)
-    assert r["residual_calls_per_particle"] > 50 and r["convolved_particles_per_s"] > 0
-    p = bench.cpu_product_shaped(w, nvars=40)
-    assert p["variables_per_s"] > 0 and p["s_per_sweep_extrapolated"] > 0
-    w2 = bench.build_workload(2)  # weak scaling: two graph copies with globally numbered variables
+    wl, scaling = bench.make_workload(bench.WORKLOAD, 1)
+    assert scaling == "weak"
+    step, evals, sample = bench.cpu_step_prepare(wl, nthreads=2)
+    assert evals == (len(w["ip"]) + 1) * bench.NPART and "11999 of 11999" in sample
+    v, nt, reps, dt = bench.cpu_rate(step, evals, 0.3)
+    assert v > 1e6 and nt == 2 and reps >= 1
+    step2, evals2, sample2 = bench.cpu_step_prepare(wl, max_factors=1200, nthreads=1)   # bounded sample
+    assert evals2 < evals / 5 and step2(3) == 1
+    bare = bench.cpu_bare_sweep_rate(wl, seconds=0.2)
+    assert bare["value"] > 1e6
+    w2 = bench.build_workload(2)  # weak scaling: one graph of 2 x 10 000 poses
     assert w2["poses"].shape[0] == 2 * bench.NPOSES and w2["ip"].max() >= bench.NPOSES
+    # the statistics the CPU step accumulates are the sums of its residual rows
+    from oracle import oracle as O
+    import rome_b200 as rb
+    f = wl["families"][rb.POSE2POSE2]
+    mu, Lc = bench.cholesky_of(rb.POSE2POSE2, f)
+    call, res, st = O.step_prepare(0, f["i0"][:50], f["i1"][:50], wl["particles"][rb.POSE2], None, mu[:50], Lc[:50], 1)
+    call(5)
+    assert np.allclose(st[:, :3], res.sum(1)) and np.allclose(st[:, 3], (res[..., 0] ** 2).sum(1))
+    first = res.copy()
+    call(5)
+    assert np.array_equal(res, first)   # seeded per factor: independent of threads and repetitions
+    call(6)
+    assert not np.array_equal(res, first)
 
 
 def test_launch_plans_fit_the_sm():
