@@ -332,15 +332,20 @@ __global__ void __launch_bounds__(eval_threads<FT>(), eval_min_ctas<Fam, FT>()) 
     constexpr int TPC = 32 / FT;  // tiles per chunk
     const int jl = lane / FT, fl_in_tile = lane % FT;
     int2 ids_cur = make_int2(0, 0);
+    // Multi-GPU features (per-factor row destinations, peer replication, the fused rank barrier with its tile order) are
+    // compiled into the run-time-flag variant, the forward-proposal variant and the routed variant only: the plain
+    // RESIDUAL|STATS variant -- the single-GPU hot path -- carries none of their state through its loop (launches that
+    // need them are planned onto the routed variant, plan_launch).
+    constexpr bool kMulti = kRouted || kStatic == 0u || (kStatic & ROME_B200_PROPOSAL_FWD) != 0u;
     TileOrder ord;  // visiting order of this CTA's tiles (peer-dependent tiles first when the launch takes part in the barrier)
     {
-        int c0, c1;
-        barrier_tiles(P, FT, c0, c1);
-        ord.init(nTiles, (int)gridDim.x, (int)blockIdx.x, c1 >= c0, c0, c1);
+        int c0 = 0, c1 = -1;
+        if (kMulti) barrier_tiles(P, FT, c0, c1);
+        ord.init(nTiles, (int)gridDim.x, (int)blockIdx.x, kMulti && c1 >= c0, c0, c1);
     }
     // the signal goes out as soon as the peer-dependent tiles have landed (early), or -- a launch without such tiles, or
     // one that replicates its rows to every peer -- when the whole grid has finished
-    const bool sig_early = (P.flags & ROME_B200_BARRIER_SIGNAL) && ord.cut_ctas > 0 && P.n_peers == 0;
+    const bool sig_early = kMulti && (P.flags & ROME_B200_BARRIER_SIGNAL) && ord.cut_ctas > 0 && P.n_peers == 0;
     int* sig_count = reinterpret_cast<int*>(smem + 2 * kMaxStages * 8);
     auto fetch_chunk = [&](int base_j) {  // ids of visiting positions base_j .. base_j + TPC - 1
         const int j = base_j + jl;
@@ -378,7 +383,7 @@ __global__ void __launch_bounds__(eval_threads<FT>(), eval_min_ctas<Fam, FT>()) 
         int s = 0;
         uint32_t phase = 1;  // parity of the previous round; the first pass over the ring does not wait
         bool first_round = true;
-        bool synced = !(P.flags & ROME_B200_BARRIER_WAIT);  // rank barrier still to be passed?
+        bool synced = !kMulti || !(P.flags & ROME_B200_BARRIER_WAIT);  // rank barrier still to be passed?
         for (int base = 0; base < ord.n; base += TPC) {
             const int2 ids_next = fetch_chunk(base + TPC);  // in flight while this chunk is issued
 #pragma unroll 1
@@ -412,7 +417,7 @@ __global__ void __launch_bounds__(eval_threads<FT>(), eval_min_ctas<Fam, FT>()) 
             }
             ids_cur = ids_next;
         }
-        if (sig_early && ord.nc > 0) {  // early signal, second half: when all consumer warps have reported their rows landed
+        if (kMulti && sig_early && ord.nc > 0) {  // early signal, second half: when all consumer warps have reported their rows landed
             if (lane == 0)
                 while (*reinterpret_cast<volatile int*>(sig_count) < FT) spin_pause();
             __syncwarp();
@@ -436,7 +441,7 @@ __global__ void __launch_bounds__(eval_threads<FT>(), eval_min_ctas<Fam, FT>()) 
             // owner-sharded exchange: this factor's forward row may have its own destination (a peer GPU); requested
             // before the wait for the stage so that the load's latency hides behind it (warp-uniform address)
             unsigned long long fdst = 0;
-            if (mine && ((flags & ROME_B200_PROPOSAL_FWD) || kRouted) && P.fwd_dst) fdst = __ldg(P.fwd_dst + f);
+            if (kMulti && mine && ((flags & ROME_B200_PROPOSAL_FWD) || kRouted) && P.fwd_dst) fdst = __ldg(P.fwd_dst + f);
             mbar_wait(&full[s], phase);
             const unsigned char* st = stage0 + (size_t)s * L.bytes;
             if (mine) {
@@ -447,8 +452,8 @@ __global__ void __launch_bounds__(eval_threads<FT>(), eval_min_ctas<Fam, FT>()) 
                 V.meas = kSample ? nullptr : reinterpret_cast<const float*>(st + L.meas_off + (size_t)warp * L.mb);
                 V.out_res = out;
                 V.out_fwd = out + res_floats;
-                V.fwd_on = !(P.flags & ROME_B200_ROUTED_ONLY) || fdst != 0;
-                wrote_peer = wrote_peer || fdst != 0 || P.n_peers > 0;
+                V.fwd_on = !kMulti || !(P.flags & ROME_B200_ROUTED_ONLY) || fdst != 0;
+                if (kMulti) wrote_peer = wrote_peer || fdst != 0 || P.n_peers > 0;
                 if (flags & (ROME_B200_RESIDUAL | ROME_B200_PROPOSAL_FWD)) {
                     if (lane == 0) tma_store_wait_read();  // the previous tile's rows have left the slice
                     __syncwarp();
@@ -465,30 +470,31 @@ __global__ void __launch_bounds__(eval_threads<FT>(), eval_min_ctas<Fam, FT>()) 
                         if (((flags & ROME_B200_PROPOSAL_FWD) && V.fwd_on) || routed) {
                             const size_t off = (size_t)f * Fam::DFWD * P.Npad;
                             const uint32_t bytes = (uint32_t)(Fam::DFWD * P.Npad * 4);
-                            tma_store_1d(fdst ? reinterpret_cast<float*>(fdst) : P.prop_fwd + off, V.out_fwd, bytes);
+                            tma_store_1d((kMulti && fdst) ? reinterpret_cast<float*>(fdst) : P.prop_fwd + off, V.out_fwd, bytes);
                             // fused all-gather: the same slice goes to every peer GPU over NVLink
-                            for (int r = 0; r < P.n_peers; ++r) tma_store_1d(P.peer_fwd[r] + off, V.out_fwd, bytes);
+                            if (kMulti)
+                                for (int r = 0; r < P.n_peers; ++r) tma_store_1d(P.peer_fwd[r] + off, V.out_fwd, bytes);
                         }
                         tma_store_commit();
-                        if (j >= cut_end) ++after_cut;
+                        if (kMulti && j >= cut_end) ++after_cut;
                     }
                 }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
             if (++s == S) { s = 0; phase ^= 1u; }
-            if (j == sig_pos) early_signal_arrive(lane, after_cut, sig_count);
+            if (kMulti && j == sig_pos) early_signal_arrive(lane, after_cut, sig_count);
         }
         if (lane == 0) {
             tma_store_wait_all();
             // end-of-grid signal: rows stored into peer memory are performed system-wide before this CTA reports
             // completion (only the warps that have such rows pay for the system-scope fence)
-            if ((P.flags & ROME_B200_BARRIER_SIGNAL) && !sig_early && wrote_peer) __threadfence_system();
+            if (kMulti && (P.flags & ROME_B200_BARRIER_SIGNAL) && !sig_early && wrote_peer) __threadfence_system();
         }
     }
     // a launch that overlapped its predecessor must not be seen as complete before the predecessor is
     if (P.flags & ROME_B200_INDEPENDENT) asm volatile("griddepcontrol.wait;" ::: "memory");
-    if ((P.flags & ROME_B200_BARRIER_SIGNAL) && !sig_early) fused_barrier_signal(P);
+    if (kMulti && (P.flags & ROME_B200_BARRIER_SIGNAL) && !sig_early) fused_barrier_signal(P);
 }
 // =============================================================================================
 // per-warp pipeline ("warp pipeline"): no producer warp and no CTA-wide barrier.  Warp w of a CTA owns slot w of

@@ -85,7 +85,10 @@ int plan_launch(int family, uint32_t flags, int Npad, int smem_per_sm, int smem_
     if (fd.dfwd == 0) flags &= ~ROME_B200_PROPOSAL_FWD;
     const uint32_t out_flags = flags & ~kSchedFlags;
     // 3: RESIDUAL|STATS compiled in, forward rows only for the factors that have a destination (ROUTED_ONLY)
-    const int hot = out_flags == kHot1 ? 1 : out_flags == kHot2 ? ((flags & ROME_B200_ROUTED_ONLY) ? 3 : 2) : 0;
+    // (the plain RESIDUAL|STATS variant carries no multi-GPU code: with barrier flags it runs as the routed variant too)
+    const uint32_t multi = flags & (ROME_B200_ROUTED_ONLY | ROME_B200_BARRIER_WAIT | ROME_B200_BARRIER_SIGNAL);
+    const int hot = out_flags == kHot1 ? ((multi && fd.dfwd) ? 3 : 1)
+                                       : out_flags == kHot2 ? ((flags & ROME_B200_ROUTED_ONLY) ? 3 : 2) : 0;
     plan->pipeline = 0;
     if (se3 && pipeline_choice() == 1) {
         // per-warp pipelines: W warps per CTA, each with its own ring of `stages` slots + output slice
