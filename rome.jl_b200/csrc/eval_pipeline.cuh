@@ -537,13 +537,14 @@ __global__ void __launch_bounds__(FT * 32, Fam::kMinCtas) eval_kernel_w(const __
     const uint32_t flags = kStatic ? kStatic : P.flags;
     const int res_floats = Fam::DR * P.Npad;
     // the i-th factor of this warp: tile blockIdx.x + i * gridDim.x, slot `warp` (-1: none)
+    constexpr bool kMulti = kRouted || kStatic == 0u || (kStatic & ROME_B200_PROPOSAL_FWD) != 0u;  // see eval_kernel
     TileOrder ord;
     {
-        int c0, c1;
-        barrier_tiles(P, FT, c0, c1);
-        ord.init((P.count + FT - 1) / FT, (int)gridDim.x, (int)blockIdx.x, c1 >= c0, c0, c1);
+        int c0 = 0, c1 = -1;
+        if (kMulti) barrier_tiles(P, FT, c0, c1);
+        ord.init((P.count + FT - 1) / FT, (int)gridDim.x, (int)blockIdx.x, kMulti && c1 >= c0, c0, c1);
     }
-    const bool sig_early = (P.flags & ROME_B200_BARRIER_SIGNAL) && ord.cut_ctas > 0 && P.n_peers == 0;
+    const bool sig_early = kMulti && (P.flags & ROME_B200_BARRIER_SIGNAL) && ord.cut_ctas > 0 && P.n_peers == 0;
     auto factor_of = [&](int j) {  // the factor this warp evaluates at visiting position j
         if (j >= ord.n) return -1;
         const int fl = ((int)blockIdx.x + ord.at(j) * (int)gridDim.x) * FT + warp;
@@ -579,7 +580,7 @@ __global__ void __launch_bounds__(FT * 32, Fam::kMinCtas) eval_kernel_w(const __
     __syncwarp();
     if (!(P.flags & ROME_B200_INDEPENDENT)) asm volatile("griddepcontrol.wait;" ::: "memory");  // see eval_kernel
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    bool synced = !(P.flags & ROME_B200_BARRIER_WAIT);  // rank barrier still to be passed (every warp fetches for itself)
+    bool synced = !kMulti || !(P.flags & ROME_B200_BARRIER_WAIT);  // rank barrier still to be passed (every warp fetches for itself)
     auto sync_before = [&](int i) {
         const int fl = factor_of(i);
         if (!synced && fl >= 0 && P.first + fl >= P.bar_lo && P.first + fl < P.bar_hi) {
@@ -587,7 +588,8 @@ __global__ void __launch_bounds__(FT * 32, Fam::kMinCtas) eval_kernel_w(const __
             synced = true;
         }
     };
-    for (int i = 0; i < S; ++i) sync_before(i);
+    if (kMulti)
+        for (int i = 0; i < S; ++i) sync_before(i);
     if (lane < S) issue(lane, lane, ids);
 
     int s = 0;
@@ -600,7 +602,7 @@ __global__ void __launch_bounds__(FT * 32, Fam::kMinCtas) eval_kernel_w(const __
         const int fl = factor_of(i);
         const int f = P.first + fl;
         unsigned long long fdst = 0;  // owner-sharded exchange: per-factor destination of the forward row
-        if (fl >= 0 && ((flags & ROME_B200_PROPOSAL_FWD) || kRouted) && P.fwd_dst) fdst = __ldg(P.fwd_dst + f);
+        if (kMulti && fl >= 0 && ((flags & ROME_B200_PROPOSAL_FWD) || kRouted) && P.fwd_dst) fdst = __ldg(P.fwd_dst + f);
         if (lane == s) ids = fetch_ids(i + S);  // consumed when this factor is done: hidden behind its arithmetic
         mbar_wait(&bar[s], phase);
         if (fl >= 0) {
@@ -612,8 +614,8 @@ __global__ void __launch_bounds__(FT * 32, Fam::kMinCtas) eval_kernel_w(const __
         V.meas = kSample ? nullptr : reinterpret_cast<const float*>(st + L.meas_off);
         V.out_res = out;
         V.out_fwd = out + res_floats;
-        V.fwd_on = !(P.flags & ROME_B200_ROUTED_ONLY) || fdst != 0;
-        wrote_peer = wrote_peer || fdst != 0 || P.n_peers > 0;
+        V.fwd_on = !kMulti || !(P.flags & ROME_B200_ROUTED_ONLY) || fdst != 0;
+        if (kMulti) wrote_peer = wrote_peer || fdst != 0 || P.n_peers > 0;
         if (flags & (ROME_B200_RESIDUAL | ROME_B200_PROPOSAL_FWD)) {
             if (lane == 0) tma_store_wait_read();  // the previous factor's rows have left the slice
             __syncwarp();
@@ -630,30 +632,31 @@ __global__ void __launch_bounds__(FT * 32, Fam::kMinCtas) eval_kernel_w(const __
                 if (((flags & ROME_B200_PROPOSAL_FWD) && V.fwd_on) || routed) {
                     const size_t off = (size_t)f * Fam::DFWD * P.Npad;
                     const uint32_t bytes = (uint32_t)(Fam::DFWD * P.Npad * 4);
-                    tma_store_1d(fdst ? reinterpret_cast<float*>(fdst) : P.prop_fwd + off, V.out_fwd, bytes);
-                    for (int r = 0; r < P.n_peers; ++r) tma_store_1d(P.peer_fwd[r] + off, V.out_fwd, bytes);
+                    tma_store_1d((kMulti && fdst) ? reinterpret_cast<float*>(fdst) : P.prop_fwd + off, V.out_fwd, bytes);
+                    if (kMulti)
+                        for (int r = 0; r < P.n_peers; ++r) tma_store_1d(P.peer_fwd[r] + off, V.out_fwd, bytes);
                 }
                 tma_store_commit();
-                if (i >= cut_end) ++after_cut;
+                if (kMulti && i >= cut_end) ++after_cut;
             }
         }
         }
         __syncwarp();  // every lane has finished reading stage s
         // early signal: every warp of a CTA with peer-dependent tiles is counted (FT warps per such CTA)
-        if (i == sig_pos) {
+        if (kMulti && i == sig_pos) {
             if (lane == 0) tma_store_wait_pending(after_cut);
             early_signal_publish(P, lane, (uint32_t)(ord.cut_ctas * FT));
         }
-        sync_before(i + S);
+        if (kMulti) sync_before(i + S);
         if (lane == s) issue(i + S, s, ids);
         if (++s == S) { s = 0; phase ^= 1u; }
     }
     if (lane == 0) {
         tma_store_wait_all();
-        if ((P.flags & ROME_B200_BARRIER_SIGNAL) && !sig_early && wrote_peer) __threadfence_system();
+        if (kMulti && (P.flags & ROME_B200_BARRIER_SIGNAL) && !sig_early && wrote_peer) __threadfence_system();
     }
     if (P.flags & ROME_B200_INDEPENDENT) asm volatile("griddepcontrol.wait;" ::: "memory");
-    if ((P.flags & ROME_B200_BARRIER_SIGNAL) && !sig_early) fused_barrier_signal(P);
+    if (kMulti && (P.flags & ROME_B200_BARRIER_SIGNAL) && !sig_early) fused_barrier_signal(P);
 }
 
 template <class K>
