@@ -441,7 +441,11 @@ __global__ void __launch_bounds__(eval_threads<FT>(), eval_min_ctas<Fam, FT>()) 
             // owner-sharded exchange: this factor's forward row may have its own destination (a peer GPU); requested
             // before the wait for the stage so that the load's latency hides behind it (warp-uniform address)
             unsigned long long fdst = 0;
-            if (kMulti && mine && ((flags & ROME_B200_PROPOSAL_FWD) || kRouted) && P.fwd_dst) fdst = __ldg(P.fwd_dst + f);
+            // (interior factors -- outside the range that holds every destination -- skip the load: its L2 latency would
+            // otherwise be paid by every factor once the ring runs ahead and the wait below returns at once)
+            if (kMulti && mine && ((flags & ROME_B200_PROPOSAL_FWD) || kRouted) && P.fwd_dst && f >= P.fwd_dst_lo &&
+                f < P.fwd_dst_hi)
+                fdst = __ldg(P.fwd_dst + f);
             mbar_wait(&full[s], phase);
             const unsigned char* st = stage0 + (size_t)s * L.bytes;
             if (mine) {
@@ -602,7 +606,9 @@ __global__ void __launch_bounds__(FT * 32, Fam::kMinCtas) eval_kernel_w(const __
         const int fl = factor_of(i);
         const int f = P.first + fl;
         unsigned long long fdst = 0;  // owner-sharded exchange: per-factor destination of the forward row
-        if (kMulti && fl >= 0 && ((flags & ROME_B200_PROPOSAL_FWD) || kRouted) && P.fwd_dst) fdst = __ldg(P.fwd_dst + f);
+        if (kMulti && fl >= 0 && ((flags & ROME_B200_PROPOSAL_FWD) || kRouted) && P.fwd_dst && f >= P.fwd_dst_lo &&
+            f < P.fwd_dst_hi)
+            fdst = __ldg(P.fwd_dst + f);
         if (lane == s) ids = fetch_ids(i + S);  // consumed when this factor is done: hidden behind its arithmetic
         mbar_wait(&bar[s], phase);
         if (fl >= 0) {
@@ -667,6 +673,10 @@ int launch_kernel_cfg(K k, int* configured, int threads, const EvalParams& p, co
     if (dev < 0 || dev >= 64 || plan.smem_bytes > configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes);
         if (e != cudaSuccess) return (int)e;
+        // shared memory and L1 share one array: ask for no more carve-out than the resident CTAs need, the rest stays L1
+        // (it backs the kernels' local memory -- loop state spilled around the factor body)
+        const int pct = (int)((100LL * plan.ctas_per_sm * (plan.smem_bytes + 1024) + 233471) / 233472);
+        cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
         if (dev >= 0 && dev < 64) configured[dev] = plan.smem_bytes;
     }
     cudaLaunchConfig_t cfg = {};

@@ -68,6 +68,23 @@ static int tile_choice() {
     return v;
 }
 
+// Pipeline depth vs L1.  Shared memory and L1 are one 256 KB array per SM; the carve-out steps are ... 132, 164, 196,
+// 228 KB.  The kernels keep a few loop variables in local memory (spilled around the factor body), and with the
+// largest carve-out the 28 KB of L1 left no longer hold the resident threads' stack frames (Pose3: 384 threads x 128 B),
+// so every spill access goes to L2.  Measured (profiles/r02_analysis.md): Pose3Pose3 50.8 -> 47.1 us and BearingRange
+// at N = 200 23.6 -> 22.6 us with two stages instead of three, Pose2Pose2 at N = 100 unchanged between 2, 3 and 4.
+// Rule: the deepest ring (>= 2) whose resident CTAs stay within the 164 KB carve-out; ROME_B200_MAX_STAGES overrides.
+static int trim_stages(int stages, int ctas, int fixed_bytes, int stage_bytes) {
+    static int cap = 0;
+    if (!cap) {
+        const char* e = getenv("ROME_B200_MAX_STAGES");
+        cap = e ? atoi(e) : -1;
+    }
+    if (cap >= 2) return stages < cap ? stages : cap;
+    while (stages > 2 && ctas * (fixed_bytes + stages * stage_bytes + 1024) > 164 * 1024) --stages;
+    return stages;
+}
+
 // pipeline selection for the Pose3 families: per-warp pipelines unless ROME_B200_PIPELINE=cta
 static int pipeline_choice() {
     static int v = -1;
@@ -102,6 +119,7 @@ int plan_launch(int family, uint32_t flags, int Npad, int smem_per_sm, int smem_
             int stages = (cap - bar_bytes - W * out_warp) / (W * L.bytes);
             if (stages > 4) stages = 4;
             if (stages >= 2) {
+                stages = trim_stages(stages, ctas, bar_bytes + W * out_warp, W * L.bytes);
                 plan->pipeline = 1; plan->ft = W; plan->variant = hot; plan->stages = stages;
                 plan->stage_bytes = L.bytes; plan->out_warp_bytes = out_warp;
                 plan->smem_bytes = bar_bytes + W * (stages * L.bytes + out_warp);
@@ -145,6 +163,7 @@ int plan_launch(int family, uint32_t flags, int Npad, int smem_per_sm, int smem_
             const int need = ctas == 2 ? min_stages_2cta() : 2;
             if (stages >= need) {
                 if (ctas == 2 && stages > 4) stages = 4;
+                stages = trim_stages(stages, ctas, kBarrierBytes + ft * out_warp, L.bytes);
                 plan->ft = ft; plan->variant = variant; plan->stages = stages;
                 plan->stage_bytes = L.bytes;
                 plan->out_warp_bytes = out_warp;

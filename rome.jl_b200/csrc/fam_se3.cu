@@ -29,11 +29,11 @@ struct FamPose3Pose3 {
             float p[2][6], q[2][6], m[2][6];
             double X[2][6], wp[2][3], wq[2][3], t2p[2], t2q[2], t2m[2];
             bool ok = true;
+            meas6_pair<kSample>(row, P, V, f, lane, it, pr, m);
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 load6(Pp + 6 * pr.n[j], p[j]);
                 load6(Qp + 6 * pr.n[j], q[j]);
-                meas6<kSample>(row, P, V, f, lane, 2 * it + j, pr.n[j], m[j]);
 #pragma unroll
                 for (int i = 0; i < 6; ++i) X[j][i] = row.mu[i] + (double)m[j][i];
 #pragma unroll
@@ -181,13 +181,15 @@ struct FamPriorPose3 {
         for (int i = 0; i < 32; ++i) st[i] = 0.f;
         for (int it = 0; 64 * it < Npad; ++it) {
             const Pair pr = pair_of(it, lane, Npad);
+            float mm[2][6];
+            meas6_pair<kSample>(row, P, V, f, lane, it, pr, mm);
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 const int n = pr.n[j];
                 const bool live = pr.live[j];
-                float p[6], m[6];
+                float p[6];
+                const float (&m)[6] = mm[j];
                 load6(Pp + 6 * n, p);
-                meas6<kSample>(row, P, V, f, lane, 2 * it + j, n, m);
                 double X[6];  // sampled point coordinates: exp(e, hat(mu + L z)) = (t, Exp(w))
 #pragma unroll
                 for (int i = 0; i < 6; ++i) X[i] = row.mu[i] + (double)m[i];

@@ -80,6 +80,8 @@ struct rome_b200_ctx {
     float* peers[ROME_B200_NFAMILIES][7] = {};
     Scratch row_dst[ROME_B200_NFAMILIES][2];     // per-factor proposal row destinations (fwd, bwd), device arrays
     int row_dst_n[ROME_B200_NFAMILIES][2] = {};  // number of factors they cover (0 = not set)
+    int row_dst_lo[ROME_B200_NFAMILIES][2] = {}; // factors [lo, hi) hold every non-null destination (a rank's cut block):
+    int row_dst_hi[ROME_B200_NFAMILIES][2] = {}; // the kernels read the destination array only inside this range
     Scratch halo_src[ROME_B200_NVARTYPES], halo_dst[ROME_B200_NVARTYPES];
     int halo_n[ROME_B200_NVARTYPES] = {};
     uint32_t* bar_state = nullptr;   // fused step barrier (rome_b200_set_step_barrier)
@@ -597,12 +599,14 @@ int rome_b200_eval(rome_b200_ctx* ctx, int family, uint32_t flags, uint64_t seed
     p.n_peers = (flags & ROME_B200_PROPOSAL_FWD) ? ctx->n_peers[family] : 0;
     for (int r = 0; r < 7; ++r) p.peer_fwd[r] = ctx->peers[family][r];
     p.fwd_dst = p.bwd_dst = nullptr;
+    p.fwd_dst_lo = p.fwd_dst_hi = 0;
     for (int dir = 0; dir < 2; ++dir) {
         const int n = ctx->row_dst_n[family][dir];
         if (!n) continue;
         if (n != ctx->fac[family].nF)
             return fail(ctx, ROME_B200_SHAPE_MISMATCH, "proposal destinations were set for a different number of factors");
         (dir ? p.bwd_dst : p.fwd_dst) = static_cast<const unsigned long long*>(ctx->row_dst[family][dir].p);
+        if (dir == 0) { p.fwd_dst_lo = ctx->row_dst_lo[family][0]; p.fwd_dst_hi = ctx->row_dst_hi[family][0]; }
     }
     p.bar_state = ctx->bar_state; p.bar_n = ctx->bar_n; p.bar_timeout = 0; p.bar_lo = ctx->bar_lo[family]; p.bar_hi = ctx->bar_hi[family];
     for (int r = 0; r < 7; ++r) p.bar_peer[r] = ctx->bar_peer[r];
@@ -801,6 +805,11 @@ int rome_b200_set_proposal_destinations(rome_b200_ctx* ctx, int family, int dire
     CK(cudaMemcpyAsync(sc.p, rows, (size_t)nF * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));  // the caller's array may be a temporary
     ctx->row_dst_n[family][direction] = nF;
+    int lo = nF, hi = 0;
+    for (int f = 0; f < nF; ++f)
+        if (rows[f]) { if (f < lo) lo = f; hi = f + 1; }
+    ctx->row_dst_lo[family][direction] = lo < hi ? lo : 0;
+    ctx->row_dst_hi[family][direction] = lo < hi ? hi : 0;
     return ROME_B200_OK;
 }
 int rome_b200_set_step_barrier(rome_b200_ctx* ctx, void* d_state, uint32_t* const* peer_slots, int n_peers) {

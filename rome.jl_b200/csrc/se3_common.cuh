@@ -225,4 +225,22 @@ __device__ __forceinline__ void meas6(const RowSE3& row, const EvalParams& P, co
     }
 }
 
+// measurements of the lane's PAIR of particles of iteration `it` (Pose3Pose3, PriorPose3): three Philox blocks
+// (3 it, 3 it + 1, 3 it + 2) give the 12 normals of the two particles -- no wasted draws (meas6 spends two blocks on six)
+template <bool kSample>
+__device__ __forceinline__ void meas6_pair(const RowSE3& row, const EvalParams& P, const FactorView& V, int f, int lane,
+                                           int it, const Pair& pr, float (&m)[2][6]) {
+    if (!kSample) {
+        load6(V.meas + 6 * pr.n[0], m[0]);
+        load6(V.meas + 6 * pr.n[1], m[1]);
+    } else {
+        float z[12];
+#pragma unroll
+        for (int b = 0; b < 3; ++b)
+            normal4(P.seed_lo, P.seed_hi, P.stream_id, (uint32_t)f, (uint32_t)lane, (uint32_t)(3 * it + b), z + 4 * b);
+        sample6(row, z, m[0]);
+        sample6(row, z + 6, m[1]);
+    }
+}
+
 }  // namespace rome

@@ -87,6 +87,7 @@ struct EvalParams {
     // into a peer GPU's memory; 0 = the default row of prop_fwd / prop_bwd); arrays indexed by factor id, or null
     const unsigned long long* fwd_dst;
     const unsigned long long* bwd_dst;
+    int fwd_dst_lo, fwd_dst_hi;  // every non-null entry of fwd_dst lies in [lo, hi): the array is only read there
     // rank barrier fused into the launch (ROME_B200_BARRIER_WAIT / _SIGNAL): this rank's state words, the slot it owns
     // in every peer's state, the number of peers, and the give-up limit of the wait in clock cycles
     uint32_t* bar_state;

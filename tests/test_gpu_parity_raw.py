@@ -302,11 +302,13 @@ def test_priorpose3_parity(ctx):
 
 def twin_normals(seed, sid, f, n, d):
     """host twin of the device sampler's addressing (csrc/factor_kernels.cu): particle n is slot n>>5 of lane n&31.
-    SE(2) families (d = 2, 3): one batch of d Philox blocks serves the 4 slots of a group; SE(3) (d = 6): two
-    blocks per slot."""
+    SE(2) families (d = 2, 3): one batch of d Philox blocks serves the 4 slots of a group; Pose3Pose3 / PriorPose3
+    (d = 6): three blocks serve the lane's pair of slots (2 it, 2 it + 1) of iteration it -- 12 normals, none wasted."""
     lane, slot = n & 31, n >> 5
     if d == 6:
-        return np.concatenate([O.normal4(seed, sid, f, lane, 2 * slot), O.normal4(seed, sid, f, lane, 2 * slot + 1)])[:6]
+        it, j = slot >> 1, slot & 1
+        z = np.concatenate([O.normal4(seed, sid, f, lane, 3 * it + b) for b in range(3)])
+        return z[6 * j:6 * j + 6]
     g, k = slot >> 2, slot & 3
     z = np.concatenate([O.normal4(seed, sid, f, lane, g * d + b) for b in range(d)])
     return z[d * k:d * k + d]
