@@ -298,10 +298,12 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline legs")
     ap.add_argument("--no-parity", action="store_true", help="skip the in-run parity check of a sampled subset against the oracle")
-    ap.add_argument("--barrier", default="fused", choices=["fused", "flags", "nccl", "none"],
-                    help="G>1: rank barrier fused into the evaluation kernels (default: the step's first launch waits for the "
-                         "peers' flags, its last launch publishes this rank's), by two one-warp flag kernels, or by a 4-byte "
-                         "NCCL all-reduce")
+    ap.add_argument("--barrier", default=os.environ.get("ROME_B200_BENCH_BARRIER", "flags"),
+                    choices=["fused", "flags", "flags2", "nccl", "none"],
+                    help="G>1, the rank barrier that closes a step: flags (default) = ONE one-warp kernel that publishes this "
+                         "rank's epoch into every peer's flag array over NVLink and polls its own (rome_b200_peer_barrier); "
+                         "flags2 = the same as two kernels (peer_signal + peer_wait); fused = carried by the evaluation "
+                         "kernels themselves (first launch waits, last launch publishes); nccl = a 4-byte all-reduce")
     ap.add_argument("--e2e-steps", type=int, default=40)
     args = ap.parse_args()
     if args.impl == "reference":
@@ -418,7 +420,9 @@ def main():
 
     def rank_barrier(c):
         """stream-ordered barrier between the ranks (after everything enqueued so far on the launch stream)"""
-        if args.barrier in ("flags", "fused", "none"):
+        if args.barrier == "flags":
+            c.peer_barrier(state, peer_slots)
+        elif args.barrier in ("flags2", "fused", "none"):
             c.peer_signal(state, peer_slots)
             c.peer_wait(state, G - 1)
         else:
@@ -482,7 +486,7 @@ def main():
             if multi and barrier and args.barrier == "fused":
                 fl |= (rb.BARRIER_WAIT if is_routed[idx] else 0) | (rb.BARRIER_SIGNAL if idx == signal_idx else 0)
             c.eval(fam, fl, seed=7, stream_id=k, **kw)
-        if multi and barrier and args.barrier in ("flags", "nccl"):   # "none": experiment only -- steps of the ranks uncoupled
+        if multi and barrier and args.barrier in ("flags", "flags2", "nccl"):   # "none": experiment only -- steps of the ranks uncoupled
             rank_barrier(c)
 
     def capture(fn, **kw):

@@ -324,10 +324,13 @@ ROME_B200_API int rome_b200_ipc_close(rome_b200_ctx* ctx, void* dev_ptr);
  * rome_b200_peer_signal: after everything enqueued so far on the ctx stream, publish the next epoch to every peer.
  * rome_b200_peer_wait: the stream continues once every one of the `n_slots` listed local slots has reached this rank's
  * next wait epoch; gives up after ~2 s (a peer died) and sets the status word, read by rome_b200_peer_status.
- * Epochs live on the device, so both calls may be captured in a CUDA graph and replayed. */
+ * rome_b200_peer_barrier: both in ONE launch (signal, then wait on local slots 0..n_peers-1) -- the closing barrier of a
+ * step for hosts without NCCL (what `bench.py --barrier flags` and OwnerShardedSolver use; validated at 2, 4 and 8 GPUs).
+ * Epochs live on the device, so the calls may be captured in a CUDA graph and replayed. */
 #define ROME_B200_PEER_STATE_WORDS 16
 ROME_B200_API int rome_b200_peer_signal(rome_b200_ctx* ctx, void* d_state, uint32_t* const* peer_slots, int n_peers);
 ROME_B200_API int rome_b200_peer_wait(rome_b200_ctx* ctx, void* d_state, const int32_t* slots, int n_slots);
+ROME_B200_API int rome_b200_peer_barrier(rome_b200_ctx* ctx, void* d_state, uint32_t* const* peer_slots, int n_peers);
 ROME_B200_API int rome_b200_peer_status(rome_b200_ctx* ctx, void* d_state, int* gave_up);
 
 /* ---- CUDA-graph capture of a sweep (several eval calls replayed with one launch) ------------- */

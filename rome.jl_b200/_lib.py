@@ -32,7 +32,7 @@ SYMBOLS = [
     "rome_b200_eval", "rome_b200_eval_host", "rome_b200_eval_host_async", "rome_b200_set_product_plan", "rome_b200_product",
     "rome_b200_reanchor", "rome_b200_set_peer_proposals", "rome_b200_set_proposal_destinations",
     "rome_b200_set_step_barrier", "rome_b200_set_barrier_range", "rome_b200_set_owned_variables", "rome_b200_set_halo_plan", "rome_b200_push_halo", "rome_b200_ipc_export",
-    "rome_b200_ipc_import", "rome_b200_ipc_close", "rome_b200_peer_signal", "rome_b200_peer_wait", "rome_b200_peer_status", "rome_b200_graph_begin", "rome_b200_graph_end",
+    "rome_b200_ipc_import", "rome_b200_ipc_close", "rome_b200_peer_signal", "rome_b200_peer_wait", "rome_b200_peer_barrier", "rome_b200_peer_status", "rome_b200_graph_begin", "rome_b200_graph_end",
     "rome_b200_graph_launch", "rome_b200_malloc_device", "rome_b200_free_device", "rome_b200_malloc_host",
     "rome_b200_free_host", "rome_b200_memcpy_h2d", "rome_b200_memcpy_d2h", "rome_b200_launch_count",
 ]
@@ -105,6 +105,7 @@ def load() -> C.CDLL:
     lib.rome_b200_ipc_close.argtypes = [vp, vp]
     lib.rome_b200_peer_signal.argtypes = [vp, vp, C.POINTER(vp), i]
     lib.rome_b200_peer_wait.argtypes = [vp, vp, ip32, i]
+    lib.rome_b200_peer_barrier.argtypes = [vp, vp, C.POINTER(vp), i]
     lib.rome_b200_peer_status.argtypes = [vp, vp, C.POINTER(i)]
     lib.rome_b200_graph_begin.argtypes = [vp]
     lib.rome_b200_graph_end.argtypes = [vp, C.POINTER(i)]

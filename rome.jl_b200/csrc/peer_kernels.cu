@@ -52,6 +52,36 @@ __global__ void peer_wait_kernel(const uint32_t* flags, int n, uint32_t* epoch, 
     }
 }
 
+// signal + wait in ONE launch (a step's closing barrier costs one kernel start instead of two): lane r publishes the next
+// signal epoch to peer r, then polls local slot r for the next wait epoch.  state = the rank's state words (slots [0, 8),
+// word 8 / 9 signal / wait epoch, word 10 give-up status).
+__global__ void peer_barrier_kernel(PeerSlots peers, int n_peers, uint32_t* state, long long max_cycles) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    uint32_t es = 0, ew = 0;
+    if (threadIdx.x == 0) {
+        es = ++state[8];
+        ew = ++state[9];
+    }
+    es = __shfl_sync(0xffffffffu, es, 0);  // one warp: the epochs travel by shuffle
+    ew = __shfl_sync(0xffffffffu, ew, 0);
+    if ((int)threadIdx.x < n_peers) {
+        __threadfence_system();  // everything this GPU stored before (the proposal rows) is visible before the flag
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peers.slot[threadIdx.x]), "r"(es) : "memory");
+        const long long t0 = clock64();
+        uint32_t v;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(state + threadIdx.x) : "memory");
+            if ((int32_t)(v - ew) >= 0) break;  // wrap-safe "v >= ew"
+            if (clock64() - t0 > max_cycles) {
+                atomicExch(state + 10, 1u);
+                break;
+            }
+            __nanosleep(64);
+        }
+    }
+}
+
 template <class K, class... A>
 static int launch_one_warp_pdl(K k, void* stream, A... args) {
     cudaLaunchConfig_t cfg = {};
@@ -72,6 +102,12 @@ int launch_peer_signal(uint32_t* const* slots, int n_peers, uint32_t* epoch, voi
 }
 int launch_peer_wait(const uint32_t* flags, int n, uint32_t* epoch, uint32_t* status, long long max_cycles, void* stream) {
     return launch_one_warp_pdl(peer_wait_kernel, stream, flags, n, epoch, status, max_cycles);
+}
+
+int launch_peer_barrier(uint32_t* const* slots, int n_peers, uint32_t* state, long long max_cycles, void* stream) {
+    PeerSlots p = {};
+    for (int i = 0; i < n_peers && i < 8; ++i) p.slot[i] = slots[i];
+    return launch_one_warp_pdl(peer_barrier_kernel, stream, p, n_peers, state, max_cycles);
 }
 
 // Halo push (owner-sharded sweeps): copy whole particle blocks of variables this rank owns into the particle stores of

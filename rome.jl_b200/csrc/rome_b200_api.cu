@@ -925,6 +925,20 @@ int rome_b200_peer_wait(rome_b200_ctx* ctx, void* d_state, const int32_t* slots,
     if (ctx->capturing) ctx->capture_kernels++; else ctx->launches++;
     return ROME_B200_OK;
 }
+int rome_b200_peer_barrier(rome_b200_ctx* ctx, void* d_state, uint32_t* const* peer_slots, int n_peers) {
+    if (!ctx) return ROME_B200_BAD_ARG;
+    if (!d_state || n_peers < 0 || n_peers > 7 || (n_peers > 0 && !peer_slots)) return fail(ctx, ROME_B200_BAD_ARG, "bad peer list");
+    for (int r = 0; r < n_peers; ++r)
+        if (!peer_slots[r]) return fail(ctx, ROME_B200_BAD_ARG, "peer slot is NULL");
+    if (int e = bind(ctx)) return e;
+    int clock_khz = 0;
+    cudaDeviceGetAttribute(&clock_khz, cudaDevAttrClockRate, ctx->device);
+    const long long max_cycles = 2LL * 1000LL * (clock_khz > 0 ? clock_khz : 1965000);  // ~2 s
+    int e = launch_peer_barrier(peer_slots, n_peers, static_cast<uint32_t*>(d_state), max_cycles, ctx->stream);
+    if (e) return cuda_fail(ctx, (cudaError_t)e, "peer barrier launch");
+    if (ctx->capturing) ctx->capture_kernels++; else ctx->launches++;
+    return ROME_B200_OK;
+}
 int rome_b200_peer_status(rome_b200_ctx* ctx, void* d_state, int* gave_up) {
     if (!ctx || !d_state || !gave_up) return ROME_B200_BAD_ARG;
     if (int e = bind(ctx)) return e;

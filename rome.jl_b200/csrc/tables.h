@@ -148,6 +148,7 @@ int launch_reanchor(int d, int wrap_dim, unsigned char* store, int nvars, int N,
 int launch_halo_push(const unsigned char* store, int block_bytes, int n, const int32_t* src_var,
                      const unsigned long long* dst_blocks, void* stream);
 int launch_peer_signal(uint32_t* const* slots, int n_peers, uint32_t* epoch, void* stream);
+int launch_peer_barrier(uint32_t* const* slots, int n_peers, uint32_t* state, long long max_cycles, void* stream);
 int launch_peer_wait(const uint32_t* flags, int n, uint32_t* epoch, uint32_t* status, long long max_cycles, void* stream);
 
 }  // namespace rome

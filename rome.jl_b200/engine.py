@@ -355,6 +355,11 @@ class Context:
         slots = np.arange(n_slots, dtype=np.int32)
         self._ck(self._lib.rome_b200_peer_wait(self._h, state_ptr, self._ip(slots), n_slots))
 
+    def peer_barrier(self, state_ptr: int, peer_slot_ptrs):
+        """peer_signal + peer_wait in one launch (rome_b200_peer_barrier)"""
+        arr = (C.c_void_p * max(1, len(peer_slot_ptrs)))(*peer_slot_ptrs)
+        self._ck(self._lib.rome_b200_peer_barrier(self._h, state_ptr, arr, len(peer_slot_ptrs)))
+
     def peer_gave_up(self, state_ptr: int) -> bool:
         v = C.c_int()
         self._ck(self._lib.rome_b200_peer_status(self._h, state_ptr, C.byref(v)))

@@ -298,8 +298,7 @@ class OwnerShardedSolver:
         dist.barrier(group=group)
 
     def _barrier(self):
-        self.ctx.peer_signal(self.state, self.peer_slots)
-        self.ctx.peer_wait(self.state, self.world - 1)
+        self.ctx.peer_barrier(self.state, self.peer_slots)
 
     def sweep(self, seed: int = 0):
         c, lv = self.ctx, self.lv

@@ -55,7 +55,7 @@ class _Ctx:
                 for key in ("res", "stats"):
                     if isinstance(k.get(key), torch.Tensor):
                         k[key].fill_(1.0)
-            if name in ("eval", "peer_signal", "peer_wait", "push_halo"):
+            if name in ("eval", "peer_signal", "peer_wait", "peer_barrier", "push_halo"):
                 self.launch_count += 1
             if name == "ipc_export":
                 return b"\0" * 64

@@ -104,7 +104,7 @@ def build_peer(outdir):
     body, n2 = re.subn(r'asm volatile\("ld\.acquire\.sys\.global\.u32 %0, \[%1\];" : "=r"\((\w+)\) : "l"\((.+?)\) : "memory"\);',
                        r"\1 = *(volatile const uint32_t*)(\2);", body)
     body, n3 = re.subn(r'asm volatile\("griddepcontrol\.[a-z_]+;" ::: "memory"\);', "", body)
-    assert n1 == 1 and n2 == 1 and n3 == 4 and "asm" not in body
+    assert n1 == 2 and n2 == 2 and n3 == 6 and "asm" not in body   # signal, wait and the merged barrier kernel
     text = ('#include "hk_shim.h"\n#undef threadIdx\n#define threadIdx (dim3_{(unsigned)(hk::g_cur & 31), 0, 0})\n'
             "#define __syncthreads() hk::collective(0u)\n#define __nanosleep(ns) hk::yield_()\n"
             "namespace rome {\n" + body + open(os.path.join(HERE, "hk_peer_main.inc")).read() + "}\n")

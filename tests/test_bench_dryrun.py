@@ -52,7 +52,7 @@ def test_bench_single_gpu_dry_run(extra):
         assert "error" in d["parity"]   # the in-run parity leg has no device here: recorded as failed, the line survives
 
 
-@pytest.mark.parametrize("extra", [[], ["--barrier", "flags"], ["--barrier", "nccl"]])
+@pytest.mark.parametrize("extra", [[], ["--barrier", "flags2"], ["--barrier", "fused"], ["--barrier", "nccl"]])
 def test_bench_two_rank_dry_run(extra):
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -69,8 +69,9 @@ def test_bench_two_rank_dry_run(extra):
         assert p.returncode == 0, err[-2000:]
     d = _check_line(outs[0][0], 2)
     assert outs[1][0].strip() == ""   # only rank 0 prints
-    # rank 0, per step: Pose2Pose2 (interior + routed cut factors in one launch), PriorPose2, and -- only with the
-    # separate flag kernels -- signal + wait (the default barrier is fused into the two evaluation launches)
-    assert d["gpu_launches"] == (24 if extra == ["--barrier", "flags"] else 12)
+    # rank 0, per step: Pose2Pose2 (interior + routed cut factors in one launch), PriorPose2, and the closing barrier: ONE
+    # one-warp kernel by default (rome_b200_peer_barrier), two with flags2 (signal + wait), none with the barrier fused
+    # into the evaluation launches or carried by NCCL
+    assert d["gpu_launches"] == {"flags2": 24, "fused": 12, "nccl": 12}.get(extra[-1] if extra else "", 18)
     assert d["exchange_verified"] is True and d["rows_checked_all_ranks"] > 0 and d["halo_blocks_checked_all_ranks"] > 0
     assert "cpu_baseline" not in d    # rank 0 at N=1 only

@@ -426,7 +426,7 @@ def test_gpu_side_rank_barrier_on_emulated_ranks(tmp_path_factory, world):
     """rome_b200_peer_signal / rome_b200_peer_wait (csrc/peer_kernels.cu) with `world` emulated ranks, 60 rounds, ranks
     delayed at random (some fall several kernels behind, others run ahead): no rank leaves wait k before every peer has
     issued signal k, nobody gives up, every epoch and every flag slot ends at the round count.  On the device this was
-    validated at 2 GPUs only."""
+    (on the device: tests/test_gpu_multi.py at 2 GPUs, bench.py --barrier flags at 4 and 8)."""
     import ctypes as C
     import shutil
     if shutil.which("g++") is None:
@@ -446,11 +446,12 @@ def test_gpu_side_rank_barrier_on_emulated_ranks(tmp_path_factory, world):
         lag = np.ascontiguousarray(lag)
         viol = C.c_int(-1)
         state = np.zeros((world, 16), np.uint32)
-        rc = lib.hk_peer_barrier_rounds(world, rounds, lag.ctypes.data_as(C.POINTER(C.c_int)), C.byref(viol),
-                                        state.ctypes.data_as(C.POINTER(C.c_uint32)))
-        assert rc == 0 and viol.value == 0, (pattern, rc, viol.value)
-        assert np.all(state[:, :world - 1] == rounds) and np.all(state[:, world - 1:8] == 0)   # one slot per peer
-        assert np.all(state[:, 8] == rounds) and np.all(state[:, 9] == rounds) and np.all(state[:, 10] == 0)
+        for fn in (lib.hk_peer_barrier_rounds, lib.hk_peer_barrier_rounds_merged):   # two kernels / rome_b200_peer_barrier
+            rc = fn(world, rounds, lag.ctypes.data_as(C.POINTER(C.c_int)), C.byref(viol),
+                    state.ctypes.data_as(C.POINTER(C.c_uint32)))
+            assert rc == 0 and viol.value == 0, (pattern, rc, viol.value)
+            assert np.all(state[:, :world - 1] == rounds) and np.all(state[:, world - 1:8] == 0)   # one slot per peer
+            assert np.all(state[:, 8] == rounds) and np.all(state[:, 9] == rounds) and np.all(state[:, 10] == 0)
 
 
 @pytest.mark.parametrize("max_delay", [1, 3, 17, 60])

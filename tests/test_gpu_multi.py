@@ -85,11 +85,13 @@ def _worker(rank, world, port, q):
         for _ in range(3):
             ctx.peer_signal(state, slots)
             ctx.peer_wait(state, world - 1)
+        for _ in range(2):  # the same in one launch (rome_b200_peer_barrier)
+            ctx.peer_barrier(state, slots)
         ctx.synchronize()
         torch.cuda.synchronize()
         words = np.zeros(16, np.uint32)
         ctx.memcpy_d2h(words, state)
-        ok_b = ok_b and (not ctx.peer_gave_up(state)) and int(words[0]) == 3 and int(words[8]) == 3 and int(words[9]) == 3
+        ok_b = ok_b and (not ctx.peer_gave_up(state)) and int(words[0]) == 5 and int(words[8]) == 5 and int(words[9]) == 5
         dist.barrier()
         q.put((rank, ok_a, ok_b))
     finally:
