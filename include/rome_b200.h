@@ -75,7 +75,8 @@ enum rome_b200_vartype {
     ROME_B200_POINT2 = 1,
     ROME_B200_POSE3 = 2,
     ROME_B200_POINT3 = 3,
-    ROME_B200_NVARTYPES = 4
+    ROME_B200_ROTATION3 = 4, /* src/variables/VariableTypes.jl:50 (Rotation3, SO(3)): rotation-vector coordinates */
+    ROME_B200_NVARTYPES = 5
 };
 
 enum rome_b200_family {
@@ -96,7 +97,10 @@ enum rome_b200_family {
     ROME_B200_POSE3POSE3XYYAW = 13,    /* src/factors/PartialPose3.jl:103-134 SE(2) residual of (x, y, yaw)     */
     ROME_B200_POSE3POSE3ROTATION = 14, /* src/factors/PartialPose3.jl:198-226 r = m - Log(R_p' R_q)             */
     ROME_B200_POSE3POSE3UNITTRANS = 15,/* src/factors/Pose3Pose3.jl:100-116   Pose3Pose3, unit translation part */
-    ROME_B200_NFAMILIES = 16
+    /* families with a THIRD variable (rome_b200_set_factors_ternary) */
+    ROME_B200_POSE3POSE3ROTOFFSET = 16,/* src/factors/Pose3Pose3.jl:57-78  qhat = p o (m.t, bRa Exp(m.w)), bRa: Rotation3 */
+    ROME_B200_POSE3POSE3TRANSFORM = 17,/* src/factors/Pose3Pose3.jl:80-95  qhat = p o Delta o exp(m), Delta: Pose3        */
+    ROME_B200_NFAMILIES = 18
 };
 
 /* eval flags */
@@ -225,6 +229,13 @@ ROME_B200_API int rome_b200_set_factors_scalar(rome_b200_ctx* ctx, int family, i
  * ones): i1 = NULL for priors.  The typed entry points above are thin wrappers of this one. */
 ROME_B200_API int rome_b200_set_factors_gaussian(rome_b200_ctx* ctx, int family, int nF, const int32_t* i0,
                                                  const int32_t* i1, const double* mu, const double* cov);
+/* Families with a third variable (Pose3Pose3RotOffset: i2 indexes Rotation3 variables; Pose3Pose3Transform: i2 indexes
+ * Pose3 variables): one MvNormal(mu[6], cov[6x6]) per factor like rome_b200_set_factors_pose3pose3.  The residual and
+ * the forward proposal (onto the SECOND variable) are closed-form; convolutions onto the first or third variable are
+ * left to the caller's numeric solver, as in the reference. */
+ROME_B200_API int rome_b200_set_factors_ternary(rome_b200_ctx* ctx, int family, int nF, const int32_t* i0,
+                                                const int32_t* i1, const int32_t* i2, const double* mu,
+                                                const double* cov);
 ROME_B200_API int rome_b200_num_factors(rome_b200_ctx* ctx, int family);
 
 /* ---- the hot path --------------------------------------------------------------------------- */

@@ -49,7 +49,8 @@ def lib() -> C.CDLL:
                         ("so3_exp", 2), ("so3_log", 2), ("priorpoint2", 3), ("point2point2", 4), ("pose2point2", 4),
                         ("range2", 4), ("pose2point2bearing", 4), ("priorpoint3", 3), ("point3point3", 4),
                         ("pose3pose3xyyaw", 4), ("pose3pose3rotation", 4), ("pose3pose3unittrans", 4),
-                        ("pose3_point", 3), ("pose3_coords", 3)]:
+                        ("pose3_point", 3), ("pose3_coords", 3), ("pose3pose3rotoffset", 5),
+                        ("pose3pose3transform", 5)]:
             fn = getattr(_lib, "rome_oracle_" + name)
             fn.restype = None
             fn.argtypes = [d] * n
@@ -150,6 +151,16 @@ def pose3pose3xyyaw(X, p, q):
 
 def pose3pose3rotation(m, p, q):
     return _call("pose3pose3rotation", 3, m, p, q)
+
+
+def pose3pose3rotoffset(X, p, q, w):
+    """src/factors/Pose3Pose3.jl:57-78; w = rotation-vector coordinates of the Rotation3 variable bRa"""
+    return _call("pose3pose3rotoffset", 6, X, p, q, w)
+
+
+def pose3pose3transform(X, p, q, D):
+    """src/factors/Pose3Pose3.jl:80-95; D = coordinates of the Pose3 variable Delta"""
+    return _call("pose3pose3transform", 6, X, p, q, D)
 
 
 def pose3pose3unittrans(X, p, q):
@@ -403,6 +414,25 @@ def np_pose3pose3rotation(m, p, q):
     m, p, q = (np.asarray(a, dtype=np.float64) for a in (m, p, q))
     U = np.swapaxes(np_so3_exp(p[..., 3:]), -1, -2) @ np_so3_exp(q[..., 3:])
     return m - np_so3_log(U)
+
+
+def np_pose3pose3rotoffset(X, p, q, w):
+    """NumPy twin of src/factors/Pose3Pose3.jl:57-78 (batched)"""
+    X, p, q, w = (np.asarray(a, dtype=np.float64) for a in (X, p, q, w))
+    Rp, Rq = np_so3_exp(p[..., 3:]), np_so3_exp(q[..., 3:])
+    rt = p[..., :3] + np.einsum("...ij,...j->...i", Rp, X[..., :3]) - q[..., :3]
+    U = np.swapaxes(Rq, -1, -2) @ Rp @ np_so3_exp(w) @ np_so3_exp(X[..., 3:])
+    return np.concatenate([rt, np_so3_log(U)], -1)
+
+
+def np_pose3pose3transform(X, p, q, D):
+    """NumPy twin of src/factors/Pose3Pose3.jl:80-95 (batched)"""
+    X, p, q, D = (np.asarray(a, dtype=np.float64) for a in (X, p, q, D))
+    Rp, Rq, RD = np_so3_exp(p[..., 3:]), np_so3_exp(q[..., 3:]), np_so3_exp(D[..., 3:])
+    lever = D[..., :3] + np.einsum("...ij,...j->...i", RD, X[..., :3])
+    rt = p[..., :3] + np.einsum("...ij,...j->...i", Rp, lever) - q[..., :3]
+    U = np.swapaxes(Rq, -1, -2) @ Rp @ RD @ np_so3_exp(X[..., 3:])
+    return np.concatenate([rt, np_so3_log(U)], -1)
 
 
 def np_pose3pose3unittrans(X, p, q):

@@ -174,6 +174,44 @@ void rome_oracle_pose3pose3(const double X[6], const double p[6], const double q
     rome_oracle_so3_log(U, r + 3);
 }
 
+/* src/factors/Pose3Pose3.jl:57-78 (Pose3Pose3RotOffset): the measurement is taken in frame a, p and q live in frame b,
+ * bRa (a Rotation3 variable, rotation-vector coordinates w) rotates a into b:
+ *   a_m = exp(M, e, aX) = (X.t, Exp(X.w));  b_m = (a_m.t, bRa a_m.R);  qhat = compose(M, p, b_m)
+ *   return vee(M, q, log(M, q, qhat)) = (qhat.t - q.t, vee(Log(q.R' qhat.R))) */
+void rome_oracle_pose3pose3rotoffset(const double X[6], const double p[6], const double q[6], const double w[3],
+                                     double r[6]) {
+    double tp[3], Rp[9], tq[3], Rq[9], M[9], B[9], BM[9], Rh[9], U[9], v[3];
+    rome_oracle_pose3_point(p, tp, Rp);
+    rome_oracle_pose3_point(q, tq, Rq);
+    rome_oracle_so3_exp(X + 3, M);
+    rome_oracle_so3_exp(w, B);
+    mat3_vec(Rp, X, v);
+    mat3_mul(B, M, BM);
+    mat3_mul(Rp, BM, Rh);
+    mat3_tmul(Rq, Rh, U);
+    for (int i = 0; i < 3; ++i) r[i] = tp[i] + v[i] - tq[i];
+    rome_oracle_so3_log(U, r + 3);
+}
+/* src/factors/Pose3Pose3.jl:80-95 (Pose3Pose3Transform): Delta is a Pose3 variable:
+ *   Dn = compose(M, Delta, exp(M, e, X)) = (D.t + D.R X.t, D.R Exp(X.w));  qhat = compose(M, p, Dn)
+ *   return get_coordinates(M, q, log(M, q, qhat)) */
+void rome_oracle_pose3pose3transform(const double X[6], const double p[6], const double q[6], const double D[6],
+                                     double r[6]) {
+    double tp[3], Rp[9], tq[3], Rq[9], tD[3], RD[9], M[9], DM[9], Rh[9], U[9], v[3], l[3];
+    rome_oracle_pose3_point(p, tp, Rp);
+    rome_oracle_pose3_point(q, tq, Rq);
+    rome_oracle_pose3_point(D, tD, RD);
+    rome_oracle_so3_exp(X + 3, M);
+    mat3_vec(RD, X, v);
+    for (int i = 0; i < 3; ++i) l[i] = tD[i] + v[i];
+    mat3_vec(Rp, l, v);
+    mat3_mul(RD, M, DM);
+    mat3_mul(Rp, DM, Rh);
+    mat3_tmul(Rq, Rh, U);
+    for (int i = 0; i < 3; ++i) r[i] = tp[i] + v[i] - tq[i];
+    rome_oracle_so3_log(U, r + 3);
+}
+
 /* src/factors/Pose3D.jl:15-19: vee(M, p, log(M, p, m)) = (m.t - p.t, vee(Log(p.R' m.R))) */
 void rome_oracle_priorpose3(const double m[6], const double p[6], double r[6]) {
     double tp[3], Rp[9], tm[3], Rm[9], U[9];

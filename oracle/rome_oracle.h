@@ -73,6 +73,11 @@ void rome_oracle_pose3pose3xyyaw(const double X[3], const double p[6], const dou
 /* src/factors/PartialPose3.jl:212-226 Pose3Pose3Rotation: m - Log(R_p' R_q) */
 void rome_oracle_pose3pose3rotation(const double m[3], const double p[6], const double q[6], double r[3]);
 /* src/factors/Pose3Pose3.jl:107-116 Pose3Pose3UnitTrans */
+/* families with a third variable: src/factors/Pose3Pose3.jl:57-78 (w: Rotation3 coordinates), :80-95 (D: Pose3) */
+void rome_oracle_pose3pose3rotoffset(const double X[6], const double p[6], const double q[6], const double w[3],
+                                     double r[6]);
+void rome_oracle_pose3pose3transform(const double X[6], const double p[6], const double q[6], const double D[6],
+                                     double r[6]);
 void rome_oracle_pose3pose3unittrans(const double X[6], const double p[6], const double q[6], double r[6]);
 
 /* ---- closed-form roots of the residual (what the per-particle solve converges to) */

@@ -10,10 +10,11 @@ SO_PATH = os.path.join(HERE, "librome_b200.so")
 
 # enums of include/rome_b200.h
 OK, BAD_ARG, CUDA_ERROR, SHAPE_MISMATCH, NOT_SET, NO_DEVICE = 0, -1, -2, -3, -4, -5
-POSE2, POINT2, POSE3, POINT3 = 0, 1, 2, 3
+POSE2, POINT2, POSE3, POINT3, ROTATION3 = 0, 1, 2, 3, 4
 POSE2POSE2, PRIORPOSE2, BEARINGRANGE, POSE3POSE3, PRIORPOSE3 = 0, 1, 2, 3, 4
 PRIORPOINT2, POINT2POINT2, POSE2POINT2, POSE2POINT2RANGE, POINT2POINT2RANGE, POSE2POINT2BEARING = 5, 6, 7, 8, 9, 10
 PRIORPOINT3, POINT3POINT3, POSE3POSE3XYYAW, POSE3POSE3ROTATION, POSE3POSE3UNITTRANS = 11, 12, 13, 14, 15
+POSE3POSE3ROTOFFSET, POSE3POSE3TRANSFORM = 16, 17   # families with a third variable
 RESIDUAL, PROPOSAL_FWD, PROPOSAL_BWD, STATS, SAMPLE, WRITE_MEAS, JACOBIAN, INDEPENDENT = 1, 2, 4, 8, 16, 32, 64, 128
 DECONV = 256
 PRECISE = 512
@@ -28,7 +29,7 @@ SYMBOLS = [
     "rome_b200_set_particles", "rome_b200_set_particles_anchored", "rome_b200_get_particles", "rome_b200_particles_device", "rome_b200_adopt_proposal",
     "rome_b200_set_factors_pose2pose2", "rome_b200_set_factors_priorpose2", "rome_b200_set_factors_bearingrange",
     "rome_b200_set_factors_pose3pose3", "rome_b200_set_factors_priorpose3", "rome_b200_set_factors_point2",
-    "rome_b200_set_factors_scalar", "rome_b200_set_factors_gaussian", "rome_b200_num_factors",
+    "rome_b200_set_factors_scalar", "rome_b200_set_factors_gaussian", "rome_b200_set_factors_ternary", "rome_b200_num_factors",
     "rome_b200_eval", "rome_b200_eval_host", "rome_b200_eval_host_async", "rome_b200_set_product_plan", "rome_b200_product",
     "rome_b200_reanchor", "rome_b200_set_peer_proposals", "rome_b200_set_proposal_destinations",
     "rome_b200_set_step_barrier", "rome_b200_set_barrier_range", "rome_b200_set_owned_variables", "rome_b200_set_halo_plan", "rome_b200_push_halo", "rome_b200_ipc_export",
@@ -86,6 +87,7 @@ def load() -> C.CDLL:
     lib.rome_b200_set_factors_point2.argtypes = [vp, i, i, ip32, ip32, dp, dp]
     lib.rome_b200_set_factors_scalar.argtypes = [vp, i, i, ip32, ip32, dp]
     lib.rome_b200_set_factors_gaussian.argtypes = [vp, i, i, ip32, ip32, dp, dp]
+    lib.rome_b200_set_factors_ternary.argtypes = [vp, i, i, ip32, ip32, ip32, dp, dp]
     lib.rome_b200_num_factors.argtypes = [vp, i]
     lib.rome_b200_eval.argtypes = [vp, i, u32, u64, u32, i, i, C.POINTER(Buffers)]
     lib.rome_b200_eval_host.argtypes = [vp, i, u32, u64, u32, i, i, C.POINTER(Buffers)]

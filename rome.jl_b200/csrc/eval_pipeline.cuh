@@ -49,6 +49,7 @@ __device__ __forceinline__ void write_stats16(float (&st)[16], float* stats, int
 struct FactorView {
     const unsigned char* b0;  // particle block of the first variable  {anchor, rows}
     const unsigned char* b1;  // particle block of the second variable (nullptr for priors)
+    const unsigned char* b2;  // particle block of the third variable (families with three variables, else nullptr)
     const float* meas;        // [dm][Npad] measurement offsets (nullptr with SAMPLE)
     float* out_res;           // [dr][Npad] residual rows, flushed by a warp-local TMA bulk store
     float* out_fwd;           // [dfwd][Npad] forward-proposal rows, same
@@ -130,19 +131,21 @@ __device__ __forceinline__ void normals_for_group(const EvalParams& P, int f, in
 // stage layout (shared by host planning and the kernel)
 // =============================================================================================
 struct StageLayout {
-    int rows_off, v0_off, v1_off, meas_off, bytes;
-    int b0, b1, mb;  // bytes of one slot-0 block, slot-1 block, one factor's measurement block
+    int rows_off, v0_off, v1_off, v2_off, meas_off, bytes;
+    int b0, b1, b2, mb;  // bytes of one slot-0 / slot-1 / slot-2 block, one factor's measurement block
 };
 __host__ __device__ inline StageLayout stage_layout(int ft, int row_bytes, int d0, int d1, int dm, bool sample,
-                                                    int Npad) {
+                                                    int Npad, int d2 = 0) {
     StageLayout L;
     L.b0 = var_block_bytes(d0, Npad);
     L.b1 = d1 ? var_block_bytes(d1, Npad) : 0;
+    L.b2 = d2 ? var_block_bytes(d2, Npad) : 0;
     L.mb = sample ? 0 : dm * Npad * 4;
     L.rows_off = 0;
     L.v0_off = (ft * row_bytes + 127) / 128 * 128;
     L.v1_off = L.v0_off + ft * L.b0;
-    L.meas_off = L.v1_off + ft * L.b1;
+    L.v2_off = L.v1_off + ft * L.b1;
+    L.meas_off = L.v2_off + ft * L.b2;
     L.bytes = (L.meas_off + ft * L.mb + 127) / 128 * 128;
     return L;
 }
@@ -304,6 +307,11 @@ __device__ __forceinline__ void early_signal_publish(const EvalParams& P, int la
 // launch of the bench workload; requesting more registers than the CTA was launched with hangs.  profiles/r02_analysis.md)
 template <int FT>
 constexpr int eval_threads() { return (FT + 1) * 32; }
+// dimension of a family's THIRD variable (0: none) -- families declare `static constexpr int D2` only when they have one
+template <class Fam, class = void>
+struct FamD2 { static constexpr int value = 0; };
+template <class Fam>
+struct FamD2<Fam, decltype((void)Fam::D2)> { static constexpr int value = Fam::D2; };
 // resident CTAs per SM the kernel is compiled for: the 4-factor tile runs twice as many CTAs as the 8-factor tile
 template <class Fam, int FT>
 constexpr int eval_min_ctas() { return FT == 4 ? 2 * Fam::kMinCtas : Fam::kMinCtas; }
@@ -322,7 +330,8 @@ __global__ void __launch_bounds__(eval_threads<FT>(), eval_min_ctas<Fam, FT>()) 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = P.stages;
     const int nTiles = (P.count + FT - 1) / FT;
-    const StageLayout L = stage_layout(FT, (int)sizeof(Row), Fam::D0, Fam::D1, Fam::DM, kSample, P.Npad);
+    constexpr int D2 = FamD2<Fam>::value;
+    const StageLayout L = stage_layout(FT, (int)sizeof(Row), Fam::D0, Fam::D1, Fam::DM, kSample, P.Npad, D2);
     const Row* __restrict__ table = reinterpret_cast<const Row*>(P.rows) + P.first;
     const uint32_t flags = kStatic ? kStatic : P.flags;
 
@@ -332,6 +341,7 @@ __global__ void __launch_bounds__(eval_threads<FT>(), eval_min_ctas<Fam, FT>()) 
     constexpr int TPC = 32 / FT;  // tiles per chunk
     const int jl = lane / FT, fl_in_tile = lane % FT;
     int2 ids_cur = make_int2(0, 0);
+    int id2_cur = 0;  // third variable of the factor (families with three variables)
     // Multi-GPU features (per-factor row destinations, peer replication, the fused rank barrier with its tile order) are
     // compiled into the run-time-flag variant, the forward-proposal variant and the routed variant only: the plain
     // RESIDUAL|STATS variant -- the single-GPU hot path -- carries none of their state through its loop (launches that
@@ -347,16 +357,20 @@ __global__ void __launch_bounds__(eval_threads<FT>(), eval_min_ctas<Fam, FT>()) 
     // one that replicates its rows to every peer -- when the whole grid has finished
     const bool sig_early = kMulti && (P.flags & ROME_B200_BARRIER_SIGNAL) && ord.cut_ctas > 0 && P.n_peers == 0;
     int* sig_count = reinterpret_cast<int*>(smem + 2 * kMaxStages * 8);
-    auto fetch_chunk = [&](int base_j) {  // ids of visiting positions base_j .. base_j + TPC - 1
+    auto fetch_chunk = [&](int base_j, int& id2) {  // ids of visiting positions base_j .. base_j + TPC - 1
         const int j = base_j + jl;
         int2 ids = make_int2(0, 0);
+        id2 = 0;
         if (j < ord.n) {
             const int fl = ((int)blockIdx.x + ord.at(j) * (int)gridDim.x) * FT + fl_in_tile;
-            if (fl < P.count) ids = __ldg(reinterpret_cast<const int2*>(table + fl));
+            if (fl < P.count) {
+                ids = __ldg(reinterpret_cast<const int2*>(table + fl));
+                if constexpr (D2 > 0) id2 = __ldg(&table[fl].ir);
+            }
         }
         return ids;
     };
-    if (warp == FT) ids_cur = fetch_chunk(0);
+    if (warp == FT) ids_cur = fetch_chunk(0, id2_cur);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
@@ -385,7 +399,8 @@ __global__ void __launch_bounds__(eval_threads<FT>(), eval_min_ctas<Fam, FT>()) 
         bool first_round = true;
         bool synced = !kMulti || !(P.flags & ROME_B200_BARRIER_WAIT);  // rank barrier still to be passed?
         for (int base = 0; base < ord.n; base += TPC) {
-            const int2 ids_next = fetch_chunk(base + TPC);  // in flight while this chunk is issued
+            int id2_next = 0;
+            const int2 ids_next = fetch_chunk(base + TPC, id2_next);  // in flight while this chunk is issued
 #pragma unroll 1
             for (int j = 0; j < TPC; ++j) {
                 if (base + j >= ord.n) break;
@@ -399,7 +414,7 @@ __global__ void __launch_bounds__(eval_threads<FT>(), eval_min_ctas<Fam, FT>()) 
                 }
                 if (lane == j * FT) {
                     fence_proxy_async();
-                    mbar_arrive_expect_tx(&full[s], (uint32_t)(nf * ((int)sizeof(Row) + L.b0 + L.b1 + L.mb)));
+                    mbar_arrive_expect_tx(&full[s], (uint32_t)(nf * ((int)sizeof(Row) + L.b0 + L.b1 + L.b2 + L.mb)));
                     tma_load_1d(st + L.rows_off, table + t0, (uint32_t)(nf * sizeof(Row)), &full[s]);
                     if (!kSample)
                         tma_load_1d(st + L.meas_off, P.meas + (size_t)(P.first + t0) * Fam::DM * P.Npad,
@@ -412,10 +427,14 @@ __global__ void __launch_bounds__(eval_threads<FT>(), eval_min_ctas<Fam, FT>()) 
                     if (Fam::D1)
                         tma_load_1d(st + L.v1_off + fl_in_tile * L.b1, P.v1 + (size_t)ids_cur.y * L.b1,
                                     (uint32_t)L.b1, &full[s]);
+                    if constexpr (D2 > 0)
+                        tma_load_1d(st + L.v2_off + fl_in_tile * L.b2, P.v2 + (size_t)id2_cur * L.b2, (uint32_t)L.b2,
+                                    &full[s]);
                 }
                 if (++s == S) { s = 0; phase ^= 1u; first_round = false; }
             }
             ids_cur = ids_next;
+            id2_cur = id2_next;
         }
         if (kMulti && sig_early && ord.nc > 0) {  // early signal, second half: when all consumer warps have reported their rows landed
             if (lane == 0)
@@ -453,6 +472,7 @@ __global__ void __launch_bounds__(eval_threads<FT>(), eval_min_ctas<Fam, FT>()) 
                 FactorView V;
                 V.b0 = st + L.v0_off + warp * L.b0;
                 V.b1 = Fam::D1 ? st + L.v1_off + warp * L.b1 : nullptr;
+                V.b2 = D2 ? st + L.v2_off + warp * L.b2 : nullptr;
                 V.meas = kSample ? nullptr : reinterpret_cast<const float*>(st + L.meas_off + (size_t)warp * L.mb);
                 V.out_res = out;
                 V.out_fwd = out + res_floats;
@@ -617,6 +637,7 @@ __global__ void __launch_bounds__(FT * 32, Fam::kMinCtas) eval_kernel_w(const __
         FactorView V;
         V.b0 = st + L.v0_off;
         V.b1 = Fam::D1 ? st + L.v1_off : nullptr;
+        V.b2 = nullptr;  // families with a third variable run the CTA pipeline (kWarpFT = 0)
         V.meas = kSample ? nullptr : reinterpret_cast<const float*>(st + L.meas_off);
         V.out_res = out;
         V.out_fwd = out + res_floats;

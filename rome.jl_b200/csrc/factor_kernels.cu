@@ -16,12 +16,13 @@ int launch_pose3pose3(const EvalParams&, const LaunchPlan&, int, cudaStream_t);
 int launch_priorpose3(const EvalParams&, const LaunchPlan&, int, cudaStream_t);
 int launch_point3(int family, const EvalParams&, const LaunchPlan&, int, cudaStream_t);
 int launch_pose3_partial(int family, const EvalParams&, const LaunchPlan&, int, cudaStream_t);
+int launch_pose3_ternary(int family, const EvalParams&, const LaunchPlan&, int, cudaStream_t);
 
 // =============================================================================================
 // host side: launch planning + dispatch
 // =============================================================================================
 struct FamDims {
-    int row_bytes, d0, d1, dm, dr, dfwd;
+    int row_bytes, d0, d1, dm, dr, dfwd, d2;  // d2: dimension of a third variable (0: none)
 };
 static FamDims fam_dims(int family) {
     switch (family) {
@@ -40,6 +41,8 @@ static FamDims fam_dims(int family) {
         case ROME_B200_POSE3POSE3XYYAW:
         case ROME_B200_POSE3POSE3ROTATION: return {(int)sizeof(RowSE2), 6, 6, 3, 3, 0};
         case ROME_B200_POSE3POSE3UNITTRANS: return {(int)sizeof(RowSE3), 6, 6, 6, 6, 0};
+        case ROME_B200_POSE3POSE3ROTOFFSET: return {(int)sizeof(RowSE3), 6, 6, 6, 6, 6, 3};
+        case ROME_B200_POSE3POSE3TRANSFORM: return {(int)sizeof(RowSE3), 6, 6, 6, 6, 6, 6};
         default: return {(int)sizeof(RowSE3), 6, 0, 6, 6, 6};
     }
 }
@@ -107,7 +110,7 @@ int plan_launch(int family, uint32_t flags, int Npad, int smem_per_sm, int smem_
     const int hot = out_flags == kHot1 ? ((multi && fd.dfwd) ? 3 : 1)
                                        : out_flags == kHot2 ? ((flags & ROME_B200_ROUTED_ONLY) ? 3 : 2) : 0;
     plan->pipeline = 0;
-    if (se3 && pipeline_choice() == 1) {
+    if (se3 && fd.d2 == 0 && pipeline_choice() == 1) {  // (families with a third variable are built for the CTA pipeline)
         // per-warp pipelines: W warps per CTA, each with its own ring of `stages` slots + output slice
         const int W = 12;
         const int out_warp = (fd.dr + (hot == 1 ? 0 : fd.dfwd)) * Npad * 4;
@@ -153,7 +156,7 @@ int plan_launch(int family, uint32_t flags, int Npad, int smem_per_sm, int smem_
         const int variant = ft == 8 ? hot : 0;  // compile-time flag variants exist for the 8- and 4-factor tiles only
         // per-warp output slice: residual rows, then forward-proposal rows (the generic variant reserves both)
         const int out_warp = (fd.dr + (variant == 1 ? 0 : fd.dfwd)) * Npad * 4;
-        const StageLayout L = stage_layout(ft, fd.row_bytes, fd.d0, fd.d1, fd.dm, sample, Npad);
+        const StageLayout L = stage_layout(ft, fd.row_bytes, fd.d0, fd.d1, fd.dm, sample, Npad, fd.d2);
         // prefer 2 CTAs/SM (register cap of the SE(2) kernels allows it) with >= 3 stages each, else 1 CTA/SM
         for (int ctas = (se3 ? 1 : 2); ctas >= 1; --ctas) {
             const int budget = (smem_per_sm / ctas) - 1024;  // 1 KB per CTA is reserved by the system
@@ -195,6 +198,8 @@ int launch_eval(int family, const EvalParams& p, const LaunchPlan& plan, int gri
         case ROME_B200_POSE3POSE3XYYAW:
         case ROME_B200_POSE3POSE3ROTATION:
         case ROME_B200_POSE3POSE3UNITTRANS: return launch_pose3_partial(family, p, plan, grid, s);
+        case ROME_B200_POSE3POSE3ROTOFFSET:
+        case ROME_B200_POSE3POSE3TRANSFORM: return launch_pose3_ternary(family, p, plan, grid, s);
     }
     return (int)cudaErrorInvalidValue;
 }
@@ -229,6 +234,7 @@ __global__ void pack_kernel(int nvars, int N, int Npad, int wrap_dim, const doub
 #pragma unroll
         for (int c = 0; c < D; ++c) x[c] = n < N ? src[(size_t)n * D + c] : a[c];
         if (D == 6) closest_rotvec(x[3], x[4], x[5], a[3], a[4], a[5]);  // Pose3: rotation vector nearest the anchor's
+        if (D == 3 && wrap_dim == -2) closest_rotvec(x[0], x[1], x[2], a[0], a[1], a[2]);  // Rotation3 likewise
 #pragma unroll
         for (int c = 0; c < D; ++c) {
             double o = x[c] - a[c];
@@ -276,6 +282,7 @@ __global__ void unpack_kernel(int nvars, int N, int Npad, int wrap_dim, const un
             if (c == wrap_dim) x[c] = wrap_pi(x[c]);
         }
         if (D == 6) closest_rotvec(x[3], x[4], x[5], 0.0, 0.0, 0.0);  // Pose3: report the principal rotation vector
+        if (D == 3 && wrap_dim == -2) closest_rotvec(x[0], x[1], x[2], 0.0, 0.0, 0.0);  // Rotation3 likewise
 #pragma unroll
         for (int c = 0; c < D; ++c) dst[(size_t)n * D + c] = x[c];
     }

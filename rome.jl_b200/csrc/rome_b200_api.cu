@@ -25,7 +25,7 @@ struct FactorStore {
     int nF = 0;
     void* rows = nullptr;
     size_t cap = 0;
-    int max_i0 = -1, max_i1 = -1;
+    int max_i0 = -1, max_i1 = -1, max_i2 = -1;
 };
 struct Scratch {
     void* p = nullptr;
@@ -36,8 +36,15 @@ struct ProductPlan {
     Scratch off, buf, row;  // device copies of the CSR arrays
 };
 
-const int kVarDim[ROME_B200_NVARTYPES] = {3, 2, 6, 3};
-const int kWrapDim[ROME_B200_NVARTYPES] = {2, -1, -1, -1};
+const int kVarDim[ROME_B200_NVARTYPES] = {3, 2, 6, 3, 3};
+// heading coordinate that wraps (Pose2), -1: none, -2: the three coordinates are a rotation vector (Rotation3; the
+// rotation part of Pose3 is recognised by d = 6)
+const int kWrapDim[ROME_B200_NVARTYPES] = {2, -1, -1, -1, -2};
+// third variable type of a family (-1: none)
+inline int fam_vt2(int family) {
+    return family == ROME_B200_POSE3POSE3ROTOFFSET ? ROME_B200_ROTATION3
+         : family == ROME_B200_POSE3POSE3TRANSFORM ? ROME_B200_POSE3 : -1;
+}
 // family -> (first variable type, second variable type or -1, dm, dr, nstats, dj, row bytes, prop dims fwd/bwd)
 struct FamInfo {
     int vt0, vt1, dm, dr, nstats, dj, row_bytes, dfwd, dbwd;
@@ -59,6 +66,8 @@ const FamInfo kFam[ROME_B200_NFAMILIES] = {
     {ROME_B200_POSE3, ROME_B200_POSE3, 3, 3, 16, 0, (int)sizeof(RowSE2), 0, 0},    // Pose3Pose3XYYaw
     {ROME_B200_POSE3, ROME_B200_POSE3, 3, 3, 16, 0, (int)sizeof(RowSE2), 0, 0},    // Pose3Pose3Rotation
     {ROME_B200_POSE3, ROME_B200_POSE3, 6, 6, 32, 0, (int)sizeof(RowSE3), 0, 0},    // Pose3Pose3UnitTrans
+    {ROME_B200_POSE3, ROME_B200_POSE3, 6, 6, 32, 0, (int)sizeof(RowSE3), 6, 0},    // Pose3Pose3RotOffset (+ Rotation3)
+    {ROME_B200_POSE3, ROME_B200_POSE3, 6, 6, 32, 0, (int)sizeof(RowSE3), 6, 0},    // Pose3Pose3Transform (+ Pose3)
 };
 
 thread_local std::string g_create_error;
@@ -173,17 +182,17 @@ int upload_rows(rome_b200_ctx* ctx, int family, const void* host_rows, int nF, i
         CK(cudaMemcpyAsync(fs.rows, host_rows, bytes, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));  // host_rows is a temporary
     }
-    fs.nF = nF; fs.max_i0 = max_i0; fs.max_i1 = max_i1;
+    fs.nF = nF; fs.max_i0 = max_i0; fs.max_i1 = max_i1; fs.max_i2 = -1;
     return 0;
 }
 
 template <class Row, int D>
 int set_gaussian_factors(rome_b200_ctx* ctx, int family, int nF, const int32_t* ip, const int32_t* iq,
-                         const double* mu, const double* cov) {
+                         const double* mu, const double* cov, const int32_t* ir = nullptr) {
     if (!ctx) return ROME_B200_BAD_ARG;
     if (nF < 0 || (nF > 0 && (!ip || !mu || !cov))) return fail(ctx, ROME_B200_BAD_ARG, "null factor arrays");
     std::vector<Row> rows((size_t)nF);
-    int m0 = -1, m1 = -1;
+    int m0 = -1, m1 = -1, m2 = -1;
     double L[D * D];
     for (int f = 0; f < nF; ++f) {
         Row& r = rows[f];
@@ -193,6 +202,13 @@ int set_gaussian_factors(rome_b200_ctx* ctx, int family, int nF, const int32_t* 
         if (r.ip < 0 || (iq && r.iq < 0)) return fail(ctx, ROME_B200_BAD_ARG, "negative variable index");
         if (r.ip > m0) m0 = r.ip;
         if (r.iq > m1) m1 = r.iq;
+        if constexpr (D == 6) {
+            if (ir) {
+                if (ir[f] < 0) return fail(ctx, ROME_B200_BAD_ARG, "negative variable index");
+                r.ir = ir[f];
+                if (r.ir > m2) m2 = r.ir;
+            }
+        }
         for (int i = 0; i < D; ++i) r.mu[i] = mu[(size_t)f * D + i];
         if (!cholesky(cov + (size_t)f * D * D, D, L)) {
             char b[96];
@@ -203,7 +219,9 @@ int set_gaussian_factors(rome_b200_ctx* ctx, int family, int nF, const int32_t* 
         for (int i = 0; i < D; ++i)
             for (int j = 0; j <= i; ++j) r.L[k++] = (float)L[i * D + j];
     }
-    return upload_rows(ctx, family, rows.data(), nF, m0, m1);
+    if (int e = upload_rows(ctx, family, rows.data(), nF, m0, m1)) return e;
+    ctx->fac[family].max_i2 = m2;
+    return 0;
 }
 
 }  // namespace
@@ -519,6 +537,7 @@ int rome_b200_set_factors_gaussian(rome_b200_ctx* ctx, int family, int nF, const
     if (family < 0 || family >= ROME_B200_NFAMILIES) return fail(ctx, ROME_B200_BAD_ARG, "bad family");
     const FamInfo& fi = kFam[family];
     const bool binary = fi.vt1 >= 0;
+    if (fam_vt2(family) >= 0) return fail(ctx, ROME_B200_BAD_ARG, "family has a third variable: use rome_b200_set_factors_ternary");
     if (binary && nF > 0 && !i1) return fail(ctx, ROME_B200_BAD_ARG, "second variable index array is NULL");
     if (fi.row_bytes == (int)sizeof(RowSE3))
         return set_gaussian_factors<RowSE3, 6>(ctx, family, nF, i0, binary ? i1 : nullptr, mu, cov);
@@ -526,6 +545,14 @@ int rome_b200_set_factors_gaussian(rome_b200_ctx* ctx, int family, int nF, const
         return set_gaussian_factors<RowSE2, 3>(ctx, family, nF, i0, binary ? i1 : nullptr, mu, cov);
     if (fi.row_bytes == (int)sizeof(RowPT2)) return rome_b200_set_factors_point2(ctx, family, nF, i0, i1, mu, cov);
     return fail(ctx, ROME_B200_BAD_ARG, "family does not hold a single MvNormal belief");
+}
+int rome_b200_set_factors_ternary(rome_b200_ctx* ctx, int family, int nF, const int32_t* i0, const int32_t* i1,
+                                  const int32_t* i2, const double* mu, const double* cov) {
+    if (!ctx) return ROME_B200_BAD_ARG;
+    if (family < 0 || family >= ROME_B200_NFAMILIES || fam_vt2(family) < 0)
+        return fail(ctx, ROME_B200_BAD_ARG, "family has no third variable");
+    if (nF > 0 && (!i1 || !i2)) return fail(ctx, ROME_B200_BAD_ARG, "second / third variable index array is NULL");
+    return set_gaussian_factors<RowSE3, 6>(ctx, family, nF, i0, i1, mu, cov, i2);
 }
 int rome_b200_num_factors(rome_b200_ctx* ctx, int family) {
     if (!ctx || family < 0 || family >= ROME_B200_NFAMILIES) return ROME_B200_BAD_ARG;
@@ -551,6 +578,13 @@ static int check_eval(rome_b200_ctx* ctx, int family, uint32_t flags, int first,
         if (v1.nvars == 0) return fail(ctx, ROME_B200_NOT_SET, "particles of the second variable type are not set");
         if (fs.max_i1 >= v1.nvars) return fail(ctx, ROME_B200_SHAPE_MISMATCH, "factor refers to a variable index beyond the particle store");
         if (v1.N != v0.N) return fail(ctx, ROME_B200_SHAPE_MISMATCH, "particle counts differ between variable types");
+    }
+    if (const int vt2 = fam_vt2(family); vt2 >= 0) {
+        const VarStore& v2 = ctx->vars[vt2];
+        if (v2.nvars == 0) return fail(ctx, ROME_B200_NOT_SET, "particles of the third variable type are not set");
+        if (fs.max_i2 < 0) return fail(ctx, ROME_B200_NOT_SET, "factors of this family must be set with rome_b200_set_factors_ternary");
+        if (fs.max_i2 >= v2.nvars) return fail(ctx, ROME_B200_SHAPE_MISMATCH, "factor refers to a variable index beyond the particle store");
+        if (v2.N != v0.N) return fail(ctx, ROME_B200_SHAPE_MISMATCH, "particle counts differ between variable types");
     }
     if (!(flags & ROME_B200_SAMPLE) && !b->meas) return fail(ctx, ROME_B200_BAD_ARG, "meas is NULL and SAMPLE is not set");
     if ((flags & ROME_B200_WRITE_MEAS) && (!(flags & ROME_B200_SAMPLE) || !b->meas_out))
@@ -594,6 +628,7 @@ int rome_b200_eval(rome_b200_ctx* ctx, int family, uint32_t flags, uint64_t seed
     p.first = first; p.count = count;
     p.N = v0.N; p.Npad = v0.Npad;
     p.v0 = v0.store; p.v1 = v1.store;
+    p.v2 = fam_vt2(family) >= 0 ? ctx->vars[fam_vt2(family)].store : nullptr;
     p.meas = b->meas; p.meas_out = b->meas_out; p.res = b->res; p.prop_fwd = b->prop_fwd; p.prop_bwd = b->prop_bwd;
     p.stats = b->stats; p.jac = b->jac;
     p.n_peers = (flags & ROME_B200_PROPOSAL_FWD) ? ctx->n_peers[family] : 0;
@@ -754,7 +789,7 @@ int rome_b200_product(rome_b200_ctx* ctx, int vartype, int n_bufs, const float* 
     p.iters = gibbs_iters > 0 ? gibbs_iters : 2;
     p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32); p.stream_id = stream_id;
     p.bw_scale = (float)std::pow(4.0 / ((d + 2.0) * vs.N), 1.0 / (d + 4.0));
-    int e = launch_product(d, kWrapDim[vartype], &p, ctx->num_sms, ctx->stream);
+    int e = launch_product(d, kWrapDim[vartype] < 0 ? -1 : kWrapDim[vartype], &p, ctx->num_sms, ctx->stream);
     if (e) return cuda_fail(ctx, (cudaError_t)e, "product kernel launch");
     if (ctx->capturing) ctx->capture_kernels++; else ctx->launches++;
     if (flags & ROME_B200_PRODUCT_REANCHOR) return rome_b200_reanchor(ctx, vartype);
@@ -768,7 +803,7 @@ int rome_b200_reanchor(rome_b200_ctx* ctx, int vartype) {
     if (vs.nvars == 0) return fail(ctx, ROME_B200_NOT_SET, "particles of this variable type are not set");
     if (int e = bind(ctx)) return e;
     const int nown = (ctx->owned[vartype] >= 0 && ctx->owned[vartype] < vs.nvars) ? ctx->owned[vartype] : vs.nvars;
-    int e = launch_reanchor(kVarDim[vartype], kWrapDim[vartype], vs.store, nown, vs.N, vs.Npad, ctx->stream);
+    int e = launch_reanchor(kVarDim[vartype], kWrapDim[vartype] < 0 ? -1 : kWrapDim[vartype], vs.store, nown, vs.N, vs.Npad, ctx->stream);
     if (e) return cuda_fail(ctx, (cudaError_t)e, "reanchor kernel launch");
     if (ctx->capturing) ctx->capture_kernels++; else ctx->launches++;
     return ROME_B200_OK;

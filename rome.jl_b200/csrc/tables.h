@@ -33,7 +33,8 @@ struct alignas(32) RowSE3 {
     int32_t ip, iq;
     double mu[6];
     float L[21];  // row-major lower triangle: L00 L10 L11 L20 L21 L22 ...
-    float pad[5];
+    int32_t ir;   // third variable (Pose3Pose3RotOffset / Pose3Pose3Transform), 0 otherwise
+    float pad[4];
 };
 static_assert(sizeof(RowSE3) == 160, "RowSE3 must be 160 B");
 
@@ -69,6 +70,7 @@ struct EvalParams {
     int N, Npad;
     const unsigned char* v0;  // particle store of the first variable's type
     const unsigned char* v1;  // second variable's type (may alias v0; unused for priors)
+    const unsigned char* v2;  // third variable's type (families with three variables), else null
     const float* meas;
     float* meas_out;
     float* res;

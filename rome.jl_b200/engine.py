@@ -12,10 +12,11 @@ import numpy as np
 from . import _lib as L
 from ._lib import (BEARINGRANGE, JACOBIAN, POINT2, POINT2POINT2, POINT2POINT2RANGE, POINT3, POINT3POINT3, POSE2,
                    POSE2POINT2, POSE2POINT2BEARING, POSE2POINT2RANGE, POSE2POSE2, POSE3, POSE3POSE3,
-                   POSE3POSE3ROTATION, POSE3POSE3UNITTRANS, POSE3POSE3XYYAW, PRIORPOINT2, PRIORPOINT3, PRIORPOSE2,
+                   POSE3POSE3ROTATION, POSE3POSE3ROTOFFSET, POSE3POSE3TRANSFORM, POSE3POSE3UNITTRANS, POSE3POSE3XYYAW,
+                   PRIORPOINT2, PRIORPOINT3, PRIORPOSE2, ROTATION3,
                    PRIORPOSE3, PROPOSAL_BWD, PROPOSAL_FWD, RESIDUAL, SAMPLE, STATS, WRITE_MEAS, Buffers, RomeB200Error)
 
-VAR_DIM = {POSE2: 3, POINT2: 2, POSE3: 6, POINT3: 3}
+VAR_DIM = {POSE2: 3, POINT2: 2, POSE3: 6, POINT3: 3, ROTATION3: 3}
 # family -> (vartype of first variable, vartype of second variable or None, dm, dr, nstats, dj, dfwd, dbwd)
 FAMILY = {
     POSE2POSE2: (POSE2, POSE2, 3, 3, 16, 4, 3, 3),
@@ -35,17 +36,23 @@ FAMILY = {
     POSE3POSE3XYYAW: (POSE3, POSE3, 3, 3, 16, 0, 0, 0),
     POSE3POSE3ROTATION: (POSE3, POSE3, 3, 3, 16, 0, 0, 0),
     POSE3POSE3UNITTRANS: (POSE3, POSE3, 6, 6, 32, 0, 0, 0),
+    # families with a third variable (FAMILY_VT2): src/factors/Pose3Pose3.jl:57-95
+    POSE3POSE3ROTOFFSET: (POSE3, POSE3, 6, 6, 32, 0, 6, 0),
+    POSE3POSE3TRANSFORM: (POSE3, POSE3, 6, 6, 32, 0, 6, 0),
 }
+# vartype of the THIRD variable of a family
+FAMILY_VT2 = {POSE3POSE3ROTOFFSET: ROTATION3, POSE3POSE3TRANSFORM: POSE3}
 # algorithmic bytes per factor-particle eval with this layout (DESIGN.md "bytes per eval"):
 # read both variables' offsets + the measurement offsets, write the residual (float32 each)
 BYTES_PER_EVAL = {POSE2POSE2: 48, PRIORPOSE2: 36, BEARINGRANGE: 36, POSE3POSE3: 96, PRIORPOSE3: 72,
                   PRIORPOINT2: 24, POINT2POINT2: 32, POSE2POINT2: 36, POSE2POINT2RANGE: 28, POINT2POINT2RANGE: 24,
                   POSE2POINT2BEARING: 28, PRIORPOINT3: 36, POINT3POINT3: 48, POSE3POSE3XYYAW: 72,
-                  POSE3POSE3ROTATION: 72, POSE3POSE3UNITTRANS: 96}
+                  POSE3POSE3ROTATION: 72, POSE3POSE3UNITTRANS: 96, POSE3POSE3ROTOFFSET: 108, POSE3POSE3TRANSFORM: 120}
 BYTES_PER_EVAL_SAMPLED = {POSE2POSE2: 36, PRIORPOSE2: 24, BEARINGRANGE: 28, POSE3POSE3: 72, PRIORPOSE3: 48,
                           PRIORPOINT2: 16, POINT2POINT2: 24, POSE2POINT2: 28, POSE2POINT2RANGE: 24,
                           POINT2POINT2RANGE: 20, POSE2POINT2BEARING: 24, PRIORPOINT3: 24, POINT3POINT3: 36,
-                          POSE3POSE3XYYAW: 60, POSE3POSE3ROTATION: 60, POSE3POSE3UNITTRANS: 72}
+                          POSE3POSE3XYYAW: 60, POSE3POSE3ROTATION: 60, POSE3POSE3UNITTRANS: 72,
+                          POSE3POSE3ROTOFFSET: 84, POSE3POSE3TRANSFORM: 96}
 
 
 def plan_query(family: int, flags: int, N: int):
@@ -239,6 +246,12 @@ class Context:
         self._ck(self._lib.rome_b200_set_factors_gaussian(self._h, family, len(i0), self._ip(i0),
                                                           None if i1 is None else self._ip(i1), self._dp(mu),
                                                           self._dp(cov)))
+
+    def set_factors_ternary(self, family, i0, i1, i2, mu, cov):
+        """Pose3Pose3RotOffset (i2: Rotation3 variables) / Pose3Pose3Transform (i2: Pose3 variables): MvNormal(mu[6], cov)"""
+        i0, i1, i2, mu, cov = _i32(i0), _i32(i1), _i32(i2), _f64(mu), _f64(cov)
+        self._ck(self._lib.rome_b200_set_factors_ternary(self._h, family, len(i0), self._ip(i0), self._ip(i1),
+                                                         self._ip(i2), self._dp(mu), self._dp(cov)))
 
     def set_factors_scalar(self, family, i0, i1, belief):
         """Pose2Point2Range / Point2Point2Range / Pose2Point2Bearing: Normal(mean, sigma) rows [nF][2]"""

@@ -72,6 +72,10 @@ class Point3(InferenceVariable):  # src/variables/VariableTypes.jl:23
     vartype, dim, manifold = L.POINT3, 3, "TranslationGroup(3)"
 
 
+class Rotation3(InferenceVariable):  # src/variables/VariableTypes.jl:50; coordinates = rotation vector
+    vartype, dim, manifold = L.ROTATION3, 3, "SpecialOrthogonal(3)"
+
+
 # ---- factors -----------------------------------------------------------------------------------------
 class AbstractFactor:
     family: int
@@ -231,6 +235,23 @@ class Pose3Pose3UnitTrans(AbstractManifoldMinimize):  # src/factors/Pose3Pose3.j
     variabletypes = (Pose3, Pose3)
 
 
+@dataclass
+class Pose3Pose3RotOffset(AbstractManifoldMinimize):  # src/factors/Pose3Pose3.jl:57-78
+    """odometry measured in a rotated frame: qhat = p o (m.t, bRa Exp(m.w)) with bRa a Rotation3 variable"""
+    Z: MvNormal = field(default_factory=lambda: _default_mv(6, [0.01] * 3 + [0.0001] * 3))
+    family = L.POSE3POSE3ROTOFFSET
+    variabletypes = (Pose3, Pose3, Rotation3)
+
+
+@dataclass
+class Pose3Pose3Transform(AbstractManifoldMinimize):  # src/factors/Pose3Pose3.jl:80-95
+    """qhat = p o Delta o exp(m) with the extrinsic Delta a Pose3 variable"""
+    Z: MvNormal = field(default_factory=lambda: _default_mv(6, [0.01] * 3 + [0.0001] * 3))
+    family = L.POSE3POSE3TRANSFORM
+    variabletypes = (Pose3, Pose3, Pose3)
+
+
+TERNARY_FACTORS = (Pose3Pose3RotOffset, Pose3Pose3Transform)
 SCALAR_FACTORS = (Pose2Point2Range, Point2Point2Range, Pose2Point2Bearing)
 POINT2_FACTORS = (PriorPoint2, Point2Point2, Pose2Point2)
 PARTIAL_FACTORS = (Pose3Pose3XYYaw, Pose3Pose3Rotation, Pose3Pose3UnitTrans)  # no closed-form full proposal
@@ -254,8 +275,10 @@ def getManifold(x) -> str:
         return Pose2.manifold  # PartialPose3.jl:113
     if isinstance(x, Pose3Pose3Rotation):
         return "SpecialOrthogonal(3)"  # PartialPose3.jl:204
-    if isinstance(x, Pose3Pose3UnitTrans):
-        return Pose3.manifold  # Pose3Pose3.jl:105
+    if isinstance(x, (Pose3Pose3UnitTrans, Pose3Pose3RotOffset, Pose3Pose3Transform)):
+        return Pose3.manifold  # Pose3Pose3.jl:105, :61, :84
+    if isinstance(x, Rotation3) or x is Rotation3:
+        return Rotation3.manifold
     if isinstance(x, (Pose2Point2Range, Point2Point2Range)):
         return "TranslationGroup(1)"  # Range2D.jl:9,49
     if isinstance(x, Pose2Point2Bearing):

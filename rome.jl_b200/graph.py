@@ -15,10 +15,10 @@ import numpy as np
 
 from . import _lib as L
 from .engine import FAMILY, VAR_DIM, Context, meas_to_offsets, offsets_to_meas, rows_to_particle_major
-from .factors import (PARTIAL_FACTORS, POINT2_FACTORS, SCALAR_FACTORS, AbstractFactor, InferenceVariable, Point2, Point3,
+from .factors import (PARTIAL_FACTORS, POINT2_FACTORS, SCALAR_FACTORS, TERNARY_FACTORS, Rotation3, AbstractFactor, InferenceVariable, Point2, Point3,
                       Pose2, Pose2Point2BearingRange, Pose3, factor_mean)
 
-_VARCLASS = {L.POSE2: Pose2, L.POINT2: Point2, L.POSE3: Pose3, L.POINT3: Point3}
+_VARCLASS = {L.POSE2: Pose2, L.POINT2: Point2, L.POSE3: Pose3, L.POINT3: Point3, L.ROTATION3: Rotation3}
 
 
 @dataclass
@@ -203,6 +203,9 @@ class DeviceGraph:
                 c.set_factors_pose3pose3(i0, i1, a, b)
             elif fam == L.PRIORPOSE3:
                 c.set_factors_priorpose3(i0, a, b)
+            elif isinstance(facs[0].fnc, TERNARY_FACTORS):
+                i2 = [fg.variables[f.variableOrderSymbols[2]].index for f in facs]
+                c.set_factors_ternary(fam, i0, i1, i2, a, b)
             elif isinstance(facs[0].fnc, POINT2_FACTORS):
                 c.set_factors_point2(fam, i0, i1, a, b)
             elif isinstance(facs[0].fnc, SCALAR_FACTORS):
@@ -309,6 +312,10 @@ def approxConv(fg: FactorGraph, flabel, target, N: int | None = None, seed=0, ct
     fnc = f.fnc
     N = N or fg.solverParams.N
     slot = f.variableOrderSymbols.index(target)
+    if isinstance(fnc, TERNARY_FACTORS) and slot != 1:
+        # qhat = p o (...) has a closed form onto the SECOND variable; onto p or onto the third variable (bRa / Delta)
+        # the reference runs its numeric solver -- not shipped
+        raise NotImplementedError(f"{type(fnc).__name__}: only the convolution onto the second variable is closed-form here")
     pts = []
     for k, (l, t) in enumerate(zip(f.variableOrderSymbols, fnc.variabletypes)):
         v = fg.variables[l]
@@ -330,7 +337,9 @@ def approxConv(fg: FactorGraph, flabel, target, N: int | None = None, seed=0, ct
         raise NotImplementedError(f"{type(fnc).__name__}: the convolution has no unique root")
     if isinstance(fnc, POINT2_FACTORS) and not fnc.is_prior and slot != last:
         raise NotImplementedError(f"{type(fnc).__name__}: only the convolution onto the last variable is closed-form here")
-    if fnc.is_prior or slot == last:
+    if isinstance(fnc, TERNARY_FACTORS):
+        flag, key = L.PROPOSAL_FWD, "prop_fwd"
+    elif fnc.is_prior or slot == last:
         flag, key = L.PROPOSAL_FWD, "prop_fwd"
     elif isinstance(fnc, Pose2Point2BearingRange):
         # pose from landmark is a 1-parameter family: the reference leaves it to the optimiser's start
@@ -434,6 +443,8 @@ def initAll(fg: FactorGraph, seed=0, ctx: Context | None = None):
                     vs[0].val = approxConv(fg, f.label, vs[0].label, seed=seed + k, ctx=ctx)
                     progress, k = True, k + 1
             elif vs[0].initialized and not vs[1].initialized:
+                if len(vs) > 2 and not vs[2].initialized:
+                    continue  # a third variable (bRa / Delta) nothing has initialised yet: test/testPose3.jl:118-119
                 if FAMILY[f.fnc.family][6] == 0:
                     continue  # no closed-form root toward the last variable (ranges, bearing, partial Pose3): defer it
                 vs[1].val = approxConv(fg, f.label, vs[1].label, seed=seed + k, ctx=ctx)

@@ -69,6 +69,7 @@ def source_text():
     parts.append("\n// ===== se3_common.cuh =====\n" + se_body)
     parts.append(family_region("fam_se3.cu"))
     parts.append(family_region("fam_se3_partial.cu"))
+    parts.append(family_region("fam_se3_ternary.cu"))
     pk = _read("product_kernels.cu")
     parts.append("\n// ===== product_kernels.cu =====\n" + pk[pk.index("constexpr int kProdWarps"):pk.index("\nint launch_product")] + "\n")
     parts.append(open(os.path.join(HERE, "hk_main.inc")).read())

@@ -9,13 +9,13 @@ import numpy as np
 
 import rome_b200 as rb
 from rome_b200 import _lib as L
-from rome_b200.engine import FAMILY, VAR_DIM
+from rome_b200.engine import FAMILY, FAMILY_VT2, VAR_DIM
 
-_WRAP = {L.POSE2: 2, L.POINT2: -1, L.POSE3: -1, L.POINT3: -1}
+_WRAP = {L.POSE2: 2, L.POINT2: -1, L.POSE3: -1, L.POINT3: -1, L.ROTATION3: -2}
 _ROW = {
     "se2": np.dtype([("ip", "i4"), ("iq", "i4"), ("mu", "f8", 3), ("L", "f4", 6), ("pad", "f4", 2)]),
     "br": np.dtype([("ip", "i4"), ("iq", "i4"), ("mu_b", "f8"), ("mu_r", "f8"), ("sig_b", "f4"), ("sig_r", "f4")]),
-    "se3": np.dtype([("ip", "i4"), ("iq", "i4"), ("mu", "f8", 6), ("L", "f4", 21), ("pad", "f4", 5)]),
+    "se3": np.dtype([("ip", "i4"), ("iq", "i4"), ("mu", "f8", 6), ("L", "f4", 21), ("ir", "i4"), ("pad", "f4", 4)]),
     "pt2": np.dtype([("ip", "i4"), ("iq", "i4"), ("mu", "f8", 2), ("L", "f4", 3), ("pad", "f4", 3)]),
     "s1": np.dtype([("ip", "i4"), ("iq", "i4"), ("mu", "f8"), ("sigma", "f4"), ("pad", "f4", 3)]),
 }
@@ -44,6 +44,7 @@ class EmulatedContext:
                                      C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float),
                                      C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_uint64, C.c_uint32,
                                      C.c_int]
+        self._hk.hk_set_v2.argtypes = [C.c_void_p]
         self._hk.hk_pack.argtypes = [C.c_int] * 5 + [C.c_void_p, C.c_void_p]
         self._hk.hk_unpack.argtypes = [C.c_int] * 5 + [C.c_void_p, C.c_void_p]
         for kind, dt in _ROW.items():  # the numpy row layouts must be the C structs'
@@ -85,12 +86,14 @@ class EmulatedContext:
         return np.ascontiguousarray(self._store[vartype][:, hb:]).view(np.float32).reshape(-1, Np, d).copy()
 
     # -- factors (rows as rome_b200_api.cu builds them: Float64 Cholesky, float32 lower triangle row-major) ----------
-    def _gauss(self, family, kind, i0, i1, mu, cov):
+    def _gauss(self, family, kind, i0, i1, mu, cov, i2=None):
         mu, cov = np.asarray(mu, np.float64), np.asarray(cov, np.float64)
         nF, d = mu.shape
         rows = np.zeros(nF, _ROW[kind])
         rows["ip"] = np.asarray(i0, np.int32)
         rows["iq"] = -1 if i1 is None else np.asarray(i1, np.int32)
+        if i2 is not None:
+            rows["ir"] = np.asarray(i2, np.int32)
         rows["mu"] = mu
         Lc = np.linalg.cholesky(0.5 * (cov + np.swapaxes(cov, 1, 2))) if nF else np.zeros((0, d, d))
         rows["L"] = np.stack([Lc[:, i, j] for i in range(d) for j in range(i + 1)], 1).astype(np.float32) if nF else 0
@@ -112,8 +115,14 @@ class EmulatedContext:
         self._gauss(family, "pt2", i0, i1, mu, cov)
 
     def set_factors_gaussian(self, family, i0, i1, mu, cov):
+        if family in FAMILY_VT2:  # as rome_b200_set_factors_gaussian
+            raise rb.RomeB200Error(L.BAD_ARG, "family has a third variable: use rome_b200_set_factors_ternary")
         kind = {64: "se2", 160: "se3", 48: "pt2"}[self._hk.hk_row_bytes(family)]
         self._gauss(family, kind, i0, i1, mu, cov)
+
+    def set_factors_ternary(self, family, i0, i1, i2, mu, cov):
+        assert family in FAMILY_VT2
+        self._gauss(family, "se3", i0, i1, mu, cov, i2)
 
     def set_factors_bearingrange(self, ip, il, bearing, rng):
         bearing, rng = np.asarray(bearing, np.float64), np.asarray(rng, np.float64)
@@ -177,6 +186,10 @@ class EmulatedContext:
                         ("stats", stats), ("jac", jac)):
             assert a is None or (isinstance(a, np.ndarray) and a.dtype == np.float32 and a.flags.c_contiguous), name
         v1 = self._store[vt1] if vt1 is not None else self._store[vt0]
+        vt2 = FAMILY_VT2.get(family)
+        if vt2 is not None:
+            assert rows["ir"].max() < self._shape[vt2][0] and self._shape[vt2][1] == N
+        self._hk.hk_set_v2(C.c_void_p(self._store[vt2].ctypes.data if vt2 is not None else None))
         if self.pipeline:
             info = (C.c_int * 6)()
             peers = self._peers.get(family, [])

@@ -97,7 +97,13 @@ def test_next_families_3d(ectx, N, golden_dir):
     import test_gpu_next_families_3d as T
     T.test_point3_families(ectx, N)
     T.test_pose3_partial_families(ectx, N)
+    T.test_pose3_ternary_families(ectx, N)
     T.test_known_answers_3d(ectx, golden_dir)
+
+
+def test_ternary_families_through_the_graph_api(emulated_api):
+    import test_gpu_next_families_3d as T
+    T.test_rotoffset_known_answer_and_graph_api(emulated_api)
 
 
 def test_next_families_through_the_graph_api(emulated_api, golden_dir):
@@ -293,8 +299,9 @@ def test_pipeline_fuzz_against_direct_family_arithmetic(hk_so):
     rng = np.random.default_rng(2024)
     direct = EmulatedContext(hk_so)
     fams = [rb.POSE2POSE2, rb.PRIORPOSE2, rb.BEARINGRANGE, rb.POSE3POSE3, rb.PRIORPOSE3, rb.POINT2POINT2, rb.POSE2POINT2,
-            rb.POSE2POINT2RANGE, rb.POINT3POINT3, rb.POSE3POSE3XYYAW, rb.POSE3POSE3UNITTRANS]
-    for trial in range(264):
+            rb.POSE2POINT2RANGE, rb.POINT3POINT3, rb.POSE3POSE3XYYAW, rb.POSE3POSE3UNITTRANS, rb.POSE3POSE3ROTOFFSET,
+            rb.POSE3POSE3TRANSFORM]
+    for trial in range(286):
         fam = fams[trial % len(fams)]
         vt0, vt1, dm, dr, ns, dj, dfwd, dbwd = rb.FAMILY[fam]
         N = int(rng.choice([1, 5, 31, 32, 33, 100, 104, 200, 333, 700]))
@@ -304,9 +311,10 @@ def test_pipeline_fuzz_against_direct_family_arithmetic(hk_so):
         count = int(rng.integers(1, nF - first + 1))
         pipe = EmulatedContext(hk_so, pipeline=True, grid_cap=int(rng.integers(1, 6)))
         parts = {t: rng.normal(size=(nv, N, rb.VAR_DIM[t])) * 0.3 + rng.normal(size=(nv, 1, rb.VAR_DIM[t])) * 2
-                 for t in {vt0, vt1} - {None}}
+                 for t in {vt0, vt1, rb.FAMILY_VT2.get(fam)} - {None}}
         i0 = rng.integers(0, nv, nF).astype(np.int32)
         i1 = rng.integers(0, nv, nF).astype(np.int32)
+        i2 = rng.integers(0, nv, nF).astype(np.int32)
         for c in (direct, pipe):
             for t, p in parts.items():
                 c.set_particles(t, p)
@@ -318,7 +326,10 @@ def test_pipeline_fuzz_against_direct_family_arithmetic(hk_so):
             else:
                 A = np.random.default_rng(trial).normal(size=(nF, dm, dm)) * 0.1
                 cov = A @ np.swapaxes(A, 1, 2) + 0.01 * np.eye(dm)
-                c.set_factors_gaussian(fam, i0, None if vt1 is None else i1, np.random.default_rng(trial).normal(size=(nF, dm)), cov)
+                if fam in rb.FAMILY_VT2:
+                    c.set_factors_ternary(fam, i0, i1, i2, np.random.default_rng(trial).normal(size=(nF, dm)), cov)
+                else:
+                    c.set_factors_gaussian(fam, i0, None if vt1 is None else i1, np.random.default_rng(trial).normal(size=(nF, dm)), cov)
         flags = rb.RESIDUAL
         if rng.random() < 0.7:
             flags |= rb.STATS
@@ -475,8 +486,10 @@ def test_pipeline_with_asynchronous_copies(hk_so, max_delay):
         first = int(rng.integers(0, nF))
         count = int(rng.integers(1, nF - first + 1))
         pipe = EmulatedContext(hk_so, pipeline=True, grid_cap=int(rng.integers(1, 5)))
-        parts = {t: rng.normal(size=(nv, N, rb.VAR_DIM[t])) * 0.3 + rng.normal(size=(nv, 1, rb.VAR_DIM[t])) * 3 for t in {vt0, vt1} - {None}}
+        parts = {t: rng.normal(size=(nv, N, rb.VAR_DIM[t])) * 0.3 + rng.normal(size=(nv, 1, rb.VAR_DIM[t])) * 3
+                 for t in {vt0, vt1, rb.FAMILY_VT2.get(fam)} - {None}}
         i0, i1 = rng.integers(0, nv, nF).astype(np.int32), rng.integers(0, nv, nF).astype(np.int32)
+        i2 = rng.integers(0, nv, nF).astype(np.int32)
         for c in (direct, pipe):
             for t, p in parts.items():
                 c.set_particles(t, p)
@@ -487,8 +500,12 @@ def test_pipeline_with_asynchronous_copies(hk_so, max_delay):
                 c.set_factors_scalar(fam, i0, i1, np.column_stack([np.linspace(1, 3, nF), np.full(nF, 0.3)]))
             else:
                 A = np.random.default_rng(trial).normal(size=(nF, dm, dm)) * 0.1
-                c.set_factors_gaussian(fam, i0, None if vt1 is None else i1, np.random.default_rng(trial).normal(size=(nF, dm)),
-                                       A @ np.swapaxes(A, 1, 2) + 0.01 * np.eye(dm))
+                if fam in rb.FAMILY_VT2:
+                    c.set_factors_ternary(fam, i0, i1, i2, np.random.default_rng(trial).normal(size=(nF, dm)),
+                                          A @ np.swapaxes(A, 1, 2) + 0.01 * np.eye(dm))
+                else:
+                    c.set_factors_gaussian(fam, i0, None if vt1 is None else i1, np.random.default_rng(trial).normal(size=(nF, dm)),
+                                           A @ np.swapaxes(A, 1, 2) + 0.01 * np.eye(dm))
         flags = rb.RESIDUAL | (rb.STATS if rng.random() < 0.6 else 0) | (rb.PROPOSAL_FWD if dfwd and rng.random() < 0.7 else 0)
         sample = rng.random() < 0.5
         flags |= rb.SAMPLE if sample else 0

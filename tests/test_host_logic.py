@@ -385,7 +385,8 @@ def test_launch_plans_fit_the_sm():
     """rome_b200_plan_query (pure host arithmetic): for every family, the flag sets the API distinguishes and particle
     counts from 1 to 4000 the chosen geometry fits a B200 SM -- or the library says the N is too large"""
     smem_sm, smem_cta = 233472, 232448
-    pose3 = {rb.POSE3POSE3, rb.PRIORPOSE3, rb.POSE3POSE3XYYAW, rb.POSE3POSE3ROTATION, rb.POSE3POSE3UNITTRANS}
+    pose3 = {rb.POSE3POSE3, rb.PRIORPOSE3, rb.POSE3POSE3XYYAW, rb.POSE3POSE3ROTATION, rb.POSE3POSE3UNITTRANS,
+             rb.POSE3POSE3ROTOFFSET, rb.POSE3POSE3TRANSFORM}
     flag_sets = [rb.RESIDUAL, rb.RESIDUAL | rb.STATS, rb.RESIDUAL | rb.STATS | rb.SAMPLE,
                  rb.RESIDUAL | rb.STATS | rb.PROPOSAL_FWD, rb.RESIDUAL | rb.STATS | rb.PROPOSAL_FWD | rb.SAMPLE,
                  rb.SAMPLE | rb.PROPOSAL_FWD | rb.PROPOSAL_BWD, rb.SAMPLE | rb.DECONV]

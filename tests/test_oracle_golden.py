@@ -260,6 +260,31 @@ def test_next_row_3d_families(ka):
         assert np.allclose(d, 0, atol=1e-12)
 
 
+def test_ternary_families(ka):
+    """Pose3Pose3RotOffset / Pose3Pose3Transform (src/factors/Pose3Pose3.jl:57-95): the parametric solution asserted by
+    test/testPose3.jl:72-112 has zero residual, the C and NumPy restatements agree, and both reduce to Pose3Pose3 when the
+    third variable is the identity"""
+    for c in ka["pose3pose3rotoffset"]:
+        r = O.pose3pose3rotoffset(c["X"], c["p"], c["q"], c["w"])
+        assert np.allclose(r, c["expect"], atol=1e-12), (c["src"], r)
+        assert np.allclose(O.np_pose3pose3rotoffset(c["X"], c["p"], c["q"], c["w"]), c["expect"], atol=1e-9)
+    rng = np.random.default_rng(5)
+    for _ in range(100):
+        X = rng.normal(size=6) * [1, 1, 1, .3, .3, .3]
+        p, q = (rng.normal(size=6) * [5, 5, 5, .8, .8, .8] for _ in range(2))
+        w, D = rng.normal(size=3) * .5, rng.normal(size=6) * [1, 1, 1, .4, .4, .4]
+        for a, b in ((O.pose3pose3rotoffset(X, p, q, w), O.np_pose3pose3rotoffset(X, p, q, w)),
+                     (O.pose3pose3transform(X, p, q, D), O.np_pose3pose3transform(X, p, q, D))):
+            assert np.allclose(a[:3], b[:3], atol=1e-12) and np.allclose(O.np_so3_exp(a[3:]), O.np_so3_exp(b[3:]), atol=1e-9)
+        assert np.allclose(O.pose3pose3rotoffset(X, p, q, np.zeros(3)), O.pose3pose3(X, p, q), atol=1e-12)
+        assert np.allclose(O.pose3pose3transform(X, p, q, np.zeros(6)), O.pose3pose3(X, p, q), atol=1e-12)
+        # Transform = Pose3Pose3 evaluated with the composed measurement Delta o exp(X)
+        tD, RD = D[:3], O.np_so3_exp(D[3:])
+        Xc = np.concatenate([tD + RD @ X[:3], O.so3_log(RD @ O.np_so3_exp(X[3:]))])
+        assert np.allclose(O.np_so3_exp(O.pose3pose3transform(X, p, q, D)[3:]), O.np_so3_exp(O.pose3pose3(Xc, p, q)[3:]), atol=1e-9)
+        assert np.allclose(O.pose3pose3transform(X, p, q, D)[:3], O.pose3pose3(Xc, p, q)[:3], atol=1e-10)
+
+
 def test_product_twins_match_the_exact_mixture():
     """SURVEY 8f N2 (parity unpinned, statistical): the C and NumPy product samplers reproduce the mean and variance of the
     exact product mixture (N^2 resp. N^3 components enumerated) of two and three KDEs, and wrap headings correctly"""
