@@ -156,7 +156,7 @@ def exportG2o(fg: FactorGraph, poseRegex: str = r"x\d", ignorePriors: bool = Tru
     The estimate is the variable's PPE `suggested` for that key (`setPPE`), else the parametric solution
     ("parametric"), else the particle mean."""
     pat = re.compile(poseRegex)
-    poses = sorted((l for l in fg.variables if pat.match(l)), key=_natural_key)
+    poses = sorted((l for l in fg.variables if pat.search(l)), key=_natural_key)  # occursin, like ls(dfg, regex)
     remaining = list(fg.factors)  # insertion order, like DFG's neighbour lists
     ids, lines = {str(k): int(v) for k, v in (varIntLabel or {}).items()}, []
     vertex_labels = list(ids) if varIntLabel is not None else None
