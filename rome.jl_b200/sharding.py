@@ -102,6 +102,32 @@ def balanced_bounds(i0_lists, nvars: int, world: int):
     return b
 
 
+def cut_block_start(n_interior: int, n_cut: int, ft: int = 0, grid: int = 0) -> int:
+    """local index at which a rank's cut block starts inside its factor table: behind ~40 % of the interior factors,
+    tile aligned (24 = lcm of the 8- and 12-factor tiles).  When the launch geometry is known (`ft` factors per tile, `grid`
+    persistent CTAs) the start is moved to the nearest tile whose CTAs do NOT also take one of the grid's leftover tiles:
+    with T tiles on `grid` CTAs the first T mod grid CTAs run one tile more than the others, and a cut tile is heavier
+    than an interior one (it also writes the forward row into peer memory) -- both on one CTA set the kernel's tail.
+    ROME_B200_CUT_PLACEMENT=legacy keeps the plain 40 % rule (A/B measurements)."""
+    import os
+    base = (int(0.4 * n_interior) // 24) * 24 if n_cut else n_interior
+    if not n_cut or ft <= 0 or grid <= 0 or os.environ.get("ROME_B200_CUT_PLACEMENT") == "legacy":
+        return base
+    tiles = -(-(n_interior + n_cut) // ft)
+    tail, nc = tiles % grid, -(-n_cut // ft) + 1
+    if tiles <= grid or tail == 0 or nc > grid - tail:
+        return base
+    step = 24 // ft if 24 % ft == 0 else 24       # tile indices whose first factor is a multiple of 24
+    best = None
+    for r in range(tiles // grid + 1):
+        lo, hi = r * grid + tail, r * grid + grid - nc
+        c = min(max(base // ft, lo), hi)
+        c = -(-c // step) * step
+        if lo <= c <= hi and c * ft <= n_interior and (best is None or abs(c * ft - base) < abs(best - base)):
+            best = c * ft
+    return base if best is None else best
+
+
 class OwnerSharding:
     """Plan of an owner-sharded sweep.
 
@@ -113,9 +139,10 @@ class OwnerSharding:
 
     families: {family id: (vt0, vt1 or None, i0 array, i1 array or None)}    nvars: {vt: count}"""
 
-    def __init__(self, world: int, nvars: dict, families: dict, bounds: dict | None = None):
+    def __init__(self, world: int, nvars: dict, families: dict, bounds: dict | None = None, geometry: dict | None = None):
         import numpy as np
         self.world, self.nvars, self.families = world, dict(nvars), {}
+        self.geometry = dict(geometry or {})   # {family: (factors per tile, persistent CTAs)} of the evaluation launches
         self.bounds = {}
         for vt, n in nvars.items():
             if bounds and vt in bounds:
@@ -186,7 +213,8 @@ class OwnerSharding:
             # local table order: the cut block sits BEHIND the first ~40 % of the interior factors (tile aligned): when a
             # persistent grid reaches it, the peers' signals of the previous step have long arrived (the barrier is only
             # passed there), and the NVLink latency of its rows hides behind the interior factors that follow
-            cut_first = (int(0.4 * len(interior)) // 24) * 24 if len(cutf) else len(interior)
+            # (cut_block_start: the rule, refined by the launch geometry when it is known)
+            cut_first = cut_block_start(len(interior), len(cutf), *self.geometry.get(fam, (0, 0)))
             order = np.concatenate([interior[:cut_first], cutf, interior[cut_first:]])
             dst_rank = F["dst"][cutf]
             dst_row = np.zeros(len(cutf), dtype=np.int64)

@@ -120,7 +120,17 @@ def sharding_of(w, world, balance=True):
             firsts = [f["i0"] for fam, f in w["families"].items() if FAMILY[fam][0] == vt]
             if firsts:
                 bounds[vt] = balanced_bounds(firsts, nvars[vt], world)
-    return OwnerSharding(world, nvars, fams, bounds)
+    # launch geometry of every family's sampled RESIDUAL|STATS launch on a B200 (148 SMs): where the cut block is placed
+    from . import _lib as L
+    from .engine import plan_query
+    geometry = {}
+    for fam in fams:
+        try:
+            p = plan_query(fam, L.RESIDUAL | L.STATS | L.SAMPLE, int(w["N"]))
+            geometry[fam] = (p["warps"], 148 * p["ctas_per_sm"])
+        except Exception:
+            pass
+    return OwnerSharding(world, nvars, fams, bounds, geometry)
 
 
 def local_view(w, sh, rank, fill_halo=False):
