@@ -22,7 +22,7 @@ every rank evaluates the same number of factors), a factor lives on the owner of
 edges need crosses NVLink: the forward-proposal rows of cut factors are written by the evaluating kernel's own TMA bulk
 stores straight into a receive buffer of the target variable's owner (rome_b200_set_proposal_destinations), halo
 particle blocks are pushed once (rome_b200_push_halo; in a solve: after every belief update), and a GPU-side flag
-barrier over peer memory (rome_b200_peer_signal / _wait) closes every step.  After the timed region every rank
+barrier over peer memory closes every step (rome_b200_peer_barrier: one one-warp kernel; --barrier selects the others).  After the timed region every rank
 recomputes, from the same seeds, the rows its peers should have delivered and compares them bit for bit
 (`exchange_verified`).
 

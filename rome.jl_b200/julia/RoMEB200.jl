@@ -19,13 +19,15 @@ using RoME, DistributedFactorGraphs, IncrementalInference
 const LIB = get(ENV, "ROME_B200_LIB", joinpath(@__DIR__, "..", "librome_b200.so"))
 
 # enums of include/rome_b200.h
-const POSE2, POINT2, POSE3, POINT3 = Cint(0), Cint(1), Cint(2), Cint(3)
+const POSE2, POINT2, POSE3, POINT3, ROTATION3 = Cint(0), Cint(1), Cint(2), Cint(3), Cint(4)
 const POSE2POSE2, PRIORPOSE2, BEARINGRANGE, POSE3POSE3, PRIORPOSE3 = Cint(0), Cint(1), Cint(2), Cint(3), Cint(4)
 # next-row families (SURVEY.md 8f N1)
 const PRIORPOINT2, POINT2POINT2, POSE2POINT2, POSE2POINT2RANGE, POINT2POINT2RANGE, POSE2POINT2BEARING =
     Cint(5), Cint(6), Cint(7), Cint(8), Cint(9), Cint(10)
 const PRIORPOINT3, POINT3POINT3, POSE3POSE3XYYAW, POSE3POSE3ROTATION, POSE3POSE3UNITTRANS =
     Cint(11), Cint(12), Cint(13), Cint(14), Cint(15)
+# families with a third variable (src/factors/Pose3Pose3.jl:57-95)
+const POSE3POSE3ROTOFFSET, POSE3POSE3TRANSFORM = Cint(16), Cint(17)
 const RESIDUAL, PROPOSAL_FWD, PROPOSAL_BWD, STATS, SAMPLE, WRITE_MEAS, JACOBIAN, INDEPENDENT, DECONV, PRECISE =
     UInt32(1), UInt32(2), UInt32(4), UInt32(8), UInt32(16), UInt32(32), UInt32(64), UInt32(128), UInt32(256), UInt32(512)
 const ROUTED_ONLY, BARRIER_WAIT, BARRIER_SIGNAL = UInt32(1024), UInt32(2048), UInt32(4096)
@@ -109,6 +111,14 @@ function set_factors!(ctx::Context, family::Cint, ip::Vector{Int32}, iq::Union{N
     check(ctx, ccall((:rome_b200_set_factors_gaussian, LIB), Cint,
                      (Ptr{Cvoid}, Cint, Cint, Ptr{Int32}, Ptr{Int32}, Ptr{Cdouble}, Ptr{Cdouble}),
                      ctx.h, family, length(ip), ip, iq === nothing ? C_NULL : iq, mu, cv))
+end
+
+# families with a third variable: Pose3Pose3RotOffset (ir: Rotation3 variables), Pose3Pose3Transform (ir: Pose3 variables)
+function set_factors!(ctx::Context, family::Cint, ip::Vector{Int32}, iq::Vector{Int32}, ir::Vector{Int32}, Z::Vector{<:MvNormal})
+    mu = reduce(hcat, mean.(Z)); cv = reduce(hcat, vec.(Matrix.(cov.(Z))))
+    check(ctx, ccall((:rome_b200_set_factors_ternary, LIB), Cint,
+                     (Ptr{Cvoid}, Cint, Cint, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Cdouble}, Ptr{Cdouble}),
+                     ctx.h, family, length(ip), ip, iq, ir, mu, cv))
 end
 
 # ---- belief update on the device (SURVEY.md 8f N2): product of the proposal densities of every variable ---------
