@@ -399,6 +399,13 @@ def test_fused_sampling_matches_supplied_and_host_twin(ctx, family):
     out3 = ctx.alloc_host_outputs(fam, flags)
     ctx.eval_host(fam, flags, seed=seed, stream_id=sid + 1, **out3)
     assert not np.array_equal(out3["meas_out"], out["meas_out"])
+    # the compile-time flag variants the timed loops run (SAMPLE|RESIDUAL|STATS [|PROPOSAL_FWD]) draw the SAME samples and
+    # compute the SAME rows as the run-time-flag variant checked above: bit-identical residuals, equal statistics
+    for hot in (rb.RESIDUAL | rb.STATS | rb.SAMPLE, rb.RESIDUAL | rb.STATS | rb.PROPOSAL_FWD | rb.SAMPLE):
+        oh = ctx.alloc_host_outputs(fam, hot)
+        ctx.eval_host(fam, hot, seed=seed, stream_id=sid, **oh)
+        assert np.array_equal(oh["res"][:, :N], out["res"][:, :N]), hex(hot)
+        assert np.allclose(oh["stats"][:, :out["res"].shape[2]], rb.rows_to_particle_major(out["res"], N).sum(1), rtol=1e-3, atol=1e-3)
 
 
 def test_device_pointer_path_and_graph(ctx):
