@@ -72,8 +72,8 @@ struct FamBearingRange {
                 const float2 m2 = *reinterpret_cast<const float2*>(V.meas + 2 * n);
                 mb = m2.x; mr = m2.y;
             } else {
-                mb = row.sig_b * z[2 * k];
-                mr = row.sig_r * z[2 * k + 1];
+                mb = __fmul_rn(row.sig_b, z[2 * k]);
+                mr = __fmul_rn(row.sig_r, z[2 * k + 1]);
                 if ((flags & ROME_B200_WRITE_MEAS) && live)
                     __stcs(reinterpret_cast<float2*>(P.meas_out + fo + 2 * n), make_float2(mb, mr));
             }

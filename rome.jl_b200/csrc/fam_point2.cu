@@ -45,7 +45,7 @@ struct FamPoint2Gauss {
             if (!kSample) {
                 m2 = *reinterpret_cast<const float2*>(V.meas + 2 * n);
             } else {
-                m2.x = row.L[0] * z[2 * k];
+                m2.x = __fmul_rn(row.L[0], z[2 * k]);
                 m2.y = fmaf(row.L[2], z[2 * k + 1], row.L[1] * z[2 * k]);
                 if ((flags & ROME_B200_WRITE_MEAS) && live)
                     __stcs(reinterpret_cast<float2*>(P.meas_out + fo + 2 * n), m2);
@@ -120,7 +120,7 @@ struct FamScalar {
             if (!kSample) {
                 m1 = V.meas[n];
             } else {
-                m1 = row.sigma * z[k];
+                m1 = __fmul_rn(row.sigma, z[k]);
                 if ((flags & ROME_B200_WRITE_MEAS) && live) __stcs(P.meas_out + fo + n, m1);
             }
             const float2 l = *reinterpret_cast<const float2*>(X1 + 2 * n);

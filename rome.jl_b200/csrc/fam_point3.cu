@@ -44,7 +44,7 @@ struct FamPoint3Gauss {
             if (!kSample) {
                 m[0] = V.meas[3 * n]; m[1] = V.meas[3 * n + 1]; m[2] = V.meas[3 * n + 2];
             } else {
-                m[0] = row.L[0] * z[3 * k];
+                m[0] = __fmul_rn(row.L[0], z[3 * k]);
                 m[1] = fmaf(row.L[2], z[3 * k + 1], row.L[1] * z[3 * k]);
                 m[2] = fmaf(row.L[5], z[3 * k + 2], fmaf(row.L[4], z[3 * k + 1], row.L[3] * z[3 * k]));
                 if ((flags & ROME_B200_WRITE_MEAS) && live) {

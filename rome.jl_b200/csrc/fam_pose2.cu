@@ -62,7 +62,7 @@ struct FamPose2Pose2 {
             if (!kSample) {
                 mx = V.meas[3 * n]; my = V.meas[3 * n + 1]; mt = V.meas[3 * n + 2];
             } else {
-                mx = row.L[0] * z[3 * k];
+                mx = __fmul_rn(row.L[0], z[3 * k]);
                 my = fmaf(row.L[2], z[3 * k + 1], row.L[1] * z[3 * k]);
                 mt = fmaf(row.L[5], z[3 * k + 2], fmaf(row.L[4], z[3 * k + 1], row.L[3] * z[3 * k]));
                 if ((flags & ROME_B200_WRITE_MEAS) && live) {
@@ -200,7 +200,7 @@ struct FamPriorPose2 {
             if (!kSample) {
                 mx = V.meas[3 * n]; my = V.meas[3 * n + 1]; mt = V.meas[3 * n + 2];
             } else {
-                mx = row.L[0] * z[3 * k];
+                mx = __fmul_rn(row.L[0], z[3 * k]);
                 my = fmaf(row.L[2], z[3 * k + 1], row.L[1] * z[3 * k]);
                 mt = fmaf(row.L[5], z[3 * k + 2], fmaf(row.L[4], z[3 * k + 1], row.L[3] * z[3 * k]));
                 if ((flags & ROME_B200_WRITE_MEAS) && live) {

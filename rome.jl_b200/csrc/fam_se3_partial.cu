@@ -19,7 +19,7 @@ __device__ __forceinline__ void meas3(const RowSE2& row, const EvalParams& P, co
     } else {
         float z[4];
         normal4(P.seed_lo, P.seed_hi, P.stream_id, (uint32_t)f, (uint32_t)lane, (uint32_t)slot, z);
-        m[0] = row.L[0] * z[0];
+        m[0] = __fmul_rn(row.L[0], z[0]);
         m[1] = fmaf(row.L[2], z[1], row.L[1] * z[0]);
         m[2] = fmaf(row.L[5], z[2], fmaf(row.L[4], z[1], row.L[3] * z[0]));
     }
