@@ -46,6 +46,7 @@ static inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4
 static inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 static inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
+static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __fdividef(float a, float b) { return a / b; }
 static inline void sincospif(float x, float* s, float* c) {
     *s = (float)std::sin(3.14159265358979323846 * (double)x);
