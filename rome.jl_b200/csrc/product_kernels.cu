@@ -18,6 +18,17 @@
 //   then x ~ Normal(mu_all, var_all).  Heading dimensions (Pose2 theta) use wrapped differences.
 // Proposal rows are read through the read-only path: all lanes of a warp read the same component in the categorical
 // scan (a broadcast), the k rows of a variable (k x Npad x d floats) stay L1-resident.
+//
+// STAGED path (the usual case: the k rows of the variable fit kProdRowFloats of shared memory and no heading offset is
+// beyond 1.5 rad, so no difference needs wrapping): the rows are copied once into shared memory, coordinate-major
+// ([source][dim][Nst], padding components parked at 1e18 = weight 0), and every N-component scan reads four components
+// per 16-byte broadcast load.  Weights are evaluated in scaled coordinates, w_i = 2^-(sum_c (s_c x_ic - s_c mu_c)^2),
+// s_c = sqrt(log2(e) / 2 / (h_c^2 + var_c)): two FFMA per dimension and ONE special-function instruction per
+// component.  The categorical draw is a one-pass weighted reservoir (component i replaces the choice with probability
+// w_i / (w_1 + .. + w_i): exactly w_i / sum w overall), the pair stage sums the weights directly.  Weights are at most
+// 1, so only far-apart densities can defeat this (every weight underflows): a draw whose weight sum is below 1e-30 and a
+// pair stage whose total is below 1e-25 are redone by the log-domain code of the general path (Gumbel-max draw,
+// log-sum-exp marginals), which is also what variables that do not fit or need wrapped differences use throughout.
 #include <cuda_runtime.h>
 
 #include "../../include/rome_b200.h"
@@ -42,6 +53,11 @@ __device__ __forceinline__ float u01(uint32_t& s) {
 __device__ __forceinline__ float lg2f(float x) {
     float r;
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float ex2f(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
 __device__ __forceinline__ float warp_sum(float v) {
@@ -104,9 +120,76 @@ struct ProdOps {
         }
         return arg;
     }
+    // ---- staged path: rows in shared memory, coordinate-major: xs[(j * D + c) * Nst + i] ---------------------------
+    static __device__ __forceinline__ void fuse_s(const float* xs, int Nst, const float (*bw)[D],
+                                                  const uint16_t (*lab)[32], int upto, int skip, int lane, float (&mu)[D],
+                                                  float (&vr)[D]) {
+        float lam[D], s[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) { lam[c] = 0.f; s[c] = 0.f; }
+        for (int jj = 0; jj < upto; ++jj) {
+            if (jj == skip) continue;
+            const float* x = xs + (size_t)jj * D * Nst + lab[jj][lane];
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+                const float w = bw[jj][c];
+                lam[c] += w;
+                s[c] = fmaf(w, x[c * Nst], s[c]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < D; ++c) { vr[c] = 1.0f / lam[c]; mu[c] = s[c] * vr[c]; }
+    }
+    // sum_i w_i and a component drawn with probability w_i / sum: a one-pass weighted reservoir over BLOCKS of four
+    // components (one uniform per block: block B replaces the choice with probability W_B / (W_1 + .. + W_B)), then one
+    // component of the chosen block by its four recomputed weights.
+    // w_i = 2^-(sum_c (sc_c x_ic + nm_c)^2), nm_c = -sc_c mu_c.  xj: the source's rows, N4: N rounded up to 4
+    static __device__ __forceinline__ void weights4(const float* xj, int Nst, int i, const float (&sc)[D],
+                                                    const float (&nm)[D], float (&w)[4]) {
+        float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            const float4 x = *reinterpret_cast<const float4*>(xj + c * Nst + i);
+            const float d0 = fmaf(x.x, sc[c], nm[c]), d1 = fmaf(x.y, sc[c], nm[c]);
+            const float d2 = fmaf(x.z, sc[c], nm[c]), d3 = fmaf(x.w, sc[c], nm[c]);
+            q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1); q2 = fmaf(d2, d2, q2); q3 = fmaf(d3, d3, q3);
+        }
+        w[0] = ex2f(-q0); w[1] = ex2f(-q1); w[2] = ex2f(-q2); w[3] = ex2f(-q3);
+    }
+    static __device__ __forceinline__ int draw_s(const float* xj, int Nst, int N4, const float (&sc)[D],
+                                                 const float (&nm)[D], uint32_t& rng, float& Ssum) {
+        float S = 0.f;
+        int blk = 0;
+        for (int i = 0; i < N4; i += 4) {
+            float w[4];
+            weights4(xj, Nst, i, sc, nm, w);
+            const float W = (w[0] + w[1]) + (w[2] + w[3]);
+            S += W;
+            rng = rng * 1664525u + 1013904223u;
+            const float u = __uint_as_float(0x3f800000u | (rng >> 9));  // [1, 2)
+            if (fmaf(u, S, -S) < W) blk = i;                            // (u - 1) S < W: probability W / S
+        }
+        Ssum = S;
+        float w[4];
+        weights4(xj, Nst, blk, sc, nm, w);
+        rng = rng * 1664525u + 1013904223u;
+        const float u = __uint_as_float(0x3f800000u | (rng >> 9));
+        const float W = (w[0] + w[1]) + (w[2] + w[3]);
+        const float tgt = fmaf(u, W, -W);  // uniform in [0, W)
+        int t = 0;
+        if (tgt >= w[0]) t = 1;
+        if (tgt >= w[0] + w[1]) t = 2;
+        if (tgt >= (w[0] + w[1]) + w[2]) t = 3;
+        // a padding component (weight 0) can only be reached through rounding of the partial sums: step back to a live one
+        if (t == 3 && !(w[3] > 0.f)) t = 2;
+        if (t == 2 && !(w[2] > 0.f)) t = 1;
+        if (t == 1 && !(w[1] > 0.f)) t = 0;
+        return blk + t;
+    }
 };
 
-constexpr int kProdMaxN = 1024;  // components per proposal for which the exact pair stage is used
+constexpr int kProdMaxN = 1024;
+constexpr int kProdRowFloats = 5120;  // staged rows per variable: k * D * Nst floats (20 KB; 16 SE(2) proposals at N = 100)  // components per proposal for which the exact pair stage is used
 
 template <int D, int WRAP>
 __global__ void __launch_bounds__(kProdWarps * 32) product_kernel(const __grid_constant__ ProductParams P) {
@@ -114,10 +197,13 @@ __global__ void __launch_bounds__(kProdWarps * 32) product_kernel(const __grid_c
     __shared__ float s_bw[ROME_B200_MAX_PRODUCT_SOURCES][D];                   // 1 / h^2 per source and dimension
     __shared__ uint16_t s_lab[kProdWarps][ROME_B200_MAX_PRODUCT_SOURCES][32];  // labels of the lane's chain
     __shared__ float s_cdf[kProdMaxN];                                         // pair stage: CDF over source-0 components
+    __shared__ float s_tmax[ROME_B200_MAX_PRODUCT_SOURCES];                    // largest |heading offset| per source
+    __shared__ __align__(16) float s_rows[kProdRowFloats];                     // staged rows [source][dim][Nst]
     using Ops = ProdOps<D, WRAP>;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int blocks = (P.Npad + 31) / 32;
     const int row_floats = D * P.Npad;
+    const int N4 = (P.N + 3) & ~3, Nst = N4;
     const float kLog2e = 1.4426950408889634f;
     for (int v = blockIdx.x; v < P.nvars; v += gridDim.x) {
         const int s0 = P.var_off[v], k = P.var_off[v + 1] - s0;
@@ -132,20 +218,37 @@ __global__ void __launch_bounds__(kProdWarps * 32) product_kernel(const __grid_c
             continue;
         }
         __syncthreads();  // the previous variable's shared state is no longer read
+        // ---- staging: the k rows, coordinate-major, coalesced reads; padding components sit at 1e18 (weight 0)
+        const bool fits = P.N <= kProdMaxN && k * D * Nst <= kProdRowFloats;
+        if (fits) {
+            for (int j = 0; j < k; ++j) {
+                const float* row = P.bufs[P.src_buf[s0 + j]] + (size_t)P.src_row[s0 + j] * row_floats;
+                float* xj = s_rows + j * D * Nst;
+                for (int idx = threadIdx.x; idx < Nst * D; idx += blockDim.x) {
+                    const int i = idx / D, c = idx - i * D;
+                    xj[c * Nst + i] = i < P.N ? __ldg(row + idx) : 1e18f;
+                }
+            }
+        }
         // ---- per-source bandwidths: h = std * bw_scale (circular statistics for the heading); sources split over warps
         for (int j = warp; j < k; j += kProdWarps) {
             const float* row = P.bufs[P.src_buf[s0 + j]] + (size_t)P.src_row[s0 + j] * row_floats;
             float mean[D];
 #pragma unroll
             for (int c = 0; c < D; ++c) {
-                float a = 0.f, b = 0.f;
+                float a = 0.f, b = 0.f, tm = 0.f;
                 for (int i = lane; i < P.N; i += 32) {
                     const float x = __ldg(row + i * D + c);
-                    if (c == WRAP) { float sn, cs; __sincosf(x, &sn, &cs); a += cs; b += sn; }
+                    if (c == WRAP) { float sn, cs; __sincosf(x, &sn, &cs); a += cs; b += sn; tm = fmaxf(tm, fabsf(x)); }
                     else a += x;
                 }
                 a = warp_sum(a);
-                if (c == WRAP) { b = warp_sum(b); mean[c] = atan2f(b, a); }
+                if (c == WRAP) {
+                    b = warp_sum(b); mean[c] = atan2f(b, a);
+#pragma unroll
+                    for (int o = 16; o >= 1; o >>= 1) tm = fmaxf(tm, __shfl_xor_sync(0xffffffffu, tm, o));
+                    if (lane == 0) s_tmax[j] = tm;
+                }
                 else mean[c] = a / (float)P.N;
             }
 #pragma unroll
@@ -165,11 +268,64 @@ __global__ void __launch_bounds__(kProdWarps * 32) product_kernel(const __grid_c
             }
         }
         __syncthreads();
+        // staged path: rows fit and no difference of headings needs wrapping (CTA-uniform)
+        bool staged = fits;
+        if (WRAP >= 0 && staged) {
+            float tm = 0.f;
+            for (int j = 0; j < k; ++j) tm = fmaxf(tm, s_tmax[j]);
+            staged = tm < 1.5f;
+        }
         // ---- exact pair stage for sources 0 and 1: the product of two KDEs is a mixture of N^2 Gaussians with weights
         //      w_ab = Normal(x_0a - x_1b; 0, h_0^2 + h_1^2); marginal W_a = sum_b w_ab -> CDF over a (shared by all
-        //      chains of the variable); a chain draws a ~ W, then b | a.  log-sum-exp keeps far-apart proposals finite.
+        //      chains of the variable); a chain draws a ~ W, then b | a.
         const bool pair = P.N <= kProdMaxN;
-        if (pair) {
+        bool pair_done = false;
+        if (pair && staged) {  // weights summed directly in scaled coordinates
+            float sc[D];
+#pragma unroll
+            for (int c = 0; c < D; ++c) sc[c] = sqrtf(0.5f * kLog2e / (1.0f / s_bw[0][c] + 1.0f / s_bw[1][c]));
+            const float* x1 = s_rows + D * Nst;
+            for (int a = threadIdx.x; a < P.N; a += blockDim.x) {
+                float na[D];
+#pragma unroll
+                for (int c = 0; c < D; ++c) na[c] = -sc[c] * s_rows[c * Nst + a];
+                float W = 0.f;
+                for (int b = 0; b < N4; b += 4) {
+                    float4 x[D];
+#pragma unroll
+                    for (int c = 0; c < D; ++c) x[c] = *reinterpret_cast<const float4*>(x1 + c * Nst + b);
+                    float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+                    for (int c = 0; c < D; ++c) {
+                        const float d0 = fmaf(x[c].x, sc[c], na[c]), d1 = fmaf(x[c].y, sc[c], na[c]);
+                        const float d2 = fmaf(x[c].z, sc[c], na[c]), d3 = fmaf(x[c].w, sc[c], na[c]);
+                        q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1); q2 = fmaf(d2, d2, q2); q3 = fmaf(d3, d3, q3);
+                    }
+                    W += (ex2f(-q0) + ex2f(-q1)) + (ex2f(-q2) + ex2f(-q3));
+                }
+                s_cdf[a] = W;
+            }
+            __syncthreads();
+            if (warp == 0) {  // inclusive prefix sum over a (warp scan per chunk of 32 with a running carry)
+                float carry = 0.f;
+                for (int base = 0; base < P.N; base += 32) {
+                    const int a = base + lane;
+                    float x = a < P.N ? s_cdf[a] : 0.f;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const float y = __shfl_up_sync(0xffffffffu, x, o);
+                        if (lane >= o) x += y;
+                    }
+                    x += carry;
+                    if (a < P.N) s_cdf[a] = x;
+                    carry = __shfl_sync(0xffffffffu, x, 31);
+                }
+            }
+            __syncthreads();
+            pair_done = s_cdf[P.N - 1] >= 1e-25f;  // far-apart proposals: every weight underflowed -> log-domain code
+            __syncthreads();                       // (everyone has read the total before the general path rewrites it)
+        }
+        if (pair && !pair_done) {  // general path: log-sum-exp keeps far-apart proposals finite
             const float* r0 = P.bufs[P.src_buf[s0]] + (size_t)P.src_row[s0] * row_floats;
             const float* r1 = P.bufs[P.src_buf[s0 + 1]] + (size_t)P.src_row[s0 + 1] * row_floats;
             float c2[D];
@@ -218,6 +374,25 @@ __global__ void __launch_bounds__(kProdWarps * 32) product_kernel(const __grid_c
             }
             __syncthreads();
         }
+        // fusion of the chosen components / categorical draw of source j given the others, on the staged rows when
+        // they exist (a draw whose weights all underflowed is redone by the log-domain scan)
+        auto fuse_any = [&](int upto, int skip, float (&mu)[D], float (&vr)[D]) {
+            if (staged) Ops::fuse_s(s_rows, Nst, s_bw, s_lab[warp], upto, skip, lane, mu, vr);
+            else Ops::fuse(P, s_bw, s_lab[warp], s0, upto, skip, lane, row_floats, mu, vr);
+        };
+        auto draw_any = [&](int j, const float (&mu)[D], const float (&vr)[D], uint32_t& rng) -> int {
+            if (staged) {
+                float sc[D], nm[D], S;
+#pragma unroll
+                for (int c = 0; c < D; ++c) {
+                    sc[c] = sqrtf(0.5f * kLog2e / (1.0f / s_bw[j][c] + vr[c]));
+                    nm[c] = -sc[c] * mu[c];
+                }
+                const int arg = Ops::draw_s(s_rows + j * D * Nst, Nst, N4, sc, nm, rng, S);
+                if (S >= 1e-30f) return arg;
+            }
+            return Ops::draw(P, s_bw, s0, j, row_floats, mu, vr, rng);
+        };
         // ---- chains: lane = chain n; blocks of 32 chains are dealt to the warps round-robin -------------------------
         for (int blk = warp; blk < blocks; blk += kProdWarps) {
             const int n = blk * 32 + lane;
@@ -235,8 +410,8 @@ __global__ void __launch_bounds__(kProdWarps * 32) product_kernel(const __grid_c
                     if (s_cdf[mid] < target) lo = mid + 1; else hi = mid;
                 }
                 s_lab[warp][0][lane] = (uint16_t)lo;
-                Ops::fuse(P, s_bw, s_lab[warp], s0, 1, -1, lane, row_floats, mu, vr);
-                s_lab[warp][1][lane] = (uint16_t)Ops::draw(P, s_bw, s0, 1, row_floats, mu, vr, rng);
+                fuse_any(1, -1, mu, vr);
+                s_lab[warp][1][lane] = (uint16_t)draw_any(1, mu, vr, rng);
             } else {
                 s_lab[warp][0][lane] = (uint16_t)(xorshift32(rng) % (uint32_t)P.N);
                 s_lab[warp][1][lane] = (uint16_t)(xorshift32(rng) % (uint32_t)P.N);
@@ -244,17 +419,17 @@ __global__ void __launch_bounds__(kProdWarps * 32) product_kernel(const __grid_c
             if (k > 2 || !pair) {
                 // further sources enter one at a time conditioned on the ones already chosen, then Gibbs sweeps over all
                 for (int j = 2; j < k; ++j) {
-                    Ops::fuse(P, s_bw, s_lab[warp], s0, j, -1, lane, row_floats, mu, vr);
-                    s_lab[warp][j][lane] = (uint16_t)Ops::draw(P, s_bw, s0, j, row_floats, mu, vr, rng);
+                    fuse_any(j, -1, mu, vr);
+                    s_lab[warp][j][lane] = (uint16_t)draw_any(j, mu, vr, rng);
                 }
                 for (int t = 0; t < P.iters; ++t)
                     for (int j = 0; j < k; ++j) {
-                        Ops::fuse(P, s_bw, s_lab[warp], s0, k, j, lane, row_floats, mu, vr);
-                        s_lab[warp][j][lane] = (uint16_t)Ops::draw(P, s_bw, s0, j, row_floats, mu, vr, rng);
+                        fuse_any(k, j, mu, vr);
+                        s_lab[warp][j][lane] = (uint16_t)draw_any(j, mu, vr, rng);
                     }
             }
             // the sample: Normal(fused mean, fused variance) of the chosen components
-            Ops::fuse(P, s_bw, s_lab[warp], s0, k, -1, lane, row_floats, mu, vr);
+            fuse_any(k, -1, mu, vr);
             float z[8];
             const uint4 a = philox4x32_10(make_uint4((uint32_t)n, (uint32_t)v, P.stream_id, 0x50524f45u), P.seed_lo, P.seed_hi);
             box_muller(a.x, a.y, z[0], z[1]); box_muller(a.z, a.w, z[2], z[3]);
@@ -313,9 +488,10 @@ int launch_product(int d, int wrap_dim, const void* params, int num_sms, void* s
     const ProductParams& p = *static_cast<const ProductParams*>(params);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (p.nvars == 0) return 0;
-    int grid = p.nvars;
-    const int cap = num_sms * 16;
-    if (grid > cap) grid = cap;
+    // one CTA per variable: the cost of a variable grows with its number of proposals (one N x N scan for two, a dozen
+    // for four), so the hardware block scheduler balances the SMs better than a static grid-stride assignment would
+    const int grid = p.nvars;
+    (void)num_sms;
     if (d == 3 && wrap_dim == 2) product_kernel<3, 2><<<grid, kProdWarps * 32, 0, s>>>(p);
     else if (d == 3) product_kernel<3, -1><<<grid, kProdWarps * 32, 0, s>>>(p);
     else if (d == 2) product_kernel<2, -1><<<grid, kProdWarps * 32, 0, s>>>(p);

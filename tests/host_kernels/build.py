@@ -75,7 +75,7 @@ def source_text():
     parts.append(open(os.path.join(HERE, "hk_main.inc")).read())
     text = "".join(parts)
     # the few PTX statements of the compiled regions are MUFU approximations: substitute the exact functions
-    exact = {"rsqrt": "1.0f / std::sqrt", "lg2": "std::log2"}
+    exact = {"rsqrt": "1.0f / std::sqrt", "lg2": "std::log2", "ex2": "std::exp2"}
     text, n = re.subn(r'asm\("(\w+)\.approx\.ftz\.f32 %0, %1;"\s*:\s*"=f"\((\w+)\)\s*:\s*"f"\((.+?)\)\);',
                       lambda m: f"{m.group(2)} = {exact[m.group(1)]}({m.group(3)});", text)
     assert n >= 2 and "asm(" not in text and "asm volatile" not in text

@@ -107,6 +107,59 @@ def test_product_multimodal_matches_numpy_twin(ctx):
     assert np.allclose(g.std(0), t.std(0), rtol=0.2), (g.std(0), t.std(0))
 
 
+def _mixture_moments(rows, h):
+    """exact mean / variance per dimension of the product of k KDEs (rows[j]: [N][d] components, h[j]: [d] bandwidths):
+    a mixture over all N^k index tuples, component = precision-weighted fusion, weight = the Gaussian overlap"""
+    import itertools
+    k, (N, d) = len(rows), rows[0].shape
+    prec = np.array([1.0 / np.square(h[j].astype(np.float64)) for j in range(k)])     # [k][d]
+    lam = prec.sum(0)
+    idx = np.array(list(itertools.product(range(N), repeat=k)))                       # [N^k][k]
+    x = np.stack([rows[j][idx[:, j]] for j in range(k)], 1)                           # [N^k][k][d]
+    m = (x * prec[None]).sum(1) / lam
+    logw = (-0.5 * ((x * x * prec[None]).sum(1) - lam * m * m)).sum(1)
+    w = np.exp(logw - logw.max()); w /= w.sum()
+    mean = (w[:, None] * m).sum(0)
+    var = (w[:, None] * (1.0 / lam + m * m)).sum(0) - mean * mean
+    return mean, var
+
+
+@pytest.mark.parametrize("case", ["pair_point2_N10", "pair_pose2_N13", "triple_point2_N6", "far_apart_pose2_N10",
+                                  "wide_headings_pose2_N10"])
+def test_product_matches_exact_mixture(ctx, case):
+    """few components, many variables with the SAME proposals (every variable = fresh chains): the pooled samples have
+    the mean and variance of the exact N^k-component product mixture.  Particle counts that are not multiples of four
+    exercise the padding of the staged rows; `far_apart` (densities 60 bandwidths apart: every direct weight underflows)
+    and `wide_headings` (offsets beyond 1.5 rad) take the log-domain code of the general path."""
+    rng = np.random.default_rng(5)
+    k = 3 if case.startswith("triple") else 2
+    N = int(case.rsplit("N", 1)[1])
+    pose = "pose2" in case
+    vt, d = (rb.POSE2, 3) if pose else (rb.POINT2, 2)
+    nv = 1500
+    base = [rng.normal(size=(N, d)) * 0.5 + 0.4 * j for j in range(k)]
+    if pose:
+        for b in base:
+            b[:, 2] *= 0.3
+    if case.startswith("far_apart"):
+        base[1][:, 0] += 60.0
+    if case.startswith("wide_headings"):
+        for b in base:
+            b[:, 2] += 2.0
+    rows = np.concatenate([np.repeat(b[None], nv, 0) for b in base])       # row j * nv + v
+    off = (k * np.arange(nv + 1)).astype(np.int32)
+    sr = np.stack([j * nv + np.arange(nv) for j in range(k)], 1).reshape(-1).astype(np.int32)
+    out, h = _run_product(ctx, vt, np.zeros((nv, N, d)), rows, off, np.zeros(k * nv, np.int32), sr, iters=4)
+    assert np.isfinite(out).all()
+    mean, var = _mixture_moments(base, [h[j] for j in range(k)])
+    got = out.reshape(-1, d)
+    se = np.sqrt(var / got.shape[0])
+    # pooled samples: 5 standard errors (+ a little slack for the finite Gibbs sweeps of the triple product)
+    slack = 0.02 if k > 2 else 0.0
+    assert np.all(np.abs(got.mean(0) - mean) < 5 * se + slack * np.sqrt(var)), (got.mean(0), mean, se)
+    assert np.allclose(got.var(0), var, rtol=0.08 + 2 * slack), (got.var(0), var)
+
+
 def test_plan_errors(ctx):
     ctx.set_particles(rb.POINT2, np.zeros((2, 16, 2)))
     with pytest.raises(rb.RomeB200Error):  # more sources than ROME_B200_MAX_PRODUCT_SOURCES
