@@ -60,6 +60,11 @@ __device__ __forceinline__ float ex2f(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+__device__ __forceinline__ float rsqrt_fast(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int b = 16; b >= 1; b >>= 1) v += __shfl_xor_sync(0xffffffffu, v, b);
@@ -71,12 +76,13 @@ template <int D, int WRAP>
 struct ProdOps {
     // precision-weighted fusion of the selected components of sources [0, upto) except `skip`
     static __device__ __forceinline__ void fuse(const ProductParams& P, const float (*bw)[D], const uint16_t (*lab)[32],
-                                                int s0, int upto, int skip, int lane, int row_floats, float (&mu)[D],
-                                                float (&vr)[D]) {
+                                                int s0, int upto, int skip, int lane /* of the chain */, int row_floats,
+                                                float (&mu)[D], float (&vr)[D]) {
         float lam[D], s[D], ref = 0.f;
         bool have_ref = false;
 #pragma unroll
         for (int c = 0; c < D; ++c) { lam[c] = 0.f; s[c] = 0.f; }
+#pragma unroll 1
         for (int jj = 0; jj < upto; ++jj) {
             if (jj == skip) continue;
             const float* row = P.bufs[P.src_buf[s0 + jj]] + (size_t)P.src_row[s0 + jj] * row_floats;
@@ -107,6 +113,7 @@ struct ProdOps {
         float best = -3.0e38f;
         int arg = 0;
         const float* x = row;
+#pragma unroll 1
         for (int i = 0; i < P.N; ++i, x += D) {  // running pointer: the D loads take immediate offsets
             float q = 0.f;
 #pragma unroll
@@ -120,16 +127,44 @@ struct ProdOps {
         }
         return arg;
     }
+    // log2 of the pair-stage marginals W_a = sum_b w_ab by log-sum-exp (rows in global memory, wrapped heading differences)
+    static __device__ __forceinline__ void pair_log(const ProductParams& P, const float (*bw)[D], const float* r0,
+                                                    const float* r1, float* cdf) {
+        float c2[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) c2[c] = -0.5f * 1.4426950408889634f / (1.0f / bw[0][c] + 1.0f / bw[1][c]);
+        for (int a = threadIdx.x; a < P.N; a += blockDim.x) {
+            float xa[D];
+#pragma unroll
+            for (int c = 0; c < D; ++c) xa[c] = __ldg(r0 + a * D + c);
+            float m = -3.0e38f, sum = 0.f;
+            const float* xb = r1;
+#pragma unroll 1
+            for (int b = 0; b < P.N; ++b, xb += D) {
+                float q = 0.f;
+#pragma unroll
+                for (int c = 0; c < D; ++c) {
+                    float dlt = __ldg(xb + c) - xa[c];
+                    if (c == WRAP) dlt = wrap_pi_f(dlt);
+                    q = fmaf(c2[c] * dlt, dlt, q);
+                }
+                const float m2 = fmaxf(m, q);
+                sum = fmaf(sum, exp2f(m - m2), exp2f(q - m2));
+                m = m2;
+            }
+            cdf[a] = m + lg2f(sum);
+        }
+    }
     // ---- staged path: rows in shared memory, coordinate-major: xs[(j * D + c) * Nst + i] ---------------------------
     static __device__ __forceinline__ void fuse_s(const float* xs, int Nst, const float (*bw)[D],
-                                                  const uint16_t (*lab)[32], int upto, int skip, int lane, float (&mu)[D],
+                                                  const uint16_t (*lab)[32], int upto, int skip, int cl, float (&mu)[D],
                                                   float (&vr)[D]) {
         float lam[D], s[D];
 #pragma unroll
         for (int c = 0; c < D; ++c) { lam[c] = 0.f; s[c] = 0.f; }
         for (int jj = 0; jj < upto; ++jj) {
             if (jj == skip) continue;
-            const float* x = xs + (size_t)jj * D * Nst + lab[jj][lane];
+            const float* x = xs + (size_t)jj * D * Nst + lab[jj][cl];
 #pragma unroll
             for (int c = 0; c < D; ++c) {
                 const float w = bw[jj][c];
@@ -138,7 +173,7 @@ struct ProdOps {
             }
         }
 #pragma unroll
-        for (int c = 0; c < D; ++c) { vr[c] = 1.0f / lam[c]; mu[c] = s[c] * vr[c]; }
+        for (int c = 0; c < D; ++c) { vr[c] = __fdividef(1.0f, lam[c]); mu[c] = s[c] * vr[c]; }
     }
     // sum_i w_i and a component drawn with probability w_i / sum: a one-pass weighted reservoir over BLOCKS of four
     // components (one uniform per block: block B replaces the choice with probability W_B / (W_1 + .. + W_B)), then one
@@ -156,11 +191,15 @@ struct ProdOps {
         }
         w[0] = ex2f(-q0); w[1] = ex2f(-q1); w[2] = ex2f(-q2); w[3] = ex2f(-q3);
     }
+    // `r` lanes share a chain (r = 1, or a power of two for the trailing block of chains, warp-uniform): sub-lane `sub`
+    // scans the blocks sub, sub + r, ..., the r reservoirs are merged pairwise (the partner's choice is taken with
+    // probability S' / (S + S')) and every lane of the group returns the group's component and weight sum.
     static __device__ __forceinline__ int draw_s(const float* xj, int Nst, int N4, const float (&sc)[D],
-                                                 const float (&nm)[D], uint32_t& rng, float& Ssum) {
+                                                 const float (&nm)[D], uint32_t& rng, float& Ssum, int r, int sub,
+                                                 int lane) {
         float S = 0.f;
-        int blk = 0;
-        for (int i = 0; i < N4; i += 4) {
+        int blk = 4 * sub < N4 ? 4 * sub : 0;
+        for (int i = 4 * sub; i < N4; i += 4 * r) {
             float w[4];
             weights4(xj, Nst, i, sc, nm, w);
             const float W = (w[0] + w[1]) + (w[2] + w[3]);
@@ -169,11 +208,25 @@ struct ProdOps {
             const float u = __uint_as_float(0x3f800000u | (rng >> 9));  // [1, 2)
             if (fmaf(u, S, -S) < W) blk = i;                            // (u - 1) S < W: probability W / S
         }
+        rng = rng * 1664525u + 1013904223u;
+        float u = __uint_as_float(0x3f800000u | (rng >> 9));
+        if (r > 1) {
+            for (int o = 1; o < r; o <<= 1) {
+                const float S2 = __shfl_down_sync(0xffffffffu, S, o);
+                const int blk2 = __shfl_down_sync(0xffffffffu, blk, o);
+                rng = rng * 1664525u + 1013904223u;
+                const float um = __uint_as_float(0x3f800000u | (rng >> 9));
+                S += S2;                                   // (only the group's first lane ends with the right values)
+                if (fmaf(um, S, -S) < S2) blk = blk2;
+            }
+            const int lead = lane & ~(r - 1);
+            S = __shfl_sync(0xffffffffu, S, lead);
+            blk = __shfl_sync(0xffffffffu, blk, lead);
+            u = __shfl_sync(0xffffffffu, u, lead);
+        }
         Ssum = S;
         float w[4];
         weights4(xj, Nst, blk, sc, nm, w);
-        rng = rng * 1664525u + 1013904223u;
-        const float u = __uint_as_float(0x3f800000u | (rng >> 9));
         const float W = (w[0] + w[1]) + (w[2] + w[3]);
         const float tgt = fmaf(u, W, -W);  // uniform in [0, W)
         int t = 0;
@@ -189,16 +242,52 @@ struct ProdOps {
 };
 
 constexpr int kProdMaxN = 1024;
-constexpr int kProdRowFloats = 5120;  // staged rows per variable: k * D * Nst floats (20 KB; 16 SE(2) proposals at N = 100)  // components per proposal for which the exact pair stage is used
+constexpr int kProdRowFloats = 5120;  // shared pool per variable: k * D * Nst floats of staged rows + the labels (20 KB)  // components per proposal for which the exact pair stage is used
+
+// bandwidth of dimension c of one source (a warp's task): h = std * bw_scale, circular statistics for the heading.
+// Element (component i, dimension c) sits at base[i * si + c * sd]: (D, 1) for a row in global memory, (1, Nst) staged.
+template <int WRAP>
+__device__ __forceinline__ void bandwidth_task(const float* base, int si, int sd, int N, int c, int lane, float bw_scale,
+                                               float& h, float& tmax) {
+    const bool circ = c == WRAP;
+    const float* x0 = base + c * sd;
+    float a = 0.f, b = 0.f, tm = 0.f;
+    for (int i = lane; i < N; i += 32) {
+        const float x = x0[i * si];
+        if (circ) { float sn, cs; __sincosf(x, &sn, &cs); a += cs; b += sn; tm = fmaxf(tm, fabsf(x)); }
+        else a += x;
+    }
+    a = warp_sum(a);
+    float mean;
+    if (circ) {
+        b = warp_sum(b);
+        mean = atan2f(b, a);
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) tm = fmaxf(tm, __shfl_xor_sync(0xffffffffu, tm, o));
+    } else {
+        mean = a / (float)N;
+    }
+    float acc = 0.f;
+    for (int i = lane; i < N; i += 32) {
+        float dlt = x0[i * si] - mean;
+        if (circ) dlt = wrap_pi_f(dlt);
+        acc = fmaf(dlt, dlt, acc);
+    }
+    const float var = warp_sum(acc) / (float)max(N - 1, 1);
+    h = fmaxf(sqrtf(var) * bw_scale, 1e-6f);
+    tmax = tm;
+}
 
 template <int D, int WRAP>
-__global__ void __launch_bounds__(kProdWarps * 32) product_kernel(const __grid_constant__ ProductParams P) {
+__global__ void __launch_bounds__(kProdWarps * 32, 8) product_kernel(const __grid_constant__ ProductParams P) {
     // one CTA per variable (grid-stride); its warps share the bandwidths and the pair-stage CDF and split the chains
     __shared__ float s_bw[ROME_B200_MAX_PRODUCT_SOURCES][D];                   // 1 / h^2 per source and dimension
-    __shared__ uint16_t s_lab[kProdWarps][ROME_B200_MAX_PRODUCT_SOURCES][32];  // labels of the lane's chain
     __shared__ float s_cdf[kProdMaxN];                                         // pair stage: CDF over source-0 components
     __shared__ float s_tmax[ROME_B200_MAX_PRODUCT_SOURCES];                    // largest |heading offset| per source
-    __shared__ __align__(16) float s_rows[kProdRowFloats];                     // staged rows [source][dim][Nst]
+    __shared__ const float* s_row[ROME_B200_MAX_PRODUCT_SOURCES];              // the sources' rows in global memory
+    // one pool: the staged rows [source][dim][Nst], then the chains' labels [warp][source][32] (uint16); 20 KB keep
+    // eight CTAs resident per SM (64 registers per thread)
+    __shared__ __align__(16) float s_rows[kProdRowFloats];
     using Ops = ProdOps<D, WRAP>;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int blocks = (P.Npad + 31) / 32;
@@ -218,53 +307,72 @@ __global__ void __launch_bounds__(kProdWarps * 32) product_kernel(const __grid_c
             continue;
         }
         __syncthreads();  // the previous variable's shared state is no longer read
-        // ---- staging: the k rows, coordinate-major, coalesced reads; padding components sit at 1e18 (weight 0)
-        const bool fits = P.N <= kProdMaxN && k * D * Nst <= kProdRowFloats;
+        if (threadIdx.x < k)
+            s_row[threadIdx.x] = P.bufs[P.src_buf[s0 + threadIdx.x]] + (size_t)P.src_row[s0 + threadIdx.x] * row_floats;
+        __syncthreads();
+        bool vec = true;  // every row 16-byte aligned: staged by 16-byte loads
+        for (int j = 0; j < k; ++j) vec = vec && (reinterpret_cast<uintptr_t>(s_row[j]) & 15) == 0;
+        // ---- staging: the k rows, coordinate-major; padding components sit at 1e18 (weight 0).  Every thread issues
+        //      its (up to four) 16-byte loads before it scatters the first one, so one round trip to L2 covers a batch
+        const int lab_floats = kProdWarps * k * 16;  // 32 uint16 per (warp, source)
+        const bool fits = P.N <= kProdMaxN && k * D * Nst + lab_floats <= kProdRowFloats;
         if (fits) {
-            for (int j = 0; j < k; ++j) {
-                const float* row = P.bufs[P.src_buf[s0 + j]] + (size_t)P.src_row[s0 + j] * row_floats;
-                float* xj = s_rows + j * D * Nst;
-                for (int idx = threadIdx.x; idx < Nst * D; idx += blockDim.x) {
-                    const int i = idx / D, c = idx - i * D;
-                    xj[c * Nst + i] = i < P.N ? __ldg(row + idx) : 1e18f;
+            const int ND = P.N * D;
+            if (vec) {
+                const int R4 = (ND + 3) >> 2, total = k * R4;
+                for (int t0 = 0; t0 < total; t0 += 4 * blockDim.x) {
+                    float4 val[4];
+                    int jq[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int t = t0 + u * blockDim.x + threadIdx.x;
+                        jq[u] = -1;
+                        if (t < total) {
+                            const int j = t / R4, q = t - j * R4;
+                            jq[u] = (j << 16) | q;
+                            val[u] = __ldg(reinterpret_cast<const float4*>(s_row[j]) + q);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (jq[u] < 0) continue;
+                        const int j = jq[u] >> 16, q = jq[u] & 0xffff;
+                        float* xj = s_rows + j * D * Nst;
+                        const float e[4] = {val[u].x, val[u].y, val[u].z, val[u].w};
+#pragma unroll
+                        for (int w = 0; w < 4; ++w) {
+                            const int idx = 4 * q + w, i = idx / D, c = idx - i * D;
+                            if (idx < ND) xj[c * Nst + i] = e[w];
+                        }
+                    }
+                }
+            } else {
+                for (int j = 0; j < k; ++j) {
+                    const float* row = s_row[j];
+                    float* xj = s_rows + j * D * Nst;
+                    for (int idx = threadIdx.x; idx < ND; idx += blockDim.x) {
+                        const int i = idx / D, c = idx - i * D;
+                        xj[c * Nst + i] = __ldg(row + idx);
+                    }
                 }
             }
+            const int npadc = Nst - P.N;
+            for (int t = threadIdx.x; t < k * D * npadc; t += blockDim.x) {
+                const int jc = t / npadc, i = P.N + (t - jc * npadc);
+                s_rows[jc * Nst + i] = 1e18f;
+            }
+            __syncthreads();
         }
-        // ---- per-source bandwidths: h = std * bw_scale (circular statistics for the heading); sources split over warps
-        for (int j = warp; j < k; j += kProdWarps) {
-            const float* row = P.bufs[P.src_buf[s0 + j]] + (size_t)P.src_row[s0 + j] * row_floats;
-            float mean[D];
-#pragma unroll
-            for (int c = 0; c < D; ++c) {
-                float a = 0.f, b = 0.f, tm = 0.f;
-                for (int i = lane; i < P.N; i += 32) {
-                    const float x = __ldg(row + i * D + c);
-                    if (c == WRAP) { float sn, cs; __sincosf(x, &sn, &cs); a += cs; b += sn; tm = fmaxf(tm, fabsf(x)); }
-                    else a += x;
-                }
-                a = warp_sum(a);
-                if (c == WRAP) {
-                    b = warp_sum(b); mean[c] = atan2f(b, a);
-#pragma unroll
-                    for (int o = 16; o >= 1; o >>= 1) tm = fmaxf(tm, __shfl_xor_sync(0xffffffffu, tm, o));
-                    if (lane == 0) s_tmax[j] = tm;
-                }
-                else mean[c] = a / (float)P.N;
-            }
-#pragma unroll
-            for (int c = 0; c < D; ++c) {
-                float a = 0.f;
-                for (int i = lane; i < P.N; i += 32) {
-                    float dlt = __ldg(row + i * D + c) - mean[c];
-                    if (c == WRAP) dlt = wrap_pi_f(dlt);
-                    a = fmaf(dlt, dlt, a);
-                }
-                const float var = warp_sum(a) / (float)max(P.N - 1, 1);
-                const float h = fmaxf(sqrtf(var) * P.bw_scale, 1e-6f);
-                if (lane == 0) {
-                    s_bw[j][c] = 1.0f / (h * h);
-                    if (P.bw_out) P.bw_out[(size_t)(s0 + j) * D + c] = h;
-                }
+        // ---- per-source bandwidths; the k * D (source, dimension) tasks are dealt to the warps
+        for (int t = warp; t < k * D; t += kProdWarps) {
+            const int j = t / D, c = t - j * D;
+            float h, tm;
+            bandwidth_task<WRAP>(fits ? s_rows + j * D * Nst : s_row[j], fits ? 1 : D, fits ? Nst : 1, P.N, c, lane,
+                                 P.bw_scale, h, tm);
+            if (lane == 0) {
+                s_bw[j][c] = 1.0f / (h * h);
+                if (c == WRAP) s_tmax[j] = tm;
+                if (P.bw_out) P.bw_out[(size_t)(s0 + j) * D + c] = h;
             }
         }
         __syncthreads();
@@ -279,38 +387,42 @@ __global__ void __launch_bounds__(kProdWarps * 32) product_kernel(const __grid_c
         //      w_ab = Normal(x_0a - x_1b; 0, h_0^2 + h_1^2); marginal W_a = sum_b w_ab -> CDF over a (shared by all
         //      chains of the variable); a chain draws a ~ W, then b | a.
         const bool pair = P.N <= kProdMaxN;
-        bool pair_done = false;
-        if (pair && staged) {  // weights summed directly in scaled coordinates
-            float sc[D];
+        for (int pass = pair ? 0 : 2; pass < 2; ++pass) {
+            const bool logw = !staged || pass == 1;
+            if (!logw) {  // weights summed directly in scaled coordinates
+                float sc[D];
 #pragma unroll
-            for (int c = 0; c < D; ++c) sc[c] = sqrtf(0.5f * kLog2e / (1.0f / s_bw[0][c] + 1.0f / s_bw[1][c]));
-            const float* x1 = s_rows + D * Nst;
-            for (int a = threadIdx.x; a < P.N; a += blockDim.x) {
-                float na[D];
+                for (int c = 0; c < D; ++c) sc[c] = sqrtf(0.5f * kLog2e / (1.0f / s_bw[0][c] + 1.0f / s_bw[1][c]));
+                const float* x1 = s_rows + D * Nst;
+                for (int a = threadIdx.x; a < P.N; a += blockDim.x) {
+                    float na[D];
 #pragma unroll
-                for (int c = 0; c < D; ++c) na[c] = -sc[c] * s_rows[c * Nst + a];
-                float W = 0.f;
-                for (int b = 0; b < N4; b += 4) {
-                    float4 x[D];
-#pragma unroll
-                    for (int c = 0; c < D; ++c) x[c] = *reinterpret_cast<const float4*>(x1 + c * Nst + b);
-                    float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
-#pragma unroll
-                    for (int c = 0; c < D; ++c) {
-                        const float d0 = fmaf(x[c].x, sc[c], na[c]), d1 = fmaf(x[c].y, sc[c], na[c]);
-                        const float d2 = fmaf(x[c].z, sc[c], na[c]), d3 = fmaf(x[c].w, sc[c], na[c]);
-                        q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1); q2 = fmaf(d2, d2, q2); q3 = fmaf(d3, d3, q3);
+                    for (int c = 0; c < D; ++c) na[c] = -sc[c] * s_rows[c * Nst + a];
+                    float W = 0.f;
+                    for (int b = 0; b < N4; b += 4) {
+                        float w[4];
+                        Ops::weights4(x1, Nst, b, sc, na, w);
+                        W += (w[0] + w[1]) + (w[2] + w[3]);
                     }
-                    W += (ex2f(-q0) + ex2f(-q1)) + (ex2f(-q2) + ex2f(-q3));
+                    s_cdf[a] = W;
                 }
-                s_cdf[a] = W;
+            } else {  // general path: log-sum-exp keeps far-apart proposals finite; s_cdf[a] = log2 W_a
+                Ops::pair_log(P, s_bw, s_row[0], s_row[1], s_cdf);
             }
             __syncthreads();
             if (warp == 0) {  // inclusive prefix sum over a (warp scan per chunk of 32 with a running carry)
+                float wmax = 0.f;
+                if (logw) {
+                    wmax = -3.0e38f;
+                    for (int a = lane; a < P.N; a += 32) wmax = fmaxf(wmax, s_cdf[a]);
+#pragma unroll
+                    for (int b = 16; b >= 1; b >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, b));
+                }
                 float carry = 0.f;
+#pragma unroll 1
                 for (int base = 0; base < P.N; base += 32) {
                     const int a = base + lane;
-                    float x = a < P.N ? s_cdf[a] : 0.f;
+                    float x = a < P.N ? (logw ? exp2f(s_cdf[a] - wmax) : s_cdf[a]) : 0.f;
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) {
                         const float y = __shfl_up_sync(0xffffffffu, x, o);
@@ -322,83 +434,28 @@ __global__ void __launch_bounds__(kProdWarps * 32) product_kernel(const __grid_c
                 }
             }
             __syncthreads();
-            pair_done = s_cdf[P.N - 1] >= 1e-25f;  // far-apart proposals: every weight underflowed -> log-domain code
-            __syncthreads();                       // (everyone has read the total before the general path rewrites it)
+            // far-apart proposals: every direct weight underflowed -> the log-domain marginals in a second pass
+            if (logw || s_cdf[P.N - 1] >= 1e-25f) break;
+            __syncthreads();  // (everyone has read the total before it is rewritten)
         }
-        if (pair && !pair_done) {  // general path: log-sum-exp keeps far-apart proposals finite
-            const float* r0 = P.bufs[P.src_buf[s0]] + (size_t)P.src_row[s0] * row_floats;
-            const float* r1 = P.bufs[P.src_buf[s0 + 1]] + (size_t)P.src_row[s0 + 1] * row_floats;
-            float c2[D];
+        uint16_t (*const lab)[32] =
+            reinterpret_cast<uint16_t (*)[32]>(s_rows + (fits ? k * D * Nst : 0)) + warp * k;  // this warp's [source][32]
+        // ---- chains: one output particle each; blocks of 32 chains are dealt to the warps round-robin.  In the trailing
+        //      block (N = 100: 4 chains) r = 32 / chains lanes share a chain and split its component scans (draw_s)
+        for (int n = P.N + threadIdx.x; n < P.Npad; n += blockDim.x) {
 #pragma unroll
-            for (int c = 0; c < D; ++c) c2[c] = -0.5f * kLog2e / (1.0f / s_bw[0][c] + 1.0f / s_bw[1][c]);
-            for (int a = threadIdx.x; a < P.N; a += blockDim.x) {
-                float xa[D];
-#pragma unroll
-                for (int c = 0; c < D; ++c) xa[c] = __ldg(r0 + a * D + c);
-                float m = -3.0e38f, sum = 0.f;
-                const float* xb = r1;
-                for (int b = 0; b < P.N; ++b, xb += D) {
-                    float q = 0.f;
-#pragma unroll
-                    for (int c = 0; c < D; ++c) {
-                        float dlt = __ldg(xb + c) - xa[c];
-                        if (c == WRAP) dlt = wrap_pi_f(dlt);
-                        q = fmaf(c2[c] * dlt, dlt, q);
-                    }
-                    const float m2 = fmaxf(m, q);
-                    sum = fmaf(sum, exp2f(m - m2), exp2f(q - m2));
-                    m = m2;
-                }
-                s_cdf[a] = m + lg2f(sum);  // log2 W_a
-            }
-            __syncthreads();
-            if (warp == 0) {
-                float wmax = -3.0e38f;
-                for (int a = lane; a < P.N; a += 32) wmax = fmaxf(wmax, s_cdf[a]);
-#pragma unroll
-                for (int b = 16; b >= 1; b >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, b));
-                // inclusive prefix sum of 2^(lw - wmax) over a (warp scan per chunk of 32 with a running carry)
-                float carry = 0.f;
-                for (int base = 0; base < P.N; base += 32) {
-                    const int a = base + lane;
-                    float x = a < P.N ? exp2f(s_cdf[a] - wmax) : 0.f;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const float y = __shfl_up_sync(0xffffffffu, x, o);
-                        if (lane >= o) x += y;
-                    }
-                    x += carry;
-                    if (a < P.N) s_cdf[a] = x;
-                    carry = __shfl_sync(0xffffffffu, x, 31);
-                }
-            }
-            __syncthreads();
+            for (int c = 0; c < D; ++c) dst[n * D + c] = 0.f;
         }
-        // fusion of the chosen components / categorical draw of source j given the others, on the staged rows when
-        // they exist (a draw whose weights all underflowed is redone by the log-domain scan)
-        auto fuse_any = [&](int upto, int skip, float (&mu)[D], float (&vr)[D]) {
-            if (staged) Ops::fuse_s(s_rows, Nst, s_bw, s_lab[warp], upto, skip, lane, mu, vr);
-            else Ops::fuse(P, s_bw, s_lab[warp], s0, upto, skip, lane, row_floats, mu, vr);
-        };
-        auto draw_any = [&](int j, const float (&mu)[D], const float (&vr)[D], uint32_t& rng) -> int {
-            if (staged) {
-                float sc[D], nm[D], S;
-#pragma unroll
-                for (int c = 0; c < D; ++c) {
-                    sc[c] = sqrtf(0.5f * kLog2e / (1.0f / s_bw[j][c] + vr[c]));
-                    nm[c] = -sc[c] * mu[c];
-                }
-                const int arg = Ops::draw_s(s_rows + j * D * Nst, Nst, N4, sc, nm, rng, S);
-                if (S >= 1e-30f) return arg;
-            }
-            return Ops::draw(P, s_bw, s0, j, row_floats, mu, vr, rng);
-        };
-        // ---- chains: lane = chain n; blocks of 32 chains are dealt to the warps round-robin -------------------------
         for (int blk = warp; blk < blocks; blk += kProdWarps) {
-            const int n = blk * 32 + lane;
+            const int cnt = min(32, P.N - blk * 32);
+            if (cnt <= 0) continue;
+            int r = 1;
+            if (staged) while (2 * r * cnt <= 32) r *= 2;
+            const int sub = lane & (r - 1), lead = lane & ~(r - 1), cl = lane / r;
+            const int n = blk * 32 + cl;
             uint32_t rng;
             {
-                const uint4 x = philox4x32_10(make_uint4((uint32_t)n, (uint32_t)v, P.stream_id, 0x50524f44u), P.seed_lo, P.seed_hi);
+                const uint4 x = philox4x32_10(make_uint4((uint32_t)(blk * 32 + lane), (uint32_t)v, P.stream_id, 0x50524f44u), P.seed_lo, P.seed_hi);
                 rng = x.x | 1u;
             }
             float mu[D], vr[D];
@@ -409,27 +466,42 @@ __global__ void __launch_bounds__(kProdWarps * 32) product_kernel(const __grid_c
                     const int mid = (lo + hi) >> 1;
                     if (s_cdf[mid] < target) lo = mid + 1; else hi = mid;
                 }
-                s_lab[warp][0][lane] = (uint16_t)lo;
-                fuse_any(1, -1, mu, vr);
-                s_lab[warp][1][lane] = (uint16_t)draw_any(1, mu, vr, rng);
+                if (r > 1) lo = __shfl_sync(0xffffffffu, lo, lead);
+                lab[0][cl] = (uint16_t)lo;
             } else {
-                s_lab[warp][0][lane] = (uint16_t)(xorshift32(rng) % (uint32_t)P.N);
-                s_lab[warp][1][lane] = (uint16_t)(xorshift32(rng) % (uint32_t)P.N);
+                lab[0][lane] = (uint16_t)(xorshift32(rng) % (uint32_t)P.N);
+                lab[1][lane] = (uint16_t)(xorshift32(rng) % (uint32_t)P.N);
             }
-            if (k > 2 || !pair) {
-                // further sources enter one at a time conditioned on the ones already chosen, then Gibbs sweeps over all
-                for (int j = 2; j < k; ++j) {
-                    fuse_any(j, -1, mu, vr);
-                    s_lab[warp][j][lane] = (uint16_t)draw_any(j, mu, vr, rng);
-                }
-                for (int t = 0; t < P.iters; ++t)
-                    for (int j = 0; j < k; ++j) {
-                        fuse_any(k, j, mu, vr);
-                        s_lab[warp][j][lane] = (uint16_t)draw_any(j, mu, vr, rng);
+            // sources `first` .. k - 1 enter one at a time conditioned on the components already chosen (with the exact
+            // pair stage: b | a first), then -- unless the pair stage already sampled the whole product exactly --
+            // `iters` Gibbs sweeps over all sources.  ONE fuse / draw site serves every step (instruction-cache footprint)
+            const int first = pair ? 1 : 2, nseq = k - first;
+            const int nsteps = nseq + ((k > 2 || !pair) ? P.iters * k : 0);
+            for (int s = 0, g = 0; s < nsteps; ++s) {
+                int j, upto, skip;
+                if (s < nseq) { j = first + s; upto = j; skip = -1; }
+                else { j = g; upto = k; skip = g; g = g + 1 == k ? 0 : g + 1; }
+                int arg = -1;
+                if (staged) {
+                    Ops::fuse_s(s_rows, Nst, s_bw, lab, upto, skip, cl, mu, vr);
+                    float sc[D], nm[D], S;
+#pragma unroll
+                    for (int c = 0; c < D; ++c) {  // sqrt(log2(e) / 2 / (h_j^2 + var))
+                        sc[c] = rsqrt_fast((__fdividef(1.0f, s_bw[j][c]) + vr[c]) * (2.0f / kLog2e));
+                        nm[c] = -sc[c] * mu[c];
                     }
+                    arg = Ops::draw_s(s_rows + j * D * Nst, Nst, N4, sc, nm, rng, S, r, sub, lane);
+                    if (S < 1e-30f) arg = -1;  // every weight underflowed: the log-domain scan decides
+                } else {
+                    Ops::fuse(P, s_bw, lab, s0, upto, skip, cl, row_floats, mu, vr);
+                }
+                if (arg < 0) arg = Ops::draw(P, s_bw, s0, j, row_floats, mu, vr, rng);
+                if (r > 1) arg = __shfl_sync(0xffffffffu, arg, lead);
+                lab[j][cl] = (uint16_t)arg;
             }
             // the sample: Normal(fused mean, fused variance) of the chosen components
-            fuse_any(k, -1, mu, vr);
+            if (staged) Ops::fuse_s(s_rows, Nst, s_bw, lab, k, -1, cl, mu, vr);
+            else Ops::fuse(P, s_bw, lab, s0, k, -1, cl, row_floats, mu, vr);
             float z[8];
             const uint4 a = philox4x32_10(make_uint4((uint32_t)n, (uint32_t)v, P.stream_id, 0x50524f45u), P.seed_lo, P.seed_hi);
             box_muller(a.x, a.y, z[0], z[1]); box_muller(a.z, a.w, z[2], z[3]);
@@ -437,12 +509,12 @@ __global__ void __launch_bounds__(kProdWarps * 32) product_kernel(const __grid_c
                 const uint4 b = philox4x32_10(make_uint4((uint32_t)n, (uint32_t)v, P.stream_id, 0x50524f46u), P.seed_lo, P.seed_hi);
                 box_muller(b.x, b.y, z[4], z[5]); box_muller(b.z, b.w, z[6], z[7]);
             }
-            if (n < P.Npad) {
+            if (sub == 0 && n < P.N) {
 #pragma unroll
                 for (int c = 0; c < D; ++c) {
                     float x = fmaf(sqrtf(vr[c]), z[c], mu[c]);
                     if (c == WRAP) x = wrap_pi_f(x);
-                    dst[n * D + c] = n < P.N ? x : 0.f;
+                    dst[n * D + c] = x;
                 }
             }
             __syncwarp();

@@ -200,6 +200,12 @@ static inline float __shfl_xor_sync(unsigned, float v, int bit) { return hk_shfl
 static inline float __shfl_up_sync(unsigned, float v, int d) { return hk_shfl(v, [](int l, int a) { return l - a; }, d); }
 static inline float __shfl_sync(unsigned, float v, int src) { return hk_shfl(v, [](int, int a) { return a & 31; }, src); }
 static inline uint32_t __shfl_sync(unsigned, uint32_t v, int src) { return hk::collective(v)[src & 31]; }
+static inline int __shfl_sync(unsigned, int v, int src) { return (int)hk::collective((uint32_t)v)[src & 31]; }
+static inline float __shfl_down_sync(unsigned, float v, int d) { return hk_shfl(v, [](int l, int a) { return l + a; }, d); }
+static inline int __shfl_down_sync(unsigned, int v, int d) {
+    const int lane = hk::g_cur & 31, src = lane + d;
+    return (int)hk::collective((uint32_t)v)[src > 31 ? lane : src];
+}
 static inline void __syncwarp(unsigned = 0xffffffffu) { hk::collective(0u); }
 static inline void __syncthreads() { hk::block_barrier(); }
 template <class T> static inline T __ldg(const T* p) { return *p; }

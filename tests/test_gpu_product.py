@@ -18,14 +18,15 @@ def ctx():
     c.close()
 
 
-def _run_product(ctx, vartype, particles, rows, off, sb, sr, seed=1, iters=3, reanchor=False):
+def _run_product(ctx, vartype, particles, rows, off, sb, sr, seed=1, iters=3, reanchor=False, shift=0):
     """rows: [nrows][N][d] Float64 proposal offsets (from the target's anchor); returns new particles [nvars][N][d]"""
     nv, N, d = particles.shape
     Np = rb.npad(N)
     ctx.set_particles(vartype, particles)
     buf = np.zeros((len(rows), Np, d), np.float32)
     buf[:, :N] = rows
-    ptr = ctx.malloc_device(buf.nbytes)
+    base = ctx.malloc_device(buf.nbytes + 16)
+    ptr = base + shift  # shift = 4: rows that are not 16-byte aligned (scalar staging loads)
     ctx.memcpy_h2d(ptr, buf)
     ctx.set_product_plan(vartype, off, sb, sr)
     bw = ctx.malloc_device(max(1, len(sb)) * d * 4)
@@ -33,7 +34,7 @@ def _run_product(ctx, vartype, particles, rows, off, sb, sr, seed=1, iters=3, re
     out = ctx.get_particles(vartype)
     h = np.zeros((max(1, len(sb)), d), np.float32)
     ctx.memcpy_d2h(h, bw)
-    ctx.free_device(ptr); ctx.free_device(bw)
+    ctx.free_device(base); ctx.free_device(bw)
     return out, h
 
 
@@ -124,7 +125,7 @@ def _mixture_moments(rows, h):
     return mean, var
 
 
-@pytest.mark.parametrize("case", ["pair_point2_N10", "pair_pose2_N13", "triple_point2_N6", "far_apart_pose2_N10",
+@pytest.mark.parametrize("case", ["pair_point2_N10", "unaligned_pair_point2_N11", "pair_pose2_N13", "triple_point2_N6", "far_apart_pose2_N10",
                                   "wide_headings_pose2_N10"])
 def test_product_matches_exact_mixture(ctx, case):
     """few components, many variables with the SAME proposals (every variable = fresh chains): the pooled samples have
@@ -149,7 +150,8 @@ def test_product_matches_exact_mixture(ctx, case):
     rows = np.concatenate([np.repeat(b[None], nv, 0) for b in base])       # row j * nv + v
     off = (k * np.arange(nv + 1)).astype(np.int32)
     sr = np.stack([j * nv + np.arange(nv) for j in range(k)], 1).reshape(-1).astype(np.int32)
-    out, h = _run_product(ctx, vt, np.zeros((nv, N, d)), rows, off, np.zeros(k * nv, np.int32), sr, iters=4)
+    out, h = _run_product(ctx, vt, np.zeros((nv, N, d)), rows, off, np.zeros(k * nv, np.int32), sr, iters=4,
+                          shift=4 if case.startswith("unaligned") else 0)
     assert np.isfinite(out).all()
     mean, var = _mixture_moments(base, [h[j] for j in range(k)])
     got = out.reshape(-1, d)
