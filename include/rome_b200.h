@@ -271,6 +271,11 @@ ROME_B200_API int rome_b200_eval_host_async(rome_b200_ctx* ctx, int family, uint
 #define ROME_B200_MAX_PRODUCT_SOURCES 32 /* proposals per variable */
 #define ROME_B200_MAX_PRODUCT_BUFFERS 16 /* distinct proposal buffers per call */
 #define ROME_B200_PRODUCT_REANCHOR 1u    /* afterwards move every anchor onto the variable's new first particle */
+#define ROME_B200_PRODUCT_MANIFOLD 2u    /* Pose3: the rotation part of every proposal is taken to the tangent space at the
+                                          * variable's anchor rotation, xi = Log(R_anchor^-1 R) (the logmap-at-a-point the
+                                          * reference's manifold KDEs use, src/services/FixmeManifolds.jl:32-38), the product is
+                                          * sampled there and retracted, R_anchor Exp(xi), instead of multiplying rotation-vector
+                                          * offsets as Euclidean coordinates.  Other variable types ignore the flag. */
 ROME_B200_API int rome_b200_set_product_plan(rome_b200_ctx* ctx, int vartype, int nvars, const int32_t* var_offsets,
                                              const int32_t* src_buf, const int32_t* src_row);
 /* gibbs_iters <= 0 selects the default (2; only variables with more than two proposals iterate).  d_bw_out: optional device [nsrc][d] bandwidths (diagnostics). */
@@ -284,6 +289,10 @@ ROME_B200_API int rome_b200_reanchor(rome_b200_ctx* ctx, int vartype);
  * stores, to the identically indexed buffer of every peer (device pointers into the peers' memory, obtained with
  * rome_b200_ipc_import over NVLink).  Ranks that split the factor list therefore end the kernel holding all
  * proposals -- no separate all-gather pass; only a stream-ordered barrier between the ranks is still needed.
+ * A sweep LOOP needs TWO barriers per sweep (or receive buffers alternating with the sweep's parity): one after the
+ * evaluation (every peer's rows have landed before the belief update reads them) and one after the belief update
+ * (no peer's next evaluation may store into a buffer this rank's product is still reading) -- the order
+ * OwnerShardedSolver.sweep keeps: eval, barrier A, product + halo push, barrier B.
  * n_peers <= 7; n_peers = 0 clears. */
 ROME_B200_API int rome_b200_set_peer_proposals(rome_b200_ctx* ctx, int family, int n_peers, float* const* peer_prop_fwd);
 /* ---- multi-GPU, owner-sharded (the exchange of a sweep whose variables AND factors are partitioned) ---------------

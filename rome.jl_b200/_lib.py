@@ -20,6 +20,7 @@ DECONV = 256
 PRECISE = 512
 ROUTED_ONLY, BARRIER_WAIT, BARRIER_SIGNAL = 1024, 2048, 4096
 PRODUCT_REANCHOR, MAX_PRODUCT_SOURCES, MAX_PRODUCT_BUFFERS = 1, 32, 16
+PRODUCT_MANIFOLD = 2
 PEER_STATE_WORDS = 16
 
 # every symbol include/rome_b200.h declares (tests check the library exports each one)

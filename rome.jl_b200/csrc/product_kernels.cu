@@ -33,6 +33,7 @@
 
 #include "../../include/rome_b200.h"
 #include "device_utils.cuh"
+#include "se3_common.cuh"
 #include "tables.h"
 
 namespace rome {
@@ -363,6 +364,28 @@ __global__ void __launch_bounds__(kProdWarps * 32, 8) product_kernel(const __gri
             }
             __syncthreads();
         }
+        // ---- Pose3 on the manifold (ROME_B200_PRODUCT_MANIFOLD): the staged rotation-vector offsets become tangent
+        //      coordinates at the anchor rotation, xi = Log(R_anchor^-1 Exp(anchor_w + offset)); bandwidths, weights and
+        //      fusion below then work in that tangent space and the sample is retracted, R_anchor Exp(xi)
+        bool man = false;
+        const double* const hdr = reinterpret_cast<const double*>(P.store + (size_t)v * var_block_bytes(D, P.Npad));
+        if constexpr (D == 6) {
+            man = P.manifold && fits;
+            if (man) {
+                const double manA[3] = {hdr[3], hdr[4], hdr[5]};
+                const Quat qa = qconj(quat_exp<false>(manA[0], manA[1], manA[2]));
+                for (int t = threadIdx.x; t < k * P.N; t += blockDim.x) {
+                    const int j = t / P.N, i = t - j * P.N;
+                    float* x = s_rows + j * D * Nst + i;
+                    const Quat q = quat_exp<false>(manA[0] + (double)x[3 * Nst], manA[1] + (double)x[4 * Nst],
+                                                   manA[2] + (double)x[5 * Nst]);
+                    double ex, ey, ez;
+                    quat_log_any(qmul(qa, q), ex, ey, ez);
+                    x[3 * Nst] = (float)ex; x[4 * Nst] = (float)ey; x[5 * Nst] = (float)ez;
+                }
+                __syncthreads();
+            }
+        }
         // ---- per-source bandwidths; the k * D (source, dimension) tasks are dealt to the warps
         for (int t = warp; t < k * D; t += kProdWarps) {
             const int j = t / D, c = t - j * D;
@@ -510,12 +533,25 @@ __global__ void __launch_bounds__(kProdWarps * 32, 8) product_kernel(const __gri
                 box_muller(b.x, b.y, z[4], z[5]); box_muller(b.z, b.w, z[6], z[7]);
             }
             if (sub == 0 && n < P.N) {
+                float xo[D];
 #pragma unroll
                 for (int c = 0; c < D; ++c) {
-                    float x = fmaf(sqrtf(vr[c]), z[c], mu[c]);
-                    if (c == WRAP) x = wrap_pi_f(x);
-                    dst[n * D + c] = x;
+                    xo[c] = fmaf(sqrtf(vr[c]), z[c], mu[c]);
+                    if (c == WRAP) xo[c] = wrap_pi_f(xo[c]);
                 }
+                if constexpr (D == 6) {
+                    if (man) {  // retraction: rotation vector of R_anchor Exp(xi), the representative closest to the anchor
+                        const double manA[3] = {hdr[3], hdr[4], hdr[5]};
+                        const Quat q = qmul(quat_exp<false>(manA[0], manA[1], manA[2]),
+                                            quat_exp<false>((double)xo[3], (double)xo[4], (double)xo[5]));
+                        double wx, wy, wz;
+                        quat_log_any(q, wx, wy, wz);
+                        closest_rotvec(wx, wy, wz, manA[0], manA[1], manA[2]);
+                        xo[3] = (float)(wx - manA[0]); xo[4] = (float)(wy - manA[1]); xo[5] = (float)(wz - manA[2]);
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < D; ++c) dst[n * D + c] = xo[c];
             }
             __syncwarp();
         }

@@ -789,6 +789,7 @@ int rome_b200_product(rome_b200_ctx* ctx, int vartype, int n_bufs, const float* 
     p.iters = gibbs_iters > 0 ? gibbs_iters : 2;
     p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32); p.stream_id = stream_id;
     p.bw_scale = (float)std::pow(4.0 / ((d + 2.0) * vs.N), 1.0 / (d + 4.0));
+    p.manifold = ((flags & ROME_B200_PRODUCT_MANIFOLD) && vartype == ROME_B200_POSE3) ? 1 : 0;
     int e = launch_product(d, kWrapDim[vartype] < 0 ? -1 : kWrapDim[vartype], &p, ctx->num_sms, ctx->stream);
     if (e) return cuda_fail(ctx, (cudaError_t)e, "product kernel launch");
     if (ctx->capturing) ctx->capture_kernels++; else ctx->launches++;

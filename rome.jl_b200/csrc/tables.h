@@ -121,6 +121,7 @@ struct ProductParams {
     int nvars, N, Npad, iters;
     uint32_t seed_lo, seed_hi, stream_id;
     float bw_scale;              // rule-of-thumb factor (4 / ((d + 2) N))^(1 / (d + 4))
+    int manifold;                // Pose3: rotation part multiplied in the tangent space at the anchor rotation
 };
 
 // launch geometry chosen on the host for (family, sample, Npad)

@@ -308,11 +308,13 @@ class Context:
         self._ck(self._lib.rome_b200_set_product_plan(self._h, vartype, len(off) - 1, self._ip(off), self._ip(sb),
                                                       self._ip(sr)))
 
-    def product(self, vartype: int, bufs, *, seed=0, stream_id=0, gibbs_iters=0, reanchor=True, bw_out=None):
-        """bufs: device pointers / CUDA tensors of the proposal buffers the plan indexes; updates the particle store"""
+    def product(self, vartype: int, bufs, *, seed=0, stream_id=0, gibbs_iters=0, reanchor=True, bw_out=None, manifold=True):
+        """bufs: device pointers / CUDA tensors of the proposal buffers the plan indexes; updates the particle store.
+        manifold: Pose3 rotations are multiplied in the tangent space at the anchor rotation (ROME_B200_PRODUCT_MANIFOLD)"""
         arr = (C.c_void_p * max(1, len(bufs)))(*[_ptr(b) for b in bufs])
         self._ck(self._lib.rome_b200_product(self._h, vartype, len(bufs), arr, seed, stream_id, gibbs_iters,
-                                             L.PRODUCT_REANCHOR if reanchor else 0, _ptr(bw_out)))
+                                             (L.PRODUCT_REANCHOR if reanchor else 0) | (L.PRODUCT_MANIFOLD if manifold else 0),
+                                             _ptr(bw_out)))
 
     def reanchor(self, vartype: int):
         self._ck(self._lib.rome_b200_reanchor(self._h, vartype))

@@ -32,6 +32,7 @@ const RESIDUAL, PROPOSAL_FWD, PROPOSAL_BWD, STATS, SAMPLE, WRITE_MEAS, JACOBIAN,
     UInt32(1), UInt32(2), UInt32(4), UInt32(8), UInt32(16), UInt32(32), UInt32(64), UInt32(128), UInt32(256), UInt32(512)
 const ROUTED_ONLY, BARRIER_WAIT, BARRIER_SIGNAL = UInt32(1024), UInt32(2048), UInt32(4096)
 const PRODUCT_REANCHOR = UInt32(1)
+const PRODUCT_MANIFOLD = UInt32(2)   # Pose3: rotations multiplied in the tangent space at the anchor rotation
 
 struct Buffers            # struct rome_b200_buffers
     meas::Ptr{Cfloat}
@@ -131,7 +132,7 @@ end
 function product!(ctx::Context, vartype::Cint, bufs::Vector{Ptr{Cfloat}}; seed=UInt64(0), sweep=UInt32(0), gibbs_iters=0)
     check(ctx, ccall((:rome_b200_product, LIB), Cint,
                      (Ptr{Cvoid}, Cint, Cint, Ptr{Ptr{Cfloat}}, UInt64, UInt32, Cint, UInt32, Ptr{Cfloat}),
-                     ctx.h, vartype, length(bufs), bufs, seed, sweep, gibbs_iters, PRODUCT_REANCHOR, C_NULL))
+                     ctx.h, vartype, length(bufs), bufs, seed, sweep, gibbs_iters, PRODUCT_REANCHOR | PRODUCT_MANIFOLD, C_NULL))
 end
 function get_particles(ctx::Context, vartype::Cint, d::Int, N::Int, nvars::Int)
     out = Array{Float64,3}(undef, d, N, nvars)

@@ -258,7 +258,7 @@ class EmulatedContext:
         self._plan = getattr(self, "_plan", {})
         self._plan[vartype] = (off, sb, sr)
 
-    def product(self, vartype, bufs, *, seed=0, stream_id=0, gibbs_iters=0, reanchor=True, bw_out=None):
+    def product(self, vartype, bufs, *, seed=0, stream_id=0, gibbs_iters=0, reanchor=True, bw_out=None, manifold=True):
         off, sb, sr = self._plan[vartype]
         nvars, N, Np = self._shape[vartype]
         if len(off) - 1 != nvars:
@@ -268,11 +268,11 @@ class EmulatedContext:
         d = VAR_DIM[vartype]
         arr = (C.c_void_p * max(1, len(bufs)))(*[int(b) for b in bufs])
         self._hk.hk_product.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
-                                        C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint32, C.c_float]
+                                        C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint32, C.c_float, C.c_int]
         rc = self._hk.hk_product(d, _WRAP[vartype], self._store[vartype].ctypes.data, off.ctypes.data, sb.ctypes.data,
                                  sr.ctypes.data, len(bufs), arr, None if bw_out is None else int(bw_out), nvars, N, Np,
                                  gibbs_iters if gibbs_iters > 0 else 2, seed, stream_id,
-                                 float((4.0 / ((d + 2.0) * N)) ** (1.0 / (d + 4.0))))
+                                 float((4.0 / ((d + 2.0) * N)) ** (1.0 / (d + 4.0))), 1 if manifold else 0)
         assert rc == 0
         self.launch_count += 1
         if reanchor:

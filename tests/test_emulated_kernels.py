@@ -239,6 +239,7 @@ def test_product_kernel_and_device_resident_sweeps(emulated_api):
     T.test_product_multimodal_matches_numpy_twin(emulated_api)
     for case in ("pair_point2_N10", "unaligned_pair_point2_N11", "pair_pose2_N13", "triple_point2_N6", "far_apart_pose2_N10", "wide_headings_pose2_N10"):
         T.test_product_matches_exact_mixture(emulated_api, case)
+    T.test_product_pose3_on_manifold(emulated_api)
     T.test_plan_errors(emulated_api)
     T.test_hexagonal_solve_reference_boxes(emulated_api)
     T.test_sweeps_on_pose3_chain_and_beehive(emulated_api)

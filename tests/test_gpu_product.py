@@ -18,7 +18,7 @@ def ctx():
     c.close()
 
 
-def _run_product(ctx, vartype, particles, rows, off, sb, sr, seed=1, iters=3, reanchor=False, shift=0):
+def _run_product(ctx, vartype, particles, rows, off, sb, sr, seed=1, iters=3, reanchor=False, shift=0, manifold=True):
     """rows: [nrows][N][d] Float64 proposal offsets (from the target's anchor); returns new particles [nvars][N][d]"""
     nv, N, d = particles.shape
     Np = rb.npad(N)
@@ -30,7 +30,7 @@ def _run_product(ctx, vartype, particles, rows, off, sb, sr, seed=1, iters=3, re
     ctx.memcpy_h2d(ptr, buf)
     ctx.set_product_plan(vartype, off, sb, sr)
     bw = ctx.malloc_device(max(1, len(sb)) * d * 4)
-    ctx.product(vartype, [ptr], seed=seed, gibbs_iters=iters, reanchor=reanchor, bw_out=bw)
+    ctx.product(vartype, [ptr], seed=seed, gibbs_iters=iters, reanchor=reanchor, bw_out=bw, manifold=manifold)
     out = ctx.get_particles(vartype)
     h = np.zeros((max(1, len(sb)), d), np.float32)
     ctx.memcpy_d2h(h, bw)
@@ -160,6 +160,58 @@ def test_product_matches_exact_mixture(ctx, case):
     slack = 0.02 if k > 2 else 0.0
     assert np.all(np.abs(got.mean(0) - mean) < 5 * se + slack * np.sqrt(var)), (got.mean(0), mean, se)
     assert np.allclose(got.var(0), var, rtol=0.08 + 2 * slack), (got.var(0), var)
+
+
+def test_product_pose3_on_manifold(ctx):
+    """ROME_B200_PRODUCT_MANIFOLD: two wide rotation clouds (0.30 / 0.45 rad) around an anchor next to the |w| = pi
+    sphere, Gaussian in the tangent space at the anchor rotation.  The product sampled in that tangent space has the
+    analytic Gaussian-product moments there (bandwidths are those of the tangent coordinates); multiplying the
+    rotation-vector offsets as Euclidean coordinates (flag off) is measurably further from them."""
+    from scipy.spatial.transform import Rotation as R
+    rng = np.random.default_rng(11)
+    N, nv = 100, 60
+    w0 = np.array([2.9, 0.3, -0.2])
+    Ra = R.from_rotvec(w0)
+    m, sg = [np.array([0.25, -0.1, 0.15]), np.array([-0.15, 0.2, 0.05])], [0.30, 0.45]
+    tm, ts = [np.array([1.0, -0.5, 0.2]), np.array([0.6, 0.1, -0.3])], [0.5, 0.8]
+    parts = np.zeros((nv, N, 6))
+    parts[..., 3:] = w0                     # anchor (= first particle) at the rotation w0, translation 0
+    rows, xis = [], []
+    for j in range(2):
+        xi = m[j] + sg[j] * rng.normal(size=(nv, N, 3))
+        w = (Ra * R.from_rotvec(xi.reshape(-1, 3))).as_rotvec().reshape(nv, N, 3)
+        th = np.linalg.norm(w, axis=-1, keepdims=True)
+        alt = w * (1.0 - 2.0 * np.pi / np.maximum(th, 1e-12))   # the other representative of the same rotation
+        near = np.linalg.norm(alt - w0, axis=-1, keepdims=True) < np.linalg.norm(w - w0, axis=-1, keepdims=True)
+        w = np.where(near, alt, w)
+        rows.append(np.concatenate([tm[j] + ts[j] * rng.normal(size=(nv, N, 3)), w - w0], -1))
+        xis.append(xi)
+    rows = np.concatenate(rows)
+    off = (2 * np.arange(nv + 1)).astype(np.int32)
+    sr = np.stack([np.arange(nv), nv + np.arange(nv)], 1).reshape(-1).astype(np.int32)
+    scale = (4.0 / (8.0 * N)) ** (1.0 / 10.0)
+
+    def tangent_moments(manifold):
+        out, h = _run_product(ctx, rb.POSE3, parts.copy(), rows, off, np.zeros(2 * nv, np.int32), sr, manifold=manifold)
+        assert np.isfinite(out).all()
+        xi = (Ra.inv() * R.from_rotvec(out[..., 3:].reshape(-1, 3))).as_rotvec()
+        return out, h, xi.mean(0), xi.var(0)
+
+    out, h, mean_w, var_w = tangent_moments(True)
+    v = [np.square(s_) * (1 + scale ** 2) for s_ in sg]
+    want_mean = (m[0] / v[0] + m[1] / v[1]) / (1 / v[0] + 1 / v[1])
+    want_var = 1.0 / (1 / v[0] + 1 / v[1])
+    assert np.allclose(h[0, 3:], xis[0][0].std(0, ddof=1) * scale, rtol=5e-3), (h[0], xis[0][0].std(0, ddof=1) * scale)
+    assert np.allclose(mean_w, want_mean, atol=0.03), (mean_w, want_mean)
+    assert np.allclose(var_w, want_var, rtol=0.15), (var_w, want_var)
+    vt = [np.square(s_) * (1 + scale ** 2) for s_ in ts]
+    t = out[..., :3].reshape(-1, 3)
+    assert np.allclose(t.mean(0), (tm[0] / vt[0] + tm[1] / vt[1]) / (1 / vt[0] + 1 / vt[1]), atol=0.05)
+    assert np.allclose(t.var(0), 1.0 / (1 / vt[0] + 1 / vt[1]), rtol=0.15)
+    _, _, mean_e, var_e = tangent_moments(False)
+    err_m = np.abs(mean_w - want_mean).max() + np.abs(var_w / want_var - 1).max()
+    err_e = np.abs(mean_e - want_mean).max() + np.abs(var_e / want_var - 1).max()
+    assert err_m < err_e, (err_m, err_e)
 
 
 def test_plan_errors(ctx):
