@@ -25,4 +25,8 @@ for F in pose2pose2 bearingrange pose3pose3; do
     python tools/prof_kernel.py $F 1 > $O/${P}_ncu_$F.log 2>&1
 done
 timeout 200 python tools/bench_families.py > $O/${P}_families.jsonl 2> $O/${P}_families.err
+# device-resident sweeps (convolutions + product of proposals) and a full capture of the product kernel
+timeout 100 python tools/bench_solver.py > $O/${P}_solver.json 2> $O/${P}_solver.err
+timeout 150 ncu --set full --import-source on --clock-control none -k regex:product_kernel -c 1 --launch-skip 1 -f -o $O/${P}_product \
+  python tools/bench_solver.py > $O/${P}_ncu_product.log 2>&1
 tail -2 $O/${P}_tests.log; tail -1 $O/${P}_smoke.log; tail -3 $O/${P}_hexagonal_c.log; cut -c1-300 $O/${P}_bench_n1.json
