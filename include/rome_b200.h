@@ -272,10 +272,13 @@ ROME_B200_API int rome_b200_eval_host_async(rome_b200_ctx* ctx, int family, uint
 #define ROME_B200_MAX_PRODUCT_BUFFERS 16 /* distinct proposal buffers per call */
 #define ROME_B200_PRODUCT_REANCHOR 1u    /* afterwards move every anchor onto the variable's new first particle */
 #define ROME_B200_PRODUCT_MANIFOLD 2u    /* Pose3: the rotation part of every proposal is taken to the tangent space at the
-                                          * variable's anchor rotation, xi = Log(R_anchor^-1 R) (the logmap-at-a-point the
-                                          * reference's manifold KDEs use, src/services/FixmeManifolds.jl:32-38), the product is
+                                          * variable's anchor rotation, xi = Log(R_anchor^-1 R) (how ApproxManifoldProducts -- absent
+                                          * third-party package -- treats group-valued KDE points; the reference's own manifold
+                                          * glue for it: src/services/FixmeManifolds.jl:22-38), the product is
                                           * sampled there and retracted, R_anchor Exp(xi), instead of multiplying rotation-vector
-                                          * offsets as Euclidean coordinates.  Other variable types ignore the flag. */
+                                          * offsets as Euclidean coordinates.  Other variable types ignore the flag; a variable whose proposal rows
+                                          * do not fit the kernel's 20 KB shared-memory pool (more than 7 proposals at N = 100) is
+                                          * multiplied in chart coordinates as without the flag. */
 ROME_B200_API int rome_b200_set_product_plan(rome_b200_ctx* ctx, int vartype, int nvars, const int32_t* var_offsets,
                                              const int32_t* src_buf, const int32_t* src_row);
 /* gibbs_iters <= 0 selects the default (2; only variables with more than two proposals iterate).  d_bw_out: optional device [nsrc][d] bandwidths (diagnostics). */
