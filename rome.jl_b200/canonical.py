@@ -11,6 +11,7 @@ Each variable also receives a `simulated` ground-truth coordinate vector (the re
 from __future__ import annotations
 
 import math
+import re
 
 import numpy as np
 
@@ -71,17 +72,23 @@ def generateGraph_ZeroPose(fg: FactorGraph | None = None, varType=Pose2, mu0=Non
 
 
 def generateGraph_Circle(poses=6, fg: FactorGraph | None = None, graphinit=True, landmark=True, loopClosure=True,
-                         biasTurn=0.0, kappaOdo=1.0, cyclePoses=None):
+                         biasTurn=0.0, kappaOdo=1.0, cyclePoses=None, offsetPoses=None, stopEarly=9999999):
     """GenerateCircular.jl:31-94 with the same parameters: prior 0.01*I on :x0, `poses` odometry legs
     [10, 0, 2pi/cyclePoses + biasTurn] with sigma kappaOdo*0.1, landmark :l1 sighted (0, 20) from :x0 and :x<poses>."""
     fg = fg or initfg()
     cyclePoses = cyclePoses or poses
+    if offsetPoses is None:  # continue an existing graph behind its last pose (GenerateCircular.jl:33)
+        offsetPoses = max(sum(1 for l in fg.variables if re.search(r"x\d", l)) - 1, 0)
+    if not offsetPoses < poses:
+        raise ValueError("`offsetPoses` must be smaller than total number of `poses`")
     if "x0" not in fg.variables:
         v = addVariable(fg, "x0", Pose2)
         v.simulated = np.zeros(3)
         addFactor(fg, ["x0"], PriorPose2(MvNormal(np.zeros(3), 0.01 * np.eye(3))), graphinit=graphinit)
     X = np.array([10.0, 0.0, 2 * math.pi / cyclePoses + biasTurn])
-    for i in range(poses):
+    for i in range(offsetPoses, poses):
+        if stopEarly <= i:
+            break
         p, n = f"x{i}", f"x{i + 1}"
         v = addVariable(fg, n, Pose2)
         v.simulated = _se2_compose(_truth(fg, p), X)

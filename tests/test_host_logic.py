@@ -211,6 +211,27 @@ def test_generators_shapes():
     assert rb.getVal(p3, "x5").shape == (16, 6)
 
 
+def test_circle_generator_continues_an_existing_graph():
+    """generateGraph_Circle(fg=..., offsetPoses=...) (GenerateCircular.jl:31-94): by default the drive continues behind
+    the last pose of the graph it is handed; :x0's prior and the first sighting of :l1 are not repeated, the loop closure
+    is added once :x<poses> exists; offsetPoses >= poses is the reference's assertion; stopEarly ends the drive."""
+    fg = rb.generateGraph_Circle(6, graphinit=False)
+    assert (len(fg.variables), len(fg.factors)) == (8, 9)            # x0..x6 + l1; prior + 6 odometry + 2 sightings
+    fg = rb.generateGraph_Circle(10, fg=fg, graphinit=False)
+    assert (len(fg.variables), len(fg.factors)) == (12, 14)          # + x7..x10, 4 odometry legs, sighting from x10
+    assert sum(1 for f in fg.factors.values() if f.fnc.is_prior) == 1
+    assert sum(1 for f in fg.factors.values() if "l1" in f.variableOrderSymbols) == 3
+    with pytest.raises(ValueError):
+        rb.generateGraph_Circle(4, fg=fg, graphinit=False)
+    short = rb.generateGraph_Circle(6, graphinit=False, stopEarly=3)
+    assert sorted(l for l in short.variables if l.startswith("x")) == ["x0", "x1", "x2", "x3"]
+    assert not any("x6" in f.variableOrderSymbols for f in short.factors.values())  # no loop closure without :x6
+    # with the same turn per leg the continued drive is the same circle
+    part = rb.generateGraph_Circle(10, fg=rb.generateGraph_Circle(6, graphinit=False, cyclePoses=10), graphinit=False)
+    full = rb.generateGraph_Circle(10, graphinit=False)
+    assert np.allclose(part.variables["x10"].simulated, full.variables["x10"].simulated, atol=1e-9)
+
+
 def test_honeycomb_matches_reference_recipe():
     """generateGraph_Honeycomb! (GenerateHoneycomb.jl:179-231).  With the reference's forced association table the graph
     is the reference's label for label; the geometric association (default) agrees with the table on every entry except
