@@ -129,6 +129,12 @@ class GibbsSolver:
     def sweep(self, seed: int = 0):
         """one synchronous sweep: every factor convolves (fused getSample + closed-form roots), then every variable
         takes the product of its proposals; 1 launch per family + 1-2 per variable type, nothing leaves the device"""
+        self.convolve(seed)
+        self.update(seed)
+        self.sweeps_done += 1
+
+    def convolve(self, seed: int = 0):
+        """first half of a sweep: one launch per family writes every factor's proposal rows (+ the exchange when distributed)"""
         c = self.ctx
         index = {b: i for i, b in enumerate(self.buffers)}
         launched = False  # has a kernel of THIS sweep been launched yet?
@@ -155,10 +161,12 @@ class GibbsSolver:
             with torch.cuda.stream(self._tstream):
                 for _, t, nF in self._tensors:  # the one exchange of the path: every rank ends up with all proposal rows
                     allgather_rows(t, nF, self.group)
+
+    def update(self, seed: int = 0):
+        """second half of a sweep: every variable takes the product of its proposal densities (+ re-anchoring)"""
         ptrs = list(self._dev)
         for t in self.plans:
-            c.product(t, ptrs, seed=seed, stream_id=self.sweeps_done, gibbs_iters=self.gibbs_inner, reanchor=True)
-        self.sweeps_done += 1
+            self.ctx.product(t, ptrs, seed=seed, stream_id=self.sweeps_done, gibbs_iters=self.gibbs_inner, reanchor=True)
 
     def solve(self, sweeps: int | None = None, seed: int = 0):
         for s in range(sweeps if sweeps is not None else self.dg.fg.solverParams.gibbsIters):

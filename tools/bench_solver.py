@@ -28,25 +28,31 @@ def main(poses=10000, N=100, sweeps=3):
         gs.sweep(1 + s)
     c.synchronize()
     dt = time.perf_counter() - t0
-    # split: convolutions only / products only (same launches, timed apart)
-    ptrs = [p or next(q for q in gs._dev if q) for p in gs._dev]
-    t1 = time.perf_counter()
-    for s in range(sweeps):
-        for t in gs.plans:
-            c.product(t, ptrs, seed=s, stream_id=s, gibbs_iters=gs.gibbs_inner, reanchor=True)
+    dg.download_particles()  # the state after the sweeps (the timing loops below go on changing it)
+    truth = np.stack([v.simulated for v in fg.variables.values()])
+    est = np.stack([v.val.mean(0) for v in fg.variables.values()])
+    # the two halves of a sweep, each timed in its OWN loop between synchronisations (no subtraction of wall clocks):
+    # the convolution launches are ~40 us per sweep, so that loop repeats them often enough to last milliseconds
+    reps = 50
     c.synchronize()
-    dprod = time.perf_counter() - t1
+    t1 = time.perf_counter()
+    for s in range(reps):
+        gs.convolve(100 + s)
+    c.synchronize()
+    dconv = (time.perf_counter() - t1) / reps
+    t2 = time.perf_counter()
+    for s in range(sweeps):
+        gs.update(200 + s)
+    c.synchronize()
+    dprod = (time.perf_counter() - t2) / sweeps
     k = np.diff(gs.plans[rb.POSE2][0])
     nfac = sum(c.num_factors(f) for f in gs.families)
     out = dict(workload=f"manhattan_shaped_{poses}_se2_N{N}", sweeps=sweeps, ms_per_sweep=1e3 * dt / sweeps,
-               ms_product_per_sweep=1e3 * dprod / sweeps, ms_convolution_per_sweep=1e3 * (dt - dprod) / sweeps,
+               ms_product_per_sweep=1e3 * dprod, ms_convolution_per_sweep=1e3 * dconv,
                variables=int(len(k)), factors=int(nfac), proposals_per_variable_mean=float(k.mean()),
                proposals_per_variable_max=int(k.max()),
                convolved_particles_per_sweep=int(k.sum()) * N,
                convolved_particles_per_s=float(k.sum()) * N / (dt / sweeps))
-    dg.download_particles()
-    truth = np.stack([v.simulated for v in fg.variables.values()])
-    est = np.stack([v.val.mean(0) for v in fg.variables.values()])
     out["mean_abs_translation_error_m"] = float(np.abs(est[:, :2] - truth[:, :2]).mean())
     out["mean_abs_translation_error_before_m"] = err_before  # the seeded particles the sweeps start from: simulated truth + 0.1 m spread, i.e. BETTER than the noisy measurements support -- the sweeps move the beliefs to what the measurements say
     print(json.dumps(out))
