@@ -270,7 +270,9 @@ ROME_B200_API int rome_b200_eval_host_async(rome_b200_ctx* ctx, int family, uint
  * library does not know the buffers' sizes).  Variables without sources keep their particles; one source is adopted as is. */
 #define ROME_B200_MAX_PRODUCT_SOURCES 32 /* proposals per variable */
 #define ROME_B200_MAX_PRODUCT_BUFFERS 16 /* distinct proposal buffers per call */
-#define ROME_B200_PRODUCT_REANCHOR 1u    /* afterwards move every anchor onto the variable's new first particle */
+#define ROME_B200_PRODUCT_REANCHOR 1u    /* afterwards move every anchor onto the variable's new first particle.  Proposal rows are
+                                          * offsets from the anchor their evaluation saw: rows written BEFORE a re-anchoring must not
+                                          * be multiplied again afterwards (evaluate again first) */
 #define ROME_B200_PRODUCT_MANIFOLD 2u    /* Pose3: the rotation part of every proposal is taken to the tangent space at the
                                           * variable's anchor rotation, xi = Log(R_anchor^-1 R) (how ApproxManifoldProducts -- absent
                                           * third-party package -- treats group-valued KDE points; the reference's own manifold
